@@ -1,0 +1,127 @@
+/* snag_b200 — C ABI of the B200-native SNAG_MMEA hot path (libsnag_b200.so).
+ *
+ * Drop-in boundary for three parts of zjukg/SNAG's SNAG_MMEA trainer (citations relative to the
+ * reference checkout, SNAG_MMEA/...):
+ *   - Gauss modality noise masking        model/SNAG.py:66-98, model/SNAG_tools.py:127-128
+ *   - ICL / IAL in-batch contrastive loss model/SNAG_loss.py:58-128, :148-202
+ *   - alignment evaluation                src/utils.py:202-218 (pairwise_distances), :417-435 (csls_sim),
+ *                                         main.py:359-455 (Runner._test ranking -> Hits@k / MR / MRR)
+ *
+ * Conventions
+ *   - every function returns int: 0 = ok, < 0 = SNAG_ERR_* (bad argument / shape / alignment / driver /
+ *     device), > 0 = a cudaError_t raised by the launch. Nothing is written on a negative return.
+ *   - all pointers are DEVICE pointers owned by the caller; the library never allocates, frees or
+ *     retains device memory, never synchronises, and enqueues on the cudaStream_t passed as `stream`
+ *     (void* here so the header stays plain C).
+ *   - bf16 operands are row-major [n, Dpad] with Dpad a multiple of 64, zero padded, 128-byte aligned
+ *     (what snag_prep_bf16 writes). They feed TMA (128-byte swizzle) -> tcgen05.mma directly.
+ *   - kernels are compiled for sm_100a only; on any other device the tcgen05 entry points return
+ *     SNAG_ERR_DEVICE. There is no CPU or library fallback.
+ */
+#ifndef SNAG_B200_H
+#define SNAG_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SNAG_OK 0
+#define SNAG_ERR_ARG (-1)
+#define SNAG_ERR_SHAPE (-2)
+#define SNAG_ERR_ALIGN (-3)
+#define SNAG_ERR_DRIVER (-4)
+#define SNAG_ERR_DEVICE (-5)
+
+#define SNAG_KT 16 /* candidate-list length of the CSLS top-k path; csls_k must be <= SNAG_KT */
+
+/* ---- library ------------------------------------------------------------------------------ */
+int snag_version(void);                      /* ABI version, currently 1 */
+const char* snag_error_string(int code);     /* static string for SNAG_ERR_* codes; "cuda error" for > 0 */
+int snag_device_check(void);                 /* 0 if the current device is sm_100, SNAG_ERR_DEVICE otherwise */
+int snag_num_sms(void);
+
+/* Work decomposition of an [n_rows x n_cols] similarity sweep (needed to size the `part` workspaces). */
+int snag_sim_plan(int n_rows, int n_cols, int Dpad, int* tiles_per_chunk, int* n_chunks);
+
+/* ---- noise masking ------------------------------------------------------------------------ */
+/* SNAG.add_noise_to_embeddings (model/SNAG.py:66-75):
+ *   rows with mask: out = (1-rho)*x + rho*(mean + std*z), other rows: out = x   (out may alias x)
+ * keep = (float)(1.0 - rho), rho = (float)mask_ratio are passed separately because the reference
+ * computes 1.0 - mask_ratio in double before the fp32 multiply.
+ * mask (uint8 [N]) / zsel (fp32 [n_sel, F], rows in selection order) / selpos (int32 [N]) inject the
+ * reference's own draws for bit parity; pass all three NULL to draw in-kernel with Philox4x32-10:
+ * row i selected iff u(seed, row0+i) < ratio; z is a function of (seed, (row0+i)*F + col) only. */
+int snag_noise_mask(const float* x, float* out, const float* mean, const float* std_, const uint8_t* mask,
+                    const float* zsel, const int32_t* selpos, int64_t N, int32_t F, int64_t ld_in, int64_t ld_out,
+                    float ratio, float keep, float rho, uint64_t seed, int64_t row0, void* stream);
+/* the Philox row selection itself (entity_noise_mask, model/SNAG.py:98) */
+int snag_philox_rowmask(uint8_t* mask, int64_t N, float ratio, uint64_t seed, int64_t row0, void* stream);
+/* out = mean + std * N(0,1) (entity_noise, model/SNAG.py:96) */
+int snag_gauss_fill(float* out, const float* mean, const float* std_, int64_t N, int32_t F, int64_t ld, uint64_t seed,
+                    int64_t row0, void* stream);
+/* column mean / unbiased std over rows with valid[i] != 0 (valid may be NULL = all rows)
+ * (SNAG.get_mean_std, model/SNAG.py:77-84; update_noise :94-95). workspace: (2*F+1)*8 bytes. */
+int snag_col_mean_std(const float* x, const uint8_t* valid, int64_t N, int32_t F, int64_t ld, float* mean, float* std_,
+                      void* workspace, void* stream);
+/* entity-embedding blend of MultiModalEncoder.forward (model/SNAG_tools.py:127-128) and its gradient:
+ *   fwd: out = mask ? a*e + c*noise : e      bwd: g_in = mask ? a*g_out : g_out
+ * a = (float)(1.0 - mask_ratio*0.5), c = (float)(mask_ratio*0.5). */
+int snag_rowblend_fwd(const float* e, const float* noise, const uint8_t* mask, float* out, int64_t N, int32_t D, float a,
+                      float c, void* stream);
+int snag_rowblend_bwd(const float* g_out, const uint8_t* mask, float* g_in, int64_t N, int32_t D, float a, void* stream);
+
+/* ---- operand prologue ----------------------------------------------------------------------- */
+/* out[r, :] = bf16( normalize ? emb[idx[r]] / max(||emb[idx[r]]||, 1e-12) : emb[idx[r]] ), zero padded
+ * to Dpad; norm2[r] = ||out[r]||^2 (fp64 accumulate, one rounding). idx may be NULL (identity).
+ * Replaces F.normalize + gather (main.py:379,386; model/SNAG_loss.py:60-64) + (x**2).sum(1)
+ * (src/utils.py:210-212). out is uint16_t* = raw bf16. */
+int snag_prep_bf16(const float* emb, int64_t ld, const int64_t* idx, int32_t n, int32_t D, int32_t normalize,
+                   uint16_t* out, int32_t Dpad, float* norm2, void* stream);
+
+/* ---- alignment evaluation ------------------------------------------------------------------- */
+/* pairwise_distances (src/utils.py:202-218), materialising: mode 1: out[i,j] = clamp(xn_i + yn_j - 2 x_i.y_j, 0);
+ * mode 0: out[i,j] = x_i.y_j. out is fp32 [n1, ld]. */
+int snag_sim_write(const uint16_t* X, const uint16_t* Y, const float* xn, const float* yn, int32_t n1, int32_t n2,
+                   int32_t Dpad, int32_t mode, float* out, int64_t ld, void* stream);
+/* CSLS sweep 1 (src/utils.py:431-432 without the matrix): for every row of X the SNAG_KT largest
+ * c_ij = 1 - d_ij over the columns of each chunk. part: fp32 [n_chunks][n1][SNAG_KT] (n_chunks from
+ * snag_sim_plan(n1, n2, Dpad)). Call with X and Y swapped for the column neighbourhoods. */
+int snag_eval_rowtopk(const uint16_t* X, const uint16_t* Y, const float* xn, const float* yn, int32_t n1, int32_t n2,
+                      int32_t Dpad, float* part, void* stream);
+/* merge n_lists candidate lists per row ([n_lists][n_rows][SNAG_KT]); nv[row] = mean of the k largest
+ * (may be NULL); cand_out [n_rows][SNAG_KT] = merged list (may be NULL) for the cross-GPU exchange. */
+int snag_topk_merge_mean(const float* part, int32_t n_lists, int64_t n_rows, int32_t k, float* nv, float* cand_out,
+                         void* stream);
+/* ground-truth scores g[p] = distance of pair (x_p, y_p): CSLS distance 1 - ((2(1-d) - nv1_p) - nv2_p) if
+ * use_csls else d; dot product accumulated in fp64 in index order. s_out (may be NULL) gets x_p.y_p. */
+int snag_pair_score(const uint16_t* X, const uint16_t* Y, int32_t Dpad, int64_t n, const float* xn, const float* yn,
+                    const float* nv1, const float* nv2, int32_t use_csls, float* g, float* s_out, void* stream);
+/* CSLS sweep 2 = the two ranking loops of Runner._test (main.py:400-411, 422-429) without the matrix:
+ *   cnt_row[i] += #{j != i : dist_ij < g_row[i] or (== and gid(j) < gid(i))}     l2r rank of pair gid(i)
+ *   cnt_col[j] += #{i != j : dist_ij < g_col[j] or (== and gid(i) < gid(j))}     r2l rank of pair gid(j)
+ * gid(i) = row_gid0 + i, gid(j) = col_gid0 + j (column shards of a multi-GPU evaluation pass their offset).
+ * Counters are accumulated atomically: zero them first. top3_val/top3_idx (both NULL or both fp32/int32
+ * [n_chunks][n1][4]) receive each row's 3 nearest columns per chunk (merge with snag_top3_merge). */
+int snag_eval_rank(const uint16_t* X, const uint16_t* Y, const float* xn, const float* yn, const float* nv1,
+                   const float* nv2, const float* g_row, const float* g_col, int32_t row_gid0, int32_t col_gid0,
+                   int32_t n1, int32_t n2, int32_t Dpad, int32_t use_csls, int32_t* cnt_row, int32_t* cnt_col,
+                   float* top3_val, int32_t* top3_idx, void* stream);
+int snag_top3_merge(const float* val, const int32_t* idx, int32_t n_lists, int64_t n_rows, float* oval, int32_t* oidx,
+                    void* stream);
+
+/* ---- ICL loss --------------------------------------------------------------------------------- */
+/* One side of icl_loss.forward (model/SNAG_loss.py:98-126). X = this side [Bp, Dpad], Y = [other side ; this
+ * side] [2*Bp, Dpad], each part zero padded from B to Bp rows (Bp multiple of 256).
+ *   rowsum_part[c][i] = sum over chunk c of exp(logit_ij - 1/tau), self-similarity excluded
+ *   pos[i] = x_i . other_i                       then snag_icl_finalize: lse, nll = lse - pos/tau */
+int snag_icl_rowsum(const uint16_t* X, const uint16_t* Y, int32_t B, int32_t Bp, int32_t Dpad, float inv_tau,
+                    float* rowsum_part, float* pos, void* stream);
+int snag_icl_finalize(const float* rowsum_part, int32_t n_chunks, int32_t B, int32_t Bp, const float* pos,
+                      float inv_tau, float* lse, float* nll, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SNAG_B200_H */

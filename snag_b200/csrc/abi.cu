@@ -1,0 +1,107 @@
+// extern "C" surface of libsnag_b200.so — see include/snag_b200.h for the contract.
+#include "../../include/snag_b200.h"
+#include "snag_internal.h"
+
+using namespace snag;
+
+static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline const __nv_bfloat16* BF(const uint16_t* p) { return reinterpret_cast<const __nv_bfloat16*>(p); }
+
+extern "C" {
+
+int snag_version(void) { return 1; }
+
+const char* snag_error_string(int code) {
+  switch (code) {
+    case SNAG_OK: return "ok";
+    case SNAG_ERR_ARG: return "bad argument (null pointer or non-positive size)";
+    case SNAG_ERR_SHAPE: return "unsupported shape (Dpad not a multiple of 64, k > 16, ...)";
+    case SNAG_ERR_ALIGN: return "pointer or leading dimension not aligned as required";
+    case SNAG_ERR_DRIVER: return "cuTensorMapEncodeTiled unavailable or failed";
+    case SNAG_ERR_DEVICE: return "current device is not sm_100 (B200); no fallback path exists";
+    default: return code > 0 ? cudaGetErrorString(static_cast<cudaError_t>(code)) : "unknown error";
+  }
+}
+
+int snag_device_check(void) { return device_is_sm100() ? SNAG_OK : SNAG_ERR_DEVICE; }
+int snag_num_sms(void) { return num_sms(); }
+
+int snag_sim_plan(int n_rows, int n_cols, int Dpad, int* tiles_per_chunk, int* n_chunks) {
+  SimPlan pl;
+  const int rc = make_plan(n_rows, n_cols, Dpad, &pl);
+  if (rc) return rc;
+  if (tiles_per_chunk) *tiles_per_chunk = pl.tiles_per_chunk;
+  if (n_chunks) *n_chunks = pl.n_chunks;
+  return SNAG_OK;
+}
+
+int snag_noise_mask(const float* x, float* out, const float* mean, const float* std_, const uint8_t* mask,
+                    const float* zsel, const int32_t* selpos, int64_t N, int32_t F, int64_t ld_in, int64_t ld_out,
+                    float ratio, float keep, float rho, uint64_t seed, int64_t row0, void* stream) {
+  return launch_noise_mask(x, out, mean, std_, mask, zsel, selpos, N, F, ld_in, ld_out, ratio, keep, rho, seed, row0,
+                           S(stream));
+}
+int snag_philox_rowmask(uint8_t* mask, int64_t N, float ratio, uint64_t seed, int64_t row0, void* stream) {
+  return launch_philox_rowmask(mask, N, ratio, seed, row0, S(stream));
+}
+int snag_gauss_fill(float* out, const float* mean, const float* std_, int64_t N, int32_t F, int64_t ld, uint64_t seed,
+                    int64_t row0, void* stream) {
+  return launch_gauss_fill(out, mean, std_, N, F, ld, seed, row0, S(stream));
+}
+int snag_col_mean_std(const float* x, const uint8_t* valid, int64_t N, int32_t F, int64_t ld, float* mean, float* std_,
+                      void* workspace, void* stream) {
+  return launch_col_mean_std(x, valid, N, F, ld, mean, std_, workspace, S(stream));
+}
+int snag_rowblend_fwd(const float* e, const float* noise, const uint8_t* mask, float* out, int64_t N, int32_t D, float a,
+                      float c, void* stream) {
+  return launch_rowblend_fwd(e, noise, mask, out, N, D, a, c, S(stream));
+}
+int snag_rowblend_bwd(const float* g_out, const uint8_t* mask, float* g_in, int64_t N, int32_t D, float a, void* stream) {
+  return launch_rowblend_bwd(g_out, mask, g_in, N, D, a, S(stream));
+}
+
+int snag_prep_bf16(const float* emb, int64_t ld, const int64_t* idx, int32_t n, int32_t D, int32_t normalize,
+                   uint16_t* out, int32_t Dpad, float* norm2, void* stream) {
+  return launch_prep_bf16(emb, ld, reinterpret_cast<const long long*>(idx), n, D, normalize,
+                          reinterpret_cast<__nv_bfloat16*>(out), Dpad, norm2, S(stream));
+}
+
+int snag_sim_write(const uint16_t* X, const uint16_t* Y, const float* xn, const float* yn, int32_t n1, int32_t n2,
+                   int32_t Dpad, int32_t mode, float* out, int64_t ld, void* stream) {
+  return launch_sim_write(BF(X), BF(Y), xn, yn, n1, n2, Dpad, mode, out, ld, S(stream));
+}
+int snag_eval_rowtopk(const uint16_t* X, const uint16_t* Y, const float* xn, const float* yn, int32_t n1, int32_t n2,
+                      int32_t Dpad, float* part, void* stream) {
+  return launch_eval_rowtopk(BF(X), BF(Y), xn, yn, n1, n2, Dpad, part, S(stream));
+}
+int snag_topk_merge_mean(const float* part, int32_t n_lists, int64_t n_rows, int32_t k, float* nv, float* cand_out,
+                         void* stream) {
+  return launch_topk_merge_mean(part, n_lists, n_rows, k, nv, cand_out, S(stream));
+}
+int snag_pair_score(const uint16_t* X, const uint16_t* Y, int32_t Dpad, int64_t n, const float* xn, const float* yn,
+                    const float* nv1, const float* nv2, int32_t use_csls, float* g, float* s_out, void* stream) {
+  return launch_pair_score(BF(X), BF(Y), Dpad, n, xn, yn, nv1, nv2, use_csls, g, s_out, S(stream));
+}
+int snag_eval_rank(const uint16_t* X, const uint16_t* Y, const float* xn, const float* yn, const float* nv1,
+                   const float* nv2, const float* g_row, const float* g_col, int32_t row_gid0, int32_t col_gid0,
+                   int32_t n1, int32_t n2, int32_t Dpad, int32_t use_csls, int32_t* cnt_row, int32_t* cnt_col,
+                   float* top3_val, int32_t* top3_idx, void* stream) {
+  return launch_eval_rank(BF(X), BF(Y), xn, yn, nv1, nv2, g_row, g_col, row_gid0, col_gid0, n1, n2, Dpad, use_csls, cnt_row,
+                          cnt_col, top3_val, top3_idx, S(stream));
+}
+int snag_top3_merge(const float* val, const int32_t* idx, int32_t n_lists, int64_t n_rows, float* oval, int32_t* oidx,
+                    void* stream) {
+  return launch_top3_merge(val, idx, n_lists, n_rows, oval, oidx, S(stream));
+}
+
+int snag_icl_rowsum(const uint16_t* X, const uint16_t* Y, int32_t B, int32_t Bp, int32_t Dpad, float inv_tau,
+                    float* rowsum_part, float* pos, void* stream) {
+  return launch_icl_rowsum(BF(X), BF(Y), B, Bp, Dpad, inv_tau, rowsum_part, pos, S(stream));
+}
+int snag_icl_finalize(const float* rowsum_part, int32_t n_chunks, int32_t B, int32_t Bp, const float* pos,
+                      float inv_tau, float* lse, float* nll, void* stream) {
+  if (!rowsum_part || !pos || !lse || !nll || B <= 0 || n_chunks <= 0) return SNAG_ERR_ARG;
+  return launch_icl_finalize(rowsum_part, n_chunks, B, Bp, pos, inv_tau, lse, nll, S(stream));
+}
+
+}  // extern "C"

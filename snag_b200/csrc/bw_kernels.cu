@@ -1,0 +1,475 @@
+// HBM-bound kernels of the SNAG hot path: normalise+gather+cast prologue, Gauss modality noise mask,
+// column mean/std, entity-row blend (fwd/bwd), CSLS candidate merge, ground-truth ("diagonal") scores,
+// and the materialised CSLS drop-in. All vectorised, coalesced, grid sized from the SM count.
+#include "common.cuh"
+#include "snag_internal.h"
+
+namespace snag {
+
+// ------------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. 2011) — counter-based, so the noise is a pure function of
+// (seed, stream, global element index) and identical for any row sharding across GPUs.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += 0x9E3779B9u;
+    key.y += 0xBB67AE85u;
+  }
+  return ctr;
+}
+__device__ __forceinline__ float u32_to_unit(uint32_t x) { return static_cast<float>(x >> 8) * (1.0f / 16777216.0f); }
+// Box-Muller on two 32-bit draws; u1 in (0,1]
+__device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
+  const float u1 = (static_cast<float>(a >> 8) + 1.0f) * (1.0f / 16777216.0f);
+  const float u2 = static_cast<float>(b >> 8) * (1.0f / 16777216.0f);
+  const float rad = sqrtf(-2.0f * logf(u1));
+  float s, c;
+  sincospif(2.0f * u2, &s, &c);
+  return make_float2(rad * c, rad * s);
+}
+__device__ __forceinline__ bool philox_row_selected(unsigned long long seed, long long row, float ratio) {
+  const uint4 r = philox4x32_10(make_uint4(static_cast<uint32_t>(row), static_cast<uint32_t>(row >> 32), 0u, 1u),
+                                make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
+  return u32_to_unit(r.x) < ratio;
+}
+
+// ------------------------------------------------------------------------------------------------
+// a1  SNAG.add_noise_to_embeddings  (model/SNAG.py:66-75)
+//   selected rows:  out = (1-rho)*x + rho*(mean + std*z)     every op rounded separately, like torch
+//   other rows:     out = x
+// mask/z may be injected (bit parity with the reference's own draws) or generated in-kernel (Philox).
+//   mask   : uint8 [N] or null          zsel : fp32 [n_sel, F] or null, row order = selected rows
+//   selpos : int32 [N] (position of row in zsel; only read for selected rows) or null
+// One float4 per thread-iteration; rows are contiguous so every access is a full 16-byte coalesced lane.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) noise_mask_kernel(const float* __restrict__ x, float* __restrict__ out,
+                                                         const float* __restrict__ mean, const float* __restrict__ stdv,
+                                                         const uint8_t* __restrict__ mask, const float* __restrict__ zsel,
+                                                         const int* __restrict__ selpos, long long N, int F, long long ld_in,
+                                                         long long ld_out, float ratio, float keep, float rho,
+                                                         unsigned long long seed, long long row0) {
+  const int f4 = F >> 2;
+  const long long total = N * f4;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long row = i / f4;
+    const int c = static_cast<int>(i - row * f4) << 2;
+    float4 v = __ldg(reinterpret_cast<const float4*>(x + row * ld_in + c));
+    const bool sel = mask ? (mask[row] != 0) : philox_row_selected(seed, row0 + row, ratio);
+    if (sel) {
+      float4 z;
+      if (zsel) {
+        z = __ldg(reinterpret_cast<const float4*>(zsel + static_cast<long long>(selpos[row]) * F + c));
+      } else {
+        const unsigned long long e = static_cast<unsigned long long>(row0 + row) * F + c;   // global element index
+        const uint4 r = philox4x32_10(make_uint4(static_cast<uint32_t>(e >> 2), static_cast<uint32_t>(e >> 34), 0u, 2u),
+                                      make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
+        const float2 a = box_muller(r.x, r.y), b = box_muller(r.z, r.w);
+        z = make_float4(a.x, a.y, b.x, b.y);
+      }
+      const float4 m = __ldg(reinterpret_cast<const float4*>(mean + c));
+      const float4 s = __ldg(reinterpret_cast<const float4*>(stdv + c));
+      v.x = __fadd_rn(__fmul_rn(keep, v.x), __fmul_rn(rho, __fadd_rn(m.x, __fmul_rn(s.x, z.x))));
+      v.y = __fadd_rn(__fmul_rn(keep, v.y), __fmul_rn(rho, __fadd_rn(m.y, __fmul_rn(s.y, z.y))));
+      v.z = __fadd_rn(__fmul_rn(keep, v.z), __fmul_rn(rho, __fadd_rn(m.z, __fmul_rn(s.z, z.z))));
+      v.w = __fadd_rn(__fmul_rn(keep, v.w), __fmul_rn(rho, __fadd_rn(m.w, __fmul_rn(s.w, z.w))));
+    }
+    *reinterpret_cast<float4*>(out + row * ld_out + c) = v;
+  }
+}
+
+// writes the Philox row selection as a uint8 mask (entity_noise_mask of update_noise, SNAG.py:98)
+__global__ void philox_rowmask_kernel(uint8_t* mask, long long N, float ratio, unsigned long long seed, long long row0) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i < N) mask[i] = philox_row_selected(seed, row0 + i, ratio) ? 1 : 0;
+}
+
+// out[i,:] = mean + std * z(i,:)   (entity_noise of update_noise, SNAG.py:96), z from Philox stream 3
+__global__ void __launch_bounds__(256) gauss_fill_kernel(float* __restrict__ out, const float* __restrict__ mean,
+                                                         const float* __restrict__ stdv, long long N, int F,
+                                                         long long ld, unsigned long long seed, long long row0) {
+  const int f4 = F >> 2;
+  const long long total = N * f4;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long row = i / f4;
+    const int c = static_cast<int>(i - row * f4) << 2;
+    const unsigned long long e = static_cast<unsigned long long>(row0 + row) * F + c;
+    const uint4 r = philox4x32_10(make_uint4(static_cast<uint32_t>(e >> 2), static_cast<uint32_t>(e >> 34), 0u, 3u),
+                                  make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
+    const float2 a = box_muller(r.x, r.y), b = box_muller(r.z, r.w);
+    const float4 m = __ldg(reinterpret_cast<const float4*>(mean + c));
+    const float4 s = __ldg(reinterpret_cast<const float4*>(stdv + c));
+    float4 v;
+    v.x = __fadd_rn(m.x, __fmul_rn(s.x, a.x));
+    v.y = __fadd_rn(m.y, __fmul_rn(s.y, a.y));
+    v.z = __fadd_rn(m.z, __fmul_rn(s.z, b.x));
+    v.w = __fadd_rn(m.w, __fmul_rn(s.w, b.y));
+    *reinterpret_cast<float4*>(out + row * ld + c) = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// a2/a3  column mean and unbiased std over (optionally a subset of) rows  (SNAG.py:77-84, 94-95)
+// pass 1: per-(row slab, column) partial sum / sum of squares in fp64 -> atomics into acc[2][F]
+// pass 2: mean = S/n, std = sqrt((SS - S*S/n)/(n-1))
+// threads map to consecutive columns, so each warp reads 128 contiguous bytes of a row.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) col_stats_partial_kernel(const float* __restrict__ x, const uint8_t* __restrict__ valid,
+                                                                long long N, int F, long long ld, int rows_per_slab,
+                                                                double* __restrict__ acc, unsigned long long* __restrict__ cnt) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  const long long r0 = static_cast<long long>(blockIdx.y) * rows_per_slab;
+  const long long r1 = min(r0 + rows_per_slab, N);
+  double s = 0.0, ss = 0.0;
+  unsigned long long n = 0;
+  if (col < F) {
+    for (long long r = r0; r < r1; ++r) {
+      if (valid && !valid[r]) continue;
+      const double v = static_cast<double>(__ldg(x + r * ld + col));
+      s += v;
+      ss += v * v;
+      ++n;
+    }
+    atomicAdd(acc + col, s);
+    atomicAdd(acc + F + col, ss);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (valid == nullptr) n = static_cast<unsigned long long>(r1 - r0);
+    atomicAdd(cnt, n);
+  }
+}
+__global__ void col_stats_final_kernel(const double* __restrict__ acc, const unsigned long long* __restrict__ cnt, int F,
+                                       float* __restrict__ mean, float* __restrict__ stdv) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= F) return;
+  const double n = static_cast<double>(*cnt);
+  const double s = acc[col], ss = acc[F + col];
+  const double m = s / n;
+  double var = (ss - s * m) / (n - 1.0);
+  if (var < 0.0) var = 0.0;
+  mean[col] = static_cast<float>(m);
+  stdv[col] = static_cast<float>(sqrt(var));
+}
+
+// ------------------------------------------------------------------------------------------------
+// a4  entity-embedding blend inside MultiModalEncoder.forward (model/SNAG_tools.py:127-128)
+//   fwd: out = mask ? a*e + c*noise : e        bwd: grad_e = mask ? a*g : g
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) rowblend_fwd_kernel(const float* __restrict__ e, const float* __restrict__ noise,
+                                                           const uint8_t* __restrict__ mask, float* __restrict__ out,
+                                                           long long N, int D, float a, float c) {
+  const int d4 = D >> 2;
+  const long long total = N * d4;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long row = i / d4;
+    float4 v = __ldg(reinterpret_cast<const float4*>(e) + i);
+    if (mask[row]) {
+      const float4 z = __ldg(reinterpret_cast<const float4*>(noise) + i);
+      v.x = __fadd_rn(__fmul_rn(a, v.x), __fmul_rn(c, z.x));
+      v.y = __fadd_rn(__fmul_rn(a, v.y), __fmul_rn(c, z.y));
+      v.z = __fadd_rn(__fmul_rn(a, v.z), __fmul_rn(c, z.z));
+      v.w = __fadd_rn(__fmul_rn(a, v.w), __fmul_rn(c, z.w));
+    }
+    reinterpret_cast<float4*>(out)[i] = v;
+  }
+}
+__global__ void __launch_bounds__(256) rowblend_bwd_kernel(const float* __restrict__ g, const uint8_t* __restrict__ mask,
+                                                           float* __restrict__ gin, long long N, int D, float a) {
+  const int d4 = D >> 2;
+  const long long total = N * d4;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long row = i / d4;
+    float4 v = __ldg(reinterpret_cast<const float4*>(g) + i);
+    if (mask[row]) { v.x = __fmul_rn(a, v.x); v.y = __fmul_rn(a, v.y); v.z = __fmul_rn(a, v.z); v.w = __fmul_rn(a, v.w); }
+    reinterpret_cast<float4*>(gin)[i] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// prologue: (gather) -> (L2 normalise, F.normalize eps 1e-12) -> round to bf16 -> zero-pad to Dpad,
+// plus ||row||^2 of the ROUNDED row (fp64 accumulate, rounded once to fp32): the xn/yn of
+// pairwise_distances (src/utils.py:210-212) on exactly the values the tensor cores will see.
+// One warp per row; lanes stride the row so loads/stores are coalesced.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) prep_bf16_kernel(const float* __restrict__ emb, long long ld,
+                                                        const long long* __restrict__ idx, int n, int D, int normalize,
+                                                        __nv_bfloat16* __restrict__ out, int Dpad,
+                                                        float* __restrict__ norm2) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= n) return;
+  const float* src = emb + (idx ? idx[warp] : static_cast<long long>(warp)) * ld;
+  float denom = 1.0f;
+  if (normalize) {
+    float ss = 0.f;
+    for (int c = lane; c < D; c += 32) { const float v = __ldg(src + c); ss = __fmaf_rn(v, v, ss); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    denom = fmaxf(sqrtf(ss), 1e-12f);
+  }
+  double acc = 0.0;
+  __nv_bfloat16* dst = out + static_cast<long long>(warp) * Dpad;
+  for (int c = lane; c < Dpad; c += 32) {
+    float v = 0.f;
+    if (c < D) v = normalize ? __fdiv_rn(__ldg(src + c), denom) : __ldg(src + c);
+    const __nv_bfloat16 b = __float2bfloat16_rn(v);
+    dst[c] = b;
+    const double w = static_cast<double>(__bfloat162float(b));
+    acc += w * w;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0 && norm2) norm2[warp] = static_cast<float>(acc);
+}
+
+// ------------------------------------------------------------------------------------------------
+// CSLS neighbourhood means: merge the per-chunk ascending KT-lists of every row, keep the KT largest,
+// nv[row] = (sum of the k largest, accumulated largest-first in fp32) / k     (src/utils.py:431-432)
+// Optionally also emits the merged KT-list (descending) for the cross-GPU candidate exchange.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) topk_merge_mean_kernel(const float* __restrict__ part, int n_lists, long long n_rows,
+                                                              int k, float* __restrict__ nv, float* __restrict__ cand_out) {
+  const long long row = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (row >= n_rows) return;
+  float top[KT_LIST];
+#pragma unroll
+  for (int t = 0; t < KT_LIST; ++t) top[t] = -INFINITY;
+  for (int l = 0; l < n_lists; ++l) {
+    const float4* src = reinterpret_cast<const float4*>(part + (static_cast<long long>(l) * n_rows + row) * KT_LIST);
+#pragma unroll
+    for (int q = 0; q < KT_LIST / 4; ++q) {
+      const float4 v4 = __ldg(src + q);
+      const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float v = vv[e];
+        if (v > top[0]) {
+          top[0] = v;
+#pragma unroll
+          for (int t = 0; t < KT_LIST - 1; ++t) {
+            const float lo = fminf(top[t], top[t + 1]), hi = fmaxf(top[t], top[t + 1]);
+            top[t] = lo;
+            top[t + 1] = hi;
+          }
+        }
+      }
+    }
+  }
+  if (nv) {
+    float s = 0.f;
+#pragma unroll
+    for (int t = 0; t < KT_LIST; ++t)
+      if (t < k) s = __fadd_rn(s, top[KT_LIST - 1 - t]);
+    nv[row] = __fdiv_rn(s, static_cast<float>(k));
+  }
+  if (cand_out) {
+    float4* o = reinterpret_cast<float4*>(cand_out + row * KT_LIST);
+#pragma unroll
+    for (int q = 0; q < KT_LIST / 4; ++q) o[q] = make_float4(top[4 * q], top[4 * q + 1], top[4 * q + 2], top[4 * q + 3]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// ground-truth scores: g[p] = CSLS distance of pair p = (x_p, y_p), with the dot product accumulated
+// in fp64 in index order and rounded once to fp32 (the oracle's definition of s_pp), then the same
+// fp32 chain as the fused epilogue. One thread per pair; 16-byte loads.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) pair_score_kernel(const __nv_bfloat16* __restrict__ X, const __nv_bfloat16* __restrict__ Y,
+                                                         int Dpad, long long n, const float* __restrict__ xn,
+                                                         const float* __restrict__ yn, const float* __restrict__ nv1,
+                                                         const float* __restrict__ nv2, int use_csls, float* __restrict__ g,
+                                                         float* __restrict__ s_out) {
+  const long long p = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (p >= n) return;
+  const uint4* xr = reinterpret_cast<const uint4*>(X + p * Dpad);
+  const uint4* yr = reinterpret_cast<const uint4*>(Y + p * Dpad);
+  double acc = 0.0;
+  for (int c = 0; c < Dpad / 8; ++c) {
+    const uint4 a = __ldg(xr + c), b = __ldg(yr + c);
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      // bf16 -> fp32 is a 16-bit shift; low half first (little endian = lower column index)
+      const float a0 = __uint_as_float(aw[e] << 16), a1 = __uint_as_float(aw[e] & 0xffff0000u);
+      const float b0 = __uint_as_float(bw[e] << 16), b1 = __uint_as_float(bw[e] & 0xffff0000u);
+      acc = fma(static_cast<double>(a0), static_cast<double>(b0), acc);
+      acc = fma(static_cast<double>(a1), static_cast<double>(b1), acc);
+    }
+  }
+  const float s = static_cast<float>(acc);
+  if (s_out) s_out[p] = s;
+  const float t = __fadd_rn(xn[p], yn[p]);
+  const float d = fmaxf(__fmaf_rn(-2.0f, s, t), 0.0f);
+  if (!use_csls) { g[p] = d; return; }
+  const float c = __fsub_rn(1.0f, d);
+  const float u = __fmaf_rn(2.0f, c, -nv1[p]);
+  g[p] = __fsub_rn(1.0f, __fsub_rn(u, nv2[p]));
+}
+
+// merge per-chunk top-3 (value asc, index asc on ties) lists of each row
+__global__ void __launch_bounds__(128) top3_merge_kernel(const float* __restrict__ val, const int* __restrict__ idx, int n_lists,
+                                                         long long n_rows, float* __restrict__ oval, int* __restrict__ oidx) {
+  const long long row = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (row >= n_rows) return;
+  float v[3] = {INFINITY, INFINITY, INFINITY};
+  int id[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff};
+  for (int l = 0; l < n_lists; ++l) {
+    const float4 cv = __ldg(reinterpret_cast<const float4*>(val + (static_cast<long long>(l) * n_rows + row) * 4));
+    const int4 ci = __ldg(reinterpret_cast<const int4*>(idx + (static_cast<long long>(l) * n_rows + row) * 4));
+    const float cvv[3] = {cv.x, cv.y, cv.z};
+    const int cii[3] = {ci.x, ci.y, ci.z};
+#pragma unroll
+    for (int e = 0; e < 3; ++e) {
+      if (cvv[e] < v[2] || (cvv[e] == v[2] && cii[e] < id[2])) {
+        v[2] = cvv[e]; id[2] = cii[e];
+#pragma unroll
+        for (int t = 2; t > 0; --t) {
+          if (v[t] < v[t - 1] || (v[t] == v[t - 1] && id[t] < id[t - 1])) {
+            const float tv = v[t]; v[t] = v[t - 1]; v[t - 1] = tv;
+            const int ti = id[t]; id[t] = id[t - 1]; id[t - 1] = ti;
+          }
+        }
+      }
+    }
+  }
+  *reinterpret_cast<float4*>(oval + row * 4) = make_float4(v[0], v[1], v[2], 0.f);
+  *reinterpret_cast<int4*>(oidx + row * 4) = make_int4(id[0], id[1], id[2], 0);
+}
+
+// ICL forward finalize: lse = log(sum over chunks) + 1/tau ; nll = lse - pos/tau
+__global__ void icl_finalize_kernel(const float* __restrict__ rowsum_part, int n_chunks, int B, int Bp,
+                                    const float* __restrict__ pos, float inv_tau, float* __restrict__ lse,
+                                    float* __restrict__ nll) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B) return;
+  float s = 0.f;
+  for (int c = 0; c < n_chunks; ++c) s += rowsum_part[static_cast<long long>(c) * Bp + i];
+  const float l = logf(s) + inv_tau;
+  lse[i] = l;
+  nll[i] = l - pos[i] * inv_tau;
+}
+
+// ================================================================================================
+// host launchers
+// ================================================================================================
+static inline int grid_for(long long work_items, int block, int num_sms, int ctas_per_sm) {
+  long long g = (work_items + block - 1) / block;
+  const long long cap = static_cast<long long>(num_sms) * ctas_per_sm;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return static_cast<int>(g);
+}
+
+int launch_noise_mask(const float* x, float* out, const float* mean, const float* stdv, const uint8_t* mask,
+                      const float* zsel, const int* selpos, long long N, int F, long long ld_in, long long ld_out,
+                      float ratio, float keep, float rho, unsigned long long seed, long long row0, cudaStream_t st) {
+  if (!x || !out || !mean || !stdv || N <= 0 || F <= 0) return SNAG_ERR_ARG;
+  if ((F & 3) || (ld_in & 3) || (ld_out & 3)) return SNAG_ERR_ALIGN;
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(mean) |
+       reinterpret_cast<uintptr_t>(stdv) | reinterpret_cast<uintptr_t>(zsel)) & 15) return SNAG_ERR_ALIGN;
+  if (zsel && (!selpos || !mask)) return SNAG_ERR_ARG;
+  const int g = grid_for(N * (F >> 2), 256, num_sms(), 8);
+  noise_mask_kernel<<<g, 256, 0, st>>>(x, out, mean, stdv, mask, zsel, selpos, N, F, ld_in, ld_out, ratio, keep, rho, seed, row0);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int launch_philox_rowmask(uint8_t* mask, long long N, float ratio, unsigned long long seed, long long row0, cudaStream_t st) {
+  if (!mask || N <= 0) return SNAG_ERR_ARG;
+  philox_rowmask_kernel<<<static_cast<int>((N + 255) / 256), 256, 0, st>>>(mask, N, ratio, seed, row0);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int launch_gauss_fill(float* out, const float* mean, const float* stdv, long long N, int F, long long ld,
+                      unsigned long long seed, long long row0, cudaStream_t st) {
+  if (!out || !mean || !stdv || N <= 0 || F <= 0) return SNAG_ERR_ARG;
+  if ((F & 3) || (ld & 3)) return SNAG_ERR_ALIGN;
+  if ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(mean) | reinterpret_cast<uintptr_t>(stdv)) & 15)
+    return SNAG_ERR_ALIGN;
+  const int g = grid_for(N * (F >> 2), 256, num_sms(), 8);
+  gauss_fill_kernel<<<g, 256, 0, st>>>(out, mean, stdv, N, F, ld, seed, row0);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int launch_col_mean_std(const float* x, const uint8_t* valid, long long N, int F, long long ld, float* mean, float* stdv,
+                        void* workspace, cudaStream_t st) {
+  if (!x || !mean || !stdv || !workspace || N <= 1 || F <= 0) return SNAG_ERR_ARG;
+  double* acc = reinterpret_cast<double*>(workspace);
+  unsigned long long* cnt = reinterpret_cast<unsigned long long*>(acc + 2 * static_cast<long long>(F));
+  cudaError_t e = cudaMemsetAsync(workspace, 0, (2 * static_cast<size_t>(F) + 1) * 8, st);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  const int bx = (F + 255) / 256;
+  // enough row slabs to fill the machine a few times over, at least 64 rows each
+  long long slabs = (static_cast<long long>(num_sms()) * 8 + bx - 1) / bx;
+  long long rows_per_slab = (N + slabs - 1) / slabs;
+  if (rows_per_slab < 64) rows_per_slab = 64;
+  slabs = (N + rows_per_slab - 1) / rows_per_slab;
+  col_stats_partial_kernel<<<dim3(bx, static_cast<unsigned>(slabs)), 256, 0, st>>>(x, valid, N, F, ld, static_cast<int>(rows_per_slab), acc, cnt);
+  col_stats_final_kernel<<<bx, 256, 0, st>>>(acc, cnt, F, mean, stdv);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int launch_rowblend_fwd(const float* e, const float* noise, const uint8_t* mask, float* out, long long N, int D, float a,
+                        float c, cudaStream_t st) {
+  if (!e || !noise || !mask || !out || N <= 0 || D <= 0) return SNAG_ERR_ARG;
+  if (D & 3) return SNAG_ERR_ALIGN;
+  if ((reinterpret_cast<uintptr_t>(e) | reinterpret_cast<uintptr_t>(noise) | reinterpret_cast<uintptr_t>(out)) & 15)
+    return SNAG_ERR_ALIGN;
+  const int g = grid_for(N * (D >> 2), 256, num_sms(), 8);
+  rowblend_fwd_kernel<<<g, 256, 0, st>>>(e, noise, mask, out, N, D, a, c);
+  return static_cast<int>(cudaGetLastError());
+}
+int launch_rowblend_bwd(const float* g_out, const uint8_t* mask, float* g_in, long long N, int D, float a, cudaStream_t st) {
+  if (!g_out || !mask || !g_in || N <= 0 || D <= 0) return SNAG_ERR_ARG;
+  if (D & 3) return SNAG_ERR_ALIGN;
+  if ((reinterpret_cast<uintptr_t>(g_out) | reinterpret_cast<uintptr_t>(g_in)) & 15) return SNAG_ERR_ALIGN;
+  const int g = grid_for(N * (D >> 2), 256, num_sms(), 8);
+  rowblend_bwd_kernel<<<g, 256, 0, st>>>(g_out, mask, g_in, N, D, a);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int launch_prep_bf16(const float* emb, long long ld, const long long* idx, int n, int D, int normalize,
+                     __nv_bfloat16* out, int Dpad, float* norm2, cudaStream_t st) {
+  if (!emb || !out || n <= 0 || D <= 0) return SNAG_ERR_ARG;
+  if (Dpad < D || (Dpad % 64) != 0) return SNAG_ERR_SHAPE;
+  const long long threads = static_cast<long long>(n) * 32;
+  prep_bf16_kernel<<<static_cast<int>((threads + 255) / 256), 256, 0, st>>>(emb, ld, idx, n, D, normalize, out, Dpad, norm2);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int launch_topk_merge_mean(const float* part, int n_lists, long long n_rows, int k, float* nv, float* cand_out,
+                           cudaStream_t st) {
+  if (!part || n_lists <= 0 || n_rows <= 0 || (!nv && !cand_out)) return SNAG_ERR_ARG;
+  if (k < 1 || k > KT_LIST) return SNAG_ERR_SHAPE;
+  topk_merge_mean_kernel<<<static_cast<int>((n_rows + 127) / 128), 128, 0, st>>>(part, n_lists, n_rows, k, nv, cand_out);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int launch_pair_score(const __nv_bfloat16* X, const __nv_bfloat16* Y, int Dpad, long long n, const float* xn, const float* yn,
+                      const float* nv1, const float* nv2, int use_csls, float* g, float* s_out, cudaStream_t st) {
+  if (!X || !Y || !xn || !yn || !g || n <= 0) return SNAG_ERR_ARG;
+  if (use_csls && (!nv1 || !nv2)) return SNAG_ERR_ARG;
+  if (Dpad % 64) return SNAG_ERR_SHAPE;
+  pair_score_kernel<<<static_cast<int>((n + 127) / 128), 128, 0, st>>>(X, Y, Dpad, n, xn, yn, nv1, nv2, use_csls, g, s_out);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int launch_top3_merge(const float* val, const int* idx, int n_lists, long long n_rows, float* oval, int* oidx, cudaStream_t st) {
+  if (!val || !idx || !oval || !oidx || n_lists <= 0 || n_rows <= 0) return SNAG_ERR_ARG;
+  top3_merge_kernel<<<static_cast<int>((n_rows + 127) / 128), 128, 0, st>>>(val, idx, n_lists, n_rows, oval, oidx);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int launch_icl_finalize(const float* rowsum_part, int n_chunks, int B, int Bp, const float* pos, float inv_tau, float* lse,
+                        float* nll, cudaStream_t st) {
+  icl_finalize_kernel<<<(B + 255) / 256, 256, 0, st>>>(rowsum_part, n_chunks, B, Bp, pos, inv_tau, lse, nll);
+  return static_cast<int>(cudaGetLastError());
+}
+
+}  // namespace snag

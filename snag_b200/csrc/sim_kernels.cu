@@ -1,0 +1,167 @@
+// Host side of the tcgen05 similarity sweeps: TMA descriptors, work plan, launches.
+#include <mutex>
+#include "simgemm.cuh"
+#include "snag_internal.h"
+
+namespace snag {
+
+static_assert(KT == KT_LIST, "candidate list length mismatch");
+
+// ------------------------------------------------------------------------------------------------
+// device info
+// ------------------------------------------------------------------------------------------------
+static int g_sms[64];
+static int g_cc[64];
+static std::once_flag g_dev_once[64];
+
+static void query_dev(int dev) {
+  cudaDeviceProp p;
+  if (cudaGetDeviceProperties(&p, dev) == cudaSuccess) {
+    g_sms[dev] = p.multiProcessorCount;
+    g_cc[dev] = p.major * 10 + p.minor;
+  } else {
+    g_sms[dev] = 1;
+    g_cc[dev] = 0;
+  }
+}
+int num_sms() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  std::call_once(g_dev_once[dev], query_dev, dev);
+  return g_sms[dev];
+}
+int device_is_sm100() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  dev &= 63;
+  std::call_once(g_dev_once[dev], query_dev, dev);
+  return g_cc[dev] / 10 == 10;
+}
+
+// ------------------------------------------------------------------------------------------------
+// work plan: chunk of Y kept <= ~40 MB (L2 resident while ~148 row blocks sweep it), and enough
+// units (>= ~4 per SM) for the persistent grid to balance.
+// ------------------------------------------------------------------------------------------------
+int make_plan(int n_rows, int n_cols, int Dpad, SimPlan* pl) {
+  if (n_rows <= 0 || n_cols <= 0 || Dpad <= 0 || (Dpad % BK) != 0 || !pl) return SNAG_ERR_SHAPE;
+  pl->kblocks = Dpad / BK;
+  pl->row_blocks = (n_rows + BM - 1) / BM;
+  pl->col_tiles = (n_cols + BN - 1) / BN;
+  const long long tile_bytes = static_cast<long long>(BN) * Dpad * 2;
+  long long max_tiles_l2 = (40ll << 20) / tile_bytes;
+  if (max_tiles_l2 < 1) max_tiles_l2 = 1;
+  const int sms = num_sms();
+  long long want_chunks = (4ll * sms + pl->row_blocks - 1) / pl->row_blocks;
+  if (want_chunks < 1) want_chunks = 1;
+  long long tpc = (pl->col_tiles + want_chunks - 1) / want_chunks;
+  if (tpc > max_tiles_l2) tpc = max_tiles_l2;
+  if (tpc < 1) tpc = 1;
+  pl->tiles_per_chunk = static_cast<int>(tpc);
+  pl->n_chunks = (pl->col_tiles + pl->tiles_per_chunk - 1) / pl->tiles_per_chunk;
+  const long long units = static_cast<long long>(pl->row_blocks) * pl->n_chunks;
+  if (units > 0x7fffffffll) return SNAG_ERR_SHAPE;
+  pl->n_units = static_cast<int>(units);
+  return SNAG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// TMA descriptors through the driver entry point (no link-time dependency on libcuda)
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+static std::once_flag g_encode_once;
+static void load_encode() {
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess &&
+      q == cudaDriverEntryPointSuccess)
+    g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+}
+
+// bf16 row-major [rows, Dpad] operand, box = [box_rows x 64 elements], 128-byte swizzle, zero OOB fill
+static int make_operand_map(CUtensorMap* m, const __nv_bfloat16* ptr, long long rows, int Dpad, int box_rows) {
+  std::call_once(g_encode_once, load_encode);
+  if (!g_encode) return SNAG_ERR_DRIVER;
+  if (reinterpret_cast<uintptr_t>(ptr) & 127) return SNAG_ERR_ALIGN;
+  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(Dpad), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(Dpad) * 2};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(box_rows)};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(ptr), dims, strides, box,
+                              estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? SNAG_OK : SNAG_ERR_DRIVER;
+}
+
+template <class Epi>
+static int launch_sim(const __nv_bfloat16* X, const __nv_bfloat16* Y, int n1, int n2, int Dpad,
+                      const typename Epi::Params& ep, cudaStream_t st) {
+  if (!X || !Y) return SNAG_ERR_ARG;
+  if (!device_is_sm100()) return SNAG_ERR_DEVICE;
+  SimPlan pl;
+  int rc = make_plan(n1, n2, Dpad, &pl);
+  if (rc) return rc;
+  CUtensorMap tmX, tmY;
+  if ((rc = make_operand_map(&tmX, X, n1, Dpad, BM))) return rc;
+  if ((rc = make_operand_map(&tmY, Y, n2, Dpad, BN))) return rc;
+  // the attribute is per device; setting it on every call is cheap and covers multi-device processes
+  const cudaError_t attr_err =
+      cudaFuncSetAttribute(sim_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, SIM_SMEM_BYTES);
+  if (attr_err != cudaSuccess) return static_cast<int>(attr_err);
+  SimShape shp;
+  shp.n_rows = n1;
+  shp.n_cols = n2;
+  shp.kblocks = pl.kblocks;
+  shp.row_blocks = pl.row_blocks;
+  shp.col_tiles = pl.col_tiles;
+  shp.tiles_per_chunk = pl.tiles_per_chunk;
+  shp.n_chunks = pl.n_chunks;
+  shp.n_units = pl.n_units;
+  const int grid = pl.n_units < num_sms() ? pl.n_units : num_sms();
+  sim_kernel<Epi><<<grid, NUM_THREADS, SIM_SMEM_BYTES, st>>>(tmX, tmY, shp, ep);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int launch_sim_write(const __nv_bfloat16* X, const __nv_bfloat16* Y, const float* xn, const float* yn, int n1, int n2,
+                     int Dpad, int mode, float* out, long long ld, cudaStream_t st) {
+  if (!out || ld < n2) return SNAG_ERR_ARG;
+  if (mode == 1 && (!xn || !yn)) return SNAG_ERR_ARG;
+  EpiWrite::Params p{out, ld, xn, yn, mode};
+  return launch_sim<EpiWrite>(X, Y, n1, n2, Dpad, p, st);
+}
+
+int launch_eval_rowtopk(const __nv_bfloat16* X, const __nv_bfloat16* Y, const float* xn, const float* yn, int n1, int n2,
+                        int Dpad, float* part, cudaStream_t st) {
+  if (!xn || !yn || !part) return SNAG_ERR_ARG;
+  if (reinterpret_cast<uintptr_t>(part) & 15) return SNAG_ERR_ALIGN;
+  EpiRowTopK::Params p{xn, yn, part};
+  return launch_sim<EpiRowTopK>(X, Y, n1, n2, Dpad, p, st);
+}
+
+int launch_eval_rank(const __nv_bfloat16* X, const __nv_bfloat16* Y, const float* xn, const float* yn, const float* nv1,
+                     const float* nv2, const float* g_row, const float* g_col, int row_gid0, int col_gid0, int n1, int n2,
+                     int Dpad, int use_csls, int* cnt_row, int* cnt_col, float* top3_val, int* top3_idx, cudaStream_t st) {
+  if (!xn || !yn || !g_row || !g_col || !cnt_row || !cnt_col) return SNAG_ERR_ARG;
+  if (use_csls && (!nv1 || !nv2)) return SNAG_ERR_ARG;
+  if (!use_csls) { nv1 = xn; nv2 = yn; }   // never read for their values; keeps the staging loads valid
+  if ((top3_val == nullptr) != (top3_idx == nullptr)) return SNAG_ERR_ARG;
+  if (top3_val) {
+    if ((reinterpret_cast<uintptr_t>(top3_val) | reinterpret_cast<uintptr_t>(top3_idx)) & 15) return SNAG_ERR_ALIGN;
+    EpiRank<true>::Params p{xn, yn, nv1, nv2, g_row, g_col, row_gid0, col_gid0, cnt_row, cnt_col, top3_val, top3_idx, use_csls};
+    return launch_sim<EpiRank<true>>(X, Y, n1, n2, Dpad, p, st);
+  }
+  EpiRank<false>::Params p{xn, yn, nv1, nv2, g_row, g_col, row_gid0, col_gid0, cnt_row, cnt_col, nullptr, nullptr, use_csls};
+  return launch_sim<EpiRank<false>>(X, Y, n1, n2, Dpad, p, st);
+}
+
+int launch_icl_rowsum(const __nv_bfloat16* X, const __nv_bfloat16* Y, int B, int Bp, int Dpad, float inv_tau,
+                      float* rowsum_part, float* pos, cudaStream_t st) {
+  if (!rowsum_part || !pos || B <= 0 || Bp < B || (Bp % BN) != 0) return SNAG_ERR_ARG;
+  EpiIclFwd::Params p{inv_tau * 1.4426950408889634f, B, Bp, rowsum_part, pos};
+  return launch_sim<EpiIclFwd>(X, Y, Bp, 2 * Bp, Dpad, p, st);
+}
+
+}  // namespace snag

@@ -1,0 +1,53 @@
+// Internal C++ declarations shared by the translation units of libsnag_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace snag {
+
+constexpr int KT_LIST = 16;   // candidate-list length of the CSLS top-k path (must equal KT in simgemm.cuh)
+
+int num_sms();                // SM count of the current device (cached per device)
+int device_is_sm100();        // 1 if the current device is compute capability 10.x
+
+struct SimPlan {
+  int kblocks, row_blocks, col_tiles, tiles_per_chunk, n_chunks, n_units;
+};
+// Deterministic work decomposition for an [n_rows x n_cols] similarity sweep with padded width Dpad.
+int make_plan(int n_rows, int n_cols, int Dpad, SimPlan* plan);
+
+// ---- bandwidth kernels (bw_kernels.cu)
+int launch_noise_mask(const float* x, float* out, const float* mean, const float* stdv, const uint8_t* mask,
+                      const float* zsel, const int* selpos, long long N, int F, long long ld_in, long long ld_out,
+                      float ratio, float keep, float rho, unsigned long long seed, long long row0, cudaStream_t st);
+int launch_philox_rowmask(uint8_t* mask, long long N, float ratio, unsigned long long seed, long long row0, cudaStream_t st);
+int launch_gauss_fill(float* out, const float* mean, const float* stdv, long long N, int F, long long ld,
+                      unsigned long long seed, long long row0, cudaStream_t st);
+int launch_col_mean_std(const float* x, const uint8_t* valid, long long N, int F, long long ld, float* mean, float* stdv,
+                        void* workspace, cudaStream_t st);
+int launch_rowblend_fwd(const float* e, const float* noise, const uint8_t* mask, float* out, long long N, int D, float a,
+                        float c, cudaStream_t st);
+int launch_rowblend_bwd(const float* g_out, const uint8_t* mask, float* g_in, long long N, int D, float a, cudaStream_t st);
+int launch_prep_bf16(const float* emb, long long ld, const long long* idx, int n, int D, int normalize,
+                     __nv_bfloat16* out, int Dpad, float* norm2, cudaStream_t st);
+int launch_topk_merge_mean(const float* part, int n_lists, long long n_rows, int k, float* nv, float* cand_out,
+                           cudaStream_t st);
+int launch_pair_score(const __nv_bfloat16* X, const __nv_bfloat16* Y, int Dpad, long long n, const float* xn, const float* yn,
+                      const float* nv1, const float* nv2, int use_csls, float* g, float* s_out, cudaStream_t st);
+int launch_top3_merge(const float* val, const int* idx, int n_lists, long long n_rows, float* oval, int* oidx, cudaStream_t st);
+int launch_icl_finalize(const float* rowsum_part, int n_chunks, int B, int Bp, const float* pos, float inv_tau, float* lse,
+                        float* nll, cudaStream_t st);
+
+// ---- tcgen05 similarity sweeps (sim_kernels.cu)
+int launch_sim_write(const __nv_bfloat16* X, const __nv_bfloat16* Y, const float* xn, const float* yn, int n1, int n2,
+                     int Dpad, int mode, float* out, long long ld, cudaStream_t st);
+int launch_eval_rowtopk(const __nv_bfloat16* X, const __nv_bfloat16* Y, const float* xn, const float* yn, int n1, int n2,
+                        int Dpad, float* part, cudaStream_t st);
+int launch_eval_rank(const __nv_bfloat16* X, const __nv_bfloat16* Y, const float* xn, const float* yn, const float* nv1,
+                     const float* nv2, const float* g_row, const float* g_col, int row_gid0, int col_gid0, int n1, int n2,
+                     int Dpad, int use_csls, int* cnt_row, int* cnt_col, float* top3_val, int* top3_idx, cudaStream_t st);
+int launch_icl_rowsum(const __nv_bfloat16* X, const __nv_bfloat16* Y, int B, int Bp, int Dpad, float inv_tau,
+                      float* rowsum_part, float* pos, cudaStream_t st);
+
+}  // namespace snag

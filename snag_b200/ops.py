@@ -1,0 +1,222 @@
+"""Thin torch-tensor wrappers over the C ABI: shape/dtype/contiguity validation in Python, pointers and
+the current CUDA stream passed down, return codes turned into exceptions. No compute happens here."""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import KT, SnagError, call, current_stream, ptr
+
+
+def _need(t: torch.Tensor, dtype, name: str, ndim: int | None = None) -> None:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor")
+    if not t.is_cuda:
+        raise SnagError(f"{name} must live on a CUDA device: snag_b200 has no CPU path")
+    if t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+    if ndim is not None and t.dim() != ndim:
+        raise ValueError(f"{name} must be {ndim}-D, got shape {tuple(t.shape)}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+
+
+def round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+def sim_plan(n_rows: int, n_cols: int, dpad: int) -> tuple[int, int]:
+    """(tiles_per_chunk, n_chunks) of an [n_rows x n_cols] sweep."""
+    return _lib.sim_plan(n_rows, n_cols, dpad)
+
+
+# ------------------------------------------------------------------------------------------------ prologue
+def prep_bf16(emb: torch.Tensor, idx: torch.Tensor | None = None, normalize: bool = True,
+              rows_pad_to: int = 1) -> tuple[torch.Tensor, torch.Tensor]:
+    """(gather ->) L2-normalise -> bf16, zero padded to a multiple of 64 columns; plus ||row||^2 (fp32) of the
+    rounded rows. Returns (operand [n_pad, Dpad] bf16, norm2 [n] fp32); rows n..n_pad are zero."""
+    _need(emb, torch.float32, "emb", 2)
+    n = emb.shape[0] if idx is None else idx.numel()
+    if idx is not None:
+        _need(idx, torch.int64, "idx", 1)
+    if n == 0:
+        raise ValueError("empty operand")
+    d = emb.shape[1]
+    dpad = round_up(d, 64)
+    n_pad = round_up(n, rows_pad_to)
+    if n_pad == n:
+        out = torch.empty((n_pad, dpad), dtype=torch.bfloat16, device=emb.device)
+    else:
+        out = torch.zeros((n_pad, dpad), dtype=torch.bfloat16, device=emb.device)
+    norm2 = torch.empty((n,), dtype=torch.float32, device=emb.device)
+    call("snag_prep_bf16", ptr(emb), emb.stride(0), ptr(idx), n, d, int(normalize), ptr(out), dpad, ptr(norm2),
+         current_stream())
+    return out, norm2
+
+
+def _check_operand(t: torch.Tensor, name: str) -> None:
+    _need(t, torch.bfloat16, name, 2)
+    if t.shape[1] % 64:
+        raise ValueError(f"{name}: width {t.shape[1]} is not a multiple of 64 (use prep_bf16)")
+    if t.data_ptr() % 128:
+        raise ValueError(f"{name}: base pointer must be 128-byte aligned")
+
+
+# ------------------------------------------------------------------------------------------------ eval sweeps
+def sim_write(X: torch.Tensor, Y: torch.Tensor, xn: torch.Tensor | None, yn: torch.Tensor | None, n1: int, n2: int,
+              mode: int) -> torch.Tensor:
+    _check_operand(X, "X")
+    _check_operand(Y, "Y")
+    if mode == 1:
+        _need(xn, torch.float32, "xn", 1)
+        _need(yn, torch.float32, "yn", 1)
+    out = torch.empty((n1, n2), dtype=torch.float32, device=X.device)
+    call("snag_sim_write", ptr(X), ptr(Y), ptr(xn), ptr(yn), n1, n2, X.shape[1], mode, ptr(out), out.stride(0),
+         current_stream())
+    return out
+
+
+def eval_rowtopk(X, Y, xn, yn, n1: int, n2: int) -> torch.Tensor:
+    """Per-chunk candidate lists [n_chunks, n1, KT] of c = 1 - d for every row of X against the rows of Y."""
+    _check_operand(X, "X")
+    _check_operand(Y, "Y")
+    _need(xn, torch.float32, "xn", 1)
+    _need(yn, torch.float32, "yn", 1)
+    _, nch = sim_plan(n1, n2, X.shape[1])
+    part = torch.empty((nch, n1, KT), dtype=torch.float32, device=X.device)
+    call("snag_eval_rowtopk", ptr(X), ptr(Y), ptr(xn), ptr(yn), n1, n2, X.shape[1], ptr(part), current_stream())
+    return part
+
+
+def topk_merge_mean(part: torch.Tensor, k: int, want_nv: bool = True, want_cand: bool = False):
+    _need(part, torch.float32, "part", 3)
+    if part.shape[2] != KT:
+        raise ValueError("candidate lists must have SNAG_KT entries")
+    if not 1 <= k <= KT:
+        raise SnagError(f"csls_k={k} unsupported: the fused CSLS path keeps {KT} candidates per row")
+    n_lists, n_rows = part.shape[0], part.shape[1]
+    nv = torch.empty((n_rows,), dtype=torch.float32, device=part.device) if want_nv else None
+    cand = torch.empty((n_rows, KT), dtype=torch.float32, device=part.device) if want_cand else None
+    call("snag_topk_merge_mean", ptr(part), n_lists, n_rows, k, ptr(nv), ptr(cand), current_stream())
+    return nv, cand
+
+
+def pair_score(X, Y, n: int, xn, yn, nv1, nv2, use_csls: bool, want_dot: bool = False):
+    _check_operand(X, "X")
+    _check_operand(Y, "Y")
+    g = torch.empty((n,), dtype=torch.float32, device=X.device)
+    s = torch.empty((n,), dtype=torch.float32, device=X.device) if want_dot else None
+    call("snag_pair_score", ptr(X), ptr(Y), X.shape[1], n, ptr(xn), ptr(yn), ptr(nv1), ptr(nv2), int(use_csls), ptr(g),
+         ptr(s), current_stream())
+    return (g, s) if want_dot else g
+
+
+def eval_rank(X, Y, xn, yn, nv1, nv2, g_row, g_col, row_gid0: int, col_gid0: int, n1: int, n2: int, use_csls: bool,
+              cnt_row: torch.Tensor, cnt_col: torch.Tensor, want_top3: bool = False):
+    _check_operand(X, "X")
+    _check_operand(Y, "Y")
+    _need(cnt_row, torch.int32, "cnt_row", 1)
+    _need(cnt_col, torch.int32, "cnt_col", 1)
+    t3v = t3i = None
+    if want_top3:
+        _, nch = sim_plan(n1, n2, X.shape[1])
+        t3v = torch.empty((nch, n1, 4), dtype=torch.float32, device=X.device)
+        t3i = torch.empty((nch, n1, 4), dtype=torch.int32, device=X.device)
+    call("snag_eval_rank", ptr(X), ptr(Y), ptr(xn), ptr(yn), ptr(nv1), ptr(nv2), ptr(g_row), ptr(g_col), row_gid0,
+         col_gid0, n1, n2, X.shape[1], int(use_csls), ptr(cnt_row), ptr(cnt_col), ptr(t3v), ptr(t3i), current_stream())
+    return t3v, t3i
+
+
+def top3_merge(val: torch.Tensor, idx: torch.Tensor):
+    _need(val, torch.float32, "val", 3)
+    _need(idx, torch.int32, "idx", 3)
+    n_lists, n_rows = val.shape[0], val.shape[1]
+    oval = torch.empty((n_rows, 4), dtype=torch.float32, device=val.device)
+    oidx = torch.empty((n_rows, 4), dtype=torch.int32, device=val.device)
+    call("snag_top3_merge", ptr(val), ptr(idx), n_lists, n_rows, ptr(oval), ptr(oidx), current_stream())
+    return oval, oidx
+
+
+# ------------------------------------------------------------------------------------------------ ICL
+def icl_side(X: torch.Tensor, Y: torch.Tensor, B: int, Bp: int, inv_tau: float):
+    """Row log-sum-exp and NLL of one side of the ICL loss. X [Bp, Dpad], Y [2*Bp, Dpad]."""
+    _check_operand(X, "X")
+    _check_operand(Y, "Y")
+    _, nch = sim_plan(Bp, 2 * Bp, X.shape[1])
+    part = torch.empty((nch, Bp), dtype=torch.float32, device=X.device)
+    pos = torch.empty((Bp,), dtype=torch.float32, device=X.device)
+    lse = torch.empty((B,), dtype=torch.float32, device=X.device)
+    nll = torch.empty((B,), dtype=torch.float32, device=X.device)
+    st = current_stream()
+    call("snag_icl_rowsum", ptr(X), ptr(Y), B, Bp, X.shape[1], inv_tau, ptr(part), ptr(pos), st)
+    call("snag_icl_finalize", ptr(part), nch, B, Bp, ptr(pos), inv_tau, ptr(lse), ptr(nll), st)
+    return lse, nll, pos
+
+
+# ------------------------------------------------------------------------------------------------ noise
+def noise_mask(x: torch.Tensor, mean: torch.Tensor, std: torch.Tensor, noise_ratio: float, mask_ratio: float, *,
+               out: torch.Tensor | None = None, mask: torch.Tensor | None = None, zsel: torch.Tensor | None = None,
+               seed: int = 0, row0: int = 0) -> torch.Tensor:
+    _need(x, torch.float32, "x", 2)
+    _need(mean, torch.float32, "mean", 1)
+    _need(std, torch.float32, "std", 1)
+    if out is None:
+        out = torch.empty_like(x)
+    _need(out, torch.float32, "out", 2)
+    selpos = None
+    if mask is not None:
+        _need(mask, torch.uint8, "mask", 1)
+    if zsel is not None:
+        if mask is None:
+            raise ValueError("zsel needs the row mask it was drawn for")
+        _need(zsel, torch.float32, "zsel", 2)
+        selpos = (torch.cumsum(mask.to(torch.int32), 0, dtype=torch.int32) - 1).contiguous()
+    keep = float(1.0 - mask_ratio)
+    call("snag_noise_mask", ptr(x), ptr(out), ptr(mean), ptr(std), ptr(mask), ptr(zsel), ptr(selpos), x.shape[0],
+         x.shape[1], x.stride(0), out.stride(0), float(noise_ratio), keep, float(mask_ratio), int(seed), int(row0),
+         current_stream())
+    return out
+
+
+def philox_rowmask(n: int, ratio: float, seed: int, device, row0: int = 0) -> torch.Tensor:
+    mask = torch.empty((n,), dtype=torch.uint8, device=device)
+    call("snag_philox_rowmask", ptr(mask), n, float(ratio), int(seed), int(row0), current_stream())
+    return mask
+
+
+def gauss_fill(mean: torch.Tensor, std: torch.Tensor, n: int, seed: int, row0: int = 0) -> torch.Tensor:
+    _need(mean, torch.float32, "mean", 1)
+    _need(std, torch.float32, "std", 1)
+    out = torch.empty((n, mean.numel()), dtype=torch.float32, device=mean.device)
+    call("snag_gauss_fill", ptr(out), ptr(mean), ptr(std), n, mean.numel(), out.stride(0), int(seed), int(row0),
+         current_stream())
+    return out
+
+
+def col_mean_std(x: torch.Tensor, valid: torch.Tensor | None = None) -> tuple[torch.Tensor, torch.Tensor]:
+    _need(x, torch.float32, "x", 2)
+    if valid is not None:
+        _need(valid, torch.uint8, "valid", 1)
+    f = x.shape[1]
+    mean = torch.empty((f,), dtype=torch.float32, device=x.device)
+    std = torch.empty((f,), dtype=torch.float32, device=x.device)
+    ws = torch.empty((2 * f + 1,), dtype=torch.float64, device=x.device)
+    call("snag_col_mean_std", ptr(x), ptr(valid), x.shape[0], f, x.stride(0), ptr(mean), ptr(std), ptr(ws),
+         current_stream())
+    return mean, std
+
+
+def rowblend_fwd(e: torch.Tensor, noise: torch.Tensor, mask: torch.Tensor, a: float, c: float) -> torch.Tensor:
+    _need(e, torch.float32, "e", 2)
+    _need(noise, torch.float32, "noise", 2)
+    _need(mask, torch.uint8, "mask", 1)
+    out = torch.empty_like(e)
+    call("snag_rowblend_fwd", ptr(e), ptr(noise), ptr(mask), ptr(out), e.shape[0], e.shape[1], a, c, current_stream())
+    return out
+
+
+def rowblend_bwd(g: torch.Tensor, mask: torch.Tensor, a: float) -> torch.Tensor:
+    _need(g, torch.float32, "g", 2)
+    gin = torch.empty_like(g)
+    call("snag_rowblend_bwd", ptr(g), ptr(mask), ptr(gin), g.shape[0], g.shape[1], a, current_stream())
+    return gin
