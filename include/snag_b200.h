@@ -42,8 +42,9 @@ const char* snag_error_string(int code);     /* static string for SNAG_ERR_* cod
 int snag_device_check(void);                 /* 0 if the current device is sm_100, SNAG_ERR_DEVICE otherwise */
 int snag_num_sms(void);
 
-/* Work decomposition of an [n_rows x n_cols] similarity sweep (needed to size the `part` workspaces). */
-int snag_sim_plan(int n_rows, int n_cols, int Dpad, int* tiles_per_chunk, int* n_chunks);
+/* Work decomposition of an [n_rows x n_cols] similarity sweep. n_lists = number of partial per-row output
+ * lists the sweep writes (column chunks x epilogue warpgroups): sizes the `part` / top3 / rowsum workspaces. */
+int snag_sim_plan(int n_rows, int n_cols, int Dpad, int* tiles_per_chunk, int* n_lists);
 
 /* ---- noise masking ------------------------------------------------------------------------ */
 /* SNAG.add_noise_to_embeddings (model/SNAG.py:66-75):
@@ -85,8 +86,11 @@ int snag_prep_bf16(const float* emb, int64_t ld, const int64_t* idx, int32_t n, 
  * mode 0: out[i,j] = x_i.y_j. out is fp32 [n1, ld]. */
 int snag_sim_write(const uint16_t* X, const uint16_t* Y, const float* xn, const float* yn, int32_t n1, int32_t n2,
                    int32_t Dpad, int32_t mode, float* out, int64_t ld, void* stream);
+/* Measurement aid: the same TMA + tcgen05 sweep with the accumulators dropped (no epilogue, no output).
+ * Times the mainloop alone so that bench.py can attribute a sweep's time to mainloop vs fused epilogue. */
+int snag_sim_mainloop_only(const uint16_t* X, const uint16_t* Y, int32_t n1, int32_t n2, int32_t Dpad, void* stream);
 /* CSLS sweep 1 (src/utils.py:431-432 without the matrix): for every row of X the SNAG_KT largest
- * c_ij = 1 - d_ij over the columns of each chunk. part: fp32 [n_chunks][n1][SNAG_KT] (n_chunks from
+ * c_ij = 1 - d_ij over the columns of each chunk. part: fp32 [n_lists][n1][SNAG_KT] (n_lists from
  * snag_sim_plan(n1, n2, Dpad)). Call with X and Y swapped for the column neighbourhoods. */
 int snag_eval_rowtopk(const uint16_t* X, const uint16_t* Y, const float* xn, const float* yn, int32_t n1, int32_t n2,
                       int32_t Dpad, float* part, void* stream);
@@ -103,7 +107,7 @@ int snag_pair_score(const uint16_t* X, const uint16_t* Y, int32_t Dpad, int64_t 
  *   cnt_col[j] += #{i != j : dist_ij < g_col[j] or (== and gid(i) < gid(j))}     r2l rank of pair gid(j)
  * gid(i) = row_gid0 + i, gid(j) = col_gid0 + j (column shards of a multi-GPU evaluation pass their offset).
  * Counters are accumulated atomically: zero them first. top3_val/top3_idx (both NULL or both fp32/int32
- * [n_chunks][n1][4]) receive each row's 3 nearest columns per chunk (merge with snag_top3_merge). */
+ * [n_lists][n1][4]) receive each row's 3 nearest columns per list (merge with snag_top3_merge). */
 int snag_eval_rank(const uint16_t* X, const uint16_t* Y, const float* xn, const float* yn, const float* nv1,
                    const float* nv2, const float* g_row, const float* g_col, int32_t row_gid0, int32_t col_gid0,
                    int32_t n1, int32_t n2, int32_t Dpad, int32_t use_csls, int32_t* cnt_row, int32_t* cnt_col,
@@ -114,11 +118,11 @@ int snag_top3_merge(const float* val, const int32_t* idx, int32_t n_lists, int64
 /* ---- ICL loss --------------------------------------------------------------------------------- */
 /* One side of icl_loss.forward (model/SNAG_loss.py:98-126). X = this side [Bp, Dpad], Y = [other side ; this
  * side] [2*Bp, Dpad], each part zero padded from B to Bp rows (Bp multiple of 256).
- *   rowsum_part[c][i] = sum over chunk c of exp(logit_ij - 1/tau), self-similarity excluded
+ *   rowsum_part[l][i] = partial sum l (of n_lists) of exp(logit_ij - 1/tau), self-similarity excluded
  *   pos[i] = x_i . other_i                       then snag_icl_finalize: lse, nll = lse - pos/tau */
 int snag_icl_rowsum(const uint16_t* X, const uint16_t* Y, int32_t B, int32_t Bp, int32_t Dpad, float inv_tau,
                     float* rowsum_part, float* pos, void* stream);
-int snag_icl_finalize(const float* rowsum_part, int32_t n_chunks, int32_t B, int32_t Bp, const float* pos,
+int snag_icl_finalize(const float* rowsum_part, int32_t n_lists, int32_t B, int32_t Bp, const float* pos,
                       float inv_tau, float* lse, float* nll, void* stream);
 
 #ifdef __cplusplus

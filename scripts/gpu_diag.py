@@ -214,7 +214,7 @@ def stage_perf():
     """First timing numbers for the sweeps (CUDA events, after warm-up)."""
     import torch
     from snag_b200 import evaluate, ops
-    for (n, d, k) in [(10500, 1200, 10), (10500, 1800, 10), (32768, 1200, 10), (100000, 1200, 10)]:
+    for (n, d, k) in [(10500, 1200, 10), (10500, 1800, 10), (32768, 300, 10), (32768, 1200, 10), (100000, 1200, 10)]:
         x, y = _clustered(n, d, 8.0, 5)
         X, xn = ops.prep_bf16(x, None, True)
         Y, yn = ops.prep_bf16(y, None, True)
@@ -232,6 +232,8 @@ def stage_perf():
             torch.cuda.synchronize()
             return e0.elapsed_time(e1) / reps
 
+        ms_null = t(lambda: ops.sim_mainloop_only(X, Y, n, n))
+        emit("perf_mainloop", n=n, d=d, dpad=dpad, ms=ms_null, tf=2.0 * n * n * dpad / ms_null / 1e9)
         ms_topk = t(lambda: ops.eval_rowtopk(X, Y, xn, yn, n, n))
         res = evaluate.align_ranks(X, Y, xn, yn, n, k)
         cr = torch.zeros(n, dtype=torch.int32, device="cuda")

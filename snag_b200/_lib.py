@@ -28,6 +28,7 @@ _SIGNATURES = {
     "snag_rowblend_bwd": [_vp, _vp, _vp, _i64, _i32, _f32, _vp],
     "snag_prep_bf16": [_vp, _i64, _vp, _i32, _i32, _i32, _vp, _i32, _vp, _vp],
     "snag_sim_write": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _i64, _vp],
+    "snag_sim_mainloop_only": [_vp, _vp, _i32, _i32, _i32, _vp],
     "snag_eval_rowtopk": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp],
     "snag_topk_merge_mean": [_vp, _i32, _i64, _i32, _vp, _vp, _vp],
     "snag_pair_score": [_vp, _vp, _i32, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp],

@@ -26,12 +26,12 @@ const char* snag_error_string(int code) {
 int snag_device_check(void) { return device_is_sm100() ? SNAG_OK : SNAG_ERR_DEVICE; }
 int snag_num_sms(void) { return num_sms(); }
 
-int snag_sim_plan(int n_rows, int n_cols, int Dpad, int* tiles_per_chunk, int* n_chunks) {
+int snag_sim_plan(int n_rows, int n_cols, int Dpad, int* tiles_per_chunk, int* n_lists) {
   SimPlan pl;
   const int rc = make_plan(n_rows, n_cols, Dpad, &pl);
   if (rc) return rc;
   if (tiles_per_chunk) *tiles_per_chunk = pl.tiles_per_chunk;
-  if (n_chunks) *n_chunks = pl.n_chunks;
+  if (n_lists) *n_lists = pl.n_lists;
   return SNAG_OK;
 }
 
@@ -66,6 +66,9 @@ int snag_prep_bf16(const float* emb, int64_t ld, const int64_t* idx, int32_t n, 
                           reinterpret_cast<__nv_bfloat16*>(out), Dpad, norm2, S(stream));
 }
 
+int snag_sim_mainloop_only(const uint16_t* X, const uint16_t* Y, int32_t n1, int32_t n2, int32_t Dpad, void* stream) {
+  return launch_sim_null(BF(X), BF(Y), n1, n2, Dpad, S(stream));
+}
 int snag_sim_write(const uint16_t* X, const uint16_t* Y, const float* xn, const float* yn, int32_t n1, int32_t n2,
                    int32_t Dpad, int32_t mode, float* out, int64_t ld, void* stream) {
   return launch_sim_write(BF(X), BF(Y), xn, yn, n1, n2, Dpad, mode, out, ld, S(stream));
@@ -98,10 +101,10 @@ int snag_icl_rowsum(const uint16_t* X, const uint16_t* Y, int32_t B, int32_t Bp,
                     float* rowsum_part, float* pos, void* stream) {
   return launch_icl_rowsum(BF(X), BF(Y), B, Bp, Dpad, inv_tau, rowsum_part, pos, S(stream));
 }
-int snag_icl_finalize(const float* rowsum_part, int32_t n_chunks, int32_t B, int32_t Bp, const float* pos,
+int snag_icl_finalize(const float* rowsum_part, int32_t n_lists, int32_t B, int32_t Bp, const float* pos,
                       float inv_tau, float* lse, float* nll, void* stream) {
-  if (!rowsum_part || !pos || !lse || !nll || B <= 0 || n_chunks <= 0) return SNAG_ERR_ARG;
-  return launch_icl_finalize(rowsum_part, n_chunks, B, Bp, pos, inv_tau, lse, nll, S(stream));
+  if (!rowsum_part || !pos || !lse || !nll || B <= 0 || n_lists <= 0) return SNAG_ERR_ARG;
+  return launch_icl_finalize(rowsum_part, n_lists, B, Bp, pos, inv_tau, lse, nll, S(stream));
 }
 
 }  // extern "C"

@@ -6,6 +6,7 @@
 namespace snag {
 
 static_assert(KT == KT_LIST, "candidate list length mismatch");
+static_assert(NUM_EPI_WG == LISTS_PER_CHUNK, "partial list count mismatch");
 
 // ------------------------------------------------------------------------------------------------
 // device info
@@ -62,6 +63,7 @@ int make_plan(int n_rows, int n_cols, int Dpad, SimPlan* pl) {
   const long long units = static_cast<long long>(pl->row_blocks) * pl->n_chunks;
   if (units > 0x7fffffffll) return SNAG_ERR_SHAPE;
   pl->n_units = static_cast<int>(units);
+  pl->n_lists = pl->n_chunks * LISTS_PER_CHUNK;
   return SNAG_OK;
 }
 
@@ -125,6 +127,11 @@ static int launch_sim(const __nv_bfloat16* X, const __nv_bfloat16* Y, int n1, in
   return static_cast<int>(cudaGetLastError());
 }
 
+int launch_sim_null(const __nv_bfloat16* X, const __nv_bfloat16* Y, int n1, int n2, int Dpad, cudaStream_t st) {
+  EpiNull::Params p{0};
+  return launch_sim<EpiNull>(X, Y, n1, n2, Dpad, p, st);
+}
+
 int launch_sim_write(const __nv_bfloat16* X, const __nv_bfloat16* Y, const float* xn, const float* yn, int n1, int n2,
                      int Dpad, int mode, float* out, long long ld, cudaStream_t st) {
   if (!out || ld < n2) return SNAG_ERR_ARG;
@@ -148,13 +155,18 @@ int launch_eval_rank(const __nv_bfloat16* X, const __nv_bfloat16* Y, const float
   if (use_csls && (!nv1 || !nv2)) return SNAG_ERR_ARG;
   if (!use_csls) { nv1 = xn; nv2 = yn; }   // never read for their values; keeps the staging loads valid
   if ((top3_val == nullptr) != (top3_idx == nullptr)) return SNAG_ERR_ARG;
-  if (top3_val) {
-    if ((reinterpret_cast<uintptr_t>(top3_val) | reinterpret_cast<uintptr_t>(top3_idx)) & 15) return SNAG_ERR_ALIGN;
-    EpiRank<true>::Params p{xn, yn, nv1, nv2, g_row, g_col, row_gid0, col_gid0, cnt_row, cnt_col, top3_val, top3_idx, use_csls};
-    return launch_sim<EpiRank<true>>(X, Y, n1, n2, Dpad, p, st);
+  if (top3_val && ((reinterpret_cast<uintptr_t>(top3_val) | reinterpret_cast<uintptr_t>(top3_idx)) & 15)) return SNAG_ERR_ALIGN;
+#define SNAG_RANK_CASE(T3, CS)                                                                                       \
+  {                                                                                                                  \
+    typename EpiRank<T3, CS>::Params p{xn, yn, nv1, nv2, g_row, g_col, row_gid0, col_gid0, cnt_row, cnt_col, top3_val, top3_idx}; \
+    return launch_sim<EpiRank<T3, CS>>(X, Y, n1, n2, Dpad, p, st);                                                   \
   }
-  EpiRank<false>::Params p{xn, yn, nv1, nv2, g_row, g_col, row_gid0, col_gid0, cnt_row, cnt_col, nullptr, nullptr, use_csls};
-  return launch_sim<EpiRank<false>>(X, Y, n1, n2, Dpad, p, st);
+  if (top3_val) {
+    if (use_csls) SNAG_RANK_CASE(true, true) else SNAG_RANK_CASE(true, false)
+  } else {
+    if (use_csls) SNAG_RANK_CASE(false, true) else SNAG_RANK_CASE(false, false)
+  }
+#undef SNAG_RANK_CASE
 }
 
 int launch_icl_rowsum(const __nv_bfloat16* X, const __nv_bfloat16* Y, int B, int Bp, int Dpad, float inv_tau,

@@ -4,7 +4,8 @@
 //   warp 0      TMA producer   : X tile [128 x 64] + Y tile [256 x 64] per k-block -> 4-stage smem ring
 //   warp 1      UMMA issuer    : tcgen05.mma 128x256x16, 4 per k-block, accumulator double-buffered in TMEM
 //   warp 2      TMEM allocator : 512 columns (2 accumulator stages x 256 fp32 columns)
-//   warps 4..7  epilogue       : tcgen05.ld 32 lanes x 32 columns at a time, thread t <-> row t of the tile
+//   warps 4..11 epilogue       : two warpgroups, each owning half of the tile's columns; tcgen05.ld 32 lanes x 32
+//                                columns at a time, thread <-> one row of the tile (TMEM lane = 32*(warp%4)+lane)
 //
 // Work decomposition: a *unit* is (row block of 128 sources) x (chunk of `tiles_per_chunk` column tiles);
 // per-row epilogue state (top-k list, rank counter, softmax row sum) lives in registers for the whole
@@ -26,9 +27,12 @@ constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int ACC_STAGES = 2;
 constexpr int TMEM_COLS = ACC_STAGES * BN;   // 512
 constexpr int NUM_CTRL_THREADS = 128;
-constexpr int NUM_EPI_THREADS = 128;
+constexpr int NUM_EPI_WG = 2;                 // epilogue warpgroups; WG w owns columns [w*128, w*128+128) of every tile
+constexpr int NUM_EPI_THREADS = 128 * NUM_EPI_WG;
 constexpr int NUM_THREADS = NUM_CTRL_THREADS + NUM_EPI_THREADS;
-constexpr int EPI_SCRATCH_BYTES = 8192;
+constexpr int STRIPS_PER_WG = BN / 32 / NUM_EPI_WG;
+constexpr int EPI_VEC_FLOATS = 2048;      // per-tile column vectors (double-buffered): 8 KB
+constexpr int EPI_SCRATCH_BYTES = EPI_VEC_FLOATS * 4 + NUM_EPI_THREADS * 16 * 4;   // + 16 KB half-strip staging
 constexpr int BAR_BYTES = 256;
 constexpr int SIM_SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + BAR_BYTES + EPI_SCRATCH_BYTES;
 constexpr int KT = 16;            // per-row candidate list length kept by the top-k epilogue (k <= KT)
@@ -45,7 +49,10 @@ struct SimShape {
 };
 
 struct EpiCtx {
-  int et;        // epilogue thread 0..127 == row within the tile == TMEM lane
+  int et;        // row within the tile == TMEM lane (0..127)
+  int wg;        // epilogue warpgroup (0..NUM_EPI_WG-1): which half of the tile's columns this thread consumes
+  int tid;       // epilogue thread id 0..NUM_EPI_THREADS-1
+  int list;      // index of this thread's partial output list: chunk * NUM_EPI_WG + wg
   int lane;      // lane in warp
   int row;       // row index inside the X view
   bool row_ok;   // row < n_rows
@@ -151,7 +158,9 @@ sim_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
   } else if (warp >= NUM_CTRL_THREADS / 32) {
     // ------------------------------------------------------------------ epilogue warpgroup
     EpiCtx cx;
-    cx.et = threadIdx.x - NUM_CTRL_THREADS;
+    cx.tid = threadIdx.x - NUM_CTRL_THREADS;
+    cx.et = cx.tid & 127;
+    cx.wg = cx.tid >> 7;
     cx.lane = lane;
     cx.scratch = scratch;
     const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
@@ -161,6 +170,7 @@ sim_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
       cx.rb = u % shp.row_blocks;
       cx.chunk = u / shp.row_blocks;
       cx.row = cx.rb * BM + cx.et;
+      cx.list = cx.chunk * NUM_EPI_WG + cx.wg;
       cx.row_ok = cx.row < shp.n_rows;
       const int ct0 = cx.chunk * shp.tiles_per_chunk;
       const int ct1 = min(ct0 + shp.tiles_per_chunk, shp.col_tiles);
@@ -173,17 +183,16 @@ sim_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
         mbar_wait(tfull_bar(as), aphase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + lane_base + as * BN;
-        uint32_t r0[32], r1[32];
-        // software pipeline: the load of strip c+1 is in flight while strip c is consumed
-        SNAG_TMEM_LD32(taddr, r0);
-#pragma unroll
-        for (int c = 0; c < BN / 32; c += 2) {
-          SNAG_TMEM_WAIT32(r0);
-          SNAG_TMEM_LD32(taddr + (c + 1) * 32, r1);
-          Epi::chunk(ep, shp, cx, st, ct, c, r0, buf);
-          SNAG_TMEM_WAIT32(r1);
-          if (c + 2 < BN / 32) SNAG_TMEM_LD32(taddr + (c + 2) * 32, r0);
-          Epi::chunk(ep, shp, cx, st, ct, c + 1, r1, buf);
+        // Rolled on purpose: one copy of the strip body keeps the epilogue inside the instruction cache
+        // (a fully unrolled tile body was ~150 KB of SASS and ran instruction-fetch bound).
+        if constexpr (!Epi::kNoLoad) {
+#pragma unroll 1
+          for (int c = cx.wg * STRIPS_PER_WG; c < (cx.wg + 1) * STRIPS_PER_WG; ++c) {
+            uint32_t r[32];
+            SNAG_TMEM_LD32(taddr + c * 32, r);
+            SNAG_TMEM_WAIT32(r);
+            Epi::chunk(ep, shp, cx, st, ct, c, r, buf);
+          }
         }
         tc_fence_before();
         mbar_arrive(tempty_bar(as));
@@ -221,9 +230,25 @@ __device__ __forceinline__ float csls_dist_from_c(float c, float nv1, float nv2)
 }
 
 // ------------------------------------------------------------------------------------------------
+// Epilogue: none (accumulators are dropped) — measures the TMA + UMMA mainloop alone (bench/diagnostics)
+// ------------------------------------------------------------------------------------------------
+struct EpiNull {
+  static constexpr bool kNoLoad = true;
+  struct Params { int unused; };
+  struct State {};
+  static __device__ __forceinline__ void unit_begin(const Params&, const SimShape&, const EpiCtx&, State&) {}
+  static __device__ __forceinline__ void tile_begin(const Params&, const SimShape&, const EpiCtx&, State&, int, int) {}
+  static __device__ __forceinline__ void chunk(const Params&, const SimShape&, const EpiCtx&, State&, int, int,
+                                               const uint32_t (&)[32], int) {}
+  static __device__ __forceinline__ void tile_end(const Params&, const SimShape&, const EpiCtx&, State&, int, int) {}
+  static __device__ __forceinline__ void unit_end(const Params&, const SimShape&, const EpiCtx&, State&) {}
+};
+
+// ------------------------------------------------------------------------------------------------
 // Epilogue: write S (mode 0) or the squared-L2 distance (mode 1) — drop-in pairwise_distances
 // ------------------------------------------------------------------------------------------------
 struct EpiWrite {
+  static constexpr bool kNoLoad = false;
   struct Params {
     float* out;        // [n_rows, ld]
     long long ld;
@@ -240,7 +265,7 @@ struct EpiWrite {
   static __device__ __forceinline__ void tile_begin(const Params& p, const SimShape& shp, const EpiCtx& cx, State&,
                                                     int ct, int buf) {
     float* yn_s = cx.scratch + buf * BN;
-    for (int j = cx.et; j < BN; j += NUM_EPI_THREADS) {
+    for (int j = cx.tid; j < BN; j += NUM_EPI_THREADS) {
       const int col = ct * BN + j;
       yn_s[j] = (p.mode == 1 && col < shp.n_cols) ? p.yn[col] : 0.f;
     }
@@ -277,10 +302,11 @@ struct EpiWrite {
 // Output: part[chunk][row][KT], ascending, -inf padded. A merge kernel reduces over chunks.
 // ------------------------------------------------------------------------------------------------
 struct EpiRowTopK {
+  static constexpr bool kNoLoad = false;
   struct Params {
     const float* xn;   // [n_rows]
     const float* yn;   // [n_cols]
-    float* part;       // [n_chunks][n_rows][KT]
+    float* part;       // [n_lists][n_rows][KT]
   };
   struct State {
     float xn;
@@ -294,7 +320,7 @@ struct EpiRowTopK {
   static __device__ __forceinline__ void tile_begin(const Params& p, const SimShape& shp, const EpiCtx& cx, State&,
                                                     int ct, int buf) {
     float* yn_s = cx.scratch + buf * BN;
-    for (int j = cx.et; j < BN; j += NUM_EPI_THREADS) {
+    for (int j = cx.tid; j < BN; j += NUM_EPI_THREADS) {
       const int col = ct * BN + j;
       // out-of-range columns get yn = +inf  ->  d = +inf, c = -inf: never admitted
       yn_s[j] = (col < shp.n_cols) ? p.yn[col] : INFINITY;
@@ -303,18 +329,35 @@ struct EpiRowTopK {
   static __device__ __forceinline__ void chunk(const Params&, const SimShape&, const EpiCtx& cx, State& st, int,
                                                int c, const uint32_t (&r)[32], int buf) {
     const float* yn_s = cx.scratch + buf * BN + c * 32;
+    float v[32];
+    float mx = -INFINITY;
 #pragma unroll
     for (int q = 0; q < 32; ++q) {
-      const float d = sqdist_from_dot(__uint_as_float(r[q]), st.xn, yn_s[q]);
-      const float cval = __fsub_rn(1.0f, d);
-      if (cval > st.top[0]) {
-        st.top[0] = cval;
+      v[q] = __fsub_rn(1.0f, sqdist_from_dot(__uint_as_float(r[q]), st.xn, yn_s[q]));
+      mx = fmaxf(mx, v[q]);
+    }
+    // common case after the list has warmed up: nothing in this strip beats the current KT-th largest
+    if (mx > st.top[0]) {
+      // rare path, kept small on purpose (instruction cache): park the strip in shared memory
+      // ([q][thread] layout, conflict-free) and walk it with a rolled loop around ONE copy of the insertion
+      float* stage = cx.scratch + EPI_VEC_FLOATS + cx.tid;
 #pragma unroll
-        for (int t = 0; t < KT - 1; ++t) {
-          const float lo = fminf(st.top[t], st.top[t + 1]);
-          const float hi = fmaxf(st.top[t], st.top[t + 1]);
-          st.top[t] = lo;
-          st.top[t + 1] = hi;
+      for (int h = 0; h < 2; ++h) {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) stage[q * NUM_EPI_THREADS] = v[h * 16 + q];
+#pragma unroll 1
+        for (int q = 0; q < 16; ++q) {
+          const float x = stage[q * NUM_EPI_THREADS];
+          if (x > st.top[0]) {
+            st.top[0] = x;
+#pragma unroll
+            for (int t = 0; t < KT - 1; ++t) {
+              const float lo = fminf(st.top[t], st.top[t + 1]);
+              const float hi = fmaxf(st.top[t], st.top[t + 1]);
+              st.top[t] = lo;
+              st.top[t + 1] = hi;
+            }
+          }
         }
       }
     }
@@ -322,7 +365,7 @@ struct EpiRowTopK {
   static __device__ __forceinline__ void tile_end(const Params&, const SimShape&, const EpiCtx&, State&, int, int) {}
   static __device__ __forceinline__ void unit_end(const Params& p, const SimShape& shp, const EpiCtx& cx, State& st) {
     if (!cx.row_ok) return;
-    float4* o = reinterpret_cast<float4*>(p.part + (static_cast<long long>(cx.chunk) * shp.n_rows + cx.row) * KT);
+    float4* o = reinterpret_cast<float4*>(p.part + (static_cast<long long>(cx.list) * shp.n_rows + cx.row) * KT);
 #pragma unroll
     for (int t = 0; t < KT; t += 4) o[t / 4] = make_float4(st.top[t], st.top[t + 1], st.top[t + 2], st.top[t + 3]);
   }
@@ -335,8 +378,9 @@ struct EpiRowTopK {
 // i.e. the position of the ground truth in a stable ascending sort (main.py:400-411, 422-429).
 // Optionally tracks the 3 nearest columns per row (the ret1..ret3 of the prediction CSV, main.py:411).
 // ------------------------------------------------------------------------------------------------
-template <bool kTop3>
+template <bool kTop3, bool kCsls>
 struct EpiRank {
+  static constexpr bool kNoLoad = false;
   struct Params {
     const float* xn;     // [n_rows]
     const float* yn;     // [n_cols]
@@ -348,15 +392,13 @@ struct EpiRank {
     int col_gid0;        // global pair id of view column 0
     int* cnt_row;        // [n_rows]  (atomically accumulated, caller zeroes)
     int* cnt_col;        // [n_cols]
-    float* top3_val;     // [n_chunks][n_rows][4] (kTop3) ascending distance
-    int* top3_idx;       // [n_chunks][n_rows][4] (kTop3) column gid
-    int use_csls;        // 0: rank on the plain squared distance d (args.csls False, main.py:392)
-  };
+    float* top3_val;     // [n_lists][n_rows][4] (kTop3) ascending distance
+    int* top3_idx;       // [n_lists][n_rows][4] (kTop3) column gid
+  };                     // kCsls == false: rank on the plain squared distance d (args.csls False, main.py:392)
   struct State {
     float xn, nv1, g;
     int gid;
     int cnt;
-    int colcnt[BN / 32];
     float t3v[3];
     int t3i[3];
   };
@@ -372,80 +414,97 @@ struct EpiRank {
       for (int t = 0; t < 3; ++t) { st.t3v[t] = INFINITY; st.t3i[t] = 0x7fffffff; }
     }
   }
-  static __device__ __forceinline__ void tile_begin(const Params& p, const SimShape& shp, const EpiCtx& cx, State& st,
+  static __device__ __forceinline__ void tile_begin(const Params& p, const SimShape& shp, const EpiCtx& cx, State&,
                                                     int ct, int buf) {
     float* s = cx.scratch + buf * (3 * BN);
-    for (int j = cx.et; j < BN; j += NUM_EPI_THREADS) {
+    for (int j = cx.tid; j < BN; j += NUM_EPI_THREADS) {
       const int col = ct * BN + j;
       const bool ok = col < shp.n_cols;
       s[j] = ok ? p.yn[col] : INFINITY;        // d = inf -> dist = +inf: never smaller than anything
       s[BN + j] = ok ? p.nv2[col] : 0.f;
       s[2 * BN + j] = ok ? p.g_col[col] : -INFINITY;
     }
-#pragma unroll
-    for (int q = 0; q < BN / 32; ++q) st.colcnt[q] = 0;
   }
-  static __device__ __forceinline__ void chunk(const Params& p, const SimShape&, const EpiCtx& cx, State& st, int ct,
+  static __device__ __forceinline__ void chunk(const Params& p, const SimShape& shp, const EpiCtx& cx, State& st, int ct,
                                                int c, const uint32_t (&r)[32], int buf) {
     const float* s = cx.scratch + buf * (3 * BN) + c * 32;
-    const int cgid0 = p.col_gid0 + ct * BN + c * 32;
-    // relation of this 32-column strip to the rows of the tile (global pair ids), warp-uniform
-    const int rgid_lo = p.row_gid0 + cx.rb * BM, rgid_hi = rgid_lo + BM - 1;
-    const bool all_cols_below = (cgid0 + 31) < rgid_lo;   // every gid(j) < every gid(i)
-    const bool all_cols_above = cgid0 > rgid_hi;          // every gid(j) > every gid(i)
-    int cc = 0;
+    const int col0 = ct * BN + c * 32;
+    const int cgid0 = p.col_gid0 + col0;
+    // does this 32-column strip contain the ground-truth column of one of this warp's 32 rows? (warp-uniform)
+    const int wgid0 = p.row_gid0 + cx.rb * BM + (cx.et & ~31);
+    const bool diag_strip = (cgid0 <= wgid0 + 31) && (cgid0 + 31 >= wgid0);
+    float dist[32];
+    uint32_t rmask = 0, cmask = 0;
+    bool tie = diag_strip;
+    // fast path: strict comparisons only; any exact equality (or the diagonal) defers to the exact path below
 #pragma unroll
     for (int q = 0; q < 32; ++q) {
       const float d = sqdist_from_dot(__uint_as_float(r[q]), st.xn, s[q]);
-      const float dist = p.use_csls ? csls_dist_from_c(__fsub_rn(1.0f, d), st.nv1, s[BN + q]) : d;
+      dist[q] = kCsls ? csls_dist_from_c(__fsub_rn(1.0f, d), st.nv1, s[BN + q]) : d;
       const float gj = s[2 * BN + q];
-      bool prow, pcol;
-      if (all_cols_below) {
-        prow = dist <= st.g;
-        pcol = dist < gj;
-      } else if (all_cols_above) {
-        prow = dist < st.g;
-        pcol = dist <= gj;
-      } else {
-        const int jg = cgid0 + q;
-        prow = (dist < st.g) || (dist == st.g && jg < st.gid);
-        pcol = (dist < gj) || (dist == gj && st.gid < jg);
-        if (jg == st.gid) { prow = false; pcol = false; }
-      }
-      pcol = pcol && cx.row_ok;
-      st.cnt += prow ? 1 : 0;
-      const int votes = __popc(__ballot_sync(0xffffffffu, pcol));
-      if (cx.lane == q) cc = votes;
-      if (kTop3) {
-        const int jg = cgid0 + q;
-        if (dist < st.t3v[2] || (dist == st.t3v[2] && jg < st.t3i[2])) {
-          st.t3v[2] = dist; st.t3i[2] = jg;
+      if (dist[q] < st.g) rmask |= (1u << q);
+      if (dist[q] < gj) cmask |= (1u << q);
+      tie |= (dist[q] == st.g);
+      tie |= (dist[q] == gj);
+    }
+    if (tie) {
+      // exact path: stable-sort tie-break on the pair id, ground-truth column excluded
+      rmask = 0;
+      cmask = 0;
 #pragma unroll
-          for (int t = 2; t > 0; --t) {
-            const bool sw = (st.t3v[t] < st.t3v[t - 1]) || (st.t3v[t] == st.t3v[t - 1] && st.t3i[t] < st.t3i[t - 1]);
-            if (sw) {
-              const float tv = st.t3v[t]; st.t3v[t] = st.t3v[t - 1]; st.t3v[t - 1] = tv;
-              const int ti = st.t3i[t]; st.t3i[t] = st.t3i[t - 1]; st.t3i[t - 1] = ti;
+      for (int q = 0; q < 32; ++q) {
+        const int jg = cgid0 + q;
+        const float gj = s[2 * BN + q];
+        bool prow = (dist[q] < st.g) || (dist[q] == st.g && jg < st.gid);
+        bool pcol = (dist[q] < gj) || (dist[q] == gj && st.gid < jg);
+        if (jg == st.gid) { prow = false; pcol = false; }
+        if (prow) rmask |= (1u << q);
+        if (pcol) cmask |= (1u << q);
+      }
+    }
+    const int cnt = __popc(rmask);
+    st.cnt += cnt;
+    if (!cx.row_ok) cmask = 0;
+    // column counts: transpose the warp's 32x32 predicate bit-matrix, then popc -> lane l owns column l
+    uint32_t x = cmask;
+#pragma unroll
+    for (int sft = 16; sft >= 1; sft >>= 1) {
+      const uint32_t m = sft == 16 ? 0x0000FFFFu : sft == 8 ? 0x00FF00FFu : sft == 4 ? 0x0F0F0F0Fu
+                                                 : sft == 2 ? 0x33333333u : 0x55555555u;
+      const uint32_t y = __shfl_xor_sync(0xffffffffu, x, sft);
+      x = (cx.lane & sft) ? ((x & ~m) | ((y >> sft) & m)) : ((x & m) | ((y << sft) & ~m));
+    }
+    const int votes = __popc(x);
+    if (votes != 0 && col0 + cx.lane < shp.n_cols) atomicAdd(p.cnt_col + col0 + cx.lane, votes);
+    if (kTop3) {
+      float mn = INFINITY;
+#pragma unroll
+      for (int q = 0; q < 32; ++q) mn = fminf(mn, dist[q]);
+      if (mn <= st.t3v[2]) {
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+          const int jg = cgid0 + q;
+          if (dist[q] < st.t3v[2] || (dist[q] == st.t3v[2] && jg < st.t3i[2])) {
+            st.t3v[2] = dist[q]; st.t3i[2] = jg;
+#pragma unroll
+            for (int t = 2; t > 0; --t) {
+              const bool sw = (st.t3v[t] < st.t3v[t - 1]) || (st.t3v[t] == st.t3v[t - 1] && st.t3i[t] < st.t3i[t - 1]);
+              if (sw) {
+                const float tv = st.t3v[t]; st.t3v[t] = st.t3v[t - 1]; st.t3v[t - 1] = tv;
+                const int ti = st.t3i[t]; st.t3i[t] = st.t3i[t - 1]; st.t3i[t - 1] = ti;
+              }
             }
           }
         }
       }
     }
-    st.colcnt[c] += cc;   // lane q holds the votes of column c*32+q (c is a compile-time constant after unrolling)
   }
-  static __device__ __forceinline__ void tile_end(const Params& p, const SimShape& shp, const EpiCtx& cx, State& st,
-                                                  int ct, int) {
-#pragma unroll
-    for (int c = 0; c < BN / 32; ++c) {
-      const int col = ct * BN + c * 32 + cx.lane;
-      if (st.colcnt[c] != 0 && col < shp.n_cols) atomicAdd(p.cnt_col + col, st.colcnt[c]);
-    }
-  }
+  static __device__ __forceinline__ void tile_end(const Params&, const SimShape&, const EpiCtx&, State&, int, int) {}
   static __device__ __forceinline__ void unit_end(const Params& p, const SimShape& shp, const EpiCtx& cx, State& st) {
     if (!cx.row_ok) return;
     if (st.cnt != 0) atomicAdd(p.cnt_row + cx.row, st.cnt);
     if (kTop3) {
-      const long long o = (static_cast<long long>(cx.chunk) * shp.n_rows + cx.row) * 4;
+      const long long o = (static_cast<long long>(cx.list) * shp.n_rows + cx.row) * 4;
       *reinterpret_cast<float4*>(p.top3_val + o) = make_float4(st.t3v[0], st.t3v[1], st.t3v[2], 0.f);
       *reinterpret_cast<int4*>(p.top3_idx + o) = make_int4(st.t3i[0], st.t3i[1], st.t3i[2], 0);
     }
@@ -462,11 +521,12 @@ struct EpiRank {
 //   pos[row]                = s_{row,row} of part 0
 // ------------------------------------------------------------------------------------------------
 struct EpiIclFwd {
+  static constexpr bool kNoLoad = false;
   struct Params {
     float scale_log2;   // log2(e) / tau
     int B;              // valid rows per part
     int Bp;             // padded rows per part (multiple of 256)
-    float* rowsum_part; // [n_chunks][Bp]
+    float* rowsum_part; // [n_lists][Bp]
     float* pos;         // [Bp]
   };
   struct State {
@@ -506,7 +566,7 @@ struct EpiIclFwd {
   }
   static __device__ __forceinline__ void tile_end(const Params&, const SimShape&, const EpiCtx&, State&, int, int) {}
   static __device__ __forceinline__ void unit_end(const Params& p, const SimShape&, const EpiCtx& cx, State& st) {
-    if (cx.row < p.Bp) p.rowsum_part[static_cast<long long>(cx.chunk) * p.Bp + cx.row] = st.sum;
+    if (cx.row < p.Bp) p.rowsum_part[static_cast<long long>(cx.list) * p.Bp + cx.row] = st.sum;
   }
 };
 

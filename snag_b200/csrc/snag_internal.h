@@ -7,12 +7,14 @@
 namespace snag {
 
 constexpr int KT_LIST = 16;   // candidate-list length of the CSLS top-k path (must equal KT in simgemm.cuh)
+constexpr int LISTS_PER_CHUNK = 2;   // partial per-row outputs per column chunk (= epilogue warpgroups)
 
 int num_sms();                // SM count of the current device (cached per device)
 int device_is_sm100();        // 1 if the current device is compute capability 10.x
 
 struct SimPlan {
   int kblocks, row_blocks, col_tiles, tiles_per_chunk, n_chunks, n_units;
+  int n_lists;   // partial per-row output lists a sweep produces: n_chunks * LISTS_PER_CHUNK
 };
 // Deterministic work decomposition for an [n_rows x n_cols] similarity sweep with padded width Dpad.
 int make_plan(int n_rows, int n_cols, int Dpad, SimPlan* plan);
@@ -40,6 +42,7 @@ int launch_icl_finalize(const float* rowsum_part, int n_chunks, int B, int Bp, c
                         float* nll, cudaStream_t st);
 
 // ---- tcgen05 similarity sweeps (sim_kernels.cu)
+int launch_sim_null(const __nv_bfloat16* X, const __nv_bfloat16* Y, int n1, int n2, int Dpad, cudaStream_t st);
 int launch_sim_write(const __nv_bfloat16* X, const __nv_bfloat16* Y, const float* xn, const float* yn, int n1, int n2,
                      int Dpad, int mode, float* out, long long ld, cudaStream_t st);
 int launch_eval_rowtopk(const __nv_bfloat16* X, const __nv_bfloat16* Y, const float* xn, const float* yn, int n1, int n2,

@@ -26,7 +26,7 @@ def round_up(x: int, m: int) -> int:
 
 
 def sim_plan(n_rows: int, n_cols: int, dpad: int) -> tuple[int, int]:
-    """(tiles_per_chunk, n_chunks) of an [n_rows x n_cols] sweep."""
+    """(tiles_per_chunk, n_lists) of an [n_rows x n_cols] sweep; n_lists partial lists per row are written."""
     return _lib.sim_plan(n_rows, n_cols, dpad)
 
 
@@ -74,6 +74,13 @@ def sim_write(X: torch.Tensor, Y: torch.Tensor, xn: torch.Tensor | None, yn: tor
     call("snag_sim_write", ptr(X), ptr(Y), ptr(xn), ptr(yn), n1, n2, X.shape[1], mode, ptr(out), out.stride(0),
          current_stream())
     return out
+
+
+def sim_mainloop_only(X: torch.Tensor, Y: torch.Tensor, n1: int, n2: int) -> None:
+    """Measurement aid: the sweep without any epilogue (see snag_sim_mainloop_only)."""
+    _check_operand(X, "X")
+    _check_operand(Y, "Y")
+    call("snag_sim_mainloop_only", ptr(X), ptr(Y), n1, n2, X.shape[1], current_stream())
 
 
 def eval_rowtopk(X, Y, xn, yn, n1: int, n2: int) -> torch.Tensor:
