@@ -32,7 +32,8 @@ constexpr int NUM_EPI_THREADS = 128 * NUM_EPI_WG;
 constexpr int NUM_THREADS = NUM_CTRL_THREADS + NUM_EPI_THREADS;
 constexpr int STRIPS_PER_WG = BN / 32 / NUM_EPI_WG;
 constexpr int EPI_VEC_FLOATS = 2048;      // per-tile column vectors (double-buffered): 8 KB
-constexpr int EPI_SCRATCH_BYTES = EPI_VEC_FLOATS * 4 + NUM_EPI_THREADS * 16 * 4;   // + 16 KB half-strip staging
+constexpr int EPI_STAGE_FLOATS = NUM_EPI_THREADS * 16;   // half a fp32 strip per epilogue thread: 16 KB
+constexpr int EPI_SCRATCH_BYTES = (EPI_VEC_FLOATS + EPI_STAGE_FLOATS) * 4;
 constexpr int BAR_BYTES = 256;
 constexpr int SIM_SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + BAR_BYTES + EPI_SCRATCH_BYTES;
 constexpr int KT = 16;            // per-row candidate list length kept by the top-k epilogue (k <= KT)
@@ -317,37 +318,49 @@ struct EpiRowTopK {
 #pragma unroll
     for (int t = 0; t < KT; ++t) st.top[t] = -INFINITY;
   }
+  // scratch layout per buffer: yn[BN] then the minimum of yn over each 32-column strip [BN/32]
+  static constexpr int kVecStride = BN + BN / 32;
   static __device__ __forceinline__ void tile_begin(const Params& p, const SimShape& shp, const EpiCtx& cx, State&,
                                                     int ct, int buf) {
-    float* yn_s = cx.scratch + buf * BN;
-    for (int j = cx.tid; j < BN; j += NUM_EPI_THREADS) {
-      const int col = ct * BN + j;
-      // out-of-range columns get yn = +inf  ->  d = +inf, c = -inf: never admitted
-      yn_s[j] = (col < shp.n_cols) ? p.yn[col] : INFINITY;
-    }
+    static_assert(NUM_EPI_THREADS == BN, "one epilogue thread stages one column");
+    static_assert(2 * kVecStride <= EPI_VEC_FLOATS, "scratch too small");
+    float* yn_s = cx.scratch + buf * kVecStride;
+    const int col = ct * BN + cx.tid;
+    // out-of-range columns get yn = +inf  ->  d = +inf, c = -inf: never admitted
+    const float v = (col < shp.n_cols) ? p.yn[col] : INFINITY;
+    yn_s[cx.tid] = v;
+    float m = v;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (cx.lane == 0) yn_s[BN + (cx.tid >> 5)] = m;
   }
   static __device__ __forceinline__ void chunk(const Params&, const SimShape&, const EpiCtx& cx, State& st, int,
                                                int c, const uint32_t (&r)[32], int buf) {
-    const float* yn_s = cx.scratch + buf * BN + c * 32;
-    float v[32];
-    float mx = -INFINITY;
+    const float* yn_s = cx.scratch + buf * kVecStride + c * 32;
+    // Conservative pre-filter in s-space. c_ij = fl(1 - max(fl(fl(xn_i + yn_j) - 2 s), 0)) can exceed the current
+    // KT-th largest top0 only if s > ((xn_i + min_j yn_j) - 1 + top0)/2; every quantity is below 4 in magnitude, so
+    // the roundings involved total < 2e-6 and a margin of 4e-6 makes the skip safe (false positives are re-checked
+    // exactly below). Fast path: one compare + one predicated bit-set per element.
+    const float tmin = __fadd_rn(st.xn, cx.scratch[buf * kVecStride + BN + c]);
+    const float thr = __fmaf_rn(0.5f, __fadd_rn(__fadd_rn(tmin, -1.0f), st.top[0]), -4e-6f);
+    uint32_t pm = 0;
 #pragma unroll
-    for (int q = 0; q < 32; ++q) {
-      v[q] = __fsub_rn(1.0f, sqdist_from_dot(__uint_as_float(r[q]), st.xn, yn_s[q]));
-      mx = fmaxf(mx, v[q]);
-    }
-    // common case after the list has warmed up: nothing in this strip beats the current KT-th largest
-    if (mx > st.top[0]) {
-      // rare path, kept small on purpose (instruction cache): park the strip in shared memory
-      // ([q][thread] layout, conflict-free) and walk it with a rolled loop around ONE copy of the insertion
+    for (int q = 0; q < 32; ++q)
+      if (__uint_as_float(r[q]) > thr) pm |= (1u << q);
+    if (pm != 0) {
+      // rare path, kept small on purpose (instruction cache): park the strip's accumulators in shared memory
+      // ([q][thread] layout, conflict-free) and visit only the flagged elements
       float* stage = cx.scratch + EPI_VEC_FLOATS + cx.tid;
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
+      for (int h = 0; h < 2; ++h) {      // two half-strips: the staging area holds 16 values per thread
+        uint32_t ph = (pm >> (16 * h)) & 0xffffu;
+        if (ph == 0) continue;
 #pragma unroll
-        for (int q = 0; q < 16; ++q) stage[q * NUM_EPI_THREADS] = v[h * 16 + q];
-#pragma unroll 1
-        for (int q = 0; q < 16; ++q) {
-          const float x = stage[q * NUM_EPI_THREADS];
+        for (int q = 0; q < 16; ++q) stage[q * NUM_EPI_THREADS] = __uint_as_float(r[16 * h + q]);
+        while (ph != 0) {
+          const int q = __ffs(ph) - 1;
+          ph &= ph - 1;
+          const float x = __fsub_rn(1.0f, sqdist_from_dot(stage[q * NUM_EPI_THREADS], st.xn, yn_s[16 * h + q]));
           if (x > st.top[0]) {
             st.top[0] = x;
 #pragma unroll
