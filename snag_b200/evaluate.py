@@ -7,9 +7,10 @@ Host-side mirror of the reference's evaluation interface
 on top of the fused tcgen05 sweeps of libsnag_b200.so. The n x n matrix is never materialised on the
 fused path (`align_ranks`); the two drop-ins that must return a matrix do materialise it.
 
-Sharded evaluation (targets split across ranks, one process per GPU) lives in `align_ranks` too: pass a
-torch.distributed process group. Per-row candidates / counters are exchanged with NCCL all-gather /
-all-reduce; integer counters make the result identical for any number of ranks.
+Sharded evaluation: targets are split into contiguous shards, one per rank (one process per GPU); every
+rank holds both embedding tables and sweeps all sources against its own targets. Per sweep there is one
+exchange step (NCCL all-gather of per-row CSLS candidates / neighbourhood means / column counters, all-reduce
+of the integer row counters). Integer counters make the result identical for any number of ranks.
 """
 from __future__ import annotations
 
@@ -18,7 +19,7 @@ from dataclasses import dataclass, field
 import numpy as np
 import torch
 
-from . import ops
+from . import ops as _cuda_ops
 from ._lib import KT, SnagError
 
 TOP_K = (1, 10, 50)   # main.py:380
@@ -36,38 +37,31 @@ class AlignRanks:
     g: torch.Tensor                   # fp32 [n]   distance of the ground-truth pair
     top3_idx: torch.Tensor | None = None   # int32 [n,3] pair ids of the 3 nearest targets per source
     top3_val: torch.Tensor | None = None
-    launches: int = 0                 # kernels of libsnag_b200.so launched
+    launches: int = 0                 # kernels of libsnag_b200.so launched by this rank
     info: dict = field(default_factory=dict)
 
 
+def round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
 def shard_bounds(n: int, world: int, rank: int, align: int = 256) -> tuple[int, int]:
-    """Contiguous target shard [c0, c1) of rank `rank`; shard size is a multiple of `align` except the last."""
-    per = ops.round_up((n + world - 1) // world, align)
+    """Contiguous target shard [c0, c1) of `rank`; every shard but the last has `per` = ceil(n/world) rounded
+    up to `align` targets (column tiles are 256 wide), trailing ranks may own nothing."""
+    per = round_up((n + world - 1) // world, align)
     c0 = min(rank * per, n)
     c1 = min(c0 + per, n)
     return c0, c1
 
 
-def align_ranks(X: torch.Tensor, Y: torch.Tensor, xn: torch.Tensor, yn: torch.Tensor, n: int, csls_k: int = 10,
-                use_csls: bool = True, want_top3: bool = False, group=None) -> AlignRanks:
-    """Fused evaluation of n aligned pairs (x_i <-> y_i).
-
-    X, Y : bf16 operands [>=n, Dpad] from ops.prep_bf16; xn, yn : their squared norms [n].
-    With `group` (torch.distributed), every rank holds all of X and Y and sweeps only its target shard.
-    """
-    if use_csls and not 1 <= csls_k <= KT:
-        raise SnagError(f"csls_k={csls_k} unsupported: the fused CSLS path keeps {KT} candidates per row")
-    if use_csls and csls_k > n:
-        # torch.topk raises in the reference (src/utils.py:431) when k exceeds the matrix side
-        raise ValueError(f"csls_k={csls_k} exceeds the number of evaluated pairs n={n}")
+def _align_ranks_steps(be, X, Y, xn, yn, n: int, csls_k: int, use_csls: bool, want_top3: bool, world: int, rank: int):
+    """Generator form of the sharded evaluation. Yields ("all_gather", t) / ("all_reduce", t) whenever the ranks
+    must exchange data and receives the collective's result (all_gather: tensor with a new leading dim of size
+    world; all_reduce: the elementwise sum). Returning through StopIteration.value keeps the data path identical
+    for torch.distributed (NCCL / gloo) and for the in-process lockstep simulator used by the tests.
+    `be` is the kernel backend (snag_b200.ops)."""
     dev = X.device
     launches = 0
-    if group is not None:
-        import torch.distributed as dist
-        world, rank = dist.get_world_size(group), dist.get_rank(group)
-    else:
-        dist = None
-        world, rank = 1, 0
     c0, c1 = shard_bounds(n, world, rank)
     ns = c1 - c0                                   # targets owned by this rank
     per = shard_bounds(n, world, 0)[1]             # padded shard size used for the gathers
@@ -76,37 +70,35 @@ def align_ranks(X: torch.Tensor, Y: torch.Tensor, xn: torch.Tensor, yn: torch.Te
 
     nv1 = nv2 = None
     if use_csls:
-        # sweep 1: row neighbourhoods (every source against this rank's targets)
+        # sweep 1: row neighbourhoods — every source against this rank's targets
         if ns > 0:
-            part = ops.eval_rowtopk(X, Ys, xn, yns, n, ns)
+            part = be.eval_rowtopk(X, Ys, xn, yns, n, ns)
             launches += 1
         else:
             part = torch.full((1, n, KT), float("-inf"), dtype=torch.float32, device=dev)
         if world == 1:
-            nv1, _ = ops.topk_merge_mean(part, csls_k)
+            nv1, _ = be.topk_merge_mean(part, csls_k)
             launches += 1
         else:
-            _, cand = ops.topk_merge_mean(part, csls_k, want_nv=False, want_cand=True)
-            allc = torch.empty((world, n, KT), dtype=torch.float32, device=dev)
-            dist.all_gather_into_tensor(allc, cand, group=group)
-            nv1, _ = ops.topk_merge_mean(allc, csls_k)
+            _, cand = be.topk_merge_mean(part, csls_k, want_nv=False, want_cand=True)
+            allc = yield ("all_gather", cand)                          # [world, n, KT]
+            nv1, _ = be.topk_merge_mean(allc.contiguous(), csls_k)
             launches += 2
-        # sweep 1': column neighbourhoods (this rank's targets against every source)
+        # sweep 1': column neighbourhoods — this rank's targets against every source
         nv2_loc = torch.zeros((per,), dtype=torch.float32, device=dev)
         if ns > 0:
-            part2 = ops.eval_rowtopk(Ys, X, yns, xn, ns, n)
-            nv2s, _ = ops.topk_merge_mean(part2, csls_k)
+            part2 = be.eval_rowtopk(Ys, X, yns, xn, ns, n)
+            nv2s, _ = be.topk_merge_mean(part2, csls_k)
             nv2_loc[:ns] = nv2s
             launches += 2
         if world == 1:
             nv2 = nv2_loc[:n]
         else:
-            allv = torch.empty((world * per,), dtype=torch.float32, device=dev)
-            dist.all_gather_into_tensor(allv, nv2_loc, group=group)
-            nv2 = allv[:n].contiguous()
+            allv = yield ("all_gather", nv2_loc)                       # [world, per]
+            nv2 = allv.reshape(-1)[:n].contiguous()
 
     # ground-truth scores of all pairs (n dot products; replicated on every rank)
-    g = ops.pair_score(X, Y, n, xn, yn, nv1, nv2, use_csls)
+    g = be.pair_score(X, Y, n, xn, yn, nv1, nv2, use_csls)
     launches += 1
 
     # sweep 2: rank counters
@@ -115,36 +107,118 @@ def align_ranks(X: torch.Tensor, Y: torch.Tensor, xn: torch.Tensor, yn: torch.Te
     t3v = t3i = None
     if ns > 0:
         nv2s = nv2[c0:c1] if use_csls else None
-        t3v, t3i = ops.eval_rank(X, Ys, xn, yns, nv1, nv2s, g, g[c0:c1], 0, c0, n, ns, use_csls, cnt_row, cnt_col_loc,
-                                 want_top3)
+        t3v, t3i = be.eval_rank(X, Ys, xn, yns, nv1, nv2s, g, g[c0:c1], 0, c0, n, ns, use_csls, cnt_row, cnt_col_loc,
+                                want_top3)
         launches += 1
     top3_idx = top3_val = None
     if want_top3:
         if ns > 0:
-            t3v, t3i = ops.top3_merge(t3v, t3i)
+            t3v, t3i = be.top3_merge(t3v, t3i)
             launches += 1
         else:
             t3v = torch.full((n, 4), float("inf"), dtype=torch.float32, device=dev)
             t3i = torch.full((n, 4), 0x7FFFFFFF, dtype=torch.int32, device=dev)
     if world == 1:
         rank_l2r, rank_r2l = cnt_row, cnt_col_loc[:n]
-        if want_top3:
-            top3_idx, top3_val = t3i[:, :3], t3v[:, :3]
     else:
-        dist.all_reduce(cnt_row, group=group)
-        allc = torch.empty((world * per,), dtype=torch.int32, device=dev)
-        dist.all_gather_into_tensor(allc, cnt_col_loc, group=group)
-        rank_l2r, rank_r2l = cnt_row, allc[:n].contiguous()
+        rank_l2r = yield ("all_reduce", cnt_row)
+        allc = yield ("all_gather", cnt_col_loc)
+        rank_r2l = allc.reshape(-1)[:n].contiguous()
         if want_top3:
-            gv = torch.empty((world, n, 4), dtype=torch.float32, device=dev)
-            gi = torch.empty((world, n, 4), dtype=torch.int32, device=dev)
-            dist.all_gather_into_tensor(gv, t3v.contiguous(), group=group)
-            dist.all_gather_into_tensor(gi, t3i.contiguous(), group=group)
-            t3v, t3i = ops.top3_merge(gv, gi)
+            gv = yield ("all_gather", t3v.contiguous())                # [world, n, 4]
+            gi = yield ("all_gather", t3i.contiguous())
+            t3v, t3i = be.top3_merge(gv.contiguous(), gi.contiguous())
             launches += 1
-            top3_idx, top3_val = t3i[:, :3], t3v[:, :3]
+    if want_top3:
+        top3_idx, top3_val = t3i[:, :3], t3v[:, :3]
     return AlignRanks(rank_l2r, rank_r2l, nv1, nv2, g, top3_idx, top3_val, launches,
-                      {"world": world, "shard": (c0, c1)})
+                      {"world": world, "rank": rank, "shard": (c0, c1)})
+
+
+def _drive_with_torch_distributed(gen, group):
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    try:
+        req = next(gen)
+        while True:
+            op, t = req
+            if op == "all_gather":
+                flat = torch.empty((world * t.numel(),), dtype=t.dtype, device=t.device)
+                dist.all_gather_into_tensor(flat, t.contiguous().reshape(-1), group=group)
+                out = flat.view(world, *t.shape)
+            elif op == "all_reduce":
+                out = t.contiguous()
+                dist.all_reduce(out, group=group)
+            else:
+                raise AssertionError(op)
+            req = gen.send(out)
+    except StopIteration as stop:
+        return stop.value
+
+
+def simulate_sharded(make_gen, world: int):
+    """Run `world` rank generators in lockstep inside one process (used by tests and single-GPU checks of the
+    sharding logic): make_gen(rank) -> generator as produced by _align_ranks_steps."""
+    gens = [make_gen(r) for r in range(world)]
+    results = [None] * world
+    reqs = []
+    for r, gnr in enumerate(gens):
+        try:
+            reqs.append(next(gnr))
+        except StopIteration as stop:
+            results[r] = stop.value
+            reqs.append(None)
+    while any(q is not None for q in reqs):
+        if any(q is None for q in reqs):
+            raise AssertionError("ranks disagree on the number of collectives")
+        op = reqs[0][0]
+        if any(q[0] != op for q in reqs):
+            raise AssertionError("ranks disagree on the collective sequence")
+        if op == "all_gather":
+            out = torch.stack([q[1] for q in reqs], 0)
+            outs = [out.clone() for _ in range(world)]
+        else:
+            tot = reqs[0][1].clone()
+            for q in reqs[1:]:
+                tot += q[1]
+            outs = [tot.clone() for _ in range(world)]
+        nxt = []
+        for r, gnr in enumerate(gens):
+            try:
+                nxt.append(gnr.send(outs[r]))
+            except StopIteration as stop:
+                results[r] = stop.value
+                nxt.append(None)
+        reqs = nxt
+    return results
+
+
+def align_ranks(X: torch.Tensor, Y: torch.Tensor, xn: torch.Tensor, yn: torch.Tensor, n: int, csls_k: int = 10,
+                use_csls: bool = True, want_top3: bool = False, group=None, backend=None) -> AlignRanks:
+    """Fused evaluation of n aligned pairs (x_i <-> y_i).
+
+    X, Y : bf16 operands [>=n, Dpad] from ops.prep_bf16; xn, yn : their squared norms [n].
+    With `group` (a torch.distributed process group, NCCL on GPUs) every rank holds all of X and Y and sweeps
+    only its own shard of the targets."""
+    if use_csls and not 1 <= csls_k <= KT:
+        raise SnagError(f"csls_k={csls_k} unsupported: the fused CSLS path keeps {KT} candidates per row")
+    if use_csls and csls_k > n:
+        # torch.topk raises in the reference (src/utils.py:431) when k exceeds the matrix side
+        raise ValueError(f"csls_k={csls_k} exceeds the number of evaluated pairs n={n}")
+    be = _cuda_ops if backend is None else backend
+    if group is None:
+        world, rank = 1, 0
+    else:
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+    gen = _align_ranks_steps(be, X, Y, xn, yn, n, csls_k, use_csls, want_top3, world, rank)
+    if world == 1:
+        try:
+            next(gen)
+        except StopIteration as stop:
+            return stop.value
+        raise AssertionError("single-rank evaluation requested a collective")
+    return _drive_with_torch_distributed(gen, group)
 
 
 # =================================================================================================
@@ -182,16 +256,15 @@ def evaluate_alignment(final_emb: torch.Tensor, test_left: torch.Tensor, test_ri
     n = test_left.numel()
     if test_right.numel() != n:
         raise ValueError("test_left and test_right must pair up")
-    X, xn = ops.prep_bf16(final_emb, test_left.to(torch.int64).contiguous(), normalize)
-    Y, yn = ops.prep_bf16(final_emb, test_right.to(torch.int64).contiguous(), normalize)
+    X, xn = _cuda_ops.prep_bf16(final_emb, test_left.to(torch.int64).contiguous(), normalize)
+    Y, yn = _cuda_ops.prep_bf16(final_emb, test_right.to(torch.int64).contiguous(), normalize)
     res = align_ranks(X, Y, xn, yn, n, csls_k, csls, want_top3, group)
-    out = {
+    return {
         "l2r": metrics_from_ranks(res.rank_l2r),
         "r2l": metrics_from_ranks(res.rank_r2l),
         "ranks": res,
         "launches": res.launches + 2,
     }
-    return out
 
 
 # =================================================================================================
@@ -201,12 +274,12 @@ def pairwise_distances(x: torch.Tensor, y: torch.Tensor | None = None) -> torch.
     """Drop-in for src/utils.py:202-218: dist[i,j] = clamp(||x_i||^2 + ||y_j||^2 - 2 x_i.y_j, 0), fp32 [n1,n2].
     Operands are rounded to bf16 for the tensor-core contraction; norms are those of the rounded rows."""
     x = x.contiguous().float()
-    X, xn = ops.prep_bf16(x, None, normalize=False)
+    X, xn = _cuda_ops.prep_bf16(x, None, normalize=False)
     if y is None:
         Y, yn = X, xn
         n2 = x.shape[0]
     else:
         y = y.contiguous().float()
-        Y, yn = ops.prep_bf16(y, None, normalize=False)
+        Y, yn = _cuda_ops.prep_bf16(y, None, normalize=False)
         n2 = y.shape[0]
-    return ops.sim_write(X, Y, xn, yn, x.shape[0], n2, mode=1)
+    return _cuda_ops.sim_write(X, Y, xn, yn, x.shape[0], n2, mode=1)

@@ -1,0 +1,100 @@
+"""A CPU stand-in for snag_b200.ops built on the oracle, with the same five entry points the sharded
+evaluation driver uses. TEST-ONLY: it lets the partition / candidate-merge / counter-reduction logic of
+snag_b200.evaluate run under gloo (or the in-process lockstep simulator) without a GPU."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from oracle import oracle
+
+KT = 16
+
+
+def _np(t):
+    return t.detach().cpu().float().numpy()
+
+
+def _c_matrix(X, Y, xn, yn, n1, n2):
+    s = oracle.dot_matrix(_np(X[:n1]), _np(Y[:n2]))
+    t = (_np(xn)[:n1, None] + _np(yn)[None, :n2]).astype(np.float32)
+    d = np.maximum(t - np.float32(2.0) * s, np.float32(0.0)).astype(np.float32)
+    return d
+
+
+def eval_rowtopk(X, Y, xn, yn, n1, n2):
+    c = (np.float32(1.0) - _c_matrix(X, Y, xn, yn, n1, n2)).astype(np.float32)
+    part = np.full((1, n1, KT), -np.inf, np.float32)
+    kk = min(KT, n2)
+    part[0, :, KT - kk:] = np.sort(c, axis=1)[:, -kk:]
+    return torch.from_numpy(part)
+
+
+def topk_merge_mean(part, k, want_nv=True, want_cand=False):
+    p = part.numpy()
+    allv = np.sort(np.concatenate(list(p), axis=1), axis=1)[:, -KT:]        # ascending, KT largest
+    nv = None
+    if want_nv:
+        s = np.zeros((allv.shape[0],), np.float32)
+        for t in range(k):
+            s = (s + allv[:, KT - 1 - t]).astype(np.float32)
+        nv = torch.from_numpy((s / np.float32(k)).astype(np.float32))
+    cand = torch.from_numpy(allv.copy()) if want_cand else None
+    return nv, cand
+
+
+def _dist(X, Y, xn, yn, nv1, nv2, n1, n2, use_csls):
+    d = _c_matrix(X, Y, xn, yn, n1, n2)
+    if not use_csls:
+        return d
+    c = (np.float32(1.0) - d).astype(np.float32)
+    u = (np.float32(2.0) * c - _np(nv1)[:n1, None]).astype(np.float32)
+    v = (u - _np(nv2)[None, :n2]).astype(np.float32)
+    return (np.float32(1.0) - v).astype(np.float32)
+
+
+def pair_score(X, Y, n, xn, yn, nv1, nv2, use_csls, want_dot=False):
+    x, y = _np(X[:n]), _np(Y[:n])
+    s = np.einsum("ij,ij->i", x.astype(np.float64), y.astype(np.float64)).astype(np.float32)
+    t = (_np(xn)[:n] + _np(yn)[:n]).astype(np.float32)
+    d = np.maximum(t - np.float32(2.0) * s, np.float32(0.0)).astype(np.float32)
+    if use_csls:
+        c = (np.float32(1.0) - d).astype(np.float32)
+        u = (np.float32(2.0) * c - _np(nv1)[:n]).astype(np.float32)
+        d = (np.float32(1.0) - (u - _np(nv2)[:n]).astype(np.float32)).astype(np.float32)
+    return torch.from_numpy(d)
+
+
+def eval_rank(X, Y, xn, yn, nv1, nv2, g_row, g_col, row_gid0, col_gid0, n1, n2, use_csls, cnt_row, cnt_col,
+              want_top3=False):
+    dist = _dist(X, Y, xn, yn, nv1, nv2, n1, n2, use_csls)
+    gr, gc = _np(g_row)[:n1], _np(g_col)[:n2]
+    ri = row_gid0 + np.arange(n1)[:, None]
+    cj = col_gid0 + np.arange(n2)[None, :]
+    prow = (dist < gr[:, None]) | ((dist == gr[:, None]) & (cj < ri))
+    pcol = (dist < gc[None, :]) | ((dist == gc[None, :]) & (ri < cj))
+    same = ri == cj
+    prow &= ~same
+    pcol &= ~same
+    cnt_row[:n1] += torch.from_numpy(prow.sum(1).astype(np.int32))
+    cnt_col[:n2] += torch.from_numpy(pcol.sum(0).astype(np.int32))
+    if not want_top3:
+        return None, None
+    order = np.lexsort((np.broadcast_to(cj, dist.shape), dist), axis=1)[:, :3]
+    v = np.full((1, n1, 4), np.inf, np.float32)
+    i = np.full((1, n1, 4), 0x7FFFFFFF, np.int32)
+    m = order.shape[1]
+    v[0, :, :m] = np.take_along_axis(dist, order, 1)
+    i[0, :, :m] = order + col_gid0
+    return torch.from_numpy(v), torch.from_numpy(i)
+
+
+def top3_merge(val, idx):
+    v = np.concatenate(list(val.numpy()[:, :, :3]), axis=1)
+    i = np.concatenate(list(idx.numpy()[:, :, :3]), axis=1)
+    order = np.lexsort((i, v), axis=1)[:, :3]
+    ov = np.zeros((v.shape[0], 4), np.float32)
+    oi = np.zeros((v.shape[0], 4), np.int32)
+    ov[:, :3] = np.take_along_axis(v, order, 1)
+    oi[:, :3] = np.take_along_axis(i, order, 1)
+    return torch.from_numpy(ov), torch.from_numpy(oi)

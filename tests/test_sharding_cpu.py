@@ -1,0 +1,87 @@
+"""CPU: the sharded-evaluation driver (partition of targets, merge of per-shard CSLS candidates, reduction
+of the rank counters, top-3 merge) with the oracle standing in for the kernels — under the in-process
+lockstep simulator and under real torch.distributed with the gloo backend, world_size 2."""
+from __future__ import annotations
+
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from oracle import oracle
+from snag_b200 import evaluate
+from tests import oracle_backend
+from tests.conftest import load_golden
+
+
+def _operands(fx):
+    x, y = fx["x"], fx["y"]
+    n, d = x.shape
+    dpad = evaluate.round_up(d, 64)
+    X = torch.zeros((n, dpad), dtype=torch.bfloat16)
+    Y = torch.zeros((n, dpad), dtype=torch.bfloat16)
+    X[:, :d] = torch.from_numpy(x).to(torch.bfloat16)
+    Y[:, :d] = torch.from_numpy(y).to(torch.bfloat16)
+    return X, Y, torch.from_numpy(oracle.norm2(x)), torch.from_numpy(oracle.norm2(y)), n
+
+
+@pytest.mark.parametrize("name,world", [("eval_n384_d96_k10", 1), ("eval_n384_d96_k10", 2), ("eval_n700_d320_k10", 3),
+                                        ("eval_ties_dyadic_k4", 2), ("eval_n384_d96_nocsls", 2), ("eval_n257_d64_k16", 4)])
+def test_simulated_shards_match_reference(name, world):
+    fx = load_golden(name)
+    X, Y, xn, yn, n = _operands(fx)
+    k, csls = int(fx["k"]), bool(fx["csls"])
+    res = evaluate.simulate_sharded(
+        lambda r: evaluate._align_ranks_steps(oracle_backend, X, Y, xn, yn, n, k, csls, True, world, r), world)
+    for r in res:      # every rank ends with the full, identical result
+        np.testing.assert_array_equal(r.rank_l2r.numpy(), fx["rank_l2r"])
+        np.testing.assert_array_equal(r.rank_r2l.numpy(), fx["rank_r2l"])
+        np.testing.assert_array_equal(r.top3_idx.numpy(), fx["top3"])
+        if csls:
+            np.testing.assert_allclose(r.nv1.numpy(), fx["nv1"], atol=1e-6, rtol=0)
+            np.testing.assert_allclose(r.nv2.numpy(), fx["nv2"], atol=1e-6, rtol=0)
+
+
+def test_empty_trailing_shards_are_harmless():
+    fx = load_golden("eval_n257_d64_k16")          # 257 targets over 8 ranks: ranks 2..7 own nothing
+    X, Y, xn, yn, n = _operands(fx)
+    res = evaluate.simulate_sharded(
+        lambda r: evaluate._align_ranks_steps(oracle_backend, X, Y, xn, yn, n, 16, True, False, 8, r), 8)
+    np.testing.assert_array_equal(res[7].rank_l2r.numpy(), fx["rank_l2r"])
+    np.testing.assert_array_equal(res[0].rank_r2l.numpy(), fx["rank_r2l"])
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _gloo_worker(rank, world, port, name, out):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    fx = load_golden(name)
+    X, Y, xn, yn, n = _operands(fx)
+    res = evaluate.align_ranks(X, Y, xn, yn, n, int(fx["k"]), bool(fx["csls"]), True, group=dist.group.WORLD,
+                               backend=oracle_backend)
+    ok = (np.array_equal(res.rank_l2r.numpy(), fx["rank_l2r"]) and np.array_equal(res.rank_r2l.numpy(), fx["rank_r2l"])
+          and np.array_equal(res.top3_idx.numpy(), fx["top3"]))
+    out[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_gloo_world2_matches_reference():
+    world = 2
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_gloo_worker, args=(world, _free_port(), "eval_n384_d96_k10", out), nprocs=world, join=True)
+        assert dict(out) == {0: True, 1: True}
