@@ -125,6 +125,14 @@ int snag_icl_rowsum(const uint16_t* X, const uint16_t* Y, int32_t B, int32_t Bp,
 int snag_icl_finalize(const float* rowsum_part, int32_t n_lists, int32_t B, int32_t Bp, const float* pos,
                       float inv_tau, float* lse, float* nll, void* stream);
 
+/* ICL backward, stage 1: recompute one side's logits and write dL/dlogits as bf16 G [Bp, 2*Bp] (same X / Y views
+ * as snag_icl_rowsum). With g_x = dL/dnll_x (upstream) and lse_x from the forward:
+ *   cr[i] = g_this[i]*exp(1/tau - lse_this[i]), cc[j] = g_other[j]*exp(1/tau - lse_other[j]), dg[i] = g_this[i]+g_other[i]
+ * Stage 2 is a plain contraction dX = G . [other ; this], run with snag_sim_write(mode 0) on G and the
+ * transposed stacked operand. */
+int snag_icl_bwd_logits(const uint16_t* X, const uint16_t* Y, int32_t B, int32_t Bp, int32_t Dpad, float inv_tau,
+                        const float* cr, const float* cc, const float* dg, uint16_t* G, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

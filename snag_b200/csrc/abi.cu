@@ -107,4 +107,10 @@ int snag_icl_finalize(const float* rowsum_part, int32_t n_lists, int32_t B, int3
   return launch_icl_finalize(rowsum_part, n_lists, B, Bp, pos, inv_tau, lse, nll, S(stream));
 }
 
+int snag_icl_bwd_logits(const uint16_t* X, const uint16_t* Y, int32_t B, int32_t Bp, int32_t Dpad, float inv_tau,
+                        const float* cr, const float* cc, const float* dg, uint16_t* G, void* stream) {
+  return launch_icl_bwd_logits(BF(X), BF(Y), B, Bp, Dpad, inv_tau, cr, cc, dg, reinterpret_cast<__nv_bfloat16*>(G),
+                               S(stream));
+}
+
 }  // extern "C"

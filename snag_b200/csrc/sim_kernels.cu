@@ -176,4 +176,12 @@ int launch_icl_rowsum(const __nv_bfloat16* X, const __nv_bfloat16* Y, int B, int
   return launch_sim<EpiIclFwd>(X, Y, Bp, 2 * Bp, Dpad, p, st);
 }
 
+int launch_icl_bwd_logits(const __nv_bfloat16* X, const __nv_bfloat16* Y, int B, int Bp, int Dpad, float inv_tau,
+                          const float* cr, const float* cc, const float* dg, __nv_bfloat16* G, cudaStream_t st) {
+  if (!cr || !cc || !dg || !G || B <= 0 || Bp < B || (Bp % BN) != 0) return SNAG_ERR_ARG;
+  if (reinterpret_cast<uintptr_t>(G) & 15) return SNAG_ERR_ALIGN;
+  EpiIclBwd::Params p{inv_tau * 1.4426950408889634f, inv_tau, B, Bp, cr, cc, dg, G};
+  return launch_sim<EpiIclBwd>(X, Y, Bp, 2 * Bp, Dpad, p, st);
+}
+
 }  // namespace snag

@@ -583,4 +583,77 @@ struct EpiIclFwd {
   }
 };
 
+// ------------------------------------------------------------------------------------------------
+// Epilogue: ICL backward, stage 1 — recompute the logits tile and write dL/dlogits as a bf16 matrix
+// G [Bp, 2*Bp] (the left operand of the gradient GEMM  dX = G · [other side ; this side]).
+// With nll_x[i] = lse_x[i] - s_ii/tau and upstream gradients gx = dL/dnll_x (Appendix A of SURVEY.md):
+//   part 0 (cross):  G[i,j] = (cr_i + cc_j) * E_ij / tau  - [i == j] * dg_i / tau
+//   part 1 (self) :  G[i,j] = (cr_i + cr_j) * E_ij / tau            (0 on the diagonal)
+// where E_ij = exp(s_ij/tau - 1/tau), cr_i = g_this[i] * exp(1/tau - lse_this[i]) (row softmax term),
+// cc_j = g_other[j] * exp(1/tau - lse_other[j]) (the same s_ij seen from the other side's softmax),
+// dg_i = g_this[i] + g_other[i]. Rows >= B and columns in the padding are written as zeros.
+// ------------------------------------------------------------------------------------------------
+struct EpiIclBwd {
+  static constexpr bool kNoLoad = false;
+  struct Params {
+    float scale_log2;     // log2(e) / tau
+    float inv_tau;
+    int B, Bp;
+    const float* cr;      // [Bp] row-side coefficients (this side)
+    const float* cc;      // [Bp] column-side coefficients of part 0 (other side)
+    const float* dg;      // [Bp] diagonal term of part 0
+    __nv_bfloat16* G;     // [Bp, 2*Bp]
+  };
+  struct State {
+    float cr, dg;
+  };
+  static __device__ __forceinline__ void unit_begin(const Params& p, const SimShape&, const EpiCtx& cx, State& st) {
+    const bool ok = cx.row < p.B;
+    st.cr = ok ? p.cr[cx.row] : 0.f;
+    st.dg = ok ? p.dg[cx.row] : 0.f;
+  }
+  static __device__ __forceinline__ void tile_begin(const Params& p, const SimShape&, const EpiCtx& cx, State&, int ct,
+                                                    int buf) {
+    static_assert(NUM_EPI_THREADS == BN, "one epilogue thread stages one column");
+    const int col = ct * BN + cx.tid;
+    const int part = col >= p.Bp ? 1 : 0;
+    const int idx = col - part * p.Bp;
+    float v = 0.f;
+    if (idx < p.B) v = part ? p.cr[idx] : p.cc[idx];
+    cx.scratch[buf * BN + cx.tid] = v;
+  }
+  static __device__ __forceinline__ void chunk(const Params& p, const SimShape&, const EpiCtx& cx, State& st, int ct,
+                                               int c, const uint32_t (&r)[32], int buf) {
+    const float* cc_s = cx.scratch + buf * BN + c * 32;
+    const int col0 = ct * BN + c * 32;
+    const int part = col0 >= p.Bp ? 1 : 0;
+    const int idx0 = col0 - part * p.Bp;
+    const bool row_ok = cx.row < p.B;
+    const float nb = -p.scale_log2;
+    uint32_t packed[16];
+#pragma unroll
+    for (int q = 0; q < 32; q += 2) {
+      float v[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int idx = idx0 + q + e;
+        const float E = ex2_approx(__fmaf_rn(__uint_as_float(r[q + e]), p.scale_log2, nb));
+        float gval = (st.cr + cc_s[q + e]) * E * p.inv_tau;
+        if (idx == cx.row) gval = part ? 0.f : gval - st.dg * p.inv_tau;
+        if (!row_ok || idx >= p.B) gval = 0.f;
+        v[e] = gval;
+      }
+      const __nv_bfloat162 h = __floats2bfloat162_rn(v[0], v[1]);
+      packed[q / 2] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    if (cx.row < p.Bp) {
+      uint4* dst = reinterpret_cast<uint4*>(p.G + static_cast<long long>(cx.row) * (2 * p.Bp) + col0);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) dst[q] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+    }
+  }
+  static __device__ __forceinline__ void tile_end(const Params&, const SimShape&, const EpiCtx&, State&, int, int) {}
+  static __device__ __forceinline__ void unit_end(const Params&, const SimShape&, const EpiCtx&, State&) {}
+};
+
 }  // namespace snag

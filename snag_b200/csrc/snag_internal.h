@@ -53,4 +53,7 @@ int launch_eval_rank(const __nv_bfloat16* X, const __nv_bfloat16* Y, const float
 int launch_icl_rowsum(const __nv_bfloat16* X, const __nv_bfloat16* Y, int B, int Bp, int Dpad, float inv_tau,
                       float* rowsum_part, float* pos, cudaStream_t st);
 
+int launch_icl_bwd_logits(const __nv_bfloat16* X, const __nv_bfloat16* Y, int B, int Bp, int Dpad, float inv_tau,
+                          const float* cr, const float* cc, const float* dg, __nv_bfloat16* G, cudaStream_t st);
+
 }  // namespace snag

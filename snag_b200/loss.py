@@ -1,0 +1,219 @@
+"""ICL / IAL in-batch contrastive losses and the uncertainty-weighting layer — host-side mirror of
+SNAG_MMEA/model/SNAG_loss.py (same class names, constructor arguments, forward signatures and parameter
+names, so `from snag_b200.loss import CustomMultiLossLayer, icl_loss, ial_loss` replaces the reference import
+in model/SNAG.py:12 unchanged).
+
+icl_loss: the four B x B similarity contractions, the -1e9 self-mask, the concatenation and the soft-label
+cross entropy of model/SNAG_loss.py:98-126 are one fused tcgen05 sweep per side (row log-sum-exp in the
+epilogue, no B x 2B matrix in HBM); the backward recomputes the logits tile by tile, writes dL/dlogits in bf16
+and contracts it with the stacked embeddings on the same mainloop. Gather, normalisation, the per-pair weight
+min(w[l], w[r]) and the final means stay ordinary torch autograd, so gradients reach `emb` and `weight_norm`
+exactly as in the reference (model/SNAG_loss.py:51,66-69).
+
+ial_loss (constructed but never called by SNAG — model/SNAG.py:53; live caller model/MCLEA.py:128-139): the eight
+contractions run on the tcgen05 mainloop through a differentiable `contract`; the softmax/KL on the materialised
+[B, 2B] logits is torch. A fused row-KL epilogue is listed as next work in DESIGN.md.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from . import ops
+
+
+def cosine_sim(im, s):
+    """model/SNAG_loss.py:7-10 (helper kept for interface parity; unused by the forwards, as in the reference)."""
+    return _Contract.apply(im, s)
+
+
+class CustomMultiLossLayer(nn.Module):
+    """model/SNAG_loss.py:12-29 — sum_i exp(-s_i) * L_i + s_i over at most `loss_num` scalars. Stays in torch
+    (six scalars). The parameter keeps the name `log_vars`: src/utils.py:46-54 gives `multi_loss_layer*`
+    parameters their own learning rate by name."""
+
+    def __init__(self, loss_num):
+        super().__init__()
+        self.loss_num = loss_num
+        self.log_vars = nn.Parameter(torch.zeros(self.loss_num, ), requires_grad=True)
+
+    def forward(self, loss_list):
+        assert len(loss_list) <= self.loss_num
+        precision = torch.exp(-self.log_vars)
+        loss = 0
+        for i in range(len(loss_list)):
+            loss += precision[i] * loss_list[i] + self.log_vars[i]
+        return loss
+
+
+def _links_to_index(train_links, device):
+    """train_links is a numpy int32 [B, 2] array in the reference's data loader (src/data.py:41-44) or a tensor."""
+    if isinstance(train_links, torch.Tensor):
+        links = train_links.to(device=device, dtype=torch.int64)
+    else:
+        links = torch.from_numpy(np.ascontiguousarray(np.asarray(train_links), dtype=np.int64)).to(device)
+    if links.dim() != 2 or links.shape[1] != 2:
+        raise ValueError(f"train_links must be [B, 2], got {tuple(links.shape)}")
+    return links[:, 0].contiguous(), links[:, 1].contiguous()
+
+
+class _IclPair(torch.autograd.Function):
+    """(zis, zjs) unit rows [B, D] fp32 -> per-row NLL of both directions, fused on the tensor cores."""
+
+    @staticmethod
+    def forward(ctx, zis, zjs, inv_tau):
+        B, D = zis.shape
+        Bp = ops.round_up(B, 256)
+        dpad = ops.round_up(D, 64)
+        # stacked operand [a ; b ; a], every part zero padded to Bp rows: side a sweeps [b ; a], side b sweeps [a ; b]
+        S3 = torch.zeros((3 * Bp, dpad), dtype=torch.bfloat16, device=zis.device)
+        ops.prep_bf16(zis.contiguous(), None, normalize=False, out=S3[0:Bp])
+        ops.prep_bf16(zjs.contiguous(), None, normalize=False, out=S3[Bp:2 * Bp])
+        S3[2 * Bp:2 * Bp + B].copy_(S3[0:B])
+        lse_a, nll_a, _ = ops.icl_side(S3[0:Bp], S3[Bp:3 * Bp], B, Bp, inv_tau)
+        lse_b, nll_b, _ = ops.icl_side(S3[Bp:2 * Bp], S3[0:2 * Bp], B, Bp, inv_tau)
+        ctx.save_for_backward(S3, lse_a, lse_b)
+        ctx.dims = (B, D, Bp, inv_tau)
+        return nll_a, nll_b
+
+    @staticmethod
+    def backward(ctx, g_a, g_b):
+        S3, lse_a, lse_b = ctx.saved_tensors
+        B, D, Bp, inv_tau = ctx.dims
+        g_a = torch.zeros_like(lse_a) if g_a is None else g_a.contiguous().float()
+        g_b = torch.zeros_like(lse_b) if g_b is None else g_b.contiguous().float()
+        cra = (g_a * torch.exp(inv_tau - lse_a)).contiguous()
+        crb = (g_b * torch.exp(inv_tau - lse_b)).contiguous()
+        dg = (g_a + g_b).contiguous()
+        A, Bm = S3[0:Bp], S3[Bp:2 * Bp]
+        Ya, Yb = S3[Bp:3 * Bp], S3[0:2 * Bp]
+        Ga = ops.icl_bwd_logits(A, Ya, B, Bp, inv_tau, cra, crb, dg)         # [Bp, 2Bp] bf16
+        Gb = ops.icl_bwd_logits(Bm, Yb, B, Bp, inv_tau, crb, cra, dg)
+        dA = ops.contract(Ga, Ya.t().contiguous(), B, D)                      # [B, D] fp32
+        dB = ops.contract(Gb, Yb.t().contiguous(), B, D)
+        return dA, dB, None
+
+
+class icl_loss(nn.Module):
+    """model/SNAG_loss.py:31-128."""
+
+    def __init__(self, tau=0.05, ab_weight=0.5, n_view=2, intra_weight=1.0, inversion=False, neg_cross_kg=False):
+        super().__init__()
+        self.tau = tau
+        self.sim = cosine_sim
+        self.weight = ab_weight
+        self.n_view = n_view
+        self.intra_weight = intra_weight
+        self.inversion = inversion
+        self.neg_cross_kg = neg_cross_kg
+
+    def forward(self, emb, train_links, neg_l=None, neg_r=None, weight_norm=None, norm=True):
+        if neg_l is not None or neg_r is not None:
+            raise NotImplementedError("explicit negatives (MEAformer replay, MEAformer.py:126) are outside the SNAG path")
+        if self.inversion:
+            raise NotImplementedError("inversion=True is unreachable from SNAG (model/SNAG.py:50-51)")
+        if not norm:
+            raise NotImplementedError("norm=False: the fused kernel relies on unit rows (logits bounded by 1/tau)")
+        if self.n_view != 2:
+            raise NotImplementedError("n_view != 2")
+        idx_l, idx_r = _links_to_index(train_links, emb.device)
+        # normalising only the 2B gathered rows equals normalising all N first (model/SNAG_loss.py:60-64), row by row
+        zis = F.normalize(emb.index_select(0, idx_l).float(), dim=1)
+        zjs = F.normalize(emb.index_select(0, idx_r).float(), dim=1)
+        nll_a, nll_b = _IclPair.apply(zis, zjs, float(1.0 / self.tau))
+        batch = zis.shape[0]
+        if weight_norm is not None:
+            w = torch.min(torch.stack([weight_norm[idx_l], weight_norm[idx_r]], dim=1), 1)[0]   # :66-69
+            loss_a = (nll_a * w).sum() / batch                                                   # softXEnt :51
+            loss_b = (nll_b * w).sum() / batch
+        else:
+            loss_a = nll_a.sum() / batch                                                         # softXEnt :53
+            loss_b = nll_b.sum() / batch
+        alpha = self.weight
+        return alpha * loss_a + (1 - alpha) * loss_b
+
+
+class _Contract(torch.autograd.Function):
+    """S = P . Q^T (fp32 [n1, D] x [n2, D] -> fp32 [n1, n2]) with operands rounded to bf16, on the tcgen05 mainloop,
+    differentiable: dP = dS . Q, dQ = dS^T . P run on the same mainloop."""
+
+    @staticmethod
+    def forward(ctx, P, Q):
+        Pb, _ = ops.prep_bf16(P.contiguous().float(), None, normalize=False)
+        Qb, _ = ops.prep_bf16(Q.contiguous().float(), None, normalize=False)
+        ctx.save_for_backward(Pb, Qb)
+        ctx.dims = (P.shape[0], Q.shape[0], P.shape[1])
+        return ops.contract(Pb, Qb, P.shape[0], Q.shape[0])
+
+    @staticmethod
+    def backward(ctx, dS):
+        Pb, Qb = ctx.saved_tensors
+        n1, n2, D = ctx.dims
+        dP = dQ = None
+        dSb, _ = ops.prep_bf16(dS.contiguous().float(), None, normalize=False)            # [n1, n2pad]
+        if ctx.needs_input_grad[0]:
+            Qt = torch.zeros((Qb.shape[1], dSb.shape[1]), dtype=torch.bfloat16, device=dS.device)
+            Qt[:, :n2] = Qb[:n2].t()
+            dP = ops.contract(dSb, Qt, n1, D)
+        if ctx.needs_input_grad[1]:
+            dSt, _ = ops.prep_bf16(dS.t().contiguous().float(), None, normalize=False)    # [n2, n1pad]
+            Pt = torch.zeros((Pb.shape[1], dSt.shape[1]), dtype=torch.bfloat16, device=dS.device)
+            Pt[:, :n1] = Pb[:n1].t()
+            dQ = ops.contract(dSt, Pt, n2, D)
+        return dP, dQ
+
+
+class ial_loss(nn.Module):
+    """model/SNAG_loss.py:130-202 — unimodal/multimodal KL alignment loss."""
+
+    def __init__(self, tau=0.05, ab_weight=0.5, zoom=0.1, n_view=2, inversion=False, reduction="mean", detach=False):
+        super().__init__()
+        self.tau = tau
+        self.sim = cosine_sim
+        self.weight = ab_weight
+        self.zoom = zoom
+        self.n_view = n_view
+        self.inversion = inversion
+        self.reduction = reduction
+        self.detach = detach
+
+    def forward(self, src_emb, tar_emb, train_links, norm=True):
+        if self.inversion:
+            raise NotImplementedError("inversion=True is unreachable from SNAG / MCLEA")
+        idx_l, idx_r = _links_to_index(train_links, src_emb.device)
+        src_zis, src_zjs = src_emb.index_select(0, idx_l).float(), src_emb.index_select(0, idx_r).float()
+        tar_zis, tar_zjs = tar_emb.index_select(0, idx_l).float(), tar_emb.index_select(0, idx_r).float()
+        if norm:
+            src_zis, src_zjs = F.normalize(src_zis, dim=1), F.normalize(src_zjs, dim=1)
+            tar_zis, tar_zjs = F.normalize(tar_zis, dim=1).detach(), F.normalize(tar_zjs, dim=1).detach()
+        else:
+            tar_zis, tar_zjs = tar_zis.detach(), tar_zjs.detach()                # q is detached (:192-193)
+        temperature = self.tau
+        alpha = self.weight
+        batch_size = src_zis.shape[0]
+        LARGE_NUM = 1e9
+        masks = torch.eye(batch_size, device=src_emb.device, dtype=torch.float32)
+        mm = _Contract.apply
+        p_ab = mm(src_zis, src_zjs) / temperature
+        p_ba = p_ab.t()                                                          # b.a^T is the transpose of a.b^T
+        q_ab = mm(tar_zis, tar_zjs) / temperature
+        q_ba = q_ab.t()
+        p_aa = mm(src_zis, src_zis) / temperature - masks * LARGE_NUM
+        p_bb = mm(src_zjs, src_zjs) / temperature - masks * LARGE_NUM
+        q_aa = mm(tar_zis, tar_zis) / temperature - masks * LARGE_NUM
+        q_bb = mm(tar_zjs, tar_zjs) / temperature - masks * LARGE_NUM
+        p_ab = torch.cat([p_ab, p_aa], dim=1)
+        p_ba = torch.cat([p_ba, p_bb], dim=1)
+        q_ab = torch.cat([q_ab, q_aa], dim=1)
+        q_ba = torch.cat([q_ba, q_bb], dim=1)
+        loss_a = F.kl_div(F.log_softmax(p_ab, dim=1), F.softmax(q_ab.detach(), dim=1), reduction="none")
+        loss_b = F.kl_div(F.log_softmax(p_ba, dim=1), F.softmax(q_ba.detach(), dim=1), reduction="none")
+        if self.reduction == "mean":
+            loss_a = loss_a.mean()
+            loss_b = loss_b.mean()
+        elif self.reduction == "sum":
+            loss_a = loss_a.sum()
+            loss_b = loss_b.sum()
+        return self.zoom * (alpha * loss_a + (1 - alpha) * loss_b)

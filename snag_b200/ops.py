@@ -32,9 +32,11 @@ def sim_plan(n_rows: int, n_cols: int, dpad: int) -> tuple[int, int]:
 
 # ------------------------------------------------------------------------------------------------ prologue
 def prep_bf16(emb: torch.Tensor, idx: torch.Tensor | None = None, normalize: bool = True,
-              rows_pad_to: int = 1) -> tuple[torch.Tensor, torch.Tensor]:
+              rows_pad_to: int = 1, out: torch.Tensor | None = None) -> tuple[torch.Tensor, torch.Tensor]:
     """(gather ->) L2-normalise -> bf16, zero padded to a multiple of 64 columns; plus ||row||^2 (fp32) of the
-    rounded rows. Returns (operand [n_pad, Dpad] bf16, norm2 [n] fp32); rows n..n_pad are zero."""
+    rounded rows. Returns (operand [n_pad, Dpad] bf16, norm2 [n] fp32); rows n..n_pad are zero.
+    `out` (bf16 [>=n, Dpad], contiguous) receives the rows instead of a fresh allocation; its remaining rows are
+    left untouched."""
     _need(emb, torch.float32, "emb", 2)
     n = emb.shape[0] if idx is None else idx.numel()
     if idx is not None:
@@ -44,7 +46,11 @@ def prep_bf16(emb: torch.Tensor, idx: torch.Tensor | None = None, normalize: boo
     d = emb.shape[1]
     dpad = round_up(d, 64)
     n_pad = round_up(n, rows_pad_to)
-    if n_pad == n:
+    if out is not None:
+        _check_operand(out, "out")
+        if out.shape[0] < n or out.shape[1] != dpad:
+            raise ValueError(f"out must be [>= {n}, {dpad}], got {tuple(out.shape)}")
+    elif n_pad == n:
         out = torch.empty((n_pad, dpad), dtype=torch.bfloat16, device=emb.device)
     else:
         out = torch.zeros((n_pad, dpad), dtype=torch.bfloat16, device=emb.device)
@@ -158,6 +164,27 @@ def icl_side(X: torch.Tensor, Y: torch.Tensor, B: int, Bp: int, inv_tau: float):
     call("snag_icl_rowsum", ptr(X), ptr(Y), B, Bp, X.shape[1], inv_tau, ptr(part), ptr(pos), st)
     call("snag_icl_finalize", ptr(part), nch, B, Bp, ptr(pos), inv_tau, ptr(lse), ptr(nll), st)
     return lse, nll, pos
+
+
+def icl_bwd_logits(X: torch.Tensor, Y: torch.Tensor, B: int, Bp: int, inv_tau: float, cr: torch.Tensor,
+                   cc: torch.Tensor, dg: torch.Tensor) -> torch.Tensor:
+    """dL/dlogits of one ICL side as bf16 [Bp, 2*Bp] (see snag_icl_bwd_logits)."""
+    _check_operand(X, "X")
+    _check_operand(Y, "Y")
+    for t, nm in ((cr, "cr"), (cc, "cc"), (dg, "dg")):
+        _need(t, torch.float32, nm, 1)
+        if t.numel() < B:
+            raise ValueError(f"{nm} needs at least B entries")
+    G = torch.empty((Bp, 2 * Bp), dtype=torch.bfloat16, device=X.device)
+    call("snag_icl_bwd_logits", ptr(X), ptr(Y), B, Bp, X.shape[1], inv_tau, ptr(cr), ptr(cc), ptr(dg), ptr(G),
+         current_stream())
+    return G
+
+
+def contract(P: torch.Tensor, Q: torch.Tensor, n1: int, n2: int) -> torch.Tensor:
+    """fp32 [n1, n2] = P[:n1] . Q[:n2]^T for bf16 operands sharing the (multiple-of-64) contraction width — the
+    gradient GEMMs of the loss layer run on the same tcgen05 mainloop as the similarity sweeps."""
+    return sim_write(P, Q, None, None, n1, n2, 0)
 
 
 # ------------------------------------------------------------------------------------------------ noise

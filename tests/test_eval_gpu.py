@@ -1,0 +1,211 @@
+"""GPU parity: the fused alignment evaluation (through the C ABI) against the reference's golden vectors, the
+oracle on seeded inputs, and size-independent properties at the BASELINE sizes. Ranks / hits / top-3 ids are
+compared bit-exactly; CSLS neighbourhood means and distances within 1e-6 (tensor-core vs fp64 accumulation
+order of the dot products, everything else in the chain is the same single fp32 op)."""
+from __future__ import annotations
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle
+from snag_b200 import _lib, evaluate, ops
+from tests.conftest import golden_names, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _prep(x, y, dev):
+    X, xn = ops.prep_bf16(torch.from_numpy(np.ascontiguousarray(x)).to(dev), None, normalize=False)
+    Y, yn = ops.prep_bf16(torch.from_numpy(np.ascontiguousarray(y)).to(dev), None, normalize=False)
+    return X, Y, xn, yn
+
+
+def _clustered(n, d, sigma, seed):
+    rng = np.random.RandomState(seed)
+    centres = rng.randn(64, d).astype(np.float32)
+    x = rng.randn(n, d).astype(np.float32) + centres[rng.randint(0, 64, n)]
+    y = x + sigma * rng.randn(n, d).astype(np.float32)
+    return oracle.bf16_round(oracle.normalize_rows(x)), oracle.bf16_round(oracle.normalize_rows(y))
+
+
+@pytest.mark.parametrize("name", golden_names("eval_"))
+def test_golden_vectors(cuda_device, name):
+    fx = load_golden(name)
+    k, csls = int(fx["k"]), bool(fx["csls"])
+    X, Y, xn, yn = _prep(fx["x"], fx["y"], cuda_device)
+    n = fx["x"].shape[0]
+    res = evaluate.align_ranks(X, Y, xn, yn, n, k, csls, want_top3=True)
+    np.testing.assert_array_equal(res.rank_l2r.cpu().numpy(), fx["rank_l2r"])
+    np.testing.assert_array_equal(res.rank_r2l.cpu().numpy(), fx["rank_r2l"])
+    np.testing.assert_array_equal(res.top3_idx.cpu().numpy(), fx["top3"])
+    np.testing.assert_allclose(res.g.cpu().numpy(), fx["g"], rtol=0, atol=2e-6)
+    if csls:
+        np.testing.assert_allclose(res.nv1.cpu().numpy(), fx["nv1"], rtol=0, atol=1e-6)
+        np.testing.assert_allclose(res.nv2.cpu().numpy(), fx["nv2"], rtol=0, atol=1e-6)
+    for side, ranks in (("l2r", res.rank_l2r), ("r2l", res.rank_r2l)):
+        m = evaluate.metrics_from_ranks(ranks)
+        np.testing.assert_array_equal(m.acc, fx[f"acc_{side}"])
+        assert m.mr == float(fx[f"mr_{side}"]) and m.mrr == float(fx[f"mrr_{side}"])
+
+
+def test_dyadic_fixture_is_bit_exact_everywhere(cuda_device):
+    """Dyadic-rational inputs make every product and partial sum exact in fp32, so the tensor-core path must agree
+    with the reference on every float, not only on the ranks — and the fixture forces exact ties."""
+    fx = load_golden("eval_ties_dyadic_k4")
+    X, Y, xn, yn = _prep(fx["x"], fx["y"], cuda_device)
+    res = evaluate.align_ranks(X, Y, xn, yn, fx["x"].shape[0], 4, True)
+    np.testing.assert_array_equal(res.nv1.cpu().numpy(), fx["nv1"])
+    np.testing.assert_array_equal(res.nv2.cpu().numpy(), fx["nv2"])
+    np.testing.assert_array_equal(res.g.cpu().numpy(), fx["g"])
+
+
+@pytest.mark.parametrize("n,d,k,csls,sigma", [(2048, 1200, 10, True, 8.0), (3000, 1800, 3, True, 8.0),
+                                              (1000, 300, 10, False, 3.0), (1531, 96, 16, True, 2.0)])
+def test_against_oracle(cuda_device, n, d, k, csls, sigma):
+    x, y = _clustered(n, d, sigma, 3408)
+    X, Y, xn, yn = _prep(x, y, cuda_device)
+    res = evaluate.align_ranks(X, Y, xn, yn, n, k, csls, want_top3=True)
+    ref = oracle.align_eval(x, y, csls, k, want_dist=True)
+    np.testing.assert_array_equal(xn.cpu().numpy(), oracle.norm2(x))
+    if csls:
+        np.testing.assert_allclose(res.nv1.cpu().numpy(), ref["nv1"], rtol=0, atol=1e-6)
+        np.testing.assert_allclose(res.nv2.cpu().numpy(), ref["nv2"], rtol=0, atol=1e-6)
+    # a pair is "ambiguous" if some competitor sits within 2e-5 of its ground-truth distance: only there may the
+    # accumulation order of a dot product move a rank. Everything else must be bit-exact.
+    dist, g = ref["dist"], ref["g"]
+    off = dist.copy()
+    np.fill_diagonal(off, np.inf)
+    amb_row = np.abs(off - g[:, None]).min(1) < 2e-5
+    amb_col = np.abs(off - g[None, :]).min(0) < 2e-5
+    assert amb_row.mean() < 0.01 and amb_col.mean() < 0.01
+    l2r, r2l = res.rank_l2r.cpu().numpy(), res.rank_r2l.cpu().numpy()
+    np.testing.assert_array_equal(l2r[~amb_row], ref["rank_l2r"][~amb_row])
+    np.testing.assert_array_equal(r2l[~amb_col], ref["rank_r2l"][~amb_col])
+    assert np.abs(l2r - ref["rank_l2r"]).max() <= 2 and np.abs(r2l - ref["rank_r2l"]).max() <= 2
+    srt = np.sort(dist, 1)
+    clear3 = (srt[:, 3] - srt[:, 2] > 2e-5) & (srt[:, 2] - srt[:, 1] > 2e-5) & (srt[:, 1] - srt[:, 0] > 2e-5)
+    np.testing.assert_array_equal(res.top3_idx.cpu().numpy()[clear3], ref["top3"][clear3])
+
+
+@pytest.mark.parametrize("n,d,k", [(1, 64, 1), (2, 8, 2), (127, 40, 5), (129, 64, 10), (257, 300, 16), (513, 64, 3)])
+def test_ragged_shapes(cuda_device, n, d, k):
+    x, y = _clustered(n, d, 1.0, n)
+    X, Y, xn, yn = _prep(x, y, cuda_device)
+    res = evaluate.align_ranks(X, Y, xn, yn, n, k, True, want_top3=n >= 3)
+    ref = oracle.align_eval(x, y, True, k)
+    np.testing.assert_array_equal(res.rank_l2r.cpu().numpy(), ref["rank_l2r"])
+    np.testing.assert_array_equal(res.rank_r2l.cpu().numpy(), ref["rank_r2l"])
+
+
+def test_argument_errors(cuda_device):
+    x, y = _clustered(64, 64, 1.0, 0)
+    X, Y, xn, yn = _prep(x, y, cuda_device)
+    with pytest.raises(_lib.SnagError):
+        evaluate.align_ranks(X, Y, xn, yn, 64, 17, True)         # more neighbours than the fused path keeps
+    with pytest.raises(ValueError):
+        evaluate.align_ranks(X[:8], Y[:8], xn[:8], yn[:8], 8, 10, True)   # k > n: torch.topk raises in the reference
+    with pytest.raises((ValueError, TypeError)):
+        ops.eval_rowtopk(X.float(), Y, xn, yn, 64, 64)           # wrong dtype
+    with pytest.raises(ValueError):
+        ops.prep_bf16(torch.zeros((0, 64), device=cuda_device), None, True)
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_sharded_equals_unsharded(cuda_device, world):
+    """Targets split over `world` ranks (lockstep-simulated on one GPU, same kernels, same collectives' semantics):
+    integer counters and exactly-merged candidate lists make the result bit-identical for any number of ranks."""
+    n, d, k = 2300, 320, 10
+    x, y = _clustered(n, d, 4.0, 17)
+    X, Y, xn, yn = _prep(x, y, cuda_device)
+    one = evaluate.align_ranks(X, Y, xn, yn, n, k, True, want_top3=True)
+    many = evaluate.simulate_sharded(
+        lambda r: evaluate._align_ranks_steps(ops, X, Y, xn, yn, n, k, True, True, world, r), world)
+    for res in (many[0], many[-1]):
+        assert torch.equal(res.rank_l2r, one.rank_l2r) and torch.equal(res.rank_r2l, one.rank_r2l)
+        assert torch.equal(res.nv1, one.nv1) and torch.equal(res.nv2, one.nv2)
+        assert torch.equal(res.top3_idx, one.top3_idx)
+
+
+def test_pairwise_distances_dropin(cuda_device):
+    rng = np.random.RandomState(5)
+    x = oracle.bf16_round(rng.randn(300, 200).astype(np.float32))
+    y = oracle.bf16_round(rng.randn(421, 200).astype(np.float32))
+    got = evaluate.pairwise_distances(torch.from_numpy(x).to(cuda_device), torch.from_numpy(y).to(cuda_device))
+    ref = oracle.pairwise_distances(x, y)
+    np.testing.assert_allclose(got.cpu().numpy(), ref, rtol=2e-6, atol=2e-5)      # values up to ~800: relative
+    sym = evaluate.pairwise_distances(torch.from_numpy(x).to(cuda_device))
+    np.testing.assert_allclose(sym.cpu().numpy(), oracle.pairwise_distances(x), rtol=2e-6, atol=2e-5)
+
+
+def test_evaluate_alignment_end_to_end(cuda_device):
+    """final_emb + index tensors in, metrics out (the Runner._test data flow): gather + normalise + round on device."""
+    rng = np.random.RandomState(9)
+    N, n, d = 3000, 1200, 300
+    emb = rng.randn(N, d).astype(np.float32)
+    left = rng.permutation(N // 2)[:n]
+    right = N // 2 + rng.permutation(N // 2)[:n]
+    emb[right] = emb[left] + 0.8 * rng.randn(n, d).astype(np.float32)
+    out = evaluate.evaluate_alignment(torch.from_numpy(emb).to(cuda_device), torch.from_numpy(left).to(cuda_device),
+                                      torch.from_numpy(right).to(cuda_device), csls=True, csls_k=10)
+    xr = oracle.bf16_round(oracle.normalize_rows(emb[left]))
+    yr = oracle.bf16_round(oracle.normalize_rows(emb[right]))
+    ref = oracle.align_eval(xr, yr, True, 10)
+    # the device normalisation may differ from numpy's by one bf16 ulp on a few elements: compare metrics loosely,
+    # ranks on at least 99.5 % of the pairs
+    assert (out["ranks"].rank_l2r.cpu().numpy() == ref["rank_l2r"]).mean() > 0.995
+    assert abs(out["l2r"].mrr - oracle.metrics(ref["rank_l2r"])["mrr"]) < 2e-3
+
+
+# ------------------------------------------------------------------------------------------------ BASELINE sizes
+@pytest.fixture(scope="module")
+def c2_problem(cuda_device):
+    """configs[1]-shaped evaluation: 10 500 test pairs, joint width 1800 (fr_en + surface), CSLS k=10."""
+    n, d = 10500, 1800
+    g = torch.Generator(device="cuda").manual_seed(3408)
+    centres = torch.randn((64, d), generator=g, device="cuda")
+    x = torch.randn((n, d), generator=g, device="cuda") + centres[torch.randint(0, 64, (n,), generator=g, device="cuda")]
+    y = x + 8.0 * torch.randn((n, d), generator=g, device="cuda")
+    X, xn = ops.prep_bf16(x, None, True)
+    Y, yn = ops.prep_bf16(y, None, True)
+    return X, Y, xn, yn, n
+
+
+def test_full_size_properties(cuda_device, c2_problem):
+    X, Y, xn, yn, n = c2_problem
+    base = evaluate.align_ranks(X, Y, xn, yn, n, 10, True)
+    m = evaluate.metrics_from_ranks(base.rank_l2r)
+    assert 0.5 < m.acc[0] <= 1.0 and m.acc[0] <= m.acc[1] <= m.acc[2]
+    # determinism
+    again = evaluate.align_ranks(X, Y, xn, yn, n, 10, True)
+    assert torch.equal(again.rank_l2r, base.rank_l2r) and torch.equal(again.rank_r2l, base.rank_r2l)
+    # a common permutation of the pairs permutes the ranks (ties aside: none expected on continuous data)
+    perm = torch.randperm(n, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
+    p = evaluate.align_ranks(X[perm].contiguous(), Y[perm].contiguous(), xn[perm].contiguous(), yn[perm].contiguous(),
+                             n, 10, True)
+    assert (p.rank_l2r == base.rank_l2r[perm]).float().mean() > 0.9995
+    assert (p.rank_r2l == base.rank_r2l[perm]).float().mean() > 0.9995
+    # swapping the two sides swaps the directions
+    s = evaluate.align_ranks(Y, X, yn, xn, n, 10, True)
+    assert (s.rank_l2r == base.rank_r2l).float().mean() > 0.9995 and (s.rank_r2l == base.rank_l2r).float().mean() > 0.9995
+    # sharded over 4 ranks: identical
+    many = evaluate.simulate_sharded(lambda r: evaluate._align_ranks_steps(ops, X, Y, xn, yn, n, 10, True, False, 4, r), 4)
+    assert torch.equal(many[2].rank_l2r, base.rank_l2r) and torch.equal(many[2].rank_r2l, base.rank_r2l)
+
+
+def test_full_size_identity(cuda_device, c2_problem):
+    X, _, xn, _, n = c2_problem
+    res = evaluate.align_ranks(X, X, xn, xn, n, 10, True)
+    assert int(res.rank_l2r.max()) == 0 and int(res.rank_r2l.max()) == 0
+
+
+def test_full_size_rank_counts_against_materialised(cuda_device, c2_problem):
+    """The fused counters against a brute-force count on the materialised fp32 matrix (same kernels' distances)."""
+    X, Y, xn, yn, n = c2_problem
+    res = evaluate.align_ranks(X, Y, xn, yn, n, 10, True)
+    d = ops.sim_write(X, Y, xn, yn, n, n, 1)
+    dist = 1 - ((2 * (1 - d) - res.nv1[:, None]) - res.nv2[None, :])
+    g = res.g
+    lt = (dist < g[:, None]).sum(1).int()
+    ltc = (dist < g[None, :]).sum(0).int()
+    assert (lt == res.rank_l2r).float().mean() > 0.9995 and (ltc == res.rank_r2l).float().mean() > 0.9995
