@@ -267,6 +267,60 @@ def evaluate_alignment(final_emb: torch.Tensor, test_left: torch.Tensor, test_ri
     }
 
 
+def evaluate_alignment_host(src_rows: torch.Tensor, tgt_rows: torch.Tensor, n: int, row0: int = 0, csls: bool = True,
+                            csls_k: int = 10, normalize: bool = True, group=None, device=None) -> dict:
+    """End-to-end entry point from HOST memory: `src_rows` / `tgt_rows` are (ideally pinned) fp32 [m, D] host tensors
+    holding pairs row0 .. row0+m of the n evaluated pairs — all of them on a single GPU, or this rank's contiguous
+    slice (ceil(n / world) pairs per rank) when `group` is given. Copies them to the device, normalises and rounds
+    them, exchanges the bf16 operands over NCCL so that every rank holds both tables, runs the sharded fused
+    evaluation, brings the ranks back and reduces them to Hits@k / MR / MRR on the host."""
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    m, d = src_rows.shape
+    if tgt_rows.shape != (m, d):
+        raise ValueError("source and target slices must have the same shape")
+    if group is None:
+        world, per = 1, n
+        if m != n or row0 != 0:
+            raise ValueError("without a process group the host buffers must hold all n pairs")
+    else:
+        import torch.distributed as dist
+        world = dist.get_world_size(group)
+        per = (n + world - 1) // world
+        if row0 != dist.get_rank(group) * per or m != max(0, min(n, row0 + per) - row0):
+            raise ValueError("host slice does not match this rank's share of the pairs")
+    xs = src_rows.to(device, non_blocking=True)
+    ys = tgt_rows.to(device, non_blocking=True)
+    dpad = round_up(d, 64)
+    Xl = torch.zeros((per, dpad), dtype=torch.bfloat16, device=device) if m < per else \
+        torch.empty((per, dpad), dtype=torch.bfloat16, device=device)
+    Yl = torch.zeros_like(Xl) if m < per else torch.empty_like(Xl)
+    xnl = torch.zeros((per,), dtype=torch.float32, device=device)
+    ynl = torch.zeros((per,), dtype=torch.float32, device=device)
+    if m > 0:
+        _, a = _cuda_ops.prep_bf16(xs, None, normalize, out=Xl)
+        _, b = _cuda_ops.prep_bf16(ys, None, normalize, out=Yl)
+        xnl[:m] = a
+        ynl[:m] = b
+    launches = 2
+    if world == 1:
+        X, Y, xn, yn = Xl, Yl, xnl, ynl
+    else:
+        X = torch.empty((world * per, dpad), dtype=torch.bfloat16, device=device)
+        Y = torch.empty_like(X)
+        xn = torch.empty((world * per,), dtype=torch.float32, device=device)
+        yn = torch.empty_like(xn)
+        dist.all_gather_into_tensor(X, Xl, group=group)
+        dist.all_gather_into_tensor(Y, Yl, group=group)
+        dist.all_gather_into_tensor(xn, xnl, group=group)
+        dist.all_gather_into_tensor(yn, ynl, group=group)
+    res = align_ranks(X, Y, xn[:n].contiguous(), yn[:n].contiguous(), n, csls_k, csls, False, group)
+    l2r = res.rank_l2r.cpu()
+    r2l = res.rank_r2l.cpu()
+    return {"l2r": metrics_from_ranks(l2r), "r2l": metrics_from_ranks(r2l), "ranks": res,
+            "launches": res.launches + launches}
+
+
 # =================================================================================================
 # materialising drop-ins
 # =================================================================================================

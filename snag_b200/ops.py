@@ -89,15 +89,38 @@ def sim_mainloop_only(X: torch.Tensor, Y: torch.Tensor, n1: int, n2: int) -> Non
     call("snag_sim_mainloop_only", ptr(X), ptr(Y), n1, n2, X.shape[1], current_stream())
 
 
+# Measurement hook: when bench.py sets this to a list, every fused-sweep launch is bracketed by CUDA events on the
+# launching stream and (name, start, end, rows, cols) is appended. None (the default) adds no events.
+SWEEP_EVENT_SINK = None
+
+
+class _SweepTimer:
+    def __init__(self, name: str, rows: int, cols: int):
+        self.args = (name, rows, cols) if SWEEP_EVENT_SINK is not None else None
+
+    def __enter__(self):
+        if self.args is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.args is not None and exc[0] is None:
+            self.e1.record()
+            SWEEP_EVENT_SINK.append((self.args[0], self.e0, self.e1, self.args[1], self.args[2]))
+
+
 def eval_rowtopk(X, Y, xn, yn, n1: int, n2: int) -> torch.Tensor:
-    """Per-chunk candidate lists [n_chunks, n1, KT] of c = 1 - d for every row of X against the rows of Y."""
+    """Per-list candidate lists [n_lists, n1, KT] of c = 1 - d for every row of X against the rows of Y."""
     _check_operand(X, "X")
     _check_operand(Y, "Y")
     _need(xn, torch.float32, "xn", 1)
     _need(yn, torch.float32, "yn", 1)
     _, nch = sim_plan(n1, n2, X.shape[1])
     part = torch.empty((nch, n1, KT), dtype=torch.float32, device=X.device)
-    call("snag_eval_rowtopk", ptr(X), ptr(Y), ptr(xn), ptr(yn), n1, n2, X.shape[1], ptr(part), current_stream())
+    with _SweepTimer("sim_kernel<EpiRowTopK>", n1, n2):
+        call("snag_eval_rowtopk", ptr(X), ptr(Y), ptr(xn), ptr(yn), n1, n2, X.shape[1], ptr(part), current_stream())
     return part
 
 
@@ -135,8 +158,10 @@ def eval_rank(X, Y, xn, yn, nv1, nv2, g_row, g_col, row_gid0: int, col_gid0: int
         _, nch = sim_plan(n1, n2, X.shape[1])
         t3v = torch.empty((nch, n1, 4), dtype=torch.float32, device=X.device)
         t3i = torch.empty((nch, n1, 4), dtype=torch.int32, device=X.device)
-    call("snag_eval_rank", ptr(X), ptr(Y), ptr(xn), ptr(yn), ptr(nv1), ptr(nv2), ptr(g_row), ptr(g_col), row_gid0,
-         col_gid0, n1, n2, X.shape[1], int(use_csls), ptr(cnt_row), ptr(cnt_col), ptr(t3v), ptr(t3i), current_stream())
+    with _SweepTimer("sim_kernel<EpiRank>", n1, n2):
+        call("snag_eval_rank", ptr(X), ptr(Y), ptr(xn), ptr(yn), ptr(nv1), ptr(nv2), ptr(g_row), ptr(g_col), row_gid0,
+             col_gid0, n1, n2, X.shape[1], int(use_csls), ptr(cnt_row), ptr(cnt_col), ptr(t3v), ptr(t3i),
+             current_stream())
     return t3v, t3i
 
 
