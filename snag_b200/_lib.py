@@ -34,11 +34,12 @@ _SIGNATURES = {
     "snag_pair_score": [_vp, _vp, _i32, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp],
     "snag_eval_rank": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp],
     "snag_top3_merge": [_vp, _vp, _i32, _i64, _vp, _vp, _vp],
+    "snag_csls_sim": [_vp, _i64, _i64, _i64, _i32, _vp, _i64, _vp, _vp, _vp, _vp],
     "snag_icl_rowsum": [_vp, _vp, _i32, _i32, _i32, _f32, _vp, _vp, _vp],
     "snag_icl_finalize": [_vp, _i32, _i32, _i32, _vp, _f32, _vp, _vp, _vp],
     "snag_icl_bwd_logits": [_vp, _vp, _i32, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _vp],
 }
-EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["snag_error_string"])
+EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["snag_error_string", "snag_csls_workspace_bytes"])
 
 _lib = None
 
@@ -63,6 +64,8 @@ def load() -> C.CDLL:
         fn.restype = C.c_int
     lib.snag_error_string.argtypes = [C.c_int]
     lib.snag_error_string.restype = C.c_char_p
+    lib.snag_csls_workspace_bytes.argtypes = [_i64, _i64]
+    lib.snag_csls_workspace_bytes.restype = _i64
     _lib = lib
     return lib
 

@@ -97,6 +97,12 @@ int snag_top3_merge(const float* val, const int32_t* idx, int32_t n_lists, int64
   return launch_top3_merge(val, idx, n_lists, n_rows, oval, oidx, S(stream));
 }
 
+int64_t snag_csls_workspace_bytes(int64_t n1, int64_t n2) { return csls_workspace_floats(n1, n2) * 4; }
+int snag_csls_sim(const float* sim, int64_t n1, int64_t n2, int64_t ld, int32_t k, float* out, int64_t ld_out, float* nv1,
+                  float* nv2, void* workspace, void* stream) {
+  return launch_csls_sim(sim, n1, n2, ld, k, out, ld_out, nv1, nv2, reinterpret_cast<float*>(workspace), S(stream));
+}
+
 int snag_icl_rowsum(const uint16_t* X, const uint16_t* Y, int32_t B, int32_t Bp, int32_t Dpad, float inv_tau,
                     float* rowsum_part, float* pos, void* stream) {
   return launch_icl_rowsum(BF(X), BF(Y), B, Bp, Dpad, inv_tau, rowsum_part, pos, S(stream));

@@ -356,9 +356,99 @@ __global__ void icl_finalize_kernel(const float* __restrict__ rowsum_part, int n
   nll[i] = l - pos[i] * inv_tau;
 }
 
+// ------------------------------------------------------------------------------------------------
+// a9  csls_sim on a MATERIALISED similarity matrix (src/utils.py:417-435) — the drop-in that must take and
+// return an [n1, n2] fp32 matrix. Three bandwidth passes:
+//   rows : one warp per row, lanes stride the row (coalesced); each lane keeps its KT largest -> part_r[32][n1][KT]
+//   cols : one thread per column per row slab (consecutive threads = consecutive columns, coalesced)
+//          -> part_c[slabs][n2][KT]
+//   (topk_merge_mean_kernel reduces both to nv1 / nv2, largest-first fp32 sum / k)
+//   apply: out = (2*sim - nv1[i]) - nv2[j], float4 wide
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void topk_insert(float (&top)[KT_LIST], float v) {
+  if (v > top[0]) {
+    top[0] = v;
+#pragma unroll
+    for (int t = 0; t < KT_LIST - 1; ++t) {
+      const float lo = fminf(top[t], top[t + 1]), hi = fmaxf(top[t], top[t + 1]);
+      top[t] = lo;
+      top[t + 1] = hi;
+    }
+  }
+}
+__global__ void __launch_bounds__(256) matrix_row_topk_kernel(const float* __restrict__ sim, long long n1, long long n2,
+                                                              long long ld, float* __restrict__ part) {
+  const long long row = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= n1) return;
+  float top[KT_LIST];
+#pragma unroll
+  for (int t = 0; t < KT_LIST; ++t) top[t] = -INFINITY;
+  const float* r = sim + row * ld;
+  for (long long j = lane; j < n2; j += 32) topk_insert(top, __ldg(r + j));
+  float4* o = reinterpret_cast<float4*>(part + (static_cast<long long>(lane) * n1 + row) * KT_LIST);
+#pragma unroll
+  for (int q = 0; q < KT_LIST / 4; ++q) o[q] = make_float4(top[4 * q], top[4 * q + 1], top[4 * q + 2], top[4 * q + 3]);
+}
+__global__ void __launch_bounds__(128) matrix_col_topk_kernel(const float* __restrict__ sim, long long n1, long long n2,
+                                                              long long ld, int rows_per_slab, float* __restrict__ part) {
+  const long long col = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (col >= n2) return;
+  const long long r0 = static_cast<long long>(blockIdx.y) * rows_per_slab;
+  const long long r1 = min(r0 + rows_per_slab, n1);
+  float top[KT_LIST];
+#pragma unroll
+  for (int t = 0; t < KT_LIST; ++t) top[t] = -INFINITY;
+  for (long long i = r0; i < r1; ++i) topk_insert(top, __ldg(sim + i * ld + col));
+  float4* o = reinterpret_cast<float4*>(part + (static_cast<long long>(blockIdx.y) * n2 + col) * KT_LIST);
+#pragma unroll
+  for (int q = 0; q < KT_LIST / 4; ++q) o[q] = make_float4(top[4 * q], top[4 * q + 1], top[4 * q + 2], top[4 * q + 3]);
+}
+__global__ void __launch_bounds__(256) csls_apply_kernel(const float* __restrict__ sim, const float* __restrict__ nv1,
+                                                         const float* __restrict__ nv2, float* __restrict__ out, long long n1,
+                                                         long long n2, long long ld, long long ld_out) {
+  const long long total = n1 * n2;
+  for (long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; e < total;
+       e += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long i = e / n2, j = e - i * n2;
+    const float u = __fmaf_rn(2.0f, __ldg(sim + i * ld + j), -__ldg(nv1 + i));
+    out[i * ld_out + j] = __fsub_rn(u, __ldg(nv2 + j));
+  }
+}
+
 // ================================================================================================
 // host launchers
 // ================================================================================================
+static inline int grid_for(long long work_items, int block, int num_sms, int ctas_per_sm);
+static int csls_col_slabs(long long n1) {
+  long long s = (n1 + 255) / 256;          // >= 256 rows per slab
+  if (s > 64) s = 64;
+  if (s < 1) s = 1;
+  return static_cast<int>(s);
+}
+long long csls_workspace_floats(long long n1, long long n2) {
+  return (32 * n1 + csls_col_slabs(n1) * n2) * KT_LIST;
+}
+int launch_csls_sim(const float* sim, long long n1, long long n2, long long ld, int k, float* out, long long ld_out,
+                    float* nv1, float* nv2, float* workspace, cudaStream_t st) {
+  if (!sim || !nv1 || !nv2 || !workspace || n1 <= 0 || n2 <= 0 || ld < n2) return SNAG_ERR_ARG;
+  if (k < 1 || k > KT_LIST || k > n1 || k > n2) return SNAG_ERR_SHAPE;
+  if (reinterpret_cast<uintptr_t>(workspace) & 15) return SNAG_ERR_ALIGN;
+  float* part_r = workspace;
+  float* part_c = workspace + 32 * n1 * KT_LIST;
+  const int slabs = csls_col_slabs(n1);
+  const int rows_per_slab = static_cast<int>((n1 + slabs - 1) / slabs);
+  matrix_row_topk_kernel<<<static_cast<unsigned>((n1 * 32 + 255) / 256), 256, 0, st>>>(sim, n1, n2, ld, part_r);
+  matrix_col_topk_kernel<<<dim3(static_cast<unsigned>((n2 + 127) / 128), slabs), 128, 0, st>>>(sim, n1, n2, ld, rows_per_slab, part_c);
+  topk_merge_mean_kernel<<<static_cast<int>((n1 + 127) / 128), 128, 0, st>>>(part_r, 32, n1, k, nv1, nullptr);
+  topk_merge_mean_kernel<<<static_cast<int>((n2 + 127) / 128), 128, 0, st>>>(part_c, slabs, n2, k, nv2, nullptr);
+  if (out) {
+    const int g = grid_for(n1 * n2, 256, num_sms(), 8);
+    csls_apply_kernel<<<g, 256, 0, st>>>(sim, nv1, nv2, out, n1, n2, ld, ld_out);
+  }
+  return static_cast<int>(cudaGetLastError());
+}
+
 static inline int grid_for(long long work_items, int block, int num_sms, int ctas_per_sm) {
   long long g = (work_items + block - 1) / block;
   const long long cap = static_cast<long long>(num_sms) * ctas_per_sm;

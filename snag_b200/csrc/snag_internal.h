@@ -41,6 +41,10 @@ int launch_top3_merge(const float* val, const int* idx, int n_lists, long long n
 int launch_icl_finalize(const float* rowsum_part, int n_chunks, int B, int Bp, const float* pos, float inv_tau, float* lse,
                         float* nll, cudaStream_t st);
 
+long long csls_workspace_floats(long long n1, long long n2);
+int launch_csls_sim(const float* sim, long long n1, long long n2, long long ld, int k, float* out, long long ld_out,
+                    float* nv1, float* nv2, float* workspace, cudaStream_t st);
+
 // ---- tcgen05 similarity sweeps (sim_kernels.cu)
 int launch_sim_null(const __nv_bfloat16* X, const __nv_bfloat16* Y, int n1, int n2, int Dpad, cudaStream_t st);
 int launch_sim_write(const __nv_bfloat16* X, const __nv_bfloat16* Y, const float* xn, const float* yn, int n1, int n2,

@@ -337,3 +337,10 @@ def pairwise_distances(x: torch.Tensor, y: torch.Tensor | None = None) -> torch.
         Y, yn = _cuda_ops.prep_bf16(y, None, normalize=False)
         n2 = y.shape[0]
     return _cuda_ops.sim_write(X, Y, xn, yn, x.shape[0], n2, mode=1)
+
+
+def csls_sim(sim_mat: torch.Tensor, k: int) -> torch.Tensor:
+    """Drop-in for src/utils.py:417-435 on a materialised similarity matrix: 2*sim - mean(topk rows) - mean(topk cols).
+    Bit-exact against the oracle for the same input (top-k selection, largest-first fp32 mean, two fp32 ops)."""
+    out, _, _ = _cuda_ops.csls_sim_matrix(sim_mat.contiguous().float(), int(k))
+    return out

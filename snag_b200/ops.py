@@ -175,6 +175,22 @@ def top3_merge(val: torch.Tensor, idx: torch.Tensor):
     return oval, oidx
 
 
+def csls_sim_matrix(sim: torch.Tensor, k: int, want_out: bool = True):
+    """csls_sim on a materialised fp32 matrix: returns (out or None, nv1, nv2)."""
+    _need(sim, torch.float32, "sim_mat", 2)
+    n1, n2 = sim.shape
+    if k > n1 or k > n2:
+        raise RuntimeError("selected index k out of range")          # torch.topk's error in the reference
+    if not 1 <= k <= KT:
+        raise SnagError(f"csls_k={k} unsupported: at most {KT} neighbours")
+    ws = torch.empty((_lib.load().snag_csls_workspace_bytes(n1, n2) // 4,), dtype=torch.float32, device=sim.device)
+    nv1 = torch.empty((n1,), dtype=torch.float32, device=sim.device)
+    nv2 = torch.empty((n2,), dtype=torch.float32, device=sim.device)
+    out = torch.empty_like(sim) if want_out else None
+    call("snag_csls_sim", ptr(sim), n1, n2, sim.stride(0), k, ptr(out), n2, ptr(nv1), ptr(nv2), ptr(ws), current_stream())
+    return out, nv1, nv2
+
+
 # ------------------------------------------------------------------------------------------------ ICL
 def icl_side(X: torch.Tensor, Y: torch.Tensor, B: int, Bp: int, inv_tau: float):
     """Row log-sum-exp and NLL of one side of the ICL loss. X [Bp, Dpad], Y [2*Bp, Dpad]."""
