@@ -214,3 +214,32 @@ def test_full_size_rank_counts_against_materialised(cuda_device, c2_problem):
     lt = (dist < g[:, None]).sum(1).int()
     ltc = (dist < g[None, :]).sum(0).int()
     assert (lt == res.rank_l2r).float().mean() > 0.9995 and (ltc == res.rank_r2l).float().mean() > 0.9995
+
+
+@pytest.mark.parametrize("n1,n2,k", [(300, 421, 10), (1000, 1000, 3), (257, 96, 16), (2049, 1500, 1)])
+def test_csls_sim_dropin_bitwise(cuda_device, n1, n2, k):
+    """csls_sim on a materialised matrix (src/utils.py:417-435): selection + largest-first fp32 mean + two fp32 ops,
+    so the result is bit-identical to the oracle for the same input matrix."""
+    rng = np.random.RandomState(n1 + n2)
+    sim = rng.randn(n1, n2).astype(np.float32)
+    sim[5, :7] = sim[5, 0]                      # ties inside a row do not matter for a top-k of VALUES
+    got = evaluate.csls_sim(torch.from_numpy(sim).to(cuda_device), k)
+    ref, nv1, nv2 = oracle.csls_sim(sim, k, return_nv=True)
+    np.testing.assert_array_equal(got.cpu().numpy(), ref)
+    _, g1, g2 = ops.csls_sim_matrix(torch.from_numpy(sim).to(cuda_device), k, want_out=False)
+    np.testing.assert_array_equal(g1.cpu().numpy(), nv1)
+    np.testing.assert_array_equal(g2.cpu().numpy(), nv2)
+    with pytest.raises(RuntimeError):
+        evaluate.csls_sim(torch.from_numpy(sim[:4, :4].copy()).to(cuda_device), 5)     # k > n, as torch.topk raises
+
+
+def test_reference_call_sequence_materialised(cuda_device):
+    """main.py:386-393 exactly as the reference writes it, through the two materialising drop-ins."""
+    fx = load_golden("eval_n384_d96_k10")
+    x = torch.from_numpy(fx["x"]).to(cuda_device)
+    y = torch.from_numpy(fx["y"]).to(cuda_device)
+    distance = evaluate.pairwise_distances(x, y)
+    distance = 1 - evaluate.csls_sim(1 - distance, 10)
+    d = distance.cpu()
+    ranks = [(torch.sort(d[i], stable=True)[1] == i).nonzero().item() for i in range(d.shape[0])]
+    np.testing.assert_array_equal(np.asarray(ranks, np.int32), fx["rank_l2r"])

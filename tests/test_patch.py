@@ -1,0 +1,134 @@
+"""The drop-in boundary: signatures of the mirrors equal the reference's (checked against /root/reference when it is
+present, i.e. in the build container), patch() rebinds every name main.py / model/SNAG.py use, and Runner._test
+reproduces the reference's log lines, CSV and side effects (GPU)."""
+from __future__ import annotations
+
+import inspect
+import logging
+import os
+import sys
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle
+
+REF = "/root/reference/SNAG_MMEA"
+needs_ref = pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not present on this machine")
+
+
+def _sig(f):
+    """Parameter names, kinds and defaults (annotations do not matter to a caller)."""
+    return [(p.name, p.kind, p.default) for p in inspect.signature(f).parameters.values()]
+
+
+@needs_ref
+def test_signatures_match_reference():
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    from refshim import load_reference
+    ref = load_reference()
+    import importlib
+    from snag_b200 import evaluate, loss, noise
+    for name in ("icl_loss", "ial_loss", "CustomMultiLossLayer"):
+        r, m = getattr(ref.loss, name), getattr(loss, name)
+        assert _sig(r.__init__) == _sig(m.__init__), name
+        assert _sig(r.forward) == _sig(m.forward), name
+    assert _sig(ref.utils.pairwise_distances) == _sig(evaluate.pairwise_distances)
+    assert _sig(ref.utils.csls_sim) == _sig(evaluate.csls_sim)
+    ref_snag = importlib.import_module("model.SNAG").SNAG
+    for name in ("add_noise_to_embeddings", "get_mean_std", "update_noise"):
+        assert _sig(getattr(ref_snag, name)) == _sig(getattr(noise, name)), name
+    enc = importlib.import_module("model.SNAG_tools").MultiModalEncoder
+    assert _sig(enc.forward) == _sig(noise.encoder_forward)
+
+
+@needs_ref
+def test_patch_rebinds_reference_names(monkeypatch):
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    from refshim import load_reference
+    load_reference()
+    import importlib
+    from snag_b200 import evaluate, loss, noise, patch, runner
+    mods = {n: importlib.import_module(n) for n in ("model.SNAG_loss", "model.SNAG", "model.SNAG_tools", "src.utils")}
+    saved = {(n, k): v for n, m in mods.items() for k, v in vars(m).items()}
+    snag_cls, enc_cls = mods["model.SNAG"].SNAG, mods["model.SNAG_tools"].MultiModalEncoder
+    saved_cls = {k: getattr(snag_cls, k) for k in ("add_noise_to_embeddings", "get_mean_std", "update_noise")}
+    saved_fwd = enc_cls.forward
+    fake_main = types.ModuleType("main")
+    fake_main.Runner = type("Runner", (), {"_test": lambda self: None})
+    try:
+        done = patch.patch(fake_main)
+        assert mods["model.SNAG"].icl_loss is loss.icl_loss and mods["model.SNAG_loss"].ial_loss is loss.ial_loss
+        assert mods["src.utils"].pairwise_distances is evaluate.pairwise_distances
+        assert mods["model.SNAG"].pairwise_distances is evaluate.pairwise_distances
+        assert snag_cls.update_noise is noise.update_noise and enc_cls.forward is noise.encoder_forward
+        assert fake_main.Runner._test is runner._test and fake_main.csls_sim is evaluate.csls_sim
+        assert len(done) >= 12
+    finally:
+        for (n, k), v in saved.items():
+            setattr(mods[n], k, v)
+        for k, v in saved_cls.items():
+            setattr(snag_cls, k, v)
+        enc_cls.forward = saved_fwd
+
+
+class _Capture(logging.Handler):
+    def __init__(self):
+        super().__init__()
+        self.lines = []
+
+    def emit(self, record):
+        self.lines.append(record.getMessage())
+
+
+@pytest.mark.gpu
+def test_runner_test_mirror(cuda_device, tmp_path):
+    from snag_b200 import runner
+    rng = np.random.RandomState(3)
+    N, n, d = 900, 400, 128
+    emb = rng.randn(N, d).astype(np.float32)
+    left = rng.permutation(N // 2)[:n]
+    right = N // 2 + rng.permutation(N // 2)[:n]
+    emb[right] = emb[left] + 0.9 * rng.randn(n, d).astype(np.float32)
+    emb_t = torch.from_numpy(emb).to(cuda_device)
+
+    class FakeModel(torch.nn.Module):
+        def joint_emb_generat(self):
+            return emb_t, None
+
+    logger = logging.getLogger("snag_test_runner")
+    logger.setLevel(logging.INFO)
+    cap = _Capture()
+    logger.addHandler(cap)
+    acc_hist = [0.0]
+    me = types.SimpleNamespace(
+        args=types.SimpleNamespace(model_name="SNAG", distance=2, csls=True, csls_k=3, data_path=str(tmp_path),
+                                   data_choice="DBP15K", w_name=False, w_char=False),
+        model=FakeModel(), logger=logger, loss_item=0.1234, epoch=7, early_stop_count=5, early_stop_init=50,
+        loss_log=types.SimpleNamespace(acc=acc_hist, update_acc=lambda v: acc_hist.append(v)), best_model_wts=None)
+    tl, tr = torch.from_numpy(left).to(cuda_device), torch.from_numpy(right).to(cuda_device)
+    runner._test(me, tl, tr, last_epoch=False)
+    x = oracle.bf16_round(oracle.normalize_rows(emb[left]))
+    y = oracle.bf16_round(oracle.normalize_rows(emb[right]))
+    ref = oracle.align_eval(x, y, True, 3)
+    m = oracle.metrics(ref["rank_l2r"])
+    mr = oracle.metrics(ref["rank_r2l"])
+    # the device normalisation may round a handful of elements differently from numpy: compare the formatted lines
+    want_l2r = f"Ep 7 | l2r: acc of top [1, 10, 50] = {m['acc']}, mr = {m['mr']:.3f}, mrr = {m['mrr']:.3f}, Loss = 0.1234"
+    want_r2l = f"Ep 7 | r2l: acc of top [1, 10, 50] = {mr['acc']}, mr = {mr['mr']:.3f}, mrr = {mr['mrr']:.3f}, Loss = 0.1234"
+    assert cap.lines[0] == want_l2r and cap.lines[1] == want_r2l
+    assert cap.lines[2].startswith("Best model update in Ep 7: MRR from [0.0] --> [")
+    assert me.early_stop_count == 50 and len(acc_hist) == 2 and me.best_model_wts is not None
+    # last epoch: Res line + prediction CSV, no best-model update
+    cap.lines.clear()
+    runner._test(me, tl, tr, last_epoch=True, save_name="unit")
+    assert cap.lines[2] == f"Res:[{m['acc'][0]}\t{m['acc'][1]}\t{m['mrr']:.3f}]"
+    assert me.early_stop_count == 49
+    rows = open(os.path.join(str(tmp_path), "SNAG", "unit_pred", "DBP15K_pred.txt")).read().strip().splitlines()
+    assert rows[0] == "idx,rank,query_id,gt_id,ret1,ret2,ret3" and len(rows) == n + 1
+    got = np.array([[int(v) for v in r.split(",")] for r in rows[1:]])
+    assert (got[:, 1] == ref["rank_l2r"]).mean() > 0.99
+    assert (got[:, 2] == left).all() and (got[:, 3] == right).all()
+    assert (got[:, 4:7] == right[ref["top3"]]).mean() > 0.99
