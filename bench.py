@@ -126,6 +126,7 @@ def cpu_port_sample(n_s: int, d: int, k: int, sigma: float, steps: int, warmup: 
     """Times the oracle port (oracle/snag_oracle.c, all host threads) on an n_s x n_s sub-problem of the workload."""
     import numpy as np
     from oracle import oracle
+    oracle.set_threads()                 # all host cores (torchrun exports OMP_NUM_THREADS=1)
     rng = np.random.RandomState(SEED)
     centres = rng.randn(64, d).astype(np.float32)
     x = rng.randn(n_s, d).astype(np.float32) + centres[rng.randint(0, 64, n_s)]
@@ -151,6 +152,7 @@ def reference_steps_sample(n_s: int, d: int, k: int, sigma: float):
     the same torch CPU calls, timed once on a smaller sample — reported beside the port for context."""
     import numpy as np
     import torch
+    torch.set_num_threads(os.cpu_count() or 1)
     rng = np.random.RandomState(SEED)
     x = torch.from_numpy(rng.randn(n_s, d).astype(np.float32))
     y = x + sigma * torch.from_numpy(rng.randn(n_s, d).astype(np.float32))

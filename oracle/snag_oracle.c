@@ -44,6 +44,15 @@ int oracle_max_threads(void) {
 #endif
 }
 
+/* torchrun exports OMP_NUM_THREADS=1; the CPU legs of bench.py ask for all host threads explicitly */
+void oracle_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 /* xn[i] = fl32( sum_k fp64 x_ik^2 )  in index order */
 void oracle_norm2(const float* x, int64_t n, int64_t d, int64_t ld, float* xn) {
 #pragma omp parallel for schedule(static)
