@@ -94,6 +94,27 @@ int snag_sim_mainloop_only(const uint16_t* X, const uint16_t* Y, int32_t n1, int
  * snag_sim_plan(n1, n2, Dpad)). Call with X and Y swapped for the column neighbourhoods. */
 int snag_eval_rowtopk(const uint16_t* X, const uint16_t* Y, const float* xn, const float* yn, int32_t n1, int32_t n2,
                       int32_t Dpad, float* part, void* stream);
+/* Two-sweep variant: CSLS neighbourhoods of BOTH directions from ONE pass over S (replaces the second
+ * snag_eval_rowtopk call with swapped operands). Rows: as snag_eval_rowtopk (part). Columns: every element with
+ * c_ij >= colthr[j] is appended, as a (j, c) pair, to the private stream of the CTA that computed it
+ * (stream[cta][cta_cap] 8-byte entries, stream_cnt[cta] entries produced; both sized for snag_num_sms() CTAs,
+ * stream_cnt zeroed by the caller). colthr / colb come from snag_col_threshold applied to the merged candidate lists
+ * of a PRE-PASS snag_eval_rowtopk(Y, X_sample, ...) over a random sample of the rows of X: the k-th largest c of the
+ * sample is a lower bound of the final k-th largest, so no neighbour is ever missed; a sample of m rows leaves
+ * ~k*n1/m candidates per column. Then: snag_col_cand_hist (hist[j] = candidates of column j; sets *overflow if a
+ * stream was full), offs = exclusive prefix sum of hist (caller), snag_col_cand_scatter (vals[offs[j] + ...]),
+ * snag_col_cand_finalize (nv[j] = mean of the k largest; sets *overflow if a column has fewer than k). On overflow
+ * fall back to the swapped snag_eval_rowtopk sweep. hist / cursor / overflow are zeroed by the caller. */
+int snag_eval_rowcoltopk(const uint16_t* X, const uint16_t* Y, const float* xn, const float* yn, int32_t n1, int32_t n2,
+                         int32_t Dpad, float* part, const float* colthr, const float* colb, uint64_t* stream,
+                         int32_t* stream_cnt, int32_t cta_cap, void* stream_);
+int snag_col_threshold(const float* cand, int64_t n, int32_t k, const float* yn, float* colthr, float* colb, void* stream);
+int snag_col_cand_hist(const uint64_t* stream, const int32_t* stream_cnt, int32_t n_ctas, int32_t cta_cap, int32_t* hist,
+                       int32_t* overflow, void* stream_);
+int snag_col_cand_scatter(const uint64_t* stream, const int32_t* stream_cnt, int32_t n_ctas, int32_t cta_cap,
+                          const int64_t* offs, int32_t* cursor, float* vals, void* stream_);
+int snag_col_cand_finalize(const int64_t* offs, const int32_t* hist, const float* vals, int64_t n, int32_t k, float* nv,
+                           int32_t* overflow, void* stream);
 /* merge n_lists candidate lists per row ([n_lists][n_rows][SNAG_KT]); nv[row] = mean of the k largest
  * (may be NULL); cand_out [n_rows][SNAG_KT] = merged list (may be NULL) for the cross-GPU exchange. */
 int snag_topk_merge_mean(const float* part, int32_t n_lists, int64_t n_rows, int32_t k, float* nv, float* cand_out,

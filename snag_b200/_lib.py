@@ -30,6 +30,11 @@ _SIGNATURES = {
     "snag_sim_write": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _i64, _vp],
     "snag_sim_mainloop_only": [_vp, _vp, _i32, _i32, _i32, _vp],
     "snag_eval_rowtopk": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp],
+    "snag_eval_rowcoltopk": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _vp],
+    "snag_col_threshold": [_vp, _i64, _i32, _vp, _vp, _vp, _vp],
+    "snag_col_cand_hist": [_vp, _vp, _i32, _i32, _vp, _vp, _vp],
+    "snag_col_cand_scatter": [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp],
+    "snag_col_cand_finalize": [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp],
     "snag_topk_merge_mean": [_vp, _i32, _i64, _i32, _vp, _vp, _vp],
     "snag_pair_score": [_vp, _vp, _i32, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp],
     "snag_eval_rank": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp],

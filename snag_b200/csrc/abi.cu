@@ -113,6 +113,29 @@ int snag_icl_finalize(const float* rowsum_part, int32_t n_lists, int32_t B, int3
   return launch_icl_finalize(rowsum_part, n_lists, B, Bp, pos, inv_tau, lse, nll, S(stream));
 }
 
+int snag_eval_rowcoltopk(const uint16_t* X, const uint16_t* Y, const float* xn, const float* yn, int32_t n1, int32_t n2,
+                         int32_t Dpad, float* part, const float* colthr, const float* colb, uint64_t* stream,
+                         int32_t* stream_cnt, int32_t cta_cap, void* stream_) {
+  return launch_eval_rowcoltopk(BF(X), BF(Y), xn, yn, n1, n2, Dpad, part, colthr, colb, reinterpret_cast<uint2*>(stream),
+                                stream_cnt, cta_cap, S(stream_));
+}
+int snag_col_threshold(const float* cand, int64_t n, int32_t k, const float* yn, float* colthr, float* colb, void* stream) {
+  return launch_col_threshold(cand, n, k, yn, colthr, colb, S(stream));
+}
+int snag_col_cand_hist(const uint64_t* stream, const int32_t* stream_cnt, int32_t n_ctas, int32_t cta_cap, int32_t* hist,
+                       int32_t* overflow, void* stream_) {
+  return launch_cand_hist(reinterpret_cast<const uint2*>(stream), stream_cnt, n_ctas, cta_cap, hist, overflow, S(stream_));
+}
+int snag_col_cand_scatter(const uint64_t* stream, const int32_t* stream_cnt, int32_t n_ctas, int32_t cta_cap,
+                          const int64_t* offs, int32_t* cursor, float* vals, void* stream_) {
+  return launch_cand_scatter(reinterpret_cast<const uint2*>(stream), stream_cnt, n_ctas, cta_cap,
+                             reinterpret_cast<const long long*>(offs), cursor, vals, S(stream_));
+}
+int snag_col_cand_finalize(const int64_t* offs, const int32_t* hist, const float* vals, int64_t n, int32_t k, float* nv,
+                           int32_t* overflow, void* stream) {
+  return launch_col_cand_finalize(reinterpret_cast<const long long*>(offs), hist, vals, n, k, nv, overflow, S(stream));
+}
+
 int snag_icl_bwd_logits(const uint16_t* X, const uint16_t* Y, int32_t B, int32_t Bp, int32_t Dpad, float inv_tau,
                         const float* cr, const float* cc, const float* dg, uint16_t* G, void* stream) {
   return launch_icl_bwd_logits(BF(X), BF(Y), B, Bp, Dpad, inv_tau, cr, cc, dg, reinterpret_cast<__nv_bfloat16*>(G),

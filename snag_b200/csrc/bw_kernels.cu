@@ -416,9 +416,98 @@ __global__ void __launch_bounds__(256) csls_apply_kernel(const float* __restrict
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Column neighbourhoods of the two-sweep evaluation (see EpiRowColTopK in simgemm.cuh)
+//   col_threshold : from the merged sample lists (ascending, KT per column) take the k-th largest c as the
+//                   admission threshold, lowered by 2e-6 so that a last-bit difference between the sample
+//                   pre-pass and the main sweep can never drop a true neighbour; b_j is its s-space form.
+//   col_cand_finalize : nv[j] = mean of the k largest candidates of column j (largest-first fp32 sum / k);
+//                   sets *overflow if a column received more candidates than its buffer holds.
+// ------------------------------------------------------------------------------------------------
+__global__ void col_threshold_kernel(const float* __restrict__ cand, long long n, int k, const float* __restrict__ yn,
+                                     float* __restrict__ colthr, float* __restrict__ colb) {
+  const long long j = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (j >= n) return;
+  const float kth = cand[j * KT_LIST + (KT_LIST - k)];      // lists are ascending: index KT-k is the k-th largest
+  const float thr = kth - 2e-6f;                             // -inf stays -inf: everything is admitted
+  colthr[j] = thr;
+  colb[j] = __fmaf_rn(0.5f, __fadd_rn(__fadd_rn(yn[j], -1.0f), thr), -4e-6f);
+}
+// The fused sweep leaves one candidate stream per CTA: (column, c) pairs in arrival order. Three bandwidth passes
+// turn them into per-column segments (CSR) and reduce each segment to the column's neighbourhood mean:
+//   hist    : hist[col] += 1 per entry (RED, no return value)            -> host: offs = exclusive cumsum(hist)
+//   scatter : slot = cursor[col]++ ; vals[offs[col] + slot] = c
+//   finalize: nv[col] = mean of the k largest of the segment (largest-first fp32 sum / k)
+__global__ void __launch_bounds__(256) cand_hist_kernel(const uint2* __restrict__ stream, const int* __restrict__ stream_cnt,
+                                                        int cta_cap, int* __restrict__ hist, int* __restrict__ overflow) {
+  const int cta = blockIdx.y;
+  int cnt = stream_cnt[cta];
+  if (cnt > cta_cap) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(overflow, 1);
+    cnt = cta_cap;
+  }
+  const uint2* sp = stream + static_cast<long long>(cta) * cta_cap;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < cnt; e += gridDim.x * blockDim.x) atomicAdd(hist + sp[e].x, 1);
+}
+__global__ void __launch_bounds__(256) cand_scatter_kernel(const uint2* __restrict__ stream, const int* __restrict__ stream_cnt,
+                                                           int cta_cap, const long long* __restrict__ offs,
+                                                           int* __restrict__ cursor, float* __restrict__ vals) {
+  const int cta = blockIdx.y;
+  const int cnt = min(stream_cnt[cta], cta_cap);
+  const uint2* sp = stream + static_cast<long long>(cta) * cta_cap;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < cnt; e += gridDim.x * blockDim.x) {
+    const uint2 ent = sp[e];
+    const int slot = atomicAdd(cursor + ent.x, 1);
+    vals[offs[ent.x] + slot] = __uint_as_float(ent.y);
+  }
+}
+__global__ void __launch_bounds__(128) col_cand_finalize_kernel(const long long* __restrict__ offs, const int* __restrict__ hist,
+                                                                const float* __restrict__ vals, long long n, int k,
+                                                                float* __restrict__ nv, int* __restrict__ overflow) {
+  const long long j = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (j >= n) return;
+  const int cnt = hist[j];
+  if (cnt < k) atomicOr(overflow, 1);     // cannot happen with a valid threshold and no dropped entries
+  float top[KT_LIST];
+#pragma unroll
+  for (int t = 0; t < KT_LIST; ++t) top[t] = -INFINITY;
+  const float* v = vals + offs[j];
+  for (int e = 0; e < cnt; ++e) topk_insert(top, v[e]);
+  float s = 0.f;
+#pragma unroll
+  for (int t = 0; t < KT_LIST; ++t)
+    if (t < k) s = __fadd_rn(s, top[KT_LIST - 1 - t]);
+  nv[j] = __fdiv_rn(s, static_cast<float>(k));
+}
+
 // ================================================================================================
 // host launchers
 // ================================================================================================
+int launch_col_threshold(const float* cand, long long n, int k, const float* yn, float* colthr, float* colb, cudaStream_t st) {
+  if (!cand || !yn || !colthr || !colb || n <= 0) return SNAG_ERR_ARG;
+  if (k < 1 || k > KT_LIST) return SNAG_ERR_SHAPE;
+  col_threshold_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, st>>>(cand, n, k, yn, colthr, colb);
+  return static_cast<int>(cudaGetLastError());
+}
+int launch_cand_hist(const uint2* stream, const int* stream_cnt, int n_ctas, int cta_cap, int* hist, int* overflow,
+                     cudaStream_t st) {
+  if (!stream || !stream_cnt || !hist || !overflow || n_ctas < 1 || cta_cap < 1) return SNAG_ERR_ARG;
+  cand_hist_kernel<<<dim3(64, n_ctas), 256, 0, st>>>(stream, stream_cnt, cta_cap, hist, overflow);
+  return static_cast<int>(cudaGetLastError());
+}
+int launch_cand_scatter(const uint2* stream, const int* stream_cnt, int n_ctas, int cta_cap, const long long* offs,
+                        int* cursor, float* vals, cudaStream_t st) {
+  if (!stream || !stream_cnt || !offs || !cursor || !vals || n_ctas < 1 || cta_cap < 1) return SNAG_ERR_ARG;
+  cand_scatter_kernel<<<dim3(64, n_ctas), 256, 0, st>>>(stream, stream_cnt, cta_cap, offs, cursor, vals);
+  return static_cast<int>(cudaGetLastError());
+}
+int launch_col_cand_finalize(const long long* offs, const int* hist, const float* vals, long long n, int k, float* nv,
+                             int* overflow, cudaStream_t st) {
+  if (!offs || !hist || !vals || !nv || !overflow || n <= 0) return SNAG_ERR_ARG;
+  if (k < 1 || k > KT_LIST) return SNAG_ERR_SHAPE;
+  col_cand_finalize_kernel<<<static_cast<int>((n + 127) / 128), 128, 0, st>>>(offs, hist, vals, n, k, nv, overflow);
+  return static_cast<int>(cudaGetLastError());
+}
 static inline int grid_for(long long work_items, int block, int num_sms, int ctas_per_sm);
 static int csls_col_slabs(long long n1) {
   long long s = (n1 + 255) / 256;          // >= 256 rows per slab

@@ -176,6 +176,15 @@ int launch_icl_rowsum(const __nv_bfloat16* X, const __nv_bfloat16* Y, int B, int
   return launch_sim<EpiIclFwd>(X, Y, Bp, 2 * Bp, Dpad, p, st);
 }
 
+int launch_eval_rowcoltopk(const __nv_bfloat16* X, const __nv_bfloat16* Y, const float* xn, const float* yn, int n1, int n2,
+                           int Dpad, float* part, const float* colthr, const float* colb, uint2* stream, int* stream_cnt,
+                           int cta_cap, cudaStream_t st) {
+  if (!xn || !yn || !part || !colthr || !colb || !stream || !stream_cnt || cta_cap < 1) return SNAG_ERR_ARG;
+  if ((reinterpret_cast<uintptr_t>(part) & 15) || (reinterpret_cast<uintptr_t>(stream) & 7)) return SNAG_ERR_ALIGN;
+  EpiRowColTopK::Params p{xn, yn, part, colthr, colb, stream, stream_cnt, cta_cap};
+  return launch_sim<EpiRowColTopK>(X, Y, n1, n2, Dpad, p, st);
+}
+
 int launch_icl_bwd_logits(const __nv_bfloat16* X, const __nv_bfloat16* Y, int B, int Bp, int Dpad, float inv_tau,
                           const float* cr, const float* cc, const float* dg, __nv_bfloat16* G, cudaStream_t st) {
   if (!cr || !cc || !dg || !G || B <= 0 || Bp < B || (Bp % BN) != 0) return SNAG_ERR_ARG;

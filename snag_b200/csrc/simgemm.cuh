@@ -12,6 +12,8 @@
 // unit and is flushed once at the end. Units are ordered chunk-major so that the CTAs resident at any
 // time sweep the same Y chunk (sized to stay L2 resident) while each re-reads its own X row block.
 #pragma once
+#include <type_traits>
+#include <utility>
 #include "common.cuh"
 
 namespace snag {
@@ -58,8 +60,16 @@ struct EpiCtx {
   int row;       // row index inside the X view
   bool row_ok;   // row < n_rows
   int rb, chunk; // unit coordinates
+  int useq;      // sequence number of the unit within this CTA (parity selects double-buffered per-unit scratch)
   float* scratch;  // EPI_SCRATCH_BYTES of shared memory private to the epilogue warpgroup
 };
+
+// optional per-CTA hook run by the epilogue threads after their last unit: Epi::kernel_end(params, ctx)
+template <class E, class = void>
+struct HasKernelEnd : std::false_type {};
+template <class E>
+struct HasKernelEnd<E, decltype(E::kernel_end(std::declval<const typename E::Params&>(), std::declval<const EpiCtx&>()), void())>
+    : std::true_type {};
 
 template <class Epi>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -167,7 +177,9 @@ sim_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
     const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
     uint32_t as = 0, aphase = 0;
     uint32_t tile_seq = 0;
+    cx.useq = -1;
     for (int u = blockIdx.x; u < shp.n_units; u += gridDim.x) {
+      ++cx.useq;
       cx.rb = u % shp.row_blocks;
       cx.chunk = u / shp.row_blocks;
       cx.row = cx.rb * BM + cx.et;
@@ -202,6 +214,7 @@ sim_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
       }
       Epi::unit_end(ep, shp, cx, st);
     }
+    if constexpr (HasKernelEnd<Epi>::value) Epi::kernel_end(ep, cx);
   }
 
   tc_fence_before();
@@ -372,6 +385,148 @@ struct EpiRowTopK {
             }
           }
         }
+      }
+    }
+  }
+  static __device__ __forceinline__ void tile_end(const Params&, const SimShape&, const EpiCtx&, State&, int, int) {}
+  static __device__ __forceinline__ void unit_end(const Params& p, const SimShape& shp, const EpiCtx& cx, State& st) {
+    if (!cx.row_ok) return;
+    float4* o = reinterpret_cast<float4*>(p.part + (static_cast<long long>(cx.list) * shp.n_rows + cx.row) * KT);
+#pragma unroll
+    for (int t = 0; t < KT; t += 4) o[t / 4] = make_float4(st.top[t], st.top[t + 1], st.top[t + 2], st.top[t + 3]);
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Epilogue: CSLS neighbourhoods of BOTH directions in one sweep. Rows as in EpiRowTopK (registers). Columns:
+// column j's neighbourhood is the k largest c_ij over ALL rows, but a tile only sees 128 of them, so column
+// state cannot live in the CTA. Instead every element that could still belong to column j's top-k is appended
+// to a per-column candidate buffer in HBM and a tiny kernel selects the k largest afterwards:
+//   * a pre-pass over a random sample of the rows gives colthr[j] <= (final k-th largest c of column j);
+//     any row with c_ij >= colthr[j] is a candidate (a superset of the true top-k; ~k*n/m per column for a
+//     sample of m rows, whatever the data distribution);
+//   * fast path per element: s_ij > a_i + b_j with a_i = xn_i/2, b_j = (yn_j - 1 + colthr_j)/2 - margin — a
+//     conservative s-space form of that test (same rounding argument as the row pre-filter);
+//   * the 32x32 predicate bit-matrix of a warp's strip is transposed with 5 shuffles so that lane l owns
+//     column l, re-computes c exactly for the flagged rows (accumulators parked in shared memory) and appends.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t transpose32(uint32_t x, int lane) {
+#pragma unroll
+  for (int sft = 16; sft >= 1; sft >>= 1) {
+    const uint32_t m = sft == 16 ? 0x0000FFFFu : sft == 8 ? 0x00FF00FFu : sft == 4 ? 0x0F0F0F0Fu
+                                               : sft == 2 ? 0x33333333u : 0x55555555u;
+    const uint32_t y = __shfl_xor_sync(0xffffffffu, x, sft);
+    x = (lane & sft) ? ((x & ~m) | ((y >> sft) & m)) : ((x & m) | ((y << sft) & ~m));
+  }
+  return x;
+}
+
+struct EpiRowColTopK {
+  static constexpr bool kNoLoad = false;
+  struct Params {
+    const float* xn;       // [n_rows]
+    const float* yn;       // [n_cols]
+    float* part;           // [n_lists][n_rows][KT]   row candidates, as EpiRowTopK
+    const float* colthr;   // [n_cols] admission threshold of column j in c-space (from the sample pre-pass)
+    const float* colb;     // [n_cols] b_j of the s-space pre-filter
+    uint2* stream;         // [gridDim.x][cta_cap] (column, c bits) candidates appended by each CTA
+    int* stream_cnt;       // [gridDim.x] entries each CTA produced (may exceed cta_cap: overflow, entries dropped)
+    int cta_cap;
+  };
+  struct State {
+    float xn, a;
+    float top[KT];
+  };
+  // scratch per tile buffer: yn[BN], strip minima of yn [BN/32], colb[BN], colthr[BN]; then xn of the row block x2
+  static constexpr int kVecStride = 3 * BN + BN / 32;
+  static constexpr int kXnOff = 2 * kVecStride;
+  static constexpr int kCntOff = kXnOff + 2 * BM;        // int: candidates appended by this CTA so far
+  static __device__ __forceinline__ void kernel_end(const Params& p, const EpiCtx& cx) {
+    named_bar_sync(1, NUM_EPI_THREADS);
+    if (cx.tid == 0) p.stream_cnt[blockIdx.x] = *reinterpret_cast<const int*>(cx.scratch + kCntOff);
+  }
+  static __device__ __forceinline__ void unit_begin(const Params& p, const SimShape&, const EpiCtx& cx, State& st) {
+    static_assert(kCntOff + 1 <= EPI_VEC_FLOATS, "scratch too small");
+    if (cx.useq == 0 && cx.tid == 0) *reinterpret_cast<int*>(cx.scratch + kCntOff) = 0;   // ordered by the tile barrier
+    st.xn = cx.row_ok ? p.xn[cx.row] : 0.f;
+    st.a = cx.row_ok ? 0.5f * st.xn : INFINITY;          // padding rows never produce column candidates
+#pragma unroll
+    for (int t = 0; t < KT; ++t) st.top[t] = -INFINITY;
+    if (cx.wg == 0) cx.scratch[kXnOff + (cx.useq & 1) * BM + cx.et] = st.xn;   // visible after the tile barrier
+  }
+  static __device__ __forceinline__ void tile_begin(const Params& p, const SimShape& shp, const EpiCtx& cx, State&,
+                                                    int ct, int buf) {
+    static_assert(NUM_EPI_THREADS == BN, "one epilogue thread stages one column");
+    float* v_s = cx.scratch + buf * kVecStride;
+    const int col = ct * BN + cx.tid;
+    const bool ok = col < shp.n_cols;
+    const float v = ok ? p.yn[col] : INFINITY;
+    v_s[cx.tid] = v;
+    v_s[BN + BN / 32 + cx.tid] = ok ? p.colb[col] : INFINITY;
+    v_s[2 * BN + BN / 32 + cx.tid] = ok ? p.colthr[col] : INFINITY;
+    float m = v;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (cx.lane == 0) v_s[BN + (cx.tid >> 5)] = m;
+  }
+  static __device__ __forceinline__ void chunk(const Params& p, const SimShape&, const EpiCtx& cx, State& st, int ct,
+                                               int c, const uint32_t (&r)[32], int buf) {
+    const float* v_s = cx.scratch + buf * kVecStride;
+    const float* yn_s = v_s + c * 32;
+    const float* cb_s = v_s + BN + BN / 32 + c * 32;
+    const float* ct_s = v_s + 2 * BN + BN / 32 + c * 32;
+    const float tmin = __fadd_rn(st.xn, v_s[BN + c]);
+    const float thr = __fmaf_rn(0.5f, __fadd_rn(__fadd_rn(tmin, -1.0f), st.top[0]), -4e-6f);
+    uint32_t pm = 0, cm = 0;
+#pragma unroll
+    for (int q = 0; q < 32; ++q) {
+      const float s = __uint_as_float(r[q]);
+      if (s > thr) pm |= (1u << q);
+      if (s > __fadd_rn(st.a, cb_s[q])) cm |= (1u << q);
+    }
+    const uint32_t cmT = transpose32(cm, cx.lane);       // lane l: bit t set <=> row t of this warp flagged column l
+    if (__any_sync(0xffffffffu, (pm | cmT) != 0)) {
+      float* stage_w = cx.scratch + EPI_VEC_FLOATS + (cx.tid & ~31);      // this warp's 32 columns of the staging area
+      const float* xn_w = cx.scratch + kXnOff + (cx.useq & 1) * BM + (cx.et & ~31);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {      // two half-strips: the staging area holds 16 values per thread
+        uint32_t ph = (pm >> (16 * h)) & 0xffffu;
+        const uint32_t ch = ((cx.lane >> 4) == h) ? cmT : 0u;
+        if (!__any_sync(0xffffffffu, (ph | ch) != 0)) continue;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) stage_w[q * NUM_EPI_THREADS + cx.lane] = __uint_as_float(r[16 * h + q]);
+        __syncwarp();
+        while (ph != 0) {                                  // row direction: own staged values
+          const int q = __ffs(ph) - 1;
+          ph &= ph - 1;
+          const float x = __fsub_rn(1.0f, sqdist_from_dot(stage_w[q * NUM_EPI_THREADS + cx.lane], st.xn, yn_s[16 * h + q]));
+          if (x > st.top[0]) {
+            st.top[0] = x;
+#pragma unroll
+            for (int t = 0; t < KT - 1; ++t) {
+              const float lo = fminf(st.top[t], st.top[t + 1]);
+              const float hi = fmaxf(st.top[t], st.top[t + 1]);
+              st.top[t] = lo;
+              st.top[t + 1] = hi;
+            }
+          }
+        }
+        uint32_t cmask = ch;                               // column direction: lane l owns column l of the strip
+        const int col = ct * BN + c * 32 + cx.lane;
+        while (cmask != 0) {
+          const int t = __ffs(cmask) - 1;
+          cmask &= cmask - 1;
+          const float s = stage_w[(cx.lane & 15) * NUM_EPI_THREADS + t];
+          const float x = __fsub_rn(1.0f, sqdist_from_dot(s, xn_w[t], yn_s[cx.lane]));
+          if (x >= ct_s[cx.lane]) {
+            // append to this CTA's private stream: a shared-memory counter hands out the slot (no global-atomic
+            // round trip on the epilogue's critical path); a later pass buckets the stream by column
+            const int slot = atomicAdd(reinterpret_cast<int*>(cx.scratch + kCntOff), 1);
+            if (slot < p.cta_cap)
+              p.stream[static_cast<long long>(blockIdx.x) * p.cta_cap + slot] = make_uint2(static_cast<uint32_t>(col), __float_as_uint(x));
+          }
+        }
+        __syncwarp();
       }
     }
   }

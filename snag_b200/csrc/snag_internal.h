@@ -57,6 +57,16 @@ int launch_eval_rank(const __nv_bfloat16* X, const __nv_bfloat16* Y, const float
 int launch_icl_rowsum(const __nv_bfloat16* X, const __nv_bfloat16* Y, int B, int Bp, int Dpad, float inv_tau,
                       float* rowsum_part, float* pos, cudaStream_t st);
 
+int launch_eval_rowcoltopk(const __nv_bfloat16* X, const __nv_bfloat16* Y, const float* xn, const float* yn, int n1, int n2,
+                           int Dpad, float* part, const float* colthr, const float* colb, uint2* stream, int* stream_cnt,
+                           int cta_cap, cudaStream_t st);
+int launch_col_threshold(const float* cand, long long n, int k, const float* yn, float* colthr, float* colb, cudaStream_t st);
+int launch_cand_hist(const uint2* stream, const int* stream_cnt, int n_ctas, int cta_cap, int* hist, int* overflow,
+                     cudaStream_t st);
+int launch_cand_scatter(const uint2* stream, const int* stream_cnt, int n_ctas, int cta_cap, const long long* offs,
+                        int* cursor, float* vals, cudaStream_t st);
+int launch_col_cand_finalize(const long long* offs, const int* hist, const float* vals, long long n, int k, float* nv,
+                             int* overflow, cudaStream_t st);
 int launch_icl_bwd_logits(const __nv_bfloat16* X, const __nv_bfloat16* Y, int B, int Bp, int Dpad, float inv_tau,
                           const float* cr, const float* cc, const float* dg, __nv_bfloat16* G, cudaStream_t st);
 

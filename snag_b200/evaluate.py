@@ -54,7 +54,24 @@ def shard_bounds(n: int, world: int, rank: int, align: int = 256) -> tuple[int, 
     return c0, c1
 
 
-def _align_ranks_steps(be, X, Y, xn, yn, n: int, csls_k: int, use_csls: bool, want_top3: bool, world: int, rank: int):
+TWO_SWEEP_MIN_N = 65536     # below this the sample pre-pass costs more than the sweep it saves
+
+
+def two_sweep_plan(n: int, k: int) -> tuple[int, int] | None:
+    """(sample size m, candidate-stream capacity per CTA) of the two-sweep CSLS path, or None when n is too small.
+    A random sample of m sources leaves on average k*n/m candidates per target (for any data distribution: the
+    rows are exchangeable), i.e. k*n*n_targets/m in total, spread over the CTAs in proportion to the tiles they
+    process; each CTA's stream holds twice its even share of a full (unsharded) sweep."""
+    if n < TWO_SWEEP_MIN_N:
+        return None
+    m = min(max(round_up(n // 16, 256), 8192), 32768)
+    n_ctas = 148
+    cap = round_up(int(2.0 * k * n / m * n / n_ctas) + 4096, 1024)
+    return m, cap
+
+
+def _align_ranks_steps(be, X, Y, xn, yn, n: int, csls_k: int, use_csls: bool, want_top3: bool, world: int, rank: int,
+                       two_sweep: bool = True):
     """Generator form of the sharded evaluation. Yields ("all_gather", t) / ("all_reduce", t) whenever the ranks
     must exchange data and receives the collective's result (all_gather: tensor with a new leading dim of size
     world; all_reduce: the elementwise sum). Returning through StopIteration.value keeps the data path identical
@@ -71,7 +88,26 @@ def _align_ranks_steps(be, X, Y, xn, yn, n: int, csls_k: int, use_csls: bool, wa
     nv1 = nv2 = None
     if use_csls:
         # sweep 1: row neighbourhoods — every source against this rank's targets
-        if ns > 0:
+        nv2_fused = None
+        plan2 = two_sweep_plan(n, csls_k) if (two_sweep and ns > 0 and hasattr(be, "eval_rowcoltopk")) else None
+        if plan2 is not None:
+            # two-sweep path: a pre-pass over a random sample of the sources bounds every target's k-th best from
+            # below; the main sweep then collects, per target, every source at or above that bound while it builds
+            # the row lists, so the swapped sweep is not needed.
+            m, cap = plan2
+            gsel = torch.Generator(device="cpu").manual_seed(3408)
+            sel = torch.randperm(n, generator=gsel)[:m].sort()[0].to(dev)
+            Xs, xns = X.index_select(0, sel), xn.index_select(0, sel)
+            part_s = be.eval_rowtopk(Ys, Xs, yns, xns, ns, m)
+            _, cand_s = be.topk_merge_mean(part_s, csls_k, want_nv=False, want_cand=True)
+            colthr, colb = be.col_threshold(cand_s, csls_k, yns)
+            part, stream, stream_cnt = be.eval_rowcoltopk(X, Ys, xn, yns, n, ns, colthr, colb, cap)
+            nv2_fused, overflow, _ = be.col_cand_reduce(stream, stream_cnt, ns, csls_k)
+            launches += 7
+            if int(overflow.item()) != 0:          # a candidate stream filled up: redo the columns the classic way
+                nv2_fused = None
+            del stream
+        elif ns > 0:
             part = be.eval_rowtopk(X, Ys, xn, yns, n, ns)
             launches += 1
         else:
@@ -85,8 +121,11 @@ def _align_ranks_steps(be, X, Y, xn, yn, n: int, csls_k: int, use_csls: bool, wa
             nv1, _ = be.topk_merge_mean(allc.contiguous(), csls_k)
             launches += 2
         # sweep 1': column neighbourhoods — this rank's targets against every source
+        # (skipped when the two-sweep path already produced them from the same pass over S)
         nv2_loc = torch.zeros((per,), dtype=torch.float32, device=dev)
-        if ns > 0:
+        if ns > 0 and nv2_fused is not None:
+            nv2_loc[:ns] = nv2_fused
+        elif ns > 0:
             part2 = be.eval_rowtopk(Ys, X, yns, xn, ns, n)
             nv2s, _ = be.topk_merge_mean(part2, csls_k)
             nv2_loc[:ns] = nv2s
@@ -194,7 +233,8 @@ def simulate_sharded(make_gen, world: int):
 
 
 def align_ranks(X: torch.Tensor, Y: torch.Tensor, xn: torch.Tensor, yn: torch.Tensor, n: int, csls_k: int = 10,
-                use_csls: bool = True, want_top3: bool = False, group=None, backend=None) -> AlignRanks:
+                use_csls: bool = True, want_top3: bool = False, group=None, backend=None,
+                two_sweep: bool = True) -> AlignRanks:
     """Fused evaluation of n aligned pairs (x_i <-> y_i).
 
     X, Y : bf16 operands [>=n, Dpad] from ops.prep_bf16; xn, yn : their squared norms [n].
@@ -211,7 +251,7 @@ def align_ranks(X: torch.Tensor, Y: torch.Tensor, xn: torch.Tensor, yn: torch.Te
     else:
         import torch.distributed as dist
         world, rank = dist.get_world_size(group), dist.get_rank(group)
-    gen = _align_ranks_steps(be, X, Y, xn, yn, n, csls_k, use_csls, want_top3, world, rank)
+    gen = _align_ranks_steps(be, X, Y, xn, yn, n, csls_k, use_csls, want_top3, world, rank, two_sweep)
     if world == 1:
         try:
             next(gen)

@@ -124,6 +124,59 @@ def eval_rowtopk(X, Y, xn, yn, n1: int, n2: int) -> torch.Tensor:
     return part
 
 
+def col_threshold(cand: torch.Tensor, k: int, yn: torch.Tensor):
+    """(colthr, colb) of the two-sweep evaluation from the merged sample lists [n, KT] (see snag_col_threshold)."""
+    _need(cand, torch.float32, "cand", 2)
+    _need(yn, torch.float32, "yn", 1)
+    n = cand.shape[0]
+    colthr = torch.empty((n,), dtype=torch.float32, device=cand.device)
+    colb = torch.empty((n,), dtype=torch.float32, device=cand.device)
+    call("snag_col_threshold", ptr(cand), n, k, ptr(yn), ptr(colthr), ptr(colb), current_stream())
+    return colthr, colb
+
+
+def eval_rowcoltopk(X, Y, xn, yn, n1: int, n2: int, colthr, colb, cta_cap: int):
+    """One sweep for both CSLS directions: returns (row candidate lists [n_lists, n1, KT], per-CTA candidate streams
+    int64 [n_ctas, cta_cap] (low word column, high word c bits), stream_cnt int32 [n_ctas])."""
+    _check_operand(X, "X")
+    _check_operand(Y, "Y")
+    _need(xn, torch.float32, "xn", 1)
+    _need(yn, torch.float32, "yn", 1)
+    _need(colthr, torch.float32, "colthr", 1)
+    _need(colb, torch.float32, "colb", 1)
+    _, nch = sim_plan(n1, n2, X.shape[1])
+    n_ctas = _lib.load().snag_num_sms()
+    part = torch.empty((nch, n1, KT), dtype=torch.float32, device=X.device)
+    stream = torch.empty((n_ctas, cta_cap), dtype=torch.int64, device=X.device)
+    stream_cnt = torch.zeros((n_ctas,), dtype=torch.int32, device=X.device)
+    with _SweepTimer("sim_kernel<EpiRowColTopK>", n1, n2):
+        call("snag_eval_rowcoltopk", ptr(X), ptr(Y), ptr(xn), ptr(yn), n1, n2, X.shape[1], ptr(part), ptr(colthr),
+             ptr(colb), ptr(stream), ptr(stream_cnt), cta_cap, current_stream())
+    return part, stream, stream_cnt
+
+
+def col_cand_reduce(stream: torch.Tensor, stream_cnt: torch.Tensor, n_cols: int, k: int):
+    """Bucket the per-CTA candidate streams by column and reduce each column to its neighbourhood mean.
+    Returns (nv [n_cols], overflow int32[1] device tensor, hist int32 [n_cols])."""
+    _need(stream, torch.int64, "stream", 2)
+    _need(stream_cnt, torch.int32, "stream_cnt", 1)
+    dev = stream.device
+    n_ctas, cta_cap = stream.shape
+    st = current_stream()
+    hist = torch.zeros((n_cols,), dtype=torch.int32, device=dev)
+    overflow = torch.zeros((1,), dtype=torch.int32, device=dev)
+    call("snag_col_cand_hist", ptr(stream), ptr(stream_cnt), n_ctas, cta_cap, ptr(hist), ptr(overflow), st)
+    incl = torch.cumsum(hist, 0, dtype=torch.int64)
+    offs = (incl - hist).contiguous()
+    total = int(min(int(stream_cnt.clamp(max=cta_cap).sum().item()), n_ctas * cta_cap))
+    vals = torch.empty((max(total, 1),), dtype=torch.float32, device=dev)
+    cursor = torch.zeros((n_cols,), dtype=torch.int32, device=dev)
+    call("snag_col_cand_scatter", ptr(stream), ptr(stream_cnt), n_ctas, cta_cap, ptr(offs), ptr(cursor), ptr(vals), st)
+    nv = torch.empty((n_cols,), dtype=torch.float32, device=dev)
+    call("snag_col_cand_finalize", ptr(offs), ptr(hist), ptr(vals), n_cols, k, ptr(nv), ptr(overflow), st)
+    return nv, overflow, hist
+
+
 def topk_merge_mean(part: torch.Tensor, k: int, want_nv: bool = True, want_cand: bool = False):
     _need(part, torch.float32, "part", 3)
     if part.shape[2] != KT:
