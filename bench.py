@@ -263,6 +263,9 @@ def run_snag(args, name, n, d, k, sigma, desc):
     kstats = {nm: {"launches": len(v["ms"]), "avg_ms": sum(v["ms"]) / len(v["ms"]),
                    "tflops": v["flops"] / (sum(v["ms"]) / len(v["ms"])) / 1e9} for nm, v in kern.items()}
     dom = max(kstats, key=lambda nm: kstats[nm]["avg_ms"] * kstats[nm]["launches"])
+    # full sweeps over S executed per step: 3 on the classic path; 2 + m/n with the two-sweep CSLS path
+    plan2 = evaluate.two_sweep_plan(n, k)
+    sweeps = 3.0 if plan2 is None else 2.0 + plan2[0] / n
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
@@ -273,7 +276,7 @@ def run_snag(args, name, n, d, k, sigma, desc):
                 "peak_source": peaks["source"] + ", bf16_tflops_sustained (kernel timed inside a long step)",
                 "frac_of_burst_peak": kstats[dom]["tflops"] / peaks["tensor_burst"],
                 "algorithmic_flops_per_launch": kern[dom]["flops"], "kernels": kstats,
-                "executed_tflops_whole_step": 3 * 2.0 * n * n * d / world / ms_per_step / 1e9}
+                "sweeps_per_step": sweeps, "executed_tflops_whole_step": sweeps * 2.0 * n * n * d / world / ms_per_step / 1e9}
 
     if args.profile_run:
         if rank == 0:

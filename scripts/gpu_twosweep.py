@@ -27,7 +27,7 @@ def t(fn, reps=2):
     return e0.elapsed_time(e1) / reps
 
 
-for (n, d, k) in [(40000, 300, 10), (40000, 1200, 10), (100000, 1200, 10), (100000, 1200, 3), (250000, 1200, 10)]:
+for (n, d, k) in [(70000, 300, 10), (70000, 1800, 10), (100000, 1200, 10), (100000, 1200, 3), (250000, 1200, 10)]:
     x, y = clustered(n, d, 8.0, 5)
     X, xn = ops.prep_bf16(x, None, True)
     Y, yn = ops.prep_bf16(y, None, True)

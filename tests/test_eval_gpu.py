@@ -243,3 +243,41 @@ def test_reference_call_sequence_materialised(cuda_device):
     d = distance.cpu()
     ranks = [(torch.sort(d[i], stable=True)[1] == i).nonzero().item() for i in range(d.shape[0])]
     np.testing.assert_array_equal(np.asarray(ranks, np.int32), fx["rank_l2r"])
+
+
+def test_two_sweep_equals_three_sweep_bitwise(cuda_device):
+    """The two-sweep CSLS path (column neighbourhoods collected during the row sweep through sample-derived admission
+    thresholds) must reproduce the three-sweep path bit for bit: the candidates are a superset of every column's
+    true neighbourhood and the k largest are then selected exactly."""
+    n, d, k = evaluate.TWO_SWEEP_MIN_N + 1234, 320, 10
+    g = torch.Generator(device="cuda").manual_seed(11)
+    centres = torch.randn((64, d), generator=g, device="cuda")
+    x = torch.randn((n, d), generator=g, device="cuda") + centres[torch.randint(0, 64, (n,), generator=g, device="cuda")]
+    y = x + 4.0 * torch.randn((n, d), generator=g, device="cuda")
+    X, xn = ops.prep_bf16(x, None, True)
+    Y, yn = ops.prep_bf16(y, None, True)
+    del x, y
+    a = evaluate.align_ranks(X, Y, xn, yn, n, k, True, two_sweep=False)
+    b = evaluate.align_ranks(X, Y, xn, yn, n, k, True, two_sweep=True)
+    assert b.launches > a.launches                       # the fused path really ran
+    assert torch.equal(a.nv1, b.nv1) and torch.equal(a.nv2, b.nv2)
+    assert torch.equal(a.rank_l2r, b.rank_l2r) and torch.equal(a.rank_r2l, b.rank_r2l)
+    # sharded (3 ranks, simulated): same result again
+    many = evaluate.simulate_sharded(
+        lambda r: evaluate._align_ranks_steps(ops, X, Y, xn, yn, n, k, True, False, 3, r, True), 3)
+    assert torch.equal(many[1].nv2, a.nv2) and torch.equal(many[1].rank_r2l, a.rank_r2l)
+    # candidate statistics: the sample bound leaves ~k*n/m candidates per target, whatever the data
+    m, cap = evaluate.two_sweep_plan(n, k)
+    sel = torch.randperm(n, generator=torch.Generator(device="cpu").manual_seed(3408))[:m].sort()[0].cuda()
+    part_s = ops.eval_rowtopk(Y, X.index_select(0, sel), yn, xn.index_select(0, sel), n, m)
+    _, cand_s = ops.topk_merge_mean(part_s, k, want_nv=False, want_cand=True)
+    colthr, colb = ops.col_threshold(cand_s, k, yn)
+    _, stream, scnt = ops.eval_rowcoltopk(X, Y, xn, yn, n, n, colthr, colb, cap)
+    nv2, overflow, hist = ops.col_cand_reduce(stream, scnt, n, k)
+    assert int(overflow.item()) == 0 and int(hist.min()) >= k
+    assert abs(float(hist.float().mean()) / (k * n / m) - 1.0) < 0.1
+    assert torch.equal(nv2, a.nv2)
+    # a stream that is too small must be reported, not silently truncated
+    _, stream, scnt = ops.eval_rowcoltopk(X, Y, xn, yn, n, n, colthr, colb, 1024)
+    _, overflow, _ = ops.col_cand_reduce(stream, scnt, n, k)
+    assert int(overflow.item()) == 1
