@@ -89,6 +89,15 @@ int snag_sim_write(const uint16_t* X, const uint16_t* Y, const float* xn, const 
 /* Measurement aid: the same TMA + tcgen05 sweep with the accumulators dropped (no epilogue, no output).
  * Times the mainloop alone so that bench.py can attribute a sweep's time to mainloop vs fused epilogue. */
 int snag_sim_mainloop_only(const uint16_t* X, const uint16_t* Y, int32_t n1, int32_t n2, int32_t Dpad, void* stream);
+/* Development aid: counters = device buffer of snag_num_sms()*4 uint64 (or NULL to switch off). While set, the UMMA-
+ * issuing thread of every CTA of every sweep records {total cycles, cycles waiting for a free accumulator stage
+ * (epilogue-bound), cycles waiting for operands (TMA-bound), tiles}. Process-global, not thread-safe. */
+int snag_debug_counters(uint64_t* counters);
+/* Measurement aid: mainloop + TMEM read-out of every accumulator (sink: >= 512 uint32, never written in practice),
+ * plus a synthetic epilogue load per 32-column strip and thread: n_lds broadcast 16-byte shared loads, n_alu dependent
+ * FMAs, n_sts shared stores. Used to find which resource an epilogue takes away from the tensor pipe. */
+int snag_sim_readout_only(const uint16_t* X, const uint16_t* Y, int32_t n1, int32_t n2, int32_t Dpad, uint32_t* sink,
+                          int32_t n_lds, int32_t n_alu, int32_t n_sts, void* stream);
 /* CSLS sweep 1 (src/utils.py:431-432 without the matrix): for every row of X the SNAG_KT largest
  * c_ij = 1 - d_ij over the columns of each chunk. part: fp32 [n_lists][n1][SNAG_KT] (n_lists from
  * snag_sim_plan(n1, n2, Dpad)). Call with X and Y swapped for the column neighbourhoods. */

@@ -1,0 +1,39 @@
+"""Which resource does an epilogue take away from the tensor pipe? Mainloop + TMEM read-out + synthetic per-strip load
+(broadcast shared loads / dependent FMAs / shared stores), with the UMMA issuer's cycle counters. Development probe."""
+import json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from snag_b200 import ops
+from snag_b200._lib import call, ptr, current_stream
+
+sink = torch.zeros(1024, dtype=torch.int32, device="cuda")
+dbg = torch.zeros(148 * 4, dtype=torch.int64, device="cuda")
+
+
+def run(fn, reps=3):
+    fn(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    e0.record()
+    for _ in range(reps): fn()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    dbg.zero_()
+    call("snag_debug_counters", ptr(dbg))
+    fn(); torch.cuda.synchronize()
+    call("snag_debug_counters", None)
+    d = dbg.view(148, 4).double()
+    tiles = d[:, 3].mean().item()
+    return dict(ms=round(ms, 3), cyc_per_tile=round(d[:, 0].mean().item() / tiles), wait_acc=round(d[:, 1].mean().item() / tiles),
+                wait_ops=round(d[:, 2].mean().item() / tiles), ghz=round(d[:, 0].mean().item() / ms / 1e6, 3))
+
+
+n, d = 100000, 1200
+g = torch.Generator(device="cuda").manual_seed(1)
+X, xn = ops.prep_bf16(torch.randn((n, d), generator=g, device="cuda"), None, True)
+Y, yn = ops.prep_bf16(torch.randn((n, d), generator=g, device="cuda"), None, True)
+dp = X.shape[1]
+print(json.dumps(dict(kernel="mainloop", **run(lambda: ops.sim_mainloop_only(X, Y, n, n)))), flush=True)
+for (l, a, s) in [(0, 0, 0), (8, 0, 0), (32, 0, 0), (96, 0, 0), (0, 64, 0), (0, 256, 0), (0, 768, 0), (0, 0, 8), (0, 0, 32), (0, 0, 96)]:
+    r = run(lambda: call("snag_sim_readout_only", ptr(X), ptr(Y), n, n, dp, ptr(sink), l, a, s, current_stream()))
+    print(json.dumps(dict(kernel="readout", lds=l, alu=a, sts=s, **r)), flush=True)
+print(json.dumps(dict(kernel="topk", **run(lambda: ops.eval_rowtopk(X, Y, xn, yn, n, n)))), flush=True)

@@ -29,6 +29,8 @@ _SIGNATURES = {
     "snag_prep_bf16": [_vp, _i64, _vp, _i32, _i32, _i32, _vp, _i32, _vp, _vp],
     "snag_sim_write": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _i64, _vp],
     "snag_sim_mainloop_only": [_vp, _vp, _i32, _i32, _i32, _vp],
+    "snag_debug_counters": [_vp],
+    "snag_sim_readout_only": [_vp, _vp, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _vp],
     "snag_eval_rowtopk": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp],
     "snag_eval_rowcoltopk": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _vp],
     "snag_col_threshold": [_vp, _i64, _i32, _vp, _vp, _vp, _vp],

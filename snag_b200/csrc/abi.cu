@@ -69,6 +69,14 @@ int snag_prep_bf16(const float* emb, int64_t ld, const int64_t* idx, int32_t n, 
 int snag_sim_mainloop_only(const uint16_t* X, const uint16_t* Y, int32_t n1, int32_t n2, int32_t Dpad, void* stream) {
   return launch_sim_null(BF(X), BF(Y), n1, n2, Dpad, S(stream));
 }
+int snag_debug_counters(uint64_t* counters) {
+  set_debug_counters(reinterpret_cast<unsigned long long*>(counters));
+  return SNAG_OK;
+}
+int snag_sim_readout_only(const uint16_t* X, const uint16_t* Y, int32_t n1, int32_t n2, int32_t Dpad, uint32_t* sink,
+                          int32_t n_lds, int32_t n_alu, int32_t n_sts, void* stream) {
+  return launch_sim_loadonly(BF(X), BF(Y), n1, n2, Dpad, sink, n_lds, n_alu, n_sts, S(stream));
+}
 int snag_sim_write(const uint16_t* X, const uint16_t* Y, const float* xn, const float* yn, int32_t n1, int32_t n2,
                    int32_t Dpad, int32_t mode, float* out, int64_t ld, void* stream) {
   return launch_sim_write(BF(X), BF(Y), xn, yn, n1, n2, Dpad, mode, out, ld, S(stream));

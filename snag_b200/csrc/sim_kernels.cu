@@ -98,6 +98,10 @@ static int make_operand_map(CUtensorMap* m, const __nv_bfloat16* ptr, long long 
   return r == CUDA_SUCCESS ? SNAG_OK : SNAG_ERR_DRIVER;
 }
 
+// development aid: when set (snag_debug_counters), every sweep's UMMA issuer records its wait cycles per CTA
+static unsigned long long* g_dbg_counters = nullptr;
+void set_debug_counters(unsigned long long* p) { g_dbg_counters = p; }
+
 template <class Epi>
 static int launch_sim(const __nv_bfloat16* X, const __nv_bfloat16* Y, int n1, int n2, int Dpad,
                       const typename Epi::Params& ep, cudaStream_t st) {
@@ -122,6 +126,7 @@ static int launch_sim(const __nv_bfloat16* X, const __nv_bfloat16* Y, int n1, in
   shp.tiles_per_chunk = pl.tiles_per_chunk;
   shp.n_chunks = pl.n_chunks;
   shp.n_units = pl.n_units;
+  shp.dbg = g_dbg_counters;
   const int grid = pl.n_units < num_sms() ? pl.n_units : num_sms();
   sim_kernel<Epi><<<grid, NUM_THREADS, SIM_SMEM_BYTES, st>>>(tmX, tmY, shp, ep);
   return static_cast<int>(cudaGetLastError());
@@ -130,6 +135,12 @@ static int launch_sim(const __nv_bfloat16* X, const __nv_bfloat16* Y, int n1, in
 int launch_sim_null(const __nv_bfloat16* X, const __nv_bfloat16* Y, int n1, int n2, int Dpad, cudaStream_t st) {
   EpiNull::Params p{0};
   return launch_sim<EpiNull>(X, Y, n1, n2, Dpad, p, st);
+}
+int launch_sim_loadonly(const __nv_bfloat16* X, const __nv_bfloat16* Y, int n1, int n2, int Dpad, uint32_t* sink,
+                        int n_lds, int n_alu, int n_sts, cudaStream_t st) {
+  if (!sink) return SNAG_ERR_ARG;
+  EpiLoadOnly::Params p{sink, n_lds, n_alu, n_sts};
+  return launch_sim<EpiLoadOnly>(X, Y, n1, n2, Dpad, p, st);
 }
 
 int launch_sim_write(const __nv_bfloat16* X, const __nv_bfloat16* Y, const float* xn, const float* yn, int n1, int n2,

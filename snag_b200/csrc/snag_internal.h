@@ -7,7 +7,7 @@
 namespace snag {
 
 constexpr int KT_LIST = 16;   // candidate-list length of the CSLS top-k path (must equal KT in simgemm.cuh)
-constexpr int LISTS_PER_CHUNK = 2;   // partial per-row outputs per column chunk (= epilogue warpgroups)
+constexpr int LISTS_PER_CHUNK = 4;   // partial per-row outputs per column chunk (= epilogue warpgroups)
 
 int num_sms();                // SM count of the current device (cached per device)
 int device_is_sm100();        // 1 if the current device is compute capability 10.x
@@ -46,7 +46,10 @@ int launch_csls_sim(const float* sim, long long n1, long long n2, long long ld, 
                     float* nv1, float* nv2, float* workspace, cudaStream_t st);
 
 // ---- tcgen05 similarity sweeps (sim_kernels.cu)
+void set_debug_counters(unsigned long long* p);
 int launch_sim_null(const __nv_bfloat16* X, const __nv_bfloat16* Y, int n1, int n2, int Dpad, cudaStream_t st);
+int launch_sim_loadonly(const __nv_bfloat16* X, const __nv_bfloat16* Y, int n1, int n2, int Dpad, uint32_t* sink,
+                        int n_lds, int n_alu, int n_sts, cudaStream_t st);
 int launch_sim_write(const __nv_bfloat16* X, const __nv_bfloat16* Y, const float* xn, const float* yn, int n1, int n2,
                      int Dpad, int mode, float* out, long long ld, cudaStream_t st);
 int launch_eval_rowtopk(const __nv_bfloat16* X, const __nv_bfloat16* Y, const float* xn, const float* yn, int n1, int n2,
