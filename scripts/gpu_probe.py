@@ -24,7 +24,7 @@ def run(fn, reps=3):
     d = dbg.view(148, 4).double()
     tiles = d[:, 3].mean().item()
     return dict(ms=round(ms, 3), cyc_per_tile=round(d[:, 0].mean().item() / tiles), wait_acc=round(d[:, 1].mean().item() / tiles),
-                wait_ops=round(d[:, 2].mean().item() / tiles), ghz=round(d[:, 0].mean().item() / ms / 1e6, 3))
+                ghz=round(d[:, 0].mean().item() / ms / 1e6, 3))
 
 
 n, d = 100000, 1200
@@ -33,7 +33,11 @@ X, xn = ops.prep_bf16(torch.randn((n, d), generator=g, device="cuda"), None, Tru
 Y, yn = ops.prep_bf16(torch.randn((n, d), generator=g, device="cuda"), None, True)
 dp = X.shape[1]
 print(json.dumps(dict(kernel="mainloop", **run(lambda: ops.sim_mainloop_only(X, Y, n, n)))), flush=True)
-for (l, a, s) in [(0, 0, 0), (8, 0, 0), (32, 0, 0), (96, 0, 0), (0, 64, 0), (0, 256, 0), (0, 768, 0), (0, 0, 8), (0, 0, 32), (0, 0, 96)]:
+for (l, a, s) in [(0, 0, 0), (0, -256, 0), (0, -1024, 0)]:
     r = run(lambda: call("snag_sim_readout_only", ptr(X), ptr(Y), n, n, dp, ptr(sink), l, a, s, current_stream()))
     print(json.dumps(dict(kernel="readout", lds=l, alu=a, sts=s, **r)), flush=True)
 print(json.dumps(dict(kernel="topk", **run(lambda: ops.eval_rowtopk(X, Y, xn, yn, n, n)))), flush=True)
+from snag_b200 import evaluate
+res = evaluate.align_ranks(X, Y, xn, yn, n, 10, True)
+cr = torch.zeros(n, dtype=torch.int32, device="cuda"); cc = torch.zeros(n, dtype=torch.int32, device="cuda")
+print(json.dumps(dict(kernel="rank", **run(lambda: ops.eval_rank(X, Y, xn, yn, res.nv1, res.nv2, res.g, res.g, 0, 0, n, n, True, cr, cc)))), flush=True)

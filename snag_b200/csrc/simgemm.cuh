@@ -126,68 +126,77 @@ sim_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
 
   if (cwarp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
-      for (int u = blockIdx.x; u < shp.n_units; u += gridDim.x) {
-        const int rb = u % shp.row_blocks, ch = u / shp.row_blocks;
-        const int ct0 = ch * shp.tiles_per_chunk;
-        const int ct1 = min(ct0 + shp.tiles_per_chunk, shp.col_tiles);
-        for (int ct = ct0; ct < ct1; ++ct) {
-          for (int kb = 0; kb < shp.kblocks; ++kb) {
-            mbar_wait(empty_bar(stage), phase ^ 1);
+    // The whole warp walks the loop (so the code is convergent and stays on the uniform datapath); one elected
+    // lane arms the barrier and issues the two bulk-tensor copies. Kept as short as possible: under a busy
+    // epilogue every instruction of this warp waits for an issue slot.
+    const uint32_t leader = elect_one_sync();
+    uint32_t stage = 0, phase = 0;
+    for (int u = blockIdx.x; u < shp.n_units; u += gridDim.x) {
+      const int rb = u % shp.row_blocks, ch = u / shp.row_blocks;
+      const int ct0 = ch * shp.tiles_per_chunk;
+      const int ct1 = min(ct0 + shp.tiles_per_chunk, shp.col_tiles);
+      for (int ct = ct0; ct < ct1; ++ct) {
+        for (int kb = 0; kb < shp.kblocks; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          if (leader) {
             mbar_expect_tx(full_bar(stage), STAGE_BYTES);
             const uint32_t sa = base + stage * STAGE_BYTES;
             tma_load_2d(sa, &tmX, full_bar(stage), kb * BK, rb * BM);
             tma_load_2d(sa + A_STAGE_BYTES, &tmY, full_bar(stage), kb * BK, ct * BN);
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
+          __syncwarp();
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (cwarp == 1) {
-    // ------------------------------------------------------------------ UMMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
-      uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
-      const bool dbg = shp.dbg != nullptr;
-      long long w_acc = 0, w_ops = 0, n_tiles = 0;
-      const long long t_begin = dbg ? clock64() : 0;
-      for (int u = blockIdx.x; u < shp.n_units; u += gridDim.x) {
-        const int ch = u / shp.row_blocks;
-        const int ct0 = ch * shp.tiles_per_chunk;
-        const int ct1 = min(ct0 + shp.tiles_per_chunk, shp.col_tiles);
-        for (int ct = ct0; ct < ct1; ++ct) {
-          long long tw = dbg ? clock64() : 0;
-          mbar_wait(tempty_bar(as), aphase ^ 1);   // epilogue has drained this accumulator stage
-          if (dbg) { w_acc += clock64() - tw; ++n_tiles; }
+    // ------------------------------------------------------------------ UMMA issuer (same structure)
+    constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+    const uint32_t leader = elect_one_sync();
+    const uint64_t adesc0 = make_sdesc_k128(base);
+    const uint64_t bdesc0 = make_sdesc_k128(base + A_STAGE_BYTES);
+    uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
+    const bool dbg = shp.dbg != nullptr;
+    long long w_acc = 0, n_tiles = 0;
+    const long long t_begin = dbg ? clock64() : 0;
+    for (int u = blockIdx.x; u < shp.n_units; u += gridDim.x) {
+      const int ch = u / shp.row_blocks;
+      const int ct0 = ch * shp.tiles_per_chunk;
+      const int ct1 = min(ct0 + shp.tiles_per_chunk, shp.col_tiles);
+      for (int ct = ct0; ct < ct1; ++ct) {
+        const long long tw = dbg ? clock64() : 0;
+        mbar_wait(tempty_bar(as), aphase ^ 1);     // epilogue has drained this accumulator stage
+        if (dbg) { w_acc += clock64() - tw; ++n_tiles; }
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * BN;
+        uint32_t accumulate = 0;
+        for (int kb = 0; kb < shp.kblocks; ++kb) {
+          mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint32_t tmem_d = tmem_base + as * BN;
-          for (int kb = 0; kb < shp.kblocks; ++kb) {
-            tw = dbg ? clock64() : 0;
-            mbar_wait(full_bar(stage), phase);
-            if (dbg) w_ops += clock64() - tw;
-            tc_fence_after();
-            const uint32_t sa = base + stage * STAGE_BYTES;
-            const uint64_t adesc = make_sdesc_k128(sa);
-            const uint64_t bdesc = make_sdesc_k128(sa + A_STAGE_BYTES);
-#pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k) {
-              // +32 bytes (encoded >>4 -> +2) per 16-element K step inside the 128-byte swizzle row
-              umma_bf16_ss(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
-            }
-            umma_commit(empty_bar(stage));         // smem slot free once these MMAs retire
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (leader) {
+            // stage s starts (STAGE_BYTES >> 4) descriptor units after stage 0; +2 units (32 B) per 16-element K step
+            const uint64_t adesc = adesc0 + static_cast<uint64_t>(stage * (STAGE_BYTES >> 4));
+            const uint64_t bdesc = bdesc0 + static_cast<uint64_t>(stage * (STAGE_BYTES >> 4));
+            umma_bf16_ss(tmem_d, adesc, bdesc, idesc, accumulate);
+            umma_bf16_ss(tmem_d, adesc + 2u, bdesc + 2u, idesc, 1u);
+            umma_bf16_ss(tmem_d, adesc + 4u, bdesc + 4u, idesc, 1u);
+            umma_bf16_ss(tmem_d, adesc + 6u, bdesc + 6u, idesc, 1u);
+            umma_commit(empty_bar(stage));           // smem slot free once these MMAs retire
           }
-          umma_commit(tfull_bar(as));               // accumulator complete -> epilogue
-          if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
+          __syncwarp();
+          accumulate = 1;
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        if (leader) umma_commit(tfull_bar(as));      // accumulator complete -> epilogue
+        __syncwarp();
+        if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
       }
-      if (dbg) {
-        shp.dbg[blockIdx.x * 4 + 0] = clock64() - t_begin;
-        shp.dbg[blockIdx.x * 4 + 1] = w_acc;
-        shp.dbg[blockIdx.x * 4 + 2] = w_ops;
-        shp.dbg[blockIdx.x * 4 + 3] = n_tiles;
-      }
+    }
+    if (dbg && leader) {
+      shp.dbg[blockIdx.x * 4 + 0] = clock64() - t_begin;
+      shp.dbg[blockIdx.x * 4 + 1] = w_acc;
+      shp.dbg[blockIdx.x * 4 + 2] = 0;
+      shp.dbg[blockIdx.x * 4 + 3] = n_tiles;
     }
   } else if (cwarp < 0) {
     // ------------------------------------------------------------------ epilogue warpgroup
@@ -299,7 +308,19 @@ struct EpiLoadOnly {
       st.acc ^= __float_as_uint(t.x) + __float_as_uint(t.w);
     }
     float f = __uint_as_float(st.acc | 0x3f800000u);
-    for (int i = 0; i < p.n_alu; ++i) f = __fmaf_rn(f, 1.0000001f, 1e-9f);
+    if (p.n_alu >= 0) {
+      for (int i = 0; i < p.n_alu; ++i) f = __fmaf_rn(f, 1.0000001f, 1e-9f);       // one dependent chain (low IPC)
+    } else {
+      float g[8];                                                                     // 8 independent chains (high IPC)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) g[e] = f + static_cast<float>(e);
+      for (int i = 0; i < -p.n_alu; i += 8) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) g[e] = __fmaf_rn(g[e], 1.0000001f, 1e-9f);
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f += g[e];
+    }
     st.acc ^= __float_as_uint(f);
     for (int i = 0; i < p.n_sts; ++i)                   // conflict-free 4-byte shared stores
       cx.scratch[EPI_VEC_FLOATS + (i & 7) * NUM_EPI_THREADS + cx.tid] = f;
