@@ -41,3 +41,12 @@ from snag_b200 import evaluate
 res = evaluate.align_ranks(X, Y, xn, yn, n, 10, True)
 cr = torch.zeros(n, dtype=torch.int32, device="cuda"); cc = torch.zeros(n, dtype=torch.int32, device="cuda")
 print(json.dumps(dict(kernel="rank", **run(lambda: ops.eval_rank(X, Y, xn, yn, res.nv1, res.nv2, res.g, res.g, 0, 0, n, n, True, cr, cc)))), flush=True)
+
+# fused row+column top-k sweep with different sample sizes (admission thresholds from m sampled rows)
+for m in (8192, 32768):
+    sel = torch.randperm(n, generator=torch.Generator(device="cpu").manual_seed(3408))[:m].sort()[0].cuda()
+    part_s = ops.eval_rowtopk(Y, X.index_select(0, sel), yn, xn.index_select(0, sel), n, m)
+    _, cand_s = ops.topk_merge_mean(part_s, 10, want_nv=False, want_cand=True)
+    colthr, colb = ops.col_threshold(cand_s, 10, yn)
+    cap = int(2.0 * 10 * n / m * n / 148) + 4096
+    print(json.dumps(dict(kernel="fused", m=m, **run(lambda: ops.eval_rowcoltopk(X, Y, xn, yn, n, n, colthr, colb, cap)))), flush=True)

@@ -81,7 +81,16 @@ def _gloo_worker(rank, world, port, name, out):
 @pytest.mark.timeout(300)
 def test_gloo_world2_matches_reference():
     world = 2
-    with mp.Manager() as mgr:
-        out = mgr.dict()
-        mp.spawn(_gloo_worker, args=(world, _free_port(), "eval_n384_d96_k10", out), nprocs=world, join=True)
-        assert dict(out) == {0: True, 1: True}
+    last = None
+    for _attempt in range(2):          # the rendezvous port is picked optimistically; retry once if it was taken meanwhile
+        try:
+            with mp.Manager() as mgr:
+                out = mgr.dict()
+                mp.spawn(_gloo_worker, args=(world, _free_port(), "eval_n384_d96_k10", out), nprocs=world, join=True)
+                assert dict(out) == {0: True, 1: True}
+                return
+        except AssertionError:                     # a wrong result is never retried
+            raise
+        except Exception as e:                     # rendezvous / socket errors
+            last = e
+    raise last
