@@ -89,7 +89,7 @@ int snag_sim_write(const uint16_t* X, const uint16_t* Y, const float* xn, const 
 /* Measurement aid: the same TMA + tcgen05 sweep with the accumulators dropped (no epilogue, no output).
  * Times the mainloop alone so that bench.py can attribute a sweep's time to mainloop vs fused epilogue. */
 int snag_sim_mainloop_only(const uint16_t* X, const uint16_t* Y, int32_t n1, int32_t n2, int32_t Dpad, void* stream);
-/* Development aid: counters = device buffer of snag_num_sms()*4 uint64 (or NULL to switch off). While set, the UMMA-
+/* Development aid: counters = zeroed device buffer of 2*snag_num_sms()*4 uint64 (or NULL to switch off). While set, the UMMA-
  * issuing thread of every CTA of every sweep records {total cycles, cycles waiting for a free accumulator stage
  * (epilogue-bound), cycles waiting for operands (TMA-bound), tiles}. Process-global, not thread-safe. */
 int snag_debug_counters(uint64_t* counters);

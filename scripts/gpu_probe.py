@@ -7,7 +7,7 @@ from snag_b200 import ops
 from snag_b200._lib import call, ptr, current_stream
 
 sink = torch.zeros(1024, dtype=torch.int32, device="cuda")
-dbg = torch.zeros(148 * 4, dtype=torch.int64, device="cuda")
+dbg = torch.zeros(2 * 148 * 4, dtype=torch.int64, device="cuda")
 
 
 def run(fn, reps=3):
@@ -21,10 +21,11 @@ def run(fn, reps=3):
     call("snag_debug_counters", ptr(dbg))
     fn(); torch.cuda.synchronize()
     call("snag_debug_counters", None)
-    d = dbg.view(148, 4).double()
-    tiles = d[:, 3].mean().item()
-    return dict(ms=round(ms, 3), cyc_per_tile=round(d[:, 0].mean().item() / tiles), wait_acc=round(d[:, 1].mean().item() / tiles),
-                ghz=round(d[:, 0].mean().item() / ms / 1e6, 3))
+    d = dbg.view(296, 4).double()
+    tiles = d[:148, 3].mean().item()
+    return dict(ms=round(ms, 3), cyc_per_tile=round(d[:148, 0].mean().item() / tiles), wait_acc=round(d[:148, 1].mean().item() / tiles),
+                epi_proc=round(d[:148, 2].mean().item() / tiles / 16), epi_bar=round(d[148:, 0].mean().item() / tiles / 16),
+                ghz=round(d[:148, 0].mean().item() / ms / 1e6, 3))
 
 
 n, d = 100000, 1200

@@ -53,8 +53,9 @@ struct SimShape {
   int tiles_per_chunk;
   int n_chunks;         // ceil(col_tiles / tiles_per_chunk)
   int n_units;          // row_blocks * n_chunks
-  unsigned long long* dbg;   // optional [gridDim.x][4] cycle counters of the UMMA issuer: total, waiting for a free
-                             // accumulator stage (epilogue-bound), waiting for operands (TMA-bound), tiles; or null
+  unsigned long long* dbg;   // optional [2*gridDim.x][4] cycle counters (zeroed by the caller) or null. Row cta: UMMA issuer
+                             // total, its wait for a free accumulator stage, sum over epilogue warps of strip time,
+                             // tiles. Row gridDim.x + cta: sum over epilogue warps of commit + barrier time.
 };
 
 struct EpiCtx {
@@ -68,6 +69,11 @@ struct EpiCtx {
   int rb, chunk; // unit coordinates
   int useq;      // sequence number of the unit within this CTA (parity selects double-buffered per-unit scratch)
   float* scratch;  // EPI_SCRATCH_BYTES of shared memory private to the epilogue warpgroup
+};
+
+// registers carrying one column's prefetched per-tile values from tile_prefetch to tile_commit
+struct EpiPre {
+  float a, b, c;
 };
 
 // optional per-CTA hook run by the epilogue threads after their last unit: Epi::kernel_end(params, ctx)
@@ -195,7 +201,6 @@ sim_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
     if (dbg && leader) {
       shp.dbg[blockIdx.x * 4 + 0] = clock64() - t_begin;
       shp.dbg[blockIdx.x * 4 + 1] = w_acc;
-      shp.dbg[blockIdx.x * 4 + 2] = 0;
       shp.dbg[blockIdx.x * 4 + 3] = n_tiles;
     }
   } else if (cwarp < 0) {
@@ -210,6 +215,8 @@ sim_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
     uint32_t as = 0, aphase = 0;
     uint32_t tile_seq = 0;
     cx.useq = -1;
+    const bool dbg = shp.dbg != nullptr;
+    long long c_proc = 0, c_bar = 0;
     for (int u = blockIdx.x; u < shp.n_units; u += gridDim.x) {
       ++cx.useq;
       cx.rb = u % shp.row_blocks;
@@ -221,12 +228,20 @@ sim_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
       const int ct1 = min(ct0 + shp.tiles_per_chunk, shp.col_tiles);
       typename Epi::State st;
       Epi::unit_begin(ep, shp, cx, st);
+      // per-column vectors of a tile (norms, CSLS means, thresholds ...) are fetched from global memory one tile
+      // ahead (tile_prefetch: loads in flight while the current tile's strips are consumed) and parked in a
+      // double-buffered shared-memory area (tile_commit) that all epilogue threads read after the barrier
+      EpiPre pre = Epi::tile_prefetch(ep, shp, cx, ct0);
       for (int ct = ct0; ct < ct1; ++ct, ++tile_seq) {
         const int buf = tile_seq & 1;
-        Epi::tile_begin(ep, shp, cx, st, ct, buf);   // stage per-column vectors in smem (double-buffered)
+        long long t0 = dbg ? clock64() : 0;
+        Epi::tile_commit(ep, shp, cx, st, pre, ct, buf);
         named_bar_sync(1, NUM_EPI_THREADS);
+        if (dbg) c_bar += clock64() - t0;
+        if (ct + 1 < ct1) pre = Epi::tile_prefetch(ep, shp, cx, ct + 1);
         mbar_wait(tfull_bar(as), aphase);
         tc_fence_after();
+        t0 = dbg ? clock64() : 0;
         const uint32_t taddr = tmem_base + lane_base + as * BN;
         // Rolled on purpose: one copy of the strip body keeps the epilogue inside the instruction cache
         // (a fully unrolled tile body was ~150 KB of SASS and ran instruction-fetch bound).
@@ -241,12 +256,17 @@ sim_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
         }
         tc_fence_before();
         mbar_arrive(tempty_bar(as));
+        if (dbg) c_proc += clock64() - t0;
         if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
         Epi::tile_end(ep, shp, cx, st, ct, buf);
       }
       Epi::unit_end(ep, shp, cx, st);
     }
     if constexpr (HasKernelEnd<Epi>::value) Epi::kernel_end(ep, cx);
+    if (dbg && lane == 0) {      // summed over the epilogue warps: cycles consuming strips / cycles in commit + barrier
+      atomicAdd(shp.dbg + blockIdx.x * 4 + 2, static_cast<unsigned long long>(c_proc));
+      atomicAdd(shp.dbg + (gridDim.x + blockIdx.x) * 4 + 0, static_cast<unsigned long long>(c_bar));
+    }
   }
 
   tc_fence_before();
@@ -283,7 +303,8 @@ struct EpiNull {
   struct Params { int unused; };
   struct State {};
   static __device__ __forceinline__ void unit_begin(const Params&, const SimShape&, const EpiCtx&, State&) {}
-  static __device__ __forceinline__ void tile_begin(const Params&, const SimShape&, const EpiCtx&, State&, int, int) {}
+  static __device__ __forceinline__ EpiPre tile_prefetch(const Params&, const SimShape&, const EpiCtx&, int) { return EpiPre{}; }
+  static __device__ __forceinline__ void tile_commit(const Params&, const SimShape&, const EpiCtx&, State&, const EpiPre&, int, int) {}
   static __device__ __forceinline__ void chunk(const Params&, const SimShape&, const EpiCtx&, State&, int, int,
                                                const uint32_t (&)[32], int) {}
   static __device__ __forceinline__ void tile_end(const Params&, const SimShape&, const EpiCtx&, State&, int, int) {}
@@ -297,7 +318,8 @@ struct EpiLoadOnly {
   struct Params { uint32_t* sink; int n_lds; int n_alu; int n_sts; };   // synthetic per-strip load: see gpu_probe.py
   struct State { uint32_t acc; };
   static __device__ __forceinline__ void unit_begin(const Params&, const SimShape&, const EpiCtx&, State& st) { st.acc = 0; }
-  static __device__ __forceinline__ void tile_begin(const Params&, const SimShape&, const EpiCtx&, State&, int, int) {}
+  static __device__ __forceinline__ EpiPre tile_prefetch(const Params&, const SimShape&, const EpiCtx&, int) { return EpiPre{}; }
+  static __device__ __forceinline__ void tile_commit(const Params&, const SimShape&, const EpiCtx&, State&, const EpiPre&, int, int) {}
   static __device__ __forceinline__ void chunk(const Params& p, const SimShape&, const EpiCtx& cx, State& st, int, int c,
                                                const uint32_t (&r)[32], int) {
 #pragma unroll
@@ -349,13 +371,16 @@ struct EpiWrite {
   static __device__ __forceinline__ void unit_begin(const Params& p, const SimShape&, const EpiCtx& cx, State& st) {
     st.xn = (p.mode == 1 && cx.row_ok) ? p.xn[cx.row] : 0.f;
   }
-  static __device__ __forceinline__ void tile_begin(const Params& p, const SimShape& shp, const EpiCtx& cx, State&,
-                                                    int ct, int buf) {
-    float* yn_s = cx.scratch + buf * BN;
-    for (int j = cx.tid; j < BN; j += NUM_EPI_THREADS) {
-      const int col = ct * BN + j;
-      yn_s[j] = (p.mode == 1 && col < shp.n_cols) ? p.yn[col] : 0.f;
-    }
+  static __device__ __forceinline__ EpiPre tile_prefetch(const Params& p, const SimShape& shp, const EpiCtx& cx, int ct) {
+    static_assert(NUM_EPI_THREADS >= BN, "one epilogue thread stages one column");
+    EpiPre pre{};
+    const int col = ct * BN + cx.tid;
+    if (cx.tid < BN) pre.a = (p.mode == 1 && col < shp.n_cols) ? p.yn[col] : 0.f;
+    return pre;
+  }
+  static __device__ __forceinline__ void tile_commit(const Params&, const SimShape&, const EpiCtx& cx, State&,
+                                                     const EpiPre& pre, int, int buf) {
+    if (cx.tid < BN) cx.scratch[buf * BN + cx.tid] = pre.a;
   }
   static __device__ __forceinline__ void chunk(const Params& p, const SimShape& shp, const EpiCtx& cx, State& st,
                                                int ct, int c, const uint32_t (&r)[32], int buf) {
@@ -406,15 +431,20 @@ struct EpiRowTopK {
   }
   // scratch layout per buffer: yn[BN] then the minimum of yn over each 32-column strip [BN/32]
   static constexpr int kVecStride = BN + BN / 32;
-  static __device__ __forceinline__ void tile_begin(const Params& p, const SimShape& shp, const EpiCtx& cx, State&,
-                                                    int ct, int buf) {
+  static __device__ __forceinline__ EpiPre tile_prefetch(const Params& p, const SimShape& shp, const EpiCtx& cx, int ct) {
+    EpiPre pre{};
+    const int col = ct * BN + cx.tid;
+    // out-of-range columns get yn = +inf  ->  d = +inf, c = -inf: never admitted
+    if (cx.tid < BN) pre.a = (col < shp.n_cols) ? p.yn[col] : INFINITY;
+    return pre;
+  }
+  static __device__ __forceinline__ void tile_commit(const Params&, const SimShape&, const EpiCtx& cx, State&,
+                                                     const EpiPre& pre, int, int buf) {
     static_assert(NUM_EPI_THREADS >= BN, "one epilogue thread stages one column");
     static_assert(2 * kVecStride <= EPI_VEC_FLOATS, "scratch too small");
     if (cx.tid >= BN) return;                      // whole warps leave: the shuffles below stay warp-complete
     float* yn_s = cx.scratch + buf * kVecStride;
-    const int col = ct * BN + cx.tid;
-    // out-of-range columns get yn = +inf  ->  d = +inf, c = -inf: never admitted
-    const float v = (col < shp.n_cols) ? p.yn[col] : INFINITY;
+    const float v = pre.a;
     yn_s[cx.tid] = v;
     float m = v;
 #pragma unroll
@@ -481,8 +511,9 @@ struct EpiRowTopK {
 //     sample of m rows, whatever the data distribution);
 //   * fast path per element: s_ij > a_i + b_j with a_i = xn_i/2, b_j = (yn_j - 1 + colthr_j)/2 - margin — a
 //     conservative s-space form of that test (same rounding argument as the row pre-filter);
-//   * the 32x32 predicate bit-matrix of a warp's strip is transposed with 5 shuffles so that lane l owns
-//     column l, re-computes c exactly for the flagged rows (accumulators parked in shared memory) and appends.
+//   * the thread that owns the row re-checks its (few) flagged elements exactly and appends the survivors, as
+//     (column, c) pairs, to a stream private to the CTA (slot from a shared-memory counter); bandwidth kernels
+//     bucket the streams by column afterwards.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t transpose32(uint32_t x, int lane) {
 #pragma unroll
@@ -526,19 +557,27 @@ struct EpiRowColTopK {
     st.a = cx.row_ok ? 0.5f * st.xn : INFINITY;          // padding rows never produce column candidates
 #pragma unroll
     for (int t = 0; t < KT; ++t) st.top[t] = -INFINITY;
-    if (cx.wg == 0) cx.scratch[kXnOff + (cx.useq & 1) * BM + cx.et] = st.xn;   // visible after the tile barrier
   }
-  static __device__ __forceinline__ void tile_begin(const Params& p, const SimShape& shp, const EpiCtx& cx, State&,
-                                                    int ct, int buf) {
+  static __device__ __forceinline__ EpiPre tile_prefetch(const Params& p, const SimShape& shp, const EpiCtx& cx, int ct) {
+    EpiPre pre{};
+    const int col = ct * BN + cx.tid;
+    if (cx.tid < BN) {
+      const bool ok = col < shp.n_cols;
+      pre.a = ok ? p.yn[col] : INFINITY;
+      pre.b = ok ? p.colb[col] : INFINITY;
+      pre.c = ok ? p.colthr[col] : INFINITY;
+    }
+    return pre;
+  }
+  static __device__ __forceinline__ void tile_commit(const Params&, const SimShape&, const EpiCtx& cx, State&,
+                                                     const EpiPre& pre, int, int buf) {
     static_assert(NUM_EPI_THREADS >= BN, "one epilogue thread stages one column");
     if (cx.tid >= BN) return;                      // whole warps leave: the shuffles below stay warp-complete
     float* v_s = cx.scratch + buf * kVecStride;
-    const int col = ct * BN + cx.tid;
-    const bool ok = col < shp.n_cols;
-    const float v = ok ? p.yn[col] : INFINITY;
+    const float v = pre.a;
     v_s[cx.tid] = v;
-    v_s[BN + BN / 32 + cx.tid] = ok ? p.colb[col] : INFINITY;
-    v_s[2 * BN + BN / 32 + cx.tid] = ok ? p.colthr[col] : INFINITY;
+    v_s[BN + BN / 32 + cx.tid] = pre.b;
+    v_s[2 * BN + BN / 32 + cx.tid] = pre.c;
     float m = v;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
@@ -559,22 +598,37 @@ struct EpiRowColTopK {
       if (s > thr) pm |= (1u << q);
       if (s > __fadd_rn(st.a, cb_s[q])) cm |= (1u << q);
     }
-    const uint32_t cmT = transpose32(cm, cx.lane);       // lane l: bit t set <=> row t of this warp flagged column l
-    if (__any_sync(0xffffffffu, (pm | cmT) != 0)) {
-      float* stage_w = cx.scratch + EPI_VEC_FLOATS + (cx.tid & ~31);      // this warp's 32 columns of the staging area
-      const float* xn_w = cx.scratch + kXnOff + (cx.useq & 1) * BM + (cx.et & ~31);
+    // column direction: the thread that owns the row re-checks its flagged columns exactly (32 statically indexed,
+    // rarely taken blocks: no staging, no cross-lane traffic) and appends the survivors to this CTA's stream
+    if (cm != 0) {
+      const int col0 = ct * BN + c * 32;
 #pragma unroll
-      for (int h = 0; h < 32 / EPI_STAGE_VALS; ++h) {      // the staging area holds EPI_STAGE_VALS values per thread
+      for (int q = 0; q < 32; ++q) {
+        if (cm & (1u << q)) {
+          const float x = __fsub_rn(1.0f, sqdist_from_dot(__uint_as_float(r[q]), st.xn, yn_s[q]));
+          if (x >= ct_s[q]) {
+            // a shared-memory counter hands out the slot: no global-atomic round trip on the epilogue's critical path
+            const int slot = atomicAdd(reinterpret_cast<int*>(cx.scratch + kCntOff), 1);
+            if (slot < p.cta_cap)
+              p.stream[static_cast<long long>(blockIdx.x) * p.cta_cap + slot] =
+                  make_uint2(static_cast<uint32_t>(col0 + q), __float_as_uint(x));
+          }
+        }
+      }
+    }
+    // row direction (rare once the list has warmed up): as EpiRowTopK
+    if (pm != 0) {
+      float* stage = cx.scratch + EPI_VEC_FLOATS + cx.tid;
+#pragma unroll
+      for (int h = 0; h < 32 / EPI_STAGE_VALS; ++h) {
         uint32_t ph = (pm >> (EPI_STAGE_VALS * h)) & ((1u << EPI_STAGE_VALS) - 1u);
-        const uint32_t ch = ((cx.lane / EPI_STAGE_VALS) == h) ? cmT : 0u;
-        if (!__any_sync(0xffffffffu, (ph | ch) != 0)) continue;
+        if (ph == 0) continue;
 #pragma unroll
-        for (int q = 0; q < EPI_STAGE_VALS; ++q) stage_w[q * NUM_EPI_THREADS + cx.lane] = __uint_as_float(r[EPI_STAGE_VALS * h + q]);
-        __syncwarp();
-        while (ph != 0) {                                  // row direction: own staged values
+        for (int q = 0; q < EPI_STAGE_VALS; ++q) stage[q * NUM_EPI_THREADS] = __uint_as_float(r[EPI_STAGE_VALS * h + q]);
+        while (ph != 0) {
           const int q = __ffs(ph) - 1;
           ph &= ph - 1;
-          const float x = __fsub_rn(1.0f, sqdist_from_dot(stage_w[q * NUM_EPI_THREADS + cx.lane], st.xn, yn_s[EPI_STAGE_VALS * h + q]));
+          const float x = __fsub_rn(1.0f, sqdist_from_dot(stage[q * NUM_EPI_THREADS], st.xn, yn_s[EPI_STAGE_VALS * h + q]));
           if (x > st.top[0]) {
             st.top[0] = x;
 #pragma unroll
@@ -586,22 +640,6 @@ struct EpiRowColTopK {
             }
           }
         }
-        uint32_t cmask = ch;                               // column direction: lane l owns column l of the strip
-        const int col = ct * BN + c * 32 + cx.lane;
-        while (cmask != 0) {
-          const int t = __ffs(cmask) - 1;
-          cmask &= cmask - 1;
-          const float s = stage_w[(cx.lane % EPI_STAGE_VALS) * NUM_EPI_THREADS + t];
-          const float x = __fsub_rn(1.0f, sqdist_from_dot(s, xn_w[t], yn_s[cx.lane]));
-          if (x >= ct_s[cx.lane]) {
-            // append to this CTA's private stream: a shared-memory counter hands out the slot (no global-atomic
-            // round trip on the epilogue's critical path); a later pass buckets the stream by column
-            const int slot = atomicAdd(reinterpret_cast<int*>(cx.scratch + kCntOff), 1);
-            if (slot < p.cta_cap)
-              p.stream[static_cast<long long>(blockIdx.x) * p.cta_cap + slot] = make_uint2(static_cast<uint32_t>(col), __float_as_uint(x));
-          }
-        }
-        __syncwarp();
       }
     }
   }
@@ -657,16 +695,25 @@ struct EpiRank {
       for (int t = 0; t < 3; ++t) { st.t3v[t] = INFINITY; st.t3i[t] = 0x7fffffff; }
     }
   }
-  static __device__ __forceinline__ void tile_begin(const Params& p, const SimShape& shp, const EpiCtx& cx, State&,
-                                                    int ct, int buf) {
-    float* s = cx.scratch + buf * (3 * BN);
-    for (int j = cx.tid; j < BN; j += NUM_EPI_THREADS) {
-      const int col = ct * BN + j;
+  static __device__ __forceinline__ EpiPre tile_prefetch(const Params& p, const SimShape& shp, const EpiCtx& cx, int ct) {
+    static_assert(NUM_EPI_THREADS >= BN, "one epilogue thread stages one column");
+    EpiPre pre{};
+    const int col = ct * BN + cx.tid;
+    if (cx.tid < BN) {
       const bool ok = col < shp.n_cols;
-      s[j] = ok ? p.yn[col] : INFINITY;        // d = inf -> dist = +inf: never smaller than anything
-      s[BN + j] = ok ? p.nv2[col] : 0.f;
-      s[2 * BN + j] = ok ? p.g_col[col] : -INFINITY;
+      pre.a = ok ? p.yn[col] : INFINITY;        // d = inf -> dist = +inf: never smaller than anything
+      pre.b = ok ? p.nv2[col] : 0.f;
+      pre.c = ok ? p.g_col[col] : -INFINITY;
     }
+    return pre;
+  }
+  static __device__ __forceinline__ void tile_commit(const Params&, const SimShape&, const EpiCtx& cx, State&,
+                                                     const EpiPre& pre, int, int buf) {
+    if (cx.tid >= BN) return;
+    float* s = cx.scratch + buf * (3 * BN);
+    s[cx.tid] = pre.a;
+    s[BN + cx.tid] = pre.b;
+    s[2 * BN + cx.tid] = pre.c;
   }
   static __device__ __forceinline__ void chunk(const Params& p, const SimShape& shp, const EpiCtx& cx, State& st, int ct,
                                                int c, const uint32_t (&r)[32], int buf) {
@@ -778,7 +825,8 @@ struct EpiIclFwd {
   static __device__ __forceinline__ void unit_begin(const Params&, const SimShape&, const EpiCtx&, State& st) {
     st.sum = 0.f;
   }
-  static __device__ __forceinline__ void tile_begin(const Params&, const SimShape&, const EpiCtx&, State&, int, int) {}
+  static __device__ __forceinline__ EpiPre tile_prefetch(const Params&, const SimShape&, const EpiCtx&, int) { return EpiPre{}; }
+  static __device__ __forceinline__ void tile_commit(const Params&, const SimShape&, const EpiCtx&, State&, const EpiPre&, int, int) {}
   static __device__ __forceinline__ void chunk(const Params& p, const SimShape&, const EpiCtx& cx, State& st, int ct,
                                                int c, const uint32_t (&r)[32], int) {
     const int col0 = ct * BN + c * 32;
@@ -842,16 +890,20 @@ struct EpiIclBwd {
     st.cr = ok ? p.cr[cx.row] : 0.f;
     st.dg = ok ? p.dg[cx.row] : 0.f;
   }
-  static __device__ __forceinline__ void tile_begin(const Params& p, const SimShape&, const EpiCtx& cx, State&, int ct,
-                                                    int buf) {
+  static __device__ __forceinline__ EpiPre tile_prefetch(const Params& p, const SimShape&, const EpiCtx& cx, int ct) {
     static_assert(NUM_EPI_THREADS >= BN, "one epilogue thread stages one column");
-    if (cx.tid >= BN) return;
-    const int col = ct * BN + cx.tid;
-    const int part = col >= p.Bp ? 1 : 0;
-    const int idx = col - part * p.Bp;
-    float v = 0.f;
-    if (idx < p.B) v = part ? p.cr[idx] : p.cc[idx];
-    cx.scratch[buf * BN + cx.tid] = v;
+    EpiPre pre{};
+    if (cx.tid < BN) {
+      const int col = ct * BN + cx.tid;
+      const int part = col >= p.Bp ? 1 : 0;
+      const int idx = col - part * p.Bp;
+      if (idx < p.B) pre.a = part ? p.cr[idx] : p.cc[idx];
+    }
+    return pre;
+  }
+  static __device__ __forceinline__ void tile_commit(const Params&, const SimShape&, const EpiCtx& cx, State&,
+                                                     const EpiPre& pre, int, int buf) {
+    if (cx.tid < BN) cx.scratch[buf * BN + cx.tid] = pre.a;
   }
   static __device__ __forceinline__ void chunk(const Params& p, const SimShape&, const EpiCtx& cx, State& st, int ct,
                                                int c, const uint32_t (&r)[32], int buf) {
