@@ -66,6 +66,7 @@ class ClockSampler:
 
     def __init__(self, index: int):
         self.index, self.samples, self.mask, self.max_mhz = index, [], 0, None
+        self.power_w, self.temp_c = [], []
         self._stop = threading.Event()
         self._thr = None
         try:
@@ -82,6 +83,8 @@ class ClockSampler:
             try:
                 self.samples.append(int(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
                 self.mask |= int(self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.power_w.append(self.nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+                self.temp_c.append(int(self.nv.nvmlDeviceGetTemperature(self.h, self.nv.NVML_TEMPERATURE_GPU)))
             except Exception:
                 pass
             self._stop.wait(0.1)
@@ -99,8 +102,11 @@ class ClockSampler:
 
     def summary(self):
         s = sorted(self.samples)
+        pw, tc = sorted(self.power_w), sorted(self.temp_c)
         return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
-                "reasons": [name for bit, name in self.REASONS.items() if self.mask & bit], "samples": len(s)}
+                "reasons": [name for bit, name in self.REASONS.items() if self.mask & bit], "samples": len(s),
+                "sm_mhz_min": (s[0] if s else None), "power_w_median": (pw[len(pw) // 2] if pw else None),
+                "temp_c_max": (tc[-1] if tc else None)}
 
 
 def synth_tables(n: int, d: int, sigma: float, device, chunk: int = 65536):

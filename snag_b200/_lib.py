@@ -9,7 +9,10 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
-LIB_PATH = Path(__file__).resolve().parent / "libsnag_b200.so"
+import os
+
+# SNAG_B200_LIB selects another build of the same ABI (A/B measurements of kernel variants); default: the in-tree build
+LIB_PATH = Path(os.environ.get("SNAG_B200_LIB") or (Path(__file__).resolve().parent / "libsnag_b200.so"))
 KT = 16  # SNAG_KT
 
 _i32, _i64, _u64, _f32, _vp = C.c_int32, C.c_int64, C.c_uint64, C.c_float, C.c_void_p

@@ -43,8 +43,25 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// SNAG_TRYWAIT_HINT_NS > 0 passes a suspend-time hint: a waiting thread sleeps in hardware until the phase completes
+// or the hint expires, instead of returning to the polling loop every few dozen cycles (spinning costs issue slots
+// and power, and this chip runs power-capped).
+#ifndef SNAG_TRYWAIT_HINT_NS
+#define SNAG_TRYWAIT_HINT_NS 1000
+#endif
 __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
+#if SNAG_TRYWAIT_HINT_NS > 0
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(static_cast<uint32_t>(SNAG_TRYWAIT_HINT_NS))
+      : "memory");
+#else
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
@@ -54,6 +71,7 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
       : "=r"(ok)
       : "r"(bar), "r"(parity)
       : "memory");
+#endif
   return ok;
 }
 

@@ -1,11 +1,11 @@
 // Persistent, warp-specialised similarity contraction  S = X · Yᵀ  (bf16 in, fp32 accumulate in TMEM)
 // with the consumer of S fused into the epilogue, so S never reaches HBM.
 //
-//   warps 0..15 epilogue       : four warpgroups, each owning a quarter of the tile's columns; tcgen05.ld 32 lanes x
+//   warps 0..7  epilogue       : two warpgroups (SNAG_EPI_WG), each owning half of the tile's columns; tcgen05.ld 32 lanes x
 //                                32 columns at a time, thread <-> one row of the tile (TMEM lane = 32*(warp%4)+lane)
-//   warp 16     TMA producer   : X tile [128 x 64] + Y tile [256 x 64] per k-block -> 4-stage smem ring
-//   warp 17     UMMA issuer    : tcgen05.mma 128x256x16, 4 per k-block, accumulator double-buffered in TMEM
-//   warp 18     TMEM allocator : 512 columns (2 accumulator stages x 256 fp32 columns)
+//   warp 8      TMA producer   : X tile [128 x 64] + Y tile [256 x 64] per k-block -> 4-stage smem ring
+//   warp 9      UMMA issuer    : tcgen05.mma 128x256x16, 4 per k-block, accumulator double-buffered in TMEM
+//   warp 10     TMEM allocator : 512 columns (2 accumulator stages x 256 fp32 columns)
 //
 // Work decomposition: a *unit* is (row block of 128 sources) x (chunk of `tiles_per_chunk` column tiles);
 // per-row epilogue state (top-k list, rank counter, softmax row sum) lives in registers for the whole
@@ -30,7 +30,7 @@ constexpr int ACC_STAGES = 2;
 constexpr int TMEM_COLS = ACC_STAGES * BN;   // 512
 constexpr int NUM_CTRL_THREADS = 128;
 #ifndef SNAG_EPI_WG
-#define SNAG_EPI_WG 4
+#define SNAG_EPI_WG 2
 #endif
 constexpr int NUM_EPI_WG = SNAG_EPI_WG;       // epilogue warpgroups; WG w owns BN/NUM_EPI_WG consecutive columns of every tile
 constexpr int NUM_EPI_THREADS = 128 * NUM_EPI_WG;
@@ -70,6 +70,21 @@ struct EpiCtx {
   int useq;      // sequence number of the unit within this CTA (parity selects double-buffered per-unit scratch)
   float* scratch;  // EPI_SCRATCH_BYTES of shared memory private to the epilogue warpgroup
 };
+
+// Control warps (TMA producer, UMMA issuer): by default the whole warp walks the loop and one elected lane issues
+// (convergent code, uniform datapath). SNAG_CTRL_CONVERGED=0 builds the single-lane form for A/B measurements.
+#ifndef SNAG_CTRL_CONVERGED
+#define SNAG_CTRL_CONVERGED 1
+#endif
+#if SNAG_CTRL_CONVERGED
+#define SNAG_CTRL_ENTER true
+#define SNAG_CTRL_LEADER elect_one_sync()
+#define SNAG_CTRL_SYNC() __syncwarp()
+#else
+#define SNAG_CTRL_ENTER (lane == 0)
+#define SNAG_CTRL_LEADER 1u
+#define SNAG_CTRL_SYNC()
+#endif
 
 // registers carrying one column's prefetched per-tile values from tile_prefetch to tile_commit
 struct EpiPre {
@@ -135,9 +150,9 @@ sim_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
     // The whole warp walks the loop (so the code is convergent and stays on the uniform datapath); one elected
     // lane arms the barrier and issues the two bulk-tensor copies. Kept as short as possible: under a busy
     // epilogue every instruction of this warp waits for an issue slot.
-    const uint32_t leader = elect_one_sync();
+    const uint32_t leader = SNAG_CTRL_LEADER;
     uint32_t stage = 0, phase = 0;
-    for (int u = blockIdx.x; u < shp.n_units; u += gridDim.x) {
+    for (int u = blockIdx.x; SNAG_CTRL_ENTER && u < shp.n_units; u += gridDim.x) {
       const int rb = u % shp.row_blocks, ch = u / shp.row_blocks;
       const int ct0 = ch * shp.tiles_per_chunk;
       const int ct1 = min(ct0 + shp.tiles_per_chunk, shp.col_tiles);
@@ -150,7 +165,7 @@ sim_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
             tma_load_2d(sa, &tmX, full_bar(stage), kb * BK, rb * BM);
             tma_load_2d(sa + A_STAGE_BYTES, &tmY, full_bar(stage), kb * BK, ct * BN);
           }
-          __syncwarp();
+          SNAG_CTRL_SYNC();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -158,14 +173,14 @@ sim_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
   } else if (cwarp == 1) {
     // ------------------------------------------------------------------ UMMA issuer (same structure)
     constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
-    const uint32_t leader = elect_one_sync();
+    const uint32_t leader = SNAG_CTRL_LEADER;
     const uint64_t adesc0 = make_sdesc_k128(base);
     const uint64_t bdesc0 = make_sdesc_k128(base + A_STAGE_BYTES);
     uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
     const bool dbg = shp.dbg != nullptr;
     long long w_acc = 0, n_tiles = 0;
     const long long t_begin = dbg ? clock64() : 0;
-    for (int u = blockIdx.x; u < shp.n_units; u += gridDim.x) {
+    for (int u = blockIdx.x; SNAG_CTRL_ENTER && u < shp.n_units; u += gridDim.x) {
       const int ch = u / shp.row_blocks;
       const int ct0 = ch * shp.tiles_per_chunk;
       const int ct1 = min(ct0 + shp.tiles_per_chunk, shp.col_tiles);
@@ -189,12 +204,12 @@ sim_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
             umma_bf16_ss(tmem_d, adesc + 6u, bdesc + 6u, idesc, 1u);
             umma_commit(empty_bar(stage));           // smem slot free once these MMAs retire
           }
-          __syncwarp();
+          SNAG_CTRL_SYNC();
           accumulate = 1;
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         if (leader) umma_commit(tfull_bar(as));      // accumulator complete -> epilogue
-        __syncwarp();
+        SNAG_CTRL_SYNC();
         if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
       }
     }

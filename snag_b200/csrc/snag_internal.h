@@ -7,7 +7,10 @@
 namespace snag {
 
 constexpr int KT_LIST = 16;   // candidate-list length of the CSLS top-k path (must equal KT in simgemm.cuh)
-constexpr int LISTS_PER_CHUNK = 4;   // partial per-row outputs per column chunk (= epilogue warpgroups)
+#ifndef SNAG_EPI_WG
+#define SNAG_EPI_WG 2
+#endif
+constexpr int LISTS_PER_CHUNK = SNAG_EPI_WG;   // partial per-row outputs per column chunk (= epilogue warpgroups)
 
 int num_sms();                // SM count of the current device (cached per device)
 int device_is_sm100();        // 1 if the current device is compute capability 10.x
