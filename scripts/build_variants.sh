@@ -15,9 +15,11 @@ build() {  # name, extra flags
   nvcc -shared -o snag_b200/_variants/lib_$name.so $objs -gencode arch=compute_100a,code=sm_100a
   rm -f $objs
 }
-build base
-build wg2 -DSNAG_EPI_WG=2
-build single -DSNAG_CTRL_CONVERGED=0
-build hint1000 -DSNAG_TRYWAIT_HINT_NS=1000
-build wg2_hint -DSNAG_EPI_WG=2 -DSNAG_TRYWAIT_HINT_NS=1000
+if [ $# -eq 0 ]; then
+  build base
+  build wg4 -DSNAG_EPI_WG=4
+else
+  # usage: build_variants.sh name1 "flags1" name2 "flags2" ...
+  while [ $# -gt 0 ]; do build $1 $2; shift 2; done
+fi
 ls -la snag_b200/_variants/

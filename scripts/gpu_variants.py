@@ -24,8 +24,21 @@ def worker():
     gg = torch.zeros(n, device="cuda") + 0.9
     cr = torch.zeros(n, dtype=torch.int32, device="cuda"); cc = torch.zeros(n, dtype=torch.int32, device="cuda")
     out = {}
-    for name, fn in (("topk", lambda: ops.eval_rowtopk(X, Y, xn, yn, n, n)),
+    # two-sweep inputs: column thresholds from a sample pre-pass, exactly as evaluate._align_ranks_steps builds them
+    m, cap = evaluate.two_sweep_plan(n, k)
+    sel = torch.randperm(n, generator=torch.Generator(device="cpu").manual_seed(3408))[:m].sort()[0].cuda()
+    part_s = ops.eval_rowtopk(Y, X.index_select(0, sel), yn, xn.index_select(0, sel), n, m)
+    _, cand_s = ops.topk_merge_mean(part_s, k, want_nv=False, want_cand=True)
+    colthr, colb = ops.col_threshold(cand_s, k, yn)
+    _, _, scnt = ops.eval_rowcoltopk(X, Y, xn, yn, n, n, colthr, colb, cap)
+    out["cands_per_col"] = round(float(scnt.sum().item()) / n, 1)
+    only = os.environ.get("SNAG_VARIANT_KERNELS", "mainloop,topk,rowcol,rank").split(",")
+    for name, fn in (("mainloop", lambda: ops.sim_mainloop_only(X, Y, n, n)),
+                     ("topk", lambda: ops.eval_rowtopk(X, Y, xn, yn, n, n)),
+                     ("rowcol", lambda: ops.eval_rowcoltopk(X, Y, xn, yn, n, n, colthr, colb, cap)),
                      ("rank", lambda: ops.eval_rank(X, Y, xn, yn, nv, nv, gg, gg, 0, 0, n, n, True, cr, cc))):
+        if name not in only:
+            continue
         fn(); torch.cuda.synchronize()
         clk, pw, stop = [], [], threading.Event()
 
@@ -51,7 +64,7 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "--worker":
         worker(); sys.exit(0)
     vdir = os.path.join(ROOT, "snag_b200", "_variants")
-    order = ["base", "wg2", "single", "hint1000", "wg2_hint", "base"]
+    order = sys.argv[1:] or ["base", "wg4", "base"]
     for v in order:
         env = dict(os.environ, SNAG_B200_LIB=os.path.join(vdir, f"lib_{v}.so"))
         r = subprocess.run([sys.executable, os.path.abspath(__file__), "--worker"], env=env, capture_output=True, text=True, timeout=300)
