@@ -43,6 +43,14 @@ WORKLOADS = {
     "c2": (10_500, 1800, 10, 8.0, "configs[1] DBP15K fr_en-shaped + surface eval, 10 500 test pairs, D=1800, CSLS k=10"),
     "c3": (10_277, 1200, 10, 8.0, "configs[2] FBDB15K-shaped eval, 10 277 test pairs, D=1200, CSLS k=10"),
 }
+# loss-layer slice of one training step: name -> (batch B, modalities M, width per modality, description)
+TRAIN_WORKLOADS = {
+    "c5_train": (16384, 6, 300, "configs[4] large-batch ICL: B=16384 in-batch negatives, 6 streams x 300 (+ joint 1800), "
+                                "2 + 2*6 icl_loss calls fwd+bwd per step"),
+    "c2_train": (3500, 6, 300, "configs[1] DBP15K fr_en + surface: B=3500, 6 streams x 300 (+ joint 1800), 14 icl_loss calls"),
+    "c1_train": (3500, 4, 300, "configs[0] DBP15K ja_en: B=3500, 4 streams x 300 (+ joint 1200), 10 icl_loss calls"),
+}
+TRAIN_METRIC = "train steps/sec (loss-layer slice: 2+2M icl_loss fwd+bwd)"
 DEFAULT_WORKLOAD = "c4_1m"
 SEED = 3408                       # the reference's scripted seed (run.sh:2)
 CPU_SAMPLE_N = 4096               # bounded sample for the CPU legs: a CPU_SAMPLE_N x CPU_SAMPLE_N sub-problem
@@ -264,7 +272,7 @@ def run_snag(args, name, n, d, k, sigma, desc):
     launches_per_step = res.launches + 2
     # per-kernel durations of the fused sweeps (this rank), algorithmic flops = 2 * rows * cols * D per launch
     kern = {}
-    for nm, a, b, rows, cols in sweep_events:
+    for nm, a, b, rows, cols, _depth in sweep_events:
         kern.setdefault(nm, {"ms": [], "flops": 2.0 * rows * cols * d})["ms"].append(a.elapsed_time(b))
     kstats = {nm: {"launches": len(v["ms"]), "avg_ms": sum(v["ms"]) / len(v["ms"]),
                    "tflops": v["flops"] / (sum(v["ms"]) / len(v["ms"])) / 1e9} for nm, v in kern.items()}
@@ -347,16 +355,227 @@ def run_snag(args, name, n, d, k, sigma, desc):
         dist.destroy_process_group()
 
 
+# ================================================================================================ training slice
+def _train_tables(B, M, dm, device, seed=SEED):
+    """Stand-ins for the encoder outputs of one step (model/SNAG.py:101-102): M modality embeddings and M hidden-state
+    embeddings [N, dm], two joint embeddings [N, M*dm], modality weights [N, M]; N = 2B + 1000 entities, B random links."""
+    import numpy as np
+    import torch
+    g = torch.Generator(device=device).manual_seed(seed)
+    n_ent = 2 * B + 1000
+    mk = lambda w: torch.randn((n_ent, w), generator=g, device=device).requires_grad_(True)
+    present = [True] * M + [False] * (6 - M)              # (gph, rel, att, img, name, char): surface streams last
+    streams = [mk(dm) if p else None for p in present]
+    hidden = [mk(dm) if p else None for p in present]
+    joint, joint_fz = mk(M * dm), mk(M * dm)
+    wn = torch.softmax(torch.randn((n_ent, 6), generator=g, device=device), 1).requires_grad_(True)
+    rng = np.random.RandomState(seed)
+    links = np.stack([rng.permutation(n_ent // 2)[:B], n_ent // 2 + rng.permutation(n_ent // 2)[:B]], 1).astype(np.int32)
+    leaves = [t for t in streams + hidden + [joint, joint_fz, wn] if t is not None]
+    return streams, hidden, joint, joint_fz, wn, links, leaves
+
+
+def cpu_icl_sample(B_s, M, dm, steps, B_full=None):
+    """The reference's icl_loss op sequence (model/SNAG_loss.py:58-128: normalise, 4 matmuls, -1e9 self mask, concat,
+    log_softmax against one-hot labels, weighted mean) restated with the same torch CPU calls, forward + backward, for
+    the 2 + 2M calls of one step at batch B_s, all host threads."""
+    import torch
+    import torch.nn.functional as F
+    torch.set_num_threads(os.cpu_count() or 1)
+    g = torch.Generator().manual_seed(SEED)
+    n_ent = 2 * B_s + 100
+    links = torch.stack([torch.randperm(n_ent // 2, generator=g)[:B_s], n_ent // 2 + torch.randperm(n_ent // 2, generator=g)[:B_s]], 1)
+
+    def icl(emb, w):
+        z = F.normalize(emb, dim=1)
+        a, b = z[links[:, 0]], z[links[:, 1]]
+        eye = torch.eye(B_s) * 1e9
+        lab = F.one_hot(torch.arange(B_s), 2 * B_s).float()
+        la = torch.cat([a @ b.t(), a @ a.t() - eye], 1) / 0.1
+        lb = torch.cat([b @ a.t(), b @ b.t() - eye], 1) / 0.1
+        wt = torch.ones(B_s) if w is None else torch.min(w[links[:, 0]], w[links[:, 1]])
+        xa = -(wt * (lab * F.log_softmax(la, 1)).sum(1)).sum() / B_s
+        xb = -(wt * (lab * F.log_softmax(lb, 1)).sum(1)).sum() / B_s
+        return 0.5 * xa + 0.5 * xb
+
+    embs = [torch.randn((n_ent, dm), generator=g).requires_grad_(True) for _ in range(2 * M)]
+    joints = [torch.randn((n_ent, M * dm), generator=g).requires_grad_(True) for _ in range(2)]
+    w = torch.rand((n_ent,), generator=g)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        tot = sum(icl(e, w if i < M else None) for i, e in enumerate(embs)) + sum(icl(j, None) for j in joints)
+        tot.backward()
+    dt = (time.perf_counter() - t0) / steps
+    scale = 1.0 if not B_full else (B_s / float(B_full)) ** 2          # every term of the step is O(B^2 D)
+    return {"value": scale / dt, "unit": "steps/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"one step at batch {B_s} ({2 + 2 * M} icl_loss calls fwd+bwd, the reference's torch op sequence on CPU "
+                      f"tensors), {steps} timed step(s), {dt * 1e3:.0f} ms each, scaled by (B_s/B)^2 = {scale:.4g} to the "
+                      f"workload's batch (the step is O(B^2 D))"}
+
+
+def run_train(args, name):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from snag_b200 import loss as sloss, ops
+
+    B, M, dm, desc = TRAIN_WORKLOADS[name]
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        if rank == 0:
+            cb = cpu_icl_sample(min(B, 2048), M, dm, max(1, args.steps), B)
+            print(json.dumps({"impl": "reference", "metric": TRAIN_METRIC, "value": cb["value"], "unit": "steps/s",
+                              "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / cb["value"],
+                              "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                              "config": {"workload": name, "description": desc, "sampled": cb["sample"]}, "cpu_baseline": cb,
+                              "e2e": {"value": cb["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                              "gpu_launches": 0}), flush=True)
+        return
+    if world != args.gpus:
+        raise SystemExit(f"WORLD_SIZE={world} does not match --gpus {args.gpus}")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    group = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        group = dist.group.WORLD
+    peaks = load_peaks()
+    W, K = max(3, args.warmup), max(1, args.steps)
+    streams, hidden, joint, joint_fz, wn, links, leaves = _train_tables(B, M, dm, dev)
+    layer = sloss.SnagLossLayer(tau=0.1, ab_weight=0.5, awloss=True).to(dev)
+    if group is not None:
+        layer.distribute(group, grads="gather")
+    links_pinned = torch.from_numpy(links).pin_memory()
+
+    links_dev = links_pinned.to(dev)
+    use_graph = not args.no_graph and (world == 1 or args.graph_multi)
+    eager_ms = None
+
+    def eager_step():
+        for t in leaves:
+            t.grad = None
+        loss = layer(streams, hidden, joint, joint_fz, links_dev, wn)
+        loss.backward()
+        return loss
+
+    if use_graph:
+        # the eager step first, for the record: at the reference's batch sizes it is launch bound
+        for _ in range(3):
+            eager_step()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(K):
+            eager_step()
+        b.record()
+        torch.cuda.synchronize()
+        eager_ms = a.elapsed_time(b) / K
+        from snag_b200.graphs import GraphedStep
+        graphed = GraphedStep(lambda: layer(streams, hidden, joint, joint_fz, links_dev, wn), leaves)
+
+    def step(from_host):
+        if from_host:                                       # this step's batch arrives from pinned host memory
+            links_dev.copy_(links_pinned, non_blocking=True)
+        loss = graphed() if use_graph else eager_step()
+        return loss.item() if from_host else loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(W):
+        step(False)
+    barrier()
+    events = []
+    if not use_graph:
+        ops.SWEEP_EVENT_SINK = events
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        barrier()
+        e0.record()
+        for _ in range(K):
+            step(False)
+        e1.record()
+        barrier()
+    ops.SWEEP_EVENT_SINK = events
+    ms = torch.tensor([e0.elapsed_time(e1) / K], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(ms.item())
+    if use_graph:                     # per-kernel CUDA events cannot be recorded into a replayed graph: time the sweeps of
+        for _ in range(K):            # K eager steps of the same work instead (same kernels, same arguments)
+            eager_step()
+        torch.cuda.synchronize()
+    ops.SWEEP_EVENT_SINK = None
+    kern = {}
+    for nm, a, b, rows, cols, depth in events:
+        e = kern.setdefault(nm, {"ms": 0.0, "flops": 0.0, "launches": 0})
+        e["ms"] += a.elapsed_time(b)
+        e["flops"] += 2.0 * rows * cols * depth
+        e["launches"] += 1
+    kstats = {nm: {"launches_per_step": v["launches"] // K, "ms_per_step": v["ms"] / K, "tflops": v["flops"] / v["ms"] / 1e9}
+              for nm, v in kern.items()}
+    dom = max(kstats, key=lambda nm: kstats[nm]["ms_per_step"])
+    n_calls = 2 + 2 * M
+    d_sum = 2 * M * dm + 2 * M * dm                        # sum of the contraction widths over the calls
+    alg_fwd = 6.0 * B * B * d_sum                          # SURVEY 8(d): 3 distinct B x B x D contractions per call
+    alg_bwd = 14.0 * B * B * d_sum
+    roofline = {"bound": "tensor", "kernel": dom, "achieved": kstats[dom]["tflops"], "peak": peaks["tensor_burst"],
+                "unit": "TFLOP/s", "frac": kstats[dom]["tflops"] / peaks["tensor_burst"], "traffic": None,
+                "peak_source": peaks["source"] + ", bf16_tflops (burst: launches of a few ms, timed alone with CUDA events)",
+                "kernels": kstats, "note": "flops counted on the padded contraction width the kernel executes; "
+                "sim_kernel<EpiWrite> is the gradient GEMM dX = G.[other;this] (contraction width 2*Bp)",
+                "algorithmic_flops_per_step": alg_fwd + alg_bwd,
+                "algorithmic_tflops_whole_step": (alg_fwd + alg_bwd) / world / ms_per_step / 1e9}
+    # end to end: the step's input (the batch of links) comes from pinned host memory, the loss goes back to the host
+    step(True)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        lv = step(True)
+    barrier()
+    dt = torch.tensor([(time.perf_counter() - t0) / K], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        cb = cpu_icl_sample(min(B, 2048), M, dm, 1, B)
+        line = {"metric": TRAIN_METRIC, "value": 1e3 / ms_per_step, "unit": "steps/s", "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "bf16 operands, fp32 accumulate (tcgen05 kind::f16), fp32 softmax statistics, bf16 dL/dlogits",
+                "data": "synthetic",
+                "config": {"workload": name, "description": desc, "batch": B, "modalities": M, "width": dm, "tau": 0.1,
+                           "icl_calls_per_step": n_calls, "parallelism": f"anchors sharded over {world} rank(s)",
+                           "cuda_graph": use_graph, "eager_ms_per_step": eager_ms,
+                           "l2": "every step rewrites the bf16 operands and dL/dlogits (> L2) between launches"},
+                "clocks": clocks.summary(),
+                "e2e": {"value": 1.0 / float(dt.item()), "unit": "steps/s", "h2d_bytes_per_step": int(links_pinned.numel() * 4),
+                        "d2h_bytes_per_step": 4, "ms_per_step": float(dt.item()) * 1e3, "loss": lv},
+                "gpu_launches": sum(v["launches"] for v in kern.values()) + 4 * n_calls * K,
+                "roofline": roofline, "cpu_baseline": cb}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default=os.environ.get("SNAG_BENCH_WORKLOAD", DEFAULT_WORKLOAD), choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=os.environ.get("SNAG_BENCH_WORKLOAD", DEFAULT_WORKLOAD), choices=sorted(WORKLOADS) + sorted(TRAIN_WORKLOADS))
     ap.add_argument("--impl", default="snag", choices=["snag", "reference"])
+    ap.add_argument("--graph-multi", action="store_true", help="training slice: capture the NCCL exchanges in the graph too (N > 1)")
+    ap.add_argument("--no-graph", action="store_true", help="training slice: run the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--profile-run", action="store_true",
                     help="only the device-resident timed region (for runs under ncu); e2e and CPU legs are skipped")
     args = ap.parse_args()
+    if args.workload in TRAIN_WORKLOADS:
+        run_train(args, args.workload)
+        return
     n, d, k, sigma, desc = WORKLOADS[args.workload]
     if args.impl == "reference":
         run_reference(args, args.workload, n, d, k, sigma, desc)

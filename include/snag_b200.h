@@ -153,22 +153,27 @@ int snag_csls_sim(const float* sim, int64_t n1, int64_t n2, int64_t ld, int32_t 
                   float* nv2, void* workspace, void* stream);
 
 /* ---- ICL loss --------------------------------------------------------------------------------- */
-/* One side of icl_loss.forward (model/SNAG_loss.py:98-126). X = this side [Bp, Dpad], Y = [other side ; this
- * side] [2*Bp, Dpad], each part zero padded from B to Bp rows (Bp multiple of 256).
- *   rowsum_part[l][i] = partial sum l (of n_lists) of exp(logit_ij - 1/tau), self-similarity excluded
- *   pos[i] = x_i . other_i                       then snag_icl_finalize: lse, nll = lse - pos/tau */
-int snag_icl_rowsum(const uint16_t* X, const uint16_t* Y, int32_t B, int32_t Bp, int32_t Dpad, float inv_tau,
-                    float* rowsum_part, float* pos, void* stream);
+/* One side of icl_loss.forward (model/SNAG_loss.py:98-126). Y = [other side ; this side] [2*Bp, Dpad], each part zero
+ * padded from B to Bp rows (Bp multiple of 256). X = nx anchors of this side starting at batch index row0 (the whole
+ * side: row0 = 0, nx = Bp; a rank of the anchor-sharded loss passes its own rows), [nx, Dpad], 128-byte aligned.
+ *   rowsum_part[l][i] = partial sum l (of n_lists = snag_sim_plan(nx, 2*Bp)) of exp(logit_ij - 1/tau), self-similarity
+ *                       excluded; i = local row, row stride nx
+ *   pos[i] = x_i . other_(row0+i)                then snag_icl_finalize(.., B = valid local rows, Bp = nx, ..):
+ *                                                lse, nll = lse - pos/tau */
+int snag_icl_rowsum(const uint16_t* X, const uint16_t* Y, int32_t B, int32_t Bp, int32_t row0, int32_t nx, int32_t Dpad,
+                    float inv_tau, float* rowsum_part, float* pos, void* stream);
 int snag_icl_finalize(const float* rowsum_part, int32_t n_lists, int32_t B, int32_t Bp, const float* pos,
                       float inv_tau, float* lse, float* nll, void* stream);
 
-/* ICL backward, stage 1: recompute one side's logits and write dL/dlogits as bf16 G [Bp, 2*Bp] (same X / Y views
- * as snag_icl_rowsum). With g_x = dL/dnll_x (upstream) and lse_x from the forward:
+/* ICL backward, stage 1: recompute one side's logits and write dL/dlogits as bf16 G [nx, 2*Bp] (same X / Y views
+ * as snag_icl_rowsum; cr, cc, dg are [B], indexed by batch index). With g_x = dL/dnll_x (upstream) and lse_x from the
+ * forward:
  *   cr[i] = g_this[i]*exp(1/tau - lse_this[i]), cc[j] = g_other[j]*exp(1/tau - lse_other[j]), dg[i] = g_this[i]+g_other[i]
  * Stage 2 is a plain contraction dX = G . [other ; this], run with snag_sim_write(mode 0) on G and the
  * transposed stacked operand. */
-int snag_icl_bwd_logits(const uint16_t* X, const uint16_t* Y, int32_t B, int32_t Bp, int32_t Dpad, float inv_tau,
-                        const float* cr, const float* cc, const float* dg, uint16_t* G, void* stream);
+int snag_icl_bwd_logits(const uint16_t* X, const uint16_t* Y, int32_t B, int32_t Bp, int32_t row0, int32_t nx,
+                        int32_t Dpad, float inv_tau, const float* cr, const float* cc, const float* dg, uint16_t* G,
+                        void* stream);
 
 #ifdef __cplusplus
 }

@@ -111,9 +111,9 @@ int snag_csls_sim(const float* sim, int64_t n1, int64_t n2, int64_t ld, int32_t 
   return launch_csls_sim(sim, n1, n2, ld, k, out, ld_out, nv1, nv2, reinterpret_cast<float*>(workspace), S(stream));
 }
 
-int snag_icl_rowsum(const uint16_t* X, const uint16_t* Y, int32_t B, int32_t Bp, int32_t Dpad, float inv_tau,
-                    float* rowsum_part, float* pos, void* stream) {
-  return launch_icl_rowsum(BF(X), BF(Y), B, Bp, Dpad, inv_tau, rowsum_part, pos, S(stream));
+int snag_icl_rowsum(const uint16_t* X, const uint16_t* Y, int32_t B, int32_t Bp, int32_t row0, int32_t nx, int32_t Dpad,
+                    float inv_tau, float* rowsum_part, float* pos, void* stream) {
+  return launch_icl_rowsum(BF(X), BF(Y), B, Bp, row0, nx, Dpad, inv_tau, rowsum_part, pos, S(stream));
 }
 int snag_icl_finalize(const float* rowsum_part, int32_t n_lists, int32_t B, int32_t Bp, const float* pos,
                       float inv_tau, float* lse, float* nll, void* stream) {
@@ -144,10 +144,11 @@ int snag_col_cand_finalize(const int64_t* offs, const int32_t* hist, const float
   return launch_col_cand_finalize(reinterpret_cast<const long long*>(offs), hist, vals, n, k, nv, overflow, S(stream));
 }
 
-int snag_icl_bwd_logits(const uint16_t* X, const uint16_t* Y, int32_t B, int32_t Bp, int32_t Dpad, float inv_tau,
-                        const float* cr, const float* cc, const float* dg, uint16_t* G, void* stream) {
-  return launch_icl_bwd_logits(BF(X), BF(Y), B, Bp, Dpad, inv_tau, cr, cc, dg, reinterpret_cast<__nv_bfloat16*>(G),
-                               S(stream));
+int snag_icl_bwd_logits(const uint16_t* X, const uint16_t* Y, int32_t B, int32_t Bp, int32_t row0, int32_t nx,
+                        int32_t Dpad, float inv_tau, const float* cr, const float* cc, const float* dg, uint16_t* G,
+                        void* stream) {
+  return launch_icl_bwd_logits(BF(X), BF(Y), B, Bp, row0, nx, Dpad, inv_tau, cr, cc, dg,
+                               reinterpret_cast<__nv_bfloat16*>(G), S(stream));
 }
 
 }  // extern "C"

@@ -180,11 +180,12 @@ int launch_eval_rank(const __nv_bfloat16* X, const __nv_bfloat16* Y, const float
 #undef SNAG_RANK_CASE
 }
 
-int launch_icl_rowsum(const __nv_bfloat16* X, const __nv_bfloat16* Y, int B, int Bp, int Dpad, float inv_tau,
-                      float* rowsum_part, float* pos, cudaStream_t st) {
+int launch_icl_rowsum(const __nv_bfloat16* X, const __nv_bfloat16* Y, int B, int Bp, int row0, int nx, int Dpad,
+                      float inv_tau, float* rowsum_part, float* pos, cudaStream_t st) {
   if (!rowsum_part || !pos || B <= 0 || Bp < B || (Bp % BN) != 0) return SNAG_ERR_ARG;
-  EpiIclFwd::Params p{inv_tau * 1.4426950408889634f, B, Bp, rowsum_part, pos};
-  return launch_sim<EpiIclFwd>(X, Y, Bp, 2 * Bp, Dpad, p, st);
+  if (row0 < 0 || nx <= 0 || row0 + nx > Bp) return SNAG_ERR_ARG;
+  EpiIclFwd::Params p{inv_tau * 1.4426950408889634f, B, Bp, row0, nx, rowsum_part, pos};
+  return launch_sim<EpiIclFwd>(X, Y, nx, 2 * Bp, Dpad, p, st);
 }
 
 int launch_eval_rowcoltopk(const __nv_bfloat16* X, const __nv_bfloat16* Y, const float* xn, const float* yn, int n1, int n2,
@@ -196,12 +197,14 @@ int launch_eval_rowcoltopk(const __nv_bfloat16* X, const __nv_bfloat16* Y, const
   return launch_sim<EpiRowColTopK>(X, Y, n1, n2, Dpad, p, st);
 }
 
-int launch_icl_bwd_logits(const __nv_bfloat16* X, const __nv_bfloat16* Y, int B, int Bp, int Dpad, float inv_tau,
-                          const float* cr, const float* cc, const float* dg, __nv_bfloat16* G, cudaStream_t st) {
+int launch_icl_bwd_logits(const __nv_bfloat16* X, const __nv_bfloat16* Y, int B, int Bp, int row0, int nx, int Dpad,
+                          float inv_tau, const float* cr, const float* cc, const float* dg, __nv_bfloat16* G,
+                          cudaStream_t st) {
   if (!cr || !cc || !dg || !G || B <= 0 || Bp < B || (Bp % BN) != 0) return SNAG_ERR_ARG;
+  if (row0 < 0 || nx <= 0 || row0 + nx > Bp) return SNAG_ERR_ARG;
   if (reinterpret_cast<uintptr_t>(G) & 15) return SNAG_ERR_ALIGN;
-  EpiIclBwd::Params p{inv_tau * 1.4426950408889634f, inv_tau, B, Bp, cr, cc, dg, G};
-  return launch_sim<EpiIclBwd>(X, Y, Bp, 2 * Bp, Dpad, p, st);
+  EpiIclBwd::Params p{inv_tau * 1.4426950408889634f, inv_tau, B, Bp, row0, nx, cr, cc, dg, G};
+  return launch_sim<EpiIclBwd>(X, Y, nx, 2 * Bp, Dpad, p, st);
 }
 
 }  // namespace snag

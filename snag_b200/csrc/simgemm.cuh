@@ -822,12 +822,14 @@ struct EpiRank {
 
 // ------------------------------------------------------------------------------------------------
 // Epilogue: in-batch contrastive row sums (ICL forward, model/SNAG_loss.py:98-126).
-// X view = one side of the batch (Bp rows, B valid); Y view = [other side | same side], 2*Bp rows.
-// Column c -> part p = c / Bp, idx = c - p*Bp; valid iff idx < B. p == 1 and idx == row is the
-// self-similarity the reference kills with -1e9; p == 0 and idx == row is the positive logit.
+// X view = rows [row0, row0 + nx) of one side of the batch (the anchors this rank owns; the whole side when the
+// loss is not sharded); Y view = [other side | same side], 2*Bp rows, B valid per part.
+// Column c -> part p = c / Bp, idx = c - p*Bp; valid iff idx < B. With gr = row0 + row the anchor's index in the
+// batch: p == 1 and idx == gr is the self-similarity the reference kills with -1e9; p == 0 and idx == gr is the
+// positive logit.
 // With unit-norm rows logits are bounded by 1/tau, so exp(logit - 1/tau) needs no running max.
-//   rowsum_part[chunk][row] = sum_j exp2(s_ij * (log2e/tau) - log2e/tau)
-//   pos[row]                = s_{row,row} of part 0
+//   rowsum_part[list][row] = sum_j exp2(s_ij * (log2e/tau) - log2e/tau)       (row = local row, stride nx)
+//   pos[row]               = s_{row,gr} of part 0
 // ------------------------------------------------------------------------------------------------
 struct EpiIclFwd {
   static constexpr bool kNoLoad = false;
@@ -835,8 +837,10 @@ struct EpiIclFwd {
     float scale_log2;   // log2(e) / tau
     int B;              // valid rows per part
     int Bp;             // padded rows per part (multiple of 256)
-    float* rowsum_part; // [n_lists][Bp]
-    float* pos;         // [Bp]
+    int row0;           // batch index of X-view row 0
+    int nx;             // rows of the X view
+    float* rowsum_part; // [n_lists][nx]
+    float* pos;         // [nx]
   };
   struct State {
     float sum;
@@ -852,7 +856,8 @@ struct EpiIclFwd {
     const int part = col0 >= p.Bp ? 1 : 0;
     const int idx0 = col0 - part * p.Bp;
     if (idx0 >= p.B) return;                              // strip entirely in the padding (warp-uniform)
-    const bool plain = (idx0 + 32 <= p.B) && (idx0 + 31 < cx.rb * BM || idx0 > cx.rb * BM + BM - 1);
+    const int gr0 = p.row0 + cx.rb * BM;                 // batch index of the row block's first anchor
+    const bool plain = (idx0 + 32 <= p.B) && (idx0 + 31 < gr0 || idx0 > gr0 + BM - 1);
     const float nb = -p.scale_log2;
     if (plain) {
       float acc = 0.f;
@@ -866,7 +871,7 @@ struct EpiIclFwd {
         const float s = __uint_as_float(r[q]);
         float e = ex2_approx(__fmaf_rn(s, p.scale_log2, nb));
         if (idx >= p.B) e = 0.f;
-        if (idx == cx.row) {
+        if (idx == p.row0 + cx.row) {
           if (part == 1) e = 0.f;
           else if (cx.row_ok) p.pos[cx.row] = s;
         }
@@ -876,7 +881,7 @@ struct EpiIclFwd {
   }
   static __device__ __forceinline__ void tile_end(const Params&, const SimShape&, const EpiCtx&, State&, int, int) {}
   static __device__ __forceinline__ void unit_end(const Params& p, const SimShape&, const EpiCtx& cx, State& st) {
-    if (cx.row < p.Bp) p.rowsum_part[static_cast<long long>(cx.list) * p.Bp + cx.row] = st.sum;
+    if (cx.row_ok) p.rowsum_part[static_cast<long long>(cx.list) * p.nx + cx.row] = st.sum;
   }
 };
 
@@ -888,7 +893,8 @@ struct EpiIclFwd {
 //   part 1 (self) :  G[i,j] = (cr_i + cr_j) * E_ij / tau            (0 on the diagonal)
 // where E_ij = exp(s_ij/tau - 1/tau), cr_i = g_this[i] * exp(1/tau - lse_this[i]) (row softmax term),
 // cc_j = g_other[j] * exp(1/tau - lse_other[j]) (the same s_ij seen from the other side's softmax),
-// dg_i = g_this[i] + g_other[i]. Rows >= B and columns in the padding are written as zeros.
+// dg_i = g_this[i] + g_other[i]. Anchors >= B and columns in the padding are written as zeros. As in the forward the
+// X view is rows [row0, row0 + nx) of this side; cr / cc / dg are indexed by batch index, G by local row.
 // ------------------------------------------------------------------------------------------------
 struct EpiIclBwd {
   static constexpr bool kNoLoad = false;
@@ -896,18 +902,22 @@ struct EpiIclBwd {
     float scale_log2;     // log2(e) / tau
     float inv_tau;
     int B, Bp;
-    const float* cr;      // [Bp] row-side coefficients (this side)
-    const float* cc;      // [Bp] column-side coefficients of part 0 (other side)
-    const float* dg;      // [Bp] diagonal term of part 0
-    __nv_bfloat16* G;     // [Bp, 2*Bp]
+    int row0, nx;
+    const float* cr;      // [B] row-side coefficients (this side)
+    const float* cc;      // [B] column-side coefficients of part 0 (other side)
+    const float* dg;      // [B] diagonal term of part 0
+    __nv_bfloat16* G;     // [nx, 2*Bp]
   };
   struct State {
     float cr, dg;
+    int gr;               // batch index of this thread's anchor
+    bool ok;
   };
   static __device__ __forceinline__ void unit_begin(const Params& p, const SimShape&, const EpiCtx& cx, State& st) {
-    const bool ok = cx.row < p.B;
-    st.cr = ok ? p.cr[cx.row] : 0.f;
-    st.dg = ok ? p.dg[cx.row] : 0.f;
+    st.gr = p.row0 + cx.row;
+    st.ok = cx.row_ok && st.gr < p.B;
+    st.cr = st.ok ? p.cr[st.gr] : 0.f;
+    st.dg = st.ok ? p.dg[st.gr] : 0.f;
   }
   static __device__ __forceinline__ EpiPre tile_prefetch(const Params& p, const SimShape&, const EpiCtx& cx, int ct) {
     static_assert(NUM_EPI_THREADS >= BN, "one epilogue thread stages one column");
@@ -930,7 +940,7 @@ struct EpiIclBwd {
     const int col0 = ct * BN + c * 32;
     const int part = col0 >= p.Bp ? 1 : 0;
     const int idx0 = col0 - part * p.Bp;
-    const bool row_ok = cx.row < p.B;
+    const bool row_ok = st.ok;
     const float nb = -p.scale_log2;
     uint32_t packed[16];
 #pragma unroll
@@ -941,14 +951,14 @@ struct EpiIclBwd {
         const int idx = idx0 + q + e;
         const float E = ex2_approx(__fmaf_rn(__uint_as_float(r[q + e]), p.scale_log2, nb));
         float gval = (st.cr + cc_s[q + e]) * E * p.inv_tau;
-        if (idx == cx.row) gval = part ? 0.f : gval - st.dg * p.inv_tau;
+        if (idx == st.gr) gval = part ? 0.f : gval - st.dg * p.inv_tau;
         if (!row_ok || idx >= p.B) gval = 0.f;
         v[e] = gval;
       }
       const __nv_bfloat162 h = __floats2bfloat162_rn(v[0], v[1]);
       packed[q / 2] = *reinterpret_cast<const uint32_t*>(&h);
     }
-    if (cx.row < p.Bp) {
+    if (cx.row_ok) {
       uint4* dst = reinterpret_cast<uint4*>(p.G + static_cast<long long>(cx.row) * (2 * p.Bp) + col0);
 #pragma unroll
       for (int q = 0; q < 4; ++q) dst[q] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);

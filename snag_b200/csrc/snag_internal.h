@@ -60,7 +60,7 @@ int launch_eval_rowtopk(const __nv_bfloat16* X, const __nv_bfloat16* Y, const fl
 int launch_eval_rank(const __nv_bfloat16* X, const __nv_bfloat16* Y, const float* xn, const float* yn, const float* nv1,
                      const float* nv2, const float* g_row, const float* g_col, int row_gid0, int col_gid0, int n1, int n2,
                      int Dpad, int use_csls, int* cnt_row, int* cnt_col, float* top3_val, int* top3_idx, cudaStream_t st);
-int launch_icl_rowsum(const __nv_bfloat16* X, const __nv_bfloat16* Y, int B, int Bp, int Dpad, float inv_tau,
+int launch_icl_rowsum(const __nv_bfloat16* X, const __nv_bfloat16* Y, int B, int Bp, int row0, int nx, int Dpad, float inv_tau,
                       float* rowsum_part, float* pos, cudaStream_t st);
 
 int launch_eval_rowcoltopk(const __nv_bfloat16* X, const __nv_bfloat16* Y, const float* xn, const float* yn, int n1, int n2,
@@ -73,7 +73,7 @@ int launch_cand_scatter(const uint2* stream, const int* stream_cnt, int n_ctas, 
                         int* cursor, float* vals, cudaStream_t st);
 int launch_col_cand_finalize(const long long* offs, const int* hist, const float* vals, long long n, int k, float* nv,
                              int* overflow, cudaStream_t st);
-int launch_icl_bwd_logits(const __nv_bfloat16* X, const __nv_bfloat16* Y, int B, int Bp, int Dpad, float inv_tau,
+int launch_icl_bwd_logits(const __nv_bfloat16* X, const __nv_bfloat16* Y, int B, int Bp, int row0, int nx, int Dpad, float inv_tau,
                           const float* cr, const float* cc, const float* dg, __nv_bfloat16* G, cudaStream_t st);
 
 }  // namespace snag

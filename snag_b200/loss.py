@@ -59,41 +59,120 @@ def _links_to_index(train_links, device):
     return links[:, 0].contiguous(), links[:, 1].contiguous()
 
 
+class AnchorShard:
+    """How the anchors (rows) of an in-batch contrastive loss are split over the ranks of a process group
+    (every rank holds the whole batch of embeddings — the encoder is replicated — and owns a contiguous
+    block of `per` anchors of each side, which it sweeps against all 2B columns).
+
+    Exchange steps: forward, one all-gather of the per-anchor (lse, nll) of both sides ([4, per] fp32 per rank);
+    backward, with grads="gather", one all-gather of the owned rows of dA and dB ([2, per, D] fp32 per rank) so that
+    every rank returns the full, identical gradient (replicas stay in sync without a gradient all-reduce). With
+    grads="local" each rank returns only its own rows (zeros elsewhere): the SUM over ranks is the full gradient.
+    `be` is the kernel backend (snag_b200.ops; the tests substitute a CPU stand-in to run the host logic under gloo)."""
+
+    def __init__(self, group=None, grads: str = "gather", be=None, world: int | None = None, rank: int | None = None):
+        if grads not in ("gather", "local"):
+            raise ValueError("grads must be 'gather' or 'local'")
+        self.group, self.grads, self.be = group, grads, (ops if be is None else be)
+        if group is not None:
+            import torch.distributed as dist
+            world, rank = dist.get_world_size(group), dist.get_rank(group)
+        self.world, self.rank = (1 if world is None else int(world)), (0 if rank is None else int(rank))
+
+    def bounds(self, B: int) -> tuple[int, int, int]:
+        """(r0, r1, per): this rank owns anchors [r0, r1); `per` = ceil(B / world) rounded up to 128 (one row block)."""
+        per = ops.round_up((B + self.world - 1) // self.world, 128)
+        r0 = min(self.rank * per, B)
+        return r0, min(r0 + per, B), per
+
+    def all_gather(self, t: torch.Tensor) -> torch.Tensor:
+        """[...] per rank -> [world, ...]"""
+        if self.world == 1:
+            return t.unsqueeze(0)
+        import torch.distributed as dist
+        flat = torch.empty((self.world * t.numel(),), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(flat, t.contiguous().reshape(-1), group=self.group)
+        return flat.view(self.world, *t.shape)
+
+
+_UNSHARDED = None
+
+
+def _unsharded() -> AnchorShard:
+    global _UNSHARDED
+    if _UNSHARDED is None:
+        _UNSHARDED = AnchorShard()
+    return _UNSHARDED
+
+
 class _IclPair(torch.autograd.Function):
-    """(zis, zjs) unit rows [B, D] fp32 -> per-row NLL of both directions, fused on the tensor cores."""
+    """(zis, zjs) unit rows [B, D] fp32 -> per-row NLL of both directions, fused on the tensor cores; with an
+    AnchorShard of more than one rank every rank sweeps only its own anchors."""
 
     @staticmethod
-    def forward(ctx, zis, zjs, inv_tau):
+    def forward(ctx, zis, zjs, inv_tau, shard):
+        be = shard.be
         B, D = zis.shape
         Bp = ops.round_up(B, 256)
         dpad = ops.round_up(D, 64)
         # stacked operand [a ; b ; a], every part zero padded to Bp rows: side a sweeps [b ; a], side b sweeps [a ; b]
         S3 = torch.zeros((3 * Bp, dpad), dtype=torch.bfloat16, device=zis.device)
-        ops.prep_bf16(zis.contiguous(), None, normalize=False, out=S3[0:Bp])
-        ops.prep_bf16(zjs.contiguous(), None, normalize=False, out=S3[Bp:2 * Bp])
+        be.prep_bf16(zis.contiguous(), None, normalize=False, out=S3[0:Bp])
+        be.prep_bf16(zjs.contiguous(), None, normalize=False, out=S3[Bp:2 * Bp])
         S3[2 * Bp:2 * Bp + B].copy_(S3[0:B])
-        lse_a, nll_a, _ = ops.icl_side(S3[0:Bp], S3[Bp:3 * Bp], B, Bp, inv_tau)
-        lse_b, nll_b, _ = ops.icl_side(S3[Bp:2 * Bp], S3[0:2 * Bp], B, Bp, inv_tau)
+        r0, r1, per = shard.bounds(B)
+        if shard.world == 1:
+            lse_a, nll_a, _ = be.icl_side(S3[0:Bp], S3[Bp:3 * Bp], B, Bp, inv_tau)
+            lse_b, nll_b, _ = be.icl_side(S3[Bp:2 * Bp], S3[0:2 * Bp], B, Bp, inv_tau)
+        else:
+            loc = torch.zeros((4, per), dtype=torch.float32, device=zis.device)
+            if r1 > r0:
+                nx = r1 - r0
+                la, na, _ = be.icl_side(S3[r0:r0 + nx], S3[Bp:3 * Bp], B, Bp, inv_tau, r0, nx)
+                lb, nb, _ = be.icl_side(S3[Bp + r0:Bp + r0 + nx], S3[0:2 * Bp], B, Bp, inv_tau, r0, nx)
+                loc[0, :nx], loc[1, :nx], loc[2, :nx], loc[3, :nx] = la, na, lb, nb
+            allv = shard.all_gather(loc).permute(1, 0, 2).reshape(4, -1)[:, :B]      # [4, B] in anchor order
+            lse_a, nll_a, lse_b, nll_b = (allv[i].contiguous() for i in range(4))
         ctx.save_for_backward(S3, lse_a, lse_b)
         ctx.dims = (B, D, Bp, inv_tau)
+        ctx.shard = shard
         return nll_a, nll_b
 
     @staticmethod
     def backward(ctx, g_a, g_b):
         S3, lse_a, lse_b = ctx.saved_tensors
         B, D, Bp, inv_tau = ctx.dims
+        shard = ctx.shard
+        be = shard.be
         g_a = torch.zeros_like(lse_a) if g_a is None else g_a.contiguous().float()
         g_b = torch.zeros_like(lse_b) if g_b is None else g_b.contiguous().float()
         cra = (g_a * torch.exp(inv_tau - lse_a)).contiguous()
         crb = (g_b * torch.exp(inv_tau - lse_b)).contiguous()
         dg = (g_a + g_b).contiguous()
-        A, Bm = S3[0:Bp], S3[Bp:2 * Bp]
         Ya, Yb = S3[Bp:3 * Bp], S3[0:2 * Bp]
-        Ga = ops.icl_bwd_logits(A, Ya, B, Bp, inv_tau, cra, crb, dg)         # [Bp, 2Bp] bf16
-        Gb = ops.icl_bwd_logits(Bm, Yb, B, Bp, inv_tau, crb, cra, dg)
-        dA = ops.contract(Ga, Ya.t().contiguous(), B, D)                      # [B, D] fp32
-        dB = ops.contract(Gb, Yb.t().contiguous(), B, D)
-        return dA, dB, None
+        YaT, YbT = Ya.t().contiguous(), Yb.t().contiguous()
+        if shard.world == 1:
+            Ga = be.icl_bwd_logits(S3[0:Bp], Ya, B, Bp, inv_tau, cra, crb, dg)         # [Bp, 2Bp] bf16
+            Gb = be.icl_bwd_logits(S3[Bp:2 * Bp], Yb, B, Bp, inv_tau, crb, cra, dg)
+            return be.contract(Ga, YaT, B, D), be.contract(Gb, YbT, B, D), None, None   # [B, D] fp32 each
+        # sharded: G rows of the owned anchors only. Row i of G already carries every term of dL/d(anchor i) —
+        # its own softmax row and its appearances as a column in the other rows' softmaxes (the cc / cr_j terms of
+        # EpiIclBwd) — so the owned rows of dA, dB are complete and no reduce-scatter is needed.
+        r0, r1, per = shard.bounds(B)
+        loc = torch.zeros((2, per, D), dtype=torch.float32, device=S3.device)
+        if r1 > r0:
+            nx = r1 - r0
+            Ga = be.icl_bwd_logits(S3[r0:r0 + nx], Ya, B, Bp, inv_tau, cra, crb, dg, r0, nx)
+            Gb = be.icl_bwd_logits(S3[Bp + r0:Bp + r0 + nx], Yb, B, Bp, inv_tau, crb, cra, dg, r0, nx)
+            loc[0, :nx] = be.contract(Ga, YaT, nx, D)
+            loc[1, :nx] = be.contract(Gb, YbT, nx, D)
+        if shard.grads == "gather":
+            allg = shard.all_gather(loc).permute(1, 0, 2, 3).reshape(2, -1, D)[:, :B]   # [2, B, D]
+            return allg[0].contiguous(), allg[1].contiguous(), None, None
+        dA = torch.zeros((B, D), dtype=torch.float32, device=S3.device)
+        dB = torch.zeros((B, D), dtype=torch.float32, device=S3.device)
+        dA[r0:r1], dB[r0:r1] = loc[0, :r1 - r0], loc[1, :r1 - r0]
+        return dA, dB, None, None
 
 
 class icl_loss(nn.Module):
@@ -108,6 +187,13 @@ class icl_loss(nn.Module):
         self.intra_weight = intra_weight
         self.inversion = inversion
         self.neg_cross_kg = neg_cross_kg
+        self.shard = None            # AnchorShard, see distribute()
+
+    def distribute(self, group, grads: str = "gather", be=None):
+        """Shard the anchors of every following forward over the ranks of `group` (BASELINE configs[4]).
+        Every rank must call forward with the same batch; the returned loss is identical on all ranks."""
+        self.shard = None if group is None else AnchorShard(group, grads, be)
+        return self
 
     def forward(self, emb, train_links, neg_l=None, neg_r=None, weight_norm=None, norm=True):
         if neg_l is not None or neg_r is not None:
@@ -122,7 +208,7 @@ class icl_loss(nn.Module):
         # normalising only the 2B gathered rows equals normalising all N first (model/SNAG_loss.py:60-64), row by row
         zis = F.normalize(emb.index_select(0, idx_l).float(), dim=1)
         zjs = F.normalize(emb.index_select(0, idx_r).float(), dim=1)
-        nll_a, nll_b = _IclPair.apply(zis, zjs, float(1.0 / self.tau))
+        nll_a, nll_b = _IclPair.apply(zis, zjs, float(1.0 / self.tau), self.shard or _unsharded())
         batch = zis.shape[0]
         if weight_norm is not None:
             w = torch.min(torch.stack([weight_norm[idx_l], weight_norm[idx_r]], dim=1), 1)[0]   # :66-69
@@ -217,3 +303,47 @@ class ial_loss(nn.Module):
             loss_a = loss_a.sum()
             loss_b = loss_b.sum()
         return self.zoom * (alpha * loss_a + (1 - alpha) * loss_b)
+
+
+class SnagLossLayer(nn.Module):
+    """The loss half of SNAG.forward (model/SNAG.py:104-116, 140-160) as one module, with the reference's member names:
+    GMI = criterion_cl_joint(joint_emb) + criterion_cl_joint(joint_emb_fz); ECIA = inner_view_loss over the modality
+    embeddings with the per-modality weights; IIR = inner_view_loss over the hidden-state embeddings;
+    multi_loss_layer (6) inside inner_view_loss, multi_loss_layer_2 (3) on top when `awloss`.
+    That is 2 + 2M icl_loss calls per step for M present modalities — the "loss-layer slice" bench.py times.
+    `streams` / `hidden` are 6-tuples ordered (gph, rel, att, img, name, char) with None for absent modalities."""
+
+    WEIGHT_COLUMN = (3, 2, 1, 0, 4, 5)      # model/SNAG.py:145-150: gph<-w[:,3], rel<-w[:,2], att<-w[:,1], img<-w[:,0], ...
+
+    def __init__(self, tau=0.1, ab_weight=0.5, awloss=True):
+        super().__init__()
+        self.awloss = awloss
+        self.multi_loss_layer = CustomMultiLossLayer(loss_num=6)                         # model/SNAG.py:47
+        self.multi_loss_layer_2 = CustomMultiLossLayer(loss_num=3)
+        self.criterion_cl = icl_loss(tau=tau, ab_weight=ab_weight, n_view=2)             # :50
+        self.criterion_cl_joint = icl_loss(tau=tau, ab_weight=ab_weight, n_view=2)       # :51
+
+    def distribute(self, group, grads: str = "gather"):
+        self.criterion_cl.distribute(group, grads)
+        self.criterion_cl_joint.distribute(group, grads)
+        return self
+
+    def inner_view_loss(self, streams, train_ill, weight_norm=None):
+        losses = []
+        if weight_norm is not None:
+            weight_norm = weight_norm * weight_norm.shape[1]
+        for emb, col in zip(streams, self.WEIGHT_COLUMN):
+            if emb is None:
+                losses.append(0)
+            elif weight_norm is not None:
+                losses.append(self.criterion_cl(emb, train_ill, weight_norm=weight_norm[:, col]))
+            else:
+                losses.append(self.criterion_cl(emb, train_ill))
+        return self.multi_loss_layer(losses)
+
+    def forward(self, streams, hidden, joint_emb, joint_emb_fz, batch, weight_norm):
+        gmi = self.criterion_cl_joint(joint_emb, batch) + self.criterion_cl_joint(joint_emb_fz, batch)
+        ecia = self.inner_view_loss(streams, batch, weight_norm=weight_norm)
+        iir = self.inner_view_loss(hidden, batch)
+        loss_list = [gmi, ecia, iir]
+        return self.multi_loss_layer_2(loss_list) if self.awloss else sum(loss_list)

@@ -77,8 +77,9 @@ def sim_write(X: torch.Tensor, Y: torch.Tensor, xn: torch.Tensor | None, yn: tor
         _need(xn, torch.float32, "xn", 1)
         _need(yn, torch.float32, "yn", 1)
     out = torch.empty((n1, n2), dtype=torch.float32, device=X.device)
-    call("snag_sim_write", ptr(X), ptr(Y), ptr(xn), ptr(yn), n1, n2, X.shape[1], mode, ptr(out), out.stride(0),
-         current_stream())
+    with _SweepTimer("sim_kernel<EpiWrite>", n1, n2, X.shape[1]):
+        call("snag_sim_write", ptr(X), ptr(Y), ptr(xn), ptr(yn), n1, n2, X.shape[1], mode, ptr(out), out.stride(0),
+             current_stream())
     return out
 
 
@@ -90,13 +91,14 @@ def sim_mainloop_only(X: torch.Tensor, Y: torch.Tensor, n1: int, n2: int) -> Non
 
 
 # Measurement hook: when bench.py sets this to a list, every fused-sweep launch is bracketed by CUDA events on the
-# launching stream and (name, start, end, rows, cols) is appended. None (the default) adds no events.
+# launching stream and (name, start, end, rows, cols, depth) is appended (depth = contraction width, None = the
+# caller knows it). None (the default) adds no events.
 SWEEP_EVENT_SINK = None
 
 
 class _SweepTimer:
-    def __init__(self, name: str, rows: int, cols: int):
-        self.args = (name, rows, cols) if SWEEP_EVENT_SINK is not None else None
+    def __init__(self, name: str, rows: int, cols: int, depth: int | None = None):
+        self.args = (name, rows, cols, depth) if SWEEP_EVENT_SINK is not None else None
 
     def __enter__(self):
         if self.args is not None:
@@ -108,7 +110,7 @@ class _SweepTimer:
     def __exit__(self, *exc):
         if self.args is not None and exc[0] is None:
             self.e1.record()
-            SWEEP_EVENT_SINK.append((self.args[0], self.e0, self.e1, self.args[1], self.args[2]))
+            SWEEP_EVENT_SINK.append((self.args[0], self.e0, self.e1, self.args[1], self.args[2], self.args[3]))
 
 
 def eval_rowtopk(X, Y, xn, yn, n1: int, n2: int) -> torch.Tensor:
@@ -245,33 +247,43 @@ def csls_sim_matrix(sim: torch.Tensor, k: int, want_out: bool = True):
 
 
 # ------------------------------------------------------------------------------------------------ ICL
-def icl_side(X: torch.Tensor, Y: torch.Tensor, B: int, Bp: int, inv_tau: float):
-    """Row log-sum-exp and NLL of one side of the ICL loss. X [Bp, Dpad], Y [2*Bp, Dpad]."""
+def icl_side(X: torch.Tensor, Y: torch.Tensor, B: int, Bp: int, inv_tau: float, row0: int = 0, nx: int | None = None):
+    """Row log-sum-exp and NLL of one side of the ICL loss for the anchors [row0, row0 + nx) of the batch (default: all).
+    X [>= nx, Dpad] holds those anchors from its first row on, Y [2*Bp, Dpad] = [other side ; this side].
+    Returns (lse, nll, pos) for the min(nx, B - row0) valid anchors."""
     _check_operand(X, "X")
     _check_operand(Y, "Y")
-    _, nch = sim_plan(Bp, 2 * Bp, X.shape[1])
-    part = torch.empty((nch, Bp), dtype=torch.float32, device=X.device)
-    pos = torch.empty((Bp,), dtype=torch.float32, device=X.device)
-    lse = torch.empty((B,), dtype=torch.float32, device=X.device)
-    nll = torch.empty((B,), dtype=torch.float32, device=X.device)
+    nx = Bp if nx is None else int(nx)
+    valid = max(0, min(nx, B - row0))
+    if valid == 0:
+        raise ValueError("no valid anchors in this shard")
+    _, nch = sim_plan(nx, 2 * Bp, X.shape[1])
+    part = torch.empty((nch, nx), dtype=torch.float32, device=X.device)
+    pos = torch.empty((nx,), dtype=torch.float32, device=X.device)
+    lse = torch.empty((valid,), dtype=torch.float32, device=X.device)
+    nll = torch.empty((valid,), dtype=torch.float32, device=X.device)
     st = current_stream()
-    call("snag_icl_rowsum", ptr(X), ptr(Y), B, Bp, X.shape[1], inv_tau, ptr(part), ptr(pos), st)
-    call("snag_icl_finalize", ptr(part), nch, B, Bp, ptr(pos), inv_tau, ptr(lse), ptr(nll), st)
+    with _SweepTimer("sim_kernel<EpiIclFwd>", nx, 2 * Bp, X.shape[1]):
+        call("snag_icl_rowsum", ptr(X), ptr(Y), B, Bp, row0, nx, X.shape[1], inv_tau, ptr(part), ptr(pos), st)
+    call("snag_icl_finalize", ptr(part), nch, valid, nx, ptr(pos), inv_tau, ptr(lse), ptr(nll), st)
     return lse, nll, pos
 
 
 def icl_bwd_logits(X: torch.Tensor, Y: torch.Tensor, B: int, Bp: int, inv_tau: float, cr: torch.Tensor,
-                   cc: torch.Tensor, dg: torch.Tensor) -> torch.Tensor:
-    """dL/dlogits of one ICL side as bf16 [Bp, 2*Bp] (see snag_icl_bwd_logits)."""
+                   cc: torch.Tensor, dg: torch.Tensor, row0: int = 0, nx: int | None = None) -> torch.Tensor:
+    """dL/dlogits of one ICL side as bf16 [nx, 2*Bp] for the anchors [row0, row0 + nx) of the batch (default: all Bp
+    rows of the side); see snag_icl_bwd_logits."""
     _check_operand(X, "X")
     _check_operand(Y, "Y")
+    nx = Bp if nx is None else int(nx)
     for t, nm in ((cr, "cr"), (cc, "cc"), (dg, "dg")):
         _need(t, torch.float32, nm, 1)
         if t.numel() < B:
             raise ValueError(f"{nm} needs at least B entries")
-    G = torch.empty((Bp, 2 * Bp), dtype=torch.bfloat16, device=X.device)
-    call("snag_icl_bwd_logits", ptr(X), ptr(Y), B, Bp, X.shape[1], inv_tau, ptr(cr), ptr(cc), ptr(dg), ptr(G),
-         current_stream())
+    G = torch.empty((nx, 2 * Bp), dtype=torch.bfloat16, device=X.device)
+    with _SweepTimer("sim_kernel<EpiIclBwd>", nx, 2 * Bp, X.shape[1]):
+        call("snag_icl_bwd_logits", ptr(X), ptr(Y), B, Bp, row0, nx, X.shape[1], inv_tau, ptr(cr), ptr(cc), ptr(dg), ptr(G),
+             current_stream())
     return G
 
 

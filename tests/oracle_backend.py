@@ -98,3 +98,63 @@ def top3_merge(val, idx):
     ov[:, :3] = np.take_along_axis(v, order, 1)
     oi[:, :3] = np.take_along_axis(i, order, 1)
     return torch.from_numpy(ov), torch.from_numpy(oi)
+
+
+# ------------------------------------------------------------------------------------------------ ICL loss
+# CPU stand-ins for the four kernel entry points the (anchor-sharded) ICL loss uses, following the formulas in
+# include/snag_b200.h; fp32 torch on the bf16-rounded operands.
+def round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+def prep_bf16(emb, idx=None, normalize=True, rows_pad_to=1, out=None):
+    x = emb if idx is None else emb.index_select(0, idx)
+    if normalize:
+        x = torch.nn.functional.normalize(x, dim=1)
+    n, d = x.shape
+    if out is None:
+        out = torch.zeros((round_up(n, rows_pad_to), round_up(d, 64)), dtype=torch.bfloat16)
+    out[:n, :d] = x.to(torch.bfloat16)
+    out[:n, d:] = 0
+    return out, (out[:n].float() ** 2).sum(1)
+
+
+def _icl_logits(X, Y, B, Bp, inv_tau, row0, nx):
+    s = X[:nx].float() @ Y.float().t()                                   # [nx, 2Bp]
+    col = torch.arange(2 * Bp)
+    part, idx = col // Bp, col % Bp
+    gr = row0 + torch.arange(nx)
+    dead = (idx >= B)[None, :] | ((part == 1)[None, :] & (idx[None, :] == gr[:, None]))
+    return s, dead, gr
+
+
+def icl_side(X, Y, B, Bp, inv_tau, row0=0, nx=None):
+    nx = Bp if nx is None else nx
+    s, dead, gr = _icl_logits(X, Y, B, Bp, inv_tau, row0, nx)
+    valid = max(0, min(nx, B - row0))
+    logits = (s * inv_tau).masked_fill(dead, float("-inf"))[:valid]
+    lse = torch.logsumexp(logits, 1)
+    pos = s[torch.arange(valid), gr[:valid]]
+    return lse, lse - pos * inv_tau, pos
+
+
+def icl_bwd_logits(X, Y, B, Bp, inv_tau, cr, cc, dg, row0=0, nx=None):
+    nx = Bp if nx is None else nx
+    s, dead, gr = _icl_logits(X, Y, B, Bp, inv_tau, row0, nx)
+    E = torch.exp(s * inv_tau - inv_tau)
+    ok = gr < B
+    crp = torch.zeros(Bp); crp[:B] = cr[:B]
+    ccp = torch.zeros(Bp); ccp[:B] = cc[:B]
+    dgp = torch.zeros(Bp); dgp[:B] = dg[:B]
+    cr_i = torch.where(ok, crp[gr.clamp(max=Bp - 1)], torch.zeros(()))
+    colc = torch.cat([ccp, crp])                                         # part 0: cc_j, part 1: cr_j
+    G = (cr_i[:, None] + colc[None, :]) * E * inv_tau
+    i = torch.arange(nx)[ok]
+    G[i, gr[ok]] -= dgp[gr[ok]] * inv_tau                                # positive logit of part 0
+    G = G.masked_fill(dead, 0.0)
+    G[~ok] = 0.0
+    return G.to(torch.bfloat16)
+
+
+def contract(P, Q, n1, n2):
+    return P[:n1].float() @ Q[:n2].float().t()

@@ -63,7 +63,7 @@ def test_icl_same_operands(cuda_device, B, D, tau):
     a = a.to(torch.bfloat16).float().requires_grad_(True)
     b = b.to(torch.bfloat16).float().requires_grad_(True)
     w = torch.rand((B,), generator=g, device=cuda_device) + 0.5
-    nll_a, nll_b = sloss._IclPair.apply(a, b, 1.0 / tau)
+    nll_a, nll_b = sloss._IclPair.apply(a, b, 1.0 / tau, sloss._unsharded())
     ra, rb = _torch_icl_rows(a.detach().double(), b.detach().double(), tau)
     np.testing.assert_allclose(nll_a.detach().cpu().numpy(), ra.float().cpu().numpy(), rtol=0, atol=2e-4)
     np.testing.assert_allclose(nll_b.detach().cpu().numpy(), rb.float().cpu().numpy(), rtol=0, atol=2e-4)
@@ -76,6 +76,58 @@ def test_icl_same_operands(cuda_device, B, D, tau):
     ref.backward()
     np.testing.assert_allclose(loss.item(), ref.item(), rtol=2e-4, atol=1e-6)
     assert _relerr(a.grad, a2.grad) < 1e-2 and _relerr(b.grad, b2.grad) < 1e-2
+
+
+class _LockstepShard(sloss.AnchorShard):
+    """One GPU standing in for `world` ranks: the ranks run one after the other; all_gather returns what the
+    ranks before this one contributed plus this rank's block, the others are filled in afterwards by the test."""
+
+    def __init__(self, world, rank, store, grads):
+        super().__init__(None, grads, None, world, rank)
+        self.store = store
+
+    def all_gather(self, t):
+        key = (len(self.store.setdefault(("n", self.rank), [])), tuple(t.shape))
+        self.store[("n", self.rank)].append(key)
+        blocks = self.store.setdefault(key, {})
+        blocks[self.rank] = t.clone()
+        return torch.stack([blocks.get(r, torch.zeros_like(t)) for r in range(self.world)], 0)
+
+
+@pytest.mark.parametrize("B,D,world", [(1000, 300, 2), (700, 96, 3), (3500, 320, 8), (100, 64, 2)])
+def test_icl_anchor_shards_match_full(cuda_device, B, D, world):
+    """Anchor-sharded sweeps (row0 / nx views of the same kernels) reproduce the unsharded per-anchor lse / nll and
+    the owned rows of both gradients. Two passes over the ranks: the first fills the exchange store, the second sees
+    every rank's block, exactly what NCCL's all-gather hands each rank."""
+    g = torch.Generator(device="cuda").manual_seed(B * 3 + D)
+    a = F.normalize(torch.randn((B, D), generator=g, device=cuda_device)).to(torch.bfloat16).float()
+    b = F.normalize(a + 0.7 * F.normalize(torch.randn((B, D), generator=g, device=cuda_device))).to(torch.bfloat16).float()
+    w = torch.rand((B,), generator=g, device=cuda_device) + 0.5
+
+    def run(shard):
+        a1, b1 = a.clone().requires_grad_(True), b.clone().requires_grad_(True)
+        na, nb = sloss._IclPair.apply(a1, b1, 10.0, shard)
+        ((0.3 * (na * w).sum() + 0.7 * (nb * w).sum()) / B).backward()
+        return na.detach(), nb.detach(), a1.grad, b1.grad
+
+    full = run(sloss._unsharded())
+    store = {}
+    for _pass in range(2):
+        outs = []
+        for r in range(world):
+            store.pop(("n", r), None)
+            outs.append(run(_LockstepShard(world, r, store, "local")))
+    summed_a = sum(o[2] for o in outs)
+    summed_b = sum(o[3] for o in outs)
+    for o in outs:                                   # after the second pass every rank holds the full nll vectors
+        np.testing.assert_allclose(o[0].cpu().numpy(), full[0].cpu().numpy(), rtol=0, atol=2e-5)
+        np.testing.assert_allclose(o[1].cpu().numpy(), full[1].cpu().numpy(), rtol=0, atol=2e-5)
+    assert _relerr(summed_a, full[2]) < 2e-3 and _relerr(summed_b, full[3]) < 2e-3
+    for r, o in enumerate(outs):                     # "local": only the owned rows are non-zero
+        r0, r1, _ = sloss.AnchorShard(world=world, rank=r).bounds(B)
+        mask = torch.ones(B, dtype=torch.bool, device=cuda_device)
+        mask[r0:r1] = False
+        assert float(o[2][mask].abs().max() if mask.any() else 0.0) == 0.0
 
 
 def test_icl_oracle_numpy(cuda_device):
@@ -124,3 +176,35 @@ def test_ial_golden(cuda_device, name):
     assert _relerr(src.grad.cpu(), torch.from_numpy(fx["grad_src"])) < 5e-2
     same = crit(src.detach(), src.detach(), fx["links"])
     assert abs(same.item()) < 1e-7                                                     # KL(p || p) = 0
+
+
+def test_graphed_step_equals_eager(cuda_device):
+    """The whole loss-layer slice (10 icl_loss calls, forward + backward) captured in one CUDA graph replays to the
+    eager result, also after the batch is changed in place."""
+    from snag_b200.graphs import GraphedStep
+    g = torch.Generator(device="cuda").manual_seed(5)
+    N, B, dm, M = 900, 300, 64, 4
+    mk = lambda w: torch.randn((N, w), generator=g, device=cuda_device).requires_grad_(True)
+    streams = [mk(dm) for _ in range(M)] + [None, None]
+    hidden = [mk(dm) for _ in range(M)] + [None, None]
+    joint, joint_fz = mk(M * dm), mk(M * dm)
+    wn = torch.softmax(torch.randn((N, 6), generator=g, device=cuda_device), 1).requires_grad_(True)
+    leaves = [t for t in streams + hidden + [joint, joint_fz, wn] if t is not None]
+    layer = sloss.SnagLossLayer(tau=0.1, ab_weight=0.5, awloss=True).to(cuda_device)
+    links = torch.stack([torch.randperm(N // 2, generator=g, device=cuda_device)[:B],
+                         N // 2 + torch.randperm(N // 2, generator=g, device=cuda_device)[:B]], 1).to(torch.int32)
+    fn = lambda: layer(streams, hidden, joint, joint_fz, links, wn)
+    step = GraphedStep(fn, leaves + list(layer.parameters()))
+    for trial in range(2):
+        loss_g = step().clone()
+        grads_g = [t.grad.clone() for t in leaves]
+        for t in leaves:
+            t.grad = None
+        loss_e = fn()
+        loss_e.backward()
+        assert abs(loss_g.item() - loss_e.item()) <= 1e-6 * abs(loss_e.item())
+        for a, t in zip(grads_g, leaves):
+            assert _relerr(a, t.grad) < 1e-6
+        for t, a in zip(leaves, step.grads):        # hand the static gradient buffers back to the graph
+            t.grad = a
+        links.copy_(links.flip(0).roll(7, 0))       # next batch, in place

@@ -1,0 +1,106 @@
+"""CPU: host logic of the anchor-sharded ICL loss (snag_b200.loss.AnchorShard / _IclPair) — partition of the
+anchors, the forward all-gather of (lse, nll), the owned-rows-only backward and both gradient conventions — with a
+torch-CPU stand-in for the four kernels, under real torch.distributed (gloo), world sizes 2 and 3, and against the
+reference's own golden loss / gradients."""
+from __future__ import annotations
+
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from snag_b200 import loss as sloss
+from tests import oracle_backend
+from tests.conftest import load_golden
+
+
+def _problem(B, D, N, seed):
+    g = torch.Generator().manual_seed(seed)
+    emb = torch.randn((N, D), generator=g)
+    perm = torch.randperm(N, generator=g)
+    links = torch.stack([perm[:B], perm[B:2 * B]], 1).numpy().astype(np.int32)
+    wn = torch.softmax(torch.randn((N, 4), generator=g), 1)[:, 0] * 4
+    return emb, links, wn
+
+
+def _run(crit, emb, links, wn):
+    emb = emb.clone().requires_grad_(True)
+    wn = wn.clone().requires_grad_(True)
+    out = crit(emb, links, weight_norm=wn)
+    out.backward()
+    return out.detach(), emb.grad, wn.grad
+
+
+def _unsharded(emb, links, wn, tau=0.1):
+    crit = sloss.icl_loss(tau=tau, ab_weight=0.4, n_view=2)
+    crit.shard = sloss.AnchorShard(be=oracle_backend)
+    return _run(crit, emb, links, wn)
+
+
+def test_cpu_backend_matches_reference_golden():
+    """The stand-in itself is checked against the reference's outputs, so the sharding tests below compare like with like."""
+    fx = load_golden("icl_tau0.1_w")
+    crit = sloss.icl_loss(tau=float(fx["tau"]), ab_weight=float(fx["ab_weight"]), n_view=2)
+    crit.shard = sloss.AnchorShard(be=oracle_backend)
+    out, g, gw = _run(crit, torch.from_numpy(fx["emb"]), fx["links"], torch.from_numpy(fx["weight_norm"]))
+    np.testing.assert_allclose(out.item(), float(fx["loss"]), rtol=5e-3, atol=5e-3)
+    gref = torch.from_numpy(fx["grad_emb"])
+    assert float((g - gref).norm() / gref.norm()) < 2e-2
+
+
+def test_bounds_cover_every_anchor_once():
+    for B in (1, 127, 128, 129, 1000, 3500, 16384):
+        for world in (1, 2, 3, 8):
+            seen = []
+            for r in range(world):
+                r0, r1, per = sloss.AnchorShard(world=world, rank=r).bounds(B)
+                assert per % 128 == 0 and 0 <= r1 - r0 <= per
+                seen += list(range(r0, r1))
+            assert seen == list(range(B))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, B, D, grads, out):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    emb, links, wn = _problem(B, D, 2 * B + 50, 7)
+    ref = _unsharded(emb, links, wn)
+    crit = sloss.icl_loss(tau=0.1, ab_weight=0.4, n_view=2).distribute(dist.group.WORLD, grads=grads, be=oracle_backend)
+    loss, g, gw = _run(crit, emb, links, wn)
+    if grads == "local":          # every rank holds only its anchors' rows: the sum over ranks is the gradient
+        dist.all_reduce(g)
+    ok = (abs(loss.item() - ref[0].item()) < 1e-5 and float((g - ref[1]).abs().max()) < 1e-5 * float(ref[1].abs().max() + 1)
+          and float((gw - ref[2]).abs().max()) < 1e-5)
+    out[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("world,B,D,grads", [(2, 300, 48, "gather"), (2, 130, 32, "local"), (3, 200, 40, "gather")])
+def test_gloo_sharded_icl_equals_unsharded(world, B, D, grads):
+    last = None
+    for _attempt in range(2):
+        try:
+            with mp.Manager() as mgr:
+                out = mgr.dict()
+                mp.spawn(_worker, args=(world, _free_port(), B, D, grads, out), nprocs=world, join=True)
+                assert dict(out) == {r: True for r in range(world)}
+                return
+        except AssertionError:
+            raise
+        except Exception as e:
+            last = e
+    raise last
