@@ -152,6 +152,19 @@ int64_t snag_csls_workspace_bytes(int64_t n1, int64_t n2);
 int snag_csls_sim(const float* sim, int64_t n1, int64_t n2, int64_t ld, int32_t k, float* out, int64_t ld_out, float* nv1,
                   float* nv2, void* workspace, void* stream);
 
+/* ---- mutual nearest neighbours (iterative-learning link mining) ------------------------------- */
+/* The argmin pair of model/SNAG.py:192-208 (Iter_new_links: torch.argmin over the rows and over the columns of
+ * pairwise_distances(final_emb[left], final_emb[right])) without forming the distance matrix.
+ *   row_val / row_idx [n_lists][n1] (n_lists = snag_sim_plan(n1, n2)): per list, the smallest
+ *       d_ij = clamp(xn_i + yn_j - 2 x_i.y_j, 0) of row i and its column (lowest column among equals); the caller
+ *       reduces over lists lexicographically on (d, column).
+ *   colkey [n2], initialised by the caller to all ones: receives min over rows of (d bits << 32 | row), i.e. the
+ *       smallest d of column j and the lowest row attaining it — for every column whose minimum satisfies
+ *       x_i.y_j > xn_i/2 + colb[j]. colb comes from an upper bound ub_j of the column minimum (the minimum over any
+ *       subset of the rows): colb[j] = (yn_j - ub_j)/2 - 4e-6 admits every element with d_ij <= ub_j. */
+int snag_mutual_nn(const uint16_t* X, const uint16_t* Y, const float* xn, const float* yn, int32_t n1, int32_t n2,
+                   int32_t Dpad, const float* colb, uint64_t* colkey, float* row_val, int32_t* row_idx, void* stream);
+
 /* ---- ICL loss --------------------------------------------------------------------------------- */
 /* One side of icl_loss.forward (model/SNAG_loss.py:98-126). Y = [other side ; this side] [2*Bp, Dpad], each part zero
  * padded from B to Bp rows (Bp multiple of 256). X = nx anchors of this side starting at batch index row0 (the whole

@@ -1,0 +1,170 @@
+"""Per-row measurements of SURVEY 8(a) outside the two tensor-core sweeps bench.py reports: the bandwidth kernels
+(noise mask, column statistics, entity blend, bf16 prologue), the materialising drop-ins (pairwise_distances,
+csls_sim) and the small evaluation glue — each against the HBM roofline (MEASURED_PEAKS.json hbm_gbs, measured copy
+bandwidth) with the reference's own torch op sequence timed on the host cores beside it.
+
+    python scripts/bench_rows.py [--shape c1|c3] > gpurun_out/rows.jsonl
+
+One JSON line per row: algorithmic bytes per launch (SURVEY 8(d) figure), CUDA-event time per launch on the launching
+stream (median of `reps`, L2 flushed between launches by writing a 512 MB buffer), achieved GB/s, fraction of peak,
+CPU seconds of the reference op sequence (torch CPU, all host threads) on the same shape.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import torch
+
+from snag_b200 import evaluate, noise, ops
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    return 6650.0, "B200_PROFILING.md fallback"
+
+
+def gpu_time(fn, reps=9):
+    flush = torch.empty((512 << 20,), dtype=torch.uint8, device="cuda")
+    fn(); fn()
+    ts = []
+    for _ in range(reps):
+        flush.fill_(1)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    return float(np.median(ts))
+
+
+def cpu_time(fn, reps=3):
+    fn()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        fn()
+    return (time.perf_counter() - t0) / reps
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--shape", default="c1", choices=["c1", "c3"])
+    args = ap.parse_args()
+    N, F_img, n_test = (39594, 2048, 10500) if args.shape == "c1" else (27793, 4096, 10277)
+    D = 1200
+    hbm, src = peaks()
+    torch.set_num_threads(os.cpu_count() or 1)
+    g = torch.Generator(device="cuda").manual_seed(3408)
+    rows = []
+
+    def emit(row, kernel, nbytes, ms, cpu_s, note=""):
+        rec = {"row": row, "kernel": kernel, "shape": args.shape, "algorithmic_bytes": int(nbytes), "ms": round(ms, 4),
+               "achieved_gbs": round(nbytes / ms / 1e6, 1), "peak_gbs": hbm, "frac": round(nbytes / ms / 1e6 / hbm, 3),
+               "peak_source": src, "cpu_s": None if cpu_s is None else round(cpu_s, 4),
+               "cpu_threads": torch.get_num_threads(), "speedup_vs_cpu": None if cpu_s is None else round(cpu_s * 1e3 / ms, 1),
+               "note": note}
+        rows.append(rec)
+        print(json.dumps(rec), flush=True)
+
+    # ------------------------------------------------------------------ a1 noise mask (model/SNAG.py:66-75)
+    feats = {"rel": torch.poisson(torch.full((N, 1000), 0.05, device="cuda"), generator=g),
+             "att": torch.bernoulli(torch.full((N, 1000), 0.01, device="cuda"), generator=g),
+             "img": torch.nn.functional.normalize(torch.randn((N, F_img), generator=g, device="cuda"))}
+    r, rho = 0.2, 0.7
+
+    def ref_add_noise(x, mean, std):
+        x = x.clone()
+        m = torch.rand(x.shape[0]) < r
+        sel = x[m]
+        x[m] = (1 - rho) * sel + rho * (mean + std * torch.randn_like(sel))
+        return x
+
+    for name, x in feats.items():
+        mean, std = ops.col_mean_std(x)
+        out = torch.empty_like(x)
+        ms = gpu_time(lambda: ops.noise_mask(x, mean, std, r, rho, out=out, seed=7))
+        xc, mc, sc = x.cpu(), mean.cpu(), std.cpu()
+        emit("a1", f"noise_mask_kernel[{name} {tuple(x.shape)}]", 8 * x.numel(), ms, cpu_time(lambda: ref_add_noise(xc, mc, sc)),
+             "read x + write noisy copy, Philox drawn in-kernel")
+        ms = gpu_time(lambda: ops.col_mean_std(x))
+        emit("a3", f"col_stats[{name} {tuple(x.shape)}]", 4 * x.numel(), ms,
+             cpu_time(lambda: (torch.mean(xc, dim=0), torch.std(xc, dim=0))), "one read, fp64 partial sums")
+
+    # the same two kernels on a 10x taller matrix: launch latency amortised, the kernel's own bandwidth shows
+    xb = torch.randn((400_000, 1000), generator=g, device="cuda")
+    mb, sb = ops.col_mean_std(xb)
+    ob = torch.empty_like(xb)
+    ms = gpu_time(lambda: ops.noise_mask(xb, mb, sb, r, rho, out=ob, seed=7), reps=5)
+    emit("a1", "noise_mask_kernel[400000 x 1000] (size sweep)", 8 * xb.numel(), ms, None, "3.2 GB of traffic per launch")
+    ms = gpu_time(lambda: ops.col_mean_std(xb), reps=5)
+    emit("a3", "col_stats[400000 x 1000] (size sweep)", 4 * xb.numel(), ms, None)
+    del xb, ob
+
+    # ------------------------------------------------------------------ a2 entity noise + a4 blend (SNAG.py:94-98, SNAG_tools.py:122-129)
+    ent = torch.randn((N, 300), generator=g, device="cuda") / N ** 0.5
+    em, es = ops.col_mean_std(ent)
+    ms = gpu_time(lambda: ops.gauss_fill(em, es, N, 11))
+    emc, esc, entc = em.cpu(), es.cpu(), ent.cpu()
+    emit("a2", f"gauss_fill[{N}x300]", 4 * N * 300, ms, cpu_time(lambda: emc + esc * torch.randn_like(entc)), "write only")
+    noise_t = ops.gauss_fill(em, es, N, 11)
+    mask = ops.philox_rowmask(N, r * 0.5, 13, ent.device)
+    a, c = float(np.float32(1 - rho * 0.5)), float(np.float32(rho * 0.5))
+    ms = gpu_time(lambda: ops.rowblend_fwd(ent, noise_t, mask, a, c))
+    nc, mcpu = noise_t.cpu(), mask.cpu().bool()
+
+    def ref_blend():
+        e = entc.clone()
+        e[mcpu] = a * e[mcpu] + c * nc[mcpu]
+        return e
+    emit("a4", f"rowblend_fwd[{N}x300]", 8 * N * 300 + 4 * N * 300 * (r * 0.5), ms, cpu_time(ref_blend),
+         "read e + write e'; noise rows read only where masked")
+    gr = torch.randn_like(ent)
+    ms = gpu_time(lambda: ops.rowblend_bwd(gr, mask, a))
+    emit("a4", f"rowblend_bwd[{N}x300]", 8 * N * 300, ms, None)
+
+    # ------------------------------------------------------------------ prologue: gather + normalise + bf16 + norm
+    emb = torch.randn((N, D), generator=g, device="cuda")
+    idx = torch.randperm(N, generator=g, device="cuda")[:n_test].contiguous()
+    ms = gpu_time(lambda: ops.prep_bf16(emb, idx, True))
+    ec, ic = emb.cpu(), idx.cpu()
+    emit("prologue", f"prep_bf16[{n_test}x{D}]", n_test * (4 * D + 2 * ops.round_up(D, 64)), ms,
+         cpu_time(lambda: torch.nn.functional.normalize(ec)[ic]), "main.py:379 normalises all N rows; only the gathered rows here")
+
+    # ------------------------------------------------------------------ a8 / a9 materialising drop-ins
+    x, y = emb[idx], emb[torch.randperm(N, generator=g, device="cuda")[:n_test]]
+    x, y = torch.nn.functional.normalize(x), torch.nn.functional.normalize(y)
+    ms = gpu_time(lambda: evaluate.pairwise_distances(x, y), reps=5)
+    xc, yc = x.cpu(), y.cpu()
+
+    def ref_pd():
+        xn = (xc ** 2).sum(1).view(-1, 1)
+        yn = (yc ** 2).sum(1).view(1, -1)
+        return torch.clamp(xn + yn - 2.0 * torch.mm(xc, yc.t()), 0.0, np.inf)
+    emit("a8", f"pairwise_distances[{n_test}^2, D={D}]", 4 * n_test * n_test, ms, cpu_time(ref_pd, 2),
+         "HBM-write bound: the fp32 [n,n] output; includes both bf16 prologues")
+    sim = 1 - evaluate.pairwise_distances(x, y)
+    ms = gpu_time(lambda: evaluate.csls_sim(sim, 10), reps=5)
+    sc = sim.cpu()
+
+    def ref_csls():
+        nv1 = torch.mean(torch.topk(sc, 10)[0], 1)
+        nv2 = torch.mean(torch.topk(sc.t(), 10)[0], 1)
+        return (2 * sc.t() - nv1).t() - nv2
+    emit("a9", f"csls_sim[{n_test}^2, k=10] (materialised drop-in)", 12 * n_test * n_test, ms, cpu_time(ref_csls, 2),
+         "2 reads + 1 write of the matrix is the algorithmic minimum; executed: 3 reads + 1 write")
+    out = os.path.join(ROOT, "gpurun_out", f"rows_{args.shape}.jsonl")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    with open(out, "w") as f:
+        for rec in rows:
+            f.write(json.dumps(rec) + "\n")
+
+
+if __name__ == "__main__":
+    main()

@@ -45,6 +45,7 @@ _SIGNATURES = {
     "snag_eval_rank": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp],
     "snag_top3_merge": [_vp, _vp, _i32, _i64, _vp, _vp, _vp],
     "snag_csls_sim": [_vp, _i64, _i64, _i64, _i32, _vp, _i64, _vp, _vp, _vp, _vp],
+    "snag_mutual_nn": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp],
     "snag_icl_rowsum": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _vp, _vp, _vp],
     "snag_icl_finalize": [_vp, _i32, _i32, _i32, _vp, _f32, _vp, _vp, _vp],
     "snag_icl_bwd_logits": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _vp],

@@ -144,6 +144,12 @@ int snag_col_cand_finalize(const int64_t* offs, const int32_t* hist, const float
   return launch_col_cand_finalize(reinterpret_cast<const long long*>(offs), hist, vals, n, k, nv, overflow, S(stream));
 }
 
+int snag_mutual_nn(const uint16_t* X, const uint16_t* Y, const float* xn, const float* yn, int32_t n1, int32_t n2,
+                   int32_t Dpad, const float* colb, uint64_t* colkey, float* row_val, int32_t* row_idx, void* stream) {
+  return launch_mutual_nn(BF(X), BF(Y), xn, yn, n1, n2, Dpad, colb, reinterpret_cast<unsigned long long*>(colkey), row_val,
+                          row_idx, S(stream));
+}
+
 int snag_icl_bwd_logits(const uint16_t* X, const uint16_t* Y, int32_t B, int32_t Bp, int32_t row0, int32_t nx,
                         int32_t Dpad, float inv_tau, const float* cr, const float* cc, const float* dg, uint16_t* G,
                         void* stream) {

@@ -197,6 +197,15 @@ int launch_eval_rowcoltopk(const __nv_bfloat16* X, const __nv_bfloat16* Y, const
   return launch_sim<EpiRowColTopK>(X, Y, n1, n2, Dpad, p, st);
 }
 
+int launch_mutual_nn(const __nv_bfloat16* X, const __nv_bfloat16* Y, const float* xn, const float* yn, int n1, int n2,
+                     int Dpad, const float* colb, unsigned long long* colkey, float* row_val, int* row_idx,
+                     cudaStream_t st) {
+  if (!xn || !yn || !colb || !colkey || !row_val || !row_idx) return SNAG_ERR_ARG;
+  if (reinterpret_cast<uintptr_t>(colkey) & 7) return SNAG_ERR_ALIGN;
+  EpiMutualNN::Params p{xn, yn, colb, colkey, row_val, row_idx};
+  return launch_sim<EpiMutualNN>(X, Y, n1, n2, Dpad, p, st);
+}
+
 int launch_icl_bwd_logits(const __nv_bfloat16* X, const __nv_bfloat16* Y, int B, int Bp, int row0, int nx, int Dpad,
                           float inv_tau, const float* cr, const float* cc, const float* dg, __nv_bfloat16* G,
                           cudaStream_t st) {

@@ -672,6 +672,101 @@ struct EpiRowColTopK {
 };
 
 // ------------------------------------------------------------------------------------------------
+// Epilogue: mutual nearest neighbours (model/SNAG.py:192-208, Iter_new_links): for every row the column with the
+// smallest squared distance d_ij = clamp(xn_i + yn_j - 2 s_ij, 0) and for every column the row with the smallest
+// d_ij, first index on ties (torch.argmin). The distance matrix the reference concatenates is never formed.
+//   rows   : running (best d, its column) in registers, one partial result per list, merged afterwards;
+//   columns: a pre-pass over a sample of the rows bounds every column's minimum from above; only elements at or
+//            below that bound (a handful per column) reach a 64-bit atomicMin on  (d bits << 32 | row)  — d >= 0,
+//            so unsigned order of the packed key is the lexicographic order (d, row).
+// Both directions use the conservative s-space pre-filter of EpiRowTopK; survivors are re-checked exactly.
+// ------------------------------------------------------------------------------------------------
+struct EpiMutualNN {
+  static constexpr bool kNoLoad = false;
+  struct Params {
+    const float* xn;              // [n_rows]
+    const float* yn;              // [n_cols]
+    const float* colb;            // [n_cols] b_j of the column pre-filter: flag when s_ij > xn_i/2 + b_j
+    unsigned long long* colkey;   // [n_cols] packed (d bits << 32 | row), caller initialises to ~0
+    float* row_val;               // [n_lists][n_rows] smallest d of the list's columns
+    int* row_idx;                 // [n_lists][n_rows] its column (lowest index among equals)
+  };
+  struct State {
+    float xn, a, best;
+    int best_j;
+  };
+  static constexpr int kVecStride = 2 * BN + BN / 32;       // yn[BN], strip minima of yn, colb[BN]
+  static __device__ __forceinline__ void unit_begin(const Params& p, const SimShape&, const EpiCtx& cx, State& st) {
+    static_assert(2 * kVecStride <= EPI_VEC_FLOATS, "scratch too small");
+    st.xn = cx.row_ok ? p.xn[cx.row] : 0.f;
+    st.a = cx.row_ok ? 0.5f * st.xn : INFINITY;            // padding rows never reach a column
+    st.best = INFINITY;
+    st.best_j = 0x7fffffff;
+  }
+  static __device__ __forceinline__ EpiPre tile_prefetch(const Params& p, const SimShape& shp, const EpiCtx& cx, int ct) {
+    EpiPre pre{};
+    const int col = ct * BN + cx.tid;
+    if (cx.tid < BN) {
+      const bool ok = col < shp.n_cols;
+      pre.a = ok ? p.yn[col] : INFINITY;                   // d = +inf: never the minimum of a row
+      pre.b = ok ? p.colb[col] : INFINITY;                 // never flagged for the column side
+    }
+    return pre;
+  }
+  static __device__ __forceinline__ void tile_commit(const Params&, const SimShape&, const EpiCtx& cx, State&,
+                                                     const EpiPre& pre, int, int buf) {
+    static_assert(NUM_EPI_THREADS >= BN, "one epilogue thread stages one column");
+    if (cx.tid >= BN) return;
+    float* v_s = cx.scratch + buf * kVecStride;
+    v_s[cx.tid] = pre.a;
+    v_s[BN + BN / 32 + cx.tid] = pre.b;
+    float m = pre.a;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (cx.lane == 0) v_s[BN + (cx.tid >> 5)] = m;
+  }
+  static __device__ __forceinline__ void chunk(const Params& p, const SimShape&, const EpiCtx& cx, State& st, int ct,
+                                               int c, const uint32_t (&r)[32], int buf) {
+    const float* v_s = cx.scratch + buf * kVecStride;
+    const float* yn_s = v_s + c * 32;
+    const float* cb_s = v_s + BN + BN / 32 + c * 32;
+    // d_ij < best  =>  s_ij > (xn_i + yn_j - best)/2 >= (xn_i + min_strip yn - best)/2 ; 4e-6 covers the roundings
+    const float thr = __fmaf_rn(0.5f, __fsub_rn(__fadd_rn(st.xn, v_s[BN + c]), st.best), -4e-6f);
+    uint32_t pm = 0, cm = 0;
+#pragma unroll
+    for (int q = 0; q < 32; ++q) {
+      const float s = __uint_as_float(r[q]);
+      if (s > thr) pm |= (1u << q);
+      if (s > __fadd_rn(st.a, cb_s[q])) cm |= (1u << q);
+    }
+    if ((pm | cm) != 0) {
+      // rare after the first tiles of a unit / for a handful of elements per column: exact re-check by the row owner
+      const int col0 = ct * BN + c * 32;
+#pragma unroll
+      for (int q = 0; q < 32; ++q) {
+        if ((pm | cm) & (1u << q)) {
+          const float d = sqdist_from_dot(__uint_as_float(r[q]), st.xn, yn_s[q]);
+          if (d < st.best) {                               // columns arrive in increasing order: strict keeps the first
+            st.best = d;
+            st.best_j = col0 + q;
+          }
+          if (cm & (1u << q))
+            atomicMin(p.colkey + col0 + q, (static_cast<unsigned long long>(__float_as_uint(d)) << 32) |
+                                               static_cast<unsigned int>(cx.row));
+        }
+      }
+    }
+  }
+  static __device__ __forceinline__ void tile_end(const Params&, const SimShape&, const EpiCtx&, State&, int, int) {}
+  static __device__ __forceinline__ void unit_end(const Params& p, const SimShape& shp, const EpiCtx& cx, State& st) {
+    if (!cx.row_ok) return;
+    const long long o = static_cast<long long>(cx.list) * shp.n_rows + cx.row;
+    p.row_val[o] = st.best;
+    p.row_idx[o] = st.best_j;
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
 // Epilogue: rank counting (sweep 2). For every pair (i, j) of the unit, with dist = CSLS distance:
 //   cnt_row[i] += [dist < g_i] + [dist == g_i and gid(j) < gid(i)]      (j != i)     -> l2r rank of pair i
 //   cnt_col[j] += [dist < g_j] + [dist == g_j and gid(i) < gid(j)]      (i != j)     -> r2l rank of pair j

@@ -63,6 +63,9 @@ int launch_eval_rank(const __nv_bfloat16* X, const __nv_bfloat16* Y, const float
 int launch_icl_rowsum(const __nv_bfloat16* X, const __nv_bfloat16* Y, int B, int Bp, int row0, int nx, int Dpad, float inv_tau,
                       float* rowsum_part, float* pos, cudaStream_t st);
 
+int launch_mutual_nn(const __nv_bfloat16* X, const __nv_bfloat16* Y, const float* xn, const float* yn, int n1, int n2,
+                     int Dpad, const float* colb, unsigned long long* colkey, float* row_val, int* row_idx,
+                     cudaStream_t st);
 int launch_eval_rowcoltopk(const __nv_bfloat16* X, const __nv_bfloat16* Y, const float* xn, const float* yn, int n1, int n2,
                            int Dpad, float* part, const float* colthr, const float* colb, uint2* stream, int* stream_cnt,
                            int cta_cap, cudaStream_t st);

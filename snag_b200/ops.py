@@ -179,6 +179,23 @@ def col_cand_reduce(stream: torch.Tensor, stream_cnt: torch.Tensor, n_cols: int,
     return nv, overflow, hist
 
 
+def mutual_nn(X, Y, xn, yn, n1: int, n2: int, colb: torch.Tensor):
+    """Fused argmin sweep (snag_mutual_nn): returns (row_val [L, n1], row_idx [L, n1], colkey int64 [n2])."""
+    _check_operand(X, "X")
+    _check_operand(Y, "Y")
+    _need(xn, torch.float32, "xn", 1)
+    _need(yn, torch.float32, "yn", 1)
+    _need(colb, torch.float32, "colb", 1)
+    _, nl = sim_plan(n1, n2, X.shape[1])
+    row_val = torch.empty((nl, n1), dtype=torch.float32, device=X.device)
+    row_idx = torch.empty((nl, n1), dtype=torch.int32, device=X.device)
+    colkey = torch.full((n2,), -1, dtype=torch.int64, device=X.device)          # all ones
+    with _SweepTimer("sim_kernel<EpiMutualNN>", n1, n2, X.shape[1]):
+        call("snag_mutual_nn", ptr(X), ptr(Y), ptr(xn), ptr(yn), n1, n2, X.shape[1], ptr(colb), ptr(colkey), ptr(row_val),
+             ptr(row_idx), current_stream())
+    return row_val, row_idx, colkey
+
+
 def topk_merge_mean(part: torch.Tensor, k: int, want_nv: bool = True, want_cand: bool = False):
     _need(part, torch.float32, "part", 3)
     if part.shape[2] != KT:
@@ -311,6 +328,10 @@ def noise_mask(x: torch.Tensor, mean: torch.Tensor, std: torch.Tensor, noise_rat
             raise ValueError("zsel needs the row mask it was drawn for")
         _need(zsel, torch.float32, "zsel", 2)
         selpos = (torch.cumsum(mask.to(torch.int32), 0, dtype=torch.int32) - 1).contiguous()
+    if mask is None:
+        # the Bernoulli row selection once per row (N Philox draws) rather than once per float4 inside the mask kernel:
+        # same counter, same stream, so the output is the same function of (seed, row, column)
+        mask = philox_rowmask(x.shape[0], noise_ratio, seed, x.device, row0)
     keep = float(1.0 - mask_ratio)
     call("snag_noise_mask", ptr(x), ptr(out), ptr(mean), ptr(std), ptr(mask), ptr(zsel), ptr(selpos), x.shape[0],
          x.shape[1], x.stride(0), out.stride(0), float(noise_ratio), keep, float(mask_ratio), int(seed), int(row0),

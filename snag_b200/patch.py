@@ -9,6 +9,7 @@ patch() assigns attributes — main.py, model/*.py and src/*.py stay byte-identi
     model.SNAG.icl_loss / ial_loss / CustomMultiLossLayer                 (names already bound by `from .SNAG_loss import`)
     src.utils.pairwise_distances / csls_sim, model.SNAG.pairwise_distances -> snag_b200.evaluate
     model.SNAG.SNAG.add_noise_to_embeddings / get_mean_std / update_noise  -> snag_b200.noise
+    model.SNAG.SNAG.Iter_new_links                                         -> snag_b200.mining
     model.SNAG_tools.MultiModalEncoder.forward                             -> snag_b200.noise.encoder_forward
     main.pairwise_distances / csls_sim, main.Runner._test                  -> snag_b200.evaluate / snag_b200.runner
 There is no fallback: on a machine without a B200 the patched functions raise.
@@ -21,7 +22,7 @@ import os
 import sys
 import types
 
-from . import evaluate, loss, noise, runner
+from . import evaluate, loss, mining, noise, runner
 
 
 def patch(main_module: types.ModuleType | None = None) -> list[str]:
@@ -53,7 +54,8 @@ def patch(main_module: types.ModuleType | None = None) -> list[str]:
         cls.add_noise_to_embeddings = noise.add_noise_to_embeddings
         cls.get_mean_std = noise.get_mean_std
         cls.update_noise = noise.update_noise
-        done.append("model.SNAG.SNAG.{add_noise_to_embeddings,get_mean_std,update_noise}")
+        cls.Iter_new_links = mining.Iter_new_links
+        done.append("model.SNAG.SNAG.{add_noise_to_embeddings,get_mean_std,update_noise,Iter_new_links}")
     except ImportError:
         pass
     try:

@@ -10,6 +10,8 @@ Every .npz holds seeded inputs plus what the unmodified reference code returned 
   ial_*.npz    ial_loss.forward (model/SNAG_loss.py:148-202) loss + gradient
   noise_*.npz  SNAG.add_noise_to_embeddings (model/SNAG.py:66-75) with its RNG draws replayed
   mll_*.npz    CustomMultiLossLayer.forward (model/SNAG_loss.py:22-29)
+  mining_*.npz SNAG.Iter_new_links (model/SNAG.py:192-208): argmin vectors of the distance matrix and the returned links
+               for a refresh epoch and a filter epoch
 Inputs of the evaluation fixtures are pre-rounded to bf16 so that the reference (fp32) and the tensor-core
 path see identical values; fixtures whose ground-truth margins are within 2e-5 of a competitor are
 rejected and re-seeded, so that ranks do not depend on the accumulation order of the dot products.
@@ -213,12 +215,65 @@ def gen_noise(ref, outdir):
     print("rowblend selected", int(mask.sum()))
 
 
+def gen_mining(ref, outdir):
+    """SNAG.Iter_new_links called unbound on a stand-in `self` (it only reads self.args.semi_learn_step)."""
+    import importlib
+    ref_snag = importlib.import_module("model.SNAG")
+    fake_self = types.SimpleNamespace(args=types.SimpleNamespace(semi_learn_step=5))
+
+    def one(name, emb, left, right, require_margin=True):
+        d = ref.utils.pairwise_distances(emb[left], emb[right])
+        if require_margin:          # nearest and second nearest further apart than the accumulation-order noise
+            s1 = torch.sort(d, 1)[0]
+            s0 = torch.sort(d, 0)[0]
+            if min((s1[:, 1] - s1[:, 0]).min().item(), (s0[1] - s0[0]).min().item()) < 2e-5:
+                return False
+        preds_l = torch.argmin(d, dim=1).numpy()
+        preds_r = torch.argmin(d.t(), dim=1).numpy()
+        links_a = ref_snag.SNAG.Iter_new_links(fake_self, 4, left, emb, right, new_links=[])        # (4+1) % 25 == 5: refresh
+        prev = links_a[::2] + [(left[0], right[-1])]
+        links_b = ref_snag.SNAG.Iter_new_links(fake_self, 9, left, emb, right, new_links=prev)      # filter epoch
+        np.savez_compressed(os.path.join(outdir, name + ".npz"), emb=emb.numpy(), left=np.asarray(left, np.int64),
+                            right=np.asarray(right, np.int64), preds_l=preds_l.astype(np.int64), preds_r=preds_r.astype(np.int64),
+                            dmin_l=d.min(1)[0].numpy(), dmin_r=d.min(0)[0].numpy(),
+                            links_refresh=np.asarray(links_a, np.int64).reshape(-1, 2), prev=np.asarray(prev, np.int64).reshape(-1, 2),
+                            links_filter=np.asarray(links_b, np.int64).reshape(-1, 2))
+        print(name, "mutual pairs", len(links_a), "after filter", len(links_b))
+        return True
+
+    for name, n_l, n_r, dim, sigma in (("mining_n300x280_d96", 300, 280, 96, 1.5), ("mining_n1100x900_d320", 1100, 900, 320, 2.5)):
+        seed = 3408
+        while True:
+            g = torch.Generator().manual_seed(seed)
+            n_ent = n_l + n_r + 57
+            x, y = clustered(max(n_l, n_r), dim, sigma, seed)
+            emb = bf16_round_t(torch.nn.functional.normalize(torch.randn((n_ent, dim), generator=g)))
+            perm = torch.randperm(n_ent, generator=g)
+            left, right = perm[:n_l].tolist(), perm[n_l:n_l + n_r].tolist()
+            emb[left] = x[:n_l]
+            emb[right] = y[:n_r]
+            if one(name, emb, left, right):
+                break
+            seed += 1
+    # exact ties: dyadic rows with duplicates on both sides -> argmin must return the first index
+    g = torch.Generator().manual_seed(9)
+    emb = torch.randint(-4, 5, (120, 32), generator=g).float() / 8.0
+    left, right = list(range(0, 50)), list(range(60, 120))
+    emb[61] = emb[60]
+    emb[70] = emb[3]
+    emb[71] = emb[3]
+    emb[4] = emb[3]
+    one("mining_ties_dyadic", emb, left, right, require_margin=False)
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=HERE)
+    ap.add_argument("--only", default="", help="comma separated subset of: eval,losses,noise,mining")
     args = ap.parse_args()
     torch.set_num_threads(8)
     ref = load_reference()
-    gen_eval(ref, args.out)
-    gen_losses(ref, args.out)
-    gen_noise(ref, args.out)
+    only = [s for s in args.only.split(",") if s]
+    for nm, fn in (("eval", gen_eval), ("losses", gen_losses), ("noise", gen_noise), ("mining", gen_mining)):
+        if not only or nm in only:
+            fn(ref, args.out)

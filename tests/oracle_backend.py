@@ -158,3 +158,16 @@ def icl_bwd_logits(X, Y, B, Bp, inv_tau, cr, cc, dg, row0=0, nx=None):
 
 def contract(P, Q, n1, n2):
     return P[:n1].float() @ Q[:n2].float().t()
+
+
+# ------------------------------------------------------------------------------------------------ link mining
+def mutual_nn(X, Y, xn, yn, n1, n2, colb):
+    """CPU stand-in for ops.mutual_nn: one list; columns only where the pre-filter admits their minimum (as the kernel)."""
+    d = _c_matrix(X, Y, xn, yn, n1, n2)
+    s = oracle.dot_matrix(_np(X[:n1]), _np(Y[:n2]))
+    row_val = torch.from_numpy(d.min(1)[None, :].copy())
+    row_idx = torch.from_numpy(d.argmin(1).astype(np.int32)[None, :].copy())
+    flagged = s > (np.float32(0.5) * _np(xn)[:n1, None] + _np(colb)[None, :n2])
+    key = (d.view(np.uint32).astype(np.uint64) << np.uint64(32)) | np.arange(n1, dtype=np.uint64)[:, None]
+    key = np.where(flagged, key, np.uint64(0xFFFFFFFFFFFFFFFF)).min(0)
+    return row_val, row_idx, torch.from_numpy(key.view(np.int64).copy())

@@ -179,3 +179,38 @@ def test_philox_known_answer():
     r = oracle.philox4x32_10(np.uint32(0x243F6A88), np.uint32(0x85A308D3), np.uint32(0x13198A2E), np.uint32(0x03707344),
                              0xA4093822, 0x299F31D0)
     assert [int(v) for v in r] == [0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1]
+
+
+# ------------------------------------------------------------------------------------------------ link mining
+@pytest.mark.parametrize("name", golden_names("mining_"))
+def test_mutual_nn_matches_reference(name):
+    """oracle.mutual_nn / iter_new_links against what SNAG.Iter_new_links returned (model/SNAG.py:192-208)."""
+    fx = load_golden(name)
+    emb, left, right = fx["emb"], fx["left"].tolist(), fx["right"].tolist()
+    pl, pr, dl, dr = oracle.mutual_nn(emb[left], emb[right])
+    np.testing.assert_array_equal(pl, fx["preds_l"])
+    np.testing.assert_array_equal(pr, fx["preds_r"])
+    np.testing.assert_allclose(dl, fx["dmin_l"], atol=1e-6, rtol=0)
+    got = oracle.iter_new_links(left, right, emb, [], True)
+    assert got == [tuple(t) for t in fx["links_refresh"].tolist()]
+    got = oracle.iter_new_links(left, right, emb, [tuple(t) for t in fx["prev"].tolist()], False)
+    assert got == [tuple(t) for t in fx["links_filter"].tolist()]
+
+
+@pytest.mark.parametrize("name", golden_names("mining_"))
+def test_mining_host_logic_on_cpu_backend(name):
+    """snag_b200.mining (sample pre-pass bound, list merge, packed column keys, link filter) with the oracle standing in
+    for the kernels."""
+    import torch
+    from snag_b200 import mining
+    from tests import oracle_backend
+    fx = load_golden(name)
+    emb = torch.from_numpy(fx["emb"])
+    left, right = fx["left"].tolist(), fx["right"].tolist()
+    pl, pr, dl, dr = mining.mutual_nearest(emb[left], emb[right], backend=oracle_backend)
+    np.testing.assert_array_equal(pl.numpy(), fx["preds_l"])
+    np.testing.assert_array_equal(pr.numpy(), fx["preds_r"])
+    np.testing.assert_allclose(dr.numpy(), fx["dmin_r"], atol=1e-6, rtol=0)
+    assert mining.iter_new_links(left, right, emb, [], True, backend=oracle_backend) == [tuple(t) for t in fx["links_refresh"].tolist()]
+    prev = [tuple(t) for t in fx["prev"].tolist()]
+    assert mining.iter_new_links(left, right, emb, prev, False, backend=oracle_backend) == [tuple(t) for t in fx["links_filter"].tolist()]

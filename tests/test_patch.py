@@ -30,7 +30,7 @@ def test_signatures_match_reference():
     from refshim import load_reference
     ref = load_reference()
     import importlib
-    from snag_b200 import evaluate, loss, noise
+    from snag_b200 import evaluate, loss, mining, noise
     for name in ("icl_loss", "ial_loss", "CustomMultiLossLayer"):
         r, m = getattr(ref.loss, name), getattr(loss, name)
         assert _sig(r.__init__) == _sig(m.__init__), name
@@ -40,6 +40,7 @@ def test_signatures_match_reference():
     ref_snag = importlib.import_module("model.SNAG").SNAG
     for name in ("add_noise_to_embeddings", "get_mean_std", "update_noise"):
         assert _sig(getattr(ref_snag, name)) == _sig(getattr(noise, name)), name
+    assert _sig(ref_snag.Iter_new_links) == _sig(mining.Iter_new_links)
     enc = importlib.import_module("model.SNAG_tools").MultiModalEncoder
     assert _sig(enc.forward) == _sig(noise.encoder_forward)
 
@@ -54,7 +55,7 @@ def test_patch_rebinds_reference_names(monkeypatch):
     mods = {n: importlib.import_module(n) for n in ("model.SNAG_loss", "model.SNAG", "model.SNAG_tools", "src.utils")}
     saved = {(n, k): v for n, m in mods.items() for k, v in vars(m).items()}
     snag_cls, enc_cls = mods["model.SNAG"].SNAG, mods["model.SNAG_tools"].MultiModalEncoder
-    saved_cls = {k: getattr(snag_cls, k) for k in ("add_noise_to_embeddings", "get_mean_std", "update_noise")}
+    saved_cls = {k: getattr(snag_cls, k) for k in ("add_noise_to_embeddings", "get_mean_std", "update_noise", "Iter_new_links")}
     saved_fwd = enc_cls.forward
     fake_main = types.ModuleType("main")
     fake_main.Runner = type("Runner", (), {"_test": lambda self: None})
@@ -64,6 +65,8 @@ def test_patch_rebinds_reference_names(monkeypatch):
         assert mods["src.utils"].pairwise_distances is evaluate.pairwise_distances
         assert mods["model.SNAG"].pairwise_distances is evaluate.pairwise_distances
         assert snag_cls.update_noise is noise.update_noise and enc_cls.forward is noise.encoder_forward
+        from snag_b200 import mining
+        assert snag_cls.Iter_new_links is mining.Iter_new_links
         assert fake_main.Runner._test is runner._test and fake_main.csls_sim is evaluate.csls_sim
         assert len(done) >= 12
     finally:
