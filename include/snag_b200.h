@@ -142,6 +142,29 @@ int snag_eval_rank(const uint16_t* X, const uint16_t* Y, const float* xn, const 
                    const float* nv2, const float* g_row, const float* g_col, int32_t row_gid0, int32_t col_gid0,
                    int32_t n1, int32_t n2, int32_t Dpad, int32_t use_csls, int32_t* cnt_row, int32_t* cnt_col,
                    float* top3_val, int32_t* top3_idx, void* stream);
+/* Default form of sweep 2: the same counters, decided in s-space with a deferral band. An element
+ * whose margin to the ground-truth score exceeds `eps` (in units of the dot product) is counted in the sweep; the
+ * others — exact ties included — are appended to band[] (x = view row | direction flags << 30, y = view column;
+ * *band_cnt counts them and may exceed band_cap: re-run with a larger list) and must then be judged by
+ * snag_band_rescore, which evaluates the reference's fp32 chain on the fp64 index-order dot product with the stable
+ * tie-break. Together the two calls give ranks that do not depend on the tensor core's accumulation order.
+ * top4_val/top4_idx (both NULL or fp32/int32 [n_lists][n1][4]): each row's 4 nearest candidate columns per list
+ * (merge with snag_top4_merge, order and cut to ret1..ret3 with snag_top3_rescore). Zero *band_cnt first. */
+int snag_eval_rank_band(const uint16_t* X, const uint16_t* Y, const float* xn, const float* yn, const float* nv1,
+                        const float* nv2, const float* g_row, const float* g_col, int32_t row_gid0, int32_t col_gid0,
+                        int32_t n1, int32_t n2, int32_t Dpad, int32_t use_csls, float eps, int32_t* cnt_row, int32_t* cnt_col,
+                        float* top4_val, int32_t* top4_idx, uint64_t* band, uint32_t* band_cnt, uint32_t band_cap,
+                        void* stream);
+int snag_band_rescore(const uint16_t* X, const uint16_t* Y, int32_t Dpad, const float* xn, const float* yn, const float* nv1,
+                      const float* nv2, const float* g_row, const float* g_col, int32_t row_gid0, int32_t col_gid0,
+                      int32_t use_csls, const uint64_t* band, const uint32_t* band_cnt, uint32_t band_cap, int32_t* cnt_row,
+                      int32_t* cnt_col, void* stream);
+int snag_top4_merge(const float* val, const int32_t* idx, int32_t n_lists, int64_t n_rows, float* oval, int32_t* oidx,
+                    void* stream);
+/* cand int32 [n_rows][4] column ids (0x7fffffff = empty) -> canonical distances, ascending (id ascending on ties) */
+int snag_top3_rescore(const uint16_t* X, const uint16_t* Y, int32_t Dpad, int64_t n_rows, const float* xn, const float* yn,
+                      const float* nv1, const float* nv2, int32_t use_csls, const int32_t* cand, float* oval, int32_t* oidx,
+                      void* stream);
 int snag_top3_merge(const float* val, const int32_t* idx, int32_t n_lists, int64_t n_rows, float* oval, int32_t* oidx,
                     void* stream);
 

@@ -16,6 +16,7 @@ LIB_PATH = Path(os.environ.get("SNAG_B200_LIB") or (Path(__file__).resolve().par
 KT = 16  # SNAG_KT
 
 _i32, _i64, _u64, _f32, _vp = C.c_int32, C.c_int64, C.c_uint64, C.c_float, C.c_void_p
+_u32 = C.c_uint32
 
 # name -> argtypes ; every function returns int except the two noted below
 _SIGNATURES = {
@@ -44,6 +45,11 @@ _SIGNATURES = {
     "snag_pair_score": [_vp, _vp, _i32, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp],
     "snag_eval_rank": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp],
     "snag_top3_merge": [_vp, _vp, _i32, _i64, _vp, _vp, _vp],
+    "snag_eval_rank_band": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _vp, _vp, _vp, _vp,
+                            _vp, _vp, _u32, _vp],
+    "snag_band_rescore": [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _u32, _vp, _vp, _vp],
+    "snag_top4_merge": [_vp, _vp, _i32, _i64, _vp, _vp, _vp],
+    "snag_top3_rescore": [_vp, _vp, _i32, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp],
     "snag_csls_sim": [_vp, _i64, _i64, _i64, _i32, _vp, _i64, _vp, _vp, _vp, _vp],
     "snag_mutual_nn": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp],
     "snag_icl_rowsum": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _vp, _vp, _vp],

@@ -100,6 +100,31 @@ int snag_eval_rank(const uint16_t* X, const uint16_t* Y, const float* xn, const 
   return launch_eval_rank(BF(X), BF(Y), xn, yn, nv1, nv2, g_row, g_col, row_gid0, col_gid0, n1, n2, Dpad, use_csls, cnt_row,
                           cnt_col, top3_val, top3_idx, S(stream));
 }
+int snag_eval_rank_band(const uint16_t* X, const uint16_t* Y, const float* xn, const float* yn, const float* nv1,
+                        const float* nv2, const float* g_row, const float* g_col, int32_t row_gid0, int32_t col_gid0,
+                        int32_t n1, int32_t n2, int32_t Dpad, int32_t use_csls, float eps, int32_t* cnt_row, int32_t* cnt_col,
+                        float* top4_val, int32_t* top4_idx, uint64_t* band, uint32_t* band_cnt, uint32_t band_cap,
+                        void* stream) {
+  return launch_eval_rank_band(BF(X), BF(Y), xn, yn, nv1, nv2, g_row, g_col, row_gid0, col_gid0, n1, n2, Dpad, use_csls, eps,
+                               cnt_row, cnt_col, top4_val, top4_idx, reinterpret_cast<uint2*>(band), band_cnt, band_cap,
+                               S(stream));
+}
+int snag_band_rescore(const uint16_t* X, const uint16_t* Y, int32_t Dpad, const float* xn, const float* yn, const float* nv1,
+                      const float* nv2, const float* g_row, const float* g_col, int32_t row_gid0, int32_t col_gid0,
+                      int32_t use_csls, const uint64_t* band, const uint32_t* band_cnt, uint32_t band_cap, int32_t* cnt_row,
+                      int32_t* cnt_col, void* stream) {
+  return launch_band_rescore(BF(X), BF(Y), Dpad, xn, yn, nv1, nv2, g_row, g_col, row_gid0, col_gid0, use_csls,
+                             reinterpret_cast<const uint2*>(band), band_cnt, band_cap, cnt_row, cnt_col, S(stream));
+}
+int snag_top4_merge(const float* val, const int32_t* idx, int32_t n_lists, int64_t n_rows, float* oval, int32_t* oidx,
+                    void* stream) {
+  return launch_top4_merge(val, idx, n_lists, n_rows, oval, oidx, S(stream));
+}
+int snag_top3_rescore(const uint16_t* X, const uint16_t* Y, int32_t Dpad, int64_t n_rows, const float* xn, const float* yn,
+                      const float* nv1, const float* nv2, int32_t use_csls, const int32_t* cand, float* oval, int32_t* oidx,
+                      void* stream) {
+  return launch_top3_rescore(BF(X), BF(Y), Dpad, n_rows, xn, yn, nv1, nv2, use_csls, cand, oval, oidx, S(stream));
+}
 int snag_top3_merge(const float* val, const int32_t* idx, int32_t n_lists, int64_t n_rows, float* oval, int32_t* oidx,
                     void* stream) {
   return launch_top3_merge(val, idx, n_lists, n_rows, oval, oidx, S(stream));

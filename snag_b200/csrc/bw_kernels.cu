@@ -357,6 +357,128 @@ __global__ void __launch_bounds__(128) pair_score_kernel(const __nv_bfloat16* __
   g[p] = __fsub_rn(1.0f, __fsub_rn(u, nv2[p]));
 }
 
+// canonical dot product of two bf16 rows: fp64 accumulation in index order, rounded once to fp32 (the oracle's s_ij)
+__device__ __forceinline__ float canonical_dot(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ y, int Dpad) {
+  const uint4* xr = reinterpret_cast<const uint4*>(x);
+  const uint4* yr = reinterpret_cast<const uint4*>(y);
+  double acc = 0.0;
+  for (int c = 0; c < Dpad / 8; ++c) {
+    const uint4 a = __ldg(xr + c), b = __ldg(yr + c);
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float a0 = __uint_as_float(aw[e] << 16), a1 = __uint_as_float(aw[e] & 0xffff0000u);
+      const float b0 = __uint_as_float(bw[e] << 16), b1 = __uint_as_float(bw[e] & 0xffff0000u);
+      acc = fma(static_cast<double>(a0), static_cast<double>(b0), acc);
+      acc = fma(static_cast<double>(a1), static_cast<double>(b1), acc);
+    }
+  }
+  return static_cast<float>(acc);
+}
+// the reference's fp32 chain from s to the (CSLS) distance, one rounding per op (simgemm.cuh has the same two helpers)
+__device__ __forceinline__ float canonical_dist(float s, float xn, float yn, float nv1, float nv2, int use_csls) {
+  const float d = fmaxf(__fmaf_rn(-2.0f, s, __fadd_rn(xn, yn)), 0.0f);
+  if (!use_csls) return d;
+  const float c = __fsub_rn(1.0f, d);
+  return __fsub_rn(1.0f, __fsub_rn(__fmaf_rn(2.0f, c, -nv1), nv2));
+}
+
+// ------------------------------------------------------------------------------------------------
+// Deferred elements of the rank sweep (EpiRankBand): every (row, column) whose margin to a ground-truth score was
+// inside the band is judged here with the canonical arithmetic and the stable-sort tie-break (main.py:400-429 with
+// torch.sort(stable=True)): one thread per element.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) band_rescore_kernel(const __nv_bfloat16* __restrict__ X, const __nv_bfloat16* __restrict__ Y,
+                                                           int Dpad, const float* __restrict__ xn, const float* __restrict__ yn,
+                                                           const float* __restrict__ nv1, const float* __restrict__ nv2,
+                                                           const float* __restrict__ g_row, const float* __restrict__ g_col,
+                                                           int row_gid0, int col_gid0, int use_csls,
+                                                           const uint2* __restrict__ band, const unsigned int* __restrict__ band_cnt,
+                                                           unsigned int band_cap, int* __restrict__ cnt_row, int* __restrict__ cnt_col) {
+  const unsigned int total = min(*band_cnt, band_cap);
+  for (unsigned int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    const uint2 it = band[e];
+    const int i = static_cast<int>(it.x & 0x3fffffffu), j = static_cast<int>(it.y);
+    const uint32_t flags = it.x >> 30;
+    const float s = canonical_dot(X + static_cast<long long>(i) * Dpad, Y + static_cast<long long>(j) * Dpad, Dpad);
+    const float dist = canonical_dist(s, xn[i], yn[j], use_csls ? nv1[i] : 0.f, use_csls ? nv2[j] : 0.f, use_csls);
+    const int ig = row_gid0 + i, jg = col_gid0 + j;
+    if (ig == jg) continue;
+    if (flags & 1u) {
+      const float g = g_row[i];
+      if (dist < g || (dist == g && jg < ig)) atomicAdd(cnt_row + i, 1);
+    }
+    if (flags & 2u) {
+      const float g = g_col[j];
+      if (dist < g || (dist == g && ig < jg)) atomicAdd(cnt_col + j, 1);
+    }
+  }
+}
+
+// merge per-list top-4 candidate lists of each row (x descending = nearest first, column id ascending on ties)
+__global__ void __launch_bounds__(128) top4_merge_kernel(const float* __restrict__ val, const int* __restrict__ idx, int n_lists,
+                                                         long long n_rows, float* __restrict__ oval, int* __restrict__ oidx) {
+  const long long row = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (row >= n_rows) return;
+  float v[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+  int id[4] = {0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff};
+  for (int l = 0; l < n_lists; ++l) {
+    const float4 cv = __ldg(reinterpret_cast<const float4*>(val + (static_cast<long long>(l) * n_rows + row) * 4));
+    const int4 ci = __ldg(reinterpret_cast<const int4*>(idx + (static_cast<long long>(l) * n_rows + row) * 4));
+    const float cvv[4] = {cv.x, cv.y, cv.z, cv.w};
+    const int cii[4] = {ci.x, ci.y, ci.z, ci.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (cii[e] == 0x7fffffff) continue;
+      if (cvv[e] > v[3] || (cvv[e] == v[3] && cii[e] < id[3])) {
+        v[3] = cvv[e]; id[3] = cii[e];
+#pragma unroll
+        for (int t = 3; t > 0; --t) {
+          if (v[t] > v[t - 1] || (v[t] == v[t - 1] && id[t] < id[t - 1])) {
+            const float tv = v[t]; v[t] = v[t - 1]; v[t - 1] = tv;
+            const int ti = id[t]; id[t] = id[t - 1]; id[t - 1] = ti;
+          }
+        }
+      }
+    }
+  }
+  *reinterpret_cast<float4*>(oval + row * 4) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<int4*>(oidx + row * 4) = make_int4(id[0], id[1], id[2], id[3]);
+}
+
+// canonical distances of each row's (up to) four nearest candidates, sorted ascending (column id ascending on ties):
+// entries 0..2 are ret1..ret3 of the prediction file (main.py:411)
+__global__ void __launch_bounds__(128) top3_rescore_kernel(const __nv_bfloat16* __restrict__ X, const __nv_bfloat16* __restrict__ Y,
+                                                           int Dpad, long long n_rows, const float* __restrict__ xn,
+                                                           const float* __restrict__ yn, const float* __restrict__ nv1,
+                                                           const float* __restrict__ nv2, int use_csls,
+                                                           const int* __restrict__ cand, float* __restrict__ oval,
+                                                           int* __restrict__ oidx) {
+  const long long row = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (row >= n_rows) return;
+  const int4 ci = __ldg(reinterpret_cast<const int4*>(cand + row * 4));
+  int id[4] = {ci.x, ci.y, ci.z, ci.w};
+  float v[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    if (id[e] == 0x7fffffff) { v[e] = INFINITY; continue; }
+    const float s = canonical_dot(X + row * Dpad, Y + static_cast<long long>(id[e]) * Dpad, Dpad);
+    v[e] = canonical_dist(s, xn[row], yn[id[e]], use_csls ? nv1[row] : 0.f, use_csls ? nv2[id[e]] : 0.f, use_csls);
+  }
+#pragma unroll
+  for (int a = 1; a < 4; ++a) {           // insertion sort on (dist, id)
+#pragma unroll
+    for (int t = a; t > 0; --t) {
+      if (v[t] < v[t - 1] || (v[t] == v[t - 1] && id[t] < id[t - 1])) {
+        const float tv = v[t]; v[t] = v[t - 1]; v[t - 1] = tv;
+        const int ti = id[t]; id[t] = id[t - 1]; id[t - 1] = ti;
+      }
+    }
+  }
+  *reinterpret_cast<float4*>(oval + row * 4) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<int4*>(oidx + row * 4) = make_int4(id[0], id[1], id[2], id[3]);
+}
+
 // merge per-chunk top-3 (value asc, index asc on ties) lists of each row
 __global__ void __launch_bounds__(128) top3_merge_kernel(const float* __restrict__ val, const int* __restrict__ idx, int n_lists,
                                                          long long n_rows, float* __restrict__ oval, int* __restrict__ oidx) {
@@ -684,6 +806,36 @@ int launch_pair_score(const __nv_bfloat16* X, const __nv_bfloat16* Y, int Dpad, 
   if (use_csls && (!nv1 || !nv2)) return SNAG_ERR_ARG;
   if (Dpad % 64) return SNAG_ERR_SHAPE;
   pair_score_kernel<<<static_cast<int>((n + 127) / 128), 128, 0, st>>>(X, Y, Dpad, n, xn, yn, nv1, nv2, use_csls, g, s_out);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int launch_band_rescore(const __nv_bfloat16* X, const __nv_bfloat16* Y, int Dpad, const float* xn, const float* yn,
+                        const float* nv1, const float* nv2, const float* g_row, const float* g_col, int row_gid0, int col_gid0,
+                        int use_csls, const uint2* band, const unsigned int* band_cnt, unsigned int band_cap, int* cnt_row,
+                        int* cnt_col, cudaStream_t st) {
+  if (!X || !Y || !xn || !yn || !g_row || !g_col || !band || !band_cnt || !cnt_row || !cnt_col) return SNAG_ERR_ARG;
+  if (use_csls && (!nv1 || !nv2)) return SNAG_ERR_ARG;
+  if (Dpad % 64) return SNAG_ERR_SHAPE;
+  // grid-stride over the device-side count: no host round trip
+  band_rescore_kernel<<<num_sms() * 16, 128, 0, st>>>(X, Y, Dpad, xn, yn, nv1, nv2, g_row, g_col, row_gid0, col_gid0, use_csls,
+                                                      band, band_cnt, band_cap, cnt_row, cnt_col);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int launch_top4_merge(const float* val, const int* idx, int n_lists, long long n_rows, float* oval, int* oidx, cudaStream_t st) {
+  if (!val || !idx || !oval || !oidx || n_lists <= 0 || n_rows <= 0) return SNAG_ERR_ARG;
+  top4_merge_kernel<<<static_cast<int>((n_rows + 127) / 128), 128, 0, st>>>(val, idx, n_lists, n_rows, oval, oidx);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int launch_top3_rescore(const __nv_bfloat16* X, const __nv_bfloat16* Y, int Dpad, long long n_rows, const float* xn,
+                        const float* yn, const float* nv1, const float* nv2, int use_csls, const int* cand, float* oval,
+                        int* oidx, cudaStream_t st) {
+  if (!X || !Y || !xn || !yn || !cand || !oval || !oidx || n_rows <= 0) return SNAG_ERR_ARG;
+  if (use_csls && (!nv1 || !nv2)) return SNAG_ERR_ARG;
+  if (Dpad % 64) return SNAG_ERR_SHAPE;
+  top3_rescore_kernel<<<static_cast<int>((n_rows + 127) / 128), 128, 0, st>>>(X, Y, Dpad, n_rows, xn, yn, nv1, nv2, use_csls,
+                                                                            cand, oval, oidx);
   return static_cast<int>(cudaGetLastError());
 }
 

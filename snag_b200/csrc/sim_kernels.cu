@@ -180,6 +180,31 @@ int launch_eval_rank(const __nv_bfloat16* X, const __nv_bfloat16* Y, const float
 #undef SNAG_RANK_CASE
 }
 
+int launch_eval_rank_band(const __nv_bfloat16* X, const __nv_bfloat16* Y, const float* xn, const float* yn, const float* nv1,
+                          const float* nv2, const float* g_row, const float* g_col, int row_gid0, int col_gid0, int n1, int n2,
+                          int Dpad, int use_csls, float eps, int* cnt_row, int* cnt_col, float* top4_val, int* top4_idx,
+                          uint2* band, unsigned int* band_cnt, unsigned int band_cap, cudaStream_t st) {
+  if (!xn || !yn || !g_row || !g_col || !cnt_row || !cnt_col || !band || !band_cnt) return SNAG_ERR_ARG;
+  if (use_csls && (!nv1 || !nv2)) return SNAG_ERR_ARG;
+  if (!(eps > 0.f) || n1 >= (1 << 30)) return SNAG_ERR_ARG;
+  if (!use_csls) { nv1 = xn; nv2 = yn; }   // never read for their values
+  if ((top4_val == nullptr) != (top4_idx == nullptr)) return SNAG_ERR_ARG;
+  if (top4_val && ((reinterpret_cast<uintptr_t>(top4_val) | reinterpret_cast<uintptr_t>(top4_idx)) & 15)) return SNAG_ERR_ALIGN;
+  if (reinterpret_cast<uintptr_t>(band) & 7) return SNAG_ERR_ALIGN;
+#define SNAG_RANKB_CASE(T3, CS)                                                                                      \
+  {                                                                                                                  \
+    typename EpiRankBand<T3, CS>::Params p{xn, yn, nv1, nv2, g_row, g_col, row_gid0, col_gid0, cnt_row, cnt_col,     \
+                                           top4_val, top4_idx, eps, band, band_cnt, band_cap};                       \
+    return launch_sim<EpiRankBand<T3, CS>>(X, Y, n1, n2, Dpad, p, st);                                               \
+  }
+  if (top4_val) {
+    if (use_csls) SNAG_RANKB_CASE(true, true) else SNAG_RANKB_CASE(true, false)
+  } else {
+    if (use_csls) SNAG_RANKB_CASE(false, true) else SNAG_RANKB_CASE(false, false)
+  }
+#undef SNAG_RANKB_CASE
+}
+
 int launch_icl_rowsum(const __nv_bfloat16* X, const __nv_bfloat16* Y, int B, int Bp, int row0, int nx, int Dpad,
                       float inv_tau, float* rowsum_part, float* pos, cudaStream_t st) {
   if (!rowsum_part || !pos || B <= 0 || Bp < B || (Bp % BN) != 0) return SNAG_ERR_ARG;

@@ -86,6 +86,11 @@ struct EpiCtx {
 #define SNAG_CTRL_SYNC()
 #endif
 
+// number of 32-column strips of column tile ct that contain valid columns (BN/32 for every tile but a ragged last one)
+__device__ __forceinline__ int tile_strips(const SimShape& shp, int ct) {
+  return min(BN, shp.n_cols - ct * BN + 31) >> 5;
+}
+
 // registers carrying one column's prefetched per-tile values from tile_prefetch to tile_commit
 struct EpiPre {
   float a, b, c;
@@ -172,7 +177,6 @@ sim_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
     }
   } else if (cwarp == 1) {
     // ------------------------------------------------------------------ UMMA issuer (same structure)
-    constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
     const uint32_t leader = SNAG_CTRL_LEADER;
     const uint64_t adesc0 = make_sdesc_k128(base);
     const uint64_t bdesc0 = make_sdesc_k128(base + A_STAGE_BYTES);
@@ -190,6 +194,9 @@ sim_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
         if (dbg) { w_acc += clock64() - tw; ++n_tiles; }
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * BN;
+        // ragged last column tile: only the 32-column strips that hold valid columns are computed (UMMA N = 32..256);
+        // the epilogue skips the others
+        const uint32_t idesc = make_idesc_bf16(BM, tile_strips(shp, ct) * 32);
         uint32_t accumulate = 0;
         for (int kb = 0; kb < shp.kblocks; ++kb) {
           mbar_wait(full_bar(stage), phase);
@@ -262,7 +269,8 @@ sim_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
         // (a fully unrolled tile body was ~150 KB of SASS and ran instruction-fetch bound).
         if constexpr (!Epi::kNoLoad) {
 #pragma unroll 1
-          for (int c = cx.wg * STRIPS_PER_WG; c < (cx.wg + 1) * STRIPS_PER_WG; ++c) {
+          const int c_end = min((cx.wg + 1) * STRIPS_PER_WG, tile_strips(shp, ct));
+          for (int c = cx.wg * STRIPS_PER_WG; c < c_end; ++c) {
             uint32_t r[32];
             SNAG_TMEM_LD32(taddr + c * 32, r);
             SNAG_TMEM_WAIT32(r);
@@ -368,6 +376,26 @@ struct EpiLoadOnly {
   }
 };
 
+// Coalesced store of a warp's 32 rows x 64 bytes (thread t holds row t as four 16-byte pieces): staged through a 2 KB
+// shared-memory window private to the warp (XOR-swizzled, conflict-free both ways) and written back so that every
+// store instruction covers 8 rows x 64 contiguous bytes (full 32-byte sectors) instead of 32 rows x 16 bytes.
+// dst = address of row 0's 64 bytes; rows_ok = number of leading rows of the warp that may be written.
+__device__ __forceinline__ void warp_store_rows64(uint8_t* win, int lane, const uint4 (&v)[4], uint8_t* dst,
+                                                  long long row_stride_bytes, int rows_ok) {
+  __syncwarp();                                       // the previous use of the window has been read back
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    *reinterpret_cast<uint4*>(win + lane * 64 + 16 * (k ^ ((lane >> 1) & 3))) = v[k];
+  __syncwarp();
+  const int piece = lane & 3;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = (lane >> 2) + 8 * i;
+    const uint4 t = *reinterpret_cast<const uint4*>(win + row * 64 + 16 * (piece ^ ((row >> 1) & 3)));
+    if (row < rows_ok) *reinterpret_cast<uint4*>(dst + row * row_stride_bytes + 16 * piece) = t;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Epilogue: write S (mode 0) or the squared-L2 distance (mode 1) — drop-in pairwise_distances
 // ------------------------------------------------------------------------------------------------
@@ -399,6 +427,7 @@ struct EpiWrite {
   }
   static __device__ __forceinline__ void chunk(const Params& p, const SimShape& shp, const EpiCtx& cx, State& st,
                                                int ct, int c, const uint32_t (&r)[32], int buf) {
+    if (strip_coalesced(p, shp, cx, st, ct, c, r, buf)) return;       // warp-uniform
     const float* yn_s = cx.scratch + buf * BN + c * 32;
     const int col0 = ct * BN + c * 32;
     if (!cx.row_ok) return;
@@ -419,6 +448,33 @@ struct EpiWrite {
       for (int q = 0; q < 32; ++q)
         if (col0 + q < shp.n_cols) orow[q] = v[q];
     }
+  }
+  // full strips of 16-byte aligned outputs go through the coalescing window, two 64-byte halves per row
+  static __device__ __forceinline__ bool strip_coalesced(const Params& p, const SimShape& shp, const EpiCtx& cx, State& st,
+                                                         int ct, int c, const uint32_t (&r)[32], int buf) {
+    const int col0 = ct * BN + c * 32;
+    if (col0 + 32 > shp.n_cols || ((reinterpret_cast<uintptr_t>(p.out) | static_cast<uintptr_t>(p.ld * 4)) & 15)) return false;
+    const float* yn_s = cx.scratch + buf * BN + c * 32;
+    const int row_w0 = cx.rb * BM + (cx.et & ~31);            // first row of this warp
+    uint8_t* win = reinterpret_cast<uint8_t*>(cx.scratch + EPI_VEC_FLOATS) + (cx.tid >> 5) * 2048;
+    uint8_t* dst = reinterpret_cast<uint8_t*>(p.out + static_cast<long long>(row_w0) * p.ld + col0);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      uint4 v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float f[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int q = 16 * h + 4 * k + e;
+          const float sv = __uint_as_float(r[q]);
+          f[e] = (p.mode == 1) ? sqdist_from_dot(sv, st.xn, yn_s[q]) : sv;
+        }
+        v[k] = make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
+      }
+      warp_store_rows64(win, cx.lane, v, dst + 64 * h, p.ld * 4, shp.n_rows - row_w0);
+    }
+    return true;
   }
   static __device__ __forceinline__ void tile_end(const Params&, const SimShape&, const EpiCtx&, State&, int, int) {}
   static __device__ __forceinline__ void unit_end(const Params&, const SimShape&, const EpiCtx&, State&) {}
@@ -916,6 +972,175 @@ struct EpiRank {
 };
 
 // ------------------------------------------------------------------------------------------------
+// Epilogue: rank counting in s-space with a deferral band (the default sweep 2).
+// The CSLS chain is affine in s (apart from the clamp, which only acts within rounding distance of d = 0):
+//   dist_ij = 2 (xn_i + yn_j - 2 s_ij) - 1 + nv1_i + nv2_j
+// so   dist_ij < g_i   <=>   s_ij > R_i + C_j ,    R_i  = (2 xn_i + nv1_i - 1 - g_i)/4 ,  C_j  = (2 yn_j + nv2_j)/4
+// and  dist_ij < g_j   <=>   s_ij > R'_i + C'_j ,  R'_i = (2 xn_i + nv1_i - 1)/4 ,        C'_j = (2 yn_j + nv2_j - g_j)/4
+// (without CSLS: R = (xn - g)/2, C = yn/2, R' = xn/2, C' = (yn - g)/2).
+// An element whose margin exceeds eps in magnitude has the same verdict under the reference's fp32 chain evaluated
+// on the canonically accumulated dot product (eps covers the tensor-core accumulation error, the chain's roundings and
+// the roundings of R, C): it is counted here with two subtractions and four compares. Elements inside the band —
+// exact ties and the ground-truth column included — are NOT counted; they are appended to a list and judged afterwards
+// by band_rescore_kernel with the canonical arithmetic (fp64 index-order dot, the reference's op order, stable-sort
+// tie-break). The ranks therefore do not depend on the tensor core's accumulation order.
+// kTop3: the four columns with the largest x = s - C_j per row (nearest first; re-scored and cut to three afterwards).
+// ------------------------------------------------------------------------------------------------
+template <bool kTop3, bool kCsls>
+struct EpiRankBand {
+  static constexpr bool kNoLoad = false;
+  struct Params {
+    const float* xn;     // [n_rows]
+    const float* yn;     // [n_cols]
+    const float* nv1;    // [n_rows]
+    const float* nv2;    // [n_cols]
+    const float* g_row;  // [n_rows]  dist of pair(row gid)
+    const float* g_col;  // [n_cols]  dist of pair(col gid)
+    int row_gid0;        // global pair id of view row 0
+    int col_gid0;        // global pair id of view column 0
+    int* cnt_row;        // [n_rows]  (atomically accumulated, caller zeroes)
+    int* cnt_col;        // [n_cols]
+    float* top4_val;     // [n_lists][n_rows][4] (kTop3) x = s - C_j, descending
+    int* top4_idx;       // [n_lists][n_rows][4] (kTop3) column gid
+    float eps;           // half-width of the deferral band in s-space
+    uint2* band;         // [band_cap] deferred elements: x = view row | direction flags << 30, y = view column
+    unsigned int* band_cnt;   // number of deferred elements (may exceed band_cap: overflow, caller re-runs)
+    unsigned int band_cap;
+  };
+  struct State {
+    float r_lo, r_hi, rp;
+    int gid;
+    int cnt;
+    float t4v[4];
+    int t4i[4];
+  };
+  static __device__ __forceinline__ void unit_begin(const Params& p, const SimShape&, const EpiCtx& cx, State& st) {
+    st.gid = p.row_gid0 + cx.row;
+    st.cnt = 0;
+    if (cx.row_ok) {
+      const float xn = p.xn[cx.row], g = p.g_row[cx.row];
+      float R, Rp;
+      if (kCsls) {
+        const float base = __fmaf_rn(2.0f, xn, p.nv1[cx.row]) - 1.0f;
+        R = 0.25f * (base - g);
+        Rp = 0.25f * base;
+      } else {
+        R = 0.5f * (xn - g);
+        Rp = 0.5f * xn;
+      }
+      st.r_lo = R - p.eps;
+      st.r_hi = R + p.eps;
+      st.rp = Rp;
+    } else {                       // padding rows: nothing is ever above +inf, and s - inf = -inf on the column side
+      st.r_lo = st.r_hi = st.rp = INFINITY;
+    }
+    if (kTop3) {
+#pragma unroll
+      for (int t = 0; t < 4; ++t) { st.t4v[t] = -INFINITY; st.t4i[t] = 0x7fffffff; }
+    }
+  }
+  static __device__ __forceinline__ EpiPre tile_prefetch(const Params& p, const SimShape& shp, const EpiCtx& cx, int ct) {
+    static_assert(NUM_EPI_THREADS >= BN, "one epilogue thread stages one column");
+    EpiPre pre{INFINITY, INFINITY, INFINITY};   // out-of-range columns: x = -inf, thresholds +inf
+    const int col = ct * BN + cx.tid;
+    if (cx.tid < BN && col < shp.n_cols) {
+      const float yn = p.yn[col], g = p.g_col[col];
+      float C, Cp;
+      if (kCsls) {
+        const float base = __fmaf_rn(2.0f, yn, p.nv2[col]);
+        C = 0.25f * base;
+        Cp = 0.25f * (base - g);
+      } else {
+        C = 0.5f * yn;
+        Cp = 0.5f * (yn - g);
+      }
+      pre.a = C;
+      pre.b = Cp - p.eps;
+      pre.c = Cp + p.eps;
+    }
+    return pre;
+  }
+  static __device__ __forceinline__ void tile_commit(const Params&, const SimShape&, const EpiCtx& cx, State&,
+                                                     const EpiPre& pre, int, int buf) {
+    if (cx.tid >= BN) return;
+    float* s = cx.scratch + buf * (3 * BN);
+    s[cx.tid] = pre.a;
+    s[BN + cx.tid] = pre.b;
+    s[2 * BN + cx.tid] = pre.c;
+  }
+  static __device__ __forceinline__ void chunk(const Params& p, const SimShape& shp, const EpiCtx& cx, State& st, int ct,
+                                               int c, const uint32_t (&r)[32], int buf) {
+    const float* s = cx.scratch + buf * (3 * BN) + c * 32;
+    const int col0 = ct * BN + c * 32;
+    const int cgid0 = p.col_gid0 + col0;
+    uint32_t ra = 0, rb = 0, ca = 0, cb = 0, tm = 0;
+#pragma unroll
+    for (int q = 0; q < 32; ++q) {
+      const float sv = __uint_as_float(r[q]);
+      const float x = __fsub_rn(sv, s[q]);
+      const float y = __fsub_rn(sv, st.rp);
+      if (x > st.r_hi) ra |= (1u << q);
+      if (x > st.r_lo) rb |= (1u << q);
+      if (y > s[2 * BN + q]) ca |= (1u << q);
+      if (y > s[BN + q]) cb |= (1u << q);
+      if (kTop3) { if (x > st.t4v[3]) tm |= (1u << q); }
+    }
+    uint32_t rband = rb & ~ra, cband = cb & ~ca;
+    // the ground-truth column of this row is never a competitor (main.py:400-411 ranks it, it does not count itself)
+    const int qd = st.gid - cgid0;
+    if (qd >= 0 && qd < 32) {
+      const uint32_t keep = ~(1u << qd);
+      ra &= keep; ca &= keep; rband &= keep; cband &= keep;
+    }
+    uint32_t deferred = rband | cband;
+    while (deferred != 0) {                                   // rare: a handful of elements per row
+      const int q = __ffs(deferred) - 1;
+      deferred &= deferred - 1;
+      const unsigned int slot = atomicAdd(p.band_cnt, 1u);
+      if (slot < p.band_cap) {
+        const uint32_t flags = ((rband >> q) & 1u) | (((cband >> q) & 1u) << 1);
+        p.band[slot] = make_uint2(static_cast<uint32_t>(cx.row) | (flags << 30), static_cast<uint32_t>(col0 + q));
+      }
+    }
+    st.cnt += __popc(ra);
+    // column counts: transpose the warp's 32x32 predicate bit-matrix, then popc -> lane l owns column l
+    const int votes = __popc(transpose32(ca, cx.lane));
+    if (votes != 0 && col0 + cx.lane < shp.n_cols) atomicAdd(p.cnt_col + col0 + cx.lane, votes);
+    if (kTop3) {
+      while (tm != 0) {
+        const int q = __ffs(tm) - 1;
+        tm &= tm - 1;
+        // r[] is indexed with a run-time q here: re-read the value through a select chain the compiler keeps in registers
+        float sv = 0.f;
+#pragma unroll
+        for (int e = 0; e < 32; ++e) sv = (e == q) ? __uint_as_float(r[e]) : sv;
+        const float x = __fsub_rn(sv, s[q]);
+        if (x > st.t4v[3]) {                                  // columns arrive in increasing order: strict keeps the first
+          st.t4v[3] = x; st.t4i[3] = cgid0 + q;
+#pragma unroll
+          for (int t = 3; t > 0; --t) {
+            if (st.t4v[t] > st.t4v[t - 1]) {
+              const float tv = st.t4v[t]; st.t4v[t] = st.t4v[t - 1]; st.t4v[t - 1] = tv;
+              const int ti = st.t4i[t]; st.t4i[t] = st.t4i[t - 1]; st.t4i[t - 1] = ti;
+            }
+          }
+        }
+      }
+    }
+  }
+  static __device__ __forceinline__ void tile_end(const Params&, const SimShape&, const EpiCtx&, State&, int, int) {}
+  static __device__ __forceinline__ void unit_end(const Params& p, const SimShape& shp, const EpiCtx& cx, State& st) {
+    if (!cx.row_ok) return;
+    if (st.cnt != 0) atomicAdd(p.cnt_row + cx.row, st.cnt);
+    if (kTop3) {
+      const long long o = (static_cast<long long>(cx.list) * shp.n_rows + cx.row) * 4;
+      *reinterpret_cast<float4*>(p.top4_val + o) = make_float4(st.t4v[0], st.t4v[1], st.t4v[2], st.t4v[3]);
+      *reinterpret_cast<int4*>(p.top4_idx + o) = make_int4(st.t4i[0], st.t4i[1], st.t4i[2], st.t4i[3]);
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
 // Epilogue: in-batch contrastive row sums (ICL forward, model/SNAG_loss.py:98-126).
 // X view = rows [row0, row0 + nx) of one side of the batch (the anchors this rank owns; the whole side when the
 // loss is not sharded); Y view = [other side | same side], 2*Bp rows, B valid per part.
@@ -1011,8 +1236,9 @@ struct EpiIclBwd {
   static __device__ __forceinline__ void unit_begin(const Params& p, const SimShape&, const EpiCtx& cx, State& st) {
     st.gr = p.row0 + cx.row;
     st.ok = cx.row_ok && st.gr < p.B;
-    st.cr = st.ok ? p.cr[st.gr] : 0.f;
-    st.dg = st.ok ? p.dg[st.gr] : 0.f;
+    // coefficients carry the 1/tau factor from here on (one multiply per row / per staged column instead of per element)
+    st.cr = st.ok ? p.cr[st.gr] * p.inv_tau : 0.f;
+    st.dg = st.ok ? p.dg[st.gr] * p.inv_tau : 0.f;
   }
   static __device__ __forceinline__ EpiPre tile_prefetch(const Params& p, const SimShape&, const EpiCtx& cx, int ct) {
     static_assert(NUM_EPI_THREADS >= BN, "one epilogue thread stages one column");
@@ -1021,7 +1247,7 @@ struct EpiIclBwd {
       const int col = ct * BN + cx.tid;
       const int part = col >= p.Bp ? 1 : 0;
       const int idx = col - part * p.Bp;
-      if (idx < p.B) pre.a = part ? p.cr[idx] : p.cc[idx];
+      if (idx < p.B) pre.a = (part ? p.cr[idx] : p.cc[idx]) * p.inv_tau;
     }
     return pre;
   }
@@ -1035,29 +1261,46 @@ struct EpiIclBwd {
     const int col0 = ct * BN + c * 32;
     const int part = col0 >= p.Bp ? 1 : 0;
     const int idx0 = col0 - part * p.Bp;
-    const bool row_ok = st.ok;
     const float nb = -p.scale_log2;
+    const int gr0 = p.row0 + cx.rb * BM;                 // batch index of the row block's first anchor
+    // plain strip (CTA-uniform): every anchor of the row block and every column of the strip is valid and the strip
+    // does not meet the block's diagonal -> 4 arithmetic instructions per element (FFMA, MUFU.EX2, FADD, FMUL)
+    const bool plain = (gr0 + BM <= p.B) && ((cx.rb + 1) * BM <= p.nx) && (idx0 + 32 <= p.B) &&
+                       (idx0 + 31 < gr0 || idx0 > gr0 + BM - 1);
     uint32_t packed[16];
+    if (plain) {
 #pragma unroll
-    for (int q = 0; q < 32; q += 2) {
-      float v[2];
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int idx = idx0 + q + e;
-        const float E = ex2_approx(__fmaf_rn(__uint_as_float(r[q + e]), p.scale_log2, nb));
-        float gval = (st.cr + cc_s[q + e]) * E * p.inv_tau;
-        if (idx == st.gr) gval = part ? 0.f : gval - st.dg * p.inv_tau;
-        if (!row_ok || idx >= p.B) gval = 0.f;
-        v[e] = gval;
+      for (int q = 0; q < 32; q += 2) {
+        const float e0 = ex2_approx(__fmaf_rn(__uint_as_float(r[q]), p.scale_log2, nb));
+        const float e1 = ex2_approx(__fmaf_rn(__uint_as_float(r[q + 1]), p.scale_log2, nb));
+        const __nv_bfloat162 h = __floats2bfloat162_rn((st.cr + cc_s[q]) * e0, (st.cr + cc_s[q + 1]) * e1);
+        packed[q / 2] = *reinterpret_cast<const uint32_t*>(&h);
       }
-      const __nv_bfloat162 h = __floats2bfloat162_rn(v[0], v[1]);
-      packed[q / 2] = *reinterpret_cast<const uint32_t*>(&h);
-    }
-    if (cx.row_ok) {
-      uint4* dst = reinterpret_cast<uint4*>(p.G + static_cast<long long>(cx.row) * (2 * p.Bp) + col0);
+    } else {
+      const bool row_ok = st.ok;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) dst[q] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+      for (int q = 0; q < 32; q += 2) {
+        float v[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int idx = idx0 + q + e;
+          const float E = ex2_approx(__fmaf_rn(__uint_as_float(r[q + e]), p.scale_log2, nb));
+          float gval = (st.cr + cc_s[q + e]) * E;
+          if (idx == st.gr) gval = part ? 0.f : gval - st.dg;
+          if (!row_ok || idx >= p.B) gval = 0.f;
+          v[e] = gval;
+        }
+        const __nv_bfloat162 h = __floats2bfloat162_rn(v[0], v[1]);
+        packed[q / 2] = *reinterpret_cast<const uint32_t*>(&h);
+      }
     }
+    uint4 v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) v[q] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+    const int row_w0 = cx.rb * BM + (cx.et & ~31);              // first row of this warp
+    uint8_t* win = reinterpret_cast<uint8_t*>(cx.scratch + EPI_VEC_FLOATS) + (cx.tid >> 5) * 2048;
+    uint8_t* dst = reinterpret_cast<uint8_t*>(p.G + static_cast<long long>(row_w0) * (2 * p.Bp) + col0);
+    warp_store_rows64(win, cx.lane, v, dst, 4ll * p.Bp, p.nx - row_w0);
   }
   static __device__ __forceinline__ void tile_end(const Params&, const SimShape&, const EpiCtx&, State&, int, int) {}
   static __device__ __forceinline__ void unit_end(const Params&, const SimShape&, const EpiCtx&, State&) {}

@@ -148,14 +148,16 @@ def _align_ranks_steps(be, X, Y, xn, yn, n: int, csls_k: int, use_csls: bool, wa
         nv2s = nv2[c0:c1] if use_csls else None
         t3v, t3i = be.eval_rank(X, Ys, xn, yns, nv1, nv2s, g, g[c0:c1], 0, c0, n, ns, use_csls, cnt_row, cnt_col_loc,
                                 want_top3)
-        launches += 1
+        launches += 2                                   # the sweep and the re-score of its deferred elements
     top3_idx = top3_val = None
     if want_top3:
+        # each list holds the row's 4 nearest candidates (by the tensor-core score); merged here, exchanged when sharded,
+        # then ordered by their canonical distances and cut to ret1..ret3
         if ns > 0:
-            t3v, t3i = be.top3_merge(t3v, t3i)
+            t3v, t3i = be.top4_merge(t3v, t3i)
             launches += 1
         else:
-            t3v = torch.full((n, 4), float("inf"), dtype=torch.float32, device=dev)
+            t3v = torch.full((n, 4), float("-inf"), dtype=torch.float32, device=dev)
             t3i = torch.full((n, 4), 0x7FFFFFFF, dtype=torch.int32, device=dev)
     if world == 1:
         rank_l2r, rank_r2l = cnt_row, cnt_col_loc[:n]
@@ -166,12 +168,14 @@ def _align_ranks_steps(be, X, Y, xn, yn, n: int, csls_k: int, use_csls: bool, wa
         if want_top3:
             gv = yield ("all_gather", t3v.contiguous())                # [world, n, 4]
             gi = yield ("all_gather", t3i.contiguous())
-            t3v, t3i = be.top3_merge(gv.contiguous(), gi.contiguous())
+            t3v, t3i = be.top4_merge(gv.contiguous(), gi.contiguous())
             launches += 1
     if want_top3:
+        t3v, t3i = be.top3_rescore(X, Y, xn, yn, nv1, nv2, use_csls, t3i)
+        launches += 1
         top3_idx, top3_val = t3i[:, :3], t3v[:, :3]
     return AlignRanks(rank_l2r, rank_r2l, nv1, nv2, g, top3_idx, top3_val, launches,
-                      {"world": world, "rank": rank, "shard": (c0, c1)})
+                      {"world": world, "rank": rank, "shard": (c0, c1), "rank_sweep": dict(getattr(be, "LAST_RANK_INFO", {}))})
 
 
 def _drive_with_torch_distributed(gen, group):

@@ -219,8 +219,22 @@ def pair_score(X, Y, n: int, xn, yn, nv1, nv2, use_csls: bool, want_dot: bool = 
     return (g, s) if want_dot else g
 
 
+# Half-width of the rank sweep's deferral band, in units of the dot product s. It has to cover (a) the tensor core's
+# accumulation error against the fp64 index-order dot product (measured < 5e-7 for unit rows up to D = 1856;
+# tests/test_eval_gpu.py::test_tensor_core_dot_error pins it), (b) the roundings of the reference's fp32 chain
+# (< 1e-6 in distance = 2.5e-7 in s) and (c) the roundings of the per-row / per-column thresholds (< 3e-7).
+RANK_BAND_EPS = 4e-6
+RANK_BAND_MIN_CAP = 1 << 20
+RANK_BAND_PER_ROW = 16         # initial list capacity per evaluated row + column
+
+
 def eval_rank(X, Y, xn, yn, nv1, nv2, g_row, g_col, row_gid0: int, col_gid0: int, n1: int, n2: int, use_csls: bool,
-              cnt_row: torch.Tensor, cnt_col: torch.Tensor, want_top3: bool = False):
+              cnt_row: torch.Tensor, cnt_col: torch.Tensor, want_top3: bool = False, exact_chain: bool = False):
+    """Rank counters of sweep 2, accumulated into cnt_row / cnt_col. Default: s-space sweep with a deferral band
+    (snag_eval_rank_band) followed by the canonical re-score of the deferred elements (snag_band_rescore); a band list
+    that overflows is retried with a larger list, and degenerate inputs (almost everything tied) fall back to the
+    in-kernel fp32 chain (snag_eval_rank, `exact_chain=True`). Returns the per-list nearest-candidate lists
+    ([n_lists, n1, 4] values, ids) when want_top3, else (None, None)."""
     _check_operand(X, "X")
     _check_operand(Y, "Y")
     _need(cnt_row, torch.int32, "cnt_row", 1)
@@ -230,11 +244,66 @@ def eval_rank(X, Y, xn, yn, nv1, nv2, g_row, g_col, row_gid0: int, col_gid0: int
         _, nch = sim_plan(n1, n2, X.shape[1])
         t3v = torch.empty((nch, n1, 4), dtype=torch.float32, device=X.device)
         t3i = torch.empty((nch, n1, 4), dtype=torch.int32, device=X.device)
+    st = current_stream()
+    if not exact_chain:
+        cap = max(RANK_BAND_MIN_CAP, RANK_BAND_PER_ROW * (n1 + n2))
+        row_save = col_save = None
+        while cap <= (1 << 28):
+            band = torch.empty((cap,), dtype=torch.int64, device=X.device)
+            band_cnt = torch.zeros((1,), dtype=torch.int32, device=X.device)
+            if row_save is None:
+                row_save, col_save = cnt_row.clone(), cnt_col.clone()
+            with _SweepTimer("sim_kernel<EpiRank>", n1, n2):
+                call("snag_eval_rank_band", ptr(X), ptr(Y), ptr(xn), ptr(yn), ptr(nv1), ptr(nv2), ptr(g_row), ptr(g_col),
+                     row_gid0, col_gid0, n1, n2, X.shape[1], int(use_csls), RANK_BAND_EPS, ptr(cnt_row), ptr(cnt_col),
+                     ptr(t3v), ptr(t3i), ptr(band), ptr(band_cnt), cap, st)
+            call("snag_band_rescore", ptr(X), ptr(Y), X.shape[1], ptr(xn), ptr(yn), ptr(nv1), ptr(nv2), ptr(g_row),
+                 ptr(g_col), row_gid0, col_gid0, int(use_csls), ptr(band), ptr(band_cnt), cap, ptr(cnt_row), ptr(cnt_col), st)
+            deferred = int(band_cnt.item()) & 0xFFFFFFFF
+            LAST_RANK_INFO.update(deferred=deferred, cap=cap, mode="band")
+            if deferred <= cap:
+                return t3v, t3i
+            cnt_row.copy_(row_save)          # the list overflowed: undo the partial counts and retry
+            cnt_col.copy_(col_save)
+            cap = max(cap * 8, round_up(deferred + deferred // 8, 1024))
+        # hopeless (nearly everything within the band: duplicated / constant embeddings): in-kernel chain with exact ties
+    LAST_RANK_INFO.update(mode="chain")
     with _SweepTimer("sim_kernel<EpiRank>", n1, n2):
         call("snag_eval_rank", ptr(X), ptr(Y), ptr(xn), ptr(yn), ptr(nv1), ptr(nv2), ptr(g_row), ptr(g_col), row_gid0,
-             col_gid0, n1, n2, X.shape[1], int(use_csls), ptr(cnt_row), ptr(cnt_col), ptr(t3v), ptr(t3i),
-             current_stream())
+             col_gid0, n1, n2, X.shape[1], int(use_csls), ptr(cnt_row), ptr(cnt_col), ptr(t3v), ptr(t3i), st)
+    if want_top3:                          # the chain kernel lists distances ascending; the merge expects x descending
+        t3v = -t3v
+        t3v[..., 3] = float("-inf")
+        t3i[..., 3] = 0x7FFFFFFF
     return t3v, t3i
+
+
+LAST_RANK_INFO: dict = {}
+
+
+def top4_merge(val: torch.Tensor, idx: torch.Tensor):
+    """Merge per-list nearest-candidate lists [n_lists, n_rows, 4] (value descending, id ascending on ties) -> [n_rows, 4]."""
+    _need(val, torch.float32, "val", 3)
+    _need(idx, torch.int32, "idx", 3)
+    n_lists, n_rows = val.shape[0], val.shape[1]
+    oval = torch.empty((n_rows, 4), dtype=torch.float32, device=val.device)
+    oidx = torch.empty((n_rows, 4), dtype=torch.int32, device=val.device)
+    call("snag_top4_merge", ptr(val), ptr(idx), n_lists, n_rows, ptr(oval), ptr(oidx), current_stream())
+    return oval, oidx
+
+
+def top3_rescore(X, Y, xn, yn, nv1, nv2, use_csls: bool, cand: torch.Tensor):
+    """Canonical distances of each row's candidate columns [n_rows, 4] (ids into Y), sorted ascending with the lower id
+    first on ties: columns 0..2 are ret1..ret3 of the prediction file. Returns (val [n_rows, 4], idx [n_rows, 4])."""
+    _check_operand(X, "X")
+    _check_operand(Y, "Y")
+    _need(cand, torch.int32, "cand", 2)
+    n_rows = cand.shape[0]
+    oval = torch.empty((n_rows, 4), dtype=torch.float32, device=cand.device)
+    oidx = torch.empty((n_rows, 4), dtype=torch.int32, device=cand.device)
+    call("snag_top3_rescore", ptr(X), ptr(Y), X.shape[1], n_rows, ptr(xn), ptr(yn), ptr(nv1), ptr(nv2), int(use_csls),
+         ptr(cand), ptr(oval), ptr(oidx), current_stream())
+    return oval, oidx
 
 
 def top3_merge(val: torch.Tensor, idx: torch.Tensor):

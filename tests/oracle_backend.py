@@ -80,24 +80,33 @@ def eval_rank(X, Y, xn, yn, nv1, nv2, g_row, g_col, row_gid0, col_gid0, n1, n2, 
     cnt_col[:n2] += torch.from_numpy(pcol.sum(0).astype(np.int32))
     if not want_top3:
         return None, None
-    order = np.lexsort((np.broadcast_to(cj, dist.shape), dist), axis=1)[:, :3]
-    v = np.full((1, n1, 4), np.inf, np.float32)
+    # nearest-candidate lists as the CUDA sweep emits them: 4 per row, score descending (= distance ascending)
+    order = np.lexsort((np.broadcast_to(cj, dist.shape), dist), axis=1)[:, :4]
+    v = np.full((1, n1, 4), -np.inf, np.float32)
     i = np.full((1, n1, 4), 0x7FFFFFFF, np.int32)
     m = order.shape[1]
-    v[0, :, :m] = np.take_along_axis(dist, order, 1)
+    v[0, :, :m] = -np.take_along_axis(dist, order, 1)
     i[0, :, :m] = order + col_gid0
     return torch.from_numpy(v), torch.from_numpy(i)
 
 
-def top3_merge(val, idx):
-    v = np.concatenate(list(val.numpy()[:, :, :3]), axis=1)
-    i = np.concatenate(list(idx.numpy()[:, :, :3]), axis=1)
-    order = np.lexsort((i, v), axis=1)[:, :3]
-    ov = np.zeros((v.shape[0], 4), np.float32)
-    oi = np.zeros((v.shape[0], 4), np.int32)
-    ov[:, :3] = np.take_along_axis(v, order, 1)
-    oi[:, :3] = np.take_along_axis(i, order, 1)
-    return torch.from_numpy(ov), torch.from_numpy(oi)
+def top4_merge(val, idx):
+    v = np.concatenate(list(val.numpy()), axis=1)
+    i = np.concatenate(list(idx.numpy()), axis=1)
+    order = np.lexsort((i, -v), axis=1)[:, :4]
+    return (torch.from_numpy(np.take_along_axis(v, order, 1).astype(np.float32)),
+            torch.from_numpy(np.take_along_axis(i, order, 1).astype(np.int32)))
+
+
+def top3_rescore(X, Y, xn, yn, nv1, nv2, use_csls, cand):
+    n1, n2 = cand.shape[0], _np(yn).shape[0]
+    dist = _dist(X, Y, xn, yn, nv1, nv2, n1, n2, use_csls)
+    ci = cand.numpy().astype(np.int64)
+    ok = ci != 0x7FFFFFFF
+    v = np.where(ok, np.take_along_axis(dist, np.where(ok, ci, 0), 1), np.inf).astype(np.float32)
+    order = np.lexsort((ci, v), axis=1)
+    return (torch.from_numpy(np.take_along_axis(v, order, 1)),
+            torch.from_numpy(np.take_along_axis(ci, order, 1).astype(np.int32)))
 
 
 # ------------------------------------------------------------------------------------------------ ICL loss

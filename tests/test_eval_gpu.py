@@ -88,6 +88,58 @@ def test_against_oracle(cuda_device, n, d, k, csls, sigma):
     np.testing.assert_array_equal(res.top3_idx.cpu().numpy()[clear3], ref["top3"][clear3])
 
 
+@pytest.mark.parametrize("n,d", [(1500, 1200), (1100, 1800), (2100, 300)])
+def test_tensor_core_dot_error(cuda_device, n, d):
+    """The deferral band of the rank sweep (ops.RANK_BAND_EPS) must cover the distance between the tensor core's dot
+    product and the canonical one (fp64, index order, rounded once) for unit rows: pin it with a 4x safety factor on a few million samples."""
+    x, y = _clustered(n, d, 4.0, 11)
+    X, Y, xn, yn = _prep(x, y, cuda_device)
+    S = ops.sim_write(X, Y, None, None, n, n, 0).cpu().numpy()
+    ref = oracle.dot_matrix(x, y)
+    assert np.abs(S - ref).max() < ops.RANK_BAND_EPS / 4
+
+
+@pytest.mark.parametrize("n,d,k,csls,sigma", [(2048, 1200, 10, True, 8.0), (1000, 300, 10, False, 3.0),
+                                              (1531, 96, 16, True, 2.0)])
+def test_rank_sweep_is_canonical(cuda_device, n, d, k, csls, sigma):
+    """Given the neighbourhood means, the rank sweep + band re-score must reproduce the oracle's ranks on EVERY pair,
+    near-ties included: elements inside the band are judged with the canonical arithmetic, the others cannot flip."""
+    x, y = _clustered(n, d, sigma, 3408)
+    X, Y, xn, yn = _prep(x, y, cuda_device)
+    ref = oracle.align_eval(x, y, csls, k)
+    nv1 = torch.from_numpy(ref["nv1"]).to(cuda_device) if csls else None
+    nv2 = torch.from_numpy(ref["nv2"]).to(cuda_device) if csls else None
+    g = ops.pair_score(X, Y, n, xn, yn, nv1, nv2, csls)
+    np.testing.assert_array_equal(g.cpu().numpy(), ref["g"])
+    for exact_chain in (False, True):
+        cnt_row = torch.zeros((n,), dtype=torch.int32, device=cuda_device)
+        cnt_col = torch.zeros((n,), dtype=torch.int32, device=cuda_device)
+        ops.eval_rank(X, Y, xn, yn, nv1, nv2, g, g, 0, 0, n, n, csls, cnt_row, cnt_col, exact_chain=exact_chain)
+        if not exact_chain:
+            assert ops.LAST_RANK_INFO["mode"] == "band"
+            np.testing.assert_array_equal(cnt_row.cpu().numpy(), ref["rank_l2r"])
+            np.testing.assert_array_equal(cnt_col.cpu().numpy(), ref["rank_r2l"])
+        else:                                  # the in-kernel chain may move a near-tie by one place
+            assert np.abs(cnt_row.cpu().numpy() - ref["rank_l2r"]).max() <= 2
+
+
+def test_rank_band_overflow_retries(cuda_device, monkeypatch):
+    """All-equal embeddings put every element inside the band (every distance equals every ground-truth distance): a
+    deferral list that is too small is detected, the partial counts are undone and the sweep is re-run with a larger
+    list; the result is the stable-sort order (lower ids first)."""
+    n, d = 700, 64
+    x, _ = _clustered(n, d, 1.0, 5)
+    xc = np.tile(x[:1], (n, 1))
+    Xc, Yc, xnc, ync = _prep(xc, xc, cuda_device)
+    monkeypatch.setattr(ops, "RANK_BAND_MIN_CAP", 16)
+    monkeypatch.setattr(ops, "RANK_BAND_PER_ROW", 0)
+    for csls in (False, True):
+        res = evaluate.align_ranks(Xc, Yc, xnc, ync, n, 3, csls)
+        np.testing.assert_array_equal(res.rank_l2r.cpu().numpy(), np.arange(n))
+        np.testing.assert_array_equal(res.rank_r2l.cpu().numpy(), np.arange(n))
+        assert ops.LAST_RANK_INFO["deferred"] == n * (n - 1) and ops.LAST_RANK_INFO["cap"] >= n * (n - 1)
+
+
 @pytest.mark.parametrize("n,d,k", [(1, 64, 1), (2, 8, 2), (127, 40, 5), (129, 64, 10), (257, 300, 16), (513, 64, 3)])
 def test_ragged_shapes(cuda_device, n, d, k):
     x, y = _clustered(n, d, 1.0, n)
