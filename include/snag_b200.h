@@ -100,9 +100,11 @@ int snag_sim_readout_only(const uint16_t* X, const uint16_t* Y, int32_t n1, int3
                           int32_t n_lds, int32_t n_alu, int32_t n_sts, void* stream);
 /* CSLS sweep 1 (src/utils.py:431-432 without the matrix): for every row of X the SNAG_KT largest
  * c_ij = 1 - d_ij over the columns of each chunk. part: fp32 [n_lists][n1][SNAG_KT] (n_lists from
- * snag_sim_plan(n1, n2, Dpad)). Call with X and Y swapped for the column neighbourhoods. */
+ * snag_sim_plan(n1, n2, Dpad)); part_idx (may be NULL): int32, same shape, the column j of every entry (-1 for the
+ * -inf padding) — needed to re-score the neighbourhood canonically (snag_topk_rescore). Call with X and Y swapped
+ * for the column neighbourhoods. */
 int snag_eval_rowtopk(const uint16_t* X, const uint16_t* Y, const float* xn, const float* yn, int32_t n1, int32_t n2,
-                      int32_t Dpad, float* part, void* stream);
+                      int32_t Dpad, float* part, int32_t* part_idx, void* stream);
 /* Two-sweep variant: CSLS neighbourhoods of BOTH directions from ONE pass over S (replaces the second
  * snag_eval_rowtopk call with swapped operands). Rows: as snag_eval_rowtopk (part). Columns: every element with
  * c_ij >= colthr[j] is appended, as a (j, c) pair, to the private stream of the CTA that computed it
@@ -112,21 +114,37 @@ int snag_eval_rowtopk(const uint16_t* X, const uint16_t* Y, const float* xn, con
  * sample is a lower bound of the final k-th largest, so no neighbour is ever missed; a sample of m rows leaves
  * ~k*n1/m candidates per column. Then: snag_col_cand_hist (hist[j] = candidates of column j; sets *overflow if a
  * stream was full), offs = exclusive prefix sum of hist (caller), snag_col_cand_scatter (vals[offs[j] + ...]),
- * snag_col_cand_finalize (nv[j] = mean of the k largest; sets *overflow if a column has fewer than k). On overflow
- * fall back to the swapped snag_eval_rowtopk sweep. hist / cursor / overflow are zeroed by the caller. */
+ * snag_col_cand_finalize (nv[j] = mean of the k largest and/or cand_val/cand_idx [n][SNAG_KT] = the column's SNAG_KT
+ * best candidates with their rows; sets *overflow if a column has fewer than k). On overflow fall back to the swapped
+ * snag_eval_rowtopk sweep. hist / cursor / overflow are zeroed by the caller. part_idx / stream_row carry the column
+ * of every row candidate and the row of every stream entry (int32, same shapes as part / stream). */
 int snag_eval_rowcoltopk(const uint16_t* X, const uint16_t* Y, const float* xn, const float* yn, int32_t n1, int32_t n2,
-                         int32_t Dpad, float* part, const float* colthr, const float* colb, uint64_t* stream,
-                         int32_t* stream_cnt, int32_t cta_cap, void* stream_);
+                         int32_t Dpad, float* part, int32_t* part_idx, const float* colthr, const float* colb,
+                         uint64_t* stream, int32_t* stream_row, int32_t* stream_cnt, int32_t cta_cap, void* stream_);
 int snag_col_threshold(const float* cand, int64_t n, int32_t k, const float* yn, float* colthr, float* colb, void* stream);
 int snag_col_cand_hist(const uint64_t* stream, const int32_t* stream_cnt, int32_t n_ctas, int32_t cta_cap, int32_t* hist,
                        int32_t* overflow, void* stream_);
-int snag_col_cand_scatter(const uint64_t* stream, const int32_t* stream_cnt, int32_t n_ctas, int32_t cta_cap,
-                          const int64_t* offs, int32_t* cursor, float* vals, void* stream_);
-int snag_col_cand_finalize(const int64_t* offs, const int32_t* hist, const float* vals, int64_t n, int32_t k, float* nv,
-                           int32_t* overflow, void* stream);
+int snag_col_cand_scatter(const uint64_t* stream, const int32_t* stream_row, const int32_t* stream_cnt, int32_t n_ctas,
+                          int32_t cta_cap, const int64_t* offs, int32_t* cursor, float* vals, int32_t* rows, void* stream_);
+int snag_col_cand_finalize(const int64_t* offs, const int32_t* hist, const float* vals, const int32_t* rows, int64_t n,
+                           int32_t k, float* nv, float* cand_val, int32_t* cand_idx, int32_t* overflow, void* stream);
 /* merge n_lists candidate lists per row ([n_lists][n_rows][SNAG_KT]); nv[row] = mean of the k largest
- * (may be NULL); cand_out [n_rows][SNAG_KT] = merged list (may be NULL) for the cross-GPU exchange. */
-int snag_topk_merge_mean(const float* part, int32_t n_lists, int64_t n_rows, int32_t k, float* nv, float* cand_out,
+ * (may be NULL); cand_out [n_rows][SNAG_KT] = merged list (may be NULL) for the cross-GPU exchange; with part_idx and
+ * cand_idx_out the ids travel with the values. */
+int snag_topk_merge_mean(const float* part, const int32_t* part_idx, int32_t n_lists, int64_t n_rows, int32_t k, float* nv,
+                         float* cand_out, int32_t* cand_idx_out, void* stream);
+/* Canonical neighbourhood means (the oracle's nv bit for bit): re-score the SNAG_KT candidates of every row of A
+ * (cand_idx: rows of B, -1 = empty; cand_val: their tensor-core scores) with the fp64 index-order dot product and the
+ * fp32 chain c = 1 - clamp((an + bn) - 2 s, 0); nv[row] = fp32 sum of the k largest taken largest-first, divided by
+ * k. A row is verified when its k-th canonical score is >= (smallest tensor-core score of its full list) + delta, i.e.
+ * no row of B outside the list can belong to the true neighbourhood; the others are appended to flagged[]
+ * (*flagged_cnt counts them, zero it first) and must be completed by snag_topk_exhaustive, which scans all n_b rows
+ * of B for each flagged row. */
+int snag_topk_rescore(const uint16_t* A, const uint16_t* B, int32_t Dpad, int64_t n_rows, const float* an, const float* bn,
+                      const int32_t* cand_idx, const float* cand_val, int32_t k, float delta, float* nv, int32_t* flagged,
+                      int32_t* flagged_cnt, int32_t flagged_cap, void* stream);
+int snag_topk_exhaustive(const uint16_t* A, const uint16_t* B, int32_t Dpad, int64_t n_b, const float* an, const float* bn,
+                         const int32_t* flagged, const int32_t* flagged_cnt, int32_t flagged_cap, int32_t k, float* nv,
                          void* stream);
 /* ground-truth scores g[p] = distance of pair (x_p, y_p): CSLS distance 1 - ((2(1-d) - nv1_p) - nv2_p) if
  * use_csls else d; dot product accumulated in fp64 in index order. s_out (may be NULL) gets x_p.y_p. */

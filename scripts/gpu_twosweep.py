@@ -41,9 +41,10 @@ for (n, d, k) in [(70000, 300, 10), (70000, 1800, 10), (100000, 1200, 10), (1000
     part_s = ops.eval_rowtopk(Y, X.index_select(0, sel), yn, xn.index_select(0, sel), n, m)
     _, cand_s = ops.topk_merge_mean(part_s, k, want_nv=False, want_cand=True)
     colthr, colb = ops.col_threshold(cand_s, k, yn)
-    part, stream, scnt = ops.eval_rowcoltopk(X, Y, xn, yn, n, n, colthr, colb, cap)
-    nvx, ovf, cnt = ops.col_cand_reduce(stream, scnt, n, k)
-    ms_reduce = t(lambda: ops.col_cand_reduce(stream, scnt, n, k))
+    part, pidx, stream, srow, scnt = ops.eval_rowcoltopk(X, Y, xn, yn, n, n, colthr, colb, cap)
+    cval, cidx, ovf = ops.col_cand_reduce(stream, srow, scnt, n, k)
+    cnt = torch.full((1,), float(scnt.sum().item()) / n)
+    ms_reduce = t(lambda: ops.col_cand_reduce(stream, srow, scnt, n, k))
     ms_pre = t(lambda: ops.eval_rowtopk(Y, X.index_select(0, sel), yn, xn.index_select(0, sel), n, m))
     ms_main = t(lambda: ops.eval_rowcoltopk(X, Y, xn, yn, n, n, colthr, colb, cap))
     ms_old = t(lambda: ops.eval_rowtopk(X, Y, xn, yn, n, n))
@@ -57,5 +58,5 @@ for (n, d, k) in [(70000, 300, 10), (70000, 1800, 10), (100000, 1200, 10), (1000
                           stream_max=int(scnt.max()), stream_min=int(scnt.min()), ms_reduce=ms_reduce,
                           ms_prepass=ms_pre, ms_fused_sweep=ms_main, ms_plain_rowtopk=ms_old, ms_eval3=ms3, ms_eval2=ms2,
                           speedup=ms3 / ms2)), flush=True)
-    del X, Y, part, stream
+    del X, Y, part, pidx, stream, srow
     torch.cuda.empty_cache()

@@ -30,7 +30,7 @@ def worker():
     part_s = ops.eval_rowtopk(Y, X.index_select(0, sel), yn, xn.index_select(0, sel), n, m)
     _, cand_s = ops.topk_merge_mean(part_s, k, want_nv=False, want_cand=True)
     colthr, colb = ops.col_threshold(cand_s, k, yn)
-    _, _, scnt = ops.eval_rowcoltopk(X, Y, xn, yn, n, n, colthr, colb, cap)
+    scnt = ops.eval_rowcoltopk(X, Y, xn, yn, n, n, colthr, colb, cap)[-1]
     out["cands_per_col"] = round(float(scnt.sum().item()) / n, 1)
     only = os.environ.get("SNAG_VARIANT_KERNELS", "mainloop,topk,rowcol,rank").split(",")
     for name, fn in (("mainloop", lambda: ops.sim_mainloop_only(X, Y, n, n)),

@@ -35,13 +35,15 @@ _SIGNATURES = {
     "snag_sim_mainloop_only": [_vp, _vp, _i32, _i32, _i32, _vp],
     "snag_debug_counters": [_vp],
     "snag_sim_readout_only": [_vp, _vp, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _vp],
-    "snag_eval_rowtopk": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp],
-    "snag_eval_rowcoltopk": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _vp],
+    "snag_eval_rowtopk": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp],
+    "snag_eval_rowcoltopk": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp],
     "snag_col_threshold": [_vp, _i64, _i32, _vp, _vp, _vp, _vp],
     "snag_col_cand_hist": [_vp, _vp, _i32, _i32, _vp, _vp, _vp],
-    "snag_col_cand_scatter": [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp],
-    "snag_col_cand_finalize": [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp],
-    "snag_topk_merge_mean": [_vp, _i32, _i64, _i32, _vp, _vp, _vp],
+    "snag_col_cand_scatter": [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp],
+    "snag_col_cand_finalize": [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp],
+    "snag_topk_merge_mean": [_vp, _vp, _i32, _i64, _i32, _vp, _vp, _vp, _vp],
+    "snag_topk_rescore": [_vp, _vp, _i32, _i64, _vp, _vp, _vp, _vp, _i32, _f32, _vp, _vp, _vp, _i32, _vp],
+    "snag_topk_exhaustive": [_vp, _vp, _i32, _i64, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp],
     "snag_pair_score": [_vp, _vp, _i32, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp],
     "snag_eval_rank": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp],
     "snag_top3_merge": [_vp, _vp, _i32, _i64, _vp, _vp, _vp],

@@ -82,12 +82,23 @@ int snag_sim_write(const uint16_t* X, const uint16_t* Y, const float* xn, const 
   return launch_sim_write(BF(X), BF(Y), xn, yn, n1, n2, Dpad, mode, out, ld, S(stream));
 }
 int snag_eval_rowtopk(const uint16_t* X, const uint16_t* Y, const float* xn, const float* yn, int32_t n1, int32_t n2,
-                      int32_t Dpad, float* part, void* stream) {
-  return launch_eval_rowtopk(BF(X), BF(Y), xn, yn, n1, n2, Dpad, part, S(stream));
+                      int32_t Dpad, float* part, int32_t* part_idx, void* stream) {
+  return launch_eval_rowtopk(BF(X), BF(Y), xn, yn, n1, n2, Dpad, part, part_idx, S(stream));
 }
-int snag_topk_merge_mean(const float* part, int32_t n_lists, int64_t n_rows, int32_t k, float* nv, float* cand_out,
+int snag_topk_merge_mean(const float* part, const int32_t* part_idx, int32_t n_lists, int64_t n_rows, int32_t k, float* nv,
+                         float* cand_out, int32_t* cand_idx_out, void* stream) {
+  return launch_topk_merge_mean(part, part_idx, n_lists, n_rows, k, nv, cand_out, cand_idx_out, S(stream));
+}
+int snag_topk_rescore(const uint16_t* A, const uint16_t* B, int32_t Dpad, int64_t n_rows, const float* an, const float* bn,
+                      const int32_t* cand_idx, const float* cand_val, int32_t k, float delta, float* nv, int32_t* flagged,
+                      int32_t* flagged_cnt, int32_t flagged_cap, void* stream) {
+  return launch_topk_rescore(BF(A), BF(B), Dpad, n_rows, an, bn, cand_idx, cand_val, k, delta, nv, flagged, flagged_cnt,
+                             flagged_cap, S(stream));
+}
+int snag_topk_exhaustive(const uint16_t* A, const uint16_t* B, int32_t Dpad, int64_t n_b, const float* an, const float* bn,
+                         const int32_t* flagged, const int32_t* flagged_cnt, int32_t flagged_cap, int32_t k, float* nv,
                          void* stream) {
-  return launch_topk_merge_mean(part, n_lists, n_rows, k, nv, cand_out, S(stream));
+  return launch_topk_exhaustive(BF(A), BF(B), Dpad, n_b, an, bn, flagged, flagged_cnt, flagged_cap, k, nv, S(stream));
 }
 int snag_pair_score(const uint16_t* X, const uint16_t* Y, int32_t Dpad, int64_t n, const float* xn, const float* yn,
                     const float* nv1, const float* nv2, int32_t use_csls, float* g, float* s_out, void* stream) {
@@ -147,10 +158,10 @@ int snag_icl_finalize(const float* rowsum_part, int32_t n_lists, int32_t B, int3
 }
 
 int snag_eval_rowcoltopk(const uint16_t* X, const uint16_t* Y, const float* xn, const float* yn, int32_t n1, int32_t n2,
-                         int32_t Dpad, float* part, const float* colthr, const float* colb, uint64_t* stream,
-                         int32_t* stream_cnt, int32_t cta_cap, void* stream_) {
-  return launch_eval_rowcoltopk(BF(X), BF(Y), xn, yn, n1, n2, Dpad, part, colthr, colb, reinterpret_cast<uint2*>(stream),
-                                stream_cnt, cta_cap, S(stream_));
+                         int32_t Dpad, float* part, int32_t* part_idx, const float* colthr, const float* colb,
+                         uint64_t* stream, int32_t* stream_row, int32_t* stream_cnt, int32_t cta_cap, void* stream_) {
+  return launch_eval_rowcoltopk(BF(X), BF(Y), xn, yn, n1, n2, Dpad, part, part_idx, colthr, colb,
+                                reinterpret_cast<uint2*>(stream), stream_row, stream_cnt, cta_cap, S(stream_));
 }
 int snag_col_threshold(const float* cand, int64_t n, int32_t k, const float* yn, float* colthr, float* colb, void* stream) {
   return launch_col_threshold(cand, n, k, yn, colthr, colb, S(stream));
@@ -159,14 +170,15 @@ int snag_col_cand_hist(const uint64_t* stream, const int32_t* stream_cnt, int32_
                        int32_t* overflow, void* stream_) {
   return launch_cand_hist(reinterpret_cast<const uint2*>(stream), stream_cnt, n_ctas, cta_cap, hist, overflow, S(stream_));
 }
-int snag_col_cand_scatter(const uint64_t* stream, const int32_t* stream_cnt, int32_t n_ctas, int32_t cta_cap,
-                          const int64_t* offs, int32_t* cursor, float* vals, void* stream_) {
-  return launch_cand_scatter(reinterpret_cast<const uint2*>(stream), stream_cnt, n_ctas, cta_cap,
-                             reinterpret_cast<const long long*>(offs), cursor, vals, S(stream_));
+int snag_col_cand_scatter(const uint64_t* stream, const int32_t* stream_row, const int32_t* stream_cnt, int32_t n_ctas,
+                          int32_t cta_cap, const int64_t* offs, int32_t* cursor, float* vals, int32_t* rows, void* stream_) {
+  return launch_cand_scatter(reinterpret_cast<const uint2*>(stream), stream_row, stream_cnt, n_ctas, cta_cap,
+                             reinterpret_cast<const long long*>(offs), cursor, vals, rows, S(stream_));
 }
-int snag_col_cand_finalize(const int64_t* offs, const int32_t* hist, const float* vals, int64_t n, int32_t k, float* nv,
-                           int32_t* overflow, void* stream) {
-  return launch_col_cand_finalize(reinterpret_cast<const long long*>(offs), hist, vals, n, k, nv, overflow, S(stream));
+int snag_col_cand_finalize(const int64_t* offs, const int32_t* hist, const float* vals, const int32_t* rows, int64_t n,
+                           int32_t k, float* nv, float* cand_val, int32_t* cand_idx, int32_t* overflow, void* stream) {
+  return launch_col_cand_finalize(reinterpret_cast<const long long*>(offs), hist, vals, rows, n, k, nv, cand_val, cand_idx,
+                                  overflow, S(stream));
 }
 
 int snag_mutual_nn(const uint16_t* X, const uint16_t* Y, const float* xn, const float* yn, int32_t n1, int32_t n2,

@@ -278,32 +278,82 @@ __global__ void __launch_bounds__(256) prep_bf16_kernel(const float* __restrict_
 // nv[row] = (sum of the k largest, accumulated largest-first in fp32) / k     (src/utils.py:431-432)
 // Optionally also emits the merged KT-list (descending) for the cross-GPU candidate exchange.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) topk_merge_mean_kernel(const float* __restrict__ part, int n_lists, long long n_rows,
-                                                              int k, float* __restrict__ nv, float* __restrict__ cand_out) {
+// canonical dot product of two bf16 rows: fp64 accumulation in index order, rounded once to fp32 (the oracle's s_ij)
+__device__ __forceinline__ float canonical_dot(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ y, int Dpad) {
+  const uint4* xr = reinterpret_cast<const uint4*>(x);
+  const uint4* yr = reinterpret_cast<const uint4*>(y);
+  double acc = 0.0;
+  for (int c = 0; c < Dpad / 8; ++c) {
+    const uint4 a = __ldg(xr + c), b = __ldg(yr + c);
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float a0 = __uint_as_float(aw[e] << 16), a1 = __uint_as_float(aw[e] & 0xffff0000u);
+      const float b0 = __uint_as_float(bw[e] << 16), b1 = __uint_as_float(bw[e] & 0xffff0000u);
+      acc = fma(static_cast<double>(a0), static_cast<double>(b0), acc);
+      acc = fma(static_cast<double>(a1), static_cast<double>(b1), acc);
+    }
+  }
+  return static_cast<float>(acc);
+}
+// the reference's fp32 chain from s to the (CSLS) distance, one rounding per op (simgemm.cuh has the same two helpers)
+__device__ __forceinline__ float canonical_dist(float s, float xn, float yn, float nv1, float nv2, int use_csls) {
+  const float d = fmaxf(__fmaf_rn(-2.0f, s, __fadd_rn(xn, yn)), 0.0f);
+  if (!use_csls) return d;
+  const float c = __fsub_rn(1.0f, d);
+  return __fsub_rn(1.0f, __fsub_rn(__fmaf_rn(2.0f, c, -nv1), nv2));
+}
+
+template <bool kIdx>
+__device__ __forceinline__ void topk_pair_insert(float (&top)[KT_LIST], int (&topi)[kIdx ? KT_LIST : 1], float v, int id) {
+  // ascending list, top[0] = admission threshold; ties: the entry met first stays (callers feed ids in ascending order
+  // within a list, lists in ascending column order)
+  if (!(v > top[0])) return;
+  top[0] = v;
+  if (kIdx) topi[0] = id;
+#pragma unroll
+  for (int t = 0; t < KT_LIST - 1; ++t) {
+    const bool sw = top[t] > top[t + 1];
+    const float a = top[t], b = top[t + 1];
+    top[t] = sw ? b : a;
+    top[t + 1] = sw ? a : b;
+    if (kIdx) {
+      const int ia = topi[t], ib = topi[t + 1];
+      topi[t] = sw ? ib : ia;
+      topi[t + 1] = sw ? ia : ib;
+    }
+  }
+}
+
+template <bool kIdx>
+__global__ void __launch_bounds__(128) topk_merge_mean_kernel(const float* __restrict__ part, const int* __restrict__ part_idx,
+                                                              int n_lists, long long n_rows, int k, float* __restrict__ nv,
+                                                              float* __restrict__ cand_out, int* __restrict__ cand_idx_out) {
   const long long row = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (row >= n_rows) return;
   float top[KT_LIST];
+  int topi[kIdx ? KT_LIST : 1];
 #pragma unroll
   for (int t = 0; t < KT_LIST; ++t) top[t] = -INFINITY;
+  if (kIdx) {
+#pragma unroll
+    for (int t = 0; t < KT_LIST; ++t) topi[t] = -1;
+  }
   for (int l = 0; l < n_lists; ++l) {
-    const float4* src = reinterpret_cast<const float4*>(part + (static_cast<long long>(l) * n_rows + row) * KT_LIST);
+    const long long o0 = (static_cast<long long>(l) * n_rows + row) * KT_LIST;
+    const float4* src = reinterpret_cast<const float4*>(part + o0);
+    const int4* srci = reinterpret_cast<const int4*>(part_idx + (kIdx ? o0 : 0));
 #pragma unroll
     for (int q = 0; q < KT_LIST / 4; ++q) {
       const float4 v4 = __ldg(src + q);
       const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float v = vv[e];
-        if (v > top[0]) {
-          top[0] = v;
-#pragma unroll
-          for (int t = 0; t < KT_LIST - 1; ++t) {
-            const float lo = fminf(top[t], top[t + 1]), hi = fmaxf(top[t], top[t + 1]);
-            top[t] = lo;
-            top[t + 1] = hi;
-          }
-        }
+      int ii[4] = {0, 0, 0, 0};
+      if (kIdx) {
+        const int4 i4 = __ldg(srci + q);
+        ii[0] = i4.x; ii[1] = i4.y; ii[2] = i4.z; ii[3] = i4.w;
       }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) topk_pair_insert<kIdx>(top, topi, vv[e], ii[e]);
     }
   }
   if (nv) {
@@ -317,6 +367,107 @@ __global__ void __launch_bounds__(128) topk_merge_mean_kernel(const float* __res
     float4* o = reinterpret_cast<float4*>(cand_out + row * KT_LIST);
 #pragma unroll
     for (int q = 0; q < KT_LIST / 4; ++q) o[q] = make_float4(top[4 * q], top[4 * q + 1], top[4 * q + 2], top[4 * q + 3]);
+  }
+  if (kIdx && cand_idx_out) {
+    int4* o = reinterpret_cast<int4*>(cand_idx_out + row * KT_LIST);
+#pragma unroll
+    for (int q = 0; q < KT_LIST / 4; ++q) o[q] = make_int4(topi[4 * q], topi[4 * q + 1], topi[4 * q + 2], topi[4 * q + 3]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Canonical CSLS neighbourhood means. cand_idx[row][KT] are the rows of B that the tensor-core sweep ranked highest
+// for row `row` of A (cand_val their tensor-core scores c = 1 - d, ascending, -inf / -1 padded). Every candidate is
+// re-scored with the canonical arithmetic (fp64 index-order dot, fp32 chain); nv = mean of the k largest, summed
+// largest-first in fp32 (src/utils.py:431-432). The result equals the oracle's whenever no column outside the list
+// can belong to the true top-k: every outsider's tensor-core score is <= the list's smallest, so its canonical score
+// is <= that + delta; the row is verified if its k-th canonical score clears that bound (or the list is not full).
+// Unverified rows (plateaus of near-equal scores wider than KT - k) are appended to `flagged` for the exhaustive
+// pass below. One warp handles two rows: 16 lanes per row, one candidate per lane.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) topk_rescore_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restrict__ B,
+                                                           int Dpad, long long n_rows, const float* __restrict__ an,
+                                                           const float* __restrict__ bn, const int* __restrict__ cand_idx,
+                                                           const float* __restrict__ cand_val, int k, float delta,
+                                                           float* __restrict__ nv, int* __restrict__ flagged,
+                                                           int* __restrict__ flagged_cnt, int flagged_cap) {
+  const long long gt = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long row = gt >> 4;
+  const int sub = threadIdx.x & 15;
+  const bool live = row < n_rows;
+  const long long r = live ? row : n_rows - 1;
+  const int id = cand_idx[r * KT_LIST + sub];
+  const float tc = cand_val[r * KT_LIST + sub];
+  float c = -INFINITY;
+  if (id >= 0) {
+    const float s = canonical_dot(A + r * Dpad, B + static_cast<long long>(id) * Dpad, Dpad);
+    const float d = fmaxf(__fmaf_rn(-2.0f, s, __fadd_rn(an[r], bn[id])), 0.0f);
+    c = __fsub_rn(1.0f, d);
+  }
+  // rank of this lane's value among the 16 (descending; ties by lane so that ranks are a permutation)
+  const unsigned gmask = 0xffffu << (threadIdx.x & 16);
+  int rank = 0;
+  float tc_min = tc;
+#pragma unroll
+  for (int o = 0; o < 16; ++o) {
+    const int src = (threadIdx.x & 16) | o;
+    const float oc = __shfl_sync(gmask, c, src);
+    const float otc = __shfl_sync(gmask, tc, src);
+    rank += (oc > c) || (oc == c && o < sub);
+    tc_min = fminf(tc_min, otc);
+  }
+  // largest-first fp32 sum of the k largest: lane with rank t contributes at step t
+  float sum = 0.f, ck = 0.f;
+#pragma unroll
+  for (int t = 0; t < KT_LIST; ++t) {
+    const unsigned who = __ballot_sync(gmask, rank == t) & gmask;
+    const float v = __shfl_sync(gmask, c, __ffs(who) - 1);
+    if (t < k) { sum = __fadd_rn(sum, v); ck = v; }
+  }
+  if (live && sub == 0) {
+    nv[row] = __fdiv_rn(sum, static_cast<float>(k));
+    const bool full = tc_min > -INFINITY;                 // all KT slots hold a real candidate
+    if (full && !(ck >= tc_min + delta)) {
+      const int slot = atomicAdd(flagged_cnt, 1);
+      if (slot < flagged_cap) flagged[slot] = static_cast<int>(row);
+    }
+  }
+}
+
+// Exhaustive canonical neighbourhood of the flagged rows: one block per flagged row, threads stride over all rows of
+// B keeping their own k largest canonical scores; lists are merged through shared memory.
+__global__ void __launch_bounds__(256) topk_exhaustive_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restrict__ B,
+                                                              int Dpad, long long n_b, const float* __restrict__ an,
+                                                              const float* __restrict__ bn, const int* __restrict__ flagged,
+                                                              const int* __restrict__ flagged_cnt, int flagged_cap, int k,
+                                                              float* __restrict__ nv) {
+  __shared__ float lists[256 * KT_LIST];
+  const int total = min(*flagged_cnt, flagged_cap);
+  for (int f = blockIdx.x; f < total; f += gridDim.x) {
+    const long long row = flagged[f];
+    const float a = an[row];
+    float top[KT_LIST];
+    int dummy[1];
+#pragma unroll
+    for (int t = 0; t < KT_LIST; ++t) top[t] = -INFINITY;
+    for (long long j = threadIdx.x; j < n_b; j += blockDim.x) {
+      const float s = canonical_dot(A + row * Dpad, B + j * Dpad, Dpad);
+      const float c = __fsub_rn(1.0f, fmaxf(__fmaf_rn(-2.0f, s, __fadd_rn(a, bn[j])), 0.0f));
+      topk_pair_insert<false>(top, dummy, c, 0);
+    }
+#pragma unroll
+    for (int t = 0; t < KT_LIST; ++t) lists[threadIdx.x * KT_LIST + t] = top[t];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int o = 1; o < static_cast<int>(blockDim.x); ++o)
+        for (int t = 0; t < KT_LIST; ++t) topk_pair_insert<false>(top, dummy, lists[o * KT_LIST + t], 0);
+      float s = 0.f;
+#pragma unroll
+      for (int t = 0; t < KT_LIST; ++t)
+        if (t < k) s = __fadd_rn(s, top[KT_LIST - 1 - t]);
+      nv[row] = __fdiv_rn(s, static_cast<float>(k));
+    }
+    __syncthreads();
   }
 }
 
@@ -355,32 +506,6 @@ __global__ void __launch_bounds__(128) pair_score_kernel(const __nv_bfloat16* __
   const float c = __fsub_rn(1.0f, d);
   const float u = __fmaf_rn(2.0f, c, -nv1[p]);
   g[p] = __fsub_rn(1.0f, __fsub_rn(u, nv2[p]));
-}
-
-// canonical dot product of two bf16 rows: fp64 accumulation in index order, rounded once to fp32 (the oracle's s_ij)
-__device__ __forceinline__ float canonical_dot(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ y, int Dpad) {
-  const uint4* xr = reinterpret_cast<const uint4*>(x);
-  const uint4* yr = reinterpret_cast<const uint4*>(y);
-  double acc = 0.0;
-  for (int c = 0; c < Dpad / 8; ++c) {
-    const uint4 a = __ldg(xr + c), b = __ldg(yr + c);
-    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float a0 = __uint_as_float(aw[e] << 16), a1 = __uint_as_float(aw[e] & 0xffff0000u);
-      const float b0 = __uint_as_float(bw[e] << 16), b1 = __uint_as_float(bw[e] & 0xffff0000u);
-      acc = fma(static_cast<double>(a0), static_cast<double>(b0), acc);
-      acc = fma(static_cast<double>(a1), static_cast<double>(b1), acc);
-    }
-  }
-  return static_cast<float>(acc);
-}
-// the reference's fp32 chain from s to the (CSLS) distance, one rounding per op (simgemm.cuh has the same two helpers)
-__device__ __forceinline__ float canonical_dist(float s, float xn, float yn, float nv1, float nv2, int use_csls) {
-  const float d = fmaxf(__fmaf_rn(-2.0f, s, __fadd_rn(xn, yn)), 0.0f);
-  if (!use_csls) return d;
-  const float c = __fsub_rn(1.0f, d);
-  return __fsub_rn(1.0f, __fsub_rn(__fmaf_rn(2.0f, c, -nv1), nv2));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -615,35 +740,66 @@ __global__ void __launch_bounds__(256) cand_hist_kernel(const uint2* __restrict_
   const uint2* sp = stream + static_cast<long long>(cta) * cta_cap;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < cnt; e += gridDim.x * blockDim.x) atomicAdd(hist + sp[e].x, 1);
 }
-__global__ void __launch_bounds__(256) cand_scatter_kernel(const uint2* __restrict__ stream, const int* __restrict__ stream_cnt,
-                                                           int cta_cap, const long long* __restrict__ offs,
-                                                           int* __restrict__ cursor, float* __restrict__ vals) {
+__global__ void __launch_bounds__(256) cand_scatter_kernel(const uint2* __restrict__ stream, const int* __restrict__ stream_row,
+                                                           const int* __restrict__ stream_cnt, int cta_cap,
+                                                           const long long* __restrict__ offs, int* __restrict__ cursor,
+                                                           float* __restrict__ vals, int* __restrict__ rows) {
   const int cta = blockIdx.y;
   const int cnt = min(stream_cnt[cta], cta_cap);
   const uint2* sp = stream + static_cast<long long>(cta) * cta_cap;
+  const int* rp = stream_row ? stream_row + static_cast<long long>(cta) * cta_cap : nullptr;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < cnt; e += gridDim.x * blockDim.x) {
     const uint2 ent = sp[e];
     const int slot = atomicAdd(cursor + ent.x, 1);
     vals[offs[ent.x] + slot] = __uint_as_float(ent.y);
+    if (rows) rows[offs[ent.x] + slot] = rp[e];
   }
 }
+// per column: the KT largest candidates of its segment (value ascending, source row alongside) and, optionally, the
+// tensor-core neighbourhood mean. Segment order is arbitrary (atomics), so equal values are ordered by row id to keep
+// the emitted list deterministic.
 __global__ void __launch_bounds__(128) col_cand_finalize_kernel(const long long* __restrict__ offs, const int* __restrict__ hist,
-                                                                const float* __restrict__ vals, long long n, int k,
-                                                                float* __restrict__ nv, int* __restrict__ overflow) {
+                                                                const float* __restrict__ vals, const int* __restrict__ rows,
+                                                                long long n, int k, float* __restrict__ nv,
+                                                                float* __restrict__ cand_val, int* __restrict__ cand_idx,
+                                                                int* __restrict__ overflow) {
   const long long j = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (j >= n) return;
   const int cnt = hist[j];
   if (cnt < k) atomicOr(overflow, 1);     // cannot happen with a valid threshold and no dropped entries
   float top[KT_LIST];
+  int topi[KT_LIST];
 #pragma unroll
-  for (int t = 0; t < KT_LIST; ++t) top[t] = -INFINITY;
+  for (int t = 0; t < KT_LIST; ++t) { top[t] = -INFINITY; topi[t] = -1; }
   const float* v = vals + offs[j];
-  for (int e = 0; e < cnt; ++e) topk_insert(top, v[e]);
-  float s = 0.f;
+  const int* r = rows ? rows + offs[j] : nullptr;
+  for (int e = 0; e < cnt; ++e) {
+    const float x = v[e];
+    const int id = r ? r[e] : 0;
+    // admit on (value, then lower row id): a strict total order, independent of the arrival order
+    if (x > top[0] || (r && x == top[0] && id < topi[0])) {
+      top[0] = x; topi[0] = id;
 #pragma unroll
-  for (int t = 0; t < KT_LIST; ++t)
-    if (t < k) s = __fadd_rn(s, top[KT_LIST - 1 - t]);
-  nv[j] = __fdiv_rn(s, static_cast<float>(k));
+      for (int t = 0; t < KT_LIST - 1; ++t) {
+        const bool sw = top[t] > top[t + 1] || (top[t] == top[t + 1] && topi[t] < topi[t + 1]);
+        const float a = top[t], b = top[t + 1];
+        const int ia = topi[t], ib = topi[t + 1];
+        top[t] = sw ? b : a; top[t + 1] = sw ? a : b;
+        topi[t] = sw ? ib : ia; topi[t + 1] = sw ? ia : ib;
+      }
+    }
+  }
+  if (nv) {
+    float s = 0.f;
+#pragma unroll
+    for (int t = 0; t < KT_LIST; ++t)
+      if (t < k) s = __fadd_rn(s, top[KT_LIST - 1 - t]);
+    nv[j] = __fdiv_rn(s, static_cast<float>(k));
+  }
+  if (cand_val) {
+#pragma unroll
+    for (int t = 0; t < KT_LIST; ++t) { cand_val[j * KT_LIST + t] = top[t]; cand_idx[j * KT_LIST + t] = topi[t]; }
+  }
 }
 
 // ================================================================================================
@@ -661,17 +817,41 @@ int launch_cand_hist(const uint2* stream, const int* stream_cnt, int n_ctas, int
   cand_hist_kernel<<<dim3(64, n_ctas), 256, 0, st>>>(stream, stream_cnt, cta_cap, hist, overflow);
   return static_cast<int>(cudaGetLastError());
 }
-int launch_cand_scatter(const uint2* stream, const int* stream_cnt, int n_ctas, int cta_cap, const long long* offs,
-                        int* cursor, float* vals, cudaStream_t st) {
+int launch_cand_scatter(const uint2* stream, const int* stream_row, const int* stream_cnt, int n_ctas, int cta_cap,
+                        const long long* offs, int* cursor, float* vals, int* rows, cudaStream_t st) {
   if (!stream || !stream_cnt || !offs || !cursor || !vals || n_ctas < 1 || cta_cap < 1) return SNAG_ERR_ARG;
-  cand_scatter_kernel<<<dim3(64, n_ctas), 256, 0, st>>>(stream, stream_cnt, cta_cap, offs, cursor, vals);
+  if ((rows != nullptr) != (stream_row != nullptr)) return SNAG_ERR_ARG;
+  cand_scatter_kernel<<<dim3(64, n_ctas), 256, 0, st>>>(stream, stream_row, stream_cnt, cta_cap, offs, cursor, vals, rows);
   return static_cast<int>(cudaGetLastError());
 }
-int launch_col_cand_finalize(const long long* offs, const int* hist, const float* vals, long long n, int k, float* nv,
-                             int* overflow, cudaStream_t st) {
-  if (!offs || !hist || !vals || !nv || !overflow || n <= 0) return SNAG_ERR_ARG;
+int launch_col_cand_finalize(const long long* offs, const int* hist, const float* vals, const int* rows, long long n, int k,
+                             float* nv, float* cand_val, int* cand_idx, int* overflow, cudaStream_t st) {
+  if (!offs || !hist || !vals || !overflow || n <= 0 || (!nv && !cand_val)) return SNAG_ERR_ARG;
+  if ((cand_val != nullptr) != (cand_idx != nullptr) || (cand_val && !rows)) return SNAG_ERR_ARG;
   if (k < 1 || k > KT_LIST) return SNAG_ERR_SHAPE;
-  col_cand_finalize_kernel<<<static_cast<int>((n + 127) / 128), 128, 0, st>>>(offs, hist, vals, n, k, nv, overflow);
+  col_cand_finalize_kernel<<<static_cast<int>((n + 127) / 128), 128, 0, st>>>(offs, hist, vals, rows, n, k, nv, cand_val,
+                                                                             cand_idx, overflow);
+  return static_cast<int>(cudaGetLastError());
+}
+int launch_topk_rescore(const __nv_bfloat16* A, const __nv_bfloat16* B, int Dpad, long long n_rows, const float* an,
+                        const float* bn, const int* cand_idx, const float* cand_val, int k, float delta, float* nv,
+                        int* flagged, int* flagged_cnt, int flagged_cap, cudaStream_t st) {
+  if (!A || !B || !an || !bn || !cand_idx || !cand_val || !nv || !flagged || !flagged_cnt || n_rows <= 0 || flagged_cap < 1)
+    return SNAG_ERR_ARG;
+  if (k < 1 || k > KT_LIST || (Dpad % 64)) return SNAG_ERR_SHAPE;
+  const long long threads = n_rows * 16;
+  topk_rescore_kernel<<<static_cast<unsigned>((threads + 127) / 128), 128, 0, st>>>(A, B, Dpad, n_rows, an, bn, cand_idx,
+                                                                                   cand_val, k, delta, nv, flagged,
+                                                                                   flagged_cnt, flagged_cap);
+  return static_cast<int>(cudaGetLastError());
+}
+int launch_topk_exhaustive(const __nv_bfloat16* A, const __nv_bfloat16* B, int Dpad, long long n_b, const float* an,
+                           const float* bn, const int* flagged, const int* flagged_cnt, int flagged_cap, int k, float* nv,
+                           cudaStream_t st) {
+  if (!A || !B || !an || !bn || !flagged || !flagged_cnt || !nv || n_b <= 0 || flagged_cap < 1) return SNAG_ERR_ARG;
+  if (k < 1 || k > KT_LIST || (Dpad % 64)) return SNAG_ERR_SHAPE;
+  const int grid = flagged_cap < num_sms() * 4 ? flagged_cap : num_sms() * 4;
+  topk_exhaustive_kernel<<<grid, 256, 0, st>>>(A, B, Dpad, n_b, an, bn, flagged, flagged_cnt, flagged_cap, k, nv);
   return static_cast<int>(cudaGetLastError());
 }
 static inline int grid_for(long long work_items, int block, int num_sms, int ctas_per_sm);
@@ -695,8 +875,8 @@ int launch_csls_sim(const float* sim, long long n1, long long n2, long long ld, 
   const int rows_per_slab = static_cast<int>((n1 + slabs - 1) / slabs);
   matrix_row_topk_kernel<<<static_cast<unsigned>((n1 * 32 + 255) / 256), 256, 0, st>>>(sim, n1, n2, ld, part_r);
   matrix_col_topk_kernel<<<dim3(static_cast<unsigned>((n2 + 127) / 128), slabs), 128, 0, st>>>(sim, n1, n2, ld, rows_per_slab, part_c);
-  topk_merge_mean_kernel<<<static_cast<int>((n1 + 127) / 128), 128, 0, st>>>(part_r, 32, n1, k, nv1, nullptr);
-  topk_merge_mean_kernel<<<static_cast<int>((n2 + 127) / 128), 128, 0, st>>>(part_c, slabs, n2, k, nv2, nullptr);
+  topk_merge_mean_kernel<false><<<static_cast<int>((n1 + 127) / 128), 128, 0, st>>>(part_r, nullptr, 32, n1, k, nv1, nullptr, nullptr);
+  topk_merge_mean_kernel<false><<<static_cast<int>((n2 + 127) / 128), 128, 0, st>>>(part_c, nullptr, slabs, n2, k, nv2, nullptr, nullptr);
   if (out) {
     const int g = grid_for(n1 * n2, 256, num_sms(), 8);
     csls_apply_kernel<<<g, 256, 0, st>>>(sim, nv1, nv2, out, n1, n2, ld, ld_out);
@@ -792,11 +972,17 @@ int launch_prep_bf16(const float* emb, long long ld, const long long* idx, int n
   return static_cast<int>(cudaGetLastError());
 }
 
-int launch_topk_merge_mean(const float* part, int n_lists, long long n_rows, int k, float* nv, float* cand_out,
-                           cudaStream_t st) {
+int launch_topk_merge_mean(const float* part, const int* part_idx, int n_lists, long long n_rows, int k, float* nv,
+                           float* cand_out, int* cand_idx_out, cudaStream_t st) {
   if (!part || n_lists <= 0 || n_rows <= 0 || (!nv && !cand_out)) return SNAG_ERR_ARG;
+  if (cand_idx_out && (!part_idx || !cand_out)) return SNAG_ERR_ARG;
   if (k < 1 || k > KT_LIST) return SNAG_ERR_SHAPE;
-  topk_merge_mean_kernel<<<static_cast<int>((n_rows + 127) / 128), 128, 0, st>>>(part, n_lists, n_rows, k, nv, cand_out);
+  if (reinterpret_cast<uintptr_t>(part) & 15) return SNAG_ERR_ALIGN;
+  const int grid = static_cast<int>((n_rows + 127) / 128);
+  if (cand_idx_out)
+    topk_merge_mean_kernel<true><<<grid, 128, 0, st>>>(part, part_idx, n_lists, n_rows, k, nv, cand_out, cand_idx_out);
+  else
+    topk_merge_mean_kernel<false><<<grid, 128, 0, st>>>(part, nullptr, n_lists, n_rows, k, nv, cand_out, nullptr);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -152,11 +152,15 @@ int launch_sim_write(const __nv_bfloat16* X, const __nv_bfloat16* Y, const float
 }
 
 int launch_eval_rowtopk(const __nv_bfloat16* X, const __nv_bfloat16* Y, const float* xn, const float* yn, int n1, int n2,
-                        int Dpad, float* part, cudaStream_t st) {
+                        int Dpad, float* part, int* part_idx, cudaStream_t st) {
   if (!xn || !yn || !part) return SNAG_ERR_ARG;
-  if (reinterpret_cast<uintptr_t>(part) & 15) return SNAG_ERR_ALIGN;
-  EpiRowTopK::Params p{xn, yn, part};
-  return launch_sim<EpiRowTopK>(X, Y, n1, n2, Dpad, p, st);
+  if ((reinterpret_cast<uintptr_t>(part) | reinterpret_cast<uintptr_t>(part_idx)) & 15) return SNAG_ERR_ALIGN;
+  if (part_idx) {
+    EpiRowTopK<true>::Params p{xn, yn, part, part_idx};
+    return launch_sim<EpiRowTopK<true>>(X, Y, n1, n2, Dpad, p, st);
+  }
+  EpiRowTopK<false>::Params p{xn, yn, part, nullptr};
+  return launch_sim<EpiRowTopK<false>>(X, Y, n1, n2, Dpad, p, st);
 }
 
 int launch_eval_rank(const __nv_bfloat16* X, const __nv_bfloat16* Y, const float* xn, const float* yn, const float* nv1,
@@ -214,11 +218,14 @@ int launch_icl_rowsum(const __nv_bfloat16* X, const __nv_bfloat16* Y, int B, int
 }
 
 int launch_eval_rowcoltopk(const __nv_bfloat16* X, const __nv_bfloat16* Y, const float* xn, const float* yn, int n1, int n2,
-                           int Dpad, float* part, const float* colthr, const float* colb, uint2* stream, int* stream_cnt,
-                           int cta_cap, cudaStream_t st) {
-  if (!xn || !yn || !part || !colthr || !colb || !stream || !stream_cnt || cta_cap < 1) return SNAG_ERR_ARG;
-  if ((reinterpret_cast<uintptr_t>(part) & 15) || (reinterpret_cast<uintptr_t>(stream) & 7)) return SNAG_ERR_ALIGN;
-  EpiRowColTopK::Params p{xn, yn, part, colthr, colb, stream, stream_cnt, cta_cap};
+                           int Dpad, float* part, int* part_idx, const float* colthr, const float* colb, uint2* stream,
+                           int* stream_row, int* stream_cnt, int cta_cap, cudaStream_t st) {
+  if (!xn || !yn || !part || !part_idx || !colthr || !colb || !stream || !stream_row || !stream_cnt || cta_cap < 1)
+    return SNAG_ERR_ARG;
+  if (((reinterpret_cast<uintptr_t>(part) | reinterpret_cast<uintptr_t>(part_idx)) & 15) ||
+      (reinterpret_cast<uintptr_t>(stream) & 7))
+    return SNAG_ERR_ALIGN;
+  EpiRowColTopK::Params p{xn, yn, part, part_idx, colthr, colb, stream, stream_row, stream_cnt, cta_cap};
   return launch_sim<EpiRowColTopK>(X, Y, n1, n2, Dpad, p, st);
 }
 

@@ -268,8 +268,8 @@ sim_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
         // Rolled on purpose: one copy of the strip body keeps the epilogue inside the instruction cache
         // (a fully unrolled tile body was ~150 KB of SASS and ran instruction-fetch bound).
         if constexpr (!Epi::kNoLoad) {
-#pragma unroll 1
           const int c_end = min((cx.wg + 1) * STRIPS_PER_WG, tile_strips(shp, ct));
+#pragma unroll 1
           for (int c = cx.wg * STRIPS_PER_WG; c < c_end; ++c) {
             uint32_t r[32];
             SNAG_TMEM_LD32(taddr + c * 32, r);
@@ -480,25 +480,57 @@ struct EpiWrite {
   static __device__ __forceinline__ void unit_end(const Params&, const SimShape&, const EpiCtx&, State&) {}
 };
 
+// ascending KT-list insertion (top[0] = current KT-th largest = admission threshold); with kIdx the column ids travel
+// with the values (needed to re-score the neighbourhood canonically afterwards)
+template <bool kIdx>
+__device__ __forceinline__ void topk_list_insert(float (&top)[KT], int (&topi)[kIdx ? KT : 1], float x, int id) {
+  top[0] = x;
+  if (kIdx) topi[0] = id;
+#pragma unroll
+  for (int t = 0; t < KT - 1; ++t) {
+    if (kIdx) {
+      const bool sw = top[t] > top[t + 1];
+      const float a = top[t], b = top[t + 1];
+      const int ia = topi[t], ib = topi[t + 1];
+      top[t] = sw ? b : a;
+      top[t + 1] = sw ? a : b;
+      topi[t] = sw ? ib : ia;
+      topi[t + 1] = sw ? ia : ib;
+    } else {
+      const float lo = fminf(top[t], top[t + 1]);
+      const float hi = fmaxf(top[t], top[t + 1]);
+      top[t] = lo;
+      top[t + 1] = hi;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Epilogue: per-row top-KT of c_ij = 1 - d_ij over the unit's columns (CSLS neighbourhood, sweep 1).
 // Output: part[chunk][row][KT], ascending, -inf padded. A merge kernel reduces over chunks.
 // ------------------------------------------------------------------------------------------------
+template <bool kIdx>
 struct EpiRowTopK {
   static constexpr bool kNoLoad = false;
   struct Params {
     const float* xn;   // [n_rows]
     const float* yn;   // [n_cols]
     float* part;       // [n_lists][n_rows][KT]
+    int* part_idx;     // [n_lists][n_rows][KT] (kIdx) view column of every candidate, -1 for the -inf padding
   };
   struct State {
     float xn;
     float top[KT];     // ascending: top[0] is the current KT-th largest (the admission threshold)
+    int topi[kIdx ? KT : 1];
   };
   static __device__ __forceinline__ void unit_begin(const Params& p, const SimShape&, const EpiCtx& cx, State& st) {
     st.xn = cx.row_ok ? p.xn[cx.row] : 0.f;
 #pragma unroll
     for (int t = 0; t < KT; ++t) st.top[t] = -INFINITY;
+    if (kIdx) {
+#pragma unroll
+      for (int t = 0; t < KT; ++t) st.topi[t] = -1;
+    }
   }
   // scratch layout per buffer: yn[BN] then the minimum of yn over each 32-column strip [BN/32]
   static constexpr int kVecStride = BN + BN / 32;
@@ -522,7 +554,7 @@ struct EpiRowTopK {
     for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
     if (cx.lane == 0) yn_s[BN + (cx.tid >> 5)] = m;
   }
-  static __device__ __forceinline__ void chunk(const Params&, const SimShape&, const EpiCtx& cx, State& st, int,
+  static __device__ __forceinline__ void chunk(const Params&, const SimShape&, const EpiCtx& cx, State& st, int ct,
                                                int c, const uint32_t (&r)[32], int buf) {
     const float* yn_s = cx.scratch + buf * kVecStride + c * 32;
     // Conservative pre-filter in s-space. c_ij = fl(1 - max(fl(fl(xn_i + yn_j) - 2 s), 0)) can exceed the current
@@ -549,16 +581,7 @@ struct EpiRowTopK {
           const int q = __ffs(ph) - 1;
           ph &= ph - 1;
           const float x = __fsub_rn(1.0f, sqdist_from_dot(stage[q * NUM_EPI_THREADS], st.xn, yn_s[EPI_STAGE_VALS * h + q]));
-          if (x > st.top[0]) {
-            st.top[0] = x;
-#pragma unroll
-            for (int t = 0; t < KT - 1; ++t) {
-              const float lo = fminf(st.top[t], st.top[t + 1]);
-              const float hi = fmaxf(st.top[t], st.top[t + 1]);
-              st.top[t] = lo;
-              st.top[t + 1] = hi;
-            }
-          }
+          if (x > st.top[0]) topk_list_insert<kIdx>(st.top, st.topi, x, ct * BN + c * 32 + EPI_STAGE_VALS * h + q);
         }
       }
     }
@@ -566,9 +589,15 @@ struct EpiRowTopK {
   static __device__ __forceinline__ void tile_end(const Params&, const SimShape&, const EpiCtx&, State&, int, int) {}
   static __device__ __forceinline__ void unit_end(const Params& p, const SimShape& shp, const EpiCtx& cx, State& st) {
     if (!cx.row_ok) return;
-    float4* o = reinterpret_cast<float4*>(p.part + (static_cast<long long>(cx.list) * shp.n_rows + cx.row) * KT);
+    const long long o0 = (static_cast<long long>(cx.list) * shp.n_rows + cx.row) * KT;
+    float4* o = reinterpret_cast<float4*>(p.part + o0);
 #pragma unroll
     for (int t = 0; t < KT; t += 4) o[t / 4] = make_float4(st.top[t], st.top[t + 1], st.top[t + 2], st.top[t + 3]);
+    if (kIdx) {
+      int4* oi = reinterpret_cast<int4*>(p.part_idx + o0);
+#pragma unroll
+      for (int t = 0; t < KT; t += 4) oi[t / 4] = make_int4(st.topi[t], st.topi[t + 1], st.topi[t + 2], st.topi[t + 3]);
+    }
   }
 };
 
@@ -605,15 +634,18 @@ struct EpiRowColTopK {
     const float* xn;       // [n_rows]
     const float* yn;       // [n_cols]
     float* part;           // [n_lists][n_rows][KT]   row candidates, as EpiRowTopK
+    int* part_idx;         // [n_lists][n_rows][KT]   their view columns
     const float* colthr;   // [n_cols] admission threshold of column j in c-space (from the sample pre-pass)
     const float* colb;     // [n_cols] b_j of the s-space pre-filter
     uint2* stream;         // [gridDim.x][cta_cap] (column, c bits) candidates appended by each CTA
+    int* stream_row;       // [gridDim.x][cta_cap] view row of every stream entry
     int* stream_cnt;       // [gridDim.x] entries each CTA produced (may exceed cta_cap: overflow, entries dropped)
     int cta_cap;
   };
   struct State {
     float xn, a;
     float top[KT];
+    int topi[KT];
   };
   // scratch per tile buffer: yn[BN], strip minima of yn [BN/32], colb[BN], colthr[BN]; then xn of the row block x2
   static constexpr int kVecStride = 3 * BN + BN / 32;
@@ -629,7 +661,7 @@ struct EpiRowColTopK {
     st.xn = cx.row_ok ? p.xn[cx.row] : 0.f;
     st.a = cx.row_ok ? 0.5f * st.xn : INFINITY;          // padding rows never produce column candidates
 #pragma unroll
-    for (int t = 0; t < KT; ++t) st.top[t] = -INFINITY;
+    for (int t = 0; t < KT; ++t) { st.top[t] = -INFINITY; st.topi[t] = -1; }
     if (cx.wg == 0) cx.scratch[kXnOff + (cx.useq & 1) * BM + cx.et] = st.xn;   // visible after the tile barrier
   }
   static __device__ __forceinline__ EpiPre tile_prefetch(const Params& p, const SimShape& shp, const EpiCtx& cx, int ct) {
@@ -688,16 +720,7 @@ struct EpiRowColTopK {
           const int q = __ffs(ph) - 1;
           ph &= ph - 1;
           const float x = __fsub_rn(1.0f, sqdist_from_dot(stage_w[q * NUM_EPI_THREADS + cx.lane], st.xn, yn_s[EPI_STAGE_VALS * h + q]));
-          if (x > st.top[0]) {
-            st.top[0] = x;
-#pragma unroll
-            for (int t = 0; t < KT - 1; ++t) {
-              const float lo = fminf(st.top[t], st.top[t + 1]);
-              const float hi = fmaxf(st.top[t], st.top[t + 1]);
-              st.top[t] = lo;
-              st.top[t + 1] = hi;
-            }
-          }
+          if (x > st.top[0]) topk_list_insert<true>(st.top, st.topi, x, ct * BN + c * 32 + EPI_STAGE_VALS * h + q);
         }
         uint32_t cmask = ch;                               // column direction: lane l owns column l of the strip
         const int col = ct * BN + c * 32 + cx.lane;
@@ -710,8 +733,11 @@ struct EpiRowColTopK {
             // append to this CTA's private stream: a shared-memory counter hands out the slot (no global-atomic
             // round trip on the epilogue's critical path); a later pass buckets the stream by column
             const int slot = atomicAdd(reinterpret_cast<int*>(cx.scratch + kCntOff), 1);
-            if (slot < p.cta_cap)
-              p.stream[static_cast<long long>(blockIdx.x) * p.cta_cap + slot] = make_uint2(static_cast<uint32_t>(col), __float_as_uint(x));
+            if (slot < p.cta_cap) {
+              const long long o = static_cast<long long>(blockIdx.x) * p.cta_cap + slot;
+              p.stream[o] = make_uint2(static_cast<uint32_t>(col), __float_as_uint(x));
+              p.stream_row[o] = cx.rb * BM + (cx.et & ~31) + t;
+            }
           }
         }
         __syncwarp();
@@ -721,9 +747,14 @@ struct EpiRowColTopK {
   static __device__ __forceinline__ void tile_end(const Params&, const SimShape&, const EpiCtx&, State&, int, int) {}
   static __device__ __forceinline__ void unit_end(const Params& p, const SimShape& shp, const EpiCtx& cx, State& st) {
     if (!cx.row_ok) return;
-    float4* o = reinterpret_cast<float4*>(p.part + (static_cast<long long>(cx.list) * shp.n_rows + cx.row) * KT);
+    const long long o0 = (static_cast<long long>(cx.list) * shp.n_rows + cx.row) * KT;
+    float4* o = reinterpret_cast<float4*>(p.part + o0);
+    int4* oi = reinterpret_cast<int4*>(p.part_idx + o0);
 #pragma unroll
-    for (int t = 0; t < KT; t += 4) o[t / 4] = make_float4(st.top[t], st.top[t + 1], st.top[t + 2], st.top[t + 3]);
+    for (int t = 0; t < KT; t += 4) {
+      o[t / 4] = make_float4(st.top[t], st.top[t + 1], st.top[t + 2], st.top[t + 3]);
+      oi[t / 4] = make_int4(st.topi[t], st.topi[t + 1], st.topi[t + 2], st.topi[t + 3]);
+    }
   }
 };
 

@@ -36,7 +36,13 @@ int launch_rowblend_fwd(const float* e, const float* noise, const uint8_t* mask,
 int launch_rowblend_bwd(const float* g_out, const uint8_t* mask, float* g_in, long long N, int D, float a, cudaStream_t st);
 int launch_prep_bf16(const float* emb, long long ld, const long long* idx, int n, int D, int normalize,
                      __nv_bfloat16* out, int Dpad, float* norm2, cudaStream_t st);
-int launch_topk_merge_mean(const float* part, int n_lists, long long n_rows, int k, float* nv, float* cand_out,
+int launch_topk_merge_mean(const float* part, const int* part_idx, int n_lists, long long n_rows, int k, float* nv,
+                           float* cand_out, int* cand_idx_out, cudaStream_t st);
+int launch_topk_rescore(const __nv_bfloat16* A, const __nv_bfloat16* B, int Dpad, long long n_rows, const float* an,
+                        const float* bn, const int* cand_idx, const float* cand_val, int k, float delta, float* nv,
+                        int* flagged, int* flagged_cnt, int flagged_cap, cudaStream_t st);
+int launch_topk_exhaustive(const __nv_bfloat16* A, const __nv_bfloat16* B, int Dpad, long long n_b, const float* an,
+                           const float* bn, const int* flagged, const int* flagged_cnt, int flagged_cap, int k, float* nv,
                            cudaStream_t st);
 int launch_pair_score(const __nv_bfloat16* X, const __nv_bfloat16* Y, int Dpad, long long n, const float* xn, const float* yn,
                       const float* nv1, const float* nv2, int use_csls, float* g, float* s_out, cudaStream_t st);
@@ -64,7 +70,7 @@ int launch_sim_loadonly(const __nv_bfloat16* X, const __nv_bfloat16* Y, int n1, 
 int launch_sim_write(const __nv_bfloat16* X, const __nv_bfloat16* Y, const float* xn, const float* yn, int n1, int n2,
                      int Dpad, int mode, float* out, long long ld, cudaStream_t st);
 int launch_eval_rowtopk(const __nv_bfloat16* X, const __nv_bfloat16* Y, const float* xn, const float* yn, int n1, int n2,
-                        int Dpad, float* part, cudaStream_t st);
+                        int Dpad, float* part, int* part_idx, cudaStream_t st);
 int launch_eval_rank(const __nv_bfloat16* X, const __nv_bfloat16* Y, const float* xn, const float* yn, const float* nv1,
                      const float* nv2, const float* g_row, const float* g_col, int row_gid0, int col_gid0, int n1, int n2,
                      int Dpad, int use_csls, int* cnt_row, int* cnt_col, float* top3_val, int* top3_idx, cudaStream_t st);
@@ -79,15 +85,15 @@ int launch_mutual_nn(const __nv_bfloat16* X, const __nv_bfloat16* Y, const float
                      int Dpad, const float* colb, unsigned long long* colkey, float* row_val, int* row_idx,
                      cudaStream_t st);
 int launch_eval_rowcoltopk(const __nv_bfloat16* X, const __nv_bfloat16* Y, const float* xn, const float* yn, int n1, int n2,
-                           int Dpad, float* part, const float* colthr, const float* colb, uint2* stream, int* stream_cnt,
-                           int cta_cap, cudaStream_t st);
+                           int Dpad, float* part, int* part_idx, const float* colthr, const float* colb, uint2* stream,
+                           int* stream_row, int* stream_cnt, int cta_cap, cudaStream_t st);
 int launch_col_threshold(const float* cand, long long n, int k, const float* yn, float* colthr, float* colb, cudaStream_t st);
 int launch_cand_hist(const uint2* stream, const int* stream_cnt, int n_ctas, int cta_cap, int* hist, int* overflow,
                      cudaStream_t st);
-int launch_cand_scatter(const uint2* stream, const int* stream_cnt, int n_ctas, int cta_cap, const long long* offs,
-                        int* cursor, float* vals, cudaStream_t st);
-int launch_col_cand_finalize(const long long* offs, const int* hist, const float* vals, long long n, int k, float* nv,
-                             int* overflow, cudaStream_t st);
+int launch_cand_scatter(const uint2* stream, const int* stream_row, const int* stream_cnt, int n_ctas, int cta_cap,
+                        const long long* offs, int* cursor, float* vals, int* rows, cudaStream_t st);
+int launch_col_cand_finalize(const long long* offs, const int* hist, const float* vals, const int* rows, long long n, int k,
+                             float* nv, float* cand_val, int* cand_idx, int* overflow, cudaStream_t st);
 int launch_icl_bwd_logits(const __nv_bfloat16* X, const __nv_bfloat16* Y, int B, int Bp, int row0, int nx, int Dpad, float inv_tau,
                           const float* cr, const float* cc, const float* dg, __nv_bfloat16* G, cudaStream_t st);
 

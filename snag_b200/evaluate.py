@@ -87,8 +87,10 @@ def _align_ranks_steps(be, X, Y, xn, yn, n: int, csls_k: int, use_csls: bool, wa
 
     nv1 = nv2 = None
     if use_csls:
-        # sweep 1: row neighbourhoods — every source against this rank's targets
-        nv2_fused = None
+        # Sweep 1 selects, per source and per target, the KT partners with the largest tensor-core score and remembers
+        # WHO they are; the neighbourhood means are then computed from those candidates with the canonical arithmetic
+        # (ops.topk_rescore), so nv1 / nv2 equal the oracle's bit for bit whatever the accumulation order of the MMAs.
+        col_val = col_idx = None
         plan2 = two_sweep_plan(n, csls_k) if (two_sweep and ns > 0 and hasattr(be, "eval_rowcoltopk")) else None
         if plan2 is not None:
             # two-sweep path: a pre-pass over a random sample of the sources bounds every target's k-th best from
@@ -101,35 +103,40 @@ def _align_ranks_steps(be, X, Y, xn, yn, n: int, csls_k: int, use_csls: bool, wa
             part_s = be.eval_rowtopk(Ys, Xs, yns, xns, ns, m)
             _, cand_s = be.topk_merge_mean(part_s, csls_k, want_nv=False, want_cand=True)
             colthr, colb = be.col_threshold(cand_s, csls_k, yns)
-            part, stream, stream_cnt = be.eval_rowcoltopk(X, Ys, xn, yns, n, ns, colthr, colb, cap)
-            nv2_fused, overflow, _ = be.col_cand_reduce(stream, stream_cnt, ns, csls_k)
+            part, pidx, stream, stream_row, stream_cnt = be.eval_rowcoltopk(X, Ys, xn, yns, n, ns, colthr, colb, cap)
+            col_val, col_idx, overflow = be.col_cand_reduce(stream, stream_row, stream_cnt, ns, csls_k)
             launches += 7
             if int(overflow.item()) != 0:          # a candidate stream filled up: redo the columns the classic way
-                nv2_fused = None
-            del stream
+                col_val = col_idx = None
+            del stream, stream_row
         elif ns > 0:
-            part = be.eval_rowtopk(X, Ys, xn, yns, n, ns)
+            part, pidx = be.eval_rowtopk(X, Ys, xn, yns, n, ns, want_idx=True)
             launches += 1
         else:
             part = torch.full((1, n, KT), float("-inf"), dtype=torch.float32, device=dev)
-        if world == 1:
-            nv1, _ = be.topk_merge_mean(part, csls_k)
-            launches += 1
-        else:
-            _, cand = be.topk_merge_mean(part, csls_k, want_nv=False, want_cand=True)
+            pidx = torch.full((1, n, KT), -1, dtype=torch.int32, device=dev)
+        _, cand, cidx = be.topk_merge_mean(part, csls_k, want_nv=False, part_idx=pidx)
+        del part, pidx
+        launches += 1
+        if world > 1:
+            cidx = torch.where(cidx >= 0, cidx + c0, cidx)             # shard-local columns -> pair ids
             allc = yield ("all_gather", cand)                          # [world, n, KT]
-            nv1, _ = be.topk_merge_mean(allc.contiguous(), csls_k)
-            launches += 2
+            alli = yield ("all_gather", cidx)
+            _, cand, cidx = be.topk_merge_mean(allc.contiguous(), csls_k, want_nv=False, part_idx=alli.contiguous())
+            launches += 1
+        nv1 = be.topk_rescore(X, Y, xn, yn, cidx, cand, csls_k, n, "rows")
+        launches += 1
         # sweep 1': column neighbourhoods — this rank's targets against every source
-        # (skipped when the two-sweep path already produced them from the same pass over S)
+        # (skipped when the two-sweep path already collected them from the same pass over S)
         nv2_loc = torch.zeros((per,), dtype=torch.float32, device=dev)
-        if ns > 0 and nv2_fused is not None:
-            nv2_loc[:ns] = nv2_fused
-        elif ns > 0:
-            part2 = be.eval_rowtopk(Ys, X, yns, xn, ns, n)
-            nv2s, _ = be.topk_merge_mean(part2, csls_k)
-            nv2_loc[:ns] = nv2s
-            launches += 2
+        if ns > 0:
+            if col_val is None:
+                part2, pidx2 = be.eval_rowtopk(Ys, X, yns, xn, ns, n, want_idx=True)
+                _, col_val, col_idx = be.topk_merge_mean(part2, csls_k, want_nv=False, part_idx=pidx2)
+                del part2, pidx2
+                launches += 2
+            nv2_loc[:ns] = be.topk_rescore(Ys, X, yns, xn, col_idx, col_val, csls_k, n, "cols")
+            launches += 1
         if world == 1:
             nv2 = nv2_loc[:n]
         else:
@@ -175,7 +182,8 @@ def _align_ranks_steps(be, X, Y, xn, yn, n: int, csls_k: int, use_csls: bool, wa
         launches += 1
         top3_idx, top3_val = t3i[:, :3], t3v[:, :3]
     return AlignRanks(rank_l2r, rank_r2l, nv1, nv2, g, top3_idx, top3_val, launches,
-                      {"world": world, "rank": rank, "shard": (c0, c1), "rank_sweep": dict(getattr(be, "LAST_RANK_INFO", {}))})
+                      {"world": world, "rank": rank, "shard": (c0, c1), "rank_sweep": dict(getattr(be, "LAST_RANK_INFO", {})),
+                       "neighbourhoods": dict(getattr(be, "LAST_TOPK_INFO", {}))})
 
 
 def _drive_with_torch_distributed(gen, group):

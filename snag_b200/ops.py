@@ -113,17 +113,20 @@ class _SweepTimer:
             SWEEP_EVENT_SINK.append((self.args[0], self.e0, self.e1, self.args[1], self.args[2], self.args[3]))
 
 
-def eval_rowtopk(X, Y, xn, yn, n1: int, n2: int) -> torch.Tensor:
-    """Per-list candidate lists [n_lists, n1, KT] of c = 1 - d for every row of X against the rows of Y."""
+def eval_rowtopk(X, Y, xn, yn, n1: int, n2: int, want_idx: bool = False):
+    """Per-list candidate lists [n_lists, n1, KT] of c = 1 - d for every row of X against the rows of Y; with
+    want_idx also the column of every candidate (int32, -1 = padding): returns part or (part, part_idx)."""
     _check_operand(X, "X")
     _check_operand(Y, "Y")
     _need(xn, torch.float32, "xn", 1)
     _need(yn, torch.float32, "yn", 1)
     _, nch = sim_plan(n1, n2, X.shape[1])
     part = torch.empty((nch, n1, KT), dtype=torch.float32, device=X.device)
+    pidx = torch.empty((nch, n1, KT), dtype=torch.int32, device=X.device) if want_idx else None
     with _SweepTimer("sim_kernel<EpiRowTopK>", n1, n2):
-        call("snag_eval_rowtopk", ptr(X), ptr(Y), ptr(xn), ptr(yn), n1, n2, X.shape[1], ptr(part), current_stream())
-    return part
+        call("snag_eval_rowtopk", ptr(X), ptr(Y), ptr(xn), ptr(yn), n1, n2, X.shape[1], ptr(part), ptr(pidx),
+             current_stream())
+    return (part, pidx) if want_idx else part
 
 
 def col_threshold(cand: torch.Tensor, k: int, yn: torch.Tensor):
@@ -138,8 +141,9 @@ def col_threshold(cand: torch.Tensor, k: int, yn: torch.Tensor):
 
 
 def eval_rowcoltopk(X, Y, xn, yn, n1: int, n2: int, colthr, colb, cta_cap: int):
-    """One sweep for both CSLS directions: returns (row candidate lists [n_lists, n1, KT], per-CTA candidate streams
-    int64 [n_ctas, cta_cap] (low word column, high word c bits), stream_cnt int32 [n_ctas])."""
+    """One sweep for both CSLS directions: returns (row candidate lists [n_lists, n1, KT], their columns (int32, same
+    shape), per-CTA candidate streams int64 [n_ctas, cta_cap] (low word column, high word c bits), the row of every
+    stream entry int32 [n_ctas, cta_cap], stream_cnt int32 [n_ctas])."""
     _check_operand(X, "X")
     _check_operand(Y, "Y")
     _need(xn, torch.float32, "xn", 1)
@@ -149,18 +153,21 @@ def eval_rowcoltopk(X, Y, xn, yn, n1: int, n2: int, colthr, colb, cta_cap: int):
     _, nch = sim_plan(n1, n2, X.shape[1])
     n_ctas = _lib.load().snag_num_sms()
     part = torch.empty((nch, n1, KT), dtype=torch.float32, device=X.device)
+    pidx = torch.empty((nch, n1, KT), dtype=torch.int32, device=X.device)
     stream = torch.empty((n_ctas, cta_cap), dtype=torch.int64, device=X.device)
+    stream_row = torch.empty((n_ctas, cta_cap), dtype=torch.int32, device=X.device)
     stream_cnt = torch.zeros((n_ctas,), dtype=torch.int32, device=X.device)
     with _SweepTimer("sim_kernel<EpiRowColTopK>", n1, n2):
-        call("snag_eval_rowcoltopk", ptr(X), ptr(Y), ptr(xn), ptr(yn), n1, n2, X.shape[1], ptr(part), ptr(colthr),
-             ptr(colb), ptr(stream), ptr(stream_cnt), cta_cap, current_stream())
-    return part, stream, stream_cnt
+        call("snag_eval_rowcoltopk", ptr(X), ptr(Y), ptr(xn), ptr(yn), n1, n2, X.shape[1], ptr(part), ptr(pidx), ptr(colthr),
+             ptr(colb), ptr(stream), ptr(stream_row), ptr(stream_cnt), cta_cap, current_stream())
+    return part, pidx, stream, stream_row, stream_cnt
 
 
-def col_cand_reduce(stream: torch.Tensor, stream_cnt: torch.Tensor, n_cols: int, k: int):
-    """Bucket the per-CTA candidate streams by column and reduce each column to its neighbourhood mean.
-    Returns (nv [n_cols], overflow int32[1] device tensor, hist int32 [n_cols])."""
+def col_cand_reduce(stream: torch.Tensor, stream_row: torch.Tensor, stream_cnt: torch.Tensor, n_cols: int, k: int):
+    """Bucket the per-CTA candidate streams by column and keep each column's KT best candidates.
+    Returns (cand_val [n_cols, KT] ascending, cand_idx [n_cols, KT] rows, overflow int32[1] device tensor)."""
     _need(stream, torch.int64, "stream", 2)
+    _need(stream_row, torch.int32, "stream_row", 2)
     _need(stream_cnt, torch.int32, "stream_cnt", 1)
     dev = stream.device
     n_ctas, cta_cap = stream.shape
@@ -172,11 +179,15 @@ def col_cand_reduce(stream: torch.Tensor, stream_cnt: torch.Tensor, n_cols: int,
     offs = (incl - hist).contiguous()
     total = int(min(int(stream_cnt.clamp(max=cta_cap).sum().item()), n_ctas * cta_cap))
     vals = torch.empty((max(total, 1),), dtype=torch.float32, device=dev)
+    rows = torch.empty((max(total, 1),), dtype=torch.int32, device=dev)
     cursor = torch.zeros((n_cols,), dtype=torch.int32, device=dev)
-    call("snag_col_cand_scatter", ptr(stream), ptr(stream_cnt), n_ctas, cta_cap, ptr(offs), ptr(cursor), ptr(vals), st)
-    nv = torch.empty((n_cols,), dtype=torch.float32, device=dev)
-    call("snag_col_cand_finalize", ptr(offs), ptr(hist), ptr(vals), n_cols, k, ptr(nv), ptr(overflow), st)
-    return nv, overflow, hist
+    call("snag_col_cand_scatter", ptr(stream), ptr(stream_row), ptr(stream_cnt), n_ctas, cta_cap, ptr(offs), ptr(cursor),
+         ptr(vals), ptr(rows), st)
+    cand_val = torch.empty((n_cols, KT), dtype=torch.float32, device=dev)
+    cand_idx = torch.empty((n_cols, KT), dtype=torch.int32, device=dev)
+    call("snag_col_cand_finalize", ptr(offs), ptr(hist), ptr(vals), ptr(rows), n_cols, k, None, ptr(cand_val), ptr(cand_idx),
+         ptr(overflow), st)
+    return cand_val, cand_idx, overflow
 
 
 def mutual_nn(X, Y, xn, yn, n1: int, n2: int, colb: torch.Tensor):
@@ -196,17 +207,59 @@ def mutual_nn(X, Y, xn, yn, n1: int, n2: int, colb: torch.Tensor):
     return row_val, row_idx, colkey
 
 
-def topk_merge_mean(part: torch.Tensor, k: int, want_nv: bool = True, want_cand: bool = False):
+def topk_merge_mean(part: torch.Tensor, k: int, want_nv: bool = True, want_cand: bool = False,
+                    part_idx: torch.Tensor | None = None):
+    """Merge per-list candidate lists. Returns (nv, cand) — or (nv, cand, cand_idx) when the lists' ids are passed."""
     _need(part, torch.float32, "part", 3)
     if part.shape[2] != KT:
         raise ValueError("candidate lists must have SNAG_KT entries")
     if not 1 <= k <= KT:
         raise SnagError(f"csls_k={k} unsupported: the fused CSLS path keeps {KT} candidates per row")
+    if part_idx is not None:
+        _need(part_idx, torch.int32, "part_idx", 3)
+        want_cand = True
     n_lists, n_rows = part.shape[0], part.shape[1]
     nv = torch.empty((n_rows,), dtype=torch.float32, device=part.device) if want_nv else None
     cand = torch.empty((n_rows, KT), dtype=torch.float32, device=part.device) if want_cand else None
-    call("snag_topk_merge_mean", ptr(part), n_lists, n_rows, k, ptr(nv), ptr(cand), current_stream())
-    return nv, cand
+    cidx = torch.empty((n_rows, KT), dtype=torch.int32, device=part.device) if part_idx is not None else None
+    call("snag_topk_merge_mean", ptr(part), ptr(part_idx), n_lists, n_rows, k, ptr(nv), ptr(cand), ptr(cidx),
+         current_stream())
+    return (nv, cand) if part_idx is None else (nv, cand, cidx)
+
+
+# |c_tensor_core - c_canonical| is below 2 * (tensor-core dot error) + two fp32 roundings: same budget as RANK_BAND_EPS
+TOPK_VERIFY_DELTA = 4e-6
+TOPK_EXHAUSTIVE_BUDGET = 4.0e12     # bf16 multiply-adds the exhaustive completion may spend (~1 s of fp64 work on a B200)
+LAST_TOPK_INFO: dict = {}
+
+
+def topk_rescore(A, B, an, bn, cand_idx: torch.Tensor, cand_val: torch.Tensor, k: int, n_b: int, tag: str = "rows"):
+    """Canonical CSLS neighbourhood means of the rows of A from their KT tensor-core candidates (rows of B); rows the
+    candidates cannot vouch for are completed by an exhaustive scan of B (within TOPK_EXHAUSTIVE_BUDGET; beyond it the
+    candidate-based value stays and the count is reported in LAST_TOPK_INFO[tag]['unverified'])."""
+    _check_operand(A, "A")
+    _check_operand(B, "B")
+    _need(cand_idx, torch.int32, "cand_idx", 2)
+    _need(cand_val, torch.float32, "cand_val", 2)
+    n_rows = cand_idx.shape[0]
+    dev = A.device
+    st = current_stream()
+    nv = torch.empty((n_rows,), dtype=torch.float32, device=dev)
+    cap = n_rows
+    flagged = torch.empty((cap,), dtype=torch.int32, device=dev)
+    fcnt = torch.zeros((1,), dtype=torch.int32, device=dev)
+    call("snag_topk_rescore", ptr(A), ptr(B), A.shape[1], n_rows, ptr(an), ptr(bn), ptr(cand_idx), ptr(cand_val), k,
+         TOPK_VERIFY_DELTA, ptr(nv), ptr(flagged), ptr(fcnt), cap, st)
+    n_flag = int(fcnt.item())
+    info = {"flagged": n_flag, "unverified": 0}
+    if n_flag:
+        if float(n_flag) * n_b * A.shape[1] <= TOPK_EXHAUSTIVE_BUDGET:
+            call("snag_topk_exhaustive", ptr(A), ptr(B), A.shape[1], n_b, ptr(an), ptr(bn), ptr(flagged), ptr(fcnt), cap, k,
+                 ptr(nv), st)
+        else:
+            info["unverified"] = n_flag
+    LAST_TOPK_INFO[tag] = info
+    return nv
 
 
 def pair_score(X, Y, n: int, xn, yn, nv1, nv2, use_csls: bool, want_dot: bool = False):

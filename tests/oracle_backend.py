@@ -22,25 +22,48 @@ def _c_matrix(X, Y, xn, yn, n1, n2):
     return d
 
 
-def eval_rowtopk(X, Y, xn, yn, n1, n2):
+def eval_rowtopk(X, Y, xn, yn, n1, n2, want_idx=False):
     c = (np.float32(1.0) - _c_matrix(X, Y, xn, yn, n1, n2)).astype(np.float32)
     part = np.full((1, n1, KT), -np.inf, np.float32)
+    pidx = np.full((1, n1, KT), -1, np.int32)
     kk = min(KT, n2)
-    part[0, :, KT - kk:] = np.sort(c, axis=1)[:, -kk:]
+    order = np.lexsort((-np.broadcast_to(np.arange(n2), c.shape), c), axis=1)[:, -kk:]   # ascending, lower id wins ties
+    part[0, :, KT - kk:] = np.take_along_axis(c, order, 1)
+    pidx[0, :, KT - kk:] = order
+    if want_idx:
+        return torch.from_numpy(part), torch.from_numpy(pidx)
     return torch.from_numpy(part)
 
 
-def topk_merge_mean(part, k, want_nv=True, want_cand=False):
+def topk_merge_mean(part, k, want_nv=True, want_cand=False, part_idx=None):
     p = part.numpy()
-    allv = np.sort(np.concatenate(list(p), axis=1), axis=1)[:, -KT:]        # ascending, KT largest
+    allv = np.concatenate(list(p), axis=1)
+    if part_idx is not None:
+        alli = np.concatenate(list(part_idx.numpy()), axis=1)
+        order = np.lexsort((-alli, allv), axis=1)[:, -KT:]
+        cand_i = np.take_along_axis(alli, order, 1)
+        allv = np.take_along_axis(allv, order, 1)
+    else:
+        allv = np.sort(allv, axis=1)[:, -KT:]        # ascending, KT largest
     nv = None
     if want_nv:
         s = np.zeros((allv.shape[0],), np.float32)
         for t in range(k):
             s = (s + allv[:, KT - 1 - t]).astype(np.float32)
         nv = torch.from_numpy((s / np.float32(k)).astype(np.float32))
+    if part_idx is not None:
+        return nv, torch.from_numpy(allv.copy()), torch.from_numpy(cand_i.astype(np.int32))
     cand = torch.from_numpy(allv.copy()) if want_cand else None
     return nv, cand
+
+
+def topk_rescore(A, B, an, bn, cand_idx, cand_val, k, n_b, tag="rows"):
+    """The stand-in's scores are already canonical: the mean of the k largest candidate values, largest first."""
+    v = np.sort(cand_val.numpy(), axis=1)
+    s = np.zeros((v.shape[0],), np.float32)
+    for t in range(k):
+        s = (s + v[:, KT - 1 - t]).astype(np.float32)
+    return torch.from_numpy((s / np.float32(k)).astype(np.float32))
 
 
 def _dist(X, Y, xn, yn, nv1, nv2, n1, n2, use_csls):

@@ -43,6 +43,8 @@ def test_golden_vectors(cuda_device, name):
     if csls:
         np.testing.assert_allclose(res.nv1.cpu().numpy(), fx["nv1"], rtol=0, atol=1e-6)
         np.testing.assert_allclose(res.nv2.cpu().numpy(), fx["nv2"], rtol=0, atol=1e-6)
+        # (the goldens come from the reference's own torch.mm, whose accumulation order is the library's: 1e-6;
+        #  against the oracle's canonical accumulation the same quantities are bit-exact, see test_against_oracle)
     for side, ranks in (("l2r", res.rank_l2r), ("r2l", res.rank_r2l)):
         m = evaluate.metrics_from_ranks(ranks)
         np.testing.assert_array_equal(m.acc, fx[f"acc_{side}"])
@@ -68,24 +70,26 @@ def test_against_oracle(cuda_device, n, d, k, csls, sigma):
     res = evaluate.align_ranks(X, Y, xn, yn, n, k, csls, want_top3=True)
     ref = oracle.align_eval(x, y, csls, k, want_dist=True)
     np.testing.assert_array_equal(xn.cpu().numpy(), oracle.norm2(x))
+    # Every quantity that leaves the evaluation is computed from canonically accumulated dot products (neighbourhood
+    # candidates and near-ties are re-scored in fp64 index order): bit-exact on EVERY pair, ambiguous or not.
     if csls:
-        np.testing.assert_allclose(res.nv1.cpu().numpy(), ref["nv1"], rtol=0, atol=1e-6)
-        np.testing.assert_allclose(res.nv2.cpu().numpy(), ref["nv2"], rtol=0, atol=1e-6)
-    # a pair is "ambiguous" if some competitor sits within 2e-5 of its ground-truth distance: only there may the
-    # accumulation order of a dot product move a rank. Everything else must be bit-exact.
-    dist, g = ref["dist"], ref["g"]
-    off = dist.copy()
-    np.fill_diagonal(off, np.inf)
-    amb_row = np.abs(off - g[:, None]).min(1) < 2e-5
-    amb_col = np.abs(off - g[None, :]).min(0) < 2e-5
-    assert amb_row.mean() < 0.01 and amb_col.mean() < 0.01
-    l2r, r2l = res.rank_l2r.cpu().numpy(), res.rank_r2l.cpu().numpy()
-    np.testing.assert_array_equal(l2r[~amb_row], ref["rank_l2r"][~amb_row])
-    np.testing.assert_array_equal(r2l[~amb_col], ref["rank_r2l"][~amb_col])
-    assert np.abs(l2r - ref["rank_l2r"]).max() <= 2 and np.abs(r2l - ref["rank_r2l"]).max() <= 2
+        np.testing.assert_array_equal(res.nv1.cpu().numpy(), ref["nv1"])
+        np.testing.assert_array_equal(res.nv2.cpu().numpy(), ref["nv2"])
+        assert res.info["neighbourhoods"]["rows"]["unverified"] == 0 and res.info["neighbourhoods"]["cols"]["unverified"] == 0
+    np.testing.assert_array_equal(res.g.cpu().numpy(), ref["g"])
+    np.testing.assert_array_equal(res.rank_l2r.cpu().numpy(), ref["rank_l2r"])
+    np.testing.assert_array_equal(res.rank_r2l.cpu().numpy(), ref["rank_r2l"])
+    # top-3 ids: the four nearest by tensor-core score are re-scored canonically; exact unless the 4th and 5th
+    # nearest are closer than the tensor core can tell apart
+    dist = ref["dist"]
     srt = np.sort(dist, 1)
-    clear3 = (srt[:, 3] - srt[:, 2] > 2e-5) & (srt[:, 2] - srt[:, 1] > 2e-5) & (srt[:, 1] - srt[:, 0] > 2e-5)
-    np.testing.assert_array_equal(res.top3_idx.cpu().numpy()[clear3], ref["top3"][clear3])
+    clear = srt[:, 4] - srt[:, 3] > 2e-5
+    assert clear.mean() > 0.99
+    np.testing.assert_array_equal(res.top3_idx.cpu().numpy()[clear], ref["top3"][clear])
+    for side, ranks in (("l2r", res.rank_l2r), ("r2l", res.rank_r2l)):
+        m = evaluate.metrics_from_ranks(ranks)
+        mo = evaluate.metrics_from_ranks(ref[f"rank_{side}"])
+        assert m.mr == mo.mr and m.mrr == mo.mrr and np.array_equal(m.acc, mo.acc)
 
 
 @pytest.mark.parametrize("n,d", [(1500, 1200), (1100, 1800), (2100, 300)])
@@ -324,12 +328,14 @@ def test_two_sweep_equals_three_sweep_bitwise(cuda_device):
     part_s = ops.eval_rowtopk(Y, X.index_select(0, sel), yn, xn.index_select(0, sel), n, m)
     _, cand_s = ops.topk_merge_mean(part_s, k, want_nv=False, want_cand=True)
     colthr, colb = ops.col_threshold(cand_s, k, yn)
-    _, stream, scnt = ops.eval_rowcoltopk(X, Y, xn, yn, n, n, colthr, colb, cap)
-    nv2, overflow, hist = ops.col_cand_reduce(stream, scnt, n, k)
-    assert int(overflow.item()) == 0 and int(hist.min()) >= k
-    assert abs(float(hist.float().mean()) / (k * n / m) - 1.0) < 0.1
-    assert torch.equal(nv2, a.nv2)
+    _, _, stream, srow, scnt = ops.eval_rowcoltopk(X, Y, xn, yn, n, n, colthr, colb, cap)
+    cval, cidx, overflow = ops.col_cand_reduce(stream, srow, scnt, n, k)
+    assert int(overflow.item()) == 0 and bool((cidx[:, -k:] >= 0).all())
+    per_col = float(scnt.sum().item()) / n
+    assert abs(per_col / (k * n / m) - 1.0) < 0.1
+    nv2 = ops.topk_rescore(Y, X, yn, xn, cidx, cval, k, n, "cols")
+    assert torch.equal(nv2, a.nv2) and ops.LAST_TOPK_INFO["cols"]["flagged"] == 0
     # a stream that is too small must be reported, not silently truncated
-    _, stream, scnt = ops.eval_rowcoltopk(X, Y, xn, yn, n, n, colthr, colb, 1024)
-    _, overflow, _ = ops.col_cand_reduce(stream, scnt, n, k)
+    _, _, stream, srow, scnt = ops.eval_rowcoltopk(X, Y, xn, yn, n, n, colthr, colb, 1024)
+    _, _, overflow = ops.col_cand_reduce(stream, srow, scnt, n, k)
     assert int(overflow.item()) == 1
