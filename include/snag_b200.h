@@ -117,10 +117,13 @@ int snag_eval_rowtopk(const uint16_t* X, const uint16_t* Y, const float* xn, con
  * snag_col_cand_finalize (nv[j] = mean of the k largest and/or cand_val/cand_idx [n][SNAG_KT] = the column's SNAG_KT
  * best candidates with their rows; sets *overflow if a column has fewer than k). On overflow fall back to the swapped
  * snag_eval_rowtopk sweep. hist / cursor / overflow are zeroed by the caller. part_idx / stream_row carry the column
- * of every row candidate and the row of every stream entry (int32, same shapes as part / stream). */
+ * of every row candidate and the row of every stream entry (int32, same shapes as part / stream).
+ * rowthr (may be NULL): per row a lower bound of its final SNAG_KT-th largest c (e.g. the SNAG_KT-th largest over a
+ * sample of the columns, minus 2e-6); every partial list starts from it, slots it leaves unfilled read (rowthr, -1). */
 int snag_eval_rowcoltopk(const uint16_t* X, const uint16_t* Y, const float* xn, const float* yn, int32_t n1, int32_t n2,
-                         int32_t Dpad, float* part, int32_t* part_idx, const float* colthr, const float* colb,
-                         uint64_t* stream, int32_t* stream_row, int32_t* stream_cnt, int32_t cta_cap, void* stream_);
+                         int32_t Dpad, float* part, int32_t* part_idx, const float* rowthr, const float* colthr,
+                         const float* colb, uint64_t* stream, int32_t* stream_row, int32_t* stream_cnt, int32_t cta_cap,
+                         void* stream_);
 int snag_col_threshold(const float* cand, int64_t n, int32_t k, const float* yn, float* colthr, float* colb, void* stream);
 int snag_col_cand_hist(const uint64_t* stream, const int32_t* stream_cnt, int32_t n_ctas, int32_t cta_cap, int32_t* hist,
                        int32_t* overflow, void* stream_);

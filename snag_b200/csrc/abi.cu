@@ -158,9 +158,10 @@ int snag_icl_finalize(const float* rowsum_part, int32_t n_lists, int32_t B, int3
 }
 
 int snag_eval_rowcoltopk(const uint16_t* X, const uint16_t* Y, const float* xn, const float* yn, int32_t n1, int32_t n2,
-                         int32_t Dpad, float* part, int32_t* part_idx, const float* colthr, const float* colb,
-                         uint64_t* stream, int32_t* stream_row, int32_t* stream_cnt, int32_t cta_cap, void* stream_) {
-  return launch_eval_rowcoltopk(BF(X), BF(Y), xn, yn, n1, n2, Dpad, part, part_idx, colthr, colb,
+                         int32_t Dpad, float* part, int32_t* part_idx, const float* rowthr, const float* colthr,
+                         const float* colb, uint64_t* stream, int32_t* stream_row, int32_t* stream_cnt, int32_t cta_cap,
+                         void* stream_) {
+  return launch_eval_rowcoltopk(BF(X), BF(Y), xn, yn, n1, n2, Dpad, part, part_idx, rowthr, colthr, colb,
                                 reinterpret_cast<uint2*>(stream), stream_row, stream_cnt, cta_cap, S(stream_));
 }
 int snag_col_threshold(const float* cand, int64_t n, int32_t k, const float* yn, float* colthr, float* colb, void* stream) {

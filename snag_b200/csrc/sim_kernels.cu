@@ -218,14 +218,14 @@ int launch_icl_rowsum(const __nv_bfloat16* X, const __nv_bfloat16* Y, int B, int
 }
 
 int launch_eval_rowcoltopk(const __nv_bfloat16* X, const __nv_bfloat16* Y, const float* xn, const float* yn, int n1, int n2,
-                           int Dpad, float* part, int* part_idx, const float* colthr, const float* colb, uint2* stream,
-                           int* stream_row, int* stream_cnt, int cta_cap, cudaStream_t st) {
+                           int Dpad, float* part, int* part_idx, const float* rowthr, const float* colthr, const float* colb,
+                           uint2* stream, int* stream_row, int* stream_cnt, int cta_cap, cudaStream_t st) {
   if (!xn || !yn || !part || !part_idx || !colthr || !colb || !stream || !stream_row || !stream_cnt || cta_cap < 1)
     return SNAG_ERR_ARG;
   if (((reinterpret_cast<uintptr_t>(part) | reinterpret_cast<uintptr_t>(part_idx)) & 15) ||
       (reinterpret_cast<uintptr_t>(stream) & 7))
     return SNAG_ERR_ALIGN;
-  EpiRowColTopK::Params p{xn, yn, part, part_idx, colthr, colb, stream, stream_row, stream_cnt, cta_cap};
+  EpiRowColTopK::Params p{xn, yn, part, part_idx, rowthr, colthr, colb, stream, stream_row, stream_cnt, cta_cap};
   return launch_sim<EpiRowColTopK>(X, Y, n1, n2, Dpad, p, st);
 }
 

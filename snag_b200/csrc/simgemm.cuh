@@ -635,6 +635,9 @@ struct EpiRowColTopK {
     const float* yn;       // [n_cols]
     float* part;           // [n_lists][n_rows][KT]   row candidates, as EpiRowTopK
     int* part_idx;         // [n_lists][n_rows][KT]   their view columns
+    const float* rowthr;   // [n_rows] or null: a lower bound of row i's final KT-th largest c (from a sample of the
+                           // columns). Every list starts from it instead of -inf, which removes the ~KT*ln(cols/KT)
+                           // warm-up insertions each unit would otherwise pay; unfilled slots keep (rowthr, -1).
     const float* colthr;   // [n_cols] admission threshold of column j in c-space (from the sample pre-pass)
     const float* colb;     // [n_cols] b_j of the s-space pre-filter
     uint2* stream;         // [gridDim.x][cta_cap] (column, c bits) candidates appended by each CTA
@@ -660,8 +663,9 @@ struct EpiRowColTopK {
     if (cx.useq == 0 && cx.tid == 0) *reinterpret_cast<int*>(cx.scratch + kCntOff) = 0;   // ordered by the tile barrier
     st.xn = cx.row_ok ? p.xn[cx.row] : 0.f;
     st.a = cx.row_ok ? 0.5f * st.xn : INFINITY;          // padding rows never produce column candidates
+    const float t0 = (p.rowthr != nullptr && cx.row_ok) ? p.rowthr[cx.row] : -INFINITY;
 #pragma unroll
-    for (int t = 0; t < KT; ++t) { st.top[t] = -INFINITY; st.topi[t] = -1; }
+    for (int t = 0; t < KT; ++t) { st.top[t] = t0; st.topi[t] = -1; }
     if (cx.wg == 0) cx.scratch[kXnOff + (cx.useq & 1) * BM + cx.et] = st.xn;   // visible after the tile barrier
   }
   static __device__ __forceinline__ EpiPre tile_prefetch(const Params& p, const SimShape& shp, const EpiCtx& cx, int ct) {

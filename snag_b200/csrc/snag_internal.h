@@ -85,8 +85,8 @@ int launch_mutual_nn(const __nv_bfloat16* X, const __nv_bfloat16* Y, const float
                      int Dpad, const float* colb, unsigned long long* colkey, float* row_val, int* row_idx,
                      cudaStream_t st);
 int launch_eval_rowcoltopk(const __nv_bfloat16* X, const __nv_bfloat16* Y, const float* xn, const float* yn, int n1, int n2,
-                           int Dpad, float* part, int* part_idx, const float* colthr, const float* colb, uint2* stream,
-                           int* stream_row, int* stream_cnt, int cta_cap, cudaStream_t st);
+                           int Dpad, float* part, int* part_idx, const float* rowthr, const float* colthr, const float* colb,
+                           uint2* stream, int* stream_row, int* stream_cnt, int cta_cap, cudaStream_t st);
 int launch_col_threshold(const float* cand, long long n, int k, const float* yn, float* colthr, float* colb, cudaStream_t st);
 int launch_cand_hist(const uint2* stream, const int* stream_cnt, int n_ctas, int cta_cap, int* hist, int* overflow,
                      cudaStream_t st);

@@ -103,7 +103,18 @@ def _align_ranks_steps(be, X, Y, xn, yn, n: int, csls_k: int, use_csls: bool, wa
             part_s = be.eval_rowtopk(Ys, Xs, yns, xns, ns, m)
             _, cand_s = be.topk_merge_mean(part_s, csls_k, want_nv=False, want_cand=True)
             colthr, colb = be.col_threshold(cand_s, csls_k, yns)
-            part, pidx, stream, stream_row, stream_cnt = be.eval_rowcoltopk(X, Ys, xn, yns, n, ns, colthr, colb, cap)
+            # the same bound for the rows, from a sample of this rank's targets: the KT-th best of the sample can only
+            # be lower than the KT-th best overall, so lists seeded with it lose nothing and skip their warm-up
+            rowthr = None
+            ms = min(m, ns)
+            if ms >= KT:
+                selc = torch.randperm(ns, generator=gsel)[:ms].sort()[0].to(dev)
+                part_r = be.eval_rowtopk(X, Ys.index_select(0, selc), xn, yns.index_select(0, selc), n, ms)
+                _, cand_r = be.topk_merge_mean(part_r, csls_k, want_nv=False, want_cand=True)
+                rowthr = (cand_r[:, 0] - 2e-6).contiguous()            # lists are ascending: [0] is the KT-th largest
+                del part_r, cand_r
+                launches += 2
+            part, pidx, stream, stream_row, stream_cnt = be.eval_rowcoltopk(X, Ys, xn, yns, n, ns, colthr, colb, cap, rowthr)
             col_val, col_idx, overflow = be.col_cand_reduce(stream, stream_row, stream_cnt, ns, csls_k)
             launches += 7
             if int(overflow.item()) != 0:          # a candidate stream filled up: redo the columns the classic way

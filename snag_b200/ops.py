@@ -140,7 +140,7 @@ def col_threshold(cand: torch.Tensor, k: int, yn: torch.Tensor):
     return colthr, colb
 
 
-def eval_rowcoltopk(X, Y, xn, yn, n1: int, n2: int, colthr, colb, cta_cap: int):
+def eval_rowcoltopk(X, Y, xn, yn, n1: int, n2: int, colthr, colb, cta_cap: int, rowthr: torch.Tensor | None = None):
     """One sweep for both CSLS directions: returns (row candidate lists [n_lists, n1, KT], their columns (int32, same
     shape), per-CTA candidate streams int64 [n_ctas, cta_cap] (low word column, high word c bits), the row of every
     stream entry int32 [n_ctas, cta_cap], stream_cnt int32 [n_ctas])."""
@@ -150,6 +150,10 @@ def eval_rowcoltopk(X, Y, xn, yn, n1: int, n2: int, colthr, colb, cta_cap: int):
     _need(yn, torch.float32, "yn", 1)
     _need(colthr, torch.float32, "colthr", 1)
     _need(colb, torch.float32, "colb", 1)
+    if rowthr is not None:
+        _need(rowthr, torch.float32, "rowthr", 1)
+        if rowthr.numel() < n1:
+            raise ValueError("rowthr needs one entry per row")
     _, nch = sim_plan(n1, n2, X.shape[1])
     n_ctas = _lib.load().snag_num_sms()
     part = torch.empty((nch, n1, KT), dtype=torch.float32, device=X.device)
@@ -158,8 +162,8 @@ def eval_rowcoltopk(X, Y, xn, yn, n1: int, n2: int, colthr, colb, cta_cap: int):
     stream_row = torch.empty((n_ctas, cta_cap), dtype=torch.int32, device=X.device)
     stream_cnt = torch.zeros((n_ctas,), dtype=torch.int32, device=X.device)
     with _SweepTimer("sim_kernel<EpiRowColTopK>", n1, n2):
-        call("snag_eval_rowcoltopk", ptr(X), ptr(Y), ptr(xn), ptr(yn), n1, n2, X.shape[1], ptr(part), ptr(pidx), ptr(colthr),
-             ptr(colb), ptr(stream), ptr(stream_row), ptr(stream_cnt), cta_cap, current_stream())
+        call("snag_eval_rowcoltopk", ptr(X), ptr(Y), ptr(xn), ptr(yn), n1, n2, X.shape[1], ptr(part), ptr(pidx), ptr(rowthr),
+             ptr(colthr), ptr(colb), ptr(stream), ptr(stream_row), ptr(stream_cnt), cta_cap, current_stream())
     return part, pidx, stream, stream_row, stream_cnt
 
 
