@@ -80,6 +80,11 @@ int snag_rowblend_bwd(const float* g_out, const uint8_t* mask, float* g_in, int6
  * (src/utils.py:210-212). out is uint16_t* = raw bf16. */
 int snag_prep_bf16(const float* emb, int64_t ld, const int64_t* idx, int32_t n, int32_t D, int32_t normalize,
                    uint16_t* out, int32_t Dpad, float* norm2, void* stream);
+/* Backward of snag_prep_bf16's (gather ->) L2-normalise as autograd sees it (F.normalize, model/SNAG_loss.py:60-64):
+ * with e = emb[idx[r]] and g = dz[r] (fp32 [n, ld_dz]),  demb[idx[r]] += g/||e|| - e (e.g)/||e||^3  (atomic adds; demb
+ * fp32 [N, ld_demb], zeroed by the caller). idx may be NULL (rows 0..n-1). normalize = 0: demb[idx[r]] += g. */
+int snag_normalize_bwd_scatter(const float* emb, int64_t ld, const int64_t* idx, int32_t n, int32_t D, int32_t normalize,
+                               const float* dz, int64_t ld_dz, float* demb, int64_t ld_demb, void* stream);
 
 /* ---- alignment evaluation ------------------------------------------------------------------- */
 /* pairwise_distances (src/utils.py:202-218), materialising: mode 1: out[i,j] = clamp(xn_i + yn_j - 2 x_i.y_j, 0);

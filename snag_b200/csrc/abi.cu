@@ -66,6 +66,12 @@ int snag_prep_bf16(const float* emb, int64_t ld, const int64_t* idx, int32_t n, 
                           reinterpret_cast<__nv_bfloat16*>(out), Dpad, norm2, S(stream));
 }
 
+int snag_normalize_bwd_scatter(const float* emb, int64_t ld, const int64_t* idx, int32_t n, int32_t D, int32_t normalize,
+                               const float* dz, int64_t ld_dz, float* demb, int64_t ld_demb, void* stream) {
+  return launch_normalize_bwd_scatter(emb, ld, reinterpret_cast<const long long*>(idx), n, D, normalize, dz, ld_dz, demb,
+                                      ld_demb, S(stream));
+}
+
 int snag_sim_mainloop_only(const uint16_t* X, const uint16_t* Y, int32_t n1, int32_t n2, int32_t Dpad, void* stream) {
   return launch_sim_null(BF(X), BF(Y), n1, n2, Dpad, S(stream));
 }

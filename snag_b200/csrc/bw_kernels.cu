@@ -274,6 +274,50 @@ __global__ void __launch_bounds__(256) prep_bf16_kernel(const float* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------------
+// Backward of (gather ->) F.normalize, scattered into the embedding gradient (model/SNAG_loss.py:60-64 seen from
+// autograd): for z = e / max(||e||, 1e-12) and upstream g = dL/dz,
+//   dL/de = g / ||e|| - e (e.g) / ||e||^3        accumulated into demb[idx[r]] (atomic: a row may be linked twice)
+// One warp per gathered row; replaces torch's normalize-backward chain + index_select backward.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) normalize_bwd_scatter_kernel(const float* __restrict__ emb, long long ld,
+                                                                    const long long* __restrict__ idx, int n, int D,
+                                                                    int normalize, const float* __restrict__ dz,
+                                                                    long long ld_dz, float* __restrict__ demb,
+                                                                    long long ld_demb) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= n) return;
+  const long long row = idx ? idx[warp] : static_cast<long long>(warp);
+  const float* src = emb + row * ld;
+  const float* g = dz + static_cast<long long>(warp) * ld_dz;
+  if (!normalize) {                                 // plain gather: its backward is the scatter-add alone
+    float* d0 = demb + row * ld_demb;
+    for (int c = lane; c < D; c += 32) atomicAdd(d0 + c, __ldg(g + c));
+    return;
+  }
+  float ss = 0.f, eg = 0.f;
+  for (int c = lane; c < D; c += 32) {
+    const float v = __ldg(src + c);
+    ss = __fmaf_rn(v, v, ss);
+    eg = __fmaf_rn(v, __ldg(g + c), eg);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    eg += __shfl_xor_sync(0xffffffffu, eg, o);
+  }
+  const float nrm = sqrtf(ss);
+  float* dst = demb + row * ld_demb;
+  if (nrm > 1e-12f) {
+    const float inv = 1.0f / nrm;
+    const float k = eg * inv * inv * inv;
+    for (int c = lane; c < D; c += 32) atomicAdd(dst + c, __fmaf_rn(-__ldg(src + c), k, __ldg(g + c) * inv));
+  } else {                                         // clamped denominator: z = e / eps is linear in e
+    for (int c = lane; c < D; c += 32) atomicAdd(dst + c, __ldg(g + c) * 1e12f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // CSLS neighbourhood means: merge the per-chunk ascending KT-lists of every row, keep the KT largest,
 // nv[row] = (sum of the k largest, accumulated largest-first in fp32) / k     (src/utils.py:431-432)
 // Optionally also emits the merged KT-list (descending) for the cross-GPU candidate exchange.
@@ -969,6 +1013,15 @@ int launch_prep_bf16(const float* emb, long long ld, const long long* idx, int n
   if (Dpad < D || (Dpad % 64) != 0) return SNAG_ERR_SHAPE;
   const long long threads = static_cast<long long>(n) * 32;
   prep_bf16_kernel<<<static_cast<int>((threads + 255) / 256), 256, 0, st>>>(emb, ld, idx, n, D, normalize, out, Dpad, norm2);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int launch_normalize_bwd_scatter(const float* emb, long long ld, const long long* idx, int n, int D, int normalize,
+                                 const float* dz, long long ld_dz, float* demb, long long ld_demb, cudaStream_t st) {
+  if (!emb || !dz || !demb || n <= 0 || D <= 0 || ld < D || ld_dz < D || ld_demb < D) return SNAG_ERR_ARG;
+  const long long threads = static_cast<long long>(n) * 32;
+  normalize_bwd_scatter_kernel<<<static_cast<int>((threads + 255) / 256), 256, 0, st>>>(emb, ld, idx, n, D, normalize, dz,
+                                                                                       ld_dz, demb, ld_demb);
   return static_cast<int>(cudaGetLastError());
 }
 

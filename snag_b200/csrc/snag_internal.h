@@ -36,6 +36,8 @@ int launch_rowblend_fwd(const float* e, const float* noise, const uint8_t* mask,
 int launch_rowblend_bwd(const float* g_out, const uint8_t* mask, float* g_in, long long N, int D, float a, cudaStream_t st);
 int launch_prep_bf16(const float* emb, long long ld, const long long* idx, int n, int D, int normalize,
                      __nv_bfloat16* out, int Dpad, float* norm2, cudaStream_t st);
+int launch_normalize_bwd_scatter(const float* emb, long long ld, const long long* idx, int n, int D, int normalize,
+                                 const float* dz, long long ld_dz, float* demb, long long ld_demb, cudaStream_t st);
 int launch_topk_merge_mean(const float* part, const int* part_idx, int n_lists, long long n_rows, int k, float* nv,
                            float* cand_out, int* cand_idx_out, cudaStream_t st);
 int launch_topk_rescore(const __nv_bfloat16* A, const __nv_bfloat16* B, int Dpad, long long n_rows, const float* an,

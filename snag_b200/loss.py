@@ -106,26 +106,29 @@ def _unsharded() -> AnchorShard:
 
 
 class _IclPair(torch.autograd.Function):
-    """(zis, zjs) unit rows [B, D] fp32 -> per-row NLL of both directions, fused on the tensor cores; with an
-    AnchorShard of more than one rank every rank sweeps only its own anchors."""
+    """(emb [N, D] fp32, idx_l, idx_r [B]) -> per-row NLL of both directions of the in-batch contrastive loss of the
+    L2-normalised rows emb[idx_l], emb[idx_r], fused on the tensor cores; with an AnchorShard of more than one rank
+    every rank sweeps only its own anchors. Gather + F.normalize + bf16 cast are one kernel forward (prep_bf16) and one
+    backward (normalize_bwd_scatter), so autograd sees a single node from `emb` to the NLL vectors."""
 
     @staticmethod
-    def forward(ctx, zis, zjs, inv_tau, shard):
+    def forward(ctx, emb, idx_l, idx_r, inv_tau, shard, normalize=True):
         be = shard.be
-        B, D = zis.shape
+        emb = emb.contiguous()
+        B, D = idx_l.numel(), emb.shape[1]
         Bp = ops.round_up(B, 256)
         dpad = ops.round_up(D, 64)
         # stacked operand [a ; b ; a], every part zero padded to Bp rows: side a sweeps [b ; a], side b sweeps [a ; b]
-        S3 = torch.zeros((3 * Bp, dpad), dtype=torch.bfloat16, device=zis.device)
-        be.prep_bf16(zis.contiguous(), None, normalize=False, out=S3[0:Bp])
-        be.prep_bf16(zjs.contiguous(), None, normalize=False, out=S3[Bp:2 * Bp])
+        S3 = torch.zeros((3 * Bp, dpad), dtype=torch.bfloat16, device=emb.device)
+        be.prep_bf16(emb, idx_l, normalize=normalize, out=S3[0:Bp])
+        be.prep_bf16(emb, idx_r, normalize=normalize, out=S3[Bp:2 * Bp])
         S3[2 * Bp:2 * Bp + B].copy_(S3[0:B])
         r0, r1, per = shard.bounds(B)
         if shard.world == 1:
             lse_a, nll_a, _ = be.icl_side(S3[0:Bp], S3[Bp:3 * Bp], B, Bp, inv_tau)
             lse_b, nll_b, _ = be.icl_side(S3[Bp:2 * Bp], S3[0:2 * Bp], B, Bp, inv_tau)
         else:
-            loc = torch.zeros((4, per), dtype=torch.float32, device=zis.device)
+            loc = torch.zeros((4, per), dtype=torch.float32, device=emb.device)
             if r1 > r0:
                 nx = r1 - r0
                 la, na, _ = be.icl_side(S3[r0:r0 + nx], S3[Bp:3 * Bp], B, Bp, inv_tau, r0, nx)
@@ -133,15 +136,15 @@ class _IclPair(torch.autograd.Function):
                 loc[0, :nx], loc[1, :nx], loc[2, :nx], loc[3, :nx] = la, na, lb, nb
             allv = shard.all_gather(loc).permute(1, 0, 2).reshape(4, -1)[:, :B]      # [4, B] in anchor order
             lse_a, nll_a, lse_b, nll_b = (allv[i].contiguous() for i in range(4))
-        ctx.save_for_backward(S3, lse_a, lse_b)
-        ctx.dims = (B, D, Bp, inv_tau)
+        ctx.save_for_backward(S3, lse_a, lse_b, emb, idx_l, idx_r)
+        ctx.dims = (B, D, Bp, inv_tau, bool(normalize))
         ctx.shard = shard
         return nll_a, nll_b
 
     @staticmethod
     def backward(ctx, g_a, g_b):
-        S3, lse_a, lse_b = ctx.saved_tensors
-        B, D, Bp, inv_tau = ctx.dims
+        S3, lse_a, lse_b, emb, idx_l, idx_r = ctx.saved_tensors
+        B, D, Bp, inv_tau, nrm = ctx.dims
         shard = ctx.shard
         be = shard.be
         g_a = torch.zeros_like(lse_a) if g_a is None else g_a.contiguous().float()
@@ -151,10 +154,13 @@ class _IclPair(torch.autograd.Function):
         dg = (g_a + g_b).contiguous()
         Ya, Yb = S3[Bp:3 * Bp], S3[0:2 * Bp]
         YaT, YbT = Ya.t().contiguous(), Yb.t().contiguous()
+        demb = torch.zeros_like(emb)
         if shard.world == 1:
             Ga = be.icl_bwd_logits(S3[0:Bp], Ya, B, Bp, inv_tau, cra, crb, dg)         # [Bp, 2Bp] bf16
             Gb = be.icl_bwd_logits(S3[Bp:2 * Bp], Yb, B, Bp, inv_tau, crb, cra, dg)
-            return be.contract(Ga, YaT, B, D), be.contract(Gb, YbT, B, D), None, None   # [B, D] fp32 each
+            be.normalize_bwd_scatter(emb, idx_l, be.contract(Ga, YaT, B, D), demb, nrm)      # dz [B, D] fp32 -> demb rows
+            be.normalize_bwd_scatter(emb, idx_r, be.contract(Gb, YbT, B, D), demb, nrm)
+            return demb, None, None, None, None, None
         # sharded: G rows of the owned anchors only. Row i of G already carries every term of dL/d(anchor i) —
         # its own softmax row and its appearances as a column in the other rows' softmaxes (the cc / cr_j terms of
         # EpiIclBwd) — so the owned rows of dA, dB are complete and no reduce-scatter is needed.
@@ -168,11 +174,13 @@ class _IclPair(torch.autograd.Function):
             loc[1, :nx] = be.contract(Gb, YbT, nx, D)
         if shard.grads == "gather":
             allg = shard.all_gather(loc).permute(1, 0, 2, 3).reshape(2, -1, D)[:, :B]   # [2, B, D]
-            return allg[0].contiguous(), allg[1].contiguous(), None, None
-        dA = torch.zeros((B, D), dtype=torch.float32, device=S3.device)
-        dB = torch.zeros((B, D), dtype=torch.float32, device=S3.device)
-        dA[r0:r1], dB[r0:r1] = loc[0, :r1 - r0], loc[1, :r1 - r0]
-        return dA, dB, None, None
+            be.normalize_bwd_scatter(emb, idx_l, allg[0].contiguous(), demb, nrm)
+            be.normalize_bwd_scatter(emb, idx_r, allg[1].contiguous(), demb, nrm)
+        elif r1 > r0:                         # "local": only the owned anchors' rows; the SUM over ranks is the gradient
+            nx = r1 - r0
+            be.normalize_bwd_scatter(emb, idx_l[r0:r1].contiguous(), loc[0, :nx].contiguous(), demb, nrm)
+            be.normalize_bwd_scatter(emb, idx_r[r0:r1].contiguous(), loc[1, :nx].contiguous(), demb, nrm)
+        return demb, None, None, None, None, None
 
 
 class icl_loss(nn.Module):
@@ -206,10 +214,8 @@ class icl_loss(nn.Module):
             raise NotImplementedError("n_view != 2")
         idx_l, idx_r = _links_to_index(train_links, emb.device)
         # normalising only the 2B gathered rows equals normalising all N first (model/SNAG_loss.py:60-64), row by row
-        zis = F.normalize(emb.index_select(0, idx_l).float(), dim=1)
-        zjs = F.normalize(emb.index_select(0, idx_r).float(), dim=1)
-        nll_a, nll_b = _IclPair.apply(zis, zjs, float(1.0 / self.tau), self.shard or _unsharded())
-        batch = zis.shape[0]
+        nll_a, nll_b = _IclPair.apply(emb.float(), idx_l, idx_r, float(1.0 / self.tau), self.shard or _unsharded())
+        batch = idx_l.numel()
         if weight_norm is not None:
             w = torch.min(torch.stack([weight_norm[idx_l], weight_norm[idx_r]], dim=1), 1)[0]   # :66-69
             loss_a = (nll_a * w).sum() / batch                                                   # softXEnt :51

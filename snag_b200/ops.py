@@ -60,6 +60,22 @@ def prep_bf16(emb: torch.Tensor, idx: torch.Tensor | None = None, normalize: boo
     return out, norm2
 
 
+def normalize_bwd_scatter(emb: torch.Tensor, idx: torch.Tensor | None, dz: torch.Tensor, demb: torch.Tensor,
+                          normalize: bool = True) -> None:
+    """demb[idx[r]] += d/d emb[idx[r]] of F.normalize(emb[idx[r]]) . dz[r] — the backward of prep_bf16's gather +
+    normalise, accumulated in place (demb fp32 [N, D], same layout as emb)."""
+    _need(emb, torch.float32, "emb", 2)
+    _need(dz, torch.float32, "dz", 2)
+    _need(demb, torch.float32, "demb", 2)
+    if idx is not None:
+        _need(idx, torch.int64, "idx", 1)
+    n = emb.shape[0] if idx is None else idx.numel()
+    if dz.shape[0] < n or dz.shape[1] != emb.shape[1] or demb.shape != emb.shape:
+        raise ValueError("normalize_bwd_scatter: shape mismatch")
+    call("snag_normalize_bwd_scatter", ptr(emb), emb.stride(0), ptr(idx), n, emb.shape[1], int(normalize), ptr(dz),
+         dz.stride(0), ptr(demb), demb.stride(0), current_stream())
+
+
 def _check_operand(t: torch.Tensor, name: str) -> None:
     _need(t, torch.bfloat16, name, 2)
     if t.shape[1] % 64:

@@ -151,6 +151,17 @@ def prep_bf16(emb, idx=None, normalize=True, rows_pad_to=1, out=None):
     return out, (out[:n].float() ** 2).sum(1)
 
 
+def normalize_bwd_scatter(emb, idx, dz, demb, normalize=True):
+    with torch.enable_grad():                         # called from inside an autograd backward (grad mode is off there)
+        e = (emb if idx is None else emb.index_select(0, idx)).detach().clone().requires_grad_(True)
+        z = torch.nn.functional.normalize(e, dim=1) if normalize else e * 1.0
+        z.backward(dz[:e.shape[0]])
+    if idx is None:
+        demb += e.grad
+    else:
+        demb.index_add_(0, idx, e.grad)
+
+
 def _icl_logits(X, Y, B, Bp, inv_tau, row0, nx):
     s = X[:nx].float() @ Y.float().t()                                   # [nx, 2Bp]
     col = torch.arange(2 * Bp)

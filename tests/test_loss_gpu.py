@@ -63,7 +63,7 @@ def test_icl_same_operands(cuda_device, B, D, tau):
     a = a.to(torch.bfloat16).float().requires_grad_(True)
     b = b.to(torch.bfloat16).float().requires_grad_(True)
     w = torch.rand((B,), generator=g, device=cuda_device) + 0.5
-    nll_a, nll_b = sloss._IclPair.apply(a, b, 1.0 / tau, sloss._unsharded())
+    nll_a, nll_b = _pair(a, b, 1.0 / tau, sloss._unsharded())
     ra, rb = _torch_icl_rows(a.detach().double(), b.detach().double(), tau)
     np.testing.assert_allclose(nll_a.detach().cpu().numpy(), ra.float().cpu().numpy(), rtol=0, atol=2e-4)
     np.testing.assert_allclose(nll_b.detach().cpu().numpy(), rb.float().cpu().numpy(), rtol=0, atol=2e-4)
@@ -76,6 +76,13 @@ def test_icl_same_operands(cuda_device, B, D, tau):
     ref.backward()
     np.testing.assert_allclose(loss.item(), ref.item(), rtol=2e-4, atol=1e-6)
     assert _relerr(a.grad, a2.grad) < 1e-2 and _relerr(b.grad, b2.grad) < 1e-2
+
+
+def _pair(a, b, inv_tau, shard):
+    """_IclPair on two explicit sides: stacked as one table with identity links, rows taken as they are."""
+    B = a.shape[0]
+    ar = torch.arange(2 * B, device=a.device)
+    return sloss._IclPair.apply(torch.cat([a, b], 0), ar[:B].contiguous(), ar[B:].contiguous(), inv_tau, shard, False)
 
 
 class _LockstepShard(sloss.AnchorShard):
@@ -106,7 +113,7 @@ def test_icl_anchor_shards_match_full(cuda_device, B, D, world):
 
     def run(shard):
         a1, b1 = a.clone().requires_grad_(True), b.clone().requires_grad_(True)
-        na, nb = sloss._IclPair.apply(a1, b1, 10.0, shard)
+        na, nb = _pair(a1, b1, 10.0, shard)
         ((0.3 * (na * w).sum() + 0.7 * (nb * w).sum()) / B).backward()
         return na.detach(), nb.detach(), a1.grad, b1.grad
 
