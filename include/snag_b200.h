@@ -80,6 +80,19 @@ int snag_rowblend_bwd(const float* g_out, const uint8_t* mask, float* g_in, int6
  * (src/utils.py:210-212). out is uint16_t* = raw bf16. */
 int snag_prep_bf16(const float* emb, int64_t ld, const int64_t* idx, int32_t n, int32_t D, int32_t normalize,
                    uint16_t* out, int32_t Dpad, float* norm2, void* stream);
+/* ---- fusion-output (joint) embeddings, model/SNAG_tools.py:44-49 ------------------------------ */
+/* joint[i, off_m + c] = w_ent[i, m] * e_m[i, c] / max(||e_m[i]||, 1e-12) and joint_fz[...] = w_glob[m] * (same), for the
+ * M <= 6 present modalities concatenated along the row (off_m = widths[0] + .. + widths[m-1]). embs / widths are HOST
+ * arrays of M device pointers (fp32 [N, widths[m]], contiguous) / M ints. joint or joint_fz may be NULL (with its
+ * weights). Replaces 2M F.normalize + 2M scalings + 2 torch.cat. */
+int snag_joint_fuse_fwd(const float* const* embs, const int32_t* widths, int32_t M, int64_t N, const float* w_ent, int64_t ldw,
+                        const float* w_glob, float* joint, float* joint_fz, int64_t ld_out, void* stream);
+/* Its backward: d_embs[m] [N, widths[m]] (written), d_w_ent [N, ldw] (columns 0..M-1 written; may be NULL),
+ * d_w_glob [M] (ACCUMULATED: zero it first; may be NULL) from the upstream gradients d_joint / d_joint_fz (either may
+ * be NULL). */
+int snag_joint_fuse_bwd(const float* const* embs, float* const* d_embs, const int32_t* widths, int32_t M, int64_t N,
+                        const float* w_ent, int64_t ldw, const float* w_glob, const float* d_joint, const float* d_joint_fz,
+                        int64_t ld_out, float* d_w_ent, float* d_w_glob, void* stream);
 /* Backward of snag_prep_bf16's (gather ->) L2-normalise as autograd sees it (F.normalize, model/SNAG_loss.py:60-64):
  * with e = emb[idx[r]] and g = dz[r] (fp32 [n, ld_dz]),  demb[idx[r]] += g/||e|| - e (e.g)/||e||^3  (atomic adds; demb
  * fp32 [N, ld_demb], zeroed by the caller). idx may be NULL (rows 0..n-1). normalize = 0: demb[idx[r]] += g. */

@@ -22,7 +22,7 @@ sys.path.insert(0, ROOT)
 import numpy as np
 import torch
 
-from snag_b200 import evaluate, noise, ops
+from snag_b200 import evaluate, fusion, mining, noise, ops
 
 
 def peaks():
@@ -159,6 +159,43 @@ def main():
         return (2 * sc.t() - nv1).t() - nv2
     emit("a9", f"csls_sim[{n_test}^2, k=10] (materialised drop-in)", 12 * n_test * n_test, ms, cpu_time(ref_csls, 2),
          "2 reads + 1 write of the matrix is the algorithmic minimum; executed: 3 reads + 1 write")
+    del sim, sc
+    # ------------------------------------------------------------------ f2 fusion-output embeddings (SNAG_tools.py:44-49)
+    M = 4
+    embs = [torch.randn((N, 300), generator=g, device="cuda") for _ in range(M)]
+    wn = torch.softmax(torch.randn((N, M), generator=g, device="cuda"), 1)
+    wg = torch.softmax(torch.randn((6,), generator=g, device="cuda"), 0)
+    ms = gpu_time(lambda: ops.joint_fuse_fwd(embs, wn, wg))
+    ecs, wnc, wgc = [e.cpu() for e in embs], wn.cpu(), wg.cpu()
+
+    def ref_joint():
+        j = torch.cat([wnc[:, m].unsqueeze(1) * torch.nn.functional.normalize(ecs[m]) for m in range(M)], dim=1)
+        jf = torch.cat([wgc[m] * torch.nn.functional.normalize(ecs[m]) for m in range(M)], dim=1)
+        return j, jf
+    emit("f2", f"joint_fuse_fwd[{N} x {M}x300 -> 2 x {M * 300}]", 4 * N * 300 * M * 3, ms, cpu_time(ref_joint),
+         "read M tables once + write joint_emb and joint_emb_fz; the reference makes 4M+2 passes")
+    dj = torch.randn((N, 300 * M), generator=g, device="cuda")
+    djf = torch.randn((N, 300 * M), generator=g, device="cuda")
+    ms = gpu_time(lambda: ops.joint_fuse_bwd(embs, wn, wg, dj, djf))
+    emit("f2", f"joint_fuse_bwd[{N} x {M}x300]", 4 * N * 300 * M * 4, ms, None, "read e, dJ, dJfz + write de (each table read twice: norm pass + apply pass hits L2)")
+    del embs, dj, djf
+
+    # ------------------------------------------------------------------ f1 link mining (SNAG.py:192-208): fused mutual-NN sweep
+    n_l = n_r = N // 2 - 2250 if args.shape == "c1" else N // 2 - 1285          # the non-train entities of each KG
+    xl = torch.nn.functional.normalize(torch.randn((n_l, D), generator=g, device="cuda"))
+    yr = torch.nn.functional.normalize(xl[:n_r] + 0.5 * torch.nn.functional.normalize(torch.randn((n_r, D), generator=g, device="cuda")))
+    ms = gpu_time(lambda: mining.mutual_nearest(xl, yr, normalize=False), reps=5)
+    xlc, yrc = xl.cpu(), yr.cpu()
+
+    def ref_mine():
+        xn = (xlc ** 2).sum(1).view(-1, 1)
+        yn = (yrc ** 2).sum(1).view(1, -1)
+        d = torch.clamp(xn + yn - 2.0 * torch.mm(xlc, yrc.t()), 0.0, np.inf)
+        return torch.argmin(d, dim=1), torch.argmin(d.t(), dim=1)
+    flops = 2.0 * n_l * n_r * D
+    rec_ms = ms
+    emit("f1", f"mutual_nearest[{n_l} x {n_r}, D={D}] (pre-pass + fused argmin sweep)", 4 * n_l * n_r, rec_ms, cpu_time(ref_mine, 2),
+         f"tensor-pipe bound, not HBM: {flops / rec_ms / 1e9:.0f} TFLOP/s algorithmic; bytes = the distance matrix the reference materialises")
     out = os.path.join(ROOT, "gpurun_out", f"rows_{args.shape}.jsonl")
     os.makedirs(os.path.dirname(out), exist_ok=True)
     with open(out, "w") as f:

@@ -31,6 +31,8 @@ _SIGNATURES = {
     "snag_rowblend_fwd": [_vp, _vp, _vp, _vp, _i64, _i32, _f32, _f32, _vp],
     "snag_rowblend_bwd": [_vp, _vp, _vp, _i64, _i32, _f32, _vp],
     "snag_prep_bf16": [_vp, _i64, _vp, _i32, _i32, _i32, _vp, _i32, _vp, _vp],
+    "snag_joint_fuse_fwd": [_vp, _vp, _i32, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _vp],
+    "snag_joint_fuse_bwd": [_vp, _vp, _vp, _i32, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp],
     "snag_normalize_bwd_scatter": [_vp, _i64, _vp, _i32, _i32, _i32, _vp, _i64, _vp, _i64, _vp],
     "snag_sim_write": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _i64, _vp],
     "snag_sim_mainloop_only": [_vp, _vp, _i32, _i32, _i32, _vp],

@@ -66,6 +66,16 @@ int snag_prep_bf16(const float* emb, int64_t ld, const int64_t* idx, int32_t n, 
                           reinterpret_cast<__nv_bfloat16*>(out), Dpad, norm2, S(stream));
 }
 
+int snag_joint_fuse_fwd(const float* const* embs, const int32_t* widths, int32_t M, int64_t N, const float* w_ent, int64_t ldw,
+                        const float* w_glob, float* joint, float* joint_fz, int64_t ld_out, void* stream) {
+  return launch_joint_fuse_fwd(embs, widths, M, N, w_ent, ldw, w_glob, joint, joint_fz, ld_out, S(stream));
+}
+int snag_joint_fuse_bwd(const float* const* embs, float* const* d_embs, const int32_t* widths, int32_t M, int64_t N,
+                        const float* w_ent, int64_t ldw, const float* w_glob, const float* d_joint, const float* d_joint_fz,
+                        int64_t ld_out, float* d_w_ent, float* d_w_glob, void* stream) {
+  return launch_joint_fuse_bwd(embs, d_embs, widths, M, N, w_ent, ldw, w_glob, d_joint, d_joint_fz, ld_out, d_w_ent, d_w_glob,
+                               S(stream));
+}
 int snag_normalize_bwd_scatter(const float* emb, int64_t ld, const int64_t* idx, int32_t n, int32_t D, int32_t normalize,
                                const float* dz, int64_t ld_dz, float* demb, int64_t ld_demb, void* stream) {
   return launch_normalize_bwd_scatter(emb, ld, reinterpret_cast<const long long*>(idx), n, D, normalize, dz, ld_dz, demb,

@@ -274,6 +274,103 @@ __global__ void __launch_bounds__(256) prep_bf16_kernel(const float* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------------
+// f2  Joint (fusion-output) embeddings, model/SNAG_tools.py:44-49:
+//   joint   [i, off_m + c] = w_ent[i, m] * e_m[i, c] / max(||e_m[i]||, 1e-12)      (per-entity attention weights)
+//   joint_fz[i, off_m + c] = w_glob[m]   * e_m[i, c] / max(||e_m[i]||, 1e-12)      (softmax(weight_raw))
+// for the M present modalities, concatenated along the row. One warp per (entity, modality): the reference's
+// 2M normalise + 2M scale + 2 cat kernels become one pass that reads every table once and writes both outputs.
+// Backward (same grid): with G = w_ent*dJ + w_glob*dJfz, z = e/||e||:
+//   de = (G - z (z.G)) / ||e||,   dw_ent[i,m] = z.dJ,   dw_glob[m] += z.dJfz  (block-reduced, one atomic per block)
+// ------------------------------------------------------------------------------------------------
+struct JointTabs {
+  const float* e[SNAG_MAX_MODAL];
+  float* de[SNAG_MAX_MODAL];
+  int width[SNAG_MAX_MODAL];
+  int off[SNAG_MAX_MODAL];
+};
+
+__global__ void __launch_bounds__(256) joint_fuse_fwd_kernel(JointTabs tabs, long long N, const float* __restrict__ w_ent,
+                                                             long long ldw, const float* __restrict__ w_glob,
+                                                             float* __restrict__ joint, float* __restrict__ joint_fz,
+                                                             long long ld_out) {
+  const int m = blockIdx.y;
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (i >= N) return;
+  const int D = tabs.width[m];
+  const float* src = tabs.e[m] + i * D;
+  float ss = 0.f;
+  for (int c = lane; c < D; c += 32) { const float v = __ldg(src + c); ss = __fmaf_rn(v, v, ss); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const float denom = fmaxf(sqrtf(ss), 1e-12f);
+  const float w1 = (joint && w_ent) ? w_ent[i * ldw + m] : 0.f;
+  const float w2 = (joint_fz && w_glob) ? w_glob[m] : 0.f;
+  const long long o0 = i * ld_out + tabs.off[m];
+  for (int c = lane; c < D; c += 32) {
+    const float z = __fdiv_rn(__ldg(src + c), denom);
+    if (joint) joint[o0 + c] = __fmul_rn(w1, z);
+    if (joint_fz) joint_fz[o0 + c] = __fmul_rn(w2, z);
+  }
+}
+
+__global__ void __launch_bounds__(256) joint_fuse_bwd_kernel(JointTabs tabs, long long N, const float* __restrict__ w_ent,
+                                                             long long ldw, const float* __restrict__ w_glob,
+                                                             const float* __restrict__ d_joint,
+                                                             const float* __restrict__ d_joint_fz, long long ld_out,
+                                                             float* __restrict__ d_w_ent, float* __restrict__ d_w_glob) {
+  __shared__ float red[8];
+  const int m = blockIdx.y;
+  const int wib = threadIdx.x >> 5;
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + wib;
+  const int lane = threadIdx.x & 31;
+  float a2n = 0.f;                       // this warp's contribution to dw_glob[m]
+  if (i < N) {
+    const int D = tabs.width[m];
+    const float* src = tabs.e[m] + i * D;
+    const long long o0 = i * ld_out + tabs.off[m];
+    float ss = 0.f, a1 = 0.f, a2 = 0.f;
+    for (int c = lane; c < D; c += 32) {
+      const float v = __ldg(src + c);
+      ss = __fmaf_rn(v, v, ss);
+      if (d_joint) a1 = __fmaf_rn(v, __ldg(d_joint + o0 + c), a1);
+      if (d_joint_fz) a2 = __fmaf_rn(v, __ldg(d_joint_fz + o0 + c), a2);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+      a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+    }
+    const float nrm = sqrtf(ss);
+    const bool clamped = !(nrm > 1e-12f);
+    const float inv = clamped ? 1e12f : 1.0f / nrm;
+    const float w1 = (d_joint && w_ent) ? w_ent[i * ldw + m] : 0.f;
+    const float w2 = (d_joint_fz && w_glob) ? w_glob[m] : 0.f;
+    if (lane == 0 && d_w_ent) d_w_ent[i * ldw + m] = a1 * inv;
+    a2n = a2 * inv;
+    // z.G / ||e|| = (w1 a1 + w2 a2) inv^2 ; with a clamped denominator z = e * 1e12 is linear in e: de = G * 1e12
+    const float k = clamped ? 0.f : (w1 * a1 + w2 * a2) * inv * inv * inv;
+    float* dst = tabs.de[m] + i * D;
+    for (int c = lane; c < D; c += 32) {
+      float G = 0.f;
+      if (d_joint) G = __fmaf_rn(w1, __ldg(d_joint + o0 + c), G);
+      if (d_joint_fz) G = __fmaf_rn(w2, __ldg(d_joint_fz + o0 + c), G);
+      dst[c] = __fmaf_rn(-__ldg(src + c), k, G * inv);
+    }
+  }
+  if (d_w_glob) {
+    if (lane == 0) red[wib] = a2n;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+      for (int w = 0; w < static_cast<int>(blockDim.x >> 5); ++w) t += red[w];
+      atomicAdd(d_w_glob + m, t);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Backward of (gather ->) F.normalize, scattered into the embedding gradient (model/SNAG_loss.py:60-64 seen from
 // autograd): for z = e / max(||e||, 1e-12) and upstream g = dL/dz,
 //   dL/de = g / ||e|| - e (e.g) / ||e||^3        accumulated into demb[idx[r]] (atomic: a row may be linked twice)
@@ -1013,6 +1110,46 @@ int launch_prep_bf16(const float* emb, long long ld, const long long* idx, int n
   if (Dpad < D || (Dpad % 64) != 0) return SNAG_ERR_SHAPE;
   const long long threads = static_cast<long long>(n) * 32;
   prep_bf16_kernel<<<static_cast<int>((threads + 255) / 256), 256, 0, st>>>(emb, ld, idx, n, D, normalize, out, Dpad, norm2);
+  return static_cast<int>(cudaGetLastError());
+}
+
+static int fill_tabs(JointTabs* t, const float* const* embs, float* const* d_embs, const int* widths, int M) {
+  if (!embs || !widths || M < 1 || M > SNAG_MAX_MODAL) return SNAG_ERR_ARG;
+  int off = 0;
+  for (int m = 0; m < SNAG_MAX_MODAL; ++m) {
+    t->e[m] = nullptr; t->de[m] = nullptr; t->width[m] = 0; t->off[m] = 0;
+  }
+  for (int m = 0; m < M; ++m) {
+    if (!embs[m] || widths[m] <= 0) return SNAG_ERR_ARG;
+    if (d_embs && !d_embs[m]) return SNAG_ERR_ARG;
+    t->e[m] = embs[m];
+    t->de[m] = d_embs ? d_embs[m] : nullptr;
+    t->width[m] = widths[m];
+    t->off[m] = off;
+    off += widths[m];
+  }
+  return off;
+}
+int launch_joint_fuse_fwd(const float* const* embs, const int* widths, int M, long long N, const float* w_ent, long long ldw,
+                          const float* w_glob, float* joint, float* joint_fz, long long ld_out, cudaStream_t st) {
+  JointTabs t;
+  const int tot = fill_tabs(&t, embs, nullptr, widths, M);
+  if (tot < 0) return tot;
+  if (N <= 0 || ld_out < tot || (!joint && !joint_fz) || (joint && (!w_ent || ldw < M)) || (joint_fz && !w_glob)) return SNAG_ERR_ARG;
+  joint_fuse_fwd_kernel<<<dim3(static_cast<unsigned>((N + 7) / 8), M), 256, 0, st>>>(t, N, w_ent, ldw, w_glob, joint, joint_fz, ld_out);
+  return static_cast<int>(cudaGetLastError());
+}
+int launch_joint_fuse_bwd(const float* const* embs, float* const* d_embs, const int* widths, int M, long long N,
+                          const float* w_ent, long long ldw, const float* w_glob, const float* d_joint, const float* d_joint_fz,
+                          long long ld_out, float* d_w_ent, float* d_w_glob, cudaStream_t st) {
+  JointTabs t;
+  if (!d_embs) return SNAG_ERR_ARG;
+  const int tot = fill_tabs(&t, embs, d_embs, widths, M);
+  if (tot < 0) return tot;
+  if (N <= 0 || ld_out < tot || (!d_joint && !d_joint_fz) || (d_joint && (!w_ent || ldw < M)) || (d_joint_fz && !w_glob))
+    return SNAG_ERR_ARG;
+  joint_fuse_bwd_kernel<<<dim3(static_cast<unsigned>((N + 7) / 8), M), 256, 0, st>>>(t, N, w_ent, ldw, w_glob, d_joint, d_joint_fz,
+                                                                                    ld_out, d_w_ent, d_w_glob);
   return static_cast<int>(cudaGetLastError());
 }
 

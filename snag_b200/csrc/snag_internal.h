@@ -6,6 +6,7 @@
 
 namespace snag {
 
+constexpr int SNAG_MAX_MODAL = 6;   // gph, rel, att, img, name, char (model/SNAG_tools.py:47)
 constexpr int KT_LIST = 16;   // candidate-list length of the CSLS top-k path (must equal KT in simgemm.cuh)
 #ifndef SNAG_EPI_WG
 #define SNAG_EPI_WG 2
@@ -36,6 +37,11 @@ int launch_rowblend_fwd(const float* e, const float* noise, const uint8_t* mask,
 int launch_rowblend_bwd(const float* g_out, const uint8_t* mask, float* g_in, long long N, int D, float a, cudaStream_t st);
 int launch_prep_bf16(const float* emb, long long ld, const long long* idx, int n, int D, int normalize,
                      __nv_bfloat16* out, int Dpad, float* norm2, cudaStream_t st);
+int launch_joint_fuse_fwd(const float* const* embs, const int* widths, int M, long long N, const float* w_ent, long long ldw,
+                          const float* w_glob, float* joint, float* joint_fz, long long ld_out, cudaStream_t st);
+int launch_joint_fuse_bwd(const float* const* embs, float* const* d_embs, const int* widths, int M, long long N,
+                          const float* w_ent, long long ldw, const float* w_glob, const float* d_joint, const float* d_joint_fz,
+                          long long ld_out, float* d_w_ent, float* d_w_glob, cudaStream_t st);
 int launch_normalize_bwd_scatter(const float* emb, long long ld, const long long* idx, int n, int D, int normalize,
                                  const float* dz, long long ld_dz, float* demb, long long ld_demb, cudaStream_t st);
 int launch_topk_merge_mean(const float* part, const int* part_idx, int n_lists, long long n_rows, int k, float* nv,

@@ -60,6 +60,61 @@ def prep_bf16(emb: torch.Tensor, idx: torch.Tensor | None = None, normalize: boo
     return out, norm2
 
 
+def _ptr_array(tensors):
+    import ctypes
+    arr = (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+    return arr
+
+
+def joint_fuse_fwd(embs, w_ent: torch.Tensor | None, w_glob: torch.Tensor | None, want_joint: bool = True,
+                   want_fz: bool = True):
+    """(joint, joint_fz) [N, sum d_m] of model/SNAG_tools.py:44-49 from the M modality tables (fp32 [N, d_m])."""
+    import ctypes
+    if not 1 <= len(embs) <= 6:
+        raise ValueError("1..6 modality tables")
+    for t in embs:
+        _need(t, torch.float32, "emb", 2)
+    N = embs[0].shape[0]
+    if any(t.shape[0] != N for t in embs):
+        raise ValueError("modality tables must have the same number of rows")
+    M = len(embs)
+    widths = (ctypes.c_int32 * M)(*[int(t.shape[1]) for t in embs])
+    tot = sum(int(t.shape[1]) for t in embs)
+    if want_joint:
+        _need(w_ent, torch.float32, "w_ent", 2)
+        if w_ent.shape[0] != N or w_ent.shape[1] < M:
+            raise ValueError("w_ent must be [N, >= M]")
+    if want_fz:
+        _need(w_glob, torch.float32, "w_glob", 1)
+        if w_glob.numel() < M:
+            raise ValueError("w_glob must have >= M entries")
+    joint = torch.empty((N, tot), dtype=torch.float32, device=embs[0].device) if want_joint else None
+    fz = torch.empty((N, tot), dtype=torch.float32, device=embs[0].device) if want_fz else None
+    call("snag_joint_fuse_fwd", _ptr_array(embs), widths, M, N, ptr(w_ent) if want_joint else None,
+         w_ent.stride(0) if want_joint else 0, ptr(w_glob) if want_fz else None, ptr(joint), ptr(fz), tot, current_stream())
+    return joint, fz
+
+
+def joint_fuse_bwd(embs, w_ent, w_glob, d_joint, d_fz):
+    """Gradients of joint_fuse_fwd: (list of d_emb [N, d_m], d_w_ent [N, w_ent.shape[1]] or None, d_w_glob [len] or None)."""
+    import ctypes
+    M, N = len(embs), embs[0].shape[0]
+    widths = (ctypes.c_int32 * M)(*[int(t.shape[1]) for t in embs])
+    tot = sum(int(t.shape[1]) for t in embs)
+    for g, nm in ((d_joint, "d_joint"), (d_fz, "d_joint_fz")):
+        if g is not None:
+            _need(g, torch.float32, nm, 2)
+            if tuple(g.shape) != (N, tot):
+                raise ValueError(f"{nm} must be [N, sum of widths]")
+    d_embs = [torch.empty_like(t) for t in embs]
+    d_w_ent = torch.zeros_like(w_ent) if d_joint is not None else None
+    d_w_glob = torch.zeros_like(w_glob) if d_fz is not None else None
+    call("snag_joint_fuse_bwd", _ptr_array(embs), _ptr_array(d_embs), widths, M, N,
+         ptr(w_ent) if d_joint is not None else None, w_ent.stride(0) if d_joint is not None else 0,
+         ptr(w_glob) if d_fz is not None else None, ptr(d_joint), ptr(d_fz), tot, ptr(d_w_ent), ptr(d_w_glob), current_stream())
+    return d_embs, d_w_ent, d_w_glob
+
+
 def normalize_bwd_scatter(emb: torch.Tensor, idx: torch.Tensor | None, dz: torch.Tensor, demb: torch.Tensor,
                           normalize: bool = True) -> None:
     """demb[idx[r]] += d/d emb[idx[r]] of F.normalize(emb[idx[r]]) . dz[r] — the backward of prep_bf16's gather +

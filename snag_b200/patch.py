@@ -22,7 +22,7 @@ import os
 import sys
 import types
 
-from . import evaluate, loss, mining, noise, runner
+from . import evaluate, fusion, loss, mining, noise, runner
 
 
 def patch(main_module: types.ModuleType | None = None) -> list[str]:
@@ -62,6 +62,8 @@ def patch(main_module: types.ModuleType | None = None) -> list[str]:
         ref_tools = importlib.import_module("model.SNAG_tools")
         ref_tools.MultiModalEncoder.forward = noise.encoder_forward
         done.append("model.SNAG_tools.MultiModalEncoder.forward")
+        ref_tools.MformerFusion.forward = fusion.MformerFusion_forward
+        done.append("model.SNAG_tools.MformerFusion.forward")
     except ImportError:
         pass
     main_mod = main_module or sys.modules.get("main")

@@ -214,3 +214,13 @@ def test_mining_host_logic_on_cpu_backend(name):
     assert mining.iter_new_links(left, right, emb, [], True, backend=oracle_backend) == [tuple(t) for t in fx["links_refresh"].tolist()]
     prev = [tuple(t) for t in fx["prev"].tolist()]
     assert mining.iter_new_links(left, right, emb, prev, False, backend=oracle_backend) == [tuple(t) for t in fx["links_filter"].tolist()]
+
+
+@pytest.mark.parametrize("name", golden_names("fusion_"))
+def test_joint_fuse_matches_reference(name):
+    """model/SNAG_tools.py:44-49 as run by the reference's own MformerFusion (gen_golden_fusion.py)."""
+    fx = load_golden(name)
+    M = int(fx["M"])
+    j, fz = oracle.joint_fuse([fx[f"emb{m}"] for m in range(M)], fx["weight_norm"], fx["weight_norm_fz"])
+    np.testing.assert_allclose(j, fx["joint"], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(fz, fx["joint_fz"], rtol=0, atol=1e-6)

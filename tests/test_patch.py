@@ -43,6 +43,8 @@ def test_signatures_match_reference():
     assert _sig(ref_snag.Iter_new_links) == _sig(mining.Iter_new_links)
     enc = importlib.import_module("model.SNAG_tools").MultiModalEncoder
     assert _sig(enc.forward) == _sig(noise.encoder_forward)
+    from snag_b200 import fusion
+    assert _sig(importlib.import_module("model.SNAG_tools").MformerFusion.forward) == _sig(fusion.MformerFusion_forward)
 
 
 @needs_ref
@@ -57,6 +59,8 @@ def test_patch_rebinds_reference_names(monkeypatch):
     snag_cls, enc_cls = mods["model.SNAG"].SNAG, mods["model.SNAG_tools"].MultiModalEncoder
     saved_cls = {k: getattr(snag_cls, k) for k in ("add_noise_to_embeddings", "get_mean_std", "update_noise", "Iter_new_links")}
     saved_fwd = enc_cls.forward
+    fus_cls = mods["model.SNAG_tools"].MformerFusion
+    saved_fus = fus_cls.forward
     fake_main = types.ModuleType("main")
     fake_main.Runner = type("Runner", (), {"_test": lambda self: None})
     try:
@@ -68,13 +72,16 @@ def test_patch_rebinds_reference_names(monkeypatch):
         from snag_b200 import mining
         assert snag_cls.Iter_new_links is mining.Iter_new_links
         assert fake_main.Runner._test is runner._test and fake_main.csls_sim is evaluate.csls_sim
-        assert len(done) >= 12
+        from snag_b200 import fusion
+        assert fus_cls.forward is fusion.MformerFusion_forward
+        assert len(done) >= 13
     finally:
         for (n, k), v in saved.items():
             setattr(mods[n], k, v)
         for k, v in saved_cls.items():
             setattr(snag_cls, k, v)
         enc_cls.forward = saved_fwd
+        fus_cls.forward = saved_fus
 
 
 class _Capture(logging.Handler):
