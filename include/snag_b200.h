@@ -104,6 +104,13 @@ int snag_normalize_bwd_scatter(const float* emb, int64_t ld, const int64_t* idx,
  * mode 0: out[i,j] = x_i.y_j. out is fp32 [n1, ld]. */
 int snag_sim_write(const uint16_t* X, const uint16_t* Y, const float* xn, const float* yn, int32_t n1, int32_t n2,
                    int32_t Dpad, int32_t mode, float* out, int64_t ld, void* stream);
+/* Transposed, split-K form for products whose contraction is long and whose X side is narrow (the loss's gradient
+ * GEMMs dA = G . [b ; a] with X = [b ; a]^T [D, 2B], Y = G [B, 2B]): out[s][j * ld + i] = sum over K slice s of
+ * X[i,:] . Y[j,:], s = 0 .. ksplits-1 (slices split_stride floats apart; the caller adds them up). ksplits must be
+ * the value snag_sim_write_t_splits(n1, n2, Dpad) returns (>= 1). */
+int snag_sim_write_t_splits(int32_t n1, int32_t n2, int32_t Dpad);
+int snag_sim_write_t(const uint16_t* X, const uint16_t* Y, int32_t n1, int32_t n2, int32_t Dpad, int32_t ksplits, float* out,
+                     int64_t ld, int64_t split_stride, void* stream);
 /* Measurement aid: the same TMA + tcgen05 sweep with the accumulators dropped (no epilogue, no output).
  * Times the mainloop alone so that bench.py can attribute a sweep's time to mainloop vs fused epilogue. */
 int snag_sim_mainloop_only(const uint16_t* X, const uint16_t* Y, int32_t n1, int32_t n2, int32_t Dpad, void* stream);

@@ -97,6 +97,11 @@ int snag_sim_write(const uint16_t* X, const uint16_t* Y, const float* xn, const 
                    int32_t Dpad, int32_t mode, float* out, int64_t ld, void* stream) {
   return launch_sim_write(BF(X), BF(Y), xn, yn, n1, n2, Dpad, mode, out, ld, S(stream));
 }
+int snag_sim_write_t_splits(int32_t n1, int32_t n2, int32_t Dpad) { return sim_write_t_splits(n1, n2, Dpad); }
+int snag_sim_write_t(const uint16_t* X, const uint16_t* Y, int32_t n1, int32_t n2, int32_t Dpad, int32_t ksplits, float* out,
+                     int64_t ld, int64_t split_stride, void* stream) {
+  return launch_sim_write_t(BF(X), BF(Y), n1, n2, Dpad, ksplits, out, ld, split_stride, S(stream));
+}
 int snag_eval_rowtopk(const uint16_t* X, const uint16_t* Y, const float* xn, const float* yn, int32_t n1, int32_t n2,
                       int32_t Dpad, float* part, int32_t* part_idx, void* stream) {
   return launch_eval_rowtopk(BF(X), BF(Y), xn, yn, n1, n2, Dpad, part, part_idx, S(stream));

@@ -104,7 +104,7 @@ void set_debug_counters(unsigned long long* p) { g_dbg_counters = p; }
 
 template <class Epi>
 static int launch_sim(const __nv_bfloat16* X, const __nv_bfloat16* Y, int n1, int n2, int Dpad,
-                      const typename Epi::Params& ep, cudaStream_t st) {
+                      const typename Epi::Params& ep, cudaStream_t st, int ksplits = 1) {
   if (!X || !Y) return SNAG_ERR_ARG;
   if (!device_is_sm100()) return SNAG_ERR_DEVICE;
   SimPlan pl;
@@ -126,8 +126,14 @@ static int launch_sim(const __nv_bfloat16* X, const __nv_bfloat16* Y, int n1, in
   shp.tiles_per_chunk = pl.tiles_per_chunk;
   shp.n_chunks = pl.n_chunks;
   shp.n_units = pl.n_units;
+  if (ksplits < 1 || ksplits > pl.kblocks) return SNAG_ERR_SHAPE;
+  shp.kb_split = (pl.kblocks + ksplits - 1) / ksplits;
+  shp.ksplits = (pl.kblocks + shp.kb_split - 1) / shp.kb_split;      // no empty slice
+  if (shp.ksplits != ksplits) return SNAG_ERR_SHAPE;                 // the caller sized its partial buffers for ksplits
+  if (static_cast<long long>(pl.n_units) * shp.ksplits > 0x7fffffffll) return SNAG_ERR_SHAPE;
   shp.dbg = g_dbg_counters;
-  const int grid = pl.n_units < num_sms() ? pl.n_units : num_sms();
+  const long long all_units = static_cast<long long>(pl.n_units) * shp.ksplits;
+  const int grid = all_units < num_sms() ? static_cast<int>(all_units) : num_sms();
   sim_kernel<Epi><<<grid, NUM_THREADS, SIM_SMEM_BYTES, st>>>(tmX, tmY, shp, ep);
   return static_cast<int>(cudaGetLastError());
 }
@@ -147,8 +153,40 @@ int launch_sim_write(const __nv_bfloat16* X, const __nv_bfloat16* Y, const float
                      int Dpad, int mode, float* out, long long ld, cudaStream_t st) {
   if (!out || ld < n2) return SNAG_ERR_ARG;
   if (mode == 1 && (!xn || !yn)) return SNAG_ERR_ARG;
-  EpiWrite::Params p{out, ld, xn, yn, mode};
+  EpiWrite::Params p{out, ld, xn, yn, mode, 0, 0};
   return launch_sim<EpiWrite>(X, Y, n1, n2, Dpad, p, st);
+}
+
+// number of K slices launch_sim_write_t will use for an [n1 x n2] product of contraction width Dpad: the smallest
+// count whose units fill the persistent grid's waves to >= 90 % (else the best filling), with slices of at least 24
+// k-blocks so that a unit's MMAs outweigh its pipeline fill and its 128 KB partial-tile write
+int sim_write_t_splits(int n1, int n2, int Dpad) {
+  SimPlan pl;
+  if (make_plan(n1, n2, Dpad, &pl)) return 1;
+  const int sms = num_sms();
+  const int max_ks = pl.kblocks / 24 > 1 ? pl.kblocks / 24 : 1;
+  int best = 1;
+  double best_eff = 0.0;
+  for (int ks = 1; ks <= max_ks && ks <= 64; ++ks) {
+    const int kb_split = (pl.kblocks + ks - 1) / ks;
+    if ((pl.kblocks + kb_split - 1) / kb_split != ks) continue;          // would leave an empty slice
+    const long long units = static_cast<long long>(pl.n_units) * ks;
+    const double eff = static_cast<double>(units) / (static_cast<double>((units + sms - 1) / sms) * sms);
+    if (eff > best_eff + 1e-9) { best_eff = eff; best = ks; }
+    if (eff >= 0.9) break;
+  }
+  return best;
+}
+
+// out_t[s][j][i] = sum over K slice s of X[i,:] . Y[j,:]  — the product written TRANSPOSED ([n2, ld] with ld >= n1), one
+// partial per K slice (split_stride floats apart). Used for the loss's gradient GEMMs, whose contraction runs over the
+// whole batch while the output is only D wide: with the D rows as X a tile's 256 columns are anchors, dL/dlogits is
+// read once (the row-block CTAs that share a column tile run side by side and meet in L2), and split-K fills the SMs.
+int launch_sim_write_t(const __nv_bfloat16* X, const __nv_bfloat16* Y, int n1, int n2, int Dpad, int ksplits, float* out,
+                       long long ld, long long split_stride, cudaStream_t st) {
+  if (!out || ld < n1 || ksplits < 1 || (ksplits > 1 && split_stride < static_cast<long long>(n2) * ld)) return SNAG_ERR_ARG;
+  EpiWrite::Params p{out, ld, nullptr, nullptr, 0, 1, split_stride};
+  return launch_sim<EpiWrite>(X, Y, n1, n2, Dpad, p, st, ksplits);
 }
 
 int launch_eval_rowtopk(const __nv_bfloat16* X, const __nv_bfloat16* Y, const float* xn, const float* yn, int n1, int n2,

@@ -53,6 +53,8 @@ struct SimShape {
   int tiles_per_chunk;
   int n_chunks;         // ceil(col_tiles / tiles_per_chunk)
   int n_units;          // row_blocks * n_chunks
+  int ksplits;          // split-K factor (1 for every epilogue that needs complete dot products); unit ids run over
+  int kb_split;         // [0, n_units * ksplits): split = id / n_units owns k-blocks [split*kb_split, +kb_split)
   unsigned long long* dbg;   // optional [2*gridDim.x][4] cycle counters (zeroed by the caller) or null. Row cta: UMMA issuer
                              // total, its wait for a free accumulator stage, sum over epilogue warps of strip time,
                              // tiles. Row gridDim.x + cta: sum over epilogue warps of commit + barrier time.
@@ -67,6 +69,7 @@ struct EpiCtx {
   int row;       // row index inside the X view
   bool row_ok;   // row < n_rows
   int rb, chunk; // unit coordinates
+  int split;     // split-K slice of the unit (0 when ksplits == 1)
   int useq;      // sequence number of the unit within this CTA (parity selects double-buffered per-unit scratch)
   float* scratch;  // EPI_SCRATCH_BYTES of shared memory private to the epilogue warpgroup
 };
@@ -157,12 +160,14 @@ sim_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
     // epilogue every instruction of this warp waits for an issue slot.
     const uint32_t leader = SNAG_CTRL_LEADER;
     uint32_t stage = 0, phase = 0;
-    for (int u = blockIdx.x; SNAG_CTRL_ENTER && u < shp.n_units; u += gridDim.x) {
+    for (int uid = blockIdx.x; SNAG_CTRL_ENTER && uid < shp.n_units * shp.ksplits; uid += gridDim.x) {
+      const int u = uid % shp.n_units, split = uid / shp.n_units;
       const int rb = u % shp.row_blocks, ch = u / shp.row_blocks;
       const int ct0 = ch * shp.tiles_per_chunk;
       const int ct1 = min(ct0 + shp.tiles_per_chunk, shp.col_tiles);
+      const int kb0 = split * shp.kb_split, kb1 = min(kb0 + shp.kb_split, shp.kblocks);
       for (int ct = ct0; ct < ct1; ++ct) {
-        for (int kb = 0; kb < shp.kblocks; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           if (leader) {
             mbar_expect_tx(full_bar(stage), STAGE_BYTES);
@@ -184,10 +189,12 @@ sim_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
     const bool dbg = shp.dbg != nullptr;
     long long w_acc = 0, n_tiles = 0;
     const long long t_begin = dbg ? clock64() : 0;
-    for (int u = blockIdx.x; SNAG_CTRL_ENTER && u < shp.n_units; u += gridDim.x) {
+    for (int uid = blockIdx.x; SNAG_CTRL_ENTER && uid < shp.n_units * shp.ksplits; uid += gridDim.x) {
+      const int u = uid % shp.n_units, split = uid / shp.n_units;
       const int ch = u / shp.row_blocks;
       const int ct0 = ch * shp.tiles_per_chunk;
       const int ct1 = min(ct0 + shp.tiles_per_chunk, shp.col_tiles);
+      const int n_kb = min(split * shp.kb_split + shp.kb_split, shp.kblocks) - split * shp.kb_split;
       for (int ct = ct0; ct < ct1; ++ct) {
         const long long tw = dbg ? clock64() : 0;
         mbar_wait(tempty_bar(as), aphase ^ 1);     // epilogue has drained this accumulator stage
@@ -198,7 +205,7 @@ sim_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
         // the epilogue skips the others
         const uint32_t idesc = make_idesc_bf16(BM, tile_strips(shp, ct) * 32);
         uint32_t accumulate = 0;
-        for (int kb = 0; kb < shp.kblocks; ++kb) {
+        for (int kb = 0; kb < n_kb; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           if (leader) {
@@ -239,7 +246,9 @@ sim_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
     cx.useq = -1;
     const bool dbg = shp.dbg != nullptr;
     long long c_proc = 0, c_bar = 0;
-    for (int u = blockIdx.x; u < shp.n_units; u += gridDim.x) {
+    for (int uid = blockIdx.x; uid < shp.n_units * shp.ksplits; uid += gridDim.x) {
+      const int u = uid % shp.n_units;
+      cx.split = uid / shp.n_units;
       ++cx.useq;
       cx.rb = u % shp.row_blocks;
       cx.chunk = u / shp.row_blocks;
@@ -407,6 +416,8 @@ struct EpiWrite {
     const float* xn;   // [n_rows]  (mode 1)
     const float* yn;   // [n_cols]  (mode 1)
     int mode;
+    int transposed;          // 1: out[col * ld + row] (mode 0 only) — a warp's 32 rows are 128 contiguous bytes per column
+    long long split_stride;  // split-K: slice s writes its partial products to out + s * split_stride
   };
   struct State {
     float xn;
@@ -427,11 +438,20 @@ struct EpiWrite {
   }
   static __device__ __forceinline__ void chunk(const Params& p, const SimShape& shp, const EpiCtx& cx, State& st,
                                                int ct, int c, const uint32_t (&r)[32], int buf) {
+    if (p.transposed) {
+      if (!cx.row_ok) return;
+      const int col0 = ct * BN + c * 32;
+      float* o = p.out + cx.split * p.split_stride + static_cast<long long>(col0) * p.ld + cx.row;
+#pragma unroll
+      for (int q = 0; q < 32; ++q)
+        if (col0 + q < shp.n_cols) o[static_cast<long long>(q) * p.ld] = __uint_as_float(r[q]);
+      return;
+    }
     if (strip_coalesced(p, shp, cx, st, ct, c, r, buf)) return;       // warp-uniform
     const float* yn_s = cx.scratch + buf * BN + c * 32;
     const int col0 = ct * BN + c * 32;
     if (!cx.row_ok) return;
-    float* orow = p.out + static_cast<long long>(cx.row) * p.ld + col0;
+    float* orow = p.out + cx.split * p.split_stride + static_cast<long long>(cx.row) * p.ld + col0;
     float v[32];
 #pragma unroll
     for (int q = 0; q < 32; ++q) {
@@ -453,11 +473,13 @@ struct EpiWrite {
   static __device__ __forceinline__ bool strip_coalesced(const Params& p, const SimShape& shp, const EpiCtx& cx, State& st,
                                                          int ct, int c, const uint32_t (&r)[32], int buf) {
     const int col0 = ct * BN + c * 32;
-    if (col0 + 32 > shp.n_cols || ((reinterpret_cast<uintptr_t>(p.out) | static_cast<uintptr_t>(p.ld * 4)) & 15)) return false;
+    if (col0 + 32 > shp.n_cols ||
+        ((reinterpret_cast<uintptr_t>(p.out) | static_cast<uintptr_t>(p.ld * 4) | static_cast<uintptr_t>(p.split_stride * 4)) & 15))
+      return false;
     const float* yn_s = cx.scratch + buf * BN + c * 32;
     const int row_w0 = cx.rb * BM + (cx.et & ~31);            // first row of this warp
     uint8_t* win = reinterpret_cast<uint8_t*>(cx.scratch + EPI_VEC_FLOATS) + (cx.tid >> 5) * 2048;
-    uint8_t* dst = reinterpret_cast<uint8_t*>(p.out + static_cast<long long>(row_w0) * p.ld + col0);
+    uint8_t* dst = reinterpret_cast<uint8_t*>(p.out + cx.split * p.split_stride + static_cast<long long>(row_w0) * p.ld + col0);
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       uint4 v[4];

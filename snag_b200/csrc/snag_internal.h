@@ -77,6 +77,9 @@ int launch_sim_loadonly(const __nv_bfloat16* X, const __nv_bfloat16* Y, int n1, 
                         int n_lds, int n_alu, int n_sts, cudaStream_t st);
 int launch_sim_write(const __nv_bfloat16* X, const __nv_bfloat16* Y, const float* xn, const float* yn, int n1, int n2,
                      int Dpad, int mode, float* out, long long ld, cudaStream_t st);
+int sim_write_t_splits(int n1, int n2, int Dpad);
+int launch_sim_write_t(const __nv_bfloat16* X, const __nv_bfloat16* Y, int n1, int n2, int Dpad, int ksplits, float* out,
+                       long long ld, long long split_stride, cudaStream_t st);
 int launch_eval_rowtopk(const __nv_bfloat16* X, const __nv_bfloat16* Y, const float* xn, const float* yn, int n1, int n2,
                         int Dpad, float* part, int* part_idx, cudaStream_t st);
 int launch_eval_rank(const __nv_bfloat16* X, const __nv_bfloat16* Y, const float* xn, const float* yn, const float* nv1,

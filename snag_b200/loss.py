@@ -158,8 +158,8 @@ class _IclPair(torch.autograd.Function):
         if shard.world == 1:
             Ga = be.icl_bwd_logits(S3[0:Bp], Ya, B, Bp, inv_tau, cra, crb, dg)         # [Bp, 2Bp] bf16
             Gb = be.icl_bwd_logits(S3[Bp:2 * Bp], Yb, B, Bp, inv_tau, crb, cra, dg)
-            be.normalize_bwd_scatter(emb, idx_l, be.contract(Ga, YaT, B, D), demb, nrm)      # dz [B, D] fp32 -> demb rows
-            be.normalize_bwd_scatter(emb, idx_r, be.contract(Gb, YbT, B, D), demb, nrm)
+            be.normalize_bwd_scatter(emb, idx_l, be.grad_contract(Ga, YaT, B, D), demb, nrm)      # dz [B, D] fp32 -> demb rows
+            be.normalize_bwd_scatter(emb, idx_r, be.grad_contract(Gb, YbT, B, D), demb, nrm)
             return demb, None, None, None, None, None
         # sharded: G rows of the owned anchors only. Row i of G already carries every term of dL/d(anchor i) —
         # its own softmax row and its appearances as a column in the other rows' softmaxes (the cc / cr_j terms of
@@ -170,8 +170,8 @@ class _IclPair(torch.autograd.Function):
             nx = r1 - r0
             Ga = be.icl_bwd_logits(S3[r0:r0 + nx], Ya, B, Bp, inv_tau, cra, crb, dg, r0, nx)
             Gb = be.icl_bwd_logits(S3[Bp + r0:Bp + r0 + nx], Yb, B, Bp, inv_tau, crb, cra, dg, r0, nx)
-            loc[0, :nx] = be.contract(Ga, YaT, nx, D)
-            loc[1, :nx] = be.contract(Gb, YbT, nx, D)
+            loc[0, :nx] = be.grad_contract(Ga, YaT, nx, D)
+            loc[1, :nx] = be.grad_contract(Gb, YbT, nx, D)
         if shard.grads == "gather":
             allg = shard.all_gather(loc).permute(1, 0, 2, 3).reshape(2, -1, D)[:, :B]   # [2, B, D]
             be.normalize_bwd_scatter(emb, idx_l, allg[0].contiguous(), demb, nrm)

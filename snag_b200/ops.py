@@ -507,6 +507,22 @@ def contract(P: torch.Tensor, Q: torch.Tensor, n1: int, n2: int) -> torch.Tensor
     return sim_write(P, Q, None, None, n1, n2, 0)
 
 
+def grad_contract(G: torch.Tensor, YT: torch.Tensor, n_rows: int, d: int) -> torch.Tensor:
+    """fp32 [n_rows, d] = G[:n_rows] . YT[:d]^T for bf16 G [>= n_rows, K] and YT [>= d, K] (K a multiple of 64): the
+    loss's gradient GEMMs dX = dL/dlogits . [other ; this]. Runs with the d rows of YT as the X operand, the output
+    written transposed and the long contraction split over the SMs (see snag_sim_write_t)."""
+    _check_operand(G, "G")
+    _check_operand(YT, "YT")
+    if G.shape[1] != YT.shape[1]:
+        raise ValueError("contraction widths differ")
+    k = G.shape[1]
+    ks = int(_lib.load().snag_sim_write_t_splits(d, n_rows, k))
+    part = torch.empty((ks, n_rows, d), dtype=torch.float32, device=G.device)
+    with _SweepTimer("sim_kernel<EpiWrite>", d, n_rows, k):
+        call("snag_sim_write_t", ptr(YT), ptr(G), d, n_rows, k, ks, ptr(part), d, n_rows * d, current_stream())
+    return part[0] if ks == 1 else part.sum(0)
+
+
 # ------------------------------------------------------------------------------------------------ noise
 def noise_mask(x: torch.Tensor, mean: torch.Tensor, std: torch.Tensor, noise_ratio: float, mask_ratio: float, *,
                out: torch.Tensor | None = None, mask: torch.Tensor | None = None, zsel: torch.Tensor | None = None,

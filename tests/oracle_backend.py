@@ -204,6 +204,10 @@ def contract(P, Q, n1, n2):
 
 
 # ------------------------------------------------------------------------------------------------ link mining
+def grad_contract(G, YT, n_rows, d):
+    return contract(G, YT, n_rows, d)
+
+
 def mutual_nn(X, Y, xn, yn, n1, n2, colb):
     """CPU stand-in for ops.mutual_nn: one list; columns only where the pre-filter admits their minimum (as the kernel)."""
     d = _c_matrix(X, Y, xn, yn, n1, n2)

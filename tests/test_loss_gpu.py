@@ -13,7 +13,7 @@ import torch
 import torch.nn.functional as F
 
 from oracle import oracle
-from snag_b200 import loss as sloss
+from snag_b200 import loss as sloss, ops
 from tests.conftest import golden_names, load_golden
 
 pytestmark = pytest.mark.gpu
@@ -215,3 +215,20 @@ def test_graphed_step_equals_eager(cuda_device):
         for t, a in zip(leaves, step.grads):        # hand the static gradient buffers back to the graph
             t.grad = a
         links.copy_(links.flip(0).roll(7, 0))       # next batch, in place
+
+
+@pytest.mark.parametrize("n_rows,d,k", [(1000, 300, 2048), (3500, 300, 7168), (130, 1800, 512), (4097, 96, 8192), (64, 17, 64)])
+def test_grad_contract_split_k(cuda_device, n_rows, d, k):
+    """The transposed split-K product used for the loss's gradient GEMMs against torch on the same bf16 operands."""
+    g = torch.Generator(device="cuda").manual_seed(n_rows + d)
+    G = (torch.randn((n_rows, k), generator=g, device=cuda_device) / 8).to(torch.bfloat16)
+    dpad = ops.round_up(d, 64)
+    YT = torch.zeros((dpad, k), dtype=torch.bfloat16, device=cuda_device)
+    YT[:d] = (torch.randn((d, k), generator=g, device=cuda_device) / 8).to(torch.bfloat16)
+    out = ops.grad_contract(G, YT, n_rows, d)
+    ref = G.float() @ YT[:d].float().t()
+    assert out.shape == (n_rows, d)
+    assert (out - ref).abs().max().item() < 2e-3 * max(1.0, ref.abs().max().item())
+    assert _relerr(out, ref) < 1e-5
+    old = ops.contract(G, YT, n_rows, d)
+    assert _relerr(out, old) < 1e-5
