@@ -186,6 +186,13 @@ __device__ __forceinline__ uint64_t make_sdesc_k128(uint32_t smem_addr) {
                :                                                                                                     \
                : "memory")
 
+// 256-bit global store (sm_100: STG.E.256): one full 32-byte sector per thread, 32-byte aligned address
+__device__ __forceinline__ void st_global_256(void* ptr, const uint4& a, const uint4& b) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w),
+               "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
+
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

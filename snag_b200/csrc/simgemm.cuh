@@ -76,6 +76,10 @@ struct EpiCtx {
 
 // Control warps (TMA producer, UMMA issuer): by default the whole warp walks the loop and one elected lane issues
 // (convergent code, uniform datapath). SNAG_CTRL_CONVERGED=0 builds the single-lane form for A/B measurements.
+// SNAG_PIPE_LD=1: software-pipelined TMEM read-out in the epilogue strip loop (A/B: scripts/build_variants.sh)
+#ifndef SNAG_PIPE_LD
+#define SNAG_PIPE_LD 0
+#endif
 #ifndef SNAG_CTRL_CONVERGED
 #define SNAG_CTRL_CONVERGED 1
 #endif
@@ -99,6 +103,13 @@ struct EpiPre {
   float a, b, c;
 };
 
+// number of epilogue warpgroups of a kernel instantiation: Epi::kWG when the epilogue asks for its own count (a
+// latency-bound epilogue with no per-row state wants more warps), else the build-wide NUM_EPI_WG
+template <class E, class = void>
+struct EpiWG { static constexpr int value = NUM_EPI_WG; };
+template <class E>
+struct EpiWG<E, std::void_t<decltype(E::kWG)>> { static constexpr int value = E::kWG; };
+
 // optional per-CTA hook run by the epilogue threads after their last unit: Epi::kernel_end(params, ctx)
 template <class E, class = void>
 struct HasKernelEnd : std::false_type {};
@@ -107,9 +118,13 @@ struct HasKernelEnd<E, decltype(E::kernel_end(std::declval<const typename E::Par
     : std::true_type {};
 
 template <class Epi>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(NUM_CTRL_THREADS + 128 * EpiWG<Epi>::value, 1)
 sim_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY, const SimShape shp,
            const typename Epi::Params ep) {
+  constexpr int kWG = EpiWG<Epi>::value;              // epilogue warpgroups of this instantiation
+  constexpr int kEpiThreads = 128 * kWG;
+  constexpr int kStripsPerWG = BN / 32 / kWG;
+  static_assert(BN % (32 * kWG) == 0 && kEpiThreads >= BN, "epilogue warpgroup count");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
@@ -130,7 +145,7 @@ sim_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
   // 8-16 busy epilogue warps or their (few, latency-critical) instructions wait behind the epilogue's.
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int cwarp = warp - NUM_EPI_THREADS / 32;     // 0 = TMA producer, 1 = UMMA issuer, 2 = TMEM allocator; < 0: epilogue
+  const int cwarp = warp - kEpiThreads / 32;         // 0 = TMA producer, 1 = UMMA issuer, 2 = TMEM allocator; < 0: epilogue
 
   if (cwarp == 0 && lane == 0) {
     tma_prefetch_desc(&tmX);
@@ -143,7 +158,7 @@ sim_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
     }
     for (int a = 0; a < ACC_STAGES; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), NUM_EPI_THREADS);
+      mbar_init(tempty_bar(a), kEpiThreads);
     }
     fence_mbar_init();
   }
@@ -253,7 +268,7 @@ sim_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
       cx.rb = u % shp.row_blocks;
       cx.chunk = u / shp.row_blocks;
       cx.row = cx.rb * BM + cx.et;
-      cx.list = cx.chunk * NUM_EPI_WG + cx.wg;
+      cx.list = cx.chunk * kWG + cx.wg;
       cx.row_ok = cx.row < shp.n_rows;
       const int ct0 = cx.chunk * shp.tiles_per_chunk;
       const int ct1 = min(ct0 + shp.tiles_per_chunk, shp.col_tiles);
@@ -267,7 +282,7 @@ sim_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
         const int buf = tile_seq & 1;
         long long t0 = dbg ? clock64() : 0;
         Epi::tile_commit(ep, shp, cx, st, pre, ct, buf);
-        named_bar_sync(1, NUM_EPI_THREADS);
+        named_bar_sync(1, kEpiThreads);
         if (dbg) c_bar += clock64() - t0;
         if (ct + 1 < ct1) pre = Epi::tile_prefetch(ep, shp, cx, ct + 1);
         mbar_wait(tfull_bar(as), aphase);
@@ -277,14 +292,33 @@ sim_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
         // Rolled on purpose: one copy of the strip body keeps the epilogue inside the instruction cache
         // (a fully unrolled tile body was ~150 KB of SASS and ran instruction-fetch bound).
         if constexpr (!Epi::kNoLoad) {
-          const int c_end = min((cx.wg + 1) * STRIPS_PER_WG, tile_strips(shp, ct));
+          const int c_beg = cx.wg * kStripsPerWG;
+          const int c_end = min((cx.wg + 1) * kStripsPerWG, tile_strips(shp, ct));
+#if SNAG_PIPE_LD
+          // two strips in flight: the TMEM read of strip c+1 is issued before strip c is consumed, so its latency
+          // hides behind the epilogue arithmetic (two copies of the strip body, still well inside the i-cache)
+          uint32_t r0[32], r1[32];
+          if (c_beg < c_end) SNAG_TMEM_LD32(taddr + c_beg * 32, r0);
 #pragma unroll 1
-          for (int c = cx.wg * STRIPS_PER_WG; c < c_end; ++c) {
+          for (int c = c_beg; c < c_end; c += 2) {
+            SNAG_TMEM_WAIT32(r0);
+            if (c + 1 < c_end) SNAG_TMEM_LD32(taddr + (c + 1) * 32, r1);
+            Epi::chunk(ep, shp, cx, st, ct, c, r0, buf);
+            if (c + 1 < c_end) {
+              SNAG_TMEM_WAIT32(r1);
+              if (c + 2 < c_end) SNAG_TMEM_LD32(taddr + (c + 2) * 32, r0);
+              Epi::chunk(ep, shp, cx, st, ct, c + 1, r1, buf);
+            }
+          }
+#else
+#pragma unroll 1
+          for (int c = c_beg; c < c_end; ++c) {
             uint32_t r[32];
             SNAG_TMEM_LD32(taddr + c * 32, r);
             SNAG_TMEM_WAIT32(r);
             Epi::chunk(ep, shp, cx, st, ct, c, r, buf);
           }
+#endif
         }
         tc_fence_before();
         mbar_arrive(tempty_bar(as));
@@ -401,6 +435,22 @@ __device__ __forceinline__ void warp_store_rows64(uint8_t* win, int lane, const 
   for (int i = 0; i < 4; ++i) {
     const int row = (lane >> 2) + 8 * i;
     const uint4 t = *reinterpret_cast<const uint4*>(win + row * 64 + 16 * (piece ^ ((row >> 1) & 3)));
+    if (row < rows_ok) *reinterpret_cast<uint4*>(dst + row * row_stride_bytes + 16 * piece) = t;
+  }
+}
+// the same for 32 rows x 32 bytes through a 1 KB window: every store instruction covers 16 rows x one full sector
+__device__ __forceinline__ void warp_store_rows32(uint8_t* win, int lane, const uint4 (&v)[2], uint8_t* dst,
+                                                  long long row_stride_bytes, int rows_ok) {
+  __syncwarp();
+#pragma unroll
+  for (int k = 0; k < 2; ++k)
+    *reinterpret_cast<uint4*>(win + lane * 32 + 16 * (k ^ ((lane >> 2) & 1))) = v[k];
+  __syncwarp();
+  const int piece = lane & 1;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int row = (lane >> 1) + 16 * i;
+    const uint4 t = *reinterpret_cast<const uint4*>(win + row * 32 + 16 * (piece ^ ((row >> 2) & 1)));
     if (row < rows_ok) *reinterpret_cast<uint4*>(dst + row * row_stride_bytes + 16 * piece) = t;
   }
 }
@@ -1273,8 +1323,15 @@ struct EpiIclFwd {
 // dg_i = g_this[i] + g_other[i]. Anchors >= B and columns in the padding are written as zeros. As in the forward the
 // X view is rows [row0, row0 + nx) of this side; cr / cc / dg are indexed by batch index, G by local row.
 // ------------------------------------------------------------------------------------------------
+#ifndef SNAG_ICLBWD_WG
+#define SNAG_ICLBWD_WG 4
+#endif
 struct EpiIclBwd {
   static constexpr bool kNoLoad = false;
+  // ncu (profiles/r01c): with 2 warpgroups this epilogue keeps the tensor pipe 40 % busy at D = 300 and issues on 32 %
+  // of the cycles — 2 warps per scheduler cannot hide the TMEM-read -> exp -> pack -> shared -> global chain. It keeps
+  // no per-row state across tiles, so it simply runs with 4 warpgroups (2 column strips each).
+  static constexpr int kWG = SNAG_ICLBWD_WG;
   struct Params {
     float scale_log2;     // log2(e) / tau
     float inv_tau;
@@ -1312,52 +1369,65 @@ struct EpiIclBwd {
                                                      const EpiPre& pre, int, int buf) {
     if (cx.tid < BN) cx.scratch[buf * BN + cx.tid] = pre.a;
   }
-  static __device__ __forceinline__ void chunk(const Params& p, const SimShape&, const EpiCtx& cx, State& st, int ct,
-                                               int c, const uint32_t (&r)[32], int buf) {
-    const float* cc_s = cx.scratch + buf * BN + c * 32;
-    const int col0 = ct * BN + c * 32;
-    const int part = col0 >= p.Bp ? 1 : 0;
-    const int idx0 = col0 - part * p.Bp;
+  // 16 consecutive elements of the strip (q0 = 0 or 16) -> 8 packed bf16 pairs
+  static __device__ __forceinline__ void half_strip(const Params& p, const State& st, const float* cc_s, const uint32_t (&r)[32],
+                                                    int q0, int idx0, int part, bool plain, uint32_t (&packed)[8]) {
     const float nb = -p.scale_log2;
-    const int gr0 = p.row0 + cx.rb * BM;                 // batch index of the row block's first anchor
-    // plain strip (CTA-uniform): every anchor of the row block and every column of the strip is valid and the strip
-    // does not meet the block's diagonal -> 4 arithmetic instructions per element (FFMA, MUFU.EX2, FADD, FMUL)
-    const bool plain = (gr0 + BM <= p.B) && ((cx.rb + 1) * BM <= p.nx) && (idx0 + 32 <= p.B) &&
-                       (idx0 + 31 < gr0 || idx0 > gr0 + BM - 1);
-    uint32_t packed[16];
+    float cc[16];                                        // four 16-byte broadcast loads (not sixteen scalar ones)
+#pragma unroll
+    for (int q = 0; q < 16; q += 4) {
+      const float4 t = *reinterpret_cast<const float4*>(cc_s + q0 + q);
+      cc[q] = t.x; cc[q + 1] = t.y; cc[q + 2] = t.z; cc[q + 3] = t.w;
+    }
     if (plain) {
 #pragma unroll
-      for (int q = 0; q < 32; q += 2) {
-        const float e0 = ex2_approx(__fmaf_rn(__uint_as_float(r[q]), p.scale_log2, nb));
-        const float e1 = ex2_approx(__fmaf_rn(__uint_as_float(r[q + 1]), p.scale_log2, nb));
-        const __nv_bfloat162 h = __floats2bfloat162_rn((st.cr + cc_s[q]) * e0, (st.cr + cc_s[q + 1]) * e1);
+      for (int q = 0; q < 16; q += 2) {
+        const float e0 = ex2_approx(__fmaf_rn(__uint_as_float(r[q0 + q]), p.scale_log2, nb));
+        const float e1 = ex2_approx(__fmaf_rn(__uint_as_float(r[q0 + q + 1]), p.scale_log2, nb));
+        const __nv_bfloat162 h = __floats2bfloat162_rn((st.cr + cc[q]) * e0, (st.cr + cc[q + 1]) * e1);
         packed[q / 2] = *reinterpret_cast<const uint32_t*>(&h);
       }
     } else {
-      const bool row_ok = st.ok;
 #pragma unroll
-      for (int q = 0; q < 32; q += 2) {
+      for (int q = 0; q < 16; q += 2) {
         float v[2];
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-          const int idx = idx0 + q + e;
-          const float E = ex2_approx(__fmaf_rn(__uint_as_float(r[q + e]), p.scale_log2, nb));
-          float gval = (st.cr + cc_s[q + e]) * E;
+          const int idx = idx0 + q0 + q + e;
+          const float E = ex2_approx(__fmaf_rn(__uint_as_float(r[q0 + q + e]), p.scale_log2, nb));
+          float gval = (st.cr + cc[q + e]) * E;
           if (idx == st.gr) gval = part ? 0.f : gval - st.dg;
-          if (!row_ok || idx >= p.B) gval = 0.f;
+          if (!st.ok || idx >= p.B) gval = 0.f;
           v[e] = gval;
         }
         const __nv_bfloat162 h = __floats2bfloat162_rn(v[0], v[1]);
         packed[q / 2] = *reinterpret_cast<const uint32_t*>(&h);
       }
     }
-    uint4 v[4];
+  }
+  static __device__ __forceinline__ void chunk(const Params& p, const SimShape&, const EpiCtx& cx, State& st, int ct,
+                                               int c, const uint32_t (&r)[32], int buf) {
+    const float* cc_s = cx.scratch + buf * BN + c * 32;
+    const int col0 = ct * BN + c * 32;
+    const int part = col0 >= p.Bp ? 1 : 0;
+    const int idx0 = col0 - part * p.Bp;
+    const int gr0 = p.row0 + cx.rb * BM;                 // batch index of the row block's first anchor
+    // plain strip (CTA-uniform): every anchor of the row block and every column of the strip is valid and the strip
+    // does not meet the block's diagonal -> 4 arithmetic instructions per element (FFMA, MUFU.EX2, FADD, FMUL)
+    const bool plain = (gr0 + BM <= p.B) && ((cx.rb + 1) * BM <= p.nx) && (idx0 + 32 <= p.B) &&
+                       (idx0 + 31 < gr0 || idx0 > gr0 + BM - 1);
+    // Each thread owns one row of G: its 64 bytes of the strip leave as two 256-bit stores, i.e. two full 32-byte
+    // sectors (16-byte stores left every sector half written by two instructions and ran at 1.4 TB/s; a shared-memory
+    // transposition to 64-byte row segments fixed that but cost as many shared-memory wavefronts as the UMMA operand
+    // reads leave free — ncu, profiles/r01c_summary.md).
+    uint8_t* dst = reinterpret_cast<uint8_t*>(p.G + static_cast<long long>(cx.row) * (2 * p.Bp) + col0);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) v[q] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
-    const int row_w0 = cx.rb * BM + (cx.et & ~31);              // first row of this warp
-    uint8_t* win = reinterpret_cast<uint8_t*>(cx.scratch + EPI_VEC_FLOATS) + (cx.tid >> 5) * 2048;
-    uint8_t* dst = reinterpret_cast<uint8_t*>(p.G + static_cast<long long>(row_w0) * (2 * p.Bp) + col0);
-    warp_store_rows64(win, cx.lane, v, dst, 4ll * p.Bp, p.nx - row_w0);
+    for (int h = 0; h < 2; ++h) {
+      uint32_t pk[8];
+      half_strip(p, st, cc_s, r, 16 * h, idx0, part, plain, pk);
+      if (cx.row_ok)
+        st_global_256(dst + 32 * h, make_uint4(pk[0], pk[1], pk[2], pk[3]), make_uint4(pk[4], pk[5], pk[6], pk[7]));
+    }
   }
   static __device__ __forceinline__ void tile_end(const Params&, const SimShape&, const EpiCtx&, State&, int, int) {}
   static __device__ __forceinline__ void unit_end(const Params&, const SimShape&, const EpiCtx&, State&) {}
