@@ -419,42 +419,6 @@ struct EpiLoadOnly {
   }
 };
 
-// Coalesced store of a warp's 32 rows x 64 bytes (thread t holds row t as four 16-byte pieces): staged through a 2 KB
-// shared-memory window private to the warp (XOR-swizzled, conflict-free both ways) and written back so that every
-// store instruction covers 8 rows x 64 contiguous bytes (full 32-byte sectors) instead of 32 rows x 16 bytes.
-// dst = address of row 0's 64 bytes; rows_ok = number of leading rows of the warp that may be written.
-__device__ __forceinline__ void warp_store_rows64(uint8_t* win, int lane, const uint4 (&v)[4], uint8_t* dst,
-                                                  long long row_stride_bytes, int rows_ok) {
-  __syncwarp();                                       // the previous use of the window has been read back
-#pragma unroll
-  for (int k = 0; k < 4; ++k)
-    *reinterpret_cast<uint4*>(win + lane * 64 + 16 * (k ^ ((lane >> 1) & 3))) = v[k];
-  __syncwarp();
-  const int piece = lane & 3;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int row = (lane >> 2) + 8 * i;
-    const uint4 t = *reinterpret_cast<const uint4*>(win + row * 64 + 16 * (piece ^ ((row >> 1) & 3)));
-    if (row < rows_ok) *reinterpret_cast<uint4*>(dst + row * row_stride_bytes + 16 * piece) = t;
-  }
-}
-// the same for 32 rows x 32 bytes through a 1 KB window: every store instruction covers 16 rows x one full sector
-__device__ __forceinline__ void warp_store_rows32(uint8_t* win, int lane, const uint4 (&v)[2], uint8_t* dst,
-                                                  long long row_stride_bytes, int rows_ok) {
-  __syncwarp();
-#pragma unroll
-  for (int k = 0; k < 2; ++k)
-    *reinterpret_cast<uint4*>(win + lane * 32 + 16 * (k ^ ((lane >> 2) & 1))) = v[k];
-  __syncwarp();
-  const int piece = lane & 1;
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const int row = (lane >> 1) + 16 * i;
-    const uint4 t = *reinterpret_cast<const uint4*>(win + row * 32 + 16 * (piece ^ ((row >> 2) & 1)));
-    if (row < rows_ok) *reinterpret_cast<uint4*>(dst + row * row_stride_bytes + 16 * piece) = t;
-  }
-}
-
 // ------------------------------------------------------------------------------------------------
 // Epilogue: write S (mode 0) or the squared-L2 distance (mode 1) — drop-in pairwise_distances
 // ------------------------------------------------------------------------------------------------
@@ -519,32 +483,26 @@ struct EpiWrite {
         if (col0 + q < shp.n_cols) orow[q] = v[q];
     }
   }
-  // full strips of 16-byte aligned outputs go through the coalescing window, two 64-byte halves per row
+  // full strips of 32-byte aligned outputs: the thread's 128 bytes of the row leave as four 256-bit stores (full sectors)
   static __device__ __forceinline__ bool strip_coalesced(const Params& p, const SimShape& shp, const EpiCtx& cx, State& st,
                                                          int ct, int c, const uint32_t (&r)[32], int buf) {
     const int col0 = ct * BN + c * 32;
     if (col0 + 32 > shp.n_cols ||
-        ((reinterpret_cast<uintptr_t>(p.out) | static_cast<uintptr_t>(p.ld * 4) | static_cast<uintptr_t>(p.split_stride * 4)) & 15))
+        ((reinterpret_cast<uintptr_t>(p.out) | static_cast<uintptr_t>(p.ld * 4) | static_cast<uintptr_t>(p.split_stride * 4)) & 31))
       return false;
+    if (!cx.row_ok) return true;
     const float* yn_s = cx.scratch + buf * BN + c * 32;
-    const int row_w0 = cx.rb * BM + (cx.et & ~31);            // first row of this warp
-    uint8_t* win = reinterpret_cast<uint8_t*>(cx.scratch + EPI_VEC_FLOATS) + (cx.tid >> 5) * 2048;
-    uint8_t* dst = reinterpret_cast<uint8_t*>(p.out + cx.split * p.split_stride + static_cast<long long>(row_w0) * p.ld + col0);
+    uint8_t* dst = reinterpret_cast<uint8_t*>(p.out + cx.split * p.split_stride + static_cast<long long>(cx.row) * p.ld + col0);
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      uint4 v[4];
+    for (int h = 0; h < 4; ++h) {
+      uint32_t w[8];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        float f[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int q = 16 * h + 4 * k + e;
-          const float sv = __uint_as_float(r[q]);
-          f[e] = (p.mode == 1) ? sqdist_from_dot(sv, st.xn, yn_s[q]) : sv;
-        }
-        v[k] = make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
+      for (int e = 0; e < 8; ++e) {
+        const int q = 8 * h + e;
+        const float sv = __uint_as_float(r[q]);
+        w[e] = __float_as_uint((p.mode == 1) ? sqdist_from_dot(sv, st.xn, yn_s[q]) : sv);
       }
-      warp_store_rows64(win, cx.lane, v, dst + 64 * h, p.ld * 4, shp.n_rows - row_w0);
+      st_global_256(dst + 32 * h, make_uint4(w[0], w[1], w[2], w[3]), make_uint4(w[4], w[5], w[6], w[7]));
     }
     return true;
   }
