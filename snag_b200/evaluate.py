@@ -281,6 +281,12 @@ def align_ranks(X: torch.Tensor, Y: torch.Tensor, xn: torch.Tensor, yn: torch.Te
     if use_csls and csls_k > n:
         # torch.topk raises in the reference (src/utils.py:431) when k exceeds the matrix side
         raise ValueError(f"csls_k={csls_k} exceeds the number of evaluated pairs n={n}")
+    # The s-space pre-filter margins inside the sweeps are derived for unit rows (what main.py:379's F.normalize
+    # produces; the re-score tolerances scale with the norms, the in-kernel margins do not): refuse rows that are far
+    # from that instead of silently weakening the guarantee. Squared norms up to 8 are let through for small exact
+    # (dyadic) test inputs.
+    if float(torch.maximum(xn[:n].max(), yn[:n].max()).item()) > 8.0:
+        raise SnagError("align_ranks expects L2-normalised rows (evaluate_alignment(normalize=True))")
     be = _cuda_ops if backend is None else backend
     if group is None:
         world, rank = 1, 0

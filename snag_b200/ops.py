@@ -324,7 +324,7 @@ def topk_rescore(A, B, an, bn, cand_idx: torch.Tensor, cand_val: torch.Tensor, k
     flagged = torch.empty((cap,), dtype=torch.int32, device=dev)
     fcnt = torch.zeros((1,), dtype=torch.int32, device=dev)
     call("snag_topk_rescore", ptr(A), ptr(B), A.shape[1], n_rows, ptr(an), ptr(bn), ptr(cand_idx), ptr(cand_val), k,
-         TOPK_VERIFY_DELTA, ptr(nv), ptr(flagged), ptr(fcnt), cap, st)
+         TOPK_VERIFY_DELTA * _error_scale(an, bn, A.shape[1]), ptr(nv), ptr(flagged), ptr(fcnt), cap, st)
     n_flag = int(fcnt.item())
     info = {"flagged": n_flag, "unverified": 0}
     if n_flag:
@@ -352,6 +352,13 @@ def pair_score(X, Y, n: int, xn, yn, nv1, nv2, use_csls: bool, want_dot: bool = 
 # tests/test_eval_gpu.py::test_tensor_core_dot_error pins it), (b) the roundings of the reference's fp32 chain
 # (< 1e-6 in distance = 2.5e-7 in s) and (c) the roundings of the per-row / per-column thresholds (< 3e-7).
 RANK_BAND_EPS = 4e-6
+
+
+def _error_scale(xn: torch.Tensor, yn: torch.Tensor, dpad: int) -> float:
+    """Factor by which the tensor-core dot error can exceed the unit-row, D <= 2048 case RANK_BAND_EPS is pinned on:
+    it grows with the operands' norms (||x|| ||y||) and with the square root of the contraction width."""
+    norm = float(torch.sqrt(xn.max() * yn.max()).item())
+    return max(1.0, norm) * max(1.0, (dpad / 2048.0) ** 0.5)
 RANK_BAND_MIN_CAP = 1 << 20
 RANK_BAND_PER_ROW = 16         # initial list capacity per evaluated row + column
 
@@ -374,6 +381,7 @@ def eval_rank(X, Y, xn, yn, nv1, nv2, g_row, g_col, row_gid0: int, col_gid0: int
         t3i = torch.empty((nch, n1, 4), dtype=torch.int32, device=X.device)
     st = current_stream()
     if not exact_chain:
+        eps = RANK_BAND_EPS * _error_scale(xn, yn, X.shape[1])
         cap = max(RANK_BAND_MIN_CAP, RANK_BAND_PER_ROW * (n1 + n2))
         row_save = col_save = None
         while cap <= (1 << 28):
@@ -383,12 +391,12 @@ def eval_rank(X, Y, xn, yn, nv1, nv2, g_row, g_col, row_gid0: int, col_gid0: int
                 row_save, col_save = cnt_row.clone(), cnt_col.clone()
             with _SweepTimer("sim_kernel<EpiRank>", n1, n2):
                 call("snag_eval_rank_band", ptr(X), ptr(Y), ptr(xn), ptr(yn), ptr(nv1), ptr(nv2), ptr(g_row), ptr(g_col),
-                     row_gid0, col_gid0, n1, n2, X.shape[1], int(use_csls), RANK_BAND_EPS, ptr(cnt_row), ptr(cnt_col),
+                     row_gid0, col_gid0, n1, n2, X.shape[1], int(use_csls), eps, ptr(cnt_row), ptr(cnt_col),
                      ptr(t3v), ptr(t3i), ptr(band), ptr(band_cnt), cap, st)
             call("snag_band_rescore", ptr(X), ptr(Y), X.shape[1], ptr(xn), ptr(yn), ptr(nv1), ptr(nv2), ptr(g_row),
                  ptr(g_col), row_gid0, col_gid0, int(use_csls), ptr(band), ptr(band_cnt), cap, ptr(cnt_row), ptr(cnt_col), st)
             deferred = int(band_cnt.item()) & 0xFFFFFFFF
-            LAST_RANK_INFO.update(deferred=deferred, cap=cap, mode="band")
+            LAST_RANK_INFO.update(deferred=deferred, cap=cap, mode="band", eps=eps)
             if deferred <= cap:
                 return t3v, t3i
             cnt_row.copy_(row_save)          # the list overflowed: undo the partial counts and retry
