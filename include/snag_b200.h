@@ -170,10 +170,12 @@ int snag_topk_merge_mean(const float* part, const int32_t* part_idx, int32_t n_l
  * of B for each flagged row. */
 int snag_topk_rescore(const uint16_t* A, const uint16_t* B, int32_t Dpad, int64_t n_rows, const float* an, const float* bn,
                       const int32_t* cand_idx, const float* cand_val, int32_t k, float delta, float* nv, int32_t* flagged,
-                      int32_t* flagged_cnt, int32_t flagged_cap, void* stream);
+                      int32_t* flagged_cnt, int32_t flagged_cap, float* best_d, int32_t* best_idx, void* stream);
 int snag_topk_exhaustive(const uint16_t* A, const uint16_t* B, int32_t Dpad, int64_t n_b, const float* an, const float* bn,
                          const int32_t* flagged, const int32_t* flagged_cnt, int32_t flagged_cap, int32_t k, float* nv,
-                         void* stream);
+                         float* best_d, int32_t* best_idx, void* stream);
+/* best_d / best_idx (both NULL or fp32 / int32 [n_rows]): the nearest row of B for every row of A under the canonical
+ * squared distance clamp((an + bn) - 2 s, 0), lowest index on ties (torch.argmin) — link mining, model/SNAG.py:199-200. */
 /* ground-truth scores g[p] = distance of pair (x_p, y_p): CSLS distance 1 - ((2(1-d) - nv1_p) - nv2_p) if
  * use_csls else d; dot product accumulated in fp64 in index order. s_out (may be NULL) gets x_p.y_p. */
 int snag_pair_score(const uint16_t* X, const uint16_t* Y, int32_t Dpad, int64_t n, const float* xn, const float* yn,

@@ -22,7 +22,7 @@ sys.path.insert(0, ROOT)
 import numpy as np
 import torch
 
-from snag_b200 import evaluate, fusion, mining, noise, ops
+from snag_b200 import evaluate, fusion, loss, mining, noise, ops
 
 
 def peaks():
@@ -194,8 +194,33 @@ def main():
         return torch.argmin(d, dim=1), torch.argmin(d.t(), dim=1)
     flops = 2.0 * n_l * n_r * D
     rec_ms = ms
-    emit("f1", f"mutual_nearest[{n_l} x {n_r}, D={D}] (pre-pass + fused argmin sweep)", 4 * n_l * n_r, rec_ms, cpu_time(ref_mine, 2),
+    emit("f1", f"mutual_nearest[{n_l} x {n_r}, D={D}] (two top-k sweeps + canonical re-score of the candidates)", 4 * n_l * n_r, rec_ms, cpu_time(ref_mine, 2),
          f"tensor-pipe bound, not HBM: {flops / rec_ms / 1e9:.0f} TFLOP/s algorithmic; bytes = the distance matrix the reference materialises")
+    del xl, yr
+    # ------------------------------------------------------------------ a5 / a6 one loss call fwd+bwd (SNAG_loss.py:58-128, 148-202)
+    B = 3500
+    links = torch.stack([torch.randperm(N // 2, generator=g, device="cuda")[:B],
+                         N // 2 + torch.randperm(N // 2, generator=g, device="cuda")[:B]], 1)
+    src_emb = torch.randn((N, 300), generator=g, device="cuda", requires_grad=True)
+    tar_emb = torch.randn((N, D), generator=g, device="cuda")
+    icl = loss.icl_loss(tau=0.1, ab_weight=0.5, n_view=2)
+    ial = loss.ial_loss(tau=4.0, ab_weight=0.5, zoom=0.1, reduction="mean")
+
+    def run_icl():
+        src_emb.grad = None
+        icl(src_emb, links).backward()
+
+    def run_ial():
+        src_emb.grad = None
+        ial(src_emb, tar_emb, links).backward()
+    ms = gpu_time(run_icl, reps=5)
+    fl = (8 + 16) * B * B * 300.0
+    emit("a5", f"icl_loss fwd+bwd[B={B}, D=300]", fl, ms, None,
+         f"tensor-pipe bound: 24*B^2*D flop executed -> {fl / ms / 1e9:.0f} TFLOP/s incl. gather/normalise/scatter glue; 'bytes' column = flop")
+    ms = gpu_time(run_ial, reps=5)
+    fl = 12.0 * B * B * (300 + D) / 2 * 3
+    emit("a6", f"ial_loss fwd+bwd[B={B}, src D=300, tar D={D}]", fl, ms, None,
+         f"materialising variant: 8 contractions fwd (fp32 [B,B] each) + torch softmax/KL on [B,2B] + autograd; ~{fl / ms / 1e9:.0f} TFLOP/s; 'bytes' column = flop")
     out = os.path.join(ROOT, "gpurun_out", f"rows_{args.shape}.jsonl")
     os.makedirs(os.path.dirname(out), exist_ok=True)
     with open(out, "w") as f:

@@ -112,14 +112,15 @@ int snag_topk_merge_mean(const float* part, const int32_t* part_idx, int32_t n_l
 }
 int snag_topk_rescore(const uint16_t* A, const uint16_t* B, int32_t Dpad, int64_t n_rows, const float* an, const float* bn,
                       const int32_t* cand_idx, const float* cand_val, int32_t k, float delta, float* nv, int32_t* flagged,
-                      int32_t* flagged_cnt, int32_t flagged_cap, void* stream) {
+                      int32_t* flagged_cnt, int32_t flagged_cap, float* best_d, int32_t* best_idx, void* stream) {
   return launch_topk_rescore(BF(A), BF(B), Dpad, n_rows, an, bn, cand_idx, cand_val, k, delta, nv, flagged, flagged_cnt,
-                             flagged_cap, S(stream));
+                             flagged_cap, best_d, best_idx, S(stream));
 }
 int snag_topk_exhaustive(const uint16_t* A, const uint16_t* B, int32_t Dpad, int64_t n_b, const float* an, const float* bn,
                          const int32_t* flagged, const int32_t* flagged_cnt, int32_t flagged_cap, int32_t k, float* nv,
-                         void* stream) {
-  return launch_topk_exhaustive(BF(A), BF(B), Dpad, n_b, an, bn, flagged, flagged_cnt, flagged_cap, k, nv, S(stream));
+                         float* best_d, int32_t* best_idx, void* stream) {
+  return launch_topk_exhaustive(BF(A), BF(B), Dpad, n_b, an, bn, flagged, flagged_cnt, flagged_cap, k, nv, best_d, best_idx,
+                                S(stream));
 }
 int snag_pair_score(const uint16_t* X, const uint16_t* Y, int32_t Dpad, int64_t n, const float* xn, const float* yn,
                     const float* nv1, const float* nv2, int32_t use_csls, float* g, float* s_out, void* stream) {

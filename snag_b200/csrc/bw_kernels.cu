@@ -531,7 +531,8 @@ __global__ void __launch_bounds__(128) topk_rescore_kernel(const __nv_bfloat16* 
                                                            const float* __restrict__ bn, const int* __restrict__ cand_idx,
                                                            const float* __restrict__ cand_val, int k, float delta,
                                                            float* __restrict__ nv, int* __restrict__ flagged,
-                                                           int* __restrict__ flagged_cnt, int flagged_cap) {
+                                                           int* __restrict__ flagged_cnt, int flagged_cap,
+                                                           float* __restrict__ best_d, int* __restrict__ best_idx) {
   const long long gt = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   const long long row = gt >> 4;
   const int sub = threadIdx.x & 15;
@@ -539,23 +540,30 @@ __global__ void __launch_bounds__(128) topk_rescore_kernel(const __nv_bfloat16* 
   const long long r = live ? row : n_rows - 1;
   const int id = cand_idx[r * KT_LIST + sub];
   const float tc = cand_val[r * KT_LIST + sub];
-  float c = -INFINITY;
+  float c = -INFINITY, d = INFINITY;
   if (id >= 0) {
     const float s = canonical_dot(A + r * Dpad, B + static_cast<long long>(id) * Dpad, Dpad);
-    const float d = fmaxf(__fmaf_rn(-2.0f, s, __fadd_rn(an[r], bn[id])), 0.0f);
+    d = fmaxf(__fmaf_rn(-2.0f, s, __fadd_rn(an[r], bn[id])), 0.0f);
     c = __fsub_rn(1.0f, d);
   }
-  // rank of this lane's value among the 16 (descending; ties by lane so that ranks are a permutation)
+  // rank of this lane's candidate among the 16: by distance ascending (= score descending), lower id first on equal
+  // distances (torch.argmin / a stable sort), empty slots last — a permutation of 0..15
   const unsigned gmask = 0xffffu << (threadIdx.x & 16);
+  const unsigned uid = id >= 0 ? static_cast<unsigned>(id) : (0x80000000u | static_cast<unsigned>(sub));
   int rank = 0;
   float tc_min = tc;
 #pragma unroll
   for (int o = 0; o < 16; ++o) {
     const int src = (threadIdx.x & 16) | o;
-    const float oc = __shfl_sync(gmask, c, src);
+    const float od = __shfl_sync(gmask, d, src);
+    const unsigned oid = __shfl_sync(gmask, uid, src);
     const float otc = __shfl_sync(gmask, tc, src);
-    rank += (oc > c) || (oc == c && o < sub);
+    rank += (od < d) || (od == d && oid < uid);
     tc_min = fminf(tc_min, otc);
+  }
+  if (live && rank == 0 && best_idx) {
+    best_idx[row] = id;
+    best_d[row] = d;
   }
   // largest-first fp32 sum of the k largest: lane with rank t contributes at step t
   float sum = 0.f, ck = 0.f;
@@ -581,8 +589,11 @@ __global__ void __launch_bounds__(256) topk_exhaustive_kernel(const __nv_bfloat1
                                                               int Dpad, long long n_b, const float* __restrict__ an,
                                                               const float* __restrict__ bn, const int* __restrict__ flagged,
                                                               const int* __restrict__ flagged_cnt, int flagged_cap, int k,
-                                                              float* __restrict__ nv) {
+                                                              float* __restrict__ nv, float* __restrict__ best_d,
+                                                              int* __restrict__ best_idx) {
   __shared__ float lists[256 * KT_LIST];
+  __shared__ float bd_s[256];
+  __shared__ int bi_s[256];
   const int total = min(*flagged_cnt, flagged_cap);
   for (int f = blockIdx.x; f < total; f += gridDim.x) {
     const long long row = flagged[f];
@@ -591,14 +602,25 @@ __global__ void __launch_bounds__(256) topk_exhaustive_kernel(const __nv_bfloat1
     int dummy[1];
 #pragma unroll
     for (int t = 0; t < KT_LIST; ++t) top[t] = -INFINITY;
+    float bd = INFINITY;
+    int bi = 0x7fffffff;
     for (long long j = threadIdx.x; j < n_b; j += blockDim.x) {
       const float s = canonical_dot(A + row * Dpad, B + j * Dpad, Dpad);
-      const float c = __fsub_rn(1.0f, fmaxf(__fmaf_rn(-2.0f, s, __fadd_rn(a, bn[j])), 0.0f));
-      topk_pair_insert<false>(top, dummy, c, 0);
+      const float dd = fmaxf(__fmaf_rn(-2.0f, s, __fadd_rn(a, bn[j])), 0.0f);
+      if (dd < bd) { bd = dd; bi = static_cast<int>(j); }               // j ascending per thread: strict keeps the first
+      topk_pair_insert<false>(top, dummy, __fsub_rn(1.0f, dd), 0);
     }
 #pragma unroll
     for (int t = 0; t < KT_LIST; ++t) lists[threadIdx.x * KT_LIST + t] = top[t];
+    bd_s[threadIdx.x] = bd;
+    bi_s[threadIdx.x] = bi;
     __syncthreads();
+    if (threadIdx.x == 0 && best_idx) {
+      for (int o = 1; o < static_cast<int>(blockDim.x); ++o)
+        if (bd_s[o] < bd || (bd_s[o] == bd && bi_s[o] < bi)) { bd = bd_s[o]; bi = bi_s[o]; }
+      best_d[row] = bd;
+      best_idx[row] = bi;
+    }
     if (threadIdx.x == 0) {
       for (int o = 1; o < static_cast<int>(blockDim.x); ++o)
         for (int t = 0; t < KT_LIST; ++t) topk_pair_insert<false>(top, dummy, lists[o * KT_LIST + t], 0);
@@ -976,23 +998,25 @@ int launch_col_cand_finalize(const long long* offs, const int* hist, const float
 }
 int launch_topk_rescore(const __nv_bfloat16* A, const __nv_bfloat16* B, int Dpad, long long n_rows, const float* an,
                         const float* bn, const int* cand_idx, const float* cand_val, int k, float delta, float* nv,
-                        int* flagged, int* flagged_cnt, int flagged_cap, cudaStream_t st) {
+                        int* flagged, int* flagged_cnt, int flagged_cap, float* best_d, int* best_idx, cudaStream_t st) {
   if (!A || !B || !an || !bn || !cand_idx || !cand_val || !nv || !flagged || !flagged_cnt || n_rows <= 0 || flagged_cap < 1)
     return SNAG_ERR_ARG;
+  if ((best_d == nullptr) != (best_idx == nullptr)) return SNAG_ERR_ARG;
   if (k < 1 || k > KT_LIST || (Dpad % 64)) return SNAG_ERR_SHAPE;
   const long long threads = n_rows * 16;
   topk_rescore_kernel<<<static_cast<unsigned>((threads + 127) / 128), 128, 0, st>>>(A, B, Dpad, n_rows, an, bn, cand_idx,
                                                                                    cand_val, k, delta, nv, flagged,
-                                                                                   flagged_cnt, flagged_cap);
+                                                                                   flagged_cnt, flagged_cap, best_d, best_idx);
   return static_cast<int>(cudaGetLastError());
 }
 int launch_topk_exhaustive(const __nv_bfloat16* A, const __nv_bfloat16* B, int Dpad, long long n_b, const float* an,
                            const float* bn, const int* flagged, const int* flagged_cnt, int flagged_cap, int k, float* nv,
-                           cudaStream_t st) {
+                           float* best_d, int* best_idx, cudaStream_t st) {
   if (!A || !B || !an || !bn || !flagged || !flagged_cnt || !nv || n_b <= 0 || flagged_cap < 1) return SNAG_ERR_ARG;
+  if ((best_d == nullptr) != (best_idx == nullptr)) return SNAG_ERR_ARG;
   if (k < 1 || k > KT_LIST || (Dpad % 64)) return SNAG_ERR_SHAPE;
   const int grid = flagged_cap < num_sms() * 4 ? flagged_cap : num_sms() * 4;
-  topk_exhaustive_kernel<<<grid, 256, 0, st>>>(A, B, Dpad, n_b, an, bn, flagged, flagged_cnt, flagged_cap, k, nv);
+  topk_exhaustive_kernel<<<grid, 256, 0, st>>>(A, B, Dpad, n_b, an, bn, flagged, flagged_cnt, flagged_cap, k, nv, best_d, best_idx);
   return static_cast<int>(cudaGetLastError());
 }
 static inline int grid_for(long long work_items, int block, int num_sms, int ctas_per_sm);

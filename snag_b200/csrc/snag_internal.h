@@ -48,10 +48,10 @@ int launch_topk_merge_mean(const float* part, const int* part_idx, int n_lists, 
                            float* cand_out, int* cand_idx_out, cudaStream_t st);
 int launch_topk_rescore(const __nv_bfloat16* A, const __nv_bfloat16* B, int Dpad, long long n_rows, const float* an,
                         const float* bn, const int* cand_idx, const float* cand_val, int k, float delta, float* nv,
-                        int* flagged, int* flagged_cnt, int flagged_cap, cudaStream_t st);
+                        int* flagged, int* flagged_cnt, int flagged_cap, float* best_d, int* best_idx, cudaStream_t st);
 int launch_topk_exhaustive(const __nv_bfloat16* A, const __nv_bfloat16* B, int Dpad, long long n_b, const float* an,
                            const float* bn, const int* flagged, const int* flagged_cnt, int flagged_cap, int k, float* nv,
-                           cudaStream_t st);
+                           float* best_d, int* best_idx, cudaStream_t st);
 int launch_pair_score(const __nv_bfloat16* X, const __nv_bfloat16* Y, int Dpad, long long n, const float* xn, const float* yn,
                       const float* nv1, const float* nv2, int use_csls, float* g, float* s_out, cudaStream_t st);
 int launch_top3_merge(const float* val, const int* idx, int n_lists, long long n_rows, float* oval, int* oidx, cudaStream_t st);

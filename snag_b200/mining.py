@@ -15,13 +15,28 @@ from . import ops as _cuda_ops
 from ._lib import KT, SnagError
 
 
-def mutual_nearest(x: torch.Tensor, y: torch.Tensor, normalize: bool = False, backend=None):
+def mutual_nearest(x: torch.Tensor, y: torch.Tensor, normalize: bool = False, backend=None, canonical: bool = True):
     """(preds_l int64 [n1], preds_r int64 [n2], dmin_l fp32 [n1], dmin_r fp32 [n2]): for every row of x its nearest row
-    of y under the squared distance of src/utils.pairwise_distances, and vice versa."""
+    of y under the squared distance of src/utils.pairwise_distances, and vice versa.
+
+    canonical (default): the tensor cores pick each row's / column's 16 nearest candidates (two top-k sweeps, ids
+    tracked); the candidates are re-scored with the oracle's arithmetic (fp64 index-order dot, fp32 clamp chain) and
+    the argmin — lowest index on ties, like torch.argmin — is taken over them, with the same verification bound and
+    exhaustive completion as the CSLS neighbourhoods. The result does not depend on the MMA accumulation order.
+    canonical=False: the single fused sweep (sim_kernel<EpiMutualNN>) that takes both argmins straight from the
+    tensor-core distances — exact ties still go to the lowest index, near-ties (< 1e-6) follow the tensor core."""
     be = _cuda_ops if backend is None else backend
     n1, n2 = x.shape[0], y.shape[0]
     X, xn = be.prep_bf16(x.contiguous().float(), None, normalize)
     Y, yn = be.prep_bf16(y.contiguous().float(), None, normalize)
+    if canonical and hasattr(be, "topk_rescore"):
+        out = []
+        for A, B, an, bn, na, nb, tag in ((X, Y, xn, yn, n1, n2, "mine_rows"), (Y, X, yn, xn, n2, n1, "mine_cols")):
+            part, pidx = be.eval_rowtopk(A, B, an, bn, na, nb, want_idx=True)
+            _, cand, cidx = be.topk_merge_mean(part, 1, want_nv=False, part_idx=pidx)
+            _, best_d, best_i = be.topk_rescore(A, B, an, bn, cidx, cand, 1, nb, tag, want_best=True)
+            out.append((best_i.to(torch.int64), best_d))
+        return out[0][0], out[1][0], out[0][1], out[1][1]
     # upper bound of every column's minimum from a sample of the rows (all of them when there are few): the swapped
     # top-k sweep keeps, per column, the largest c = 1 - d over the sample in registers
     m = n1 if n1 <= 8192 else max(8192, (n1 // 16 + 255) // 256 * 256)

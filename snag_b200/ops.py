@@ -308,10 +308,13 @@ TOPK_EXHAUSTIVE_BUDGET = 4.0e12     # bf16 multiply-adds the exhaustive completi
 LAST_TOPK_INFO: dict = {}
 
 
-def topk_rescore(A, B, an, bn, cand_idx: torch.Tensor, cand_val: torch.Tensor, k: int, n_b: int, tag: str = "rows"):
+def topk_rescore(A, B, an, bn, cand_idx: torch.Tensor, cand_val: torch.Tensor, k: int, n_b: int, tag: str = "rows",
+                 want_best: bool = False):
     """Canonical CSLS neighbourhood means of the rows of A from their KT tensor-core candidates (rows of B); rows the
     candidates cannot vouch for are completed by an exhaustive scan of B (within TOPK_EXHAUSTIVE_BUDGET; beyond it the
-    candidate-based value stays and the count is reported in LAST_TOPK_INFO[tag]['unverified'])."""
+    candidate-based value stays and the count is reported in LAST_TOPK_INFO[tag]['unverified']).
+    want_best: return (nv, best_d, best_idx) — every row's nearest row of B under the canonical squared distance, lowest
+    index on ties (the argmin of link mining)."""
     _check_operand(A, "A")
     _check_operand(B, "B")
     _need(cand_idx, torch.int32, "cand_idx", 2)
@@ -320,21 +323,24 @@ def topk_rescore(A, B, an, bn, cand_idx: torch.Tensor, cand_val: torch.Tensor, k
     dev = A.device
     st = current_stream()
     nv = torch.empty((n_rows,), dtype=torch.float32, device=dev)
+    best_d = torch.empty((n_rows,), dtype=torch.float32, device=dev) if want_best else None
+    best_i = torch.empty((n_rows,), dtype=torch.int32, device=dev) if want_best else None
     cap = n_rows
     flagged = torch.empty((cap,), dtype=torch.int32, device=dev)
     fcnt = torch.zeros((1,), dtype=torch.int32, device=dev)
     call("snag_topk_rescore", ptr(A), ptr(B), A.shape[1], n_rows, ptr(an), ptr(bn), ptr(cand_idx), ptr(cand_val), k,
-         TOPK_VERIFY_DELTA * _error_scale(an, bn, A.shape[1]), ptr(nv), ptr(flagged), ptr(fcnt), cap, st)
+         TOPK_VERIFY_DELTA * _error_scale(an, bn, A.shape[1]), ptr(nv), ptr(flagged), ptr(fcnt), cap, ptr(best_d), ptr(best_i),
+         st)
     n_flag = int(fcnt.item())
     info = {"flagged": n_flag, "unverified": 0}
     if n_flag:
         if float(n_flag) * n_b * A.shape[1] <= TOPK_EXHAUSTIVE_BUDGET:
             call("snag_topk_exhaustive", ptr(A), ptr(B), A.shape[1], n_b, ptr(an), ptr(bn), ptr(flagged), ptr(fcnt), cap, k,
-                 ptr(nv), st)
+                 ptr(nv), ptr(best_d), ptr(best_i), st)
         else:
             info["unverified"] = n_flag
     LAST_TOPK_INFO[tag] = info
-    return nv
+    return (nv, best_d, best_i) if want_best else nv
 
 
 def pair_score(X, Y, n: int, xn, yn, nv1, nv2, use_csls: bool, want_dot: bool = False):

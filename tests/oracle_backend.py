@@ -57,13 +57,24 @@ def topk_merge_mean(part, k, want_nv=True, want_cand=False, part_idx=None):
     return nv, cand
 
 
-def topk_rescore(A, B, an, bn, cand_idx, cand_val, k, n_b, tag="rows"):
-    """The stand-in's scores are already canonical: the mean of the k largest candidate values, largest first."""
+def topk_rescore(A, B, an, bn, cand_idx, cand_val, k, n_b, tag="rows", want_best=False):
+    """The stand-in's scores are already canonical: the mean of the k largest candidate values, largest first; the
+    nearest candidate is the one with the smallest canonical distance, lowest id on ties."""
     v = np.sort(cand_val.numpy(), axis=1)
     s = np.zeros((v.shape[0],), np.float32)
     for t in range(k):
         s = (s + v[:, KT - 1 - t]).astype(np.float32)
-    return torch.from_numpy((s / np.float32(k)).astype(np.float32))
+    nv = torch.from_numpy((s / np.float32(k)).astype(np.float32))
+    if not want_best:
+        return nv
+    n_a = cand_idx.shape[0]
+    d = _c_matrix(A, B, an, bn, n_a, n_b)
+    ci = cand_idx.numpy().astype(np.int64)
+    ok = ci >= 0
+    dv = np.where(ok, np.take_along_axis(d, np.where(ok, ci, 0), 1), np.inf).astype(np.float32)
+    order = np.lexsort((np.where(ok, ci, 1 << 40), dv), axis=1)[:, 0]
+    rows = np.arange(n_a)
+    return nv, torch.from_numpy(dv[rows, order]), torch.from_numpy(ci[rows, order].astype(np.int32))
 
 
 def _dist(X, Y, xn, yn, nv1, nv2, n1, n2, use_csls):

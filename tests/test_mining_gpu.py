@@ -42,7 +42,15 @@ def test_mining_vs_oracle(cuda_device, n1, n2, d, sigma):
     x = oracle.bf16_round(oracle.normalize_rows(x))[:n1]
     y = oracle.bf16_round(oracle.normalize_rows(y))[rng.permutation(max(n1, n2))[:n2]]
     dmat = oracle.pairwise_distances(x, y)
-    pl, pr, dl, dr = mining.mutual_nearest(torch.from_numpy(x).to(cuda_device), torch.from_numpy(y).to(cuda_device))
+    xt, yt = torch.from_numpy(x).to(cuda_device), torch.from_numpy(y).to(cuda_device)
+    pl, pr, dl, dr = mining.mutual_nearest(xt, yt)
+    # canonical path: candidates re-scored with the oracle's arithmetic -> bit-exact on every row and column
+    np.testing.assert_array_equal(pl.cpu().numpy(), dmat.argmin(1))
+    np.testing.assert_array_equal(pr.cpu().numpy(), dmat.argmin(0))
+    np.testing.assert_array_equal(dl.cpu().numpy(), dmat.min(1))
+    np.testing.assert_array_equal(dr.cpu().numpy(), dmat.min(0))
+    # fused single-sweep path: exact wherever the runner-up is further away than the accumulation-order noise
+    pl, pr, dl, dr = mining.mutual_nearest(xt, yt, canonical=False)
     pl, pr = pl.cpu().numpy(), pr.cpu().numpy()
     np.testing.assert_allclose(dl.cpu().numpy(), dmat.min(1), atol=2e-6, rtol=0)
     np.testing.assert_allclose(dr.cpu().numpy(), dmat.min(0), atol=2e-6, rtol=0)
@@ -58,9 +66,19 @@ def test_mining_vs_oracle(cuda_device, n1, n2, d, sigma):
         np.testing.assert_array_equal(pr[clear_r], dmat.argmin(0)[clear_r])
     else:
         np.testing.assert_array_equal(pr, np.zeros(n2, np.int64))
-    # whatever index was returned attains the minimum up to the accumulation-order noise
     assert np.all(dmat[np.arange(n1), pl] <= dmat.min(1) + 2e-5)
     assert np.all(dmat[pr, np.arange(n2)] <= dmat.min(0) + 2e-5)
+
+
+@pytest.mark.parametrize("name", golden_names("mining_"))
+def test_mining_golden_fused_sweep(cuda_device, name):
+    """The single fused sweep (canonical=False) against the same reference outputs."""
+    fx = load_golden(name)
+    emb = torch.from_numpy(fx["emb"]).to(cuda_device)
+    left, right = fx["left"].tolist(), fx["right"].tolist()
+    pl, pr, _, _ = mining.mutual_nearest(emb[left], emb[right], canonical=False)
+    np.testing.assert_array_equal(pl.cpu().numpy(), fx["preds_l"])
+    np.testing.assert_array_equal(pr.cpu().numpy(), fx["preds_r"])
 
 
 def test_iter_new_links_interface(cuda_device):
