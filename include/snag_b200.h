@@ -207,6 +207,10 @@ int snag_band_rescore(const uint16_t* X, const uint16_t* Y, int32_t Dpad, const 
                       const float* nv2, const float* g_row, const float* g_col, int32_t row_gid0, int32_t col_gid0,
                       int32_t use_csls, const uint64_t* band, const uint32_t* band_cnt, uint32_t band_cap, int32_t* cnt_row,
                       int32_t* cnt_col, void* stream);
+/* s_out[p] = X[rows[p]] . Y[cols[p]] with the canonical accumulation (fp64, index order, rounded once): the re-score of
+ * explicitly listed similarity entries (unsupervised seed induction, src/data.py:367-375 + src/utils.py:437-443). */
+int snag_pairs_dot(const uint16_t* X, const uint16_t* Y, int32_t Dpad, const int32_t* rows, const int32_t* cols,
+                   int64_t n_pairs, float* s_out, void* stream);
 int snag_top4_merge(const float* val, const int32_t* idx, int32_t n_lists, int64_t n_rows, float* oval, int32_t* oidx,
                     void* stream);
 /* cand int32 [n_rows][4] column ids (0x7fffffff = empty) -> canonical distances, ascending (id ascending on ties) */

@@ -22,7 +22,7 @@ sys.path.insert(0, ROOT)
 import numpy as np
 import torch
 
-from snag_b200 import evaluate, fusion, loss, mining, noise, ops
+from snag_b200 import evaluate, fusion, loss, mining, noise, ops, seeds
 
 
 def peaks():
@@ -196,6 +196,17 @@ def main():
     rec_ms = ms
     emit("f1", f"mutual_nearest[{n_l} x {n_r}, D={D}] (two top-k sweeps + canonical re-score of the candidates)", 4 * n_l * n_r, rec_ms, cpu_time(ref_mine, 2),
          f"tensor-pipe bound, not HBM: {flops / rec_ms / 1e9:.0f} TFLOP/s algorithmic; bytes = the distance matrix the reference materialises")
+    # ------------------------------------------------------------------ f4 unsupervised seeds (src/data.py:367-402): global top-K
+    Kq = 100_000                                                             # unsup_k = 1000 (config.py:70) x 100
+    ms = gpu_time(lambda: seeds.topk_similarity_entries(xl, yr, Kq), reps=5)
+
+    def ref_topk():
+        sim = xlc.mm(yrc.t())
+        vals, ind = sim.view(-1).topk(Kq)
+        return ind // sim.shape[1], ind % sim.shape[1]
+    emit("f4", f"topk_similarity_entries[{n_l} x {n_r}, D={D}, K={Kq}] (pool sweep + thresholded sweep + re-score + sort)",
+         4 * n_l * n_r, ms, cpu_time(ref_topk, 2),
+         f"tensor-pipe bound: {2 * flops / ms / 1e9:.0f} TFLOP/s executed (two sweeps); bytes = the matrix the reference materialises")
     del xl, yr
     # ------------------------------------------------------------------ a5 / a6 one loss call fwd+bwd (SNAG_loss.py:58-128, 148-202)
     B = 3500

@@ -54,6 +54,7 @@ _SIGNATURES = {
     "snag_eval_rank_band": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _vp, _vp, _vp, _vp,
                             _vp, _vp, _u32, _vp],
     "snag_band_rescore": [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _u32, _vp, _vp, _vp],
+    "snag_pairs_dot": [_vp, _vp, _i32, _vp, _vp, _i64, _vp, _vp],
     "snag_top4_merge": [_vp, _vp, _i32, _i64, _vp, _vp, _vp],
     "snag_top3_rescore": [_vp, _vp, _i32, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp],
     "snag_csls_sim": [_vp, _i64, _i64, _i64, _i32, _vp, _i64, _vp, _vp, _vp, _vp],

@@ -149,6 +149,10 @@ int snag_band_rescore(const uint16_t* X, const uint16_t* Y, int32_t Dpad, const 
   return launch_band_rescore(BF(X), BF(Y), Dpad, xn, yn, nv1, nv2, g_row, g_col, row_gid0, col_gid0, use_csls,
                              reinterpret_cast<const uint2*>(band), band_cnt, band_cap, cnt_row, cnt_col, S(stream));
 }
+int snag_pairs_dot(const uint16_t* X, const uint16_t* Y, int32_t Dpad, const int32_t* rows, const int32_t* cols,
+                   int64_t n_pairs, float* s_out, void* stream) {
+  return launch_pairs_dot(BF(X), BF(Y), Dpad, rows, cols, n_pairs, s_out, S(stream));
+}
 int snag_top4_merge(const float* val, const int32_t* idx, int32_t n_lists, int64_t n_rows, float* oval, int32_t* oidx,
                     void* stream) {
   return launch_top4_merge(val, idx, n_lists, n_rows, oval, oidx, S(stream));

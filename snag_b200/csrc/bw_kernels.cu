@@ -703,6 +703,16 @@ __global__ void __launch_bounds__(128) band_rescore_kernel(const __nv_bfloat16* 
   }
 }
 
+// canonical dot products of an explicit list of (row of X, row of Y) pairs — the re-score of the similarity entries a
+// thresholded sweep collected (unsupervised seed induction, src/data.py:367-375)
+__global__ void __launch_bounds__(128) pairs_dot_kernel(const __nv_bfloat16* __restrict__ X, const __nv_bfloat16* __restrict__ Y,
+                                                        int Dpad, const int* __restrict__ rows, const int* __restrict__ cols,
+                                                        long long n_pairs, float* __restrict__ s_out) {
+  const long long p = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (p >= n_pairs) return;
+  s_out[p] = canonical_dot(X + static_cast<long long>(rows[p]) * Dpad, Y + static_cast<long long>(cols[p]) * Dpad, Dpad);
+}
+
 // merge per-list top-4 candidate lists of each row (x descending = nearest first, column id ascending on ties)
 __global__ void __launch_bounds__(128) top4_merge_kernel(const float* __restrict__ val, const int* __restrict__ idx, int n_lists,
                                                          long long n_rows, float* __restrict__ oval, int* __restrict__ oidx) {
@@ -1219,6 +1229,14 @@ int launch_band_rescore(const __nv_bfloat16* X, const __nv_bfloat16* Y, int Dpad
   // grid-stride over the device-side count: no host round trip
   band_rescore_kernel<<<num_sms() * 16, 128, 0, st>>>(X, Y, Dpad, xn, yn, nv1, nv2, g_row, g_col, row_gid0, col_gid0, use_csls,
                                                       band, band_cnt, band_cap, cnt_row, cnt_col);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int launch_pairs_dot(const __nv_bfloat16* X, const __nv_bfloat16* Y, int Dpad, const int* rows, const int* cols,
+                     long long n_pairs, float* s_out, cudaStream_t st) {
+  if (!X || !Y || !rows || !cols || !s_out || n_pairs <= 0) return SNAG_ERR_ARG;
+  if (Dpad % 64) return SNAG_ERR_SHAPE;
+  pairs_dot_kernel<<<static_cast<unsigned>((n_pairs + 127) / 128), 128, 0, st>>>(X, Y, Dpad, rows, cols, n_pairs, s_out);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -59,6 +59,8 @@ int launch_band_rescore(const __nv_bfloat16* X, const __nv_bfloat16* Y, int Dpad
                         const float* nv1, const float* nv2, const float* g_row, const float* g_col, int row_gid0, int col_gid0,
                         int use_csls, const uint2* band, const unsigned int* band_cnt, unsigned int band_cap, int* cnt_row,
                         int* cnt_col, cudaStream_t st);
+int launch_pairs_dot(const __nv_bfloat16* X, const __nv_bfloat16* Y, int Dpad, const int* rows, const int* cols,
+                     long long n_pairs, float* s_out, cudaStream_t st);
 int launch_top4_merge(const float* val, const int* idx, int n_lists, long long n_rows, float* oval, int* oidx, cudaStream_t st);
 int launch_top3_rescore(const __nv_bfloat16* X, const __nv_bfloat16* Y, int Dpad, long long n_rows, const float* xn,
                         const float* yn, const float* nv1, const float* nv2, int use_csls, const int* cand, float* oval,

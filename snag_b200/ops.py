@@ -423,6 +423,20 @@ def eval_rank(X, Y, xn, yn, nv1, nv2, g_row, g_col, row_gid0: int, col_gid0: int
 LAST_RANK_INFO: dict = {}
 
 
+def pairs_dot(X, Y, rows: torch.Tensor, cols: torch.Tensor) -> torch.Tensor:
+    """Canonical dot products X[rows[p]] . Y[cols[p]] (fp64 index-order accumulation, one rounding) of listed pairs."""
+    _check_operand(X, "X")
+    _check_operand(Y, "Y")
+    _need(rows, torch.int32, "rows", 1)
+    _need(cols, torch.int32, "cols", 1)
+    if rows.numel() != cols.numel():
+        raise ValueError("rows and cols must pair up")
+    out = torch.empty((rows.numel(),), dtype=torch.float32, device=X.device)
+    if rows.numel():
+        call("snag_pairs_dot", ptr(X), ptr(Y), X.shape[1], ptr(rows), ptr(cols), rows.numel(), ptr(out), current_stream())
+    return out
+
+
 def top4_merge(val: torch.Tensor, idx: torch.Tensor):
     """Merge per-list nearest-candidate lists [n_lists, n_rows, 4] (value descending, id ascending on ties) -> [n_rows, 4]."""
     _need(val, torch.float32, "val", 3)

@@ -22,7 +22,7 @@ import os
 import sys
 import types
 
-from . import evaluate, fusion, loss, mining, noise, runner
+from . import evaluate, fusion, loss, mining, noise, runner, seeds
 
 
 def patch(main_module: types.ModuleType | None = None) -> list[str]:
@@ -64,6 +64,11 @@ def patch(main_module: types.ModuleType | None = None) -> list[str]:
         done.append("model.SNAG_tools.MultiModalEncoder.forward")
         ref_tools.MformerFusion.forward = fusion.MformerFusion_forward
         done.append("model.SNAG_tools.MformerFusion.forward")
+    except ImportError:
+        pass
+    try:
+        ref_data = importlib.import_module("src.data")
+        _set(ref_data, "visual_pivot_induction", seeds.visual_pivot_induction)
     except ImportError:
         pass
     main_mod = main_module or sys.modules.get("main")

@@ -224,3 +224,11 @@ def test_joint_fuse_matches_reference(name):
     j, fz = oracle.joint_fuse([fx[f"emb{m}"] for m in range(M)], fx["weight_norm"], fx["weight_norm_fz"])
     np.testing.assert_allclose(j, fx["joint"], rtol=0, atol=1e-6)
     np.testing.assert_allclose(fz, fx["joint_fz"], rtol=0, atol=1e-6)
+
+
+@pytest.mark.parametrize("name", golden_names("seeds_"))
+def test_seed_induction_matches_reference(name):
+    """src/data.py:367-402 as run by the reference itself (gen_golden_seeds.py)."""
+    fx = load_golden(name)
+    links = oracle.visual_pivot_induction(fx["left"].tolist(), fx["right"].tolist(), fx["feats"], int(fx["unsup_k"]))
+    np.testing.assert_array_equal(links, fx["links"])

@@ -45,6 +45,8 @@ def test_signatures_match_reference():
     assert _sig(enc.forward) == _sig(noise.encoder_forward)
     from snag_b200 import fusion
     assert _sig(importlib.import_module("model.SNAG_tools").MformerFusion.forward) == _sig(fusion.MformerFusion_forward)
+    from snag_b200 import seeds
+    assert _sig(importlib.import_module("src.data").visual_pivot_induction) == _sig(seeds.visual_pivot_induction)
 
 
 @needs_ref
@@ -54,7 +56,7 @@ def test_patch_rebinds_reference_names(monkeypatch):
     load_reference()
     import importlib
     from snag_b200 import evaluate, loss, noise, patch, runner
-    mods = {n: importlib.import_module(n) for n in ("model.SNAG_loss", "model.SNAG", "model.SNAG_tools", "src.utils")}
+    mods = {n: importlib.import_module(n) for n in ("model.SNAG_loss", "model.SNAG", "model.SNAG_tools", "src.utils", "src.data")}
     saved = {(n, k): v for n, m in mods.items() for k, v in vars(m).items()}
     snag_cls, enc_cls = mods["model.SNAG"].SNAG, mods["model.SNAG_tools"].MultiModalEncoder
     saved_cls = {k: getattr(snag_cls, k) for k in ("add_noise_to_embeddings", "get_mean_std", "update_noise", "Iter_new_links")}
@@ -74,7 +76,9 @@ def test_patch_rebinds_reference_names(monkeypatch):
         assert fake_main.Runner._test is runner._test and fake_main.csls_sim is evaluate.csls_sim
         from snag_b200 import fusion
         assert fus_cls.forward is fusion.MformerFusion_forward
-        assert len(done) >= 13
+        from snag_b200 import seeds
+        assert mods["src.data"].visual_pivot_induction is seeds.visual_pivot_induction
+        assert len(done) >= 14
     finally:
         for (n, k), v in saved.items():
             setattr(mods[n], k, v)
