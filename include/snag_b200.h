@@ -257,11 +257,15 @@ int snag_icl_finalize(const float* rowsum_part, int32_t n_lists, int32_t B, int3
  * as snag_icl_rowsum; cr, cc, dg are [B], indexed by batch index). With g_x = dL/dnll_x (upstream) and lse_x from the
  * forward:
  *   cr[i] = g_this[i]*exp(1/tau - lse_this[i]), cc[j] = g_other[j]*exp(1/tau - lse_other[j]), dg[i] = g_this[i]+g_other[i]
- * Stage 2 is a plain contraction dX = G . [other ; this], run with snag_sim_write(mode 0) on G and the
- * transposed stacked operand. */
+ * Stage 2 is the contraction dX = G . [other ; this] (snag_sim_write_t on the transposed stacked operand and G).
+ * Part 0 (cross columns): G[i,j] = (cr[i] + cc[j]) E_ij / tau - [i == j] dg[i] / tau; part 1 (self columns, diagonal
+ * masked): G[i,j] = (cr[i] + (self_cols ? cr[j] : 0)) E_ij / tau. self_cols = 1 is the ICL / IAL gradient pattern;
+ * self_cols = 0 with cc = dg = 0 and cr[i] = tau * exp(1/tau - lse[i]) writes the row softmax itself (IAL forward).
+ * ebar is subtracted from E_ij (0 for ICL): IAL's gradient is the difference of two nearly uniform matrices at large tau;
+ * centring E keeps their bf16 rounding relative to the deviations (the caller adds the common, rank-one part back). */
 int snag_icl_bwd_logits(const uint16_t* X, const uint16_t* Y, int32_t B, int32_t Bp, int32_t row0, int32_t nx,
                         int32_t Dpad, float inv_tau, const float* cr, const float* cc, const float* dg, uint16_t* G,
-                        void* stream);
+                        int32_t self_cols, float ebar, void* stream);
 
 #ifdef __cplusplus
 }

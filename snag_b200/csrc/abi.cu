@@ -216,9 +216,9 @@ int snag_mutual_nn(const uint16_t* X, const uint16_t* Y, const float* xn, const 
 
 int snag_icl_bwd_logits(const uint16_t* X, const uint16_t* Y, int32_t B, int32_t Bp, int32_t row0, int32_t nx,
                         int32_t Dpad, float inv_tau, const float* cr, const float* cc, const float* dg, uint16_t* G,
-                        void* stream) {
+                        int32_t self_cols, float ebar, void* stream) {
   return launch_icl_bwd_logits(BF(X), BF(Y), B, Bp, row0, nx, Dpad, inv_tau, cr, cc, dg,
-                               reinterpret_cast<__nv_bfloat16*>(G), S(stream));
+                               reinterpret_cast<__nv_bfloat16*>(G), self_cols, ebar, S(stream));
 }
 
 }  // extern "C"

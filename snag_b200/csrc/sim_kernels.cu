@@ -325,11 +325,11 @@ int launch_mutual_nn(const __nv_bfloat16* X, const __nv_bfloat16* Y, const float
 
 int launch_icl_bwd_logits(const __nv_bfloat16* X, const __nv_bfloat16* Y, int B, int Bp, int row0, int nx, int Dpad,
                           float inv_tau, const float* cr, const float* cc, const float* dg, __nv_bfloat16* G,
-                          cudaStream_t st) {
+                          int self_cols, float ebar, cudaStream_t st) {
   if (!cr || !cc || !dg || !G || B <= 0 || Bp < B || (Bp % BN) != 0) return SNAG_ERR_ARG;
   if (row0 < 0 || nx <= 0 || row0 + nx > Bp) return SNAG_ERR_ARG;
   if (reinterpret_cast<uintptr_t>(G) & 15) return SNAG_ERR_ALIGN;
-  EpiIclBwd::Params p{inv_tau * 1.4426950408889634f, inv_tau, B, Bp, row0, nx, cr, cc, dg, G};
+  EpiIclBwd::Params p{inv_tau * 1.4426950408889634f, inv_tau, B, Bp, row0, nx, cr, cc, dg, G, self_cols, ebar};
   return launch_sim<EpiIclBwd>(X, Y, nx, 2 * Bp, Dpad, p, st);
 }
 

@@ -1299,6 +1299,12 @@ struct EpiIclBwd {
     const float* cc;      // [B] column-side coefficients of part 0 (other side)
     const float* dg;      // [B] diagonal term of part 0
     __nv_bfloat16* G;     // [nx, 2*Bp]
+    int self_cols;        // 1: part 1 carries the transposed-role term cr_j (ICL / IAL gradients); 0: row term only
+                          //    (G = cr_i E / tau in both parts: a plain row-softmax writer)
+    float ebar;           // subtracted from E_ij before it is scaled (0 for ICL). IAL's gradient is a DIFFERENCE of two
+                          // such matrices that are both nearly uniform at large tau; centring E on its value at s = 0
+                          // keeps the bf16 rounding relative to the deviations, not to the common part (the common
+                          // part's contribution to G.Y is rank one and is added back by the caller in fp32)
   };
   struct State {
     float cr, dg;
@@ -1319,7 +1325,7 @@ struct EpiIclBwd {
       const int col = ct * BN + cx.tid;
       const int part = col >= p.Bp ? 1 : 0;
       const int idx = col - part * p.Bp;
-      if (idx < p.B) pre.a = (part ? p.cr[idx] : p.cc[idx]) * p.inv_tau;
+      if (idx < p.B) pre.a = (part ? (p.self_cols ? p.cr[idx] : 0.f) : p.cc[idx]) * p.inv_tau;
     }
     return pre;
   }
@@ -1340,8 +1346,8 @@ struct EpiIclBwd {
     if (plain) {
 #pragma unroll
       for (int q = 0; q < 16; q += 2) {
-        const float e0 = ex2_approx(__fmaf_rn(__uint_as_float(r[q0 + q]), p.scale_log2, nb));
-        const float e1 = ex2_approx(__fmaf_rn(__uint_as_float(r[q0 + q + 1]), p.scale_log2, nb));
+        const float e0 = ex2_approx(__fmaf_rn(__uint_as_float(r[q0 + q]), p.scale_log2, nb)) - p.ebar;
+        const float e1 = ex2_approx(__fmaf_rn(__uint_as_float(r[q0 + q + 1]), p.scale_log2, nb)) - p.ebar;
         const __nv_bfloat162 h = __floats2bfloat162_rn((st.cr + cc[q]) * e0, (st.cr + cc[q + 1]) * e1);
         packed[q / 2] = *reinterpret_cast<const uint32_t*>(&h);
       }
@@ -1352,7 +1358,7 @@ struct EpiIclBwd {
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           const int idx = idx0 + q0 + q + e;
-          const float E = ex2_approx(__fmaf_rn(__uint_as_float(r[q0 + q + e]), p.scale_log2, nb));
+          const float E = ex2_approx(__fmaf_rn(__uint_as_float(r[q0 + q + e]), p.scale_log2, nb)) - p.ebar;
           float gval = (st.cr + cc[q + e]) * E;
           if (idx == st.gr) gval = part ? 0.f : gval - st.dg;
           if (!st.ok || idx >= p.B) gval = 0.f;

@@ -108,6 +108,6 @@ int launch_cand_scatter(const uint2* stream, const int* stream_row, const int* s
 int launch_col_cand_finalize(const long long* offs, const int* hist, const float* vals, const int* rows, long long n, int k,
                              float* nv, float* cand_val, int* cand_idx, int* overflow, cudaStream_t st);
 int launch_icl_bwd_logits(const __nv_bfloat16* X, const __nv_bfloat16* Y, int B, int Bp, int row0, int nx, int Dpad, float inv_tau,
-                          const float* cr, const float* cc, const float* dg, __nv_bfloat16* G, cudaStream_t st);
+                          const float* cr, const float* cc, const float* dg, __nv_bfloat16* G, int self_cols, float ebar, cudaStream_t st);
 
 }  // namespace snag

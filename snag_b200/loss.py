@@ -10,9 +10,10 @@ and contracts it with the stacked embeddings on the same mainloop. Gather, norma
 min(w[l], w[r]) and the final means stay ordinary torch autograd, so gradients reach `emb` and `weight_norm`
 exactly as in the reference (model/SNAG_loss.py:51,66-69).
 
-ial_loss (constructed but never called by SNAG — model/SNAG.py:53; live caller model/MCLEA.py:128-139): the eight
-contractions run on the tcgen05 mainloop through a differentiable `contract`; the softmax/KL on the materialised
-[B, 2B] logits is torch. A fused row-KL epilogue is listed as next work in DESIGN.md.
+ial_loss (constructed but never called by SNAG — model/SNAG.py:53; live caller model/MCLEA.py:128-139): the KL between
+the softmaxes of the two sets of logits is evaluated row-wise from the same fused sweeps as icl_loss — row log-sum-exps
+of both sets, the target probabilities written once in bf16 and contracted with the stacked embeddings — so no fp32
+[B, 2B] matrix exists; `norm=False` / unreduced outputs keep the materialising form (`_ial_materialised`).
 """
 from __future__ import annotations
 
@@ -257,6 +258,88 @@ class _Contract(torch.autograd.Function):
         return dP, dQ
 
 
+class _IalPair(torch.autograd.Function):
+    """Row-wise KL( softmax(q_i) || softmax(p_i) ) of both directions for unit rows: p from `src`, q from `tar`
+    (detached), logits laid out as in icl_loss ([cross | self with the diagonal masked] / tau).
+        KL_i = sum_j Q_ij (q_ij - p_ij) - lse_q_i + lse_p_i ,
+        sum_j Q_ij q_ij = (z^t_i . (Q Y^t)_i) / tau ,   sum_j Q_ij p_ij = (z^s_i . (Q Y^s)_i) / tau
+    so the forward needs the row log-sum-exps (EpiIclFwd sweeps), Q once in bf16 (EpiIclBwd with row coefficients
+    exp(1/tau - lse_q)) and two split-K products with the stacked embeddings. Backward: dL/dp = g (P - Q); both
+    probability matrices come from the dL/dlogits sweep with the ICL coefficient pattern (row term + transposed-role
+    term, see EpiIclBwd) run once on the src operands and once on the tar operands; their difference is contracted
+    with the stacked src embeddings and pushed through the normalise/gather backward."""
+
+    be = ops          # kernel backend (the CPU tests substitute tests/oracle_backend.py to check the host algebra)
+
+    @staticmethod
+    def forward(ctx, src, tar, idx_l, idx_r, inv_tau):
+        be = _IalPair.be
+        src, tar = src.contiguous(), tar.contiguous()
+        B = idx_l.numel()
+        Bp = ops.round_up(B, 256)
+        dev = src.device
+
+        def stack(emb):
+            S3 = torch.zeros((3 * Bp, ops.round_up(emb.shape[1], 64)), dtype=torch.bfloat16, device=dev)
+            be.prep_bf16(emb, idx_l, normalize=True, out=S3[0:Bp])
+            be.prep_bf16(emb, idx_r, normalize=True, out=S3[Bp:2 * Bp])
+            S3[2 * Bp:2 * Bp + B].copy_(S3[0:B])
+            return S3
+
+        Ss, St = stack(src), stack(tar)
+        Ds, Dt = src.shape[1], tar.shape[1]
+        zero = torch.zeros((B,), dtype=torch.float32, device=dev)
+        sides = ((slice(0, Bp), slice(Bp, 3 * Bp)), (slice(Bp, 2 * Bp), slice(0, 2 * Bp)))     # (anchors, [other ; this])
+        lse_p, lse_q, kl = [], [], []
+        for xs, ys in sides:
+            lp, _, _ = be.icl_side(Ss[xs], Ss[ys], B, Bp, inv_tau)
+            lq, _, _ = be.icl_side(St[xs], St[ys], B, Bp, inv_tau)
+            crq = (torch.exp(inv_tau - lq) / inv_tau).contiguous()            # EpiIclBwd multiplies by 1/tau: Q = cr E / tau
+            Q = be.icl_bwd_logits(St[xs], St[ys], B, Bp, inv_tau, crq, zero, zero, self_cols=False)   # row softmax of q
+            Ut = be.grad_contract(Q, St[ys].t().contiguous(), B, Dt)          # (Q Y^t) [B, Dt]
+            Us = be.grad_contract(Q, Ss[ys].t().contiguous(), B, Ds)
+            zq = (St[xs][:B, :Dt].float() * Ut).sum(1) * inv_tau
+            zp = (Ss[xs][:B, :Ds].float() * Us).sum(1) * inv_tau
+            kl.append(zq - zp - lq + lp)
+            lse_p.append(lp)
+            lse_q.append(lq)
+        ctx.save_for_backward(Ss, St, src, idx_l, idx_r, *lse_p, *lse_q)
+        ctx.dims = (B, Bp, Ds, inv_tau)
+        return kl[0], kl[1]
+
+    @staticmethod
+    def backward(ctx, g_a, g_b):
+        Ss, St, src, idx_l, idx_r, lpa, lpb, lqa, lqb = ctx.saved_tensors
+        B, Bp, Ds, inv_tau = ctx.dims
+        be = _IalPair.be
+        dev = Ss.device
+        g_a = torch.zeros_like(lpa) if g_a is None else g_a.contiguous().float()
+        g_b = torch.zeros_like(lpb) if g_b is None else g_b.contiguous().float()
+        zero = torch.zeros((B,), dtype=torch.float32, device=dev)
+        cpa, cpb = (g_a * torch.exp(inv_tau - lpa)).contiguous(), (g_b * torch.exp(inv_tau - lpb)).contiguous()
+        cqa, cqb = (g_a * torch.exp(inv_tau - lqa)).contiguous(), (g_b * torch.exp(inv_tau - lqb)).contiguous()
+        demb = torch.zeros_like(src)
+        # Both matrices are written centred on E(s = 0) = exp(-1/tau): at tau = 4 the softmaxes are within a few per cent
+        # of uniform, and rounding P and Q to bf16 before subtracting them would leave ~20 % noise on P - Q. The part
+        # removed by the centring, ebar/tau * (dr_i + dc_j) over the unmasked columns, is rank one and is added back to
+        # G . Y in fp32 below.
+        ebar = float(np.exp(-inv_tau))
+        sides = ((slice(0, Bp), slice(Bp, 3 * Bp), cpa, cpb, cqa, cqb, idx_l),
+                 (slice(Bp, 2 * Bp), slice(0, 2 * Bp), cpb, cpa, cqb, cqa, idx_r))
+        for xs, ys, cp_row, cp_col, cq_row, cq_col, idx in sides:
+            Gs = be.icl_bwd_logits(Ss[xs], Ss[ys], B, Bp, inv_tau, cp_row, cp_col, zero, ebar=ebar)   # g (P + transposed-role P) / tau
+            Gt = be.icl_bwd_logits(St[xs], St[ys], B, Bp, inv_tau, cq_row, cq_col, zero, ebar=ebar)   # the same for Q
+            dz = be.grad_contract(Gs - Gt, Ss[ys].t().contiguous(), B, Ds)
+            Y0 = Ss[ys][:B, :Ds].float()                       # cross columns: the other side
+            Y1 = Ss[ys][Bp:Bp + B, :Ds].float()                # self columns: this side (column i is masked for row i)
+            dr, dc0, dc1 = cp_row - cq_row, cp_col - cq_col, cp_row - cq_row
+            common = dr[:, None] * (Y0.sum(0) + Y1.sum(0))[None, :] - dr[:, None] * Y1 \
+                + (dc0 @ Y0 + dc1 @ Y1)[None, :] - dc1[:, None] * Y1
+            dz = dz + (ebar * inv_tau) * common
+            be.normalize_bwd_scatter(src, idx, dz.contiguous(), demb, True)
+        return demb, None, None, None, None
+
+
 class ial_loss(nn.Module):
     """model/SNAG_loss.py:130-202 — unimodal/multimodal KL alignment loss."""
 
@@ -275,6 +358,17 @@ class ial_loss(nn.Module):
         if self.inversion:
             raise NotImplementedError("inversion=True is unreachable from SNAG / MCLEA")
         idx_l, idx_r = _links_to_index(train_links, src_emb.device)
+        if not norm or self.reduction not in ("mean", "sum"):
+            return self._ial_materialised(src_emb, tar_emb, idx_l, idx_r, norm)
+        kl_a, kl_b = _IalPair.apply(src_emb.float(), tar_emb.detach().float(), idx_l, idx_r, float(1.0 / self.tau))
+        batch = idx_l.numel()
+        denom = float(batch * 2 * batch) if self.reduction == "mean" else 1.0     # .mean() runs over the [B, 2B] matrix (:195-197)
+        alpha = self.weight
+        return self.zoom * (alpha * kl_a.sum() / denom + (1 - alpha) * kl_b.sum() / denom)
+
+    def _ial_materialised(self, src_emb, tar_emb, idx_l, idx_r, norm):
+        """The reference's op sequence on materialised [B, 2B] logits (contractions on the tcgen05 mainloop through the
+        differentiable `_Contract`): kept for norm=False (logits not bounded by 1/tau) and unreduced outputs."""
         src_zis, src_zjs = src_emb.index_select(0, idx_l).float(), src_emb.index_select(0, idx_r).float()
         tar_zis, tar_zjs = tar_emb.index_select(0, idx_l).float(), tar_emb.index_select(0, idx_r).float()
         if norm:

@@ -512,7 +512,8 @@ def icl_side(X: torch.Tensor, Y: torch.Tensor, B: int, Bp: int, inv_tau: float, 
 
 
 def icl_bwd_logits(X: torch.Tensor, Y: torch.Tensor, B: int, Bp: int, inv_tau: float, cr: torch.Tensor,
-                   cc: torch.Tensor, dg: torch.Tensor, row0: int = 0, nx: int | None = None) -> torch.Tensor:
+                   cc: torch.Tensor, dg: torch.Tensor, row0: int = 0, nx: int | None = None,
+                   self_cols: bool = True, ebar: float = 0.0) -> torch.Tensor:
     """dL/dlogits of one ICL side as bf16 [nx, 2*Bp] for the anchors [row0, row0 + nx) of the batch (default: all Bp
     rows of the side); see snag_icl_bwd_logits."""
     _check_operand(X, "X")
@@ -525,7 +526,7 @@ def icl_bwd_logits(X: torch.Tensor, Y: torch.Tensor, B: int, Bp: int, inv_tau: f
     G = torch.empty((nx, 2 * Bp), dtype=torch.bfloat16, device=X.device)
     with _SweepTimer("sim_kernel<EpiIclBwd>", nx, 2 * Bp, X.shape[1]):
         call("snag_icl_bwd_logits", ptr(X), ptr(Y), B, Bp, row0, nx, X.shape[1], inv_tau, ptr(cr), ptr(cc), ptr(dg), ptr(G),
-             current_stream())
+             int(self_cols), float(ebar), current_stream())
     return G
 
 

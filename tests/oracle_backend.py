@@ -192,16 +192,16 @@ def icl_side(X, Y, B, Bp, inv_tau, row0=0, nx=None):
     return lse, lse - pos * inv_tau, pos
 
 
-def icl_bwd_logits(X, Y, B, Bp, inv_tau, cr, cc, dg, row0=0, nx=None):
+def icl_bwd_logits(X, Y, B, Bp, inv_tau, cr, cc, dg, row0=0, nx=None, self_cols=True, ebar=0.0):
     nx = Bp if nx is None else nx
     s, dead, gr = _icl_logits(X, Y, B, Bp, inv_tau, row0, nx)
-    E = torch.exp(s * inv_tau - inv_tau)
+    E = torch.exp(s * inv_tau - inv_tau) - ebar
     ok = gr < B
     crp = torch.zeros(Bp); crp[:B] = cr[:B]
     ccp = torch.zeros(Bp); ccp[:B] = cc[:B]
     dgp = torch.zeros(Bp); dgp[:B] = dg[:B]
     cr_i = torch.where(ok, crp[gr.clamp(max=Bp - 1)], torch.zeros(()))
-    colc = torch.cat([ccp, crp])                                         # part 0: cc_j, part 1: cr_j
+    colc = torch.cat([ccp, crp if self_cols else torch.zeros(Bp)])       # part 0: cc_j, part 1: cr_j (or nothing)
     G = (cr_i[:, None] + colc[None, :]) * E * inv_tau
     i = torch.arange(nx)[ok]
     G[i, gr[ok]] -= dgp[gr[ok]] * inv_tau                                # positive logit of part 0

@@ -185,6 +185,29 @@ def test_ial_golden(cuda_device, name):
     assert abs(same.item()) < 1e-7                                                     # KL(p || p) = 0
 
 
+@pytest.mark.parametrize("B,Ds,Dt,tau,red", [(700, 96, 320, 0.5, "mean"), (1000, 300, 1200, 4.0, "sum"), (130, 64, 64, 0.2, "mean")])
+def test_ial_fused_matches_materialised(cuda_device, B, Ds, Dt, tau, red):
+    """The row-wise fused evaluation (no [B, 2B] fp32 matrix) against the reference's op sequence on materialised
+    logits (`_ial_materialised`, same bf16 operands), loss and gradient."""
+    g = torch.Generator(device="cuda").manual_seed(B + Ds)
+    N = 2 * B + 50
+    base = torch.randn((N, Dt), generator=g, device=cuda_device)
+    tar = base + 0.3 * torch.randn((N, Dt), generator=g, device=cuda_device)
+    src0 = base[:, :Ds] + 0.5 * torch.randn((N, Ds), generator=g, device=cuda_device)
+    perm = torch.randperm(N, generator=g, device=cuda_device)
+    links = torch.stack([perm[:B], perm[B:2 * B]], 1)
+    crit = sloss.ial_loss(tau=tau, ab_weight=0.3, zoom=0.1, reduction=red)
+    il, ir = sloss._links_to_index(links, src0.device)
+    a = src0.clone().requires_grad_(True)
+    fused = crit(a, tar, links)
+    fused.backward()
+    b = src0.clone().requires_grad_(True)
+    mat = crit._ial_materialised(b, tar, il, ir, True)
+    mat.backward()
+    np.testing.assert_allclose(fused.item(), mat.item(), rtol=2e-2, atol=1e-9)
+    assert _relerr(a.grad, b.grad) < 3e-2
+
+
 def test_graphed_step_equals_eager(cuda_device):
     """The whole loss-layer slice (10 icl_loss calls, forward + backward) captured in one CUDA graph replays to the
     eager result, also after the batch is changed in place."""

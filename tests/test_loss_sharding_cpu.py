@@ -104,3 +104,44 @@ def test_gloo_sharded_icl_equals_unsharded(world, B, D, grads):
         except Exception as e:
             last = e
     raise last
+
+
+@pytest.mark.parametrize("B,Ds,Dt,tau,red", [(200, 48, 96, 4.0, "sum"), (130, 64, 64, 0.5, "mean")])
+def test_ial_row_form_host_algebra(monkeypatch, B, Ds, Dt, tau, red):
+    """ial_loss's fused evaluation (row-wise KL from log-sum-exps + one bf16 softmax matrix; gradient from two centred
+    dL/dlogits matrices plus the rank-one part added back on the host) against the reference's op sequence
+    (model/SNAG_loss.py:148-202 restated in torch on the same bf16-rounded unit rows), with the CPU stand-ins of the
+    kernels: checks the algebra, the masks and the scaling, independent of the GPU."""
+    import torch.nn.functional as F
+    monkeypatch.setattr(sloss._IalPair, "be", oracle_backend)
+    g = torch.Generator().manual_seed(B)
+    N = 2 * B + 20
+    base = torch.randn((N, Dt), generator=g)
+    tar = base + 0.3 * torch.randn((N, Dt), generator=g)
+    src0 = base[:, :Ds] + 0.5 * torch.randn((N, Ds), generator=g)
+    perm = torch.randperm(N, generator=g)
+    links = torch.stack([perm[:B], perm[B:2 * B]], 1)
+    alpha, zoom = 0.3, 0.1
+
+    def reference(src):
+        zs = F.normalize(src, dim=1)
+        zs = zs + (zs.to(torch.bfloat16).float() - zs).detach()              # the operands the kernels see
+        zt = F.normalize(tar, dim=1).to(torch.bfloat16).float()
+        out = 0
+        eye = torch.eye(B) * 1e9
+        for l, r, w in ((links[:, 0], links[:, 1], alpha), (links[:, 1], links[:, 0], 1 - alpha)):
+            p = torch.cat([zs[l] @ zs[r].T / tau, zs[l] @ zs[l].T / tau - eye], 1)
+            q = torch.cat([zt[l] @ zt[r].T / tau, zt[l] @ zt[l].T / tau - eye], 1)
+            kl = F.kl_div(F.log_softmax(p, 1), F.softmax(q, 1), reduction="none")
+            out = out + w * (kl.mean() if red == "mean" else kl.sum())
+        return zoom * out
+
+    crit = sloss.ial_loss(tau=tau, ab_weight=alpha, zoom=zoom, reduction=red)
+    a = src0.clone().requires_grad_(True)
+    fused = crit(a, tar, links)
+    fused.backward()
+    b = src0.clone().requires_grad_(True)
+    ref = reference(b)
+    ref.backward()
+    np.testing.assert_allclose(fused.item(), ref.item(), rtol=2e-3)
+    assert float((a.grad - b.grad).norm() / b.grad.norm()) < 1e-2
