@@ -241,7 +241,7 @@ def main():
          flops=20.0 * B * B * 300)
     ms = gpu_time(run_ial, reps=5)
     emit("a6", f"ial_loss fwd+bwd[B={B}, src D=300, tar D={D}] (one call, eager)", 0, ms, None,
-         "materialising variant: 6 distinct contractions fwd (12*B^2*Dbar, SURVEY 8d) + torch softmax/KL on [B,2B] + autograd",
+         "fused row-wise KL: 4 log-sum-exp sweeps + 2 softmax writers + 4 split-K products fwd, 4 dL/dlogits sweeps + 2 products bwd; algorithmic = 12*B^2*Dbar fwd (SURVEY 8d) x 3",
          flops=12.0 * B * B * (300 + D) / 2 * 3)
     out = os.path.join(ROOT, "gpurun_out", f"rows_{args.shape}.jsonl")
     os.makedirs(os.path.dirname(out), exist_ok=True)
