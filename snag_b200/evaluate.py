@@ -91,41 +91,53 @@ def _align_ranks_steps(be, X, Y, xn, yn, n: int, csls_k: int, use_csls: bool, wa
         # WHO they are; the neighbourhood means are then computed from those candidates with the canonical arithmetic
         # (ops.topk_rescore), so nv1 / nv2 equal the oracle's bit for bit whatever the accumulation order of the MMAs.
         col_val = col_idx = None
-        plan2 = two_sweep_plan(n, csls_k) if (two_sweep and ns > 0 and hasattr(be, "eval_rowcoltopk")) else None
+        plan2 = two_sweep_plan(n, csls_k) if (two_sweep and hasattr(be, "eval_rowcoltopk")) else None
+        part = pidx = None
         if plan2 is not None:
-            # two-sweep path: a pre-pass over a random sample of the sources bounds every target's k-th best from
-            # below; the main sweep then collects, per target, every source at or above that bound while it builds
-            # the row lists, so the swapped sweep is not needed.
+            # two-sweep path: sample pre-passes bound every target's k-th best and every source's KT-th best from
+            # below; the main sweep then builds the row lists from those bounds and collects, per target, every source
+            # at or above its bound, so the swapped sweep is not needed.
             m, cap = plan2
             gsel = torch.Generator(device="cpu").manual_seed(3408)
             sel = torch.randperm(n, generator=gsel)[:m].sort()[0].to(dev)
-            Xs, xns = X.index_select(0, sel), xn.index_select(0, sel)
-            part_s = be.eval_rowtopk(Ys, Xs, yns, xns, ns, m)
-            _, cand_s = be.topk_merge_mean(part_s, csls_k, want_nv=False, want_cand=True)
-            colthr, colb = be.col_threshold(cand_s, csls_k, yns)
-            # the same bound for the rows, from a sample of this rank's targets: the KT-th best of the sample can only
-            # be lower than the KT-th best overall, so lists seeded with it lose nothing and skip their warm-up
-            rowthr = None
-            # sample size: measured at 4 ranks, a sample of 8192 of 250k targets makes the pre-pass 21 ms cheaper but
-            # the sweep 88 ms slower (more insertions) than a sample of 32768: keep the full-size sample on every rank
-            ms = min(m, ns)
-            if ms >= KT:
-                selc = torch.randperm(ns, generator=gsel)[:ms].sort()[0].to(dev)
-                part_r = be.eval_rowtopk(X, Ys.index_select(0, selc), xn, yns.index_select(0, selc), n, ms)
+            selc = torch.randperm(n, generator=gsel)[:m].sort()[0].to(dev)
+            # Row bounds: the KT-th best of a source over a random sample of ALL targets can only be lower than its
+            # KT-th best overall, so lists seeded with it lose nothing and skip their warm-up. (A sample of 8192 instead
+            # of 32768 targets was measured at 4 ranks: pre-pass 21 ms cheaper, sweep 88 ms slower.) The sample is
+            # global and identical on every rank; each rank computes the bounds of its slice of the sources and the
+            # slices are all-gathered, so this pre-pass shrinks with the number of ranks like the sweeps do.
+            Yc, ync = Y.index_select(0, selc), yn.index_select(0, selc)
+            per_r = (n + world - 1) // world
+            a0, a1 = min(rank * per_r, n), min((rank + 1) * per_r, n)
+            thr_loc = torch.full((per_r,), float("-inf"), dtype=torch.float32, device=dev)
+            if a1 > a0:
+                part_r = be.eval_rowtopk(X[a0:a1], Yc, xn[a0:a1], ync, a1 - a0, m)
                 _, cand_r = be.topk_merge_mean(part_r, csls_k, want_nv=False, want_cand=True)
-                rowthr = (cand_r[:, 0] - 2e-6).contiguous()            # lists are ascending: [0] is the KT-th largest
+                thr_loc[:a1 - a0] = cand_r[:, 0] - 2e-6                # lists are ascending: [0] is the KT-th largest
                 del part_r, cand_r
                 launches += 2
-            part, pidx, stream, stream_row, stream_cnt = be.eval_rowcoltopk(X, Ys, xn, yns, n, ns, colthr, colb, cap, rowthr)
-            col_val, col_idx, overflow = be.col_cand_reduce(stream, stream_row, stream_cnt, ns, csls_k)
-            launches += 7
-            if int(overflow.item()) != 0:          # a candidate stream filled up: redo the columns the classic way
-                col_val = col_idx = None
-            del stream, stream_row
+            if world == 1:
+                rowthr = thr_loc[:n].contiguous()
+            else:
+                allt = yield ("all_gather", thr_loc)                    # [world, per_r]
+                rowthr = allt.reshape(-1)[:n].contiguous()
+            del Yc, ync
+            if ns > 0:
+                # column bounds: this rank's targets against a sample of the sources
+                Xs, xns = X.index_select(0, sel), xn.index_select(0, sel)
+                part_s = be.eval_rowtopk(Ys, Xs, yns, xns, ns, m)
+                _, cand_s = be.topk_merge_mean(part_s, csls_k, want_nv=False, want_cand=True)
+                colthr, colb = be.col_threshold(cand_s, csls_k, yns)
+                part, pidx, stream, stream_row, stream_cnt = be.eval_rowcoltopk(X, Ys, xn, yns, n, ns, colthr, colb, cap, rowthr)
+                col_val, col_idx, overflow = be.col_cand_reduce(stream, stream_row, stream_cnt, ns, csls_k)
+                launches += 7
+                if int(overflow.item()) != 0:      # a candidate stream filled up: redo the columns the classic way
+                    col_val = col_idx = None
+                del stream, stream_row, Xs, xns
         elif ns > 0:
             part, pidx = be.eval_rowtopk(X, Ys, xn, yns, n, ns, want_idx=True)
             launches += 1
-        else:
+        if part is None:
             part = torch.full((1, n, KT), float("-inf"), dtype=torch.float32, device=dev)
             pidx = torch.full((1, n, KT), -1, dtype=torch.int32, device=dev)
         _, cand, cidx = be.topk_merge_mean(part, csls_k, want_nv=False, part_idx=pidx)
