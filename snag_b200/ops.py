@@ -367,6 +367,7 @@ def _error_scale(xn: torch.Tensor, yn: torch.Tensor, dpad: int) -> float:
     return max(1.0, norm) * max(1.0, (dpad / 2048.0) ** 0.5)
 RANK_BAND_MIN_CAP = 1 << 20
 RANK_BAND_PER_ROW = 16         # initial list capacity per evaluated row + column
+RANK_BAND_MAX_CAP = 1 << 28    # beyond this many deferred elements (2 GB list) the in-kernel chain takes over
 
 
 def eval_rank(X, Y, xn, yn, nv1, nv2, g_row, g_col, row_gid0: int, col_gid0: int, n1: int, n2: int, use_csls: bool,
@@ -390,7 +391,7 @@ def eval_rank(X, Y, xn, yn, nv1, nv2, g_row, g_col, row_gid0: int, col_gid0: int
         eps = RANK_BAND_EPS * _error_scale(xn, yn, X.shape[1])
         cap = max(RANK_BAND_MIN_CAP, RANK_BAND_PER_ROW * (n1 + n2))
         row_save = col_save = None
-        while cap <= (1 << 28):
+        while cap <= RANK_BAND_MAX_CAP:
             band = torch.empty((cap,), dtype=torch.int64, device=X.device)
             band_cnt = torch.zeros((1,), dtype=torch.int32, device=X.device)
             if row_save is None:

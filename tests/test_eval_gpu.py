@@ -144,6 +144,23 @@ def test_rank_band_overflow_retries(cuda_device, monkeypatch):
         assert ops.LAST_RANK_INFO["deferred"] == n * (n - 1) and ops.LAST_RANK_INFO["cap"] >= n * (n - 1)
 
 
+def test_rank_chain_fallback_with_top3(cuda_device, monkeypatch):
+    """When the deferral list would exceed its maximum size (everything tied: constant embeddings) the in-kernel fp32
+    chain with its exact-tie path takes over. That path judges ties on the tensor core's own dot products, so the
+    check uses dyadic rows (every product and partial sum exact): ranks and top-3 ids are those of a stable sort."""
+    n, d = 300, 64
+    xc = np.full((n, d), 0.125, np.float32)                      # ||row||^2 = 1, s = 1 exactly
+    Xc, Yc, xnc, ync = _prep(xc, xc, cuda_device)
+    monkeypatch.setattr(ops, "RANK_BAND_MIN_CAP", 16)
+    monkeypatch.setattr(ops, "RANK_BAND_PER_ROW", 0)
+    monkeypatch.setattr(ops, "RANK_BAND_MAX_CAP", 64)
+    res = evaluate.align_ranks(Xc, Yc, xnc, ync, n, 3, True, want_top3=True)
+    assert ops.LAST_RANK_INFO["mode"] == "chain"
+    np.testing.assert_array_equal(res.rank_l2r.cpu().numpy(), np.arange(n))
+    np.testing.assert_array_equal(res.rank_r2l.cpu().numpy(), np.arange(n))
+    np.testing.assert_array_equal(res.top3_idx.cpu().numpy(), np.tile(np.arange(3), (n, 1)))
+
+
 @pytest.mark.parametrize("n,d,k", [(1, 64, 1), (2, 8, 2), (127, 40, 5), (129, 64, 10), (257, 300, 16), (513, 64, 3)])
 def test_ragged_shapes(cuda_device, n, d, k):
     x, y = _clustered(n, d, 1.0, n)
