@@ -146,3 +146,40 @@ def test_runner_test_mirror(cuda_device, tmp_path):
     assert (got[:, 1] == ref["rank_l2r"]).mean() > 0.99
     assert (got[:, 2] == left).all() and (got[:, 3] == right).all()
     assert (got[:, 4:7] == right[ref["top3"]]).mean() > 0.99
+
+
+@needs_ref
+@pytest.mark.parametrize("name", ["fusion_m4_d64", "fusion_m6_d96"])
+def test_mformer_fusion_mirror_on_cpu(monkeypatch, name):
+    """The drop-in MformerFusion.forward (snag_b200.fusion) run on the reference's own module instance (weights restored
+    from the golden file) reproduces what the reference's forward returned — with the CUDA tail replaced by the oracle's
+    restatement, so that the mirrored control flow around the reference's transformer layers is checked on the CPU."""
+    import io
+    import types as _types
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    from refshim import load_reference
+    load_reference()
+    import importlib
+    from snag_b200 import fusion
+    from tests.conftest import load_golden
+    fx = load_golden(name)
+    M, D, heads = int(fx["M"]), int(fx["D"]), int(fx["heads"])
+    tools = importlib.import_module("model.SNAG_tools")
+    args = _types.SimpleNamespace(num_hidden_layers=1, num_attention_heads=heads, hidden_size=D, intermediate_size=2 * D,
+                                  use_intermediate=1)
+    mod = tools.MformerFusion(args, modal_num=M, with_weight=1)
+    mod.load_state_dict(torch.load(io.BytesIO(fx["state"].tobytes())))
+    mod.eval()
+
+    def cpu_tail(embs, weight_norm, weight_norm_fz):
+        j, jf = oracle.joint_fuse([e.detach().numpy() for e in embs], weight_norm.detach().numpy(),
+                                  weight_norm_fz.detach().numpy())
+        return torch.from_numpy(j), torch.from_numpy(jf)
+    monkeypatch.setattr(fusion, "joint_embeddings", cpu_tail)
+    embs = [torch.from_numpy(fx[f"emb{m}"]) for m in range(M)] + [None] * (6 - M)
+    with torch.no_grad():
+        joint, joint_fz, hidden, weight_norm = fusion.MformerFusion_forward(mod, embs)
+    np.testing.assert_allclose(weight_norm.numpy(), fx["weight_norm"], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(hidden.numpy(), fx["hidden"], rtol=0, atol=1e-5)
+    np.testing.assert_allclose(joint.numpy(), fx["joint"], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(joint_fz.numpy(), fx["joint_fz"], rtol=0, atol=2e-6)
