@@ -15,6 +15,14 @@ counters are exchanged with NCCL. Rank 0 prints ONE JSON line (contract in the t
              D2H of the ranks, host Hits/MR/MRR reduction — all inside the timed region
   roofline   the dominant kernel (fused tcgen05 sweep) against the measured bf16 tensor peak
   cpu_baseline  the oracle port timed on this host's cores on a bounded sample of the same workload
+  parity_audit  >= 512 random sources and >= 512 random targets of the LAST timed evaluation re-scored by the oracle
+             over all n partners (neighbourhood mean, ground-truth distance, rank): mismatches must be 0
+  train      the metric's second half — train steps/sec of the loss-layer slice (2 + 2M icl_loss calls fwd+bwd) at
+             configs[4] (B = 16 384) and at the reference's own batch (B = 3500), anchors sharded over the N ranks
+  snag_step  the full SNAG training step (encoder + losses + backward) of the UNMODIFIED reference model class from
+             baseline/_ref on cuda:0, stock vs with snag_b200.patch applied (rank 0)
+  reference_gpu_eager  the reference's own GPU op sequence (torch-eager cuBLAS fp32 + 2n torch.sort/.item(),
+             main.py:385-429; icl_loss fwd+bwd) on cuda:0 at the reference's sizes — context for a SNAG user
 `--impl reference` times the CPU port alone (rank 0 only) and prints the same line with "impl": "reference".
 """
 from __future__ import annotations
@@ -212,63 +220,114 @@ def run_reference(args, name, n, d, k, sigma, desc):
 
 
 # ================================================================================================ GPU arm
-def run_snag(args, name, n, d, k, sigma, desc):
+class Ctx:
+    """One process per GPU: rank / device / process group of this run (torch.distributed NCCL when launched by torchrun)."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if self.world != args.gpus:
+            if self.world == 1 and args.gpus > 1:
+                raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
+            raise SystemExit(f"WORLD_SIZE={self.world} does not match --gpus {args.gpus}")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        self.group = None
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+            self.group = dist.group.WORLD
+        self.peaks = load_peaks()
+
+    def barrier(self):
+        import torch
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(self, x: float) -> float:
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def close(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+            dist.destroy_process_group()
+
+
+def parity_audit(X, Y, n, d, k, res, n_rows=512, n_cols=512):
+    """Sampled oracle audit of one finished evaluation (rank 0, after the timed region): `n_rows` random sources against
+    ALL n targets and `n_cols` random targets against ALL n sources are re-scored by oracle/snag_oracle.c (fp64
+    index-order dots, the reference's fp32 chain, stable tie-break) from the very bf16 operands the GPU consumed.
+    Compared bit for bit: the entity's CSLS neighbourhood mean, its ground-truth distance and its rank (the rank given
+    the GPU's neighbourhood means of the other side, which the opposite sample audits)."""
+    import numpy as np
+    import torch
+    from oracle import oracle
+    oracle.set_threads()
+    t0 = time.perf_counter()
+    rng = np.random.RandomState(SEED + 1)
+    rows = np.sort(rng.choice(n, size=min(n_rows, n), replace=False))
+    cols = np.sort(rng.choice(n, size=min(n_cols, n), replace=False))
+    xh = X[:n, :d].float().cpu().numpy()
+    yh = Y[:n, :d].float().cpu().numpy()
+    nv1, nv2 = res.nv1.cpu().numpy(), res.nv2.cpu().numpy()
+    g, l2r, r2l = res.g.cpu().numpy(), res.rank_l2r.cpu().numpy(), res.rank_r2l.cpu().numpy()
+    a = oracle.audit(xh[rows], yh, rows, True, k, nv2, False)
+    b = oracle.audit(yh[cols], xh, cols, True, k, nv1, True)
+    mism = {"nv1": int((a["nv"] != nv1[rows]).sum()), "g_rows": int((a["g"] != g[rows]).sum()),
+            "rank_l2r": int((a["rank"] != l2r[rows]).sum()), "nv2": int((b["nv"] != nv2[cols]).sum()),
+            "g_cols": int((b["g"] != g[cols]).sum()), "rank_r2l": int((b["rank"] != r2l[cols]).sum())}
+    return {"rows": int(len(rows)), "cols": int(len(cols)), "partners_each": int(n), "mismatches": int(sum(mism.values())),
+            "by_quantity": mism, "pairs_rescored": int((len(rows) + len(cols)) * n), "seconds": round(time.perf_counter() - t0, 1),
+            "oracle_threads": oracle.max_threads(),
+            "checked": "CSLS neighbourhood mean, ground-truth distance and rank of every sampled entity, bit-exact"}
+
+
+def eval_bench(ctx, args, name):
+    """The alignment-evaluation workload `name` on ctx.world GPUs -> dict of bench-line fields."""
     import torch
     import torch.distributed as dist
     from snag_b200 import evaluate, ops
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
-        raise SystemExit(f"WORLD_SIZE={world} does not match --gpus {args.gpus}")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    group = None
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-        group = dist.group.WORLD
-    peaks = load_peaks()
+    n, d, k, sigma, desc = WORKLOADS[name]
+    world, rank, dev, group, peaks = ctx.world, ctx.rank, ctx.dev, ctx.group, ctx.peaks
     W, K = max(3, args.warmup), max(1, args.steps)
-
     emb, left, right = synth_tables(n, d, sigma, dev)
     dpad = ops.round_up(d, 64)
     sweep_events = []                       # (name, start, end) per fused-sweep launch inside the timed region
-
-    def timed_sweeps(enable):
-        ops.SWEEP_EVENT_SINK = sweep_events if enable else None
+    keep = {}
 
     def step_device():
         X, xn = ops.prep_bf16(emb, left, True)
         Y, yn = ops.prep_bf16(emb, right, True)
+        keep["ops"] = (X, Y)
         return evaluate.align_ranks(X, Y, xn, yn, n, k, True, False, group)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
 
     # ---------------------------------------------------------------- device-resident timing -> value, roofline
     res = None
     for _ in range(W):
         res = step_device()
-    barrier()
-    timed_sweeps(True)
+    ctx.barrier()
+    ops.SWEEP_EVENT_SINK = sweep_events
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clocks:
-        barrier()
+    with ClockSampler(ctx.local) as clocks:
+        ctx.barrier()
         e0.record()
         for _ in range(K):
             res = step_device()
         e1.record()
-        barrier()
-    timed_sweeps(False)
-    ms = torch.tensor([e0.elapsed_time(e1) / K], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_per_step = float(ms.item())
+        ctx.barrier()
+    ops.SWEEP_EVENT_SINK = None
+    ms_per_step = ctx.max_over_ranks(e0.elapsed_time(e1) / K)
     launches_per_step = res.launches + 2
     # per-kernel durations of the fused sweeps (this rank), algorithmic flops = 2 * rows * cols * D per launch
     kern = {}
@@ -291,69 +350,66 @@ def run_snag(args, name, n, d, k, sigma, desc):
                 "frac_of_burst_peak": kstats[dom]["tflops"] / peaks["tensor_burst"],
                 "algorithmic_flops_per_launch": kern[dom]["flops"], "kernels": kstats,
                 "sweeps_per_step": sweeps, "executed_tflops_whole_step": sweeps * 2.0 * n * n * d / world / ms_per_step / 1e9}
-
+    out = {"ms_per_step": ms_per_step, "kernels": kstats, "roofline": roofline, "clocks": clocks.summary(),
+           "launches_per_step": launches_per_step, "n": n, "d": d, "k": k, "sigma": sigma, "desc": desc, "dpad": dpad,
+           "rank_sweep": res.info.get("rank_sweep", {}), "steps": K, "warmup": W}
     if args.profile_run:
-        if rank == 0:
-            print(json.dumps({"profile_run": True, "workload": name, "ms_per_step": ms_per_step, "kernels": kstats}), flush=True)
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        return out
+    # ---------------------------------------------------------------- sampled oracle audit of the last timed evaluation
+    if rank == 0 and not args.no_audit:
+        X, Y = keep["ops"]
+        out["parity_audit"] = parity_audit(X, Y, n, d, k, res)
+    keep.clear()
+    ctx.barrier()
     # ---------------------------------------------------------------- end to end from pinned host memory -> e2e
-    c0, c1 = (0, n) if world == 1 else (rank * ((n + world - 1) // world), min(n, (rank + 1) * ((n + world - 1) // world)))
+    per = (n + world - 1) // world
+    c0, c1 = (0, n) if world == 1 else (rank * per, min(n, (rank + 1) * per))
     host = torch.empty((2, max(c1 - c0, 1), d), dtype=torch.float32).pin_memory()
     host[0, :c1 - c0].copy_(emb[c0:c1])
     host[1, :c1 - c0].copy_(emb[n + c0:n + c1])
-    del emb
+    del emb, res
     torch.cuda.empty_cache()
 
     def step_e2e():
-        out = evaluate.evaluate_alignment_host(host[0, :c1 - c0], host[1, :c1 - c0], n, c0, csls=True, csls_k=k, group=group)
-        return out
+        return evaluate.evaluate_alignment_host(host[0, :c1 - c0], host[1, :c1 - c0], n, c0, csls=True, csls_k=k, group=group)
 
     n_e2e = 2 if n >= 500_000 else 5
-    out = step_e2e()
-    barrier()
+    o = step_e2e()
+    ctx.barrier()
     t0 = time.perf_counter()
     for _ in range(n_e2e):
-        out = step_e2e()
-    barrier()
-    dt = torch.tensor([(time.perf_counter() - t0) / n_e2e], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-    e2e = {"value": n * n / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": int(2 * (c1 - c0) * d * 4) * 1,
-           "d2h_bytes_per_step": int(2 * n * 4), "ms_per_step": float(dt.item()) * 1e3, "steps": n_e2e,
-           "note": "per rank: H2D of its slice of both fp32 tables from pinned memory (+ NVLink all-gather of the bf16 "
-                   "operands when sharded), evaluation, D2H of both rank vectors, host Hits/MR/MRR"}
-    metrics = out["l2r"]
+        o = step_e2e()
+    ctx.barrier()
+    dt = ctx.max_over_ranks((time.perf_counter() - t0) / n_e2e)
+    out["e2e"] = {"value": n * n / dt, "unit": UNIT, "h2d_bytes_per_step": int(2 * (c1 - c0) * d * 4),
+                  "d2h_bytes_per_step": int(2 * n * 4), "ms_per_step": dt * 1e3, "steps": n_e2e,
+                  "note": "per rank: H2D of its slice of both fp32 tables from pinned memory (+ NVLink all-gather of the bf16 "
+                          "operands when sharded), evaluation, D2H of both rank vectors, host Hits/MR/MRR"}
+    m = o["l2r"]
+    out["quality"] = {"hits@1_l2r": float(m.acc[0]), "hits@10_l2r": float(m.acc[1]), "mrr_l2r": m.mrr}
+    del host, o
+    torch.cuda.empty_cache()
+    return out
 
-    if rank == 0:
-        n_s = min(CPU_SAMPLE_N, n)
-        cb = cpu_port_sample(n_s, d, k, sigma, 3, 1)
-        extra_ref = reference_steps_sample(min(2048, n), d, k, sigma)
-        line = {
-            "metric": METRIC, "value": n * n / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "bf16 operands, fp32 accumulate (tcgen05 kind::f16), fp32 CSLS chain, int32 ranks",
-            "data": "synthetic",
-            "config": {"workload": name, "description": desc, "n_pairs": n, "width": d, "padded_width": dpad, "csls_k": k,
-                       "sigma": sigma, "seed": SEED, "parallelism": f"targets sharded over {world} rank(s)",
-                       "l2": "inputs larger than L2 (no flush needed)" if 2 * n * dpad * 2 > 200e6 else
-                             "inputs smaller than L2; every step re-reads the fp32 table and rewrites the operands "
-                             f"({2 * 2 * n * d * 4 / 1e6:.0f} MB), which exceeds and evicts L2"},
-            "clocks": clocks.summary(),
-            "e2e": e2e,
-            "gpu_launches": launches_per_step * K,
-            "roofline": roofline,
-            "cpu_baseline": {kk: cb[kk] for kk in ("value", "unit", "cores", "kind", "sample")},
-            "reference_literal_steps": extra_ref,
-            "quality": {"hits@1_l2r": float(metrics.acc[0]), "hits@10_l2r": float(metrics.acc[1]), "mrr_l2r": metrics.mrr},
-            "algorithmic_tflops": 2.0 * n * n * d / (ms_per_step * 1e-3) / 1e12,
-            "rank_sweep": res.info.get("rank_sweep", {}),
-        }
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+
+def eval_line(ctx, args, name, ev):
+    n, d, k = ev["n"], ev["d"], ev["k"]
+    ms = ev["ms_per_step"]
+    return {
+        "metric": METRIC, "value": n * n / (ms * 1e-3), "unit": UNIT, "n_gpus": ctx.world, "steps": ev["steps"],
+        "warmup": ev["warmup"], "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "bf16 operands, fp32 accumulate (tcgen05 kind::f16), fp32 CSLS chain, int32 ranks",
+        "data": "synthetic",
+        "config": {"workload": name, "description": ev["desc"], "n_pairs": n, "width": d, "padded_width": ev["dpad"],
+                   "csls_k": k, "sigma": ev["sigma"], "seed": SEED, "parallelism": f"targets sharded over {ctx.world} rank(s)",
+                   "l2": "inputs larger than L2 (no flush needed)" if 2 * n * ev["dpad"] * 2 > 200e6 else
+                         "inputs smaller than L2; every step re-reads the fp32 table and rewrites the operands "
+                         f"({2 * 2 * n * d * 4 / 1e6:.0f} MB), which exceeds and evicts L2"},
+        "clocks": ev["clocks"], "e2e": ev.get("e2e"), "gpu_launches": ev["launches_per_step"] * ev["steps"],
+        "roofline": ev["roofline"], "quality": ev.get("quality"),
+        "algorithmic_tflops": 2.0 * n * n * d / (ms * 1e-3) / 1e12, "rank_sweep": ev["rank_sweep"],
+        "parity_audit": ev.get("parity_audit"),
+    }
 
 
 # ================================================================================================ training slice
@@ -414,45 +470,22 @@ def cpu_icl_sample(B_s, M, dm, steps, B_full=None):
                       f"workload's batch (the step is O(B^2 D))"}
 
 
-def run_train(args, name):
-    import numpy as np
+def train_bench(ctx, args, name, cpu_leg=True):
+    """The loss-layer slice `name` (2 + 2M icl_loss calls, forward + backward) on ctx.world GPUs -> bench-line fields."""
     import torch
-    import torch.distributed as dist
     from snag_b200 import loss as sloss, ops
 
     B, M, dm, desc = TRAIN_WORKLOADS[name]
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.impl == "reference":
-        if rank == 0:
-            cb = cpu_icl_sample(min(B, 2048), M, dm, max(1, args.steps), B)
-            print(json.dumps({"impl": "reference", "metric": TRAIN_METRIC, "value": cb["value"], "unit": "steps/s",
-                              "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / cb["value"],
-                              "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                              "config": {"workload": name, "description": desc, "sampled": cb["sample"]}, "cpu_baseline": cb,
-                              "e2e": {"value": cb["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                              "gpu_launches": 0}), flush=True)
-        return
-    if world != args.gpus:
-        raise SystemExit(f"WORLD_SIZE={world} does not match --gpus {args.gpus}")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    group = None
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-        group = dist.group.WORLD
-    peaks = load_peaks()
+    world, rank, dev, group, peaks = ctx.world, ctx.rank, ctx.dev, ctx.group, ctx.peaks
     W, K = max(3, args.warmup), max(1, args.steps)
     streams, hidden, joint, joint_fz, wn, links, leaves = _train_tables(B, M, dm, dev)
-    layer = sloss.SnagLossLayer(tau=0.1, ab_weight=0.5, awloss=True).to(dev)
+    layer = sloss.SnagLossLayer(tau=0.1, ab_weight=0.5).to(dev)       # --awloss 0 (config.py:114): the reference's default
     if group is not None:
         layer.distribute(group, grads="gather")
     links_pinned = torch.from_numpy(links).pin_memory()
-
     links_dev = links_pinned.to(dev)
-    use_graph = not args.no_graph and (world == 1 or args.graph_multi)
     eager_ms = None
+    graph_note = None
 
     def eager_step():
         for t in leaves:
@@ -461,20 +494,32 @@ def run_train(args, name):
         loss.backward()
         return loss
 
+    for _ in range(3):
+        eager_step()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ctx.barrier()
+    a.record()
+    for _ in range(K):
+        eager_step()
+    b.record()
+    ctx.barrier()
+    eager_ms = ctx.max_over_ranks(a.elapsed_time(b) / K)
+    # Whole-step CUDA graph: every entry point of libsnag_b200.so only enqueues on the stream it is given, and NCCL's
+    # all-gathers are capturable, so the sharded step replays as one graph launch as well (at the reference's batch
+    # sizes the eager step is launch bound). Every rank must take the same path: agree on the outcome of the capture.
+    use_graph = not args.no_graph
+    graphed = None
     if use_graph:
-        # the eager step first, for the record: at the reference's batch sizes it is launch bound
-        for _ in range(3):
-            eager_step()
-        torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(K):
-            eager_step()
-        b.record()
-        torch.cuda.synchronize()
-        eager_ms = a.elapsed_time(b) / K
-        from snag_b200.graphs import GraphedStep
-        graphed = GraphedStep(lambda: layer(streams, hidden, joint, joint_fz, links_dev, wn), leaves)
+        ok = 1.0
+        try:
+            from snag_b200.graphs import GraphedStep
+            graphed = GraphedStep(lambda: layer(streams, hidden, joint, joint_fz, links_dev, wn), leaves)
+        except Exception as exc:                          # noqa: BLE001 — reported on the bench line, eager numbers stand
+            ok, graph_note = 0.0, f"graph capture failed on rank {rank}: {type(exc).__name__}: {exc}"[:300]
+        if -ctx.max_over_ranks(-ok) < 1.0:
+            use_graph, graphed = False, None
+            graph_note = graph_note or "graph capture failed on another rank"
 
     def step(from_host):
         if from_host:                                       # this step's batch arrives from pinned host memory
@@ -482,39 +527,29 @@ def run_train(args, name):
         loss = graphed() if use_graph else eager_step()
         return loss.item() if from_host else loss
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     for _ in range(W):
         step(False)
-    barrier()
-    events = []
-    if not use_graph:
-        ops.SWEEP_EVENT_SINK = events
+    ctx.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clocks:
-        barrier()
+    with ClockSampler(ctx.local) as clocks:
+        ctx.barrier()
         e0.record()
         for _ in range(K):
             step(False)
         e1.record()
-        barrier()
+        ctx.barrier()
+    ms_per_step = ctx.max_over_ranks(e0.elapsed_time(e1) / K)
+    # per-kernel CUDA events cannot be recorded into a replayed graph: time the sweeps of K eager steps of the same work
+    events = []
     ops.SWEEP_EVENT_SINK = events
-    ms = torch.tensor([e0.elapsed_time(e1) / K], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_per_step = float(ms.item())
-    if use_graph:                     # per-kernel CUDA events cannot be recorded into a replayed graph: time the sweeps of
-        for _ in range(K):            # K eager steps of the same work instead (same kernels, same arguments)
-            eager_step()
-        torch.cuda.synchronize()
+    for _ in range(K):
+        eager_step()
+    torch.cuda.synchronize()
     ops.SWEEP_EVENT_SINK = None
     kern = {}
-    for nm, a, b, rows, cols, depth in events:
+    for nm, ea, eb, rows, cols, depth in events:
         e = kern.setdefault(nm, {"ms": 0.0, "flops": 0.0, "launches": 0})
-        e["ms"] += a.elapsed_time(b)
+        e["ms"] += ea.elapsed_time(eb)
         e["flops"] += 2.0 * rows * cols * depth
         e["launches"] += 1
     kstats = {nm: {"launches_per_step": v["launches"] // K, "ms_per_step": v["ms"] / K, "tflops": v["flops"] / v["ms"] / 1e9}
@@ -527,39 +562,255 @@ def run_train(args, name):
     roofline = {"bound": "tensor", "kernel": dom, "achieved": kstats[dom]["tflops"], "peak": peaks["tensor_burst"],
                 "unit": "TFLOP/s", "frac": kstats[dom]["tflops"] / peaks["tensor_burst"], "traffic": None,
                 "peak_source": peaks["source"] + ", bf16_tflops (burst: launches of a few ms, timed alone with CUDA events)",
-                "kernels": kstats, "note": "flops counted on the padded contraction width the kernel executes; "
-                "sim_kernel<EpiWrite> is the gradient GEMM dX = G.[other;this] (contraction width 2*Bp)",
+                "kernels": kstats, "note": "flops counted on the padded contraction width the kernel executes",
                 "algorithmic_flops_per_step": alg_fwd + alg_bwd,
                 "algorithmic_tflops_whole_step": (alg_fwd + alg_bwd) / world / ms_per_step / 1e9}
     # end to end: the step's input (the batch of links) comes from pinned host memory, the loss goes back to the host
     step(True)
-    barrier()
+    ctx.barrier()
     t0 = time.perf_counter()
     for _ in range(K):
         lv = step(True)
-    barrier()
-    dt = torch.tensor([(time.perf_counter() - t0) / K], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-    if rank == 0:
-        cb = cpu_icl_sample(min(B, 2048), M, dm, 1, B)
-        line = {"metric": TRAIN_METRIC, "value": 1e3 / ms_per_step, "unit": "steps/s", "n_gpus": world, "steps": K, "warmup": W,
-                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-                "dtype": "bf16 operands, fp32 accumulate (tcgen05 kind::f16), fp32 softmax statistics, bf16 dL/dlogits",
-                "data": "synthetic",
-                "config": {"workload": name, "description": desc, "batch": B, "modalities": M, "width": dm, "tau": 0.1,
-                           "icl_calls_per_step": n_calls, "parallelism": f"anchors sharded over {world} rank(s)",
-                           "cuda_graph": use_graph, "eager_ms_per_step": eager_ms,
-                           "l2": "every step rewrites the bf16 operands and dL/dlogits (> L2) between launches"},
-                "clocks": clocks.summary(),
-                "e2e": {"value": 1.0 / float(dt.item()), "unit": "steps/s", "h2d_bytes_per_step": int(links_pinned.numel() * 4),
-                        "d2h_bytes_per_step": 4, "ms_per_step": float(dt.item()) * 1e3, "loss": lv},
-                "gpu_launches": sum(v["launches"] for v in kern.values()) + 4 * n_calls * K,
-                "roofline": roofline, "cpu_baseline": cb}
+    ctx.barrier()
+    dt = ctx.max_over_ranks((time.perf_counter() - t0) / K)
+    out = {"metric": TRAIN_METRIC, "value": 1e3 / ms_per_step, "unit": "steps/s", "n_gpus": world, "steps": K, "warmup": W,
+           "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+           "dtype": "bf16 operands, fp32 accumulate (tcgen05 kind::f16), fp32 softmax statistics",
+           "data": "synthetic",
+           "config": {"workload": name, "description": desc, "batch": B, "modalities": M, "width": dm, "tau": 0.1,
+                      "icl_calls_per_step": n_calls, "parallelism": f"anchors sharded over {world} rank(s)", "awloss": 0,
+                      "cuda_graph": use_graph, "graph_note": graph_note, "eager_ms_per_step": eager_ms,
+                      "l2": "every step rewrites the bf16 operands and gradients (> L2) between launches"},
+           "clocks": clocks.summary(),
+           "e2e": {"value": 1.0 / dt, "unit": "steps/s", "h2d_bytes_per_step": int(links_pinned.numel() * 4),
+                   "d2h_bytes_per_step": 4, "ms_per_step": dt * 1e3, "loss": lv},
+           "gpu_launches": (sum(v["launches"] for v in kern.values()) // K + 4 * n_calls) * K,
+           "roofline": roofline}
+    if cpu_leg and rank == 0:
+        out["cpu_baseline"] = cpu_icl_sample(min(B, 1024), M, dm, 1, B)
+    del graphed, layer, streams, hidden, joint, joint_fz, wn, leaves
+    torch.cuda.empty_cache()
+    return out
+
+
+# ================================================================================================ context legs (rank 0)
+def reference_gpu_eager(dev, n=10500, d=1200, k=10, sigma=8.0, B=3500, M=4, dm=300):
+    """What a SNAG user runs today on the same GPU (main.py:517-519 puts the model on one GPU): the reference's literal
+    evaluation sequence — pairwise_distances (src/utils.py:202-218), csls_sim (:417-435), then 2n x (torch.sort of a
+    row / column + .item()), main.py:385-429 — and its icl_loss forward + backward (model/SNAG_loss.py:58-128) for the
+    2 + 2M calls of one step, all in torch-eager fp32 on CUDA (cuBLAS SGEMM, TF32 off as in the reference). Imported
+    from the unmodified reference when baseline/_ref travels with the repo, restated with the same torch calls
+    otherwise. Context only: it is a GPU number of the reference, not the CPU baseline the contract asks for."""
+    import numpy as np
+    import torch
+    import torch.nn.functional as F
+    out = {}
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "baseline"))
+        from baseline import harness
+        harness.load_reference()
+        import model.SNAG_loss as ref_loss
+        import src.utils as ref_utils
+        pd, cs, icl_cls, src = ref_utils.pairwise_distances, ref_utils.csls_sim, ref_loss.icl_loss, "baseline/_ref (unmodified reference functions)"
+    except Exception:                      # noqa: BLE001 — no reference checkout on this machine: same torch calls, restated
+        def pd(x, y):
+            xn, yn = (x ** 2).sum(1).view(-1, 1), (y ** 2).sum(1).view(1, -1)
+            return torch.clamp(xn + yn - 2.0 * torch.mm(x, y.t()), 0.0, np.inf)
+
+        def cs(sim, kk):
+            nv1, nv2 = torch.mean(torch.topk(sim, kk)[0], 1), torch.mean(torch.topk(sim.t(), kk)[0], 1)
+            return (2 * sim.t() - nv1).t() - nv2
+        icl_cls, src = None, "restated torch calls (no reference checkout here)"
+    emb, left, right = synth_tables(n, d, sigma, dev)
+    torch.cuda.synchronize()
+
+    def eval_once():
+        fe = F.normalize(emb)
+        distance = pd(fe[left], fe[right])
+        distance = 1 - cs(1 - distance, k)
+        mrr = 0.0
+        for idx in range(n):
+            _, indices = torch.sort(distance[idx, :], descending=False)
+            rank_ = (indices == idx).nonzero(as_tuple=False).squeeze().item()
+            mrr += 1.0 / (rank_ + 1)
+        for idx in range(n):
+            _, indices = torch.sort(distance[:, idx], descending=False)
+            rank_ = (indices == idx).nonzero(as_tuple=False).squeeze().item()
+            mrr += 1.0 / (rank_ + 1)
+        return mrr
+
+    eval_once() if n <= 4096 else None
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    eval_once()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    out["eval"] = {"value": n * n / dt, "unit": UNIT, "seconds": dt, "n_pairs": n, "width": d, "csls_k": k,
+                   "what": "F.normalize + pairwise_distances + csls_sim + 2n x (torch.sort + .item()), fp32, cuda:0"}
+    del emb
+    torch.cuda.empty_cache()
+    if icl_cls is not None:
+        streams, hidden, joint, joint_fz, wn, links, leaves = _train_tables(B, M, dm, dev)
+        crit = icl_cls(tau=0.1, ab_weight=0.5, n_view=2)
+        cols = (3, 2, 1, 0, 4, 5)
+
+        def step():
+            for t in leaves:
+                t.grad = None
+            w = wn * wn.shape[1]
+            tot = crit(joint, links) + crit(joint_fz, links)
+            tot = tot + sum(crit(e, links, weight_norm=w[:, c]) for e, c in zip(streams, cols) if e is not None)
+            tot = tot + sum(crit(h, links) for h in hidden if h is not None)
+            tot.backward()
+            return tot
+        for _ in range(2):
+            step()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        reps = 5
+        for _ in range(reps):
+            step().item()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / reps
+        out["train_slice"] = {"value": 1.0 / dt, "unit": "steps/s", "ms_per_step": dt * 1e3, "batch": B, "modalities": M,
+                              "what": f"{2 + 2 * M} reference icl_loss calls fwd+bwd (unmodified class), fp32, cuda:0"}
+    out["source"] = src
+    return out
+
+
+def snag_full_step(dev, n_side=19797, n_links=15000, batch=3500, steps=5):
+    """the full training step of the UNMODIFIED reference SNAG model (GAT encoder, modality
+    projections, fusion transformer, 2 + 2M icl_loss calls, backward, AdamW) at the C1 shape — N = 39 594 entities,
+    4 500 seed links, B = 3500, per-modality width 300 — on cuda:0, first stock, then with snag_b200.patch applied
+    (new model instance, same state dict). Data: baseline/harness.py's synthetic graph pair in the reference's own
+    file format. Returns None when the reference does not travel with the repo (baseline/_ref)."""
+    import logging
+    import shutil
+    import tempfile
+    import numpy as np
+    import torch
+    from baseline import harness
+    if harness.ref_root() is None:
+        return None
+    from snag_b200 import patch as spatch
+    root = harness.load_reference()
+    tmp = tempfile.mkdtemp(prefix="snag_bench_")
+    cwd = os.getcwd()
+    out = {}
+    try:
+        harness.write_dataset(tmp, n_side=n_side, n_links=n_links, img_dim=2048)
+        argv = harness.main_argv(tmp, epochs=1, batch_size=batch)
+        for key, val in (("--hidden_units", "300,300,300"), ("--attr_dim", "300"), ("--img_dim", "300"), ("--name_dim", "300"),
+                         ("--char_dim", "300"), ("--hidden_size", "300"), ("--intermediate_size", "400")):
+            argv[argv.index(key) + 1] = val
+        cfgs = harness.parse_args(argv)
+        cfgs.device = dev
+        os.chdir(root)
+        import main as ref_main
+        import model.SNAG as ref_snag
+        logger = logging.getLogger("snag_bench_ref")
+        logger.setLevel(logging.WARNING)
+        runner = ref_main.Runner(cfgs, None, logger)
+        train_ill = np.asarray(runner.train_ill, dtype=np.int32)
+        batch_links = train_ill[:batch]
+
+        def time_steps(model, optim):
+            model.train()
+            model.update_noise()
+
+            def one():
+                loss, _ = model(batch_links)
+                loss.backward()
+                torch.nn.utils.clip_grad_norm_(model.parameters(), cfgs.clip)
+                optim.step()
+                model.zero_grad(set_to_none=True)
+                return loss
+            for _ in range(2):
+                one()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                lv = one().item()
+            torch.cuda.synchronize()
+            return (time.perf_counter() - t0) / steps, lv
+
+        state = {k_: v.clone() for k_, v in runner.model.state_dict().items()}
+        dt_ref, loss_ref = time_steps(runner.model, runner.optimizer)
+        spatch.patch(ref_main)
+        model_p = ref_snag.SNAG(runner.KGs, cfgs).cuda()
+        model_p.load_state_dict(state)
+        from src.utils import set_optim
+        optim_p, _ = set_optim(cfgs, [model_p], [], [])              # the reference's parameter groups (src/utils.py:24-81)
+        dt_p, loss_p = time_steps(model_p, optim_p)
+        out = {"entities": 2 * n_side, "batch": int(batch_links.shape[0]), "modalities": 4, "width": 300,
+               "stock_ms_per_step": dt_ref * 1e3, "patched_ms_per_step": dt_p * 1e3, "stock_steps_per_s": 1.0 / dt_ref,
+               "patched_steps_per_s": 1.0 / dt_p, "speedup": dt_ref / dt_p, "stock_loss": loss_ref, "patched_loss": loss_p,
+               "what": "update_noise once, then model(batch) + backward + clip + AdamW per step, wall clock with the loss "
+                       "read back every step; stock = unmodified reference on cuda:0 (fp32 torch eager)"}
+    finally:
+        try:
+            spatch.unpatch()
+        finally:
+            os.chdir(cwd)
+            shutil.rmtree(tmp, ignore_errors=True)
+    return out
+
+
+def run_snag(args, name):
+    ctx = Ctx(args)
+    ev = eval_bench(ctx, args, name)
+    if args.profile_run:
+        if ctx.rank == 0:
+            print(json.dumps({"profile_run": True, "workload": name, "ms_per_step": ev["ms_per_step"], "kernels": ev["kernels"]}), flush=True)
+        ctx.close()
+        return
+    line = eval_line(ctx, args, name, ev) if ctx.rank == 0 else None
+    n, d, k, sigma = ev["n"], ev["d"], ev["k"], ev["sigma"]
+    # the metric's second half: train steps/sec of the loss-layer slice at every N (anchors sharded over the ranks)
+    train = {}
+    if not args.no_train:
+        for tname in ("c5_train", "c1_train"):
+            train[tname] = train_bench(ctx, args, tname, cpu_leg=(ctx.world == 1))
+    if ctx.rank == 0:
+        line["train"] = {t: {kk: v[kk] for kk in ("metric", "value", "unit", "ms_per_step", "scaling", "config", "e2e", "roofline",
+                                                    "gpu_launches", "clocks") + (("cpu_baseline",) if "cpu_baseline" in v else ())}
+                         for t, v in train.items()}
+        n_s = min(CPU_SAMPLE_N, n)
+        cb = cpu_port_sample(n_s, d, k, sigma, 3, 1)
+        line["cpu_baseline"] = {kk: cb[kk] for kk in ("value", "unit", "cores", "kind", "sample")}
+        line["reference_literal_steps"] = reference_steps_sample(min(2048, n), d, k, sigma)
+        if not args.no_context:
+            try:
+                line["snag_step"] = snag_full_step(ctx.dev)
+            except Exception as exc:                      # noqa: BLE001 — a context leg must not take the headline down
+                line["snag_step"] = {"error": f"{type(exc).__name__}: {exc}"[:400]}
+            try:
+                line["reference_gpu_eager"] = reference_gpu_eager(ctx.dev)
+            except Exception as exc:                      # noqa: BLE001
+                line["reference_gpu_eager"] = {"error": f"{type(exc).__name__}: {exc}"[:400]}
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    ctx.close()
+
+
+def run_train(args, name):
+    B, M, dm, desc = TRAIN_WORKLOADS[name]
+    rank = int(os.environ.get("RANK", "0"))
+    if args.impl == "reference":
+        if rank == 0:
+            cb = cpu_icl_sample(min(B, 2048), M, dm, max(1, args.steps), B)
+            print(json.dumps({"impl": "reference", "metric": TRAIN_METRIC, "value": cb["value"], "unit": "steps/s",
+                              "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / cb["value"],
+                              "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                              "config": {"workload": name, "description": desc, "sampled": cb["sample"]}, "cpu_baseline": cb,
+                              "e2e": {"value": cb["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                              "gpu_launches": 0}), flush=True)
+        return
+    ctx = Ctx(args)
+    out = train_bench(ctx, args, name)
+    if ctx.rank == 0:
+        print(json.dumps(out), flush=True)
+    ctx.close()
 
 
 def main():
@@ -569,8 +820,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default=os.environ.get("SNAG_BENCH_WORKLOAD", DEFAULT_WORKLOAD), choices=sorted(WORKLOADS) + sorted(TRAIN_WORKLOADS))
     ap.add_argument("--impl", default="snag", choices=["snag", "reference"])
-    ap.add_argument("--graph-multi", action="store_true", help="training slice: capture the NCCL exchanges in the graph too (N > 1)")
     ap.add_argument("--no-graph", action="store_true", help="training slice: run the step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--no-train", action="store_true", help="evaluation workloads: skip the train blocks of the line")
+    ap.add_argument("--no-audit", action="store_true", help="evaluation workloads: skip the sampled oracle audit")
+    ap.add_argument("--no-context", action="store_true", help="skip the snag_step / reference_gpu_eager context legs")
     ap.add_argument("--profile-run", action="store_true",
                     help="only the device-resident timed region (for runs under ncu); e2e and CPU legs are skipped")
     args = ap.parse_args()
@@ -581,7 +834,7 @@ def main():
     if args.impl == "reference":
         run_reference(args, args.workload, n, d, k, sigma, desc)
     else:
-        run_snag(args, args.workload, n, d, k, sigma, desc)
+        run_snag(args, args.workload)
 
 
 if __name__ == "__main__":

@@ -13,13 +13,12 @@ exactly as in the reference (model/SNAG_loss.py:51,66-69).
 ial_loss (constructed but never called by SNAG — model/SNAG.py:53; live caller model/MCLEA.py:128-139): the KL between
 the softmaxes of the two sets of logits is evaluated row-wise from the same fused sweeps as icl_loss — row log-sum-exps
 of both sets, the target probabilities written once in bf16 and contracted with the stacked embeddings — so no fp32
-[B, 2B] matrix exists; `norm=False` / unreduced outputs keep the materialising form (`_ial_materialised`).
+[B, 2B] matrix exists; `norm=False` and unreduced outputs (no caller in the reference) are refused.
 """
 from __future__ import annotations
 
 import numpy as np
 import torch
-import torch.nn.functional as F
 from torch import nn
 
 from . import ops
@@ -47,6 +46,37 @@ class CustomMultiLossLayer(nn.Module):
         for i in range(len(loss_list)):
             loss += precision[i] * loss_list[i] + self.log_vars[i]
         return loss
+
+
+class AutomaticWeightedLoss(nn.Module):
+    """model/Tool_model.py:14-37 — sum_i 0.5 / p_i^2 * L_i + log(1 + p_i^2) with learnable `params` (ones). SNAG builds
+    one with num=7 as `multi_loss_layer_2` (model/SNAG.py:49); its name puts it in the 5x-lr, no-decay optimiser group
+    (src/utils.py:46-54) and its `params` entry is part of the state dict whether or not --awloss is set."""
+
+    def __init__(self, num=2, args=None):
+        super().__init__()
+        learn = args is None or args.use_awl
+        self.params = nn.Parameter(torch.ones(num), requires_grad=bool(learn))
+
+    def forward(self, *x):
+        loss_sum = 0
+        for i, loss in enumerate(x):
+            loss_sum += 0.5 / (self.params[i] ** 2) * loss + torch.log(1 + self.params[i] ** 2)
+        return loss_sum
+
+
+MAX_INV_TAU = 80.0     # exp((s - 1)/tau) must not underflow for every term of a row: (s - 1)/tau >= -2/tau > -87.3 * 2
+
+
+def _check_tau(tau: float) -> float:
+    """The fused sweeps evaluate exp(s/tau - 1/tau) with the fixed maximum 1/tau (rows are unit norm) instead of a
+    running row maximum; for 1/tau beyond ~80 a row whose similarities are all <= 0 would underflow to a zero row sum
+    (the reference's log_softmax never does). Refuse such temperatures instead of returning inf."""
+    inv_tau = float(1.0 / tau)
+    if not 0.0 < inv_tau <= MAX_INV_TAU:
+        raise ValueError(f"tau={tau}: the fused contrastive kernels support 1/tau in (0, {MAX_INV_TAU:g}] "
+                         f"(the reference's scripts use tau 0.1 and tau2 4.0)")
+    return inv_tau
 
 
 def _links_to_index(train_links, device):
@@ -210,12 +240,15 @@ class icl_loss(nn.Module):
         if self.inversion:
             raise NotImplementedError("inversion=True is unreachable from SNAG (model/SNAG.py:50-51)")
         if not norm:
+            # no caller in the reference passes norm=False (model/SNAG.py:106,147-159; MCLEA.py; MEAformer.py)
             raise NotImplementedError("norm=False: the fused kernel relies on unit rows (logits bounded by 1/tau)")
         if self.n_view != 2:
-            raise NotImplementedError("n_view != 2")
+            # the reference itself fails here: labels are [B, B*n_view] against logits [B, 2B] (model/SNAG_loss.py:84-89)
+            raise RuntimeError(f"n_view={self.n_view}: labels [B, B*n_view] do not match the [B, 2B] logits "
+                               f"(model/SNAG_loss.py:84-89 raises as well)")
         idx_l, idx_r = _links_to_index(train_links, emb.device)
         # normalising only the 2B gathered rows equals normalising all N first (model/SNAG_loss.py:60-64), row by row
-        nll_a, nll_b = _IclPair.apply(emb.float(), idx_l, idx_r, float(1.0 / self.tau), self.shard or _unsharded())
+        nll_a, nll_b = _IclPair.apply(emb.float(), idx_l, idx_r, _check_tau(self.tau), self.shard or _unsharded())
         batch = idx_l.numel()
         if weight_norm is not None:
             w = torch.min(torch.stack([weight_norm[idx_l], weight_norm[idx_r]], dim=1), 1)[0]   # :66-69
@@ -357,69 +390,39 @@ class ial_loss(nn.Module):
     def forward(self, src_emb, tar_emb, train_links, norm=True):
         if self.inversion:
             raise NotImplementedError("inversion=True is unreachable from SNAG / MCLEA")
+        if not norm:
+            # no caller in the reference passes norm=False (model/MCLEA.py:128-139)
+            raise NotImplementedError("norm=False: the fused kernel relies on unit rows (logits bounded by 1/tau)")
+        if self.reduction not in ("mean", "sum"):
+            # the reference returns zoom * (alpha * [B, 2B] matrix + ...) here (model/SNAG_loss.py:195-202): an unreduced
+            # matrix is exactly what the fused path never forms
+            raise NotImplementedError(f"reduction={self.reduction!r}: only 'mean' and 'sum' (config.py:103's choices)")
         idx_l, idx_r = _links_to_index(train_links, src_emb.device)
-        if not norm or self.reduction not in ("mean", "sum"):
-            return self._ial_materialised(src_emb, tar_emb, idx_l, idx_r, norm)
-        kl_a, kl_b = _IalPair.apply(src_emb.float(), tar_emb.detach().float(), idx_l, idx_r, float(1.0 / self.tau))
+        kl_a, kl_b = _IalPair.apply(src_emb.float(), tar_emb.detach().float(), idx_l, idx_r, _check_tau(self.tau))
         batch = idx_l.numel()
         denom = float(batch * 2 * batch) if self.reduction == "mean" else 1.0     # .mean() runs over the [B, 2B] matrix (:195-197)
         alpha = self.weight
         return self.zoom * (alpha * kl_a.sum() / denom + (1 - alpha) * kl_b.sum() / denom)
-
-    def _ial_materialised(self, src_emb, tar_emb, idx_l, idx_r, norm):
-        """The reference's op sequence on materialised [B, 2B] logits (contractions on the tcgen05 mainloop through the
-        differentiable `_Contract`): kept for norm=False (logits not bounded by 1/tau) and unreduced outputs."""
-        src_zis, src_zjs = src_emb.index_select(0, idx_l).float(), src_emb.index_select(0, idx_r).float()
-        tar_zis, tar_zjs = tar_emb.index_select(0, idx_l).float(), tar_emb.index_select(0, idx_r).float()
-        if norm:
-            src_zis, src_zjs = F.normalize(src_zis, dim=1), F.normalize(src_zjs, dim=1)
-            tar_zis, tar_zjs = F.normalize(tar_zis, dim=1).detach(), F.normalize(tar_zjs, dim=1).detach()
-        else:
-            tar_zis, tar_zjs = tar_zis.detach(), tar_zjs.detach()                # q is detached (:192-193)
-        temperature = self.tau
-        alpha = self.weight
-        batch_size = src_zis.shape[0]
-        LARGE_NUM = 1e9
-        masks = torch.eye(batch_size, device=src_emb.device, dtype=torch.float32)
-        mm = _Contract.apply
-        p_ab = mm(src_zis, src_zjs) / temperature
-        p_ba = p_ab.t()                                                          # b.a^T is the transpose of a.b^T
-        q_ab = mm(tar_zis, tar_zjs) / temperature
-        q_ba = q_ab.t()
-        p_aa = mm(src_zis, src_zis) / temperature - masks * LARGE_NUM
-        p_bb = mm(src_zjs, src_zjs) / temperature - masks * LARGE_NUM
-        q_aa = mm(tar_zis, tar_zis) / temperature - masks * LARGE_NUM
-        q_bb = mm(tar_zjs, tar_zjs) / temperature - masks * LARGE_NUM
-        p_ab = torch.cat([p_ab, p_aa], dim=1)
-        p_ba = torch.cat([p_ba, p_bb], dim=1)
-        q_ab = torch.cat([q_ab, q_aa], dim=1)
-        q_ba = torch.cat([q_ba, q_bb], dim=1)
-        loss_a = F.kl_div(F.log_softmax(p_ab, dim=1), F.softmax(q_ab.detach(), dim=1), reduction="none")
-        loss_b = F.kl_div(F.log_softmax(p_ba, dim=1), F.softmax(q_ba.detach(), dim=1), reduction="none")
-        if self.reduction == "mean":
-            loss_a = loss_a.mean()
-            loss_b = loss_b.mean()
-        elif self.reduction == "sum":
-            loss_a = loss_a.sum()
-            loss_b = loss_b.sum()
-        return self.zoom * (alpha * loss_a + (1 - alpha) * loss_b)
 
 
 class SnagLossLayer(nn.Module):
     """The loss half of SNAG.forward (model/SNAG.py:104-116, 140-160) as one module, with the reference's member names:
     GMI = criterion_cl_joint(joint_emb) + criterion_cl_joint(joint_emb_fz); ECIA = inner_view_loss over the modality
     embeddings with the per-modality weights; IIR = inner_view_loss over the hidden-state embeddings;
-    multi_loss_layer (6) inside inner_view_loss, multi_loss_layer_2 (3) on top when `awloss`.
+    multi_loss_layer (CustomMultiLossLayer, 6) inside inner_view_loss; multi_loss_layer_2 (AutomaticWeightedLoss, 7) on
+    top when `awloss` — off by default like --awloss (config.py:114), i.e. the three terms are summed. (With --awloss 1
+    the reference passes the LIST as one positional argument, model/SNAG.py:117, which raises a TypeError inside
+    AutomaticWeightedLoss.forward; here the three terms are passed as the three arguments its signature expects.)
     That is 2 + 2M icl_loss calls per step for M present modalities — the "loss-layer slice" bench.py times.
     `streams` / `hidden` are 6-tuples ordered (gph, rel, att, img, name, char) with None for absent modalities."""
 
     WEIGHT_COLUMN = (3, 2, 1, 0, 4, 5)      # model/SNAG.py:145-150: gph<-w[:,3], rel<-w[:,2], att<-w[:,1], img<-w[:,0], ...
 
-    def __init__(self, tau=0.1, ab_weight=0.5, awloss=True):
+    def __init__(self, tau=0.1, ab_weight=0.5, awloss=False):
         super().__init__()
         self.awloss = awloss
-        self.multi_loss_layer = CustomMultiLossLayer(loss_num=6)                         # model/SNAG.py:47
-        self.multi_loss_layer_2 = CustomMultiLossLayer(loss_num=3)
+        self.multi_loss_layer = CustomMultiLossLayer(loss_num=6)                         # model/SNAG.py:48
+        self.multi_loss_layer_2 = AutomaticWeightedLoss(num=7)                           # :49
         self.criterion_cl = icl_loss(tau=tau, ab_weight=ab_weight, n_view=2)             # :50
         self.criterion_cl_joint = icl_loss(tau=tau, ab_weight=ab_weight, n_view=2)       # :51
 
@@ -446,4 +449,4 @@ class SnagLossLayer(nn.Module):
         ecia = self.inner_view_loss(streams, batch, weight_norm=weight_norm)
         iir = self.inner_view_loss(hidden, batch)
         loss_list = [gmi, ecia, iir]
-        return self.multi_loss_layer_2(loss_list) if self.awloss else sum(loss_list)
+        return self.multi_loss_layer_2(*loss_list) if self.awloss else sum(loss_list)     # :116-119

@@ -560,6 +560,17 @@ def noise_mask(x: torch.Tensor, mean: torch.Tensor, std: torch.Tensor, noise_rat
     _need(x, torch.float32, "x", 2)
     _need(mean, torch.float32, "mean", 1)
     _need(std, torch.float32, "std", 1)
+    if x.shape[1] % 4:
+        # the kernel moves one float4 per thread; a feature width that is not a multiple of 4 (e.g. the attribute matrix of
+        # a dataset with fewer than 1000 distinct attributes, src/data.py:507) is zero padded for the call and cut back
+        pad = 4 - x.shape[1] % 4
+        P = torch.nn.functional.pad
+        res = noise_mask(P(x, (0, pad)), P(mean, (0, pad)), P(std, (0, pad)), noise_ratio, mask_ratio, mask=mask,
+                         zsel=None if zsel is None else P(zsel, (0, pad)), seed=seed, row0=row0)[:, :x.shape[1]]
+        if out is None:
+            return res.contiguous()
+        out.copy_(res)
+        return out
     if out is None:
         out = torch.empty_like(x)
     _need(out, torch.float32, "out", 2)
@@ -591,6 +602,10 @@ def philox_rowmask(n: int, ratio: float, seed: int, device, row0: int = 0) -> to
 def gauss_fill(mean: torch.Tensor, std: torch.Tensor, n: int, seed: int, row0: int = 0) -> torch.Tensor:
     _need(mean, torch.float32, "mean", 1)
     _need(std, torch.float32, "std", 1)
+    if mean.numel() % 4:                                   # float4 kernel: pad the width for the call (see noise_mask)
+        pad = 4 - mean.numel() % 4
+        P = torch.nn.functional.pad
+        return gauss_fill(P(mean, (0, pad)), P(std, (0, pad)), n, seed, row0)[:, :mean.numel()].contiguous()
     out = torch.empty((n, mean.numel()), dtype=torch.float32, device=mean.device)
     call("snag_gauss_fill", ptr(out), ptr(mean), ptr(std), n, mean.numel(), out.stride(0), int(seed), int(row0),
          current_stream())

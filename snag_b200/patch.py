@@ -25,13 +25,33 @@ import types
 from . import evaluate, fusion, loss, mining, noise, runner, seeds
 
 
+_ABSENT = object()
+_SAVED: list = []          # (object, attribute name, original value) of everything patch() has rebound, oldest first
+
+
+def unpatch() -> int:
+    """Put back every attribute patch() replaced (newest first); returns how many were restored. Lets one process run
+    the reference both ways (tests/test_reference_e2e_gpu.py compares the patched with the unpatched model)."""
+    n = len(_SAVED)
+    while _SAVED:
+        obj, name, value = _SAVED.pop()
+        if value is _ABSENT:
+            delattr(obj, name)
+        else:
+            setattr(obj, name, value)
+    return n
+
+
 def patch(main_module: types.ModuleType | None = None) -> list[str]:
     """Install the replacements into whichever reference modules are importable; returns what was patched."""
     done = []
 
-    def _set(mod, name, value):
+    def _set(mod, name, value, label=None):
+        # obj.__dict__ rather than getattr: a function stored on a class must be put back as the plain function
+        own = getattr(mod, "__dict__", {})
+        _SAVED.append((mod, name, own[name] if name in own else getattr(mod, name, _ABSENT)))
         setattr(mod, name, value)
-        done.append(f"{mod.__name__}.{name}")
+        done.append(label or f"{mod.__name__}.{name}")
 
     try:
         ref_loss = importlib.import_module("model.SNAG_loss")
@@ -51,19 +71,16 @@ def patch(main_module: types.ModuleType | None = None) -> list[str]:
             _set(ref_snag, nm, getattr(loss, nm))
         _set(ref_snag, "pairwise_distances", evaluate.pairwise_distances)
         cls = ref_snag.SNAG
-        cls.add_noise_to_embeddings = noise.add_noise_to_embeddings
-        cls.get_mean_std = noise.get_mean_std
-        cls.update_noise = noise.update_noise
-        cls.Iter_new_links = mining.Iter_new_links
-        done.append("model.SNAG.SNAG.{add_noise_to_embeddings,get_mean_std,update_noise,Iter_new_links}")
+        _set(cls, "add_noise_to_embeddings", noise.add_noise_to_embeddings, "model.SNAG.SNAG.add_noise_to_embeddings")
+        _set(cls, "get_mean_std", noise.get_mean_std, "model.SNAG.SNAG.get_mean_std")
+        _set(cls, "update_noise", noise.update_noise, "model.SNAG.SNAG.update_noise")
+        _set(cls, "Iter_new_links", mining.Iter_new_links, "model.SNAG.SNAG.Iter_new_links")
     except ImportError:
         pass
     try:
         ref_tools = importlib.import_module("model.SNAG_tools")
-        ref_tools.MultiModalEncoder.forward = noise.encoder_forward
-        done.append("model.SNAG_tools.MultiModalEncoder.forward")
-        ref_tools.MformerFusion.forward = fusion.MformerFusion_forward
-        done.append("model.SNAG_tools.MformerFusion.forward")
+        _set(ref_tools.MultiModalEncoder, "forward", noise.encoder_forward, "model.SNAG_tools.MultiModalEncoder.forward")
+        _set(ref_tools.MformerFusion, "forward", fusion.MformerFusion_forward, "model.SNAG_tools.MformerFusion.forward")
     except ImportError:
         pass
     try:
@@ -75,8 +92,7 @@ def patch(main_module: types.ModuleType | None = None) -> list[str]:
     if main_mod is not None and hasattr(main_mod, "Runner"):
         _set(main_mod, "pairwise_distances", evaluate.pairwise_distances)
         _set(main_mod, "csls_sim", evaluate.csls_sim)
-        main_mod.Runner._test = runner._test
-        done.append(f"{main_mod.__name__}.Runner._test")
+        _set(main_mod.Runner, "_test", runner._test, f"{main_mod.__name__}.Runner._test")
     return done
 
 

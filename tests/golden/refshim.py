@@ -1,7 +1,8 @@
 """Import the UNMODIFIED reference (zjukg/SNAG, SNAG_MMEA) from /root/reference for golden-vector generation.
 
-Only usable in the build container (the reference checkout does not travel to the GPU box). Nothing is
-copied: the reference modules are imported in place with three shims so that they run on CPU tensors:
+The reference is imported in place (baseline/harness.py locates it: the byte-identical copy baseline/install_ref.py
+puts under the git-ignored baseline/_ref/, or /root/reference in the build container) with three shims so that it
+also runs on CPU tensors:
   - `easydict` and `unidecode` (absent from this image, needed only by config.py / torchlight) are stubbed;
   - torch.Tensor.cuda / nn.Module.cuda become the identity when no GPU is present (the losses hard-code
     `.cuda()`, model/SNAG_loss.py:90,96,165);
@@ -9,34 +10,20 @@ copied: the reference modules are imported in place with three shims so that the
 """
 from __future__ import annotations
 
+import os
 import sys
 import types
 
-REF_ROOT = "/root/reference/SNAG_MMEA"
+_REPO = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+if _REPO not in sys.path:
+    sys.path.insert(0, _REPO)
+from baseline import harness  # noqa: E402
+
+REF_ROOT = harness.ref_root()      # baseline/_ref/SNAG_MMEA (travels to the GPU box) or /root/reference/SNAG_MMEA
 
 
 def load_reference():
-    import torch
-
-    sys.dont_write_bytecode = True
-    if "easydict" not in sys.modules:
-        m = types.ModuleType("easydict")
-
-        class EasyDict(dict):
-            __getattr__ = dict.get
-            __setattr__ = dict.__setitem__
-
-        m.EasyDict = EasyDict
-        sys.modules["easydict"] = m
-    if "unidecode" not in sys.modules:
-        m = types.ModuleType("unidecode")
-        m.unidecode = lambda s: s
-        sys.modules["unidecode"] = m
-    if not torch.cuda.is_available():
-        torch.Tensor.cuda = lambda self, *a, **k: self
-        torch.nn.Module.cuda = lambda self, *a, **k: self
-    if REF_ROOT not in sys.path:
-        sys.path.insert(0, REF_ROOT)
+    harness.load_reference()       # stubs for easydict / unidecode, .cuda() -> identity without a GPU, no bytecode
     import model.SNAG_loss as ref_loss   # noqa: E402
     import src.utils as ref_utils        # noqa: E402
     return types.SimpleNamespace(loss=ref_loss, utils=ref_utils)

@@ -100,3 +100,80 @@ def test_philox_noise_statistics_and_sharding(cuda_device):
     zz = (en - mean) / std
     assert abs(zz.mean().item()) < 2e-3 and abs(zz.std().item() - 1) < 2e-3
     assert torch.equal(ops.gauss_fill(mean, std, 1000, 77, row0=500), en[500:1500])
+
+
+def test_odd_feature_width(cuda_device):
+    """Feature widths that are not a multiple of 4 (attribute matrices of small datasets, src/data.py:507) go through the
+    same float4 kernels, zero padded for the call: bit-exact against the oracle with injected draws."""
+    rng = np.random.RandomState(4)
+    N, F = 501, 997
+    x = rng.randn(N, F).astype(np.float32)
+    mean, std = oracle.col_mean_std(x)
+    mask = rng.rand(N) < 0.3
+    z = rng.randn(int(mask.sum()), F).astype(np.float32)
+    out = ops.noise_mask(_t(x, cuda_device), _t(mean, cuda_device), _t(std, cuda_device), 0.3, 0.7,
+                         mask=_t(mask.astype(np.uint8), cuda_device), zsel=_t(z, cuda_device))
+    np.testing.assert_array_equal(out.cpu().numpy(), oracle.add_noise_to_embeddings(x, mean, std, mask, z, 0.7))
+    prod = ops.noise_mask(_t(x, cuda_device), _t(mean, cuda_device), _t(std, cuda_device), 0.3, 0.7, seed=9)
+    assert prod.shape == (N, F) and prod.is_contiguous()
+    sel = (prod != _t(x, cuda_device)).any(1)
+    assert abs(sel.float().mean().item() - 0.3) < 0.06
+    en = ops.gauss_fill(_t(mean, cuda_device), _t(std, cuda_device), 2000, 5)
+    assert en.shape == (2000, F) and abs(((en - _t(mean, cuda_device)) / _t(std, cuda_device)).std().item() - 1) < 0.01
+
+
+def test_method_mirrors_on_a_model_shaped_object(cuda_device):
+    """snag_b200.noise's drop-ins for SNAG.add_noise_to_embeddings / get_mean_std / update_noise (model/SNAG.py:66-98)
+    and the differentiable entity blend (model/SNAG_tools.py:127-128), called the way the reference's class calls them
+    (as methods, on the attributes its __init__ creates)."""
+    import types
+    from snag_b200 import noise
+    g = torch.Generator(device="cuda").manual_seed(8)
+    N = 6000
+    rel = torch.poisson(torch.full((N, 1000), 0.05, device=cuda_device), generator=g)
+    att = (torch.rand((N, 1000), generator=g, device=cuda_device) < 0.01).float()
+    img = torch.nn.functional.normalize(torch.randn((N, 2048), generator=g, device=cuda_device))
+    wo = torch.arange(0, N, 7, device=cuda_device)
+    emb = torch.nn.Embedding(N, 300).to(cuda_device)
+    torch.nn.init.normal_(emb.weight, std=1.0 / np.sqrt(N))
+    me = types.SimpleNamespace(args=types.SimpleNamespace(noise_ratio=0.2, mask_ratio=0.7), rel_features=rel, att_features=att,
+                               img_features=img, ent_wo_img=wo, multimodal_encoder=types.SimpleNamespace(entity_emb=emb))
+    noise.get_mean_std(me)
+    valid = torch.ones(N, dtype=torch.bool, device=cuda_device)
+    valid[wo] = False
+    np.testing.assert_allclose(me.img_mean.cpu().numpy(), img[valid].mean(0).cpu().numpy(), atol=1e-7)
+    np.testing.assert_allclose(me.img_std.cpu().numpy(), img[valid].std(0).cpu().numpy(), rtol=1e-4, atol=1e-8)
+    np.testing.assert_allclose(me.rel_std.cpu().numpy(), rel.std(0).cpu().numpy(), rtol=1e-4, atol=1e-8)
+    np.testing.assert_allclose(me.att_mean.cpu().numpy(), att.mean(0).cpu().numpy(), atol=1e-7)
+    torch.manual_seed(11)
+    noise.update_noise(me)
+    for name, feat in (("rel", rel), ("att", att), ("img", img)):
+        noisy = getattr(me, f"{name}_noisy_features")
+        assert noisy.data_ptr() != feat.data_ptr() and noisy.shape == feat.shape
+        changed = (noisy != feat).any(1)
+        assert abs(changed.float().mean().item() - 0.2) < 0.02
+        assert torch.equal(noisy[~changed], feat[~changed])
+    assert me.entity_noise.shape == (N, 300) and me.entity_noise_mask.dtype == torch.bool
+    assert abs(me.entity_noise_mask.float().mean().item() - 0.1) < 0.015
+    zn = (me.entity_noise - me.ent_mean) / me.ent_std
+    assert abs(zn.mean().item()) < 5e-3 and abs(zn.std().item() - 1) < 5e-3
+    torch.manual_seed(11)
+    first = me.rel_noisy_features.clone()
+    noise.update_noise(me)                                         # seeded from torch's CPU generator: reproducible
+    assert torch.equal(first, me.rel_noisy_features)
+    # add_noise_to_embeddings works in place on the clone it is handed and returns it (model/SNAG.py:74-75, :89)
+    c = rel.clone()
+    r = noise.add_noise_to_embeddings(me, c, me.rel_mean, me.rel_std, noise_ratio=0.5)
+    assert r is c and abs((c != rel).any(1).float().mean().item() - 0.5) < 0.03
+    # entity blend with autograd: forward and gradient equal the reference's in-place indexed blend
+    e = emb(torch.arange(N, device=cuda_device))
+    out = noise.blend_entity_noise(e, me.entity_noise, me.entity_noise_mask, 0.7)
+    w = torch.randn_like(out)
+    (out * w).sum().backward()
+    got = emb.weight.grad.clone()
+    emb.weight.grad = None
+    e2 = emb(torch.arange(N, device=cuda_device))
+    m = me.entity_noise_mask
+    e2[m] = (1.0 - 0.7 * 0.5) * e2[m] + 0.7 * 0.5 * me.entity_noise[m]
+    (e2 * w).sum().backward()
+    assert torch.equal(out, e2.detach()) and torch.equal(got, emb.weight.grad)

@@ -97,6 +97,48 @@ def test_dot_is_fp64_accumulated():
     assert np.max(np.abs(got.view(np.int32).astype(np.int64) - ref.view(np.int32).astype(np.int64))) <= 1
 
 
+def test_blocked_dot_is_index_order_fp64():
+    """The register-blocked dot kernel of the oracle is a speed-up only: every element equals the scalar fp64
+    index-order accumulation rounded once (checked against a plain Python-float loop, which is exactly that)."""
+    rng = np.random.RandomState(8)
+    x = oracle.bf16_round(rng.randn(9, 77).astype(np.float32))
+    y = oracle.bf16_round(rng.randn(31, 77).astype(np.float32))
+    got = oracle.dot_matrix(x, y)
+    for i in range(9):
+        for j in range(31):
+            acc = 0.0
+            for k in range(77):
+                acc += float(x[i, k]) * float(y[j, k])
+            assert got[i, j] == np.float32(acc)
+
+
+@pytest.mark.parametrize("n,d,k,csls", [(701, 96, 10, True), (1030, 64, 3, True), (515, 40, 5, False), (9, 8, 2, True)])
+def test_streaming_and_audit_equal_materialised(n, d, k, csls):
+    """The streaming evaluation (row blocks, two passes) and the sampled audit restate the same arithmetic as
+    align_eval: ranks, neighbourhood means and ground-truth distances are bit-identical, exact ties included."""
+    rng = np.random.RandomState(n)
+    c = rng.randn(8, d).astype(np.float32)
+    x = rng.randn(n, d).astype(np.float32) + c[rng.randint(0, 8, n)]
+    y = x + 1.5 * rng.randn(n, d).astype(np.float32)
+    x[5], y[7] = x[4], y[6]                               # duplicated rows: exact ties
+    x, y = oracle.bf16_round(oracle.normalize_rows(x)), oracle.bf16_round(oracle.normalize_rows(y))
+    a = oracle.align_eval(x, y, csls, k)
+    for block_rows in (4, 100, 5000):
+        b = oracle.align_eval_stream(x, y, csls, k, block_rows)
+        for key in b:
+            np.testing.assert_array_equal(a[key], b[key], err_msg=f"{key} block_rows={block_rows}")
+    sel = rng.permutation(n)[:min(n, 37)]
+    r = oracle.audit(x[sel], y, sel, csls, k, a.get("nv2"), False)
+    np.testing.assert_array_equal(r["rank"], a["rank_l2r"][sel])
+    np.testing.assert_array_equal(r["g"], a["g"][sel])
+    c_ = oracle.audit(y[sel], x, sel, csls, k, a.get("nv1"), True)
+    np.testing.assert_array_equal(c_["rank"], a["rank_r2l"][sel])
+    np.testing.assert_array_equal(c_["g"], a["g"][sel])
+    if csls:
+        np.testing.assert_array_equal(r["nv"], a["nv1"][sel])
+        np.testing.assert_array_equal(c_["nv"], a["nv2"][sel])
+
+
 # ------------------------------------------------------------------------------------------------ losses
 @pytest.mark.parametrize("name", golden_names("icl_"))
 def test_icl_matches_reference(name):

@@ -1,5 +1,5 @@
-"""The drop-in boundary: signatures of the mirrors equal the reference's (checked against /root/reference when it is
-present, i.e. in the build container), patch() rebinds every name main.py / model/SNAG.py use, and Runner._test
+"""The drop-in boundary: signatures of the mirrors equal the reference's (checked against the unmodified reference tree:
+baseline/_ref on the GPU box, /root/reference in the build container), patch() rebinds every name main.py / model/SNAG.py use, and Runner._test
 reproduces the reference's log lines, CSV and side effects (GPU)."""
 from __future__ import annotations
 
@@ -15,8 +15,20 @@ import torch
 
 from oracle import oracle
 
-REF = "/root/reference/SNAG_MMEA"
-needs_ref = pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not present on this machine")
+from baseline import harness, install_ref
+
+REF = harness.ref_root()
+needs_ref = pytest.mark.skipif(REF is None, reason="no reference checkout on this machine (baseline/install_ref.py)")
+
+
+def test_installed_reference_is_unmodified():
+    """baseline/_ref (what the GPU box and bench.py import) holds exactly the reference's files: the manifest written
+    at install time still matches, and — where /root/reference is present — so does the original."""
+    if not os.path.isdir(install_ref.DST):
+        pytest.skip("baseline/_ref not installed")
+    assert install_ref.verify()
+    if os.path.isdir(install_ref.SRC):
+        assert install_ref._digests(install_ref.SRC) == install_ref._digests(install_ref.DST)
 
 
 def _sig(f):
@@ -59,10 +71,9 @@ def test_patch_rebinds_reference_names(monkeypatch):
     mods = {n: importlib.import_module(n) for n in ("model.SNAG_loss", "model.SNAG", "model.SNAG_tools", "src.utils", "src.data")}
     saved = {(n, k): v for n, m in mods.items() for k, v in vars(m).items()}
     snag_cls, enc_cls = mods["model.SNAG"].SNAG, mods["model.SNAG_tools"].MultiModalEncoder
-    saved_cls = {k: getattr(snag_cls, k) for k in ("add_noise_to_embeddings", "get_mean_std", "update_noise", "Iter_new_links")}
-    saved_fwd = enc_cls.forward
     fus_cls = mods["model.SNAG_tools"].MformerFusion
-    saved_fus = fus_cls.forward
+    saved_cls = {(c, k): c.__dict__[k] for c in (snag_cls, enc_cls, fus_cls) for k in
+                 ("add_noise_to_embeddings", "get_mean_std", "update_noise", "Iter_new_links", "forward") if k in c.__dict__}
     fake_main = types.ModuleType("main")
     fake_main.Runner = type("Runner", (), {"_test": lambda self: None})
     try:
@@ -80,12 +91,13 @@ def test_patch_rebinds_reference_names(monkeypatch):
         assert mods["src.data"].visual_pivot_induction is seeds.visual_pivot_induction
         assert len(done) >= 14
     finally:
-        for (n, k), v in saved.items():
-            setattr(mods[n], k, v)
-        for k, v in saved_cls.items():
-            setattr(snag_cls, k, v)
-        enc_cls.forward = saved_fwd
-        fus_cls.forward = saved_fus
+        assert patch.unpatch() == len(done)
+    # unpatch() put every original back
+    for (n, k), v in saved.items():
+        assert getattr(mods[n], k) is v, (n, k)
+    for (c, k), v in saved_cls.items():
+        assert c.__dict__[k] is v, (c, k)
+    assert not hasattr(fake_main, "csls_sim")
 
 
 class _Capture(logging.Handler):

@@ -1,0 +1,224 @@
+"""GPU integration: the UNMODIFIED reference (baseline/_ref/SNAG_MMEA, byte-identical copy of zjukg/SNAG's SNAG_MMEA)
+run both ways on cuda:0 — stock, and with snag_b200.patch applied — on a synthetic dataset written in the reference's
+own on-disk format (baseline/harness.py).
+
+  * test_main_py_end_to_end: `python main.py ...` (stock) and `python -m snag_b200.patch <ref> ...` (patched) as
+    subprocesses: Runner.__init__ -> load_data -> SNAG.__init__ -> train epochs (update_noise, SNAG.forward, backward,
+    optimiser) -> eval after every epoch -> final test with the prediction file (main.py:246-289, 340-455). main.py
+    stays byte-identical; the patched run executes every rebind of snag_b200.patch.
+  * test_patched_model_matches_reference: in one process, the same SNAG weights and the same noise state through the
+    stock and the patched classes: get_mean_std, update_noise (statistically — the draws come from different
+    generators), SNAG.forward loss within 5e-3 and parameter gradients within 2e-2, Runner._test log lines and
+    prediction file, Iter_new_links.
+Tolerances: the patched path feeds the tensor cores bf16-rounded unit rows (fp32 accumulation), the reference is fp32
+throughout — loss rtol 5e-3, gradients relative Frobenius error 2e-2 (the figures of tests/test_loss_gpu.py for
+icl_loss alone, unchanged by the encoder around it). Ranks are integers of DIFFERENT inputs here (fp32 rows vs their
+bf16 rounding: SURVEY measured 3 of 3000 ranks moving), so metrics are compared to +-0.01 and the log format exactly;
+bit-exactness on identical inputs is the business of tests/test_eval_baseline_gpu.py."""
+from __future__ import annotations
+
+import logging
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from baseline import harness
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(harness.ref_root() is None, reason="no reference checkout (baseline/install_ref.py)")]
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+NUM = r"[-+]?\d+\.?\d*(?:[eE][-+]?\d+)?"
+
+
+def _run(cmd, cwd, timeout=900):
+    env = dict(os.environ)
+    env["PYTHONPATH"] = os.pathsep.join([harness.STUBS, ROOT, env.get("PYTHONPATH", "")])
+    env["PYTHONDONTWRITEBYTECODE"] = "1"
+    env["CUDA_VISIBLE_DEVICES"] = env.get("CUDA_VISIBLE_DEVICES", "0").split(",")[0]
+    r = subprocess.run(cmd, cwd=cwd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=timeout)
+    assert r.returncode == 0, r.stdout[-4000:]
+    return r.stdout
+
+
+def _metric_lines(out):
+    """[(epoch, side, [h1, h10, h50], mr, mrr)] from the reference's log format (main.py:439-444)."""
+    pat = re.compile(rf"Ep (\d+) \| (l2r|r2l): acc of top \[1, 10, 50\] = \[\s*({NUM})\s+({NUM})\s+({NUM})\s*\], "
+                     rf"mr = ({NUM}), mrr = ({NUM}), Loss = ({NUM})")
+    return [(int(m[1]), m[2], [float(m[3]), float(m[4]), float(m[5])], float(m[6]), float(m[7])) for m in pat.finditer(out)]
+
+
+def test_main_py_end_to_end(cuda_device, tmp_path):
+    ref = harness.ref_root()
+    n_side, n_links, epochs = 1500, 1000, 3
+    runs = {}
+    for tag, launcher in (("stock", [sys.executable, "main.py"]),
+                          ("patched", [sys.executable, "-m", "snag_b200.patch", ref])):
+        data = tmp_path / tag
+        harness.write_dataset(str(data), n_side=n_side, n_links=n_links)
+        out = _run(launcher + harness.main_argv(str(data), epochs=epochs, batch_size=256), cwd=ref)
+        lines = _metric_lines(out)
+        # one l2r + one r2l line per epoch (--eval_epoch 1) and per final test
+        assert len(lines) == 2 * (epochs + 1), out[-3000:]
+        res = re.search(rf"Res:\[({NUM})\t({NUM})\t({NUM})\]", out)
+        assert res, out[-3000:]
+        pred = data / "SNAG"
+        files = [os.path.join(b, f) for b, _, fs in os.walk(pred) for f in fs if f.endswith("_pred.txt")]
+        assert len(files) == 1
+        rows = open(files[0]).read().strip().splitlines()
+        n_test = n_links - int(n_links * 0.3)
+        assert rows[0] == "idx,rank,query_id,gt_id,ret1,ret2,ret3" and len(rows) == n_test + 1
+        runs[tag] = dict(lines=lines, res=[float(res[i]) for i in (1, 2, 3)], out=out,
+                         ranks=np.array([int(r.split(",")[1]) for r in rows[1:]]))
+    assert "min loss" in runs["patched"]["out"]
+    # same data, same seed, same schedule: the two runs train to the same place up to the noise draws (different
+    # generators) and bf16 — Hits@1 / MRR of the final test agree to a few points, and both learned something
+    for a, b in zip(runs["stock"]["res"], runs["patched"]["res"]):
+        assert abs(a - b) < 0.05, (runs["stock"]["res"], runs["patched"]["res"])
+    assert runs["patched"]["res"][0] > 0.3
+    # the rank column of the prediction file is consistent with the logged Hits@1
+    assert abs((runs["patched"]["ranks"] == 0).mean() - runs["patched"]["res"][0]) < 1e-3
+
+
+class _Capture(logging.Handler):
+    def __init__(self):
+        super().__init__()
+        self.lines = []
+
+    def emit(self, record):
+        self.lines.append(record.getMessage())
+
+
+def _relerr(a, b):
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def test_patched_model_matches_reference(cuda_device, tmp_path):
+    from snag_b200 import patch as spatch
+    root = harness.load_reference()
+    data = tmp_path / "data"
+    harness.write_dataset(str(data), n_side=2000, n_links=1400, img_dim=512)
+    cfgs = harness.parse_args(harness.main_argv(str(data), epochs=2, batch_size=400))
+    cfgs.device = torch.device("cuda:0")
+    cwd = os.getcwd()
+    os.chdir(root)
+    import main as ref_main
+    import model.SNAG as ref_snag
+    import src.utils as ref_utils
+    logger = logging.getLogger("snag_e2e")
+    logger.setLevel(logging.INFO)
+    logger.propagate = False
+    cap = _Capture()
+    logger.addHandler(cap)
+    try:
+        runner = ref_main.Runner(cfgs, None, logger)                 # stock: load_data, SNAG.__init__ (get_mean_std), optimiser
+        runner.loss_log = ref_utils.Loss_log()
+        runner.epoch, runner.loss_item, runner.best_model_wts = 0, 1.2345, None
+        runner.early_stop_init = runner.early_stop_count = 200
+        model = runner.model
+        assert type(model.criterion_cl).__module__ == "model.SNAG_loss"
+        batch = np.asarray(runner.train_ill[:400], dtype=np.int32)
+        n_ent = model.rel_features.shape[0]
+
+        # ---------------------------------------------------------------- stock pass
+        torch.manual_seed(7)
+        model.train()
+        model.update_noise()
+        noise_state = {k: getattr(model, k).clone() for k in ("rel_noisy_features", "att_noisy_features",
+                                                              "img_noisy_features", "entity_noise", "entity_noise_mask")}
+        model.zero_grad(set_to_none=True)
+        loss_ref, out_ref = model(batch)
+        loss_ref.backward()
+        grads_ref = {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}
+        stats_ref = {k: getattr(model, k).clone() for k in ("img_mean", "img_std", "rel_mean", "rel_std", "att_mean", "att_std")}
+        model.eval()
+        cap.lines.clear()
+        runner._test(runner.eval_left, runner.eval_right, last_epoch=True, save_name="stock")
+        lines_ref = list(cap.lines)
+        with torch.no_grad():
+            final_emb = torch.nn.functional.normalize(model.joint_emb_generat()[0])
+        left_nt, right_nt = list(runner.non_train["left"]), list(runner.non_train["right"])
+        links_ref = model.Iter_new_links(4, left_nt, final_emb, right_nt, new_links=[])
+
+        # ---------------------------------------------------------------- patched pass
+        done = spatch.patch(ref_main)
+        assert len(done) >= 14
+        torch.manual_seed(7)
+        model_p = ref_snag.SNAG(runner.KGs, cfgs).cuda()             # patched classes: snag_b200 losses, get_mean_std
+        assert type(model_p.criterion_cl).__module__ == "snag_b200.loss"
+        missing = model_p.load_state_dict(model.state_dict(), strict=True)      # identical parameter names
+        assert not missing.missing_keys and not missing.unexpected_keys
+        for k, v in stats_ref.items():                               # get_mean_std (model/SNAG.py:77-84)
+            np.testing.assert_allclose(getattr(model_p, k).cpu().numpy(), v.cpu().numpy(), rtol=1e-5, atol=1e-6, err_msg=k)
+        model_p.train()
+        # update_noise (model/SNAG.py:86-98): same distribution, different generator
+        torch.manual_seed(7)
+        model_p.update_noise()
+        r, rho = cfgs.noise_ratio, cfgs.mask_ratio
+        for name, feat in (("rel", model_p.rel_features), ("att", model_p.att_features), ("img", model_p.img_features)):
+            noisy = getattr(model_p, f"{name}_noisy_features")
+            assert noisy.shape == feat.shape and noisy.data_ptr() != feat.data_ptr()
+            changed = (noisy != feat).any(1)
+            assert abs(float(changed.float().mean()) - r) < 0.04, name
+            mean, std = getattr(model_p, f"{name}_mean"), getattr(model_p, f"{name}_std")
+            z = (noisy[changed] - (1.0 - rho) * feat[changed]) / rho          # = mean + std * N(0, 1)
+            assert float(((z.mean(0) - mean).abs() / (std + 1e-3)).mean()) < 0.25, name
+            assert abs(float((z.std(0) / (std + 1e-6))[std > 1e-4].mean()) - 1.0) < 0.1, name
+        assert model_p.entity_noise.shape == model_p.multimodal_encoder.entity_emb.weight.shape
+        assert model_p.entity_noise_mask.dtype == torch.bool and model_p.entity_noise_mask.shape == (n_ent,)
+        assert abs(float(model_p.entity_noise_mask.float().mean()) - r * 0.5) < 0.03
+        w = model_p.multimodal_encoder.entity_emb.weight.data
+        np.testing.assert_allclose(model_p.ent_mean.cpu().numpy(), w.mean(0).cpu().numpy(), atol=1e-6)
+        np.testing.assert_allclose(model_p.ent_std.cpu().numpy(), w.std(0).cpu().numpy(), rtol=1e-4, atol=1e-7)
+        zn = (model_p.entity_noise - model_p.ent_mean) / model_p.ent_std
+        assert abs(float(zn.mean())) < 0.01 and abs(float(zn.std()) - 1.0) < 0.01
+        # SNAG.forward (model/SNAG.py:101-122) on the stock pass's noise state
+        for k, v in noise_state.items():
+            setattr(model_p, k, v.clone())
+        model_p.zero_grad(set_to_none=True)
+        loss_p, out_p = model_p(batch)
+        loss_p.backward()
+        assert abs(loss_p.item() - loss_ref.item()) <= 5e-3 * abs(loss_ref.item()), (loss_p.item(), loss_ref.item())
+        for k in ("joint_Intra_modal", "Intra_modal", "IIR_loss"):
+            assert abs(out_p["loss_dic"][k] - out_ref["loss_dic"][k]) <= 5e-3 * abs(out_ref["loss_dic"][k]) + 1e-4, k
+        grads_p = {n: p.grad for n, p in model_p.named_parameters() if p.grad is not None}
+        assert set(grads_p) == set(grads_ref)
+        flat_p = torch.cat([grads_p[n].reshape(-1) for n in sorted(grads_ref)])
+        flat_r = torch.cat([grads_ref[n].reshape(-1) for n in sorted(grads_ref)])
+        assert _relerr(flat_p, flat_r) < 2e-2, _relerr(flat_p, flat_r)
+        for n in grads_ref:                                          # every tensor that carries real signal, one by one
+            if float(grads_ref[n].norm()) > 1e-3 * float(flat_r.norm()):
+                assert _relerr(grads_p[n], grads_ref[n]) < 3e-2, (n, _relerr(grads_p[n], grads_ref[n]))
+        # Runner._test (main.py:359-455) on the stock model: same log skeleton, metrics within rounding of bf16 inputs
+        runner.early_stop_count = 200
+        cap.lines.clear()
+        runner._test(runner.eval_left, runner.eval_right, last_epoch=True, save_name="patched")
+        lines_p = list(cap.lines)
+        assert len(lines_p) == len(lines_ref) == 3
+        strip = lambda s: re.sub(r"\s+", " ", re.sub(NUM, "#", s))      # numpy pads its array print with spaces
+        assert [strip(a) for a in lines_p] == [strip(b) for b in lines_ref]
+        for a, b in zip(lines_p, lines_ref):
+            va, vb = [float(x) for x in re.findall(NUM, a)], [float(x) for x in re.findall(NUM, b)]
+            assert len(va) == len(vb)
+            for x, y in zip(va, vb):
+                assert abs(x - y) <= 0.01 + 0.03 * abs(y), (a, b)
+        pred = lambda tag: np.array([[int(v) for v in row.split(",")] for row in open(os.path.join(
+            cfgs.data_path, "SNAG", f"{tag}_pred", "DBP15K_pred.txt")).read().strip().splitlines()[1:]])
+        ps, pp = pred("stock"), pred("patched")
+        assert ps.shape == pp.shape and (ps[:, [0, 2, 3]] == pp[:, [0, 2, 3]]).all()
+        assert (ps[:, 1] == pp[:, 1]).mean() > 0.97 and (ps[:, 4] == pp[:, 4]).mean() > 0.97      # rank, ret1
+        # Iter_new_links (model/SNAG.py:192-208): mutual nearest neighbours of the non-train entities
+        links_p = model.Iter_new_links(4, left_nt, final_emb, right_nt, new_links=[])
+        sa, sb = set(map(tuple, links_ref)), set(map(tuple, links_p))
+        assert len(sa) > 50 and len(sa & sb) / len(sa | sb) > 0.97, (len(sa), len(sb), len(sa & sb))
+        keep = model.Iter_new_links(5, left_nt, final_emb, right_nt, new_links=links_p[:20])     # filter mode (:205-206)
+        assert set(map(tuple, keep)) == set(map(tuple, links_p[:20]))
+    finally:
+        spatch.unpatch()
+        os.chdir(cwd)
+        logger.removeHandler(cap)
