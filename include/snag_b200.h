@@ -167,10 +167,13 @@ int snag_topk_merge_mean(const float* part, const int32_t* part_idx, int32_t n_l
  * k. A row is verified when its k-th canonical score is >= (smallest tensor-core score of its full list) + delta, i.e.
  * no row of B outside the list can belong to the true neighbourhood; the others are appended to flagged[]
  * (*flagged_cnt counts them, zero it first) and must be completed by snag_topk_exhaustive, which scans all n_b rows
- * of B for each flagged row. */
+ * of B for each flagged row. outsider_bound (NULL or fp32 [n_rows]): for lists that were collected under an admission
+ * threshold (the two-sweep path's column streams: only elements with c >= colthr[row] were ever candidates), that
+ * threshold — a list that is not full is then verified against it instead of being trusted. */
 int snag_topk_rescore(const uint16_t* A, const uint16_t* B, int32_t Dpad, int64_t n_rows, const float* an, const float* bn,
-                      const int32_t* cand_idx, const float* cand_val, int32_t k, float delta, float* nv, int32_t* flagged,
-                      int32_t* flagged_cnt, int32_t flagged_cap, float* best_d, int32_t* best_idx, void* stream);
+                      const int32_t* cand_idx, const float* cand_val, int32_t k, float delta, const float* outsider_bound,
+                      float* nv, int32_t* flagged, int32_t* flagged_cnt, int32_t flagged_cap, float* best_d,
+                      int32_t* best_idx, void* stream);
 int snag_topk_exhaustive(const uint16_t* A, const uint16_t* B, int32_t Dpad, int64_t n_b, const float* an, const float* bn,
                          const int32_t* flagged, const int32_t* flagged_cnt, int32_t flagged_cap, int32_t k, float* nv,
                          float* best_d, int32_t* best_idx, void* stream);

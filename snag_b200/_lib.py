@@ -46,7 +46,7 @@ _SIGNATURES = {
     "snag_col_cand_scatter": [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp],
     "snag_col_cand_finalize": [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp],
     "snag_topk_merge_mean": [_vp, _vp, _i32, _i64, _i32, _vp, _vp, _vp, _vp],
-    "snag_topk_rescore": [_vp, _vp, _i32, _i64, _vp, _vp, _vp, _vp, _i32, _f32, _vp, _vp, _vp, _i32, _vp, _vp, _vp],
+    "snag_topk_rescore": [_vp, _vp, _i32, _i64, _vp, _vp, _vp, _vp, _i32, _f32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp],
     "snag_topk_exhaustive": [_vp, _vp, _i32, _i64, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp],
     "snag_pair_score": [_vp, _vp, _i32, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp],
     "snag_eval_rank": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp],

@@ -111,10 +111,11 @@ int snag_topk_merge_mean(const float* part, const int32_t* part_idx, int32_t n_l
   return launch_topk_merge_mean(part, part_idx, n_lists, n_rows, k, nv, cand_out, cand_idx_out, S(stream));
 }
 int snag_topk_rescore(const uint16_t* A, const uint16_t* B, int32_t Dpad, int64_t n_rows, const float* an, const float* bn,
-                      const int32_t* cand_idx, const float* cand_val, int32_t k, float delta, float* nv, int32_t* flagged,
-                      int32_t* flagged_cnt, int32_t flagged_cap, float* best_d, int32_t* best_idx, void* stream) {
-  return launch_topk_rescore(BF(A), BF(B), Dpad, n_rows, an, bn, cand_idx, cand_val, k, delta, nv, flagged, flagged_cnt,
-                             flagged_cap, best_d, best_idx, S(stream));
+                      const int32_t* cand_idx, const float* cand_val, int32_t k, float delta, const float* outsider_bound,
+                      float* nv, int32_t* flagged, int32_t* flagged_cnt, int32_t flagged_cap, float* best_d,
+                      int32_t* best_idx, void* stream) {
+  return launch_topk_rescore(BF(A), BF(B), Dpad, n_rows, an, bn, cand_idx, cand_val, k, delta, outsider_bound, nv, flagged,
+                             flagged_cnt, flagged_cap, best_d, best_idx, S(stream));
 }
 int snag_topk_exhaustive(const uint16_t* A, const uint16_t* B, int32_t Dpad, int64_t n_b, const float* an, const float* bn,
                          const int32_t* flagged, const int32_t* flagged_cnt, int32_t flagged_cap, int32_t k, float* nv,

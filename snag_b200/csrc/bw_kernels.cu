@@ -530,6 +530,7 @@ __global__ void __launch_bounds__(128) topk_rescore_kernel(const __nv_bfloat16* 
                                                            int Dpad, long long n_rows, const float* __restrict__ an,
                                                            const float* __restrict__ bn, const int* __restrict__ cand_idx,
                                                            const float* __restrict__ cand_val, int k, float delta,
+                                                           const float* __restrict__ outsider_bound,
                                                            float* __restrict__ nv, int* __restrict__ flagged,
                                                            int* __restrict__ flagged_cnt, int flagged_cap,
                                                            float* __restrict__ best_d, int* __restrict__ best_idx) {
@@ -575,8 +576,13 @@ __global__ void __launch_bounds__(128) topk_rescore_kernel(const __nv_bfloat16* 
   }
   if (live && sub == 0) {
     nv[row] = __fdiv_rn(sum, static_cast<float>(k));
+    // What bounds the tensor-core score of every row of B that is NOT in the list: the list's smallest entry when all
+    // KT slots are taken; otherwise the admission threshold the list was collected under (outsider_bound: the two-sweep
+    // path only streams elements at or above the column's sample-derived threshold, so a short list says nothing about
+    // what lies just below that threshold), or nothing at all (-inf: the list saw every row of B).
     const bool full = tc_min > -INFINITY;                 // all KT slots hold a real candidate
-    if (full && !(ck >= tc_min + delta)) {
+    const float ob = full ? tc_min : (outsider_bound ? outsider_bound[row] : -INFINITY);
+    if (ob > -INFINITY && !(ck >= ob + delta)) {
       const int slot = atomicAdd(flagged_cnt, 1);
       if (slot < flagged_cap) flagged[slot] = static_cast<int>(row);
     }
@@ -1007,15 +1013,16 @@ int launch_col_cand_finalize(const long long* offs, const int* hist, const float
   return static_cast<int>(cudaGetLastError());
 }
 int launch_topk_rescore(const __nv_bfloat16* A, const __nv_bfloat16* B, int Dpad, long long n_rows, const float* an,
-                        const float* bn, const int* cand_idx, const float* cand_val, int k, float delta, float* nv,
-                        int* flagged, int* flagged_cnt, int flagged_cap, float* best_d, int* best_idx, cudaStream_t st) {
+                        const float* bn, const int* cand_idx, const float* cand_val, int k, float delta,
+                        const float* outsider_bound, float* nv, int* flagged, int* flagged_cnt, int flagged_cap,
+                        float* best_d, int* best_idx, cudaStream_t st) {
   if (!A || !B || !an || !bn || !cand_idx || !cand_val || !nv || !flagged || !flagged_cnt || n_rows <= 0 || flagged_cap < 1)
     return SNAG_ERR_ARG;
   if ((best_d == nullptr) != (best_idx == nullptr)) return SNAG_ERR_ARG;
   if (k < 1 || k > KT_LIST || (Dpad % 64)) return SNAG_ERR_SHAPE;
   const long long threads = n_rows * 16;
   topk_rescore_kernel<<<static_cast<unsigned>((threads + 127) / 128), 128, 0, st>>>(A, B, Dpad, n_rows, an, bn, cand_idx,
-                                                                                   cand_val, k, delta, nv, flagged,
+                                                                                   cand_val, k, delta, outsider_bound, nv, flagged,
                                                                                    flagged_cnt, flagged_cap, best_d, best_idx);
   return static_cast<int>(cudaGetLastError());
 }

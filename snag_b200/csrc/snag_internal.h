@@ -47,8 +47,9 @@ int launch_normalize_bwd_scatter(const float* emb, long long ld, const long long
 int launch_topk_merge_mean(const float* part, const int* part_idx, int n_lists, long long n_rows, int k, float* nv,
                            float* cand_out, int* cand_idx_out, cudaStream_t st);
 int launch_topk_rescore(const __nv_bfloat16* A, const __nv_bfloat16* B, int Dpad, long long n_rows, const float* an,
-                        const float* bn, const int* cand_idx, const float* cand_val, int k, float delta, float* nv,
-                        int* flagged, int* flagged_cnt, int flagged_cap, float* best_d, int* best_idx, cudaStream_t st);
+                        const float* bn, const int* cand_idx, const float* cand_val, int k, float delta,
+                        const float* outsider_bound, float* nv, int* flagged, int* flagged_cnt, int flagged_cap,
+                        float* best_d, int* best_idx, cudaStream_t st);
 int launch_topk_exhaustive(const __nv_bfloat16* A, const __nv_bfloat16* B, int Dpad, long long n_b, const float* an,
                            const float* bn, const int* flagged, const int* flagged_cnt, int flagged_cap, int k, float* nv,
                            float* best_d, int* best_idx, cudaStream_t st);

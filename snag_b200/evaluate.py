@@ -57,16 +57,17 @@ def shard_bounds(n: int, world: int, rank: int, align: int = 256) -> tuple[int, 
 TWO_SWEEP_MIN_N = 65536     # below this the sample pre-pass costs more than the sweep it saves
 
 
-def two_sweep_plan(n: int, k: int) -> tuple[int, int] | None:
+def two_sweep_plan(n: int, k: int, n_targets: int | None = None, n_ctas: int = 148) -> tuple[int, int] | None:
     """(sample size m, candidate-stream capacity per CTA) of the two-sweep CSLS path, or None when n is too small.
     A random sample of m sources leaves on average k*n/m candidates per target (for any data distribution: the
-    rows are exchangeable), i.e. k*n*n_targets/m in total, spread over the CTAs in proportion to the tiles they
-    process; each CTA's stream holds twice its even share of a full (unsharded) sweep."""
+    rows are exchangeable), i.e. k*n*n_targets/m in total for the n_targets this rank owns (default: all n), spread
+    over its n_ctas persistent CTAs in proportion to the tiles they process; each CTA's stream holds twice its even
+    share. m depends on n alone, so every rank of a sharded evaluation draws the same sample."""
     if n < TWO_SWEEP_MIN_N:
         return None
     m = min(max(round_up(n // 16, 256), 8192), 32768)
-    n_ctas = 148
-    cap = round_up(int(2.0 * k * n / m * n / n_ctas) + 4096, 1024)
+    nt = n if n_targets is None else max(1, int(n_targets))
+    cap = round_up(int(2.0 * k * n / m * nt / max(1, n_ctas)) + 4096, 1024)
     return m, cap
 
 
@@ -108,8 +109,8 @@ def _align_ranks_steps(be, X, Y, xn, yn, n: int, csls_k: int, use_csls: bool, wa
         # Sweep 1 selects, per source and per target, the KT partners with the largest tensor-core score and remembers
         # WHO they are; the neighbourhood means are then computed from those candidates with the canonical arithmetic
         # (ops.topk_rescore), so nv1 / nv2 equal the oracle's bit for bit whatever the accumulation order of the MMAs.
-        col_val = col_idx = None
-        plan2 = two_sweep_plan(n, csls_k) if (two_sweep and hasattr(be, "eval_rowcoltopk")) else None
+        col_val = col_idx = col_bound = None
+        plan2 = two_sweep_plan(n, csls_k, ns, be.num_sms()) if (two_sweep and hasattr(be, "eval_rowcoltopk")) else None
         part = pidx = None
         if plan2 is not None:
             # two-sweep path: sample pre-passes bound every target's k-th best and every source's KT-th best from
@@ -146,9 +147,10 @@ def _align_ranks_steps(be, X, Y, xn, yn, n: int, csls_k: int, use_csls: bool, wa
                 colthr, colb = be.col_threshold(cand_s, csls_k, yns)
                 part, pidx, stream, stream_row, stream_cnt = be.eval_rowcoltopk(X, Ys, xn, yns, n, ns, colthr, colb, cap, rowthr)
                 col_val, col_idx, overflow = be.col_cand_reduce(stream, stream_row, stream_cnt, ns, csls_k)
+                col_bound = colthr                 # nothing below a target's threshold was ever streamed
                 launches += 7
                 if int(overflow.item()) != 0:      # a candidate stream filled up: redo the columns the classic way
-                    col_val = col_idx = None
+                    col_val = col_idx = col_bound = None
                 del stream, stream_row, Xs, xns
         elif ns > 0:
             part, pidx = be.eval_rowtopk(X, Ys, xn, yns, n, ns, want_idx=True)
@@ -187,7 +189,7 @@ def _align_ranks_steps(be, X, Y, xn, yn, n: int, csls_k: int, use_csls: bool, wa
                 _, col_val, col_idx = be.topk_merge_mean(part2, csls_k, want_nv=False, part_idx=pidx2)
                 del part2, pidx2
                 launches += 2
-            nv2_loc[:ns] = be.topk_rescore(Ys, X, yns, xn, col_idx, col_val, csls_k, n, "cols")
+            nv2_loc[:ns] = be.topk_rescore(Ys, X, yns, xn, col_idx, col_val, csls_k, n, "cols", outsider_bound=col_bound)
             launches += 1
         if world == 1:
             nv2 = nv2_loc[:n]

@@ -25,6 +25,11 @@ def round_up(x: int, m: int) -> int:
     return (x + m - 1) // m * m
 
 
+def num_sms() -> int:
+    """SMs of the current device = persistent CTAs of a fused sweep (148 on a B200)."""
+    return int(_lib.load().snag_num_sms())
+
+
 def sim_plan(n_rows: int, n_cols: int, dpad: int) -> tuple[int, int]:
     """(tiles_per_chunk, n_lists) of an [n_rows x n_cols] sweep; n_lists partial lists per row are written."""
     return _lib.sim_plan(n_rows, n_cols, dpad)
@@ -226,7 +231,7 @@ def eval_rowcoltopk(X, Y, xn, yn, n1: int, n2: int, colthr, colb, cta_cap: int, 
         if rowthr.numel() < n1:
             raise ValueError("rowthr needs one entry per row")
     _, nch = sim_plan(n1, n2, X.shape[1])
-    n_ctas = _lib.load().snag_num_sms()
+    n_ctas = num_sms()
     part = torch.empty((nch, n1, KT), dtype=torch.float32, device=X.device)
     pidx = torch.empty((nch, n1, KT), dtype=torch.int32, device=X.device)
     stream = torch.empty((n_ctas, cta_cap), dtype=torch.int64, device=X.device)
@@ -309,12 +314,13 @@ LAST_TOPK_INFO: dict = {}
 
 
 def topk_rescore(A, B, an, bn, cand_idx: torch.Tensor, cand_val: torch.Tensor, k: int, n_b: int, tag: str = "rows",
-                 want_best: bool = False):
+                 want_best: bool = False, outsider_bound: torch.Tensor | None = None):
     """Canonical CSLS neighbourhood means of the rows of A from their KT tensor-core candidates (rows of B); rows the
     candidates cannot vouch for are completed by an exhaustive scan of B (within TOPK_EXHAUSTIVE_BUDGET; beyond it the
     candidate-based value stays and the count is reported in LAST_TOPK_INFO[tag]['unverified']).
     want_best: return (nv, best_d, best_idx) — every row's nearest row of B under the canonical squared distance, lowest
-    index on ties (the argmin of link mining)."""
+    index on ties (the argmin of link mining).
+    outsider_bound [n_rows]: the admission threshold the lists were collected under, if any (see snag_topk_rescore)."""
     _check_operand(A, "A")
     _check_operand(B, "B")
     _need(cand_idx, torch.int32, "cand_idx", 2)
@@ -322,6 +328,10 @@ def topk_rescore(A, B, an, bn, cand_idx: torch.Tensor, cand_val: torch.Tensor, k
     n_rows = cand_idx.shape[0]
     dev = A.device
     st = current_stream()
+    if outsider_bound is not None:
+        _need(outsider_bound, torch.float32, "outsider_bound", 1)
+        if outsider_bound.numel() < n_rows:
+            raise ValueError("outsider_bound needs one entry per row")
     nv = torch.empty((n_rows,), dtype=torch.float32, device=dev)
     best_d = torch.empty((n_rows,), dtype=torch.float32, device=dev) if want_best else None
     best_i = torch.empty((n_rows,), dtype=torch.int32, device=dev) if want_best else None
@@ -329,8 +339,8 @@ def topk_rescore(A, B, an, bn, cand_idx: torch.Tensor, cand_val: torch.Tensor, k
     flagged = torch.empty((cap,), dtype=torch.int32, device=dev)
     fcnt = torch.zeros((1,), dtype=torch.int32, device=dev)
     call("snag_topk_rescore", ptr(A), ptr(B), A.shape[1], n_rows, ptr(an), ptr(bn), ptr(cand_idx), ptr(cand_val), k,
-         TOPK_VERIFY_DELTA * _error_scale(an, bn, A.shape[1]), ptr(nv), ptr(flagged), ptr(fcnt), cap, ptr(best_d), ptr(best_i),
-         st)
+         TOPK_VERIFY_DELTA * _error_scale(an, bn, A.shape[1]), ptr(outsider_bound), ptr(nv), ptr(flagged), ptr(fcnt), cap,
+         ptr(best_d), ptr(best_i), st)
     n_flag = int(fcnt.item())
     info = {"flagged": n_flag, "unverified": 0}
     if n_flag:
@@ -339,6 +349,11 @@ def topk_rescore(A, B, an, bn, cand_idx: torch.Tensor, cand_val: torch.Tensor, k
                  ptr(nv), ptr(best_d), ptr(best_i), st)
         else:
             info["unverified"] = n_flag
+            import warnings
+            warnings.warn(f"snag_b200: {n_flag} {tag} neighbourhoods could not be verified against the canonical arithmetic "
+                          f"within the exhaustive budget (plateaus of near-equal similarities wider than {KT} - k); their "
+                          f"CSLS means come from the tensor-core candidates and may differ from the reference in the last "
+                          f"bits", RuntimeWarning, stacklevel=2)
     LAST_TOPK_INFO[tag] = info
     return (nv, best_d, best_i) if want_best else nv
 

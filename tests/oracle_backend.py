@@ -57,7 +57,7 @@ def topk_merge_mean(part, k, want_nv=True, want_cand=False, part_idx=None):
     return nv, cand
 
 
-def topk_rescore(A, B, an, bn, cand_idx, cand_val, k, n_b, tag="rows", want_best=False):
+def topk_rescore(A, B, an, bn, cand_idx, cand_val, k, n_b, tag="rows", want_best=False, outsider_bound=None):
     """The stand-in's scores are already canonical: the mean of the k largest candidate values, largest first; the
     nearest candidate is the one with the smallest canonical distance, lowest id on ties."""
     v = np.sort(cand_val.numpy(), axis=1)

@@ -95,3 +95,57 @@ def test_two_sweep_size_against_oracle(cuda_device):
     many = evaluate.simulate_sharded(
         lambda r: evaluate._align_ranks_steps(ops, X, Y, xn, yn, n, k, True, False, 4, r), 4)
     _assert_equal_to_oracle(many[1], ref, True)
+
+
+def _adversarial_rows(n, d, seed):
+    """Unit rows built to stress the tensor core's fp32 accumulation against the canonical fp64 one: dense clustered
+    rows (typical), all-positive rows (no cancellation: the largest partial sums), constant rows, rows whose mass sits
+    in a few coordinates, sign-alternating copies (s = sum |x_k y_k| cancels to ~0) — and the SAME rows on both sides,
+    so that every kind also meets its exact duplicate (s = ||x||^2 ~ 1) and its near-duplicates."""
+    rng = np.random.RandomState(seed)
+    q = n // 8
+    centres = rng.randn(16, d).astype(np.float32)
+    dense = rng.randn(2 * q, d).astype(np.float32) + centres[rng.randint(0, 16, 2 * q)]
+    pos = np.abs(rng.randn(q, d)).astype(np.float32)
+    const = np.ones((q, d), np.float32) * (1 + 1e-3 * rng.rand(q, 1).astype(np.float32))
+    spiky = (rng.randn(q, d) * (rng.rand(q, d) < 0.02)).astype(np.float32) + 1e-3 * rng.randn(q, d).astype(np.float32)
+    alt = pos * np.where(np.arange(d) % 2 == 0, 1.0, -1.0).astype(np.float32)
+    near = dense[:q] + 1e-3 * rng.randn(q, d).astype(np.float32)              # near-duplicates of the first dense rows
+    rest = rng.randn(n - 7 * q, d).astype(np.float32)
+    x = np.concatenate([dense, pos, const, spiky, alt, near, rest], 0)
+    return oracle.bf16_round(oracle.normalize_rows(x))
+
+
+@pytest.mark.parametrize("d", [1200, 1856])
+def test_band_epsilon_covers_tensor_core_error_on_1e9_pairs(cuda_device, d):
+    """ops.RANK_BAND_EPS / TOPK_VERIFY_DELTA rest on a bound for |s_tensor_core - s_canonical| on unit rows. Measure it
+    on 32 768^2 = 1.07e9 pairs per width (D = 1200 -> Dpad 1216, and Dpad 1856, the widest the configs use) that
+    include exact duplicates, near-duplicates, all-positive / constant rows (largest partial sums) and sign-alternating
+    rows (full cancellation). Comparator: fp64 GEMM rounded once to fp32 — within half an fp32 ulp (3e-8 for |s| <= 1)
+    of the oracle's index-order fp64 dot. The band must keep a 4x margin over the worst error seen."""
+    n = 32768
+    x = _adversarial_rows(n, d, 77)
+    Xf = torch.from_numpy(x).to(cuda_device)
+    X, xn = ops.prep_bf16(Xf, None, normalize=False)
+    assert torch.equal(X[:, :d].float(), Xf)                       # the operands are exactly the host rows
+    S = ops.sim_write(X, X, None, None, n, n, 0)                    # tensor-core dot products, fp32 [n, n]
+    Xd = Xf.double()
+    worst, worst_diag, pairs = 0.0, 0.0, 0
+    for r0 in range(0, n, 2048):
+        ref = (Xd[r0:r0 + 2048] @ Xd.t()).float()
+        err = (S[r0:r0 + 2048] - ref).abs()
+        worst = max(worst, float(err.max()))
+        worst_diag = max(worst_diag, float(err[torch.arange(err.shape[0]), r0 + torch.arange(err.shape[0])].max()))
+        pairs += err.numel()
+    assert pairs >= 1_000_000_000
+    # spot-check the comparator itself against the oracle's canonical dot on a few thousand pairs
+    rng = np.random.RandomState(1)
+    ri, ci = rng.randint(0, n, 4096).astype(np.int32), rng.randint(0, n, 4096).astype(np.int32)
+    ri[:1024] = ci[:1024]                                          # include diagonal (duplicate) pairs
+    canon = ops.pairs_dot(X, X, torch.from_numpy(ri).to(cuda_device), torch.from_numpy(ci).to(cuda_device))
+    ref = (Xd[torch.from_numpy(ri).long().to(cuda_device)] * Xd[torch.from_numpy(ci).long().to(cuda_device)]).sum(1).float()
+    assert float((canon - ref).abs().max()) <= 6e-8
+    print(f"\n[band] D={d}: max |s_tc - s_fp64| over {pairs:.3e} pairs = {worst:.3e} (diagonal: {worst_diag:.3e}); "
+          f"RANK_BAND_EPS = {ops.RANK_BAND_EPS:.1e}")
+    scale = max(1.0, (X.shape[1] / 2048.0) ** 0.5)
+    assert worst * 4 <= ops.RANK_BAND_EPS * scale and worst * 4 <= ops.TOPK_VERIFY_DELTA * scale, worst
