@@ -128,7 +128,8 @@ def main_argv(data_path: str, epochs: int = 2, batch_size: int = 128, extra: lis
             "--name_dim", "64", "--char_dim", "64", "--hidden_size", "64", "--intermediate_size", "128", "--tau", "0.1",
             "--tau2", "4.0", "--structure_encoder", "gat", "--num_attention_heads", "1", "--num_hidden_layers", "1",
             "--use_surface", "0", "--use_intermediate", "1", "--replay", "0", "--ratio", "1.0", "--add_noise", "1",
-            "--noise_ratio", "0.2", "--mask_ratio", "0.7", "--no_tensorboard", "--data_path", os.path.abspath(data_path)]
+            "--noise_ratio", "0.2", "--mask_ratio", "0.7", "--data_path", os.path.abspath(data_path)]
+    # (no --no_tensorboard: Runner.train calls self.writer.add_scalars unconditionally, main.py:283)
     return argv + list(extra or [])
 
 

@@ -707,8 +707,9 @@ def snag_full_step(dev, n_side=19797, n_links=15000, batch=3500, steps=5):
         cfgs = harness.parse_args(argv)
         cfgs.device = dev
         os.chdir(root)
+        import importlib
         import main as ref_main
-        import model.SNAG as ref_snag
+        ref_snag = importlib.import_module("model.SNAG")             # the module (model/__init__ re-exports the class under the same name)
         logger = logging.getLogger("snag_bench_ref")
         logger.setLevel(logging.WARNING)
         runner = ref_main.Runner(cfgs, None, logger)

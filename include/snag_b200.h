@@ -97,7 +97,27 @@ int snag_joint_fuse_bwd(const float* const* embs, float* const* d_embs, const in
  * with e = emb[idx[r]] and g = dz[r] (fp32 [n, ld_dz]),  demb[idx[r]] += g/||e|| - e (e.g)/||e||^3  (atomic adds; demb
  * fp32 [N, ld_demb], zeroed by the caller). idx may be NULL (rows 0..n-1). normalize = 0: demb[idx[r]] += g. */
 int snag_normalize_bwd_scatter(const float* emb, int64_t ld, const int64_t* idx, int32_t n, int32_t D, int32_t normalize,
-                               const float* dz, int64_t ld_dz, float* demb, int64_t ld_demb, void* stream);
+                               const float* dz, int64_t ld_dz, int32_t n_parts, int64_t part_stride, float* demb,
+                               int64_t ld_demb, void* stream);
+/* dz may be given as n_parts partial sums, part_stride floats apart (the column splits of snag_icl_bwd_fused); they are
+ * added in split order. n_parts = 1: a single gradient, part_stride ignored. */
+
+/* Fused backward of icl_loss (model/SNAG_loss.py:98-126) w.r.t. the normalised rows for contraction widths
+ * Dpad <= 320 (the per-modality calls, D = 300): for each of n_prob <= 16 calls that share the batch size,
+ *   dz_x[split][i][:] = sum over the split's columns j of G_ij y_j,   G = dL/dlogits (see snag_icl_bwd_logits),
+ * with the logits tile recomputed, turned into G in registers, kept in tensor memory as the A operand of a second
+ * tcgen05.mma and contracted with the same shared-memory tile of the stacked embeddings — neither the [B, 2B] logits
+ * nor G ever reach HBM. Per call: S3 = stacked operand [a ; b ; a] ([3 Bp, Dpad] bf16, each part zero padded to
+ * Bp = multiple of 256 rows, from snag_prep_bf16), cr_a / cr_b [B] = g_x[i] * exp(1/tau - lse_x[i]),
+ * dg [B] = g_a[i] + g_b[i]. The launch covers the anchors [128 rb0, 128 (rb0 + row_blocks)) of both sides (all of them:
+ * rb0 = 0, row_blocks = Bp / 128; a rank's shard otherwise); outputs dz_a / dz_b = nsplit partial gradients
+ * [128 row_blocks, Dpad] fp32 of those anchors, part_stride floats apart (sum them, e.g. through
+ * snag_normalize_bwd_scatter). nsplit = snag_icl_bwd_fused_splits(n_prob, B, Bp, row_blocks) or any count that leaves
+ * no split empty. Pointer arguments are HOST arrays of n_prob device pointers. */
+int32_t snag_icl_bwd_fused_splits(int32_t n_prob, int32_t B, int32_t Bp, int32_t row_blocks);
+int snag_icl_bwd_fused(int32_t n_prob, const uint16_t* const* S3, const float* const* cr_a, const float* const* cr_b,
+                       const float* const* dg, float* const* dz_a, float* const* dz_b, int32_t B, int32_t Bp, int32_t rb0,
+                       int32_t row_blocks, int32_t Dpad, float inv_tau, int32_t nsplit, int64_t part_stride, void* stream);
 
 /* ---- alignment evaluation ------------------------------------------------------------------- */
 /* pairwise_distances (src/utils.py:202-218), materialising: mode 1: out[i,j] = clamp(xn_i + yn_j - 2 x_i.y_j, 0);

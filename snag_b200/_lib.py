@@ -33,7 +33,8 @@ _SIGNATURES = {
     "snag_prep_bf16": [_vp, _i64, _vp, _i32, _i32, _i32, _vp, _i32, _vp, _vp],
     "snag_joint_fuse_fwd": [_vp, _vp, _i32, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _vp],
     "snag_joint_fuse_bwd": [_vp, _vp, _vp, _i32, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp],
-    "snag_normalize_bwd_scatter": [_vp, _i64, _vp, _i32, _i32, _i32, _vp, _i64, _vp, _i64, _vp],
+    "snag_normalize_bwd_scatter": [_vp, _i64, _vp, _i32, _i32, _i32, _vp, _i64, _i32, _i64, _vp, _i64, _vp],
+    "snag_icl_bwd_fused": [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _i32, _i64, _vp],
     "snag_sim_write": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _i64, _vp],
     "snag_sim_write_t": [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _i64, _i64, _vp],
     "snag_sim_mainloop_only": [_vp, _vp, _i32, _i32, _i32, _vp],
@@ -63,7 +64,8 @@ _SIGNATURES = {
     "snag_icl_finalize": [_vp, _i32, _i32, _i32, _vp, _f32, _vp, _vp, _vp],
     "snag_icl_bwd_logits": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _i32, _f32, _vp],
 }
-EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["snag_error_string", "snag_csls_workspace_bytes", "snag_sim_write_t_splits"])
+EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["snag_error_string", "snag_csls_workspace_bytes", "snag_sim_write_t_splits",
+                                                "snag_icl_bwd_fused_splits"])
 
 _lib = None
 
@@ -90,6 +92,8 @@ def load() -> C.CDLL:
     lib.snag_error_string.restype = C.c_char_p
     lib.snag_sim_write_t_splits.argtypes = [_i32, _i32, _i32]
     lib.snag_sim_write_t_splits.restype = C.c_int
+    lib.snag_icl_bwd_fused_splits.argtypes = [_i32, _i32, _i32, _i32]
+    lib.snag_icl_bwd_fused_splits.restype = C.c_int
     lib.snag_csls_workspace_bytes.argtypes = [_i64, _i64]
     lib.snag_csls_workspace_bytes.restype = _i64
     _lib = lib

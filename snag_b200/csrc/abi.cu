@@ -77,9 +77,19 @@ int snag_joint_fuse_bwd(const float* const* embs, float* const* d_embs, const in
                                S(stream));
 }
 int snag_normalize_bwd_scatter(const float* emb, int64_t ld, const int64_t* idx, int32_t n, int32_t D, int32_t normalize,
-                               const float* dz, int64_t ld_dz, float* demb, int64_t ld_demb, void* stream) {
-  return launch_normalize_bwd_scatter(emb, ld, reinterpret_cast<const long long*>(idx), n, D, normalize, dz, ld_dz, demb,
-                                      ld_demb, S(stream));
+                               const float* dz, int64_t ld_dz, int32_t n_parts, int64_t part_stride, float* demb,
+                               int64_t ld_demb, void* stream) {
+  return launch_normalize_bwd_scatter(emb, ld, reinterpret_cast<const long long*>(idx), n, D, normalize, dz, ld_dz, n_parts,
+                                      part_stride, demb, ld_demb, S(stream));
+}
+int32_t snag_icl_bwd_fused_splits(int32_t n_prob, int32_t B, int32_t Bp, int32_t row_blocks) {
+  return icl_bwd_fused_splits(n_prob, B, Bp, row_blocks);
+}
+int snag_icl_bwd_fused(int32_t n_prob, const uint16_t* const* S3, const float* const* cr_a, const float* const* cr_b,
+                       const float* const* dg, float* const* dz_a, float* const* dz_b, int32_t B, int32_t Bp, int32_t rb0,
+                       int32_t row_blocks, int32_t Dpad, float inv_tau, int32_t nsplit, int64_t part_stride, void* stream) {
+  return launch_icl_bwd_fused(n_prob, reinterpret_cast<const __nv_bfloat16* const*>(S3), cr_a, cr_b, dg, dz_a, dz_b, B, Bp,
+                              rb0, row_blocks, Dpad, inv_tau, nsplit, part_stride, S(stream));
 }
 
 int snag_sim_mainloop_only(const uint16_t* X, const uint16_t* Y, int32_t n1, int32_t n2, int32_t Dpad, void* stream) {

@@ -379,24 +379,31 @@ __global__ void __launch_bounds__(256) joint_fuse_bwd_kernel(JointTabs tabs, lon
 __global__ void __launch_bounds__(256) normalize_bwd_scatter_kernel(const float* __restrict__ emb, long long ld,
                                                                     const long long* __restrict__ idx, int n, int D,
                                                                     int normalize, const float* __restrict__ dz,
-                                                                    long long ld_dz, float* __restrict__ demb,
-                                                                    long long ld_demb) {
+                                                                    long long ld_dz, int n_parts, long long part_stride,
+                                                                    float* __restrict__ demb, long long ld_demb) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= n) return;
   const long long row = idx ? idx[warp] : static_cast<long long>(warp);
   const float* src = emb + row * ld;
-  const float* g = dz + static_cast<long long>(warp) * ld_dz;
+  const float* g0 = dz + static_cast<long long>(warp) * ld_dz;
+  // dz may arrive as n_parts partial sums (column splits of the fused backward), part_stride floats apart: they are
+  // added in split order, so the result does not depend on how the splits were scheduled
+  auto g_at = [&](int c) {
+    float v = __ldg(g0 + c);
+    for (int q = 1; q < n_parts; ++q) v += __ldg(g0 + q * part_stride + c);
+    return v;
+  };
   if (!normalize) {                                 // plain gather: its backward is the scatter-add alone
     float* d0 = demb + row * ld_demb;
-    for (int c = lane; c < D; c += 32) atomicAdd(d0 + c, __ldg(g + c));
+    for (int c = lane; c < D; c += 32) atomicAdd(d0 + c, g_at(c));
     return;
   }
   float ss = 0.f, eg = 0.f;
   for (int c = lane; c < D; c += 32) {
     const float v = __ldg(src + c);
     ss = __fmaf_rn(v, v, ss);
-    eg = __fmaf_rn(v, __ldg(g + c), eg);
+    eg = __fmaf_rn(v, g_at(c), eg);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -408,9 +415,9 @@ __global__ void __launch_bounds__(256) normalize_bwd_scatter_kernel(const float*
   if (nrm > 1e-12f) {
     const float inv = 1.0f / nrm;
     const float k = eg * inv * inv * inv;
-    for (int c = lane; c < D; c += 32) atomicAdd(dst + c, __fmaf_rn(-__ldg(src + c), k, __ldg(g + c) * inv));
+    for (int c = lane; c < D; c += 32) atomicAdd(dst + c, __fmaf_rn(-__ldg(src + c), k, g_at(c) * inv));
   } else {                                         // clamped denominator: z = e / eps is linear in e
-    for (int c = lane; c < D; c += 32) atomicAdd(dst + c, __ldg(g + c) * 1e12f);
+    for (int c = lane; c < D; c += 32) atomicAdd(dst + c, g_at(c) * 1e12f);
   }
 }
 
@@ -1195,11 +1202,13 @@ int launch_joint_fuse_bwd(const float* const* embs, float* const* d_embs, const 
 }
 
 int launch_normalize_bwd_scatter(const float* emb, long long ld, const long long* idx, int n, int D, int normalize,
-                                 const float* dz, long long ld_dz, float* demb, long long ld_demb, cudaStream_t st) {
-  if (!emb || !dz || !demb || n <= 0 || D <= 0 || ld < D || ld_dz < D || ld_demb < D) return SNAG_ERR_ARG;
+                                 const float* dz, long long ld_dz, int n_parts, long long part_stride, float* demb,
+                                 long long ld_demb, cudaStream_t st) {
+  if (!emb || !dz || !demb || n <= 0 || D <= 0 || ld < D || ld_dz < D || ld_demb < D || n_parts < 1) return SNAG_ERR_ARG;
   const long long threads = static_cast<long long>(n) * 32;
   normalize_bwd_scatter_kernel<<<static_cast<int>((threads + 255) / 256), 256, 0, st>>>(emb, ld, idx, n, D, normalize, dz,
-                                                                                       ld_dz, demb, ld_demb);
+                                                                                       ld_dz, n_parts, part_stride, demb,
+                                                                                       ld_demb);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -131,7 +131,7 @@ static void load_encode() {
 }
 
 // bf16 row-major [rows, Dpad] operand, box = [box_rows x 64 elements], 128-byte swizzle, zero OOB fill
-static int make_operand_map(CUtensorMap* m, const __nv_bfloat16* ptr, long long rows, int Dpad, int box_rows) {
+int make_operand_map(CUtensorMap* m, const __nv_bfloat16* ptr, long long rows, int Dpad, int box_rows) {
   std::call_once(g_encode_once, load_encode);
   if (!g_encode) return SNAG_ERR_DRIVER;
   if (reinterpret_cast<uintptr_t>(ptr) & 127) return SNAG_ERR_ALIGN;

@@ -43,7 +43,13 @@ int launch_joint_fuse_bwd(const float* const* embs, float* const* d_embs, const 
                           const float* w_ent, long long ldw, const float* w_glob, const float* d_joint, const float* d_joint_fz,
                           long long ld_out, float* d_w_ent, float* d_w_glob, cudaStream_t st);
 int launch_normalize_bwd_scatter(const float* emb, long long ld, const long long* idx, int n, int D, int normalize,
-                                 const float* dz, long long ld_dz, float* demb, long long ld_demb, cudaStream_t st);
+                                 const float* dz, long long ld_dz, int n_parts, long long part_stride, float* demb,
+                                 long long ld_demb, cudaStream_t st);
+// fused ICL backward for Dpad <= 320 (icl_fused.cu)
+int icl_bwd_fused_splits(int n_prob, int B, int Bp, int row_blocks);
+int launch_icl_bwd_fused(int n_prob, const __nv_bfloat16* const* S3, const float* const* cr_a, const float* const* cr_b,
+                         const float* const* dg, float* const* dz_a, float* const* dz_b, int B, int Bp, int rb0,
+                         int row_blocks, int Dpad, float inv_tau, int nsplit, long long part_stride, cudaStream_t st);
 int launch_topk_merge_mean(const float* part, const int* part_idx, int n_lists, long long n_rows, int k, float* nv,
                            float* cand_out, int* cand_idx_out, cudaStream_t st);
 int launch_topk_rescore(const __nv_bfloat16* A, const __nv_bfloat16* B, int Dpad, long long n_rows, const float* an,

@@ -136,82 +136,136 @@ def _unsharded() -> AnchorShard:
     return _UNSHARDED
 
 
-class _IclPair(torch.autograd.Function):
-    """(emb [N, D] fp32, idx_l, idx_r [B]) -> per-row NLL of both directions of the in-batch contrastive loss of the
-    L2-normalised rows emb[idx_l], emb[idx_r], fused on the tensor cores; with an AnchorShard of more than one rank
-    every rank sweeps only its own anchors. Gather + F.normalize + bf16 cast are one kernel forward (prep_bf16) and one
-    backward (normalize_bwd_scatter), so autograd sees a single node from `emb` to the NLL vectors."""
+# Contraction widths up to ops.FUSED_BWD_MAX_DPAD (the per-modality calls, D = 300) take the fused backward: logits tile
+# recomputed, dL/dlogits formed in registers and kept in tensor memory as the A operand of a second tcgen05.mma — no
+# [B, 2B] matrix in HBM. Wider tables (the joint embeddings) keep the two-kernel form, where the MMAs dominate anyway.
+FUSED_BACKWARD = True
+
+
+class _IclMany(torch.autograd.Function):
+    """(idx_l, idx_r [B], emb_0 .. emb_{n-1} [N, D_p] fp32) -> (nll_a_0, nll_b_0, nll_a_1, ...): per-row NLL of both
+    directions of the in-batch contrastive loss of the L2-normalised rows emb_p[idx_l], emb_p[idx_r], for n embedding
+    tables that share one batch of links (the 2 + 2M icl_loss calls of a step, model/SNAG.py:106,147-159), fused on
+    the tensor cores; with an AnchorShard of more than one rank every rank sweeps only its own anchors. Gather +
+    F.normalize + bf16 cast are one kernel forward (prep_bf16) and one backward (normalize_bwd_scatter), so autograd
+    sees a single node from the tables to the NLL vectors; the backward of all narrow tables is ONE launch."""
 
     @staticmethod
-    def forward(ctx, emb, idx_l, idx_r, inv_tau, shard, normalize=True):
+    def forward(ctx, idx_l, idx_r, inv_tau, shard, normalize, *embs):
         be = shard.be
-        emb = emb.contiguous()
-        B, D = idx_l.numel(), emb.shape[1]
+        B = idx_l.numel()
         Bp = ops.round_up(B, 256)
-        dpad = ops.round_up(D, 64)
-        # stacked operand [a ; b ; a], every part zero padded to Bp rows: side a sweeps [b ; a], side b sweeps [a ; b]
-        S3 = torch.zeros((3 * Bp, dpad), dtype=torch.bfloat16, device=emb.device)
-        be.prep_bf16(emb, idx_l, normalize=normalize, out=S3[0:Bp])
-        be.prep_bf16(emb, idx_r, normalize=normalize, out=S3[Bp:2 * Bp])
-        S3[2 * Bp:2 * Bp + B].copy_(S3[0:B])
         r0, r1, per = shard.bounds(B)
-        if shard.world == 1:
-            lse_a, nll_a, _ = be.icl_side(S3[0:Bp], S3[Bp:3 * Bp], B, Bp, inv_tau)
-            lse_b, nll_b, _ = be.icl_side(S3[Bp:2 * Bp], S3[0:2 * Bp], B, Bp, inv_tau)
-        else:
-            loc = torch.zeros((4, per), dtype=torch.float32, device=emb.device)
-            if r1 > r0:
-                nx = r1 - r0
-                la, na, _ = be.icl_side(S3[r0:r0 + nx], S3[Bp:3 * Bp], B, Bp, inv_tau, r0, nx)
-                lb, nb, _ = be.icl_side(S3[Bp + r0:Bp + r0 + nx], S3[0:2 * Bp], B, Bp, inv_tau, r0, nx)
-                loc[0, :nx], loc[1, :nx], loc[2, :nx], loc[3, :nx] = la, na, lb, nb
-            allv = shard.all_gather(loc).permute(1, 0, 2).reshape(4, -1)[:, :B]      # [4, B] in anchor order
-            lse_a, nll_a, lse_b, nll_b = (allv[i].contiguous() for i in range(4))
-        ctx.save_for_backward(S3, lse_a, lse_b, emb, idx_l, idx_r)
-        ctx.dims = (B, D, Bp, inv_tau, bool(normalize))
+        saved, outs, dims = [], [], []
+        for emb in embs:
+            emb = emb.contiguous()
+            D = emb.shape[1]
+            dpad = ops.round_up(D, 64)
+            # stacked operand [a ; b ; a], every part zero padded to Bp rows: side a sweeps [b ; a], side b sweeps [a ; b]
+            S3 = torch.zeros((3 * Bp, dpad), dtype=torch.bfloat16, device=emb.device)
+            be.prep_bf16(emb, idx_l, normalize=normalize, out=S3[0:Bp])
+            be.prep_bf16(emb, idx_r, normalize=normalize, out=S3[Bp:2 * Bp])
+            S3[2 * Bp:2 * Bp + B].copy_(S3[0:B])
+            if shard.world == 1:
+                lse_a, nll_a, _ = be.icl_side(S3[0:Bp], S3[Bp:3 * Bp], B, Bp, inv_tau)
+                lse_b, nll_b, _ = be.icl_side(S3[Bp:2 * Bp], S3[0:2 * Bp], B, Bp, inv_tau)
+            else:
+                loc = torch.zeros((4, per), dtype=torch.float32, device=emb.device)
+                if r1 > r0:
+                    nx = r1 - r0
+                    la, na, _ = be.icl_side(S3[r0:r0 + nx], S3[Bp:3 * Bp], B, Bp, inv_tau, r0, nx)
+                    lb, nb, _ = be.icl_side(S3[Bp + r0:Bp + r0 + nx], S3[0:2 * Bp], B, Bp, inv_tau, r0, nx)
+                    loc[0, :nx], loc[1, :nx], loc[2, :nx], loc[3, :nx] = la, na, lb, nb
+                allv = shard.all_gather(loc).permute(1, 0, 2).reshape(4, -1)[:, :B]      # [4, B] in anchor order
+                lse_a, nll_a, lse_b, nll_b = (allv[i].contiguous() for i in range(4))
+            saved += [S3, lse_a, lse_b, emb]
+            outs += [nll_a, nll_b]
+            dims.append(D)
+        ctx.save_for_backward(idx_l, idx_r, *saved)
+        ctx.dims = (B, Bp, inv_tau, bool(normalize), tuple(dims))
         ctx.shard = shard
-        return nll_a, nll_b
+        return tuple(outs)
 
     @staticmethod
-    def backward(ctx, g_a, g_b):
-        S3, lse_a, lse_b, emb, idx_l, idx_r = ctx.saved_tensors
-        B, D, Bp, inv_tau, nrm = ctx.dims
+    def backward(ctx, *grads):
+        idx_l, idx_r, *saved = ctx.saved_tensors
+        B, Bp, inv_tau, nrm, dims = ctx.dims
         shard = ctx.shard
         be = shard.be
-        g_a = torch.zeros_like(lse_a) if g_a is None else g_a.contiguous().float()
-        g_b = torch.zeros_like(lse_b) if g_b is None else g_b.contiguous().float()
-        cra = (g_a * torch.exp(inv_tau - lse_a)).contiguous()
-        crb = (g_b * torch.exp(inv_tau - lse_b)).contiguous()
-        dg = (g_a + g_b).contiguous()
-        Ya, Yb = S3[Bp:3 * Bp], S3[0:2 * Bp]
-        YaT, YbT = Ya.t().contiguous(), Yb.t().contiguous()
-        demb = torch.zeros_like(emb)
-        if shard.world == 1:
-            Ga = be.icl_bwd_logits(S3[0:Bp], Ya, B, Bp, inv_tau, cra, crb, dg)         # [Bp, 2Bp] bf16
-            Gb = be.icl_bwd_logits(S3[Bp:2 * Bp], Yb, B, Bp, inv_tau, crb, cra, dg)
-            be.normalize_bwd_scatter(emb, idx_l, be.grad_contract(Ga, YaT, B, D), demb, nrm)      # dz [B, D] fp32 -> demb rows
-            be.normalize_bwd_scatter(emb, idx_r, be.grad_contract(Gb, YbT, B, D), demb, nrm)
-            return demb, None, None, None, None, None
-        # sharded: G rows of the owned anchors only. Row i of G already carries every term of dL/d(anchor i) —
-        # its own softmax row and its appearances as a column in the other rows' softmaxes (the cc / cr_j terms of
-        # EpiIclBwd) — so the owned rows of dA, dB are complete and no reduce-scatter is needed.
+        n = len(dims)
         r0, r1, per = shard.bounds(B)
-        loc = torch.zeros((2, per, D), dtype=torch.float32, device=S3.device)
-        if r1 > r0:
-            nx = r1 - r0
-            Ga = be.icl_bwd_logits(S3[r0:r0 + nx], Ya, B, Bp, inv_tau, cra, crb, dg, r0, nx)
-            Gb = be.icl_bwd_logits(S3[Bp + r0:Bp + r0 + nx], Yb, B, Bp, inv_tau, crb, cra, dg, r0, nx)
-            loc[0, :nx] = be.grad_contract(Ga, YaT, nx, D)
-            loc[1, :nx] = be.grad_contract(Gb, YbT, nx, D)
-        if shard.grads == "gather":
-            allg = shard.all_gather(loc).permute(1, 0, 2, 3).reshape(2, -1, D)[:, :B]   # [2, B, D]
-            be.normalize_bwd_scatter(emb, idx_l, allg[0].contiguous(), demb, nrm)
-            be.normalize_bwd_scatter(emb, idx_r, allg[1].contiguous(), demb, nrm)
-        elif r1 > r0:                         # "local": only the owned anchors' rows; the SUM over ranks is the gradient
-            nx = r1 - r0
-            be.normalize_bwd_scatter(emb, idx_l[r0:r1].contiguous(), loc[0, :nx].contiguous(), demb, nrm)
-            be.normalize_bwd_scatter(emb, idx_r[r0:r1].contiguous(), loc[1, :nx].contiguous(), demb, nrm)
-        return demb, None, None, None, None, None
+        probs = []
+        for p in range(n):
+            S3, lse_a, lse_b, emb = saved[4 * p:4 * p + 4]
+            g_a, g_b = grads[2 * p], grads[2 * p + 1]
+            if not ctx.needs_input_grad[5 + p] or (g_a is None and g_b is None):
+                probs.append(None)
+                continue
+            g_a = torch.zeros_like(lse_a) if g_a is None else g_a.contiguous().float()
+            g_b = torch.zeros_like(lse_b) if g_b is None else g_b.contiguous().float()
+            probs.append(dict(S3=S3, emb=emb, D=dims[p], cra=(g_a * torch.exp(inv_tau - lse_a)).contiguous(),
+                              crb=(g_b * torch.exp(inv_tau - lse_b)).contiguous(), dg=(g_a + g_b).contiguous()))
+        # the anchors this rank differentiates: all of them, or its shard (whole blocks of 128 rows inside [0, Bp))
+        a0, nx = (0, Bp) if shard.world == 1 else (r0, max(0, min(per, Bp - r0)) if r1 > r0 else 0)
+        dz = [None] * n                                   # per problem: (dz_a, dz_b), rows = anchors a0 .. a0 + nx
+        if nx > 0:
+            fused = [p for p in range(n) if probs[p] is not None and FUSED_BACKWARD and hasattr(be, "icl_bwd_fused")
+                     and probs[p]["S3"].shape[1] <= ops.FUSED_BWD_MAX_DPAD]
+            by_width = {}
+            for p in fused:
+                by_width.setdefault(probs[p]["S3"].shape[1], []).append(p)
+            for group in by_width.values():
+                for i in range(0, len(group), ops.FUSED_BWD_MAX_PROBLEMS):
+                    chunk = group[i:i + ops.FUSED_BWD_MAX_PROBLEMS]
+                    res = be.icl_bwd_fused([probs[p]["S3"] for p in chunk], [probs[p]["cra"] for p in chunk],
+                                           [probs[p]["crb"] for p in chunk], [probs[p]["dg"] for p in chunk], B, Bp, inv_tau,
+                                           a0, nx)
+                    for p, pair in zip(chunk, res):
+                        dz[p] = pair
+            for p in range(n):
+                if probs[p] is None or dz[p] is not None:
+                    continue
+                q = probs[p]
+                S3, D = q["S3"], q["D"]
+                Ya, Yb = S3[Bp:3 * Bp], S3[0:2 * Bp]
+                Ga = be.icl_bwd_logits(S3[a0:a0 + nx], Ya, B, Bp, inv_tau, q["cra"], q["crb"], q["dg"], a0, nx)   # [nx, 2Bp] bf16
+                Gb = be.icl_bwd_logits(S3[Bp + a0:Bp + a0 + nx], Yb, B, Bp, inv_tau, q["crb"], q["cra"], q["dg"], a0, nx)
+                # row i of G carries every term of dL/d(anchor i) — its own softmax row and its appearances as a column
+                # in the other rows' softmaxes (the cc / cr_j terms of EpiIclBwd) — so the owned rows of dA, dB are complete
+                dz[p] = (be.grad_contract(Ga, Ya.t().contiguous(), nx, D), be.grad_contract(Gb, Yb.t().contiguous(), nx, D))
+        out = []
+        for p in range(n):
+            if probs[p] is None:
+                out.append(None)
+                continue
+            emb, D = probs[p]["emb"], probs[p]["D"]
+            demb = torch.zeros_like(emb)
+            if shard.world == 1:
+                be.normalize_bwd_scatter(emb, idx_l, dz[p][0], demb, nrm)
+                be.normalize_bwd_scatter(emb, idx_r, dz[p][1], demb, nrm)
+            else:
+                loc = torch.zeros((2, per, D), dtype=torch.float32, device=emb.device)
+                if nx > 0:
+                    for s_ in range(2):
+                        t = dz[p][s_]
+                        loc[s_, :nx] = (t.sum(0) if t.dim() == 3 else t)[:, :D]
+                if shard.grads == "gather":
+                    allg = shard.all_gather(loc).permute(1, 0, 2, 3).reshape(2, -1, D)[:, :B]   # [2, B, D]
+                    be.normalize_bwd_scatter(emb, idx_l, allg[0].contiguous(), demb, nrm)
+                    be.normalize_bwd_scatter(emb, idx_r, allg[1].contiguous(), demb, nrm)
+                elif r1 > r0:                 # "local": only the owned anchors' rows; the SUM over ranks is the gradient
+                    be.normalize_bwd_scatter(emb, idx_l[r0:r1].contiguous(), loc[0, :r1 - r0].contiguous(), demb, nrm)
+                    be.normalize_bwd_scatter(emb, idx_r[r0:r1].contiguous(), loc[1, :r1 - r0].contiguous(), demb, nrm)
+            out.append(demb)
+        return (None, None, None, None, None, *out)
+
+
+class _IclPair:
+    """One table: (emb, idx_l, idx_r, inv_tau, shard[, normalize]) -> (nll_a, nll_b)."""
+
+    @staticmethod
+    def apply(emb, idx_l, idx_r, inv_tau, shard, normalize=True):
+        return _IclMany.apply(idx_l, idx_r, inv_tau, shard, normalize, emb)
 
 
 class icl_loss(nn.Module):
@@ -246,19 +300,35 @@ class icl_loss(nn.Module):
             # the reference itself fails here: labels are [B, B*n_view] against logits [B, 2B] (model/SNAG_loss.py:84-89)
             raise RuntimeError(f"n_view={self.n_view}: labels [B, B*n_view] do not match the [B, 2B] logits "
                                f"(model/SNAG_loss.py:84-89 raises as well)")
-        idx_l, idx_r = _links_to_index(train_links, emb.device)
+        return self.forward_many([emb], train_links, [weight_norm])[0]
+
+    def forward_many(self, embs, train_links, weight_norms=None):
+        """The same loss for several embedding tables that share the batch `train_links` (what one SNAG step does 2 + 2M
+        times, model/SNAG.py:106,147-159): returns one scalar per table, each equal to forward(emb, train_links,
+        weight_norm=w). One autograd node covers all tables, so their backward sweeps are batched into one launch."""
+        if self.inversion:
+            raise NotImplementedError("inversion=True is unreachable from SNAG (model/SNAG.py:50-51)")
+        if self.n_view != 2:
+            raise RuntimeError(f"n_view={self.n_view}: labels [B, B*n_view] do not match the [B, 2B] logits "
+                               f"(model/SNAG_loss.py:84-89 raises as well)")
+        weight_norms = [None] * len(embs) if weight_norms is None else list(weight_norms)
+        idx_l, idx_r = _links_to_index(train_links, embs[0].device)
         # normalising only the 2B gathered rows equals normalising all N first (model/SNAG_loss.py:60-64), row by row
-        nll_a, nll_b = _IclPair.apply(emb.float(), idx_l, idx_r, _check_tau(self.tau), self.shard or _unsharded())
+        nll = _IclMany.apply(idx_l, idx_r, _check_tau(self.tau), self.shard or _unsharded(), True, *[e.float() for e in embs])
         batch = idx_l.numel()
-        if weight_norm is not None:
-            w = torch.min(torch.stack([weight_norm[idx_l], weight_norm[idx_r]], dim=1), 1)[0]   # :66-69
-            loss_a = (nll_a * w).sum() / batch                                                   # softXEnt :51
-            loss_b = (nll_b * w).sum() / batch
-        else:
-            loss_a = nll_a.sum() / batch                                                         # softXEnt :53
-            loss_b = nll_b.sum() / batch
         alpha = self.weight
-        return alpha * loss_a + (1 - alpha) * loss_b
+        losses = []
+        for p, weight_norm in enumerate(weight_norms):
+            nll_a, nll_b = nll[2 * p], nll[2 * p + 1]
+            if weight_norm is not None:
+                w = torch.min(torch.stack([weight_norm[idx_l], weight_norm[idx_r]], dim=1), 1)[0]   # :66-69
+                loss_a = (nll_a * w).sum() / batch                                                   # softXEnt :51
+                loss_b = (nll_b * w).sum() / batch
+            else:
+                loss_a = nll_a.sum() / batch                                                         # softXEnt :53
+                loss_b = nll_b.sum() / batch
+            losses.append(alpha * loss_a + (1 - alpha) * loss_b)
+        return losses
 
 
 class _Contract(torch.autograd.Function):
@@ -431,22 +501,28 @@ class SnagLossLayer(nn.Module):
         self.criterion_cl_joint.distribute(group, grads)
         return self
 
-    def inner_view_loss(self, streams, train_ill, weight_norm=None):
-        losses = []
-        if weight_norm is not None:
-            weight_norm = weight_norm * weight_norm.shape[1]
-        for emb, col in zip(streams, self.WEIGHT_COLUMN):
-            if emb is None:
-                losses.append(0)
-            elif weight_norm is not None:
-                losses.append(self.criterion_cl(emb, train_ill, weight_norm=weight_norm[:, col]))
-            else:
-                losses.append(self.criterion_cl(emb, train_ill))
+    def inner_view_loss(self, streams, train_ill, weight_norm=None, losses=None):
+        """model/SNAG.py:140-160; `losses` = the per-stream icl_loss values when they were already evaluated in a batch."""
+        if losses is None:
+            present = [(emb, col) for emb, col in zip(streams, self.WEIGHT_COLUMN) if emb is not None]
+            wn = None if weight_norm is None else weight_norm * weight_norm.shape[1]
+            vals = self.criterion_cl.forward_many([e for e, _ in present], train_ill,
+                                                  [None if wn is None else wn[:, c] for _, c in present])
+            it = iter(vals)
+            losses = [0 if emb is None else next(it) for emb in streams]
         return self.multi_loss_layer(losses)
 
     def forward(self, streams, hidden, joint_emb, joint_emb_fz, batch, weight_norm):
-        gmi = self.criterion_cl_joint(joint_emb, batch) + self.criterion_cl_joint(joint_emb_fz, batch)
-        ecia = self.inner_view_loss(streams, batch, weight_norm=weight_norm)
-        iir = self.inner_view_loss(hidden, batch)
+        # all 2 + 2M calls of the step share the batch: one autograd node, so that the backward of the narrow tables is a
+        # single fused launch (criterion_cl and criterion_cl_joint have the same tau / ab_weight, model/SNAG.py:50-51)
+        wn = weight_norm * weight_norm.shape[1]
+        s_pres = [(e, c) for e, c in zip(streams, self.WEIGHT_COLUMN) if e is not None]
+        h_pres = [h for h in hidden if h is not None]
+        vals = self.criterion_cl.forward_many([joint_emb, joint_emb_fz] + [e for e, _ in s_pres] + h_pres, batch,
+                                              [None, None] + [wn[:, c] for _, c in s_pres] + [None] * len(h_pres))
+        gmi = vals[0] + vals[1]
+        it = iter(vals[2:])
+        ecia = self.inner_view_loss(streams, batch, losses=[0 if e is None else next(it) for e in streams])
+        iir = self.inner_view_loss(hidden, batch, losses=[0 if h is None else next(it) for h in hidden])
         loss_list = [gmi, ecia, iir]
         return self.multi_loss_layer_2(*loss_list) if self.awloss else sum(loss_list)     # :116-119

@@ -123,17 +123,20 @@ def joint_fuse_bwd(embs, w_ent, w_glob, d_joint, d_fz):
 def normalize_bwd_scatter(emb: torch.Tensor, idx: torch.Tensor | None, dz: torch.Tensor, demb: torch.Tensor,
                           normalize: bool = True) -> None:
     """demb[idx[r]] += d/d emb[idx[r]] of F.normalize(emb[idx[r]]) . dz[r] — the backward of prep_bf16's gather +
-    normalise, accumulated in place (demb fp32 [N, D], same layout as emb)."""
+    normalise, accumulated in place (demb fp32 [N, D], same layout as emb). dz is [>= n, >= D] or, as the partial sums
+    of the fused backward's column splits, [n_parts, >= n, >= D] (added in split order)."""
     _need(emb, torch.float32, "emb", 2)
-    _need(dz, torch.float32, "dz", 2)
     _need(demb, torch.float32, "demb", 2)
+    if not isinstance(dz, torch.Tensor) or dz.dtype != torch.float32 or not dz.is_cuda or dz.dim() not in (2, 3) or dz.stride(-1) != 1:
+        raise TypeError("dz must be a CUDA fp32 tensor [n, D] or [n_parts, n, D] with contiguous rows")
     if idx is not None:
         _need(idx, torch.int64, "idx", 1)
     n = emb.shape[0] if idx is None else idx.numel()
-    if dz.shape[0] < n or dz.shape[1] != emb.shape[1] or demb.shape != emb.shape:
+    n_parts, part_stride = (1, 0) if dz.dim() == 2 else (dz.shape[0], dz.stride(0))
+    if dz.shape[-2] < n or dz.shape[-1] < emb.shape[1] or demb.shape != emb.shape:
         raise ValueError("normalize_bwd_scatter: shape mismatch")
     call("snag_normalize_bwd_scatter", ptr(emb), emb.stride(0), ptr(idx), n, emb.shape[1], int(normalize), ptr(dz),
-         dz.stride(0), ptr(demb), demb.stride(0), current_stream())
+         dz.stride(-2), n_parts, part_stride, ptr(demb), demb.stride(0), current_stream())
 
 
 def _check_operand(t: torch.Tensor, name: str) -> None:
@@ -307,8 +310,27 @@ def topk_merge_mean(part: torch.Tensor, k: int, want_nv: bool = True, want_cand:
     return (nv, cand) if part_idx is None else (nv, cand, cidx)
 
 
-# |c_tensor_core - c_canonical| is below 2 * (tensor-core dot error) + two fp32 roundings: same budget as RANK_BAND_EPS
-TOPK_VERIFY_DELTA = 4e-6
+# Worst |s_tensor_core - s_canonical| (canonical = fp64 index-order dot rounded once) measured over 2 x 1.07e9 pairs of
+# unit rows built to provoke it (tests/test_eval_baseline_gpu.py::test_band_epsilon_covers_tensor_core_error_on_1e9_pairs:
+# exact duplicates of all-positive and constant rows, where every partial sum is as large as it can be):
+#   1.03e-5 at Dpad = 1216, 1.38e-5 at Dpad = 1856
+# i.e. it grows about linearly with the number of accumulation steps (the tensor core's fp32 accumulation truncates):
+# 8.4e-9 and 7.4e-9 per contraction element, bounded here by 9e-9; on typical (mixed-sign, s << 1) pairs it stays below
+# 1e-6. Every tolerance that separates "the tensor cores decided" from "re-score canonically" is 4 x that bound plus the
+# fp32 chain's roundings.
+TC_DOT_ERR_PER_K = 9e-9
+TC_MARGIN_FLOOR = 4e-6
+
+
+def tc_margin(dpad: int, norm: float = 1.0) -> float:
+    """Half-width (in units of the dot product s) inside which a tensor-core verdict is not trusted, for operands of
+    width `dpad` whose rows have at most `norm` = ||x|| ||y||: 4 x the measured worst accumulation error + 1e-6 for the
+    roundings of the reference's fp32 chain and of the per-row / per-column thresholds."""
+    return max(TC_MARGIN_FLOOR, 4.0 * TC_DOT_ERR_PER_K * dpad * max(1.0, norm) + 1e-6)
+
+
+# |c_tensor_core - c_canonical| = 2 |s_tc - s_canonical| + two fp32 roundings: the neighbourhood verification works in c
+TOPK_VERIFY_DELTA = 2.0
 TOPK_EXHAUSTIVE_BUDGET = 4.0e12     # bf16 multiply-adds the exhaustive completion may spend (~1 s of fp64 work on a B200)
 LAST_TOPK_INFO: dict = {}
 
@@ -368,18 +390,19 @@ def pair_score(X, Y, n: int, xn, yn, nv1, nv2, use_csls: bool, want_dot: bool = 
     return (g, s) if want_dot else g
 
 
-# Half-width of the rank sweep's deferral band, in units of the dot product s. It has to cover (a) the tensor core's
-# accumulation error against the fp64 index-order dot product (measured < 5e-7 for unit rows up to D = 1856;
-# tests/test_eval_gpu.py::test_tensor_core_dot_error pins it), (b) the roundings of the reference's fp32 chain
-# (< 1e-6 in distance = 2.5e-7 in s) and (c) the roundings of the per-row / per-column thresholds (< 3e-7).
-RANK_BAND_EPS = 4e-6
+# Half-width of the rank sweep's deferral band, in units of the dot product s, as a multiple of tc_margin(): it has to
+# cover (a) the tensor core's accumulation error against the fp64 index-order dot product (TC_DOT_ERR_PER_K above),
+# (b) the roundings of the reference's fp32 chain (< 1e-6 in distance = 2.5e-7 in s) and (c) the roundings of the
+# per-row / per-column thresholds (< 3e-7). A wider band only defers more elements to the canonical re-score
+# (a few 1e4 of 1e12 at 1M x 1M).
+RANK_BAND_EPS = 1.0
 
 
 def _error_scale(xn: torch.Tensor, yn: torch.Tensor, dpad: int) -> float:
-    """Factor by which the tensor-core dot error can exceed the unit-row, D <= 2048 case RANK_BAND_EPS is pinned on:
-    it grows with the operands' norms (||x|| ||y||) and with the square root of the contraction width."""
+    """tc_margin for these operands: the measured bound scaled by the contraction width and by the largest
+    ||x|| ||y|| present (align_ranks only lets nearly-unit rows through)."""
     norm = float(torch.sqrt(xn.max() * yn.max()).item())
-    return max(1.0, norm) * max(1.0, (dpad / 2048.0) ** 0.5)
+    return tc_margin(dpad, norm)
 RANK_BAND_MIN_CAP = 1 << 20
 RANK_BAND_PER_ROW = 16         # initial list capacity per evaluated row + column
 RANK_BAND_MAX_CAP = 1 << 28    # beyond this many deferred elements (2 GB list) the in-kernel chain takes over
@@ -544,6 +567,47 @@ def icl_bwd_logits(X: torch.Tensor, Y: torch.Tensor, B: int, Bp: int, inv_tau: f
         call("snag_icl_bwd_logits", ptr(X), ptr(Y), B, Bp, row0, nx, X.shape[1], inv_tau, ptr(cr), ptr(cc), ptr(dg), ptr(G),
              int(self_cols), float(ebar), current_stream())
     return G
+
+
+FUSED_BWD_MAX_DPAD = 320      # dZ accumulator (Dpad fp32 columns) + logits stages + P buffers must fit the 512 TMEM columns
+FUSED_BWD_MAX_PROBLEMS = 16
+
+
+def icl_bwd_fused(S3s, cras, crbs, dgs, B: int, Bp: int, inv_tau: float, row0: int = 0, nx: int | None = None):
+    """Fused backward of icl_loss w.r.t. the normalised rows for Dpad <= 320 (snag_icl_bwd_fused): for each problem p
+    (stacked operand S3s[p] = [a ; b ; a] as [3 Bp, Dpad] bf16, row coefficients cras[p] / crbs[p] and diagonal term
+    dgs[p], all [>= B] fp32) returns (dz_a, dz_b), each [nsplit, nx, Dpad] fp32: the partial gradients of the anchors
+    [row0, row0 + nx) of side a / b over the column splits (sum over dim 0 = dL/dz). No [B, 2B] matrix touches HBM."""
+    import ctypes
+    n_prob = len(S3s)
+    if not 1 <= n_prob <= FUSED_BWD_MAX_PROBLEMS or not (len(cras) == len(crbs) == len(dgs) == n_prob):
+        raise ValueError(f"1..{FUSED_BWD_MAX_PROBLEMS} problems with one coefficient set each")
+    nx = Bp if nx is None else int(nx)
+    if row0 % 128 or nx % 128 or nx < 128 or row0 + nx > Bp:
+        raise ValueError("anchor range must be whole blocks of 128 rows inside [0, Bp)")
+    dpad = S3s[0].shape[1]
+    for t in S3s:
+        _check_operand(t, "S3")
+        if tuple(t.shape) != (3 * Bp, dpad):
+            raise ValueError("every stacked operand must be [3 * Bp, Dpad] with the same Dpad")
+    if dpad > FUSED_BWD_MAX_DPAD:
+        raise SnagError(f"fused ICL backward supports Dpad <= {FUSED_BWD_MAX_DPAD}, got {dpad}")
+    for lst, nm in ((cras, "cr_a"), (crbs, "cr_b"), (dgs, "dg")):
+        for t in lst:
+            _need(t, torch.float32, nm, 1)
+            if t.numel() < B:
+                raise ValueError(f"{nm} needs at least B entries")
+    dev = S3s[0].device
+    rbs = nx // 128
+    nsplit = int(_lib.load().snag_icl_bwd_fused_splits(n_prob, B, Bp, rbs))
+    # one allocation for all partial outputs: [problem][side][split][nx][Dpad]
+    out = torch.empty((n_prob, 2, nsplit, nx, dpad), dtype=torch.float32, device=dev)
+    arr = lambda ts: (ctypes.c_void_p * n_prob)(*[t.data_ptr() for t in ts])
+    with _SweepTimer("icl_bwd_fused_kernel", 2 * n_prob * nx, 2 * Bp, 2 * dpad):      # two MMAs per logits element
+        call("snag_icl_bwd_fused", n_prob, arr(S3s), arr(cras), arr(crbs), arr(dgs), arr([out[i, 0] for i in range(n_prob)]),
+             arr([out[i, 1] for i in range(n_prob)]), B, Bp, row0 // 128, rbs, dpad, float(inv_tau), nsplit, nx * dpad,
+             current_stream())
+    return [(out[i, 0], out[i, 1]) for i in range(n_prob)]
 
 
 def contract(P: torch.Tensor, Q: torch.Tensor, n1: int, n2: int) -> torch.Tensor:

@@ -82,8 +82,14 @@ def test_two_sweep_size_against_oracle(cuda_device):
     assert evaluate.two_sweep_plan(n, k) is not None
     x, y = _clustered(n, d, 8.0, 3409)
     X, Y, xn, yn = _prep(x, y, cuda_device)
-    res = evaluate.align_ranks(X, Y, xn, yn, n, k, True)
-    assert res.launches >= 17                 # the two-sweep path really ran (pre-passes + stream bucketing)
+    sweeps = []
+    ops.SWEEP_EVENT_SINK = sweeps
+    try:
+        res = evaluate.align_ranks(X, Y, xn, yn, n, k, True)
+    finally:
+        ops.SWEEP_EVENT_SINK = None
+    kinds = {nm for nm, *_ in sweeps}
+    assert "sim_kernel<EpiRowColTopK>" in kinds      # the two-sweep path really ran (one sweep for both directions)
     # the oracle: materialised when the n x n fp32 matrix fits comfortably in host memory (one pass over the dot
     # products), streaming otherwise (two passes)
     if psutil.virtual_memory().available > 3 * 4 * n * n:
@@ -118,7 +124,8 @@ def _adversarial_rows(n, d, seed):
 
 @pytest.mark.parametrize("d", [1200, 1856])
 def test_band_epsilon_covers_tensor_core_error_on_1e9_pairs(cuda_device, d):
-    """ops.RANK_BAND_EPS / TOPK_VERIFY_DELTA rest on a bound for |s_tensor_core - s_canonical| on unit rows. Measure it
+    """ops.tc_margin (the rank sweep's deferral band and the neighbourhood verification) rests on a bound for
+    |s_tensor_core - s_canonical| on unit rows (ops.TC_DOT_ERR_PER_K x Dpad). Measure it
     on 32 768^2 = 1.07e9 pairs per width (D = 1200 -> Dpad 1216, and Dpad 1856, the widest the configs use) that
     include exact duplicates, near-duplicates, all-positive / constant rows (largest partial sums) and sign-alternating
     rows (full cancellation). Comparator: fp64 GEMM rounded once to fp32 — within half an fp32 ulp (3e-8 for |s| <= 1)
@@ -146,6 +153,6 @@ def test_band_epsilon_covers_tensor_core_error_on_1e9_pairs(cuda_device, d):
     ref = (Xd[torch.from_numpy(ri).long().to(cuda_device)] * Xd[torch.from_numpy(ci).long().to(cuda_device)]).sum(1).float()
     assert float((canon - ref).abs().max()) <= 6e-8
     print(f"\n[band] D={d}: max |s_tc - s_fp64| over {pairs:.3e} pairs = {worst:.3e} (diagonal: {worst_diag:.3e}); "
-          f"RANK_BAND_EPS = {ops.RANK_BAND_EPS:.1e}")
-    scale = max(1.0, (X.shape[1] / 2048.0) ** 0.5)
-    assert worst * 4 <= ops.RANK_BAND_EPS * scale and worst * 4 <= ops.TOPK_VERIFY_DELTA * scale, worst
+          f"model {ops.TC_DOT_ERR_PER_K * X.shape[1]:.3e}, margin {ops.tc_margin(X.shape[1]):.3e}")
+    assert worst <= ops.TC_DOT_ERR_PER_K * X.shape[1], worst             # the model bounds what was measured
+    assert 4 * worst <= ops.tc_margin(X.shape[1]), worst                 # and the margins keep 4x over it

@@ -94,13 +94,13 @@ def test_against_oracle(cuda_device, n, d, k, csls, sigma):
 
 @pytest.mark.parametrize("n,d", [(1500, 1200), (1100, 1800), (2100, 300)])
 def test_tensor_core_dot_error(cuda_device, n, d):
-    """The deferral band of the rank sweep (ops.RANK_BAND_EPS) must cover the distance between the tensor core's dot
+    """The deferral band of the rank sweep (ops.tc_margin) must cover the distance between the tensor core's dot
     product and the canonical one (fp64, index order, rounded once) for unit rows: pin it with a 4x safety factor on a few million samples."""
     x, y = _clustered(n, d, 4.0, 11)
     X, Y, xn, yn = _prep(x, y, cuda_device)
     S = ops.sim_write(X, Y, None, None, n, n, 0).cpu().numpy()
     ref = oracle.dot_matrix(x, y)
-    assert np.abs(S - ref).max() < ops.RANK_BAND_EPS / 4
+    assert np.abs(S - ref).max() < ops.tc_margin(X.shape[1]) / 4
 
 
 @pytest.mark.parametrize("n,d,k,csls,sigma", [(2048, 1200, 10, True, 8.0), (1000, 300, 10, False, 3.0),

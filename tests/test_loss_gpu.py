@@ -286,3 +286,81 @@ def test_grad_contract_split_k(cuda_device, n_rows, d, k):
     assert _relerr(out, ref) < 1e-5
     old = ops.contract(G, YT, n_rows, d)
     assert _relerr(out, old) < 1e-5
+
+
+@pytest.mark.parametrize("B,D,n_prob,row0,nx", [(300, 64, 1, 0, None), (1000, 300, 3, 0, None), (3500, 300, 8, 0, None),
+                                                 (3500, 300, 2, 1024, 1536), (5000, 256, 1, 0, None), (16384, 300, 1, 8192, 2048)])
+def test_fused_backward_kernel_matches_two_kernel_form(cuda_device, B, D, n_prob, row0, nx):
+    """snag_icl_bwd_fused (logits -> dL/dlogits in registers -> second MMA from tensor memory; nothing in HBM) against
+    the two-kernel form it replaces for narrow tables: sim_kernel<EpiIclBwd> writes G in bf16, then G . [other ; this]
+    in fp32 torch. Same operands, same coefficients, same bf16 rounding of G: the difference is accumulation order."""
+    g = torch.Generator(device="cuda").manual_seed(B + D + n_prob)
+    Bp, dpad = ops.round_up(B, 256), ops.round_up(D, 64)
+    inv_tau = 10.0
+    S3s, cras, crbs, dgs = [], [], [], []
+    for _ in range(n_prob):
+        z = F.normalize(torch.randn((2 * B, D), generator=g, device=cuda_device) +
+                        torch.randn((1, D), generator=g, device=cuda_device), dim=1)
+        S3 = torch.zeros((3 * Bp, dpad), dtype=torch.bfloat16, device=cuda_device)
+        ops.prep_bf16(z[:B].contiguous(), None, normalize=False, out=S3[0:Bp])
+        ops.prep_bf16(z[B:].contiguous(), None, normalize=False, out=S3[Bp:2 * Bp])
+        S3[2 * Bp:2 * Bp + B].copy_(S3[0:B])
+        la, _, _ = ops.icl_side(S3[0:Bp], S3[Bp:3 * Bp], B, Bp, inv_tau)
+        lb, _, _ = ops.icl_side(S3[Bp:2 * Bp], S3[0:2 * Bp], B, Bp, inv_tau)
+        ga = torch.rand((B,), generator=g, device=cuda_device) / B
+        gb = torch.rand((B,), generator=g, device=cuda_device) / B
+        S3s.append(S3)
+        cras.append((ga * torch.exp(inv_tau - la)).contiguous())
+        crbs.append((gb * torch.exp(inv_tau - lb)).contiguous())
+        dgs.append((ga + gb).contiguous())
+    n_rows = Bp if nx is None else nx
+    res = ops.icl_bwd_fused(S3s, cras, crbs, dgs, B, Bp, inv_tau, row0, nx)
+    assert len(res) == n_prob
+    for p in range(n_prob):
+        S3 = S3s[p]
+        Ya, Yb = S3[Bp:3 * Bp], S3[0:2 * Bp]
+        Ga = ops.icl_bwd_logits(S3[row0:row0 + n_rows], Ya, B, Bp, inv_tau, cras[p], crbs[p], dgs[p], row0, n_rows)
+        Gb = ops.icl_bwd_logits(S3[Bp + row0:Bp + row0 + n_rows], Yb, B, Bp, inv_tau, crbs[p], cras[p], dgs[p], row0, n_rows)
+        for got, G, Y in ((res[p][0], Ga, Ya), (res[p][1], Gb, Yb)):
+            assert got.dim() == 3 and got.shape[1:] == (n_rows, dpad)
+            ref = G.float() @ Y.float()
+            tot = got.sum(0)
+            assert _relerr(tot, ref) < 2e-3, (p, _relerr(tot, ref))
+            assert float((tot - ref).abs().max()) <= 2e-3 * float(ref.abs().max())
+            valid = max(0, min(n_rows, B - row0))
+            assert float(tot[valid:].abs().max() if valid < n_rows else 0.0) == 0.0      # anchors in the padding: zero rows
+            assert float(tot[:, D:].abs().max() if D < dpad else 0.0) == 0.0              # padded columns stay zero
+
+
+@pytest.mark.parametrize("B,D,M", [(1000, 300, 4), (3500, 300, 6)])
+def test_loss_layer_fused_equals_unfused(cuda_device, B, D, M, monkeypatch):
+    """The whole loss-layer slice (2 + 2M icl_loss calls) with the batched fused backward against the same slice on the
+    two-kernel backward: losses identical (same forward), gradients equal up to accumulation order."""
+    g = torch.Generator(device="cuda").manual_seed(B + M)
+    N = 2 * B + 100
+    mk = lambda w: torch.randn((N, w), generator=g, device=cuda_device).requires_grad_(True)
+    present = [True] * M + [False] * (6 - M)
+    streams = [mk(D) if p else None for p in present]
+    hidden = [mk(D) if p else None for p in present]
+    joint, joint_fz = mk(M * D), mk(M * D)
+    wn = torch.softmax(torch.randn((N, 6), generator=g, device=cuda_device), 1).requires_grad_(True)
+    leaves = [t for t in streams + hidden + [joint, joint_fz, wn] if t is not None]
+    links = torch.stack([torch.randperm(N // 2, generator=g, device=cuda_device)[:B],
+                         N // 2 + torch.randperm(N // 2, generator=g, device=cuda_device)[:B]], 1)
+    layer = sloss.SnagLossLayer(tau=0.1, ab_weight=0.5).to(cuda_device)
+    results = []
+    for fused in (True, False):
+        monkeypatch.setattr(sloss, "FUSED_BACKWARD", fused)
+        for t in leaves:
+            t.grad = None
+        loss = layer(streams, hidden, joint, joint_fz, links, wn)
+        loss.backward()
+        results.append((loss.item(), [t.grad.clone() for t in leaves]))
+    assert results[0][0] == results[1][0]
+    for a, b in zip(results[0][1], results[1][1]):
+        assert _relerr(a, b) < 2e-3
+    # and the batched call equals separate icl_loss calls
+    crit = sloss.icl_loss(tau=0.1, ab_weight=0.5)
+    single = crit(streams[0], links, weight_norm=(wn * 6)[:, 3])
+    many = crit.forward_many([streams[0], hidden[1]], links, [(wn * 6)[:, 3], None])
+    assert abs(single.item() - many[0].item()) <= 1e-6 * abs(single.item())
