@@ -1,0 +1,3 @@
+set -x
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 2 --warmup 3 > gpurun_out/r02d_bench_n2.json 2> gpurun_out/r02d_bench_n2.err; echo "rc=$?" >> gpurun_out/r02d_bench_n2.err
+tail -c 1500 gpurun_out/r02d_bench_n2.err

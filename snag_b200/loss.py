@@ -17,6 +17,8 @@ of both sets, the target probabilities written once in bf16 and contracted with 
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 from torch import nn
@@ -139,7 +141,7 @@ def _unsharded() -> AnchorShard:
 # Contraction widths up to ops.FUSED_BWD_MAX_DPAD (the per-modality calls, D = 300) take the fused backward: logits tile
 # recomputed, dL/dlogits formed in registers and kept in tensor memory as the A operand of a second tcgen05.mma — no
 # [B, 2B] matrix in HBM. Wider tables (the joint embeddings) keep the two-kernel form, where the MMAs dominate anyway.
-FUSED_BACKWARD = True
+FUSED_BACKWARD = os.environ.get("SNAG_FUSED_BACKWARD", "1") != "0"      # A/B switch for measurements
 
 
 class _IclMany(torch.autograd.Function):
