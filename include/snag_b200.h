@@ -250,6 +250,15 @@ int64_t snag_csls_workspace_bytes(int64_t n1, int64_t n2);
 int snag_csls_sim(const float* sim, int64_t n1, int64_t n2, int64_t ld, int32_t k, float* out, int64_t ld_out, float* nv1,
                   float* nv2, void* workspace, void* stream);
 
+/* --distance 1 (main.py:387-390, scipy cdist "cityblock" on the host in the reference): out[i,j] = fp32 of the fp64
+ * index-order sum of |x_ik - y_jk| for fp32 x [n1, D], y [n2, D]. Materialising, like the reference. */
+int snag_l1_distance(const float* x, const float* y, int64_t n1, int64_t n2, int32_t D, int64_t ldx, int64_t ldy, float* out,
+                     int64_t ldo, void* stream);
+/* The ranking loops of Runner._test (main.py:400-411, 422-429) on a materialised square distance matrix d [n, ld]:
+ * cnt_row[i] / cnt_col[j] = 0-based position of the ground truth (the diagonal) in the stable ascending sort of row i /
+ * column j. Used by the --distance 1 path, where no contraction exists to fuse the counting into. */
+int snag_matrix_rank(const float* d, int64_t n, int64_t ld, int32_t* cnt_row, int32_t* cnt_col, void* stream);
+
 /* ---- mutual nearest neighbours (iterative-learning link mining) ------------------------------- */
 /* The argmin pair of model/SNAG.py:192-208 (Iter_new_links: torch.argmin over the rows and over the columns of
  * pairwise_distances(final_emb[left], final_emb[right])) without forming the distance matrix.

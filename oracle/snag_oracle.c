@@ -487,3 +487,36 @@ done:
   free(yt); free(xn); free(yn); free(blk);
   return rc;
 }
+
+/* --distance 1 (main.py:387-390): scipy.spatial.distance.cdist(..., metric="cityblock") on the fp32 embeddings, result
+ * rounded to fp32 by torch.FloatTensor. out[i,j] = fl32( sum_k |(double)x_ik - (double)y_jk| ), k ascending. */
+int oracle_l1_distance(const float* x, const float* y, int64_t n1, int64_t n2, int64_t d, int64_t ldx, int64_t ldy, float* out) {
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n1; ++i)
+    for (int64_t j = 0; j < n2; ++j) {
+      double acc = 0.0;
+      const float* a = x + i * ldx;
+      const float* b = y + j * ldy;
+      for (int64_t k = 0; k < d; ++k) acc += fabs((double)a[k] - (double)b[k]);
+      out[i * n2 + j] = (float)acc;
+    }
+  return 0;
+}
+
+/* ranks of the diagonal on a materialised distance matrix (the loops of main.py:400-411, 422-429 with a stable sort) */
+int oracle_matrix_rank(const float* dist, int64_t n, int32_t* rank_l2r, int32_t* rank_r2l) {
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n; ++i) {
+    const float g = dist[i * n + i];
+    int32_t c = 0, cc = 0;
+    for (int64_t j = 0; j < n; ++j) {
+      const float v = dist[i * n + j];
+      c += (v < g) || (v == g && j < i);
+      const float w = dist[j * n + i];
+      cc += (w < g) || (w == g && j < i);
+    }
+    rank_l2r[i] = c;
+    rank_r2l[i] = cc;
+  }
+  return 0;
+}

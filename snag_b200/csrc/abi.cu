@@ -82,6 +82,13 @@ int snag_normalize_bwd_scatter(const float* emb, int64_t ld, const int64_t* idx,
   return launch_normalize_bwd_scatter(emb, ld, reinterpret_cast<const long long*>(idx), n, D, normalize, dz, ld_dz, n_parts,
                                       part_stride, demb, ld_demb, S(stream));
 }
+int snag_l1_distance(const float* x, const float* y, int64_t n1, int64_t n2, int32_t D, int64_t ldx, int64_t ldy, float* out,
+                     int64_t ldo, void* stream) {
+  return launch_l1_distance(x, y, n1, n2, D, ldx, ldy, out, ldo, S(stream));
+}
+int snag_matrix_rank(const float* d, int64_t n, int64_t ld, int32_t* cnt_row, int32_t* cnt_col, void* stream) {
+  return launch_matrix_rank(d, n, ld, cnt_row, cnt_col, S(stream));
+}
 int32_t snag_icl_bwd_fused_splits(int32_t n_prob, int32_t B, int32_t Bp, int32_t row_blocks) {
   return icl_bwd_fused_splits(n_prob, B, Bp, row_blocks);
 }

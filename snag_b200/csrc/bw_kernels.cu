@@ -1073,12 +1073,104 @@ int launch_csls_sim(const float* sim, long long n1, long long n2, long long ld, 
   return static_cast<int>(cudaGetLastError());
 }
 
+// ------------------------------------------------------------------------------------------------
+// --distance 1 (main.py:387-390): the reference moves the embeddings to the host and calls
+// scipy.spatial.distance.cdist(..., metric="cityblock"), whose result (float64) torch.FloatTensor rounds to fp32.
+//   out[i,j] = fl32( sum_k | (double)x_ik - (double)y_jk | )      accumulated in fp64 in index order
+// Not a contraction (no tensor cores): 32 x 32 output tile per block, x / y tiles staged in shared memory 32 k at a time.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) l1_distance_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                                          long long n1, long long n2, int D, long long ldx, long long ldy,
+                                                          float* __restrict__ out, long long ldo) {
+  __shared__ float xs[32][33];
+  __shared__ float ys[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 8 warps: warp ty owns rows ty, ty+8, ty+16, ty+24
+  const long long i0 = static_cast<long long>(blockIdx.y) * 32, j0 = static_cast<long long>(blockIdx.x) * 32;
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int k0 = 0; k0 < D; k0 += 32) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int row = ty + 8 * r;
+      const int kk = k0 + tx;
+      xs[row][tx] = (i0 + row < n1 && kk < D) ? __ldg(x + (i0 + row) * ldx + kk) : 0.f;
+      ys[row][tx] = (j0 + row < n2 && kk < D) ? __ldg(y + (j0 + row) * ldy + kk) : 0.f;
+    }
+    __syncthreads();
+    const int kmax = min(32, D - k0);
+    for (int kk = 0; kk < kmax; ++kk) {
+      const double yv = static_cast<double>(ys[tx][kk]);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) acc[r] += fabs(static_cast<double>(xs[ty + 8 * r][kk]) - yv);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const long long i = i0 + ty + 8 * r, j = j0 + tx;
+    if (i < n1 && j < n2) out[i * ldo + j] = static_cast<float>(acc[r]);
+  }
+}
+
+// Ranks of the ground truth on a MATERIALISED distance matrix (the two loops of main.py:400-411, 422-429 as counts):
+//   cnt_row[i] = #{ j : d_ij < d_ii  or (d_ij == d_ii and j < i) },   cnt_col[j] = #{ i : d_ij < d_jj or (== and i < j) }
+// one warp per row for the row counts; column counts by 32-row slabs with one atomic per (slab, column).
+__global__ void __launch_bounds__(256) matrix_rank_kernel(const float* __restrict__ d, long long n, long long ld,
+                                                          int* __restrict__ cnt_row, int* __restrict__ cnt_col) {
+  const long long warp = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long n_slabs = (n + 31) / 32;
+  if (warp < n) {                                          // rows
+    const long long i = warp;
+    const float g = __ldg(d + i * ld + i);
+    int c = 0;
+    for (long long j = lane; j < n; j += 32) {
+      const float v = __ldg(d + i * ld + j);
+      c += (v < g) || (v == g && j < i);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0) cnt_row[i] = c;
+  } else if (warp < n + n_slabs * ((n + 31) / 32)) {       // columns: (row slab, column group of 32)
+    const long long t = warp - n;
+    const long long slab = t / ((n + 31) / 32), cg = t % ((n + 31) / 32);
+    const long long j = cg * 32 + lane;
+    if (j < n) {
+      const float g = __ldg(d + j * ld + j);
+      int c = 0;
+      const long long i1 = min(n, (slab + 1) * 32);
+      for (long long i = slab * 32; i < i1; ++i) {
+        const float v = __ldg(d + i * ld + j);
+        c += (v < g) || (v == g && i < j);
+      }
+      if (c) atomicAdd(cnt_col + j, c);
+    }
+  }
+}
+
 static inline int grid_for(long long work_items, int block, int num_sms, int ctas_per_sm) {
   long long g = (work_items + block - 1) / block;
   const long long cap = static_cast<long long>(num_sms) * ctas_per_sm;
   if (g > cap) g = cap;
   if (g < 1) g = 1;
   return static_cast<int>(g);
+}
+
+int launch_l1_distance(const float* x, const float* y, long long n1, long long n2, int D, long long ldx, long long ldy,
+                       float* out, long long ldo, cudaStream_t st) {
+  if (!x || !y || !out || n1 <= 0 || n2 <= 0 || D <= 0 || ldx < D || ldy < D || ldo < n2) return SNAG_ERR_ARG;
+  const dim3 grid(static_cast<unsigned>((n2 + 31) / 32), static_cast<unsigned>((n1 + 31) / 32));
+  if (grid.y > 65535) return SNAG_ERR_SHAPE;
+  l1_distance_kernel<<<grid, 256, 0, st>>>(x, y, n1, n2, D, ldx, ldy, out, ldo);
+  return static_cast<int>(cudaGetLastError());
+}
+int launch_matrix_rank(const float* d, long long n, long long ld, int* cnt_row, int* cnt_col, cudaStream_t st) {
+  if (!d || !cnt_row || !cnt_col || n <= 0 || ld < n) return SNAG_ERR_ARG;
+  const long long groups = (n + 31) / 32;
+  const long long warps = n + groups * groups;
+  const cudaError_t e = cudaMemsetAsync(cnt_col, 0, sizeof(int) * static_cast<size_t>(n), st);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  matrix_rank_kernel<<<static_cast<unsigned>((warps * 32 + 255) / 256), 256, 0, st>>>(d, n, ld, cnt_row, cnt_col);
+  return static_cast<int>(cudaGetLastError());
 }
 
 int launch_noise_mask(const float* x, float* out, const float* mean, const float* stdv, const uint8_t* mask,

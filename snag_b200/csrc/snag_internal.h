@@ -45,6 +45,9 @@ int launch_joint_fuse_bwd(const float* const* embs, float* const* d_embs, const 
 int launch_normalize_bwd_scatter(const float* emb, long long ld, const long long* idx, int n, int D, int normalize,
                                  const float* dz, long long ld_dz, int n_parts, long long part_stride, float* demb,
                                  long long ld_demb, cudaStream_t st);
+int launch_l1_distance(const float* x, const float* y, long long n1, long long n2, int D, long long ldx, long long ldy,
+                       float* out, long long ldo, cudaStream_t st);
+int launch_matrix_rank(const float* d, long long n, long long ld, int* cnt_row, int* cnt_col, cudaStream_t st);
 // fused ICL backward for Dpad <= 320 (icl_fused.cu)
 int icl_bwd_fused_splits(int n_prob, int B, int Bp, int row_blocks);
 int launch_icl_bwd_fused(int n_prob, const __nv_bfloat16* const* S3, const float* const* cr_a, const float* const* cr_b,

@@ -336,13 +336,18 @@ LAST_TOPK_INFO: dict = {}
 
 
 def topk_rescore(A, B, an, bn, cand_idx: torch.Tensor, cand_val: torch.Tensor, k: int, n_b: int, tag: str = "rows",
-                 want_best: bool = False, outsider_bound: torch.Tensor | None = None):
+                 want_best: bool = False, outsider_bound: torch.Tensor | None = None, norm_bound: float | None = None,
+                 lazy: bool = False):
     """Canonical CSLS neighbourhood means of the rows of A from their KT tensor-core candidates (rows of B); rows the
     candidates cannot vouch for are completed by an exhaustive scan of B (within TOPK_EXHAUSTIVE_BUDGET; beyond it the
     candidate-based value stays and the count is reported in LAST_TOPK_INFO[tag]['unverified']).
     want_best: return (nv, best_d, best_idx) — every row's nearest row of B under the canonical squared distance, lowest
     index on ties (the argmin of link mining).
-    outsider_bound [n_rows]: the admission threshold the lists were collected under, if any (see snag_topk_rescore)."""
+    outsider_bound [n_rows]: the admission threshold the lists were collected under, if any (see snag_topk_rescore).
+    norm_bound: an upper bound of ||a|| ||b|| the caller vouches for (saves the host round trip that measures it).
+    lazy: no host synchronisation at all — the exhaustive completion is enqueued unconditionally (it reads the flagged
+    count on the device and does nothing when it is zero) for at most the budgeted number of rows, and
+    LAST_TOPK_INFO[tag] holds the DEVICE counter ('flagged_dev') and 'budget_rows' for the caller to check later."""
     _check_operand(A, "A")
     _check_operand(B, "B")
     _need(cand_idx, torch.int32, "cand_idx", 2)
@@ -360,9 +365,17 @@ def topk_rescore(A, B, an, bn, cand_idx: torch.Tensor, cand_val: torch.Tensor, k
     cap = n_rows
     flagged = torch.empty((cap,), dtype=torch.int32, device=dev)
     fcnt = torch.zeros((1,), dtype=torch.int32, device=dev)
+    margin = tc_margin(A.shape[1], norm_bound) if norm_bound is not None else _error_scale(an, bn, A.shape[1])
     call("snag_topk_rescore", ptr(A), ptr(B), A.shape[1], n_rows, ptr(an), ptr(bn), ptr(cand_idx), ptr(cand_val), k,
-         TOPK_VERIFY_DELTA * _error_scale(an, bn, A.shape[1]), ptr(outsider_bound), ptr(nv), ptr(flagged), ptr(fcnt), cap,
+         TOPK_VERIFY_DELTA * margin, ptr(outsider_bound), ptr(nv), ptr(flagged), ptr(fcnt), cap,
          ptr(best_d), ptr(best_i), st)
+    if lazy:
+        budget_rows = int(min(cap, TOPK_EXHAUSTIVE_BUDGET // max(1, n_b * A.shape[1])))
+        if budget_rows > 0:
+            call("snag_topk_exhaustive", ptr(A), ptr(B), A.shape[1], n_b, ptr(an), ptr(bn), ptr(flagged), ptr(fcnt), budget_rows,
+                 k, ptr(nv), ptr(best_d), ptr(best_i), st)
+        LAST_TOPK_INFO[tag] = {"flagged_dev": fcnt, "budget_rows": budget_rows}
+        return (nv, best_d, best_i) if want_best else nv
     n_flag = int(fcnt.item())
     info = {"flagged": n_flag, "unverified": 0}
     if n_flag:
@@ -409,12 +422,15 @@ RANK_BAND_MAX_CAP = 1 << 28    # beyond this many deferred elements (2 GB list) 
 
 
 def eval_rank(X, Y, xn, yn, nv1, nv2, g_row, g_col, row_gid0: int, col_gid0: int, n1: int, n2: int, use_csls: bool,
-              cnt_row: torch.Tensor, cnt_col: torch.Tensor, want_top3: bool = False, exact_chain: bool = False):
+              cnt_row: torch.Tensor, cnt_col: torch.Tensor, want_top3: bool = False, exact_chain: bool = False,
+              norm_bound: float | None = None, lazy: bool = False):
     """Rank counters of sweep 2, accumulated into cnt_row / cnt_col. Default: s-space sweep with a deferral band
     (snag_eval_rank_band) followed by the canonical re-score of the deferred elements (snag_band_rescore); a band list
     that overflows is retried with a larger list, and degenerate inputs (almost everything tied) fall back to the
     in-kernel fp32 chain (snag_eval_rank, `exact_chain=True`). Returns the per-list nearest-candidate lists
-    ([n_lists, n1, 4] values, ids) when want_top3, else (None, None)."""
+    ([n_lists, n1, 4] values, ids) when want_top3, else (None, None).
+    lazy: one attempt with the initial list capacity and no host synchronisation; LAST_RANK_INFO holds the DEVICE
+    counter ('deferred_dev') and 'cap' — the caller must check deferred <= cap before trusting the counters."""
     _check_operand(X, "X")
     _check_operand(Y, "Y")
     _need(cnt_row, torch.int32, "cnt_row", 1)
@@ -426,8 +442,20 @@ def eval_rank(X, Y, xn, yn, nv1, nv2, g_row, g_col, row_gid0: int, col_gid0: int
         t3i = torch.empty((nch, n1, 4), dtype=torch.int32, device=X.device)
     st = current_stream()
     if not exact_chain:
-        eps = RANK_BAND_EPS * _error_scale(xn, yn, X.shape[1])
+        eps = RANK_BAND_EPS * (tc_margin(X.shape[1], norm_bound) if norm_bound is not None else _error_scale(xn, yn, X.shape[1]))
         cap = max(RANK_BAND_MIN_CAP, RANK_BAND_PER_ROW * (n1 + n2))
+        if lazy:
+            band = torch.empty((cap,), dtype=torch.int64, device=X.device)
+            band_cnt = torch.zeros((1,), dtype=torch.int32, device=X.device)
+            with _SweepTimer("sim_kernel<EpiRank>", n1, n2):
+                call("snag_eval_rank_band", ptr(X), ptr(Y), ptr(xn), ptr(yn), ptr(nv1), ptr(nv2), ptr(g_row), ptr(g_col),
+                     row_gid0, col_gid0, n1, n2, X.shape[1], int(use_csls), eps, ptr(cnt_row), ptr(cnt_col),
+                     ptr(t3v), ptr(t3i), ptr(band), ptr(band_cnt), cap, st)
+            call("snag_band_rescore", ptr(X), ptr(Y), X.shape[1], ptr(xn), ptr(yn), ptr(nv1), ptr(nv2), ptr(g_row),
+                 ptr(g_col), row_gid0, col_gid0, int(use_csls), ptr(band), ptr(band_cnt), cap, ptr(cnt_row), ptr(cnt_col), st)
+            LAST_RANK_INFO.clear()
+            LAST_RANK_INFO.update(deferred_dev=band_cnt, cap=cap, mode="band", eps=eps)
+            return t3v, t3i
         row_save = col_save = None
         while cap <= RANK_BAND_MAX_CAP:
             band = torch.empty((cap,), dtype=torch.int64, device=X.device)
@@ -509,6 +537,30 @@ def top3_merge(val: torch.Tensor, idx: torch.Tensor):
     oidx = torch.empty((n_rows, 4), dtype=torch.int32, device=val.device)
     call("snag_top3_merge", ptr(val), ptr(idx), n_lists, n_rows, ptr(oval), ptr(oidx), current_stream())
     return oval, oidx
+
+
+def l1_distance(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    """fp32 [n1, n2] cityblock distances of fp32 rows (fp64 index-order accumulation, rounded once): --distance 1."""
+    _need(x, torch.float32, "x", 2)
+    _need(y, torch.float32, "y", 2)
+    if x.shape[1] != y.shape[1]:
+        raise ValueError("x and y must have the same width")
+    out = torch.empty((x.shape[0], y.shape[0]), dtype=torch.float32, device=x.device)
+    call("snag_l1_distance", ptr(x), ptr(y), x.shape[0], y.shape[0], x.shape[1], x.stride(0), y.stride(0), ptr(out),
+         out.stride(0), current_stream())
+    return out
+
+
+def matrix_rank(dist: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
+    """(rank_l2r, rank_r2l) int32 [n] of the diagonal of a materialised square distance matrix (stable-sort positions)."""
+    _need(dist, torch.float32, "distance", 2)
+    n = dist.shape[0]
+    if dist.shape[1] != n:
+        raise ValueError("the distance matrix of n aligned pairs is square")
+    cnt_row = torch.empty((n,), dtype=torch.int32, device=dist.device)
+    cnt_col = torch.empty((n,), dtype=torch.int32, device=dist.device)
+    call("snag_matrix_rank", ptr(dist), n, dist.stride(0), ptr(cnt_row), ptr(cnt_col), current_stream())
+    return cnt_row, cnt_col
 
 
 def csls_sim_matrix(sim: torch.Tensor, k: int, want_out: bool = True):

@@ -34,13 +34,17 @@ def _test(self, test_left, test_right, last_epoch=False, save_name="", loss=None
             final_emb, weight_norm = self.model.joint_emb_generat()
         else:
             final_emb = self.model.joint_emb_generat()
-        if self.args.distance != 2:
-            # main.py:387-390 computes the L1 distance with scipy on the host; it is not part of the accelerated path
-            raise NotImplementedError("--distance 1 (cityblock via scipy.cdist) is a host path of the reference")
-        # F.normalize (main.py:379), the gathers final_emb[test_left/right] (:386), pairwise_distances, csls_sim (:393)
-        # and both ranking loops (:400-429) in one call; the normalisation happens on the gathered rows only
-        out = evaluate.evaluate_alignment(final_emb.float().contiguous(), test_left, test_right,
-                                          csls=self.args.csls is True, csls_k=self.args.csls_k, want_top3=bool(last_epoch))
+        if self.args.distance == 1:
+            # main.py:387-390: cityblock distances (scipy on the host in the reference) — materialised on the device
+            out = evaluate.evaluate_alignment_l1(final_emb.float().contiguous(), test_left, test_right,
+                                                 csls=self.args.csls is True, csls_k=self.args.csls_k,
+                                                 want_top3=bool(last_epoch))
+        else:
+            # F.normalize (main.py:379), the gathers final_emb[test_left/right] (:386), pairwise_distances, csls_sim (:393)
+            # and both ranking loops (:400-429) in one call; the normalisation happens on the gathered rows only
+            out = evaluate.evaluate_alignment(final_emb.float().contiguous(), test_left, test_right,
+                                              csls=self.args.csls is True, csls_k=self.args.csls_k,
+                                              want_top3=bool(last_epoch))
     top_k = [1, 10, 50]
     l2r, r2l = out["l2r"], out["r2l"]
     acc_l2r, mean_l2r, mrr_l2r = l2r.acc, l2r.mr, l2r.mrr

@@ -356,3 +356,87 @@ def test_two_sweep_equals_three_sweep_bitwise(cuda_device):
     _, _, stream, srow, scnt = ops.eval_rowcoltopk(X, Y, xn, yn, n, n, colthr, colb, 1024)
     _, _, overflow = ops.col_cand_reduce(stream, srow, scnt, n, k)
     assert int(overflow.item()) == 1
+
+
+@pytest.mark.parametrize("n,d,k,csls", [(3000, 1200, 10, True), (1200, 300, 3, True), (900, 96, 5, False)])
+def test_lazy_single_sync_path_equals_synchronising_path(cuda_device, n, d, k, csls):
+    """The sync-free evaluation (tolerances from the assumed unit norm, counters checked once at the end) returns what
+    the synchronising path returns, bit for bit, and reports the same diagnostics."""
+    x, y = _clustered(n, d, 6.0, 21)
+    X, Y, xn, yn = _prep(x, y, cuda_device)
+    a = evaluate.align_ranks(X, Y, xn, yn, n, k, csls, want_top3=True, lazy=False)
+    b = evaluate.align_ranks(X, Y, xn, yn, n, k, csls, want_top3=True, lazy=True)
+    assert torch.equal(a.rank_l2r, b.rank_l2r) and torch.equal(a.rank_r2l, b.rank_r2l) and torch.equal(a.g, b.g)
+    assert torch.equal(a.top3_idx, b.top3_idx)
+    if csls:
+        assert torch.equal(a.nv1, b.nv1) and torch.equal(a.nv2, b.nv2)
+        assert b.info["neighbourhoods"]["rows"]["unverified"] == 0 and b.info["neighbourhoods"]["cols"]["unverified"] == 0
+    assert b.info["rank_sweep"]["mode"] == "band" and b.info["rank_sweep"]["deferred"] <= b.info["rank_sweep"]["cap"]
+    ref = oracle.align_eval(x, y, csls, k)
+    np.testing.assert_array_equal(b.rank_l2r.cpu().numpy(), ref["rank_l2r"])
+    np.testing.assert_array_equal(b.rank_r2l.cpu().numpy(), ref["rank_r2l"])
+    # rows that are not unit norm break the lazy path's assumption: it must notice and hand over
+    X2, xn2 = ops.prep_bf16(torch.from_numpy(2.0 * x).to(cuda_device), None, normalize=False)
+    c = evaluate.align_ranks(X2, Y, xn2, yn, n, k, csls)
+    ref2 = oracle.align_eval(2.0 * x, y, csls, k)
+    np.testing.assert_array_equal(c.rank_l2r.cpu().numpy(), ref2["rank_l2r"])
+
+
+def test_graphed_evaluation_replays(cuda_device):
+    """evaluate_alignment replays one CUDA graph per problem shape: same metrics and ranks as the eager evaluation, also
+    after the embeddings and the test pairs change in place between replays."""
+    rng = np.random.RandomState(4)
+    N, n, d = 5000, 2100, 300
+    outs = []
+    for trial in range(3):
+        emb = rng.randn(N, d).astype(np.float32)
+        left = rng.permutation(N // 2)[:n]
+        right = N // 2 + rng.permutation(N // 2)[:n]
+        emb[right] = emb[left] + 0.9 * rng.randn(n, d).astype(np.float32)
+        args = (torch.from_numpy(emb).to(cuda_device), torch.from_numpy(left).to(cuda_device), torch.from_numpy(right).to(cuda_device))
+        g = evaluate.evaluate_alignment(*args, csls=True, csls_k=10, want_top3=True, graph=True)
+        e = evaluate.evaluate_alignment(*args, csls=True, csls_k=10, want_top3=True, graph=False)
+        assert g["ranks"].info.get("cuda_graph") is True and not e["ranks"].info.get("cuda_graph")
+        assert torch.equal(g["ranks"].rank_l2r, e["ranks"].rank_l2r) and torch.equal(g["ranks"].rank_r2l, e["ranks"].rank_r2l)
+        assert torch.equal(g["ranks"].top3_idx, e["ranks"].top3_idx) and torch.equal(g["ranks"].nv1, e["ranks"].nv1)
+        assert g["l2r"].mrr == e["l2r"].mrr and np.array_equal(g["r2l"].acc, e["r2l"].acc)
+        outs.append(g["l2r"].mrr)
+    assert len(set(outs)) == 3                      # three different problems went through the same graph
+    assert len([k for k in evaluate._GRAPHS if k[1] == n]) == 1
+
+
+@pytest.mark.parametrize("name", golden_names("l1_"))
+def test_l1_distance_golden(cuda_device, name):
+    """--distance 1 (main.py:387-390) on the device: distances bit-identical to scipy's (as stored by the reference),
+    ranks and prediction ids equal to the reference's loops."""
+    fx = load_golden(name)
+    x, y = torch.from_numpy(fx["x"]).to(cuda_device), torch.from_numpy(fx["y"]).to(cuda_device)
+    np.testing.assert_array_equal(ops.l1_distance(x, y).cpu().numpy(), fx["distance"])
+    n = x.shape[0]
+    emb = torch.cat([x, y], 0)
+    left = torch.arange(0, n, device=cuda_device)
+    right = torch.arange(n, 2 * n, device=cuda_device)
+    out = evaluate.evaluate_alignment_l1(emb, left, right, csls=bool(fx["csls"]), csls_k=int(fx["k"]), want_top3=True)
+    np.testing.assert_array_equal(out["ranks"].rank_l2r.cpu().numpy(), fx["rank_l2r"])
+    np.testing.assert_array_equal(out["ranks"].rank_r2l.cpu().numpy(), fx["rank_r2l"])
+    np.testing.assert_array_equal(out["ranks"].top3_idx.cpu().numpy(), fx["top3"])
+
+
+def test_l1_distance_against_oracle_at_c1_width(cuda_device):
+    rng = np.random.RandomState(12)
+    n, d = 1500, 1200
+    x = oracle.normalize_rows(rng.randn(n, d).astype(np.float32))
+    y = oracle.normalize_rows((x + 0.05 * rng.randn(n, d)).astype(np.float32))
+    emb = torch.from_numpy(np.concatenate([x, y], 0)).to(cuda_device)
+    out = evaluate.evaluate_alignment_l1(emb, torch.arange(0, n, device=cuda_device), torch.arange(n, 2 * n, device=cuda_device),
+                                         csls=True, csls_k=10)
+    xr = torch.nn.functional.normalize(torch.from_numpy(x)).numpy()      # the path re-normalises, as main.py:379 does
+    yr = torch.nn.functional.normalize(torch.from_numpy(y)).numpy()
+    ref = oracle.align_eval_l1(xr, yr, True, 10)
+    agree = (out["ranks"].rank_l2r.cpu().numpy() == ref["rank_l2r"]).mean()
+    assert agree > 0.995                 # F.normalize on the device vs the host may differ in the last bit of a few rows
+    got = ops.l1_distance(torch.from_numpy(xr).to(cuda_device), torch.from_numpy(yr).to(cuda_device)).cpu().numpy()
+    np.testing.assert_array_equal(got, oracle.l1_distance(xr, yr))
+    r, c = ops.matrix_rank(torch.from_numpy(ref["dist"]).to(cuda_device))
+    np.testing.assert_array_equal(r.cpu().numpy(), ref["rank_l2r"])
+    np.testing.assert_array_equal(c.cpu().numpy(), ref["rank_r2l"])

@@ -274,3 +274,18 @@ def test_seed_induction_matches_reference(name):
     fx = load_golden(name)
     links = oracle.visual_pivot_induction(fx["left"].tolist(), fx["right"].tolist(), fx["feats"], int(fx["unsup_k"]))
     np.testing.assert_array_equal(links, fx["links"])
+
+
+@pytest.mark.parametrize("name", golden_names("l1_"))
+def test_l1_distance_path_matches_reference(name):
+    """--distance 1: the oracle's cityblock distances equal scipy's cdist result as the reference stores it (fp32), and
+    CSLS + ranks + top-3 on them equal what the reference's own csls_sim and ranking loops produced."""
+    fx = load_golden(name)
+    got = oracle.l1_distance(fx["x"], fx["y"])
+    np.testing.assert_array_equal(got, fx["distance"])
+    out = oracle.align_eval_l1(fx["x"], fx["y"], bool(fx["csls"]), int(fx["k"]))
+    # L1 distances of unit rows are O(10): a few fp32 ulps (1e-6 each) from torch.mean's summation order in csls_sim
+    np.testing.assert_allclose(out["dist"], fx["dist"], rtol=1e-6, atol=2e-6)
+    np.testing.assert_array_equal(out["rank_l2r"], fx["rank_l2r"])
+    np.testing.assert_array_equal(out["rank_r2l"], fx["rank_r2l"])
+    np.testing.assert_array_equal(out["top3"], fx["top3"])
