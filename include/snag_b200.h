@@ -102,6 +102,21 @@ int snag_normalize_bwd_scatter(const float* emb, int64_t ld, const int64_t* idx,
 /* dz may be given as n_parts partial sums, part_stride floats apart (the column splits of snag_icl_bwd_fused); they are
  * added in split order. n_parts = 1: a single gradient, part_stride ignored. */
 
+/* Batched prologue / epilogue of the loss layer — the 2 + 2M icl_loss calls of a step (model/SNAG.py:106,147-159) share
+ * the batch idx_l / idx_r [B]; all array arguments are HOST arrays with one entry per call (n_prob <= 16).
+ * snag_icl_stack_prep: out[p] ([3 Bp, Dpad[p]] bf16) = [ z[idx_l] ; z[idx_r] ; z[idx_l] ] with z = F.normalize(emb[p])
+ *   (model/SNAG_loss.py:59-64) rounded to bf16, every part zero padded to Bp rows and Dpad[p] columns.
+ * snag_normalize_bwd_scatter_many: snag_normalize_bwd_scatter for both sides of every call in one launch (dz_a[p] /
+ *   dz_b[p]: gradients w.r.t. the normalised rows of side a / b, n_parts[p] partial sums part_stride[p] floats apart). */
+int snag_icl_stack_prep(int32_t n_prob, const float* const* emb, const int64_t* ld, const int32_t* D, uint16_t* const* out,
+                        const int32_t* Dpad, const int64_t* idx_l, const int64_t* idx_r, int32_t B, int32_t Bp,
+                        int32_t normalize, void* stream);
+int snag_normalize_bwd_scatter_many(int32_t n_prob, const float* const* emb, const int64_t* ld, const int32_t* D,
+                                    const float* const* dz_a, const float* const* dz_b, const int64_t* ld_dz,
+                                    const int32_t* n_parts, const int64_t* part_stride, float* const* demb,
+                                    const int64_t* ld_demb, const int64_t* idx_l, const int64_t* idx_r, int32_t n,
+                                    int32_t normalize, void* stream);
+
 /* Fused backward of icl_loss (model/SNAG_loss.py:98-126) w.r.t. the normalised rows for contraction widths
  * Dpad <= 320 (the per-modality calls, D = 300): for each of n_prob <= 16 calls that share the batch size,
  *   dz_x[split][i][:] = sum over the split's columns j of G_ij y_j,   G = dL/dlogits (see snag_icl_bwd_logits),

@@ -82,6 +82,25 @@ int snag_normalize_bwd_scatter(const float* emb, int64_t ld, const int64_t* idx,
   return launch_normalize_bwd_scatter(emb, ld, reinterpret_cast<const long long*>(idx), n, D, normalize, dz, ld_dz, n_parts,
                                       part_stride, demb, ld_demb, S(stream));
 }
+int snag_icl_stack_prep(int32_t n_prob, const float* const* emb, const int64_t* ld, const int32_t* D, uint16_t* const* out,
+                        const int32_t* Dpad, const int64_t* idx_l, const int64_t* idx_r, int32_t B, int32_t Bp,
+                        int32_t normalize, void* stream) {
+  return launch_icl_stack_prep(n_prob, emb, reinterpret_cast<const long long*>(ld), D,
+                               reinterpret_cast<__nv_bfloat16* const*>(out), Dpad, reinterpret_cast<const long long*>(idx_l),
+                               reinterpret_cast<const long long*>(idx_r), B, Bp, normalize, S(stream));
+}
+int snag_normalize_bwd_scatter_many(int32_t n_prob, const float* const* emb, const int64_t* ld, const int32_t* D,
+                                    const float* const* dz_a, const float* const* dz_b, const int64_t* ld_dz,
+                                    const int32_t* n_parts, const int64_t* part_stride, float* const* demb,
+                                    const int64_t* ld_demb, const int64_t* idx_l, const int64_t* idx_r, int32_t n,
+                                    int32_t normalize, void* stream) {
+  return launch_normalize_bwd_scatter_many(n_prob, emb, reinterpret_cast<const long long*>(ld), D, dz_a, dz_b,
+                                           reinterpret_cast<const long long*>(ld_dz), n_parts,
+                                           reinterpret_cast<const long long*>(part_stride), demb,
+                                           reinterpret_cast<const long long*>(ld_demb),
+                                           reinterpret_cast<const long long*>(idx_l),
+                                           reinterpret_cast<const long long*>(idx_r), n, normalize, S(stream));
+}
 int snag_l1_distance(const float* x, const float* y, int64_t n1, int64_t n2, int32_t D, int64_t ldx, int64_t ldy, float* out,
                      int64_t ldo, void* stream) {
   return launch_l1_distance(x, y, n1, n2, D, ldx, ldy, out, ldo, S(stream));

@@ -274,6 +274,109 @@ __global__ void __launch_bounds__(256) prep_bf16_kernel(const float* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------------
+// Batched prologue / epilogue of the loss layer: the 2 + 2M icl_loss calls of a step share the batch of links, so the
+// stacked operands of ALL calls are built by one launch and the gradients of all calls go back through one launch
+// (at the reference's batch of 3500 the per-call launches of these two small kernels were 20 % of the step).
+//   stack_prep : S3_p = [ z_p[idx_l] ; z_p[idx_r] ; z_p[idx_l] ], z = F.normalize(emb_p) rounded to bf16, every part
+//                zero padded to Bp rows and Dpad_p columns (side a sweeps rows [Bp, 3Bp), side b rows [0, 2Bp))
+//   scatter_many : normalize_bwd_scatter for both sides of every problem
+// grid.y = problem (x side); one warp per row.
+// ------------------------------------------------------------------------------------------------
+constexpr int MANY_MAX = 16;
+struct StackPrepArgs {
+  const float* emb[MANY_MAX];
+  long long ld[MANY_MAX];
+  __nv_bfloat16* out[MANY_MAX];
+  int D[MANY_MAX];
+  int Dpad[MANY_MAX];
+};
+__global__ void __launch_bounds__(256) icl_stack_prep_kernel(const __grid_constant__ StackPrepArgs a,
+                                                             const long long* __restrict__ idx_l,
+                                                             const long long* __restrict__ idx_r, int B, int Bp,
+                                                             int normalize) {
+  const int p = blockIdx.y;
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;       // row of S3_p
+  const int lane = threadIdx.x & 31;
+  if (r >= 3 * Bp) return;
+  const int part = r / Bp, i = r - part * Bp;
+  const int D = a.D[p], Dpad = a.Dpad[p];
+  __nv_bfloat16* dst = a.out[p] + static_cast<long long>(r) * Dpad;
+  if (i >= B) {
+    for (int c = lane; c < Dpad; c += 32) dst[c] = __float2bfloat16_rn(0.f);
+    return;
+  }
+  const float* src = a.emb[p] + (part == 1 ? idx_r[i] : idx_l[i]) * a.ld[p];
+  float denom = 1.0f;
+  if (normalize) {
+    float ss = 0.f;
+    for (int c = lane; c < D; c += 32) { const float v = __ldg(src + c); ss = __fmaf_rn(v, v, ss); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    denom = fmaxf(sqrtf(ss), 1e-12f);
+  }
+  for (int c = lane; c < Dpad; c += 32) {
+    float v = 0.f;
+    if (c < D) v = normalize ? __fdiv_rn(__ldg(src + c), denom) : __ldg(src + c);
+    dst[c] = __float2bfloat16_rn(v);
+  }
+}
+
+struct ScatterManyArgs {
+  const float* emb[MANY_MAX];
+  long long ld[MANY_MAX];
+  int D[MANY_MAX];
+  const float* dz[2 * MANY_MAX];          // [2 p + side]
+  long long ld_dz[MANY_MAX];
+  int n_parts[MANY_MAX];
+  long long part_stride[MANY_MAX];
+  float* demb[MANY_MAX];
+  long long ld_demb[MANY_MAX];
+};
+__global__ void __launch_bounds__(256) normalize_bwd_scatter_many_kernel(const __grid_constant__ ScatterManyArgs a,
+                                                                         const long long* __restrict__ idx_l,
+                                                                         const long long* __restrict__ idx_r, int n,
+                                                                         int normalize) {
+  const int p = blockIdx.y >> 1, side = blockIdx.y & 1;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= n) return;
+  const long long row = side ? idx_r[warp] : idx_l[warp];
+  const int D = a.D[p], n_parts = a.n_parts[p];
+  const long long part_stride = a.part_stride[p];
+  const float* src = a.emb[p] + row * a.ld[p];
+  const float* g0 = a.dz[2 * p + side] + static_cast<long long>(warp) * a.ld_dz[p];
+  float* dst = a.demb[p] + row * a.ld_demb[p];
+  auto g_at = [&](int c) {
+    float v = __ldg(g0 + c);
+    for (int q = 1; q < n_parts; ++q) v += __ldg(g0 + q * part_stride + c);
+    return v;
+  };
+  if (!normalize) {
+    for (int c = lane; c < D; c += 32) atomicAdd(dst + c, g_at(c));
+    return;
+  }
+  float ss = 0.f, eg = 0.f;
+  for (int c = lane; c < D; c += 32) {
+    const float v = __ldg(src + c);
+    ss = __fmaf_rn(v, v, ss);
+    eg = __fmaf_rn(v, g_at(c), eg);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    eg += __shfl_xor_sync(0xffffffffu, eg, o);
+  }
+  const float nrm = sqrtf(ss);
+  if (nrm > 1e-12f) {
+    const float inv = 1.0f / nrm;
+    const float k = eg * inv * inv * inv;
+    for (int c = lane; c < D; c += 32) atomicAdd(dst + c, __fmaf_rn(-__ldg(src + c), k, g_at(c) * inv));
+  } else {
+    for (int c = lane; c < D; c += 32) atomicAdd(dst + c, g_at(c) * 1e12f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // f2  Joint (fusion-output) embeddings, model/SNAG_tools.py:44-49:
 //   joint   [i, off_m + c] = w_ent[i, m] * e_m[i, c] / max(||e_m[i]||, 1e-12)      (per-entity attention weights)
 //   joint_fz[i, off_m + c] = w_glob[m]   * e_m[i, c] / max(||e_m[i]||, 1e-12)      (softmax(weight_raw))
@@ -1250,6 +1353,43 @@ int launch_prep_bf16(const float* emb, long long ld, const long long* idx, int n
   if (Dpad < D || (Dpad % 64) != 0) return SNAG_ERR_SHAPE;
   const long long threads = static_cast<long long>(n) * 32;
   prep_bf16_kernel<<<static_cast<int>((threads + 255) / 256), 256, 0, st>>>(emb, ld, idx, n, D, normalize, out, Dpad, norm2);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int launch_icl_stack_prep(int n_prob, const float* const* emb, const long long* ld, const int* D, __nv_bfloat16* const* out,
+                          const int* Dpad, const long long* idx_l, const long long* idx_r, int B, int Bp, int normalize,
+                          cudaStream_t st) {
+  if (n_prob < 1 || n_prob > MANY_MAX || !emb || !ld || !D || !out || !Dpad || !idx_l || !idx_r) return SNAG_ERR_ARG;
+  if (B <= 0 || Bp < B || (Bp % 256) != 0) return SNAG_ERR_ARG;
+  StackPrepArgs a{};
+  for (int p = 0; p < n_prob; ++p) {
+    if (!emb[p] || !out[p] || D[p] <= 0 || ld[p] < D[p]) return SNAG_ERR_ARG;
+    if (Dpad[p] < D[p] || (Dpad[p] % 64) != 0) return SNAG_ERR_SHAPE;
+    a.emb[p] = emb[p]; a.ld[p] = ld[p]; a.out[p] = out[p]; a.D[p] = D[p]; a.Dpad[p] = Dpad[p];
+  }
+  const dim3 grid(static_cast<unsigned>((3ll * Bp * 32 + 255) / 256), static_cast<unsigned>(n_prob));
+  icl_stack_prep_kernel<<<grid, 256, 0, st>>>(a, idx_l, idx_r, B, Bp, normalize);
+  return static_cast<int>(cudaGetLastError());
+}
+int launch_normalize_bwd_scatter_many(int n_prob, const float* const* emb, const long long* ld, const int* D,
+                                      const float* const* dz_a, const float* const* dz_b, const long long* ld_dz,
+                                      const int* n_parts, const long long* part_stride, float* const* demb,
+                                      const long long* ld_demb, const long long* idx_l, const long long* idx_r, int n,
+                                      int normalize, cudaStream_t st) {
+  if (n_prob < 1 || n_prob > MANY_MAX || !emb || !ld || !D || !dz_a || !dz_b || !ld_dz || !n_parts || !part_stride ||
+      !demb || !ld_demb || !idx_l || !idx_r || n <= 0)
+    return SNAG_ERR_ARG;
+  ScatterManyArgs a{};
+  for (int p = 0; p < n_prob; ++p) {
+    if (!emb[p] || !dz_a[p] || !dz_b[p] || !demb[p] || D[p] <= 0 || ld[p] < D[p] || ld_dz[p] < D[p] || ld_demb[p] < D[p] ||
+        n_parts[p] < 1)
+      return SNAG_ERR_ARG;
+    a.emb[p] = emb[p]; a.ld[p] = ld[p]; a.D[p] = D[p]; a.dz[2 * p] = dz_a[p]; a.dz[2 * p + 1] = dz_b[p];
+    a.ld_dz[p] = ld_dz[p]; a.n_parts[p] = n_parts[p]; a.part_stride[p] = part_stride[p]; a.demb[p] = demb[p];
+    a.ld_demb[p] = ld_demb[p];
+  }
+  const dim3 grid(static_cast<unsigned>((static_cast<long long>(n) * 32 + 255) / 256), static_cast<unsigned>(2 * n_prob));
+  normalize_bwd_scatter_many_kernel<<<grid, 256, 0, st>>>(a, idx_l, idx_r, n, normalize);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -45,6 +45,14 @@ int launch_joint_fuse_bwd(const float* const* embs, float* const* d_embs, const 
 int launch_normalize_bwd_scatter(const float* emb, long long ld, const long long* idx, int n, int D, int normalize,
                                  const float* dz, long long ld_dz, int n_parts, long long part_stride, float* demb,
                                  long long ld_demb, cudaStream_t st);
+int launch_icl_stack_prep(int n_prob, const float* const* emb, const long long* ld, const int* D, __nv_bfloat16* const* out,
+                          const int* Dpad, const long long* idx_l, const long long* idx_r, int B, int Bp, int normalize,
+                          cudaStream_t st);
+int launch_normalize_bwd_scatter_many(int n_prob, const float* const* emb, const long long* ld, const int* D,
+                                      const float* const* dz_a, const float* const* dz_b, const long long* ld_dz,
+                                      const int* n_parts, const long long* part_stride, float* const* demb,
+                                      const long long* ld_demb, const long long* idx_l, const long long* idx_r, int n,
+                                      int normalize, cudaStream_t st);
 int launch_l1_distance(const float* x, const float* y, long long n1, long long n2, int D, long long ldx, long long ldy,
                        float* out, long long ldo, cudaStream_t st);
 int launch_matrix_rank(const float* d, long long n, long long ld, int* cnt_row, int* cnt_col, cudaStream_t st);

@@ -159,15 +159,20 @@ class _IclMany(torch.autograd.Function):
         Bp = ops.round_up(B, 256)
         r0, r1, per = shard.bounds(B)
         saved, outs, dims = [], [], []
-        for emb in embs:
-            emb = emb.contiguous()
+        embs = [emb.contiguous() for emb in embs]
+        # stacked operands [a ; b ; a], every part zero padded to Bp rows: side a sweeps [b ; a], side b sweeps [a ; b]
+        if hasattr(be, "icl_stack_prep"):
+            stacks = be.icl_stack_prep(embs, idx_l, idx_r, Bp, normalize)          # all tables in one launch
+        else:
+            stacks = []
+            for emb in embs:
+                S3 = torch.zeros((3 * Bp, ops.round_up(emb.shape[1], 64)), dtype=torch.bfloat16, device=emb.device)
+                be.prep_bf16(emb, idx_l, normalize=normalize, out=S3[0:Bp])
+                be.prep_bf16(emb, idx_r, normalize=normalize, out=S3[Bp:2 * Bp])
+                S3[2 * Bp:2 * Bp + B].copy_(S3[0:B])
+                stacks.append(S3)
+        for emb, S3 in zip(embs, stacks):
             D = emb.shape[1]
-            dpad = ops.round_up(D, 64)
-            # stacked operand [a ; b ; a], every part zero padded to Bp rows: side a sweeps [b ; a], side b sweeps [a ; b]
-            S3 = torch.zeros((3 * Bp, dpad), dtype=torch.bfloat16, device=emb.device)
-            be.prep_bf16(emb, idx_l, normalize=normalize, out=S3[0:Bp])
-            be.prep_bf16(emb, idx_r, normalize=normalize, out=S3[Bp:2 * Bp])
-            S3[2 * Bp:2 * Bp + B].copy_(S3[0:B])
             if shard.world == 1:
                 lse_a, nll_a, _ = be.icl_side(S3[0:Bp], S3[Bp:3 * Bp], B, Bp, inv_tau)
                 lse_b, nll_b, _ = be.icl_side(S3[Bp:2 * Bp], S3[0:2 * Bp], B, Bp, inv_tau)
@@ -234,11 +239,22 @@ class _IclMany(torch.autograd.Function):
                 Gb = be.icl_bwd_logits(S3[Bp + a0:Bp + a0 + nx], Yb, B, Bp, inv_tau, q["crb"], q["cra"], q["dg"], a0, nx)
                 # row i of G carries every term of dL/d(anchor i) — its own softmax row and its appearances as a column
                 # in the other rows' softmaxes (the cc / cr_j terms of EpiIclBwd) — so the owned rows of dA, dB are complete
-                dz[p] = (be.grad_contract(Ga, Ya.t().contiguous(), nx, D), be.grad_contract(Gb, Yb.t().contiguous(), nx, D))
+                kp = {"keep_parts": True} if (shard.world == 1 and hasattr(be, "normalize_bwd_scatter_many")) else {}
+                dz[p] = (be.grad_contract(Ga, Ya.t().contiguous(), nx, D, **kp), be.grad_contract(Gb, Yb.t().contiguous(), nx, D, **kp))
         out = []
+        batched = shard.world == 1 and hasattr(be, "normalize_bwd_scatter_many")
+        if batched:                                       # both sides of every table: one launch
+            live = [p for p in range(n) if probs[p] is not None]
+            dembs = {p: torch.zeros_like(probs[p]["emb"]) for p in live}
+            if live:
+                be.normalize_bwd_scatter_many([probs[p]["emb"] for p in live], idx_l, idx_r, [dz[p] for p in live],
+                                              [dembs[p] for p in live], nrm)
         for p in range(n):
             if probs[p] is None:
                 out.append(None)
+                continue
+            if batched:
+                out.append(dembs[p])
                 continue
             emb, D = probs[p]["emb"], probs[p]["D"]
             demb = torch.zeros_like(emb)
@@ -323,7 +339,9 @@ class icl_loss(nn.Module):
         for p, weight_norm in enumerate(weight_norms):
             nll_a, nll_b = nll[2 * p], nll[2 * p + 1]
             if weight_norm is not None:
-                w = torch.min(torch.stack([weight_norm[idx_l], weight_norm[idx_r]], dim=1), 1)[0]   # :66-69
+                # :66-69 (index_select: same values and the same argmin routing of the gradient as weight_norm[idx],
+                # with an index_add backward instead of index_put's sort)
+                w = torch.min(torch.stack([weight_norm.index_select(0, idx_l), weight_norm.index_select(0, idx_r)], dim=1), 1)[0]
                 loss_a = (nll_a * w).sum() / batch                                                   # softXEnt :51
                 loss_b = (nll_b * w).sum() / batch
             else:

@@ -621,6 +621,64 @@ def icl_bwd_logits(X: torch.Tensor, Y: torch.Tensor, B: int, Bp: int, inv_tau: f
     return G
 
 
+MANY_MAX = 16                 # problems per batched launch (kernel-parameter space)
+
+
+def _carr(ctype, values):
+    return (ctype * len(values))(*values)
+
+
+def icl_stack_prep(embs, idx_l: torch.Tensor, idx_r: torch.Tensor, Bp: int, normalize: bool = True):
+    """Stacked bf16 operands of several icl_loss calls that share one batch, ONE launch per 16 tables: for each fp32
+    table emb [N, D] returns S3 = [z[idx_l] ; z[idx_r] ; z[idx_l]] as [3 Bp, Dpad] bf16 (z = F.normalize(emb) when
+    `normalize`), every part zero padded to Bp rows and Dpad = ceil(D / 64) * 64 columns."""
+    import ctypes as C
+    _need(idx_l, torch.int64, "idx_l", 1)
+    _need(idx_r, torch.int64, "idx_r", 1)
+    B = idx_l.numel()
+    if idx_r.numel() != B or B < 1 or Bp < B or Bp % 256:
+        raise ValueError("idx_l / idx_r must pair up and Bp must be a multiple of 256 >= B")
+    outs = []
+    for e in embs:
+        _need(e, torch.float32, "emb", 2)
+        outs.append(torch.empty((3 * Bp, round_up(e.shape[1], 64)), dtype=torch.bfloat16, device=e.device))
+    for i in range(0, len(embs), MANY_MAX):
+        es, os_ = embs[i:i + MANY_MAX], outs[i:i + MANY_MAX]
+        call("snag_icl_stack_prep", len(es), _carr(C.c_void_p, [e.data_ptr() for e in es]),
+             _carr(C.c_int64, [e.stride(0) for e in es]), _carr(C.c_int32, [e.shape[1] for e in es]),
+             _carr(C.c_void_p, [t.data_ptr() for t in os_]), _carr(C.c_int32, [t.shape[1] for t in os_]),
+             ptr(idx_l), ptr(idx_r), B, Bp, int(normalize), current_stream())
+    return outs
+
+
+def normalize_bwd_scatter_many(embs, idx_l: torch.Tensor, idx_r: torch.Tensor, dz_pairs, dembs, normalize: bool = True):
+    """normalize_bwd_scatter for both sides of several tables in ONE launch per 16 tables: dembs[p][idx_l[r]] +=
+    backward of F.normalize(embs[p][idx_l[r]]) applied to dz_pairs[p][0][r] (and idx_r / dz_pairs[p][1] likewise);
+    every dz is [>= n, >= D] or [n_parts, >= n, >= D] with n = idx_l.numel()."""
+    import ctypes as C
+    n = idx_l.numel()
+    for i in range(0, len(embs), MANY_MAX):
+        sl = slice(i, i + MANY_MAX)
+        es, ds, gs = embs[sl], dembs[sl], dz_pairs[sl]
+        ld_dz, n_parts, pstride = [], [], []
+        for e, d, (ga, gb) in zip(es, ds, gs):
+            _need(e, torch.float32, "emb", 2)
+            _need(d, torch.float32, "demb", 2)
+            if ga.shape != gb.shape or ga.stride() != gb.stride() or ga.dtype != torch.float32 or ga.stride(-1) != 1:
+                raise ValueError("the two sides' gradients must share shape and layout (fp32, contiguous rows)")
+            if ga.shape[-2] < n or ga.shape[-1] < e.shape[1] or d.shape != e.shape:
+                raise ValueError("normalize_bwd_scatter_many: shape mismatch")
+            ld_dz.append(ga.stride(-2))
+            n_parts.append(1 if ga.dim() == 2 else ga.shape[0])
+            pstride.append(0 if ga.dim() == 2 else ga.stride(0))
+        call("snag_normalize_bwd_scatter_many", len(es), _carr(C.c_void_p, [e.data_ptr() for e in es]),
+             _carr(C.c_int64, [e.stride(0) for e in es]), _carr(C.c_int32, [e.shape[1] for e in es]),
+             _carr(C.c_void_p, [g[0].data_ptr() for g in gs]), _carr(C.c_void_p, [g[1].data_ptr() for g in gs]),
+             _carr(C.c_int64, ld_dz), _carr(C.c_int32, n_parts), _carr(C.c_int64, pstride),
+             _carr(C.c_void_p, [d.data_ptr() for d in ds]), _carr(C.c_int64, [d.stride(0) for d in ds]),
+             ptr(idx_l), ptr(idx_r), n, int(normalize), current_stream())
+
+
 FUSED_BWD_MAX_DPAD = 320      # dZ accumulator (Dpad fp32 columns) + logits stages + P buffers must fit the 512 TMEM columns
 FUSED_BWD_MAX_PROBLEMS = 16
 
@@ -668,10 +726,11 @@ def contract(P: torch.Tensor, Q: torch.Tensor, n1: int, n2: int) -> torch.Tensor
     return sim_write(P, Q, None, None, n1, n2, 0)
 
 
-def grad_contract(G: torch.Tensor, YT: torch.Tensor, n_rows: int, d: int) -> torch.Tensor:
+def grad_contract(G: torch.Tensor, YT: torch.Tensor, n_rows: int, d: int, keep_parts: bool = False) -> torch.Tensor:
     """fp32 [n_rows, d] = G[:n_rows] . YT[:d]^T for bf16 G [>= n_rows, K] and YT [>= d, K] (K a multiple of 64): the
     loss's gradient GEMMs dX = dL/dlogits . [other ; this]. Runs with the d rows of YT as the X operand, the output
-    written transposed and the long contraction split over the SMs (see snag_sim_write_t)."""
+    written transposed and the long contraction split over the SMs (see snag_sim_write_t). keep_parts: return the
+    split-K partial products [ks, n_rows, d] instead of their sum (normalize_bwd_scatter adds them while it reads)."""
     _check_operand(G, "G")
     _check_operand(YT, "YT")
     if G.shape[1] != YT.shape[1]:
@@ -681,6 +740,8 @@ def grad_contract(G: torch.Tensor, YT: torch.Tensor, n_rows: int, d: int) -> tor
     part = torch.empty((ks, n_rows, d), dtype=torch.float32, device=G.device)
     with _SweepTimer("sim_kernel<EpiWrite>", d, n_rows, k):
         call("snag_sim_write_t", ptr(YT), ptr(G), d, n_rows, k, ks, ptr(part), d, n_rows * d, current_stream())
+    if keep_parts:                       # [ks, n_rows, d]: the consumer adds the split-K partial sums itself
+        return part
     return part[0] if ks == 1 else part.sum(0)
 
 

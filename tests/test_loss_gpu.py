@@ -364,3 +364,45 @@ def test_loss_layer_fused_equals_unfused(cuda_device, B, D, M, monkeypatch):
     single = crit(streams[0], links, weight_norm=(wn * 6)[:, 3])
     many = crit.forward_many([streams[0], hidden[1]], links, [(wn * 6)[:, 3], None])
     assert abs(single.item() - many[0].item()) <= 1e-6 * abs(single.item())
+
+
+def test_batched_prologue_and_scatter_equal_single_calls(cuda_device):
+    """snag_icl_stack_prep / snag_normalize_bwd_scatter_many (all tables of a step in one launch) against the per-table
+    kernels they replace: stacked operands bit-identical, scattered gradients equal up to the order of the atomics."""
+    g = torch.Generator(device="cuda").manual_seed(3)
+    N, B = 5000, 1100
+    Bp = ops.round_up(B, 256)
+    widths = [300, 64, 1200, 300, 97]
+    embs = [torch.randn((N, w), generator=g, device=cuda_device) for w in widths]
+    idx_l = torch.randperm(N, generator=g, device=cuda_device)[:B]
+    idx_r = torch.randperm(N, generator=g, device=cuda_device)[:B]
+    idx_r[5] = idx_l[7]                                           # an entity linked on both sides: gradients accumulate
+    stacks = ops.icl_stack_prep(embs, idx_l, idx_r, Bp, True)
+    for e, S3 in zip(embs, stacks):
+        ref = torch.zeros_like(S3)
+        ops.prep_bf16(e, idx_l, True, out=ref[0:Bp])
+        ops.prep_bf16(e, idx_r, True, out=ref[Bp:2 * Bp])
+        ref[2 * Bp:2 * Bp + B].copy_(ref[0:B])
+        assert torch.equal(S3, ref)
+    pairs, want = [], []
+    for i, e in enumerate(embs):
+        d = e.shape[1]
+        dpad = ops.round_up(d, 64)
+        shape = (Bp, dpad) if i % 2 else (3, Bp, dpad)             # plain gradients and split partial sums
+        ga = torch.randn(shape, generator=g, device=cuda_device)
+        gb = torch.randn(shape, generator=g, device=cuda_device)
+        pairs.append((ga, gb))
+        ref = torch.zeros_like(e)
+        ops.normalize_bwd_scatter(e, idx_l, ga, ref, True)
+        ops.normalize_bwd_scatter(e, idx_r, gb, ref, True)
+        want.append(ref)
+    dembs = [torch.zeros_like(e) for e in embs]
+    ops.normalize_bwd_scatter_many(embs, idx_l, idx_r, pairs, dembs, True)
+    for a, b in zip(dembs, want):
+        assert _relerr(a, b) < 1e-6
+    # against autograd through F.normalize on one table
+    e = embs[0].clone().requires_grad_(True)
+    z = F.normalize(e, dim=1)
+    (z[idx_l] * pairs[0][0].sum(0)[:B, :300]).sum().backward(retain_graph=True)
+    (z[idx_r] * pairs[0][1].sum(0)[:B, :300]).sum().backward()
+    assert _relerr(dembs[0], e.grad) < 1e-5
