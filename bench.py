@@ -336,9 +336,9 @@ def eval_bench(ctx, args, name):
     kstats = {nm: {"launches": len(v["ms"]), "avg_ms": sum(v["ms"]) / len(v["ms"]),
                    "tflops": v["flops"] / (sum(v["ms"]) / len(v["ms"])) / 1e9} for nm, v in kern.items()}
     dom = max(kstats, key=lambda nm: kstats[nm]["avg_ms"] * kstats[nm]["launches"])
-    # full sweeps over S executed per step: 3 on the classic path; 2 + m/n with the two-sweep CSLS path
-    plan2 = evaluate.two_sweep_plan(n, k)
-    sweeps = 3.0 if plan2 is None else 2.0 + plan2[0] / n
+    # full sweeps over this rank's panel of S executed per step (from the launches themselves): 3 on the classic path,
+    # 2 + 2m/n with the two-sweep CSLS path, 1 + 2m/n with the one-pass evaluation
+    sweeps = sum(rows * cols for _nm, _a, _b, rows, cols, _dp in sweep_events) / K / (n * (n / world))
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
@@ -352,7 +352,7 @@ def eval_bench(ctx, args, name):
                 "sweeps_per_step": sweeps, "executed_tflops_whole_step": sweeps * 2.0 * n * n * d / world / ms_per_step / 1e9}
     out = {"ms_per_step": ms_per_step, "kernels": kstats, "roofline": roofline, "clocks": clocks.summary(),
            "launches_per_step": launches_per_step, "n": n, "d": d, "k": k, "sigma": sigma, "desc": desc, "dpad": dpad,
-           "rank_sweep": res.info.get("rank_sweep", {}), "steps": K, "warmup": W}
+           "rank_sweep": res.info.get("rank_sweep", {}), "one_pass": res.info.get("one_pass"), "steps": K, "warmup": W}
     if args.profile_run:
         return out
     if world == 1 and n < evaluate.TWO_SWEEP_MIN_N:
@@ -424,7 +424,7 @@ def eval_line(ctx, args, name, ev):
                          f"({2 * 2 * n * d * 4 / 1e6:.0f} MB), which exceeds and evicts L2"},
         "clocks": ev["clocks"], "e2e": ev.get("e2e"), "gpu_launches": ev["launches_per_step"] * ev["steps"],
         "roofline": ev["roofline"], "quality": ev.get("quality"),
-        "algorithmic_tflops": 2.0 * n * n * d / (ms * 1e-3) / 1e12, "rank_sweep": ev["rank_sweep"],
+        "algorithmic_tflops": 2.0 * n * n * d / (ms * 1e-3) / 1e12, "rank_sweep": ev["rank_sweep"], "one_pass": ev.get("one_pass"),
         "parity_audit": ev.get("parity_audit"), "graph_replay": ev.get("graph_replay"),
     }
 

@@ -179,11 +179,41 @@ int snag_eval_rowtopk(const uint16_t* X, const uint16_t* Y, const float* xn, con
  * snag_eval_rowtopk sweep. hist / cursor / overflow are zeroed by the caller. part_idx / stream_row carry the column
  * of every row candidate and the row of every stream entry (int32, same shapes as part / stream).
  * rowthr (may be NULL): per row a lower bound of its final SNAG_KT-th largest c (e.g. the SNAG_KT-th largest over a
- * sample of the columns, minus 2e-6); every partial list starts from it, slots it leaves unfilled read (rowthr, -1). */
+ * sample of the columns, minus 2e-6); every partial list starts from it, slots it leaves unfilled read (rowthr, -1).
+ * norm2_max: the largest squared row norm among xn / yn. Up to 1.05 (L2-normalised rows rounded to bf16) the per-element
+ * pre-filter runs in fp16x2 with margins derived for such rows; above, the fp32 form is used (snag_eval_onepass: refused). */
 int snag_eval_rowcoltopk(const uint16_t* X, const uint16_t* Y, const float* xn, const float* yn, int32_t n1, int32_t n2,
                          int32_t Dpad, float* part, int32_t* part_idx, const float* rowthr, const float* colthr,
                          const float* colb, uint64_t* stream, int32_t* stream_row, int32_t* stream_cnt, int32_t cta_cap,
-                         void* stream_);
+                         float norm2_max, void* stream_);
+/* One-pass evaluation: snag_eval_rowcoltopk that ALSO streams out every element which may count towards a rank of
+ * Runner._test (main.py:400-429), so that the second sweep over the similarity matrix (snag_eval_rank_band) is not needed.
+ * rk_r / rk_rp [n1] and rk_c / rk_cp [n2] are relaxed (provably or speculatively lower) versions of the constants
+ * R, R', C, C' of snag_eval_rank_band; every element with s > rk_r[i] + rk_c[j] or s > rk_rp[i] + rk_cp[j] is appended as
+ * (column, s bits) + row to the CTA's rank stream (rk_stream[cta][rk_cap], rk_stream_row, rk_cnt[cta]; sized for
+ * snag_num_sms() CTAs, rk_cnt zeroed by the caller). After the neighbourhood means are final, snag_rank_judge settles the
+ * streamed elements against the final constants (entities whose relaxed constant was not below the final one are
+ * skipped: row_ok / col_ok = 0 — recount them with snag_rank_exhaustive), elements inside the +-eps band go to the
+ * `band` list for snag_band_rescore. *overflow is set when a rank stream was full (fall back to snag_eval_rank_band).
+ * snag_spec_bounds: lo / hi [n] = lower bound / extrapolated upper guess of every entity's neighbourhood mean from the
+ * merged sample lists cand [n][SNAG_KT] and the canonical c of its own pair (shift: extrapolation distance in units of
+ * the list's tail scale, e.g. 1.5 ln(n / sample size); delta: tensor-core tolerance in c).
+ * snag_rank_exhaustive: canonical recount of the listed rows of A against all n_b rows of B (cnt[row] += ...; the caller
+ * zeroes those entries); swapped != 0 when A holds targets and B sources (the CSLS chain is not symmetric in fp32). */
+int snag_eval_onepass(const uint16_t* X, const uint16_t* Y, const float* xn, const float* yn, int32_t n1, int32_t n2,
+                      int32_t Dpad, float* part, int32_t* part_idx, const float* rowthr, const float* colthr, const float* colb,
+                      uint64_t* stream, int32_t* stream_row, int32_t* stream_cnt, int32_t cta_cap, const float* rk_r,
+                      const float* rk_rp, const float* rk_c, const float* rk_cp, uint64_t* rk_stream, int32_t* rk_stream_row,
+                      int32_t* rk_cnt, int32_t rk_cap, float norm2_max, void* stream_);
+int snag_spec_bounds(const float* cand, int64_t n, int32_t k, const float* cdiag, float shift, float delta, float* lo,
+                     float* hi, void* stream);
+int snag_rank_judge(const uint64_t* rk_stream, const int32_t* rk_stream_row, const int32_t* rk_cnt, int32_t n_ctas,
+                    int32_t rk_cap, const float* R, const float* Rp, const float* C, const float* Cp, const uint8_t* row_ok,
+                    const uint8_t* col_ok, float eps, int32_t row_gid0, int32_t col_gid0, int32_t* cnt_row, int32_t* cnt_col,
+                    uint64_t* band, uint32_t* band_cnt, uint32_t band_cap, int32_t* overflow, void* stream);
+int snag_rank_exhaustive(const uint16_t* A, const uint16_t* B, int32_t Dpad, int64_t n_b, const float* an, const float* bn,
+                         const float* nva, const float* nvb, const float* g, const int32_t* rows, int32_t n_rows,
+                         int32_t a_gid0, int32_t b_gid0, int32_t use_csls, int32_t swapped, int32_t* cnt, void* stream);
 int snag_col_threshold(const float* cand, int64_t n, int32_t k, const float* yn, float* colthr, float* colb, void* stream);
 int snag_col_cand_hist(const uint64_t* stream, const int32_t* stream_cnt, int32_t n_ctas, int32_t cta_cap, int32_t* hist,
                        int32_t* overflow, void* stream_);
@@ -245,6 +275,21 @@ int snag_band_rescore(const uint16_t* X, const uint16_t* Y, int32_t Dpad, const 
                       const float* nv2, const float* g_row, const float* g_col, int32_t row_gid0, int32_t col_gid0,
                       int32_t use_csls, const uint64_t* band, const uint32_t* band_cnt, uint32_t band_cap, int32_t* cnt_row,
                       int32_t* cnt_col, void* stream);
+/* Recount of SELECTED entities (one-pass evaluation: entities whose guessed bound failed): the same sweep and re-score
+ * as snag_eval_rank_band / snag_band_rescore over a GATHERED subset of rows — X [n1][Dpad] holds the selected rows,
+ * xn / nv1 / g_row their per-row values, row_gids [n1] their global pair ids (for the ground-truth exclusion and the
+ * tie-break); only cnt_row [n1] is meaningful for the caller (cnt_col [n2] is scratch). To recount selected TARGETS call
+ * it with the operands exchanged (X = gathered targets with yn / nv2 / g, Y = all sources with xn / nv1) and pass
+ * swapped = 1 to the re-score, which then evaluates the fp32 CSLS chain in the reference's operand order. */
+int snag_eval_rank_band_rows(const uint16_t* X, const uint16_t* Y, const float* xn, const float* yn, const float* nv1,
+                             const float* nv2, const float* g_row, const float* g_col, const int32_t* row_gids,
+                             int32_t col_gid0, int32_t n1, int32_t n2, int32_t Dpad, int32_t use_csls, float eps,
+                             int32_t* cnt_row, int32_t* cnt_col, uint64_t* band, uint32_t* band_cnt, uint32_t band_cap,
+                             void* stream);
+int snag_band_rescore_rows(const uint16_t* X, const uint16_t* Y, int32_t Dpad, const float* xn, const float* yn,
+                           const float* nv1, const float* nv2, const float* g_row, const float* g_col, const int32_t* row_gids,
+                           int32_t col_gid0, int32_t use_csls, int32_t swapped, const uint64_t* band, const uint32_t* band_cnt,
+                           uint32_t band_cap, int32_t* cnt_row, int32_t* cnt_col, void* stream);
 /* s_out[p] = X[rows[p]] . Y[cols[p]] with the canonical accumulation (fp64, index order, rounded once): the re-score of
  * explicitly listed similarity entries (unsupervised seed induction, src/data.py:367-375 + src/utils.py:437-443). */
 int snag_pairs_dot(const uint16_t* X, const uint16_t* Y, int32_t Dpad, const int32_t* rows, const int32_t* cols,

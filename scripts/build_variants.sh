@@ -6,7 +6,7 @@ mkdir -p snag_b200/_variants
 build() {  # name, extra flags
   name=$1; shift
   objs=""
-  for f in abi bw_kernels sim_kernels; do
+  for f in abi bw_kernels sim_kernels icl_fused; do
     nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC --expt-relaxed-constexpr "$@" \
       -c snag_b200/csrc/$f.cu -o snag_b200/_variants/${name}_$f.o &
     objs="$objs snag_b200/_variants/${name}_$f.o"

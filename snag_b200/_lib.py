@@ -45,7 +45,13 @@ _SIGNATURES = {
     "snag_debug_counters": [_vp],
     "snag_sim_readout_only": [_vp, _vp, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _vp],
     "snag_eval_rowtopk": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp],
-    "snag_eval_rowcoltopk": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp],
+    "snag_eval_rowcoltopk": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _f32, _vp],
+    "snag_eval_onepass": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32,
+                          _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _f32, _vp],
+    "snag_spec_bounds": [_vp, _i64, _i32, _vp, _f32, _f32, _vp, _vp, _vp],
+    "snag_rank_judge": [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _i32, _i32, _vp, _vp, _vp, _vp, _u32,
+                        _vp, _vp],
+    "snag_rank_exhaustive": [_vp, _vp, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp],
     "snag_col_threshold": [_vp, _i64, _i32, _vp, _vp, _vp, _vp],
     "snag_col_cand_hist": [_vp, _vp, _i32, _i32, _vp, _vp, _vp],
     "snag_col_cand_scatter": [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp],
@@ -59,6 +65,10 @@ _SIGNATURES = {
     "snag_eval_rank_band": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _vp, _vp, _vp, _vp,
                             _vp, _vp, _u32, _vp],
     "snag_band_rescore": [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _u32, _vp, _vp, _vp],
+    "snag_eval_rank_band_rows": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _vp, _vp,
+                                 _vp, _vp, _u32, _vp],
+    "snag_band_rescore_rows": [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _u32, _vp, _vp,
+                               _vp],
     "snag_pairs_dot": [_vp, _vp, _i32, _vp, _vp, _i64, _vp, _vp],
     "snag_top4_merge": [_vp, _vp, _i32, _i64, _vp, _vp, _vp],
     "snag_top3_rescore": [_vp, _vp, _i32, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp],

@@ -186,6 +186,25 @@ int snag_band_rescore(const uint16_t* X, const uint16_t* Y, int32_t Dpad, const 
   return launch_band_rescore(BF(X), BF(Y), Dpad, xn, yn, nv1, nv2, g_row, g_col, row_gid0, col_gid0, use_csls,
                              reinterpret_cast<const uint2*>(band), band_cnt, band_cap, cnt_row, cnt_col, S(stream));
 }
+int snag_eval_rank_band_rows(const uint16_t* X, const uint16_t* Y, const float* xn, const float* yn, const float* nv1,
+                             const float* nv2, const float* g_row, const float* g_col, const int32_t* row_gids,
+                             int32_t col_gid0, int32_t n1, int32_t n2, int32_t Dpad, int32_t use_csls, float eps,
+                             int32_t* cnt_row, int32_t* cnt_col, uint64_t* band, uint32_t* band_cnt, uint32_t band_cap,
+                             void* stream) {
+  if (!row_gids) return SNAG_ERR_ARG;
+  return launch_eval_rank_band(BF(X), BF(Y), xn, yn, nv1, nv2, g_row, g_col, 0, col_gid0, n1, n2, Dpad, use_csls, eps,
+                               cnt_row, cnt_col, nullptr, nullptr, reinterpret_cast<uint2*>(band), band_cnt, band_cap,
+                               S(stream), row_gids);
+}
+int snag_band_rescore_rows(const uint16_t* X, const uint16_t* Y, int32_t Dpad, const float* xn, const float* yn,
+                           const float* nv1, const float* nv2, const float* g_row, const float* g_col, const int32_t* row_gids,
+                           int32_t col_gid0, int32_t use_csls, int32_t swapped, const uint64_t* band, const uint32_t* band_cnt,
+                           uint32_t band_cap, int32_t* cnt_row, int32_t* cnt_col, void* stream) {
+  if (!row_gids) return SNAG_ERR_ARG;
+  return launch_band_rescore(BF(X), BF(Y), Dpad, xn, yn, nv1, nv2, g_row, g_col, 0, col_gid0, use_csls,
+                             reinterpret_cast<const uint2*>(band), band_cnt, band_cap, cnt_row, cnt_col, S(stream), row_gids,
+                             swapped);
+}
 int snag_pairs_dot(const uint16_t* X, const uint16_t* Y, int32_t Dpad, const int32_t* rows, const int32_t* cols,
                    int64_t n_pairs, float* s_out, void* stream) {
   return launch_pairs_dot(BF(X), BF(Y), Dpad, rows, cols, n_pairs, s_out, S(stream));
@@ -223,9 +242,36 @@ int snag_icl_finalize(const float* rowsum_part, int32_t n_lists, int32_t B, int3
 int snag_eval_rowcoltopk(const uint16_t* X, const uint16_t* Y, const float* xn, const float* yn, int32_t n1, int32_t n2,
                          int32_t Dpad, float* part, int32_t* part_idx, const float* rowthr, const float* colthr,
                          const float* colb, uint64_t* stream, int32_t* stream_row, int32_t* stream_cnt, int32_t cta_cap,
-                         void* stream_) {
+                         float norm2_max, void* stream_) {
   return launch_eval_rowcoltopk(BF(X), BF(Y), xn, yn, n1, n2, Dpad, part, part_idx, rowthr, colthr, colb,
-                                reinterpret_cast<uint2*>(stream), stream_row, stream_cnt, cta_cap, S(stream_));
+                                reinterpret_cast<uint2*>(stream), stream_row, stream_cnt, cta_cap, norm2_max, S(stream_));
+}
+int snag_eval_onepass(const uint16_t* X, const uint16_t* Y, const float* xn, const float* yn, int32_t n1, int32_t n2,
+                      int32_t Dpad, float* part, int32_t* part_idx, const float* rowthr, const float* colthr, const float* colb,
+                      uint64_t* stream, int32_t* stream_row, int32_t* stream_cnt, int32_t cta_cap, const float* rk_r,
+                      const float* rk_rp, const float* rk_c, const float* rk_cp, uint64_t* rk_stream, int32_t* rk_stream_row,
+                      int32_t* rk_cnt, int32_t rk_cap, float norm2_max, void* stream_) {
+  return launch_eval_onepass(BF(X), BF(Y), xn, yn, n1, n2, Dpad, part, part_idx, rowthr, colthr, colb,
+                             reinterpret_cast<uint2*>(stream), stream_row, stream_cnt, cta_cap, rk_r, rk_rp, rk_c, rk_cp,
+                             reinterpret_cast<uint2*>(rk_stream), rk_stream_row, rk_cnt, rk_cap, norm2_max, S(stream_));
+}
+int snag_spec_bounds(const float* cand, int64_t n, int32_t k, const float* cdiag, float shift, float delta, float* lo,
+                     float* hi, void* stream) {
+  return launch_spec_bounds(cand, n, k, cdiag, shift, delta, lo, hi, S(stream));
+}
+int snag_rank_judge(const uint64_t* rk_stream, const int32_t* rk_stream_row, const int32_t* rk_cnt, int32_t n_ctas,
+                    int32_t rk_cap, const float* R, const float* Rp, const float* C, const float* Cp, const uint8_t* row_ok,
+                    const uint8_t* col_ok, float eps, int32_t row_gid0, int32_t col_gid0, int32_t* cnt_row, int32_t* cnt_col,
+                    uint64_t* band, uint32_t* band_cnt, uint32_t band_cap, int32_t* overflow, void* stream) {
+  return launch_rank_judge(reinterpret_cast<const uint2*>(rk_stream), rk_stream_row, rk_cnt, n_ctas, rk_cap, R, Rp, C, Cp,
+                           row_ok, col_ok, eps, row_gid0, col_gid0, cnt_row, cnt_col, reinterpret_cast<uint2*>(band), band_cnt,
+                           band_cap, overflow, S(stream));
+}
+int snag_rank_exhaustive(const uint16_t* A, const uint16_t* B, int32_t Dpad, int64_t n_b, const float* an, const float* bn,
+                         const float* nva, const float* nvb, const float* g, const int32_t* rows, int32_t n_rows,
+                         int32_t a_gid0, int32_t b_gid0, int32_t use_csls, int32_t swapped, int32_t* cnt, void* stream) {
+  return launch_rank_exhaustive(BF(A), BF(B), Dpad, n_b, an, bn, nva, nvb, g, rows, n_rows, a_gid0, b_gid0, use_csls, swapped,
+                                cnt, S(stream));
 }
 int snag_col_threshold(const float* cand, int64_t n, int32_t k, const float* yn, float* colthr, float* colb, void* stream) {
   return launch_col_threshold(cand, n, k, yn, colthr, colb, S(stream));

@@ -1,6 +1,7 @@
 // HBM-bound kernels of the SNAG hot path: normalise+gather+cast prologue, Gauss modality noise mask,
 // column mean/std, entity-row blend (fwd/bwd), CSLS candidate merge, ground-truth ("diagonal") scores,
 // and the materialised CSLS drop-in. All vectorised, coalesced, grid sized from the SM count.
+#include <mutex>
 #include "common.cuh"
 #include "snag_internal.h"
 
@@ -798,15 +799,20 @@ __global__ void __launch_bounds__(128) band_rescore_kernel(const __nv_bfloat16* 
                                                            const float* __restrict__ g_row, const float* __restrict__ g_col,
                                                            int row_gid0, int col_gid0, int use_csls,
                                                            const uint2* __restrict__ band, const unsigned int* __restrict__ band_cnt,
-                                                           unsigned int band_cap, int* __restrict__ cnt_row, int* __restrict__ cnt_col) {
+                                                           unsigned int band_cap, int* __restrict__ cnt_row, int* __restrict__ cnt_col,
+                                                           const int* __restrict__ row_gids, int swapped) {
+  // row_gids: the rows of X are a gathered subset (global pair ids listed); swapped: X holds TARGETS and Y sources (the
+  // recount of selected targets runs the sweep with the operands exchanged) — the fp32 CSLS chain subtracts the SOURCE's
+  // neighbourhood mean first, so the roles must be put back before it is evaluated
   const unsigned int total = min(*band_cnt, band_cap);
   for (unsigned int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
     const uint2 it = band[e];
     const int i = static_cast<int>(it.x & 0x3fffffffu), j = static_cast<int>(it.y);
     const uint32_t flags = it.x >> 30;
     const float s = canonical_dot(X + static_cast<long long>(i) * Dpad, Y + static_cast<long long>(j) * Dpad, Dpad);
-    const float dist = canonical_dist(s, xn[i], yn[j], use_csls ? nv1[i] : 0.f, use_csls ? nv2[j] : 0.f, use_csls);
-    const int ig = row_gid0 + i, jg = col_gid0 + j;
+    const float dist = swapped ? canonical_dist(s, yn[j], xn[i], use_csls ? nv2[j] : 0.f, use_csls ? nv1[i] : 0.f, use_csls)
+                               : canonical_dist(s, xn[i], yn[j], use_csls ? nv1[i] : 0.f, use_csls ? nv2[j] : 0.f, use_csls);
+    const int ig = row_gids != nullptr ? row_gids[i] : row_gid0 + i, jg = col_gid0 + j;
     if (ig == jg) continue;
     if (flags & 1u) {
       const float g = g_row[i];
@@ -817,6 +823,170 @@ __global__ void __launch_bounds__(128) band_rescore_kernel(const __nv_bfloat16* 
       if (dist < g || (dist == g && ig < jg)) atomicAdd(cnt_col + j, 1);
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// One-pass evaluation (EpiOnePass in simgemm.cuh): the rank verdicts of main.py:400-429 are taken on the elements the
+// single sweep streamed out, against thresholds known only after the sweep.
+//   spec_bounds     : from the sample pre-pass lists (KT per entity, ascending, tensor-core c) and the canonical c of
+//                     the entity's own pair:  lo = mean of the k largest of the sample - delta  (a LOWER bound of the
+//                     final neighbourhood mean: every order statistic of the full population dominates the sample's),
+//                     hi = a GUESS of an upper bound: the sample's order statistics shifted by `shift` times their
+//                     tail scale (exponential-tail extrapolation from the sample to the population: an order statistic
+//                     of rank r in a sample of m of n entities sits at population rank r n / m, i.e. ln(n/m) tail scales
+//                     lower than the population's rank-r value), the own pair merged in.
+//                     A guess that turns out too low is detected after the sweep and costs an exhaustive recount of that
+//                     entity — never a wrong rank.
+//   rank_judge      : every streamed element against the final constants of EpiRankBand: outside the band -> counted,
+//                     inside -> deferred to band_rescore (canonical arithmetic + stable tie-break), exactly like sweep 2.
+//   rank_exhaustive : canonical recount of listed rows of A against all rows of B (fp64 index-order dots).
+// ------------------------------------------------------------------------------------------------
+__global__ void spec_bounds_kernel(const float* __restrict__ cand, long long n, int k, const float* __restrict__ cdiag,
+                                   float shift, float delta, float* __restrict__ lo, float* __restrict__ hi) {
+  const long long j = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (j >= n) return;
+  float v[KT_LIST];
+#pragma unroll
+  for (int t = 0; t < KT_LIST; ++t) v[t] = cand[j * KT_LIST + t];
+  float sl = 0.f;
+#pragma unroll
+  for (int t = 0; t < KT_LIST; ++t)
+    if (t < k) sl += v[KT_LIST - 1 - t];
+  lo[j] = sl / static_cast<float>(k) - delta;
+  // tail scale of the sample: mean exceedance of the 15 largest over the 16th (the maximum-likelihood estimate for an
+  // exponential tail; far less noisy than the range v_1 - v_16). +inf when the sample list is not full.
+  float exc = 0.f;
+#pragma unroll
+  for (int t = 1; t < KT_LIST; ++t) exc += v[t] - v[0];
+  const float sh = shift * (exc / static_cast<float>(KT_LIST - 1));
+  // merged top-k of {v_t + sh} and the own pair
+  const float cd = cdiag[j];
+  float sh_sum = 0.f;
+  bool used = false;
+  int taken = 0;
+#pragma unroll
+  for (int t = KT_LIST - 1; t >= 0; --t) {
+    if (taken >= k) break;
+    const float x = v[t] + sh;
+    if (!used && cd > x) { sh_sum += cd; used = true; ++taken; if (taken >= k) break; }
+    sh_sum += x;
+    ++taken;
+  }
+  hi[j] = sh_sum / static_cast<float>(k) + delta;
+}
+
+__global__ void __launch_bounds__(256) rank_judge_kernel(const uint2* __restrict__ rk_stream, const int* __restrict__ rk_stream_row,
+                                                         const int* __restrict__ rk_cnt, int rk_cap, const float* __restrict__ R,
+                                                         const float* __restrict__ Rp, const float* __restrict__ C,
+                                                         const float* __restrict__ Cp, const unsigned char* __restrict__ row_ok,
+                                                         const unsigned char* __restrict__ col_ok, float eps, int row_gid0,
+                                                         int col_gid0, int* __restrict__ cnt_row, int* __restrict__ cnt_col,
+                                                         uint2* __restrict__ band, unsigned int* __restrict__ band_cnt,
+                                                         unsigned int band_cap, int* __restrict__ overflow) {
+  const int cta = blockIdx.y;
+  int cnt = rk_cnt[cta];
+  if (cnt > rk_cap) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(overflow, 1);
+    cnt = rk_cap;
+  }
+  const uint2* sp = rk_stream + static_cast<long long>(cta) * rk_cap;
+  const int* rp = rk_stream_row + static_cast<long long>(cta) * rk_cap;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < cnt; e += gridDim.x * blockDim.x) {
+    const uint2 it = sp[e];
+    const int j = static_cast<int>(it.x), i = rp[e];
+    if (row_gid0 + i == col_gid0 + j) continue;          // the ground-truth pair never competes with itself
+    const float s = __uint_as_float(it.y);
+    uint32_t flags = 0;
+    if (row_ok[i]) {
+      const float x = __fsub_rn(s, C[j]), r = R[i];
+      if (x > r + eps) atomicAdd(cnt_row + i, 1);
+      else if (x > r - eps) flags |= 1u;
+    }
+    if (col_ok[j]) {
+      const float y = __fsub_rn(s, Rp[i]), c = Cp[j];
+      if (y > c + eps) atomicAdd(cnt_col + j, 1);
+      else if (y > c - eps) flags |= 2u;
+    }
+    if (flags) {
+      const unsigned int slot = atomicAdd(band_cnt, 1u);
+      if (slot < band_cap) band[slot] = make_uint2(static_cast<uint32_t>(i) | (flags << 30), static_cast<uint32_t>(j));
+    }
+  }
+}
+
+constexpr int RX_ROWS = 8;       // listed rows one block of rank_exhaustive handles together (B is read once for all of them)
+__global__ void __launch_bounds__(256) rank_exhaustive_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restrict__ B,
+                                                              int Dpad, long long n_b, const float* __restrict__ an,
+                                                              const float* __restrict__ bn, const float* __restrict__ nva,
+                                                              const float* __restrict__ nvb, const float* __restrict__ g,
+                                                              const int* __restrict__ rows, int n_rows, int a_gid0, int b_gid0,
+                                                              int use_csls, int swapped, int* __restrict__ cnt) {
+  extern __shared__ float a_s[];                          // [RX_ROWS][Dpad] fp32 copies of the listed rows
+  __shared__ int cnt_s[RX_ROWS];
+  const int r0 = blockIdx.x * RX_ROWS;
+  const int nr = min(RX_ROWS, n_rows - r0);
+  for (int t = threadIdx.x; t < RX_ROWS * Dpad; t += blockDim.x) {
+    const int r = t / Dpad, c = t - r * Dpad;
+    a_s[t] = r < nr ? __bfloat162float(A[static_cast<long long>(rows[r0 + r]) * Dpad + c]) : 0.f;
+  }
+  if (threadIdx.x < RX_ROWS) cnt_s[threadIdx.x] = 0;
+  __syncthreads();
+  float a_n[RX_ROWS], a_nv[RX_ROWS], a_g[RX_ROWS];
+  int a_id[RX_ROWS], my[RX_ROWS];
+#pragma unroll
+  for (int r = 0; r < RX_ROWS; ++r) {
+    const int row = r < nr ? rows[r0 + r] : rows[r0];
+    a_n[r] = an[row];
+    a_nv[r] = use_csls ? nva[row] : 0.f;
+    a_g[r] = g[row];
+    a_id[r] = a_gid0 + row;
+    my[r] = 0;
+  }
+  const long long per = (n_b + gridDim.y - 1) / gridDim.y;
+  const long long j0 = blockIdx.y * per, j1 = min(n_b, j0 + per);
+  for (long long j = j0 + threadIdx.x; j < j1; j += blockDim.x) {
+    const uint4* br = reinterpret_cast<const uint4*>(B + j * Dpad);
+    double acc[RX_ROWS];
+#pragma unroll
+    for (int r = 0; r < RX_ROWS; ++r) acc[r] = 0.0;
+    for (int c = 0; c < Dpad / 8; ++c) {
+      const uint4 b = __ldg(br + c);
+      const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+      float bf[8];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        bf[2 * e] = __uint_as_float(bw[e] << 16);
+        bf[2 * e + 1] = __uint_as_float(bw[e] & 0xffff0000u);
+      }
+#pragma unroll
+      for (int r = 0; r < RX_ROWS; ++r) {
+        const float4 a0 = *reinterpret_cast<const float4*>(a_s + r * Dpad + c * 8);
+        const float4 a1 = *reinterpret_cast<const float4*>(a_s + r * Dpad + c * 8 + 4);
+        const float af[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        // a bf16 x bf16 product is exact in fp32, so exact product + one fp64 rounding == fma(double a, double b, acc)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[r] = __dadd_rn(acc[r], static_cast<double>(__fmul_rn(af[e], bf[e])));
+      }
+    }
+    const float b_n = bn[j], b_nv = use_csls ? nvb[j] : 0.f;
+    const int b_id = b_gid0 + static_cast<int>(j);
+#pragma unroll
+    for (int r = 0; r < RX_ROWS; ++r) {
+      const float sdot = static_cast<float>(acc[r]);
+      const float dist = swapped ? canonical_dist(sdot, b_n, a_n[r], b_nv, a_nv[r], use_csls)
+                                 : canonical_dist(sdot, a_n[r], b_n, a_nv[r], b_nv, use_csls);
+      if (b_id != a_id[r] && (dist < a_g[r] || (dist == a_g[r] && b_id < a_id[r]))) ++my[r];
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < RX_ROWS; ++r) {
+    int v = my[r];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v != 0) atomicAdd(cnt_s + r, v);
+  }
+  __syncthreads();
+  if (threadIdx.x < nr && cnt_s[threadIdx.x] != 0) atomicAdd(cnt + rows[r0 + threadIdx.x], cnt_s[threadIdx.x]);
 }
 
 // canonical dot products of an explicit list of (row of X, row of Y) pairs — the re-score of the similarity entries a
@@ -1470,13 +1640,54 @@ int launch_pair_score(const __nv_bfloat16* X, const __nv_bfloat16* Y, int Dpad, 
 int launch_band_rescore(const __nv_bfloat16* X, const __nv_bfloat16* Y, int Dpad, const float* xn, const float* yn,
                         const float* nv1, const float* nv2, const float* g_row, const float* g_col, int row_gid0, int col_gid0,
                         int use_csls, const uint2* band, const unsigned int* band_cnt, unsigned int band_cap, int* cnt_row,
-                        int* cnt_col, cudaStream_t st) {
+                        int* cnt_col, cudaStream_t st, const int* row_gids, int swapped) {
   if (!X || !Y || !xn || !yn || !g_row || !g_col || !band || !band_cnt || !cnt_row || !cnt_col) return SNAG_ERR_ARG;
   if (use_csls && (!nv1 || !nv2)) return SNAG_ERR_ARG;
   if (Dpad % 64) return SNAG_ERR_SHAPE;
   // grid-stride over the device-side count: no host round trip
   band_rescore_kernel<<<num_sms() * 16, 128, 0, st>>>(X, Y, Dpad, xn, yn, nv1, nv2, g_row, g_col, row_gid0, col_gid0, use_csls,
-                                                      band, band_cnt, band_cap, cnt_row, cnt_col);
+                                                      band, band_cnt, band_cap, cnt_row, cnt_col, row_gids, swapped);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int launch_spec_bounds(const float* cand, long long n, int k, const float* cdiag, float shift, float delta, float* lo,
+                       float* hi, cudaStream_t st) {
+  if (!cand || !cdiag || !lo || !hi || n <= 0 || k < 1 || k > KT_LIST) return SNAG_ERR_ARG;
+  spec_bounds_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, st>>>(cand, n, k, cdiag, shift, delta, lo, hi);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int launch_rank_judge(const uint2* rk_stream, const int* rk_stream_row, const int* rk_cnt, int n_ctas, int rk_cap,
+                      const float* R, const float* Rp, const float* C, const float* Cp, const unsigned char* row_ok,
+                      const unsigned char* col_ok, float eps, int row_gid0, int col_gid0, int* cnt_row, int* cnt_col,
+                      uint2* band, unsigned int* band_cnt, unsigned int band_cap, int* overflow, cudaStream_t st) {
+  if (!rk_stream || !rk_stream_row || !rk_cnt || !R || !Rp || !C || !Cp || !row_ok || !col_ok || !cnt_row || !cnt_col ||
+      !band || !band_cnt || !overflow || n_ctas < 1 || rk_cap < 1)
+    return SNAG_ERR_ARG;
+  rank_judge_kernel<<<dim3(64, n_ctas), 256, 0, st>>>(rk_stream, rk_stream_row, rk_cnt, rk_cap, R, Rp, C, Cp, row_ok, col_ok, eps,
+                                                      row_gid0, col_gid0, cnt_row, cnt_col, band, band_cnt, band_cap, overflow);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int launch_rank_exhaustive(const __nv_bfloat16* A, const __nv_bfloat16* B, int Dpad, long long n_b, const float* an,
+                           const float* bn, const float* nva, const float* nvb, const float* g, const int* rows, int n_rows,
+                           int a_gid0, int b_gid0, int use_csls, int swapped, int* cnt, cudaStream_t st) {
+  if (!A || !B || !an || !bn || !g || !rows || !cnt || n_rows < 1 || n_b < 1) return SNAG_ERR_ARG;
+  if (use_csls && (!nva || !nvb)) return SNAG_ERR_ARG;
+  if (Dpad % 64) return SNAG_ERR_SHAPE;
+  const int smem = RX_ROWS * Dpad * static_cast<int>(sizeof(float));
+  if (smem > 200 * 1024) return SNAG_ERR_SHAPE;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    cudaFuncSetAttribute(rank_exhaustive_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  });
+  const int gx = (n_rows + RX_ROWS - 1) / RX_ROWS;
+  int gy = (num_sms() * 4 + gx - 1) / gx;                  // enough blocks to fill the machine when few rows are listed
+  const long long max_gy = (n_b + 255) / 256;
+  if (gy > max_gy) gy = static_cast<int>(max_gy);
+  if (gy < 1) gy = 1;
+  rank_exhaustive_kernel<<<dim3(gx, gy), 256, smem, st>>>(A, B, Dpad, n_b, an, bn, nva, nvb, g, rows, n_rows, a_gid0, b_gid0,
+                                                          use_csls, swapped, cnt);
   return static_cast<int>(cudaGetLastError());
 }
 

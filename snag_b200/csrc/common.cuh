@@ -5,6 +5,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace snag {
@@ -176,6 +177,12 @@ __device__ __forceinline__ uint64_t make_sdesc_k128(uint32_t smem_addr) {
 
 // Wait for all TMEM loads of this thread. The registers are threaded through as "+r" operands so the
 // compiler cannot schedule a use of them above the wait.
+// one 32-bit column of 32 lanes (warp-collective): the re-read of a single accumulator the epilogue flagged
+__device__ __forceinline__ uint32_t tmem_ld_x1(uint32_t taddr) {
+  uint32_t v;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];\n\ttcgen05.wait::ld.sync.aligned;" : "=r"(v) : "r"(taddr) : "memory");
+  return v;
+}
 #define SNAG_TMEM_WAIT32(r)                                                                                          \
   asm volatile("tcgen05.wait::ld.sync.aligned;"                                                                      \
                : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),      \

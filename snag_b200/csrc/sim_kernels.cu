@@ -272,7 +272,7 @@ int launch_eval_rank(const __nv_bfloat16* X, const __nv_bfloat16* Y, const float
 int launch_eval_rank_band(const __nv_bfloat16* X, const __nv_bfloat16* Y, const float* xn, const float* yn, const float* nv1,
                           const float* nv2, const float* g_row, const float* g_col, int row_gid0, int col_gid0, int n1, int n2,
                           int Dpad, int use_csls, float eps, int* cnt_row, int* cnt_col, float* top4_val, int* top4_idx,
-                          uint2* band, unsigned int* band_cnt, unsigned int band_cap, cudaStream_t st) {
+                          uint2* band, unsigned int* band_cnt, unsigned int band_cap, cudaStream_t st, const int* row_gids) {
   if (!xn || !yn || !g_row || !g_col || !cnt_row || !cnt_col || !band || !band_cnt) return SNAG_ERR_ARG;
   if (use_csls && (!nv1 || !nv2)) return SNAG_ERR_ARG;
   if (!(eps > 0.f) || n1 >= (1 << 30)) return SNAG_ERR_ARG;
@@ -283,7 +283,7 @@ int launch_eval_rank_band(const __nv_bfloat16* X, const __nv_bfloat16* Y, const 
 #define SNAG_RANKB_CASE(T3, CS)                                                                                      \
   {                                                                                                                  \
     typename EpiRankBand<T3, CS>::Params p{xn, yn, nv1, nv2, g_row, g_col, row_gid0, col_gid0, cnt_row, cnt_col,     \
-                                           top4_val, top4_idx, eps, band, band_cnt, band_cap};                       \
+                                           top4_val, top4_idx, eps, band, band_cnt, band_cap, row_gids};             \
     return launch_sim<EpiRankBand<T3, CS>>(X, Y, n1, n2, Dpad, p, st);                                               \
   }
   if (top4_val) {
@@ -304,14 +304,37 @@ int launch_icl_rowsum(const __nv_bfloat16* X, const __nv_bfloat16* Y, int B, int
 
 int launch_eval_rowcoltopk(const __nv_bfloat16* X, const __nv_bfloat16* Y, const float* xn, const float* yn, int n1, int n2,
                            int Dpad, float* part, int* part_idx, const float* rowthr, const float* colthr, const float* colb,
-                           uint2* stream, int* stream_row, int* stream_cnt, int cta_cap, cudaStream_t st) {
+                           uint2* stream, int* stream_row, int* stream_cnt, int cta_cap, float norm2_max, cudaStream_t st) {
   if (!xn || !yn || !part || !part_idx || !colthr || !colb || !stream || !stream_row || !stream_cnt || cta_cap < 1)
     return SNAG_ERR_ARG;
   if (((reinterpret_cast<uintptr_t>(part) | reinterpret_cast<uintptr_t>(part_idx)) & 15) ||
       (reinterpret_cast<uintptr_t>(stream) & 7))
     return SNAG_ERR_ALIGN;
-  EpiRowColTopK::Params p{xn, yn, part, part_idx, rowthr, colthr, colb, stream, stream_row, stream_cnt, cta_cap};
+  if (!(norm2_max <= SNAG_HALF_PREFILTER_NORM2_MAX)) {
+    // rows that are not (nearly) unit norm: the fp16x2 pre-filter's margins do not hold — fp32 per-element tests
+    EpiRowColTopKF32::Params p{xn, yn, part, part_idx, rowthr, colthr, colb, stream, stream_row, stream_cnt, cta_cap};
+    return launch_sim<EpiRowColTopKF32>(X, Y, n1, n2, Dpad, p, st);
+  }
+  EpiRowColTopK::Params p{xn, yn, part, part_idx, rowthr, colthr, colb, stream, stream_row, stream_cnt, cta_cap,
+                          nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0};
   return launch_sim<EpiRowColTopK>(X, Y, n1, n2, Dpad, p, st);
+}
+
+int launch_eval_onepass(const __nv_bfloat16* X, const __nv_bfloat16* Y, const float* xn, const float* yn, int n1, int n2,
+                        int Dpad, float* part, int* part_idx, const float* rowthr, const float* colthr, const float* colb,
+                        uint2* stream, int* stream_row, int* stream_cnt, int cta_cap, const float* rk_r, const float* rk_rp,
+                        const float* rk_c, const float* rk_cp, uint2* rk_stream, int* rk_stream_row, int* rk_cnt, int rk_cap,
+                        float norm2_max, cudaStream_t st) {
+  if (!(norm2_max <= SNAG_HALF_PREFILTER_NORM2_MAX)) return SNAG_ERR_ARG;    // unit-norm rows only (see EpiRowColTopKT)
+  if (!xn || !yn || !part || !part_idx || !colthr || !colb || !stream || !stream_row || !stream_cnt || cta_cap < 1 ||
+      !rk_r || !rk_rp || !rk_c || !rk_cp || !rk_stream || !rk_stream_row || !rk_cnt || rk_cap < 1)
+    return SNAG_ERR_ARG;
+  if (((reinterpret_cast<uintptr_t>(part) | reinterpret_cast<uintptr_t>(part_idx)) & 15) ||
+      ((reinterpret_cast<uintptr_t>(stream) | reinterpret_cast<uintptr_t>(rk_stream)) & 7))
+    return SNAG_ERR_ALIGN;
+  EpiOnePass::Params p{xn, yn, part, part_idx, rowthr, colthr, colb, stream, stream_row, stream_cnt, cta_cap,
+                       rk_r, rk_rp, rk_c, rk_cp, rk_stream, rk_stream_row, rk_cnt, rk_cap};
+  return launch_sim<EpiOnePass>(X, Y, n1, n2, Dpad, p, st);
 }
 
 int launch_mutual_nn(const __nv_bfloat16* X, const __nv_bfloat16* Y, const float* xn, const float* yn, int n1, int n2,

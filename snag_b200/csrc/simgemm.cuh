@@ -36,7 +36,7 @@ constexpr int NUM_EPI_WG = SNAG_EPI_WG;       // epilogue warpgroups; WG w owns 
 constexpr int NUM_EPI_THREADS = 128 * NUM_EPI_WG;
 constexpr int NUM_THREADS = NUM_CTRL_THREADS + NUM_EPI_THREADS;
 constexpr int STRIPS_PER_WG = BN / 32 / NUM_EPI_WG;
-constexpr int EPI_VEC_FLOATS = 2048;      // per-tile column vectors (double-buffered): 8 KB
+constexpr int EPI_VEC_FLOATS = 3584;      // per-tile column vectors (double-buffered): 14 KB
 constexpr int EPI_STAGE_VALS = 4096 / NUM_EPI_THREADS;   // accumulators one thread can park at a time (16 KB in total)
 constexpr int EPI_STAGE_FLOATS = NUM_EPI_THREADS * EPI_STAGE_VALS;
 constexpr int EPI_SCRATCH_BYTES = (EPI_VEC_FLOATS + EPI_STAGE_FLOATS) * 4;
@@ -72,11 +72,17 @@ struct EpiCtx {
   int split;     // split-K slice of the unit (0 when ksplits == 1)
   int useq;      // sequence number of the unit within this CTA (parity selects double-buffered per-unit scratch)
   float* scratch;  // EPI_SCRATCH_BYTES of shared memory private to the epilogue warpgroup
+  uint32_t taddr;  // TMEM address of the strip handed to Epi::chunk (this warp's lanes, first of its 32 columns)
 };
 
 // Control warps (TMA producer, UMMA issuer): by default the whole warp walks the loop and one elected lane issues
 // (convergent code, uniform datapath). SNAG_CTRL_CONVERGED=0 builds the single-lane form for A/B measurements.
 // SNAG_PIPE_LD=1: software-pipelined TMEM read-out in the epilogue strip loop (A/B: scripts/build_variants.sh)
+// SNAG_OPX: development bisect switches of the one-pass epilogue (bit 0: no rank terms in the fast path, bit 1: l2r term
+// only, bit 2: no rank test / append in the slow path); 0 in the product build
+#ifndef SNAG_OPX
+#define SNAG_OPX 0
+#endif
 #ifndef SNAG_PIPE_LD
 #define SNAG_PIPE_LD 0
 #endif
@@ -100,7 +106,7 @@ __device__ __forceinline__ int tile_strips(const SimShape& shp, int ct) {
 
 // registers carrying one column's prefetched per-tile values from tile_prefetch to tile_commit
 struct EpiPre {
-  float a, b, c;
+  float a, b, c, d, e;
 };
 
 // number of epilogue warpgroups of a kernel instantiation: Epi::kWG when the epilogue asks for its own count (a
@@ -303,10 +309,12 @@ sim_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
           for (int c = c_beg; c < c_end; c += 2) {
             SNAG_TMEM_WAIT32(r0);
             if (c + 1 < c_end) SNAG_TMEM_LD32(taddr + (c + 1) * 32, r1);
+            cx.taddr = taddr + c * 32;
             Epi::chunk(ep, shp, cx, st, ct, c, r0, buf);
             if (c + 1 < c_end) {
               SNAG_TMEM_WAIT32(r1);
               if (c + 2 < c_end) SNAG_TMEM_LD32(taddr + (c + 2) * 32, r0);
+              cx.taddr = taddr + (c + 1) * 32;
               Epi::chunk(ep, shp, cx, st, ct, c + 1, r1, buf);
             }
           }
@@ -316,6 +324,7 @@ sim_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
             uint32_t r[32];
             SNAG_TMEM_LD32(taddr + c * 32, r);
             SNAG_TMEM_WAIT32(r);
+            cx.taddr = taddr + c * 32;
             Epi::chunk(ep, shp, cx, st, ct, c, r, buf);
           }
 #endif
@@ -647,6 +656,22 @@ struct EpiRowTopK {
 //     bandwidth kernels bucket the streams by column afterwards. (Letting the row owner re-check its own flagged
 //     columns through 32 predicated blocks needs no staging but measured 10-20 % slower.)
 // ------------------------------------------------------------------------------------------------
+// r[q] for a WARP-UNIFORM run-time q: a switch the compiler turns into an indexed branch (BRX) — every lane takes the same
+// case, so there is no divergence and no local-memory spill of the register strip
+__device__ __forceinline__ uint32_t strip_value(const uint32_t (&r)[32], int q) {
+  uint32_t v = 0;
+  switch (q) {
+#define SNAG_SV_CASE(i) case i: v = r[i]; break;
+    SNAG_SV_CASE(0) SNAG_SV_CASE(1) SNAG_SV_CASE(2) SNAG_SV_CASE(3) SNAG_SV_CASE(4) SNAG_SV_CASE(5) SNAG_SV_CASE(6) SNAG_SV_CASE(7)
+    SNAG_SV_CASE(8) SNAG_SV_CASE(9) SNAG_SV_CASE(10) SNAG_SV_CASE(11) SNAG_SV_CASE(12) SNAG_SV_CASE(13) SNAG_SV_CASE(14)
+    SNAG_SV_CASE(15) SNAG_SV_CASE(16) SNAG_SV_CASE(17) SNAG_SV_CASE(18) SNAG_SV_CASE(19) SNAG_SV_CASE(20) SNAG_SV_CASE(21)
+    SNAG_SV_CASE(22) SNAG_SV_CASE(23) SNAG_SV_CASE(24) SNAG_SV_CASE(25) SNAG_SV_CASE(26) SNAG_SV_CASE(27) SNAG_SV_CASE(28)
+    SNAG_SV_CASE(29) SNAG_SV_CASE(30) SNAG_SV_CASE(31)
+#undef SNAG_SV_CASE
+    default: break;
+  }
+  return v;
+}
 __device__ __forceinline__ uint32_t transpose32(uint32_t x, int lane) {
 #pragma unroll
   for (int sft = 16; sft >= 1; sft >>= 1) {
@@ -658,7 +683,255 @@ __device__ __forceinline__ uint32_t transpose32(uint32_t x, int lane) {
   return x;
 }
 
-struct EpiRowColTopK {
+// kRank (the one-pass evaluation, EpiOnePass): the same sweep also streams out every element that may count towards a
+// RANK, so that the second sweep over S is not needed. The rank verdicts are  s_ij > R_i + C_j  (l2r) and
+// s_ij > R'_i + C'_j  (r2l) with per-row / per-column constants that depend on the CSLS means this very sweep
+// produces (see EpiRankBand). The caller passes constants that are provably or speculatively BELOW the final ones —
+// rk_row = min-side R, R' built from a lower bound of nv1 and a guessed upper bound of the pair's own nv2, rk_col
+// likewise — and every element above either relaxed threshold is appended as (column, s bits, row) to a second
+// per-CTA stream. rank_judge_kernel then settles the streamed elements against the final constants (counting,
+// deferring the band to band_rescore); rows / columns whose guessed bound turned out too low are recounted
+// exhaustively. A few 1e-4 of the elements are streamed.
+template <bool kRank>
+struct EpiRowColTopKT {
+  static constexpr bool kNoLoad = false;
+  struct Params {
+    const float* xn;       // [n_rows]
+    const float* yn;       // [n_cols]
+    float* part;           // [n_lists][n_rows][KT]   row candidates, as EpiRowTopK
+    int* part_idx;         // [n_lists][n_rows][KT]   their view columns
+    const float* rowthr;   // [n_rows] or null: a lower bound of row i's final KT-th largest c (from a sample of the
+                           // columns). Every list starts from it instead of -inf, which removes the ~KT*ln(cols/KT)
+                           // warm-up insertions each unit would otherwise pay; unfilled slots keep (rowthr, -1).
+    const float* colthr;   // [n_cols] admission threshold of column j in c-space (from the sample pre-pass)
+    const float* colb;     // [n_cols] b_j of the s-space pre-filter
+    uint2* stream;         // [gridDim.x][cta_cap] (column, c bits) candidates appended by each CTA
+    int* stream_row;       // [gridDim.x][cta_cap] view row of every stream entry
+    int* stream_cnt;       // [gridDim.x] entries each CTA produced (may exceed cta_cap: overflow, entries dropped)
+    int cta_cap;
+    // kRank only
+    const float* rk_r;     // [n_rows] relaxed R_i   (l2r: s > rk_r[i] + rk_c[j])
+    const float* rk_rp;    // [n_rows] relaxed R'_i  (r2l: s > rk_rp[i] + rk_cp[j])
+    const float* rk_c;     // [n_cols] relaxed C_j
+    const float* rk_cp;    // [n_cols] relaxed C'_j
+    uint2* rk_stream;      // [gridDim.x][rk_cap] (column, s bits)
+    int* rk_stream_row;    // [gridDim.x][rk_cap]
+    int* rk_cnt;           // [gridDim.x]
+    int rk_cap;
+  };
+  struct State {
+    float xn, a;
+    float rk_r, rk_rp;
+    uint32_t a2, rk_r2, rk_rp2;      // half2 broadcasts of the row constants, rounded down and lowered by kHalfMargin
+    float top[KT];
+    int topi[KT];
+  };
+  // Pre-filter arithmetic in fp16x2 (two elements per instruction): for |values| < 2 every rounding involved (s to nearest:
+  // 2.5e-4, the per-column terms and row constants DOWN, the half2 sum to nearest: 4.9e-4) is covered by lowering the row
+  // constants by 1e-3 — the half2 test can only flag MORE than the exact fp32 test, which then decides. The caller must
+  // not use this epilogue for rows that are not (nearly) unit norm (launch_eval_rowcoltopk checks norm_max).
+  static constexpr float kHalfMargin = 1e-3f;
+  static __device__ __forceinline__ uint32_t half2_bcast_rd(float v) {
+    const __half h = __float2half_rd(v);
+    const __half2 h2 = __halves2half2(h, h);
+    return *reinterpret_cast<const uint32_t*>(&h2);
+  }
+  // scratch per tile buffer (floats): yn[BN], strip minima of yn [BN/32], colb[BN], colthr[BN] (+ rk_c[BN], rk_cp[BN]), then
+  // the fp16x2 copies (rounded down) of colb (+ rk_c, rk_cp): BN/2 words each; after the two buffers the two stream counters
+  static constexpr int kVecs = kRank ? 5 : 3;
+  static constexpr int kHalfOff = kVecs * BN + BN / 32;             // 16-byte aligned: (kVecs*256 + 8) * 4 bytes
+  static constexpr int kVecStride = kHalfOff + (kRank ? 3 : 1) * (BN / 2);
+  static constexpr int kCntOff = 2 * kVecStride;         // int: candidates appended by this CTA so far (+1: rank stream)
+  static __device__ __forceinline__ void kernel_end(const Params& p, const EpiCtx& cx) {
+    named_bar_sync(1, NUM_EPI_THREADS);
+    if (cx.tid == 0) {
+      p.stream_cnt[blockIdx.x] = *reinterpret_cast<const int*>(cx.scratch + kCntOff);
+      if (kRank) p.rk_cnt[blockIdx.x] = *reinterpret_cast<const int*>(cx.scratch + kCntOff + 1);
+    }
+  }
+  static __device__ __forceinline__ void unit_begin(const Params& p, const SimShape&, const EpiCtx& cx, State& st) {
+    static_assert(kCntOff + 2 <= EPI_VEC_FLOATS, "scratch too small");
+    static_assert((kHalfOff % 4) == 0 && (kVecStride % 4) == 0, "fp16x2 vectors must be 16-byte aligned");
+    if (cx.useq == 0 && cx.tid == 0) {                     // ordered by the tile barrier
+      *reinterpret_cast<int*>(cx.scratch + kCntOff) = 0;
+      *reinterpret_cast<int*>(cx.scratch + kCntOff + 1) = 0;
+    }
+    st.xn = cx.row_ok ? p.xn[cx.row] : 0.f;
+    st.a = cx.row_ok ? 0.5f * st.xn : INFINITY;          // padding rows never produce column candidates
+    st.a2 = half2_bcast_rd(st.a - kHalfMargin);
+    if (kRank) {
+      st.rk_r = cx.row_ok ? p.rk_r[cx.row] : INFINITY;
+      st.rk_rp = cx.row_ok ? p.rk_rp[cx.row] : INFINITY;
+      st.rk_r2 = half2_bcast_rd(st.rk_r - kHalfMargin);
+      st.rk_rp2 = half2_bcast_rd(st.rk_rp - kHalfMargin);
+    }
+    const float t0 = (p.rowthr != nullptr && cx.row_ok) ? p.rowthr[cx.row] : -INFINITY;
+#pragma unroll
+    for (int t = 0; t < KT; ++t) { st.top[t] = t0; st.topi[t] = -1; }
+  }
+  static __device__ __forceinline__ EpiPre tile_prefetch(const Params& p, const SimShape& shp, const EpiCtx& cx, int ct) {
+    EpiPre pre{};
+    const int col = ct * BN + cx.tid;
+    if (cx.tid < BN) {
+      const bool ok = col < shp.n_cols;
+      pre.a = ok ? p.yn[col] : INFINITY;
+      pre.b = ok ? p.colb[col] : INFINITY;
+      pre.c = ok ? p.colthr[col] : INFINITY;
+      if (kRank) {
+        pre.d = ok ? p.rk_c[col] : INFINITY;
+        pre.e = ok ? p.rk_cp[col] : INFINITY;
+      }
+    }
+    return pre;
+  }
+  static __device__ __forceinline__ void tile_commit(const Params&, const SimShape&, const EpiCtx& cx, State&,
+                                                     const EpiPre& pre, int, int buf) {
+    static_assert(NUM_EPI_THREADS >= BN, "one epilogue thread stages one column");
+    if (cx.tid >= BN) return;                      // whole warps leave: the shuffles below stay warp-complete
+    float* v_s = cx.scratch + buf * kVecStride;
+    const float v = pre.a;
+    v_s[cx.tid] = v;
+    v_s[BN + BN / 32 + cx.tid] = pre.b;
+    v_s[2 * BN + BN / 32 + cx.tid] = pre.c;
+    if (kRank) {
+      v_s[3 * BN + BN / 32 + cx.tid] = pre.d;
+      v_s[4 * BN + BN / 32 + cx.tid] = pre.e;
+    }
+    float m = v;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (cx.lane == 0) v_s[BN + (cx.tid >> 5)] = m;
+    // fp16x2 copies, rounded DOWN (a lower per-column term only flags more): even lanes pack (column, column + 1)
+    uint32_t* h_s = reinterpret_cast<uint32_t*>(v_s + kHalfOff);
+    const float b1 = __shfl_down_sync(0xffffffffu, pre.b, 1);
+    const float d1 = __shfl_down_sync(0xffffffffu, pre.d, 1);
+    const float e1 = __shfl_down_sync(0xffffffffu, pre.e, 1);
+    if ((cx.tid & 1) == 0) {
+      const __half2 hb = __halves2half2(__float2half_rd(pre.b), __float2half_rd(b1));
+      h_s[cx.tid >> 1] = *reinterpret_cast<const uint32_t*>(&hb);
+      if (kRank) {
+        const __half2 hd = __halves2half2(__float2half_rd(pre.d), __float2half_rd(d1));
+        const __half2 he = __halves2half2(__float2half_rd(pre.e), __float2half_rd(e1));
+        h_s[BN / 2 + (cx.tid >> 1)] = *reinterpret_cast<const uint32_t*>(&hd);
+        h_s[BN + (cx.tid >> 1)] = *reinterpret_cast<const uint32_t*>(&he);
+      }
+    }
+  }
+  // Fast path in fp16x2: two elements per instruction. flagged <=> s > min(row top-k pre-filter, a_i + b_j (column
+  // candidate), R_i + C_j, R'_i + C'_j (rank candidates, kRank)) with every term rounded conservatively (see kHalfMargin):
+  // per PAIR of elements one pack, 3 adds, 3 mins, one compare-to-mask and one LOP3 = 4.5 instructions per element
+  // (2.5 without kRank) against 11 (6) for the fp32 per-element tests, which cost 27 % of the SM clock at the 1 kW power
+  // cap. Strip-level (row x 32 columns) thresholds are useless here: column hubness — what CSLS corrects — moves the
+  // per-column terms by as much as the element noise, and the minimum over 32 columns flagged 0.8 % of all elements.
+  // Bit b of the mask: element 2b (b < 16) or 2(b - 16) + 1.
+  static __device__ __forceinline__ void chunk(const Params& p, const SimShape& shp, const EpiCtx& cx, State& st, int ct,
+                                               int c, const uint32_t (&r)[32], int buf) {
+    const float* v_s = cx.scratch + buf * kVecStride;
+    const float* yn_s = v_s + c * 32;
+    const float* cb_s = v_s + BN + BN / 32 + c * 32;
+    const float* ct_s = v_s + 2 * BN + BN / 32 + c * 32;
+    const float* kc_s = v_s + 3 * BN + BN / 32 + c * 32;
+    const float* kp_s = v_s + 4 * BN + BN / 32 + c * 32;
+    const uint32_t* h_s = reinterpret_cast<const uint32_t*>(v_s + kHalfOff) + c * 16;
+    const float tmin = __fadd_rn(st.xn, v_s[BN + c]);
+    const float thr = __fmaf_rn(0.5f, __fadd_rn(__fadd_rn(tmin, -1.0f), st.top[0]), -4e-6f);
+    const uint32_t thr2w = half2_bcast_rd(thr - 3e-4f);
+    const __half2 thr2 = *reinterpret_cast<const __half2*>(&thr2w);
+    const __half2 a2 = *reinterpret_cast<const __half2*>(&st.a2);
+    const __half2 r2 = *reinterpret_cast<const __half2*>(&st.rk_r2);
+    const __half2 rp2 = *reinterpret_cast<const __half2*>(&st.rk_rp2);
+    uint32_t fm = 0;
+#pragma unroll
+    for (int pq = 0; pq < 16; ++pq) {
+      const __half2 h = __floats2half2_rn(__uint_as_float(r[2 * pq]), __uint_as_float(r[2 * pq + 1]));
+      const __half2 cb2 = *reinterpret_cast<const __half2*>(h_s + pq);
+      __half2 m = __hmin2(thr2, __hadd2(a2, cb2));
+      if (kRank) {
+#if !(SNAG_OPX & 1)
+        const __half2 kc2 = *reinterpret_cast<const __half2*>(h_s + BN / 2 + pq);
+#if (SNAG_OPX & 2)
+        m = __hmin2(m, __hadd2(r2, kc2));
+#else
+        const __half2 kp2 = *reinterpret_cast<const __half2*>(h_s + BN + pq);
+        m = __hmin2(m, __hmin2(__hadd2(r2, kc2), __hadd2(rp2, kp2)));
+#endif
+#endif
+      }
+      fm |= __hgt2_mask(h, m) & ((1u << pq) | (0x10000u << pq));
+    }
+    if (!__any_sync(0xffffffffu, fm != 0)) return;
+    // Slow path, warp-uniform: walk the columns ANY row of this warp flagged; the column index is the same for all lanes,
+    // so the accumulator is fetched from the register strip through an indexed (uniform) branch, and the flagging rows
+    // run the exact tests. No shared-memory staging, no transposition: top-k insertion touches only the row's own
+    // registers and the two appends are stateless, so the row owner does all three. (Measured alternatives: staging the
+    // strip in shared memory + handing column candidates to a column-owning lane: -20 % SM clock at the 1 kW power cap;
+    // re-reading the column from TMEM with tcgen05.ld.x1: ~1 200 cycles per flagged column, epilogue-bound.)
+    uint32_t um = __reduce_or_sync(0xffffffffu, fm);
+    if (shp.dbg != nullptr) {               // diagnostics: flagged strips / flagged columns / flagged elements of this CTA
+      const int nf = __reduce_add_sync(0xffffffffu, __popc(fm));
+      if (cx.lane == 0) {
+        atomicAdd(shp.dbg + (gridDim.x + blockIdx.x) * 4 + 1, 1ull);
+        atomicAdd(shp.dbg + (gridDim.x + blockIdx.x) * 4 + 2, static_cast<unsigned long long>(__popc(um)));
+        atomicAdd(shp.dbg + (gridDim.x + blockIdx.x) * 4 + 3, static_cast<unsigned long long>(nf));
+      }
+    }
+    while (um != 0) {
+      const int b = __ffs(um) - 1;
+      um &= um - 1;
+      const int q = b < 16 ? 2 * b : 2 * (b - 16) + 1;
+      const float sv = __uint_as_float(strip_value(r, q));          // q is warp-uniform: an indexed branch, no divergence
+      if (((fm >> b) & 1u) != 0) {
+      const float ynq = yn_s[q];
+      float x = 0.f;
+      const bool want_row = sv > thr, want_col = sv > __fadd_rn(st.a, cb_s[q]);
+      if (want_row || want_col) x = __fsub_rn(1.0f, sqdist_from_dot(sv, st.xn, ynq));
+      if (want_row && x > st.top[0]) topk_list_insert<true>(st.top, st.topi, x, ct * BN + c * 32 + q);
+      if (want_col && x >= ct_s[q]) {
+        // column candidate (column, c, row): appended to this CTA's private stream, a shared-memory counter hands out
+        // the slot (no global-atomic round trip on the epilogue's critical path); a later pass buckets the streams by
+        // column. The counter saturates just above the capacity (overflow is detected by cnt > cap; letting it run on
+        // could wrap 32 bits when nearly everything is streamed).
+        volatile int* cc = reinterpret_cast<volatile int*>(cx.scratch + kCntOff);
+        if (*cc <= p.cta_cap) {
+          const int slot = atomicAdd(reinterpret_cast<int*>(cx.scratch + kCntOff), 1);
+          if (slot < p.cta_cap) {
+            const long long o = static_cast<long long>(blockIdx.x) * p.cta_cap + slot;
+            p.stream[o] = make_uint2(static_cast<uint32_t>(ct * BN + c * 32 + q), __float_as_uint(x));
+            p.stream_row[o] = cx.row;
+          }
+        }
+      }
+      if (kRank && !(SNAG_OPX & 4)) {
+        if (sv > fminf(__fadd_rn(st.rk_r, kc_s[q]), __fadd_rn(st.rk_rp, kp_s[q]))) {
+          // rank candidate: (column, tensor-core s, row)
+          volatile int* kc = reinterpret_cast<volatile int*>(cx.scratch + kCntOff + 1);
+          if (*kc <= p.rk_cap) {
+            const int slot = atomicAdd(reinterpret_cast<int*>(cx.scratch + kCntOff + 1), 1);
+            if (slot < p.rk_cap) {
+              const long long o = static_cast<long long>(blockIdx.x) * p.rk_cap + slot;
+              p.rk_stream[o] = make_uint2(static_cast<uint32_t>(ct * BN + c * 32 + q), __float_as_uint(sv));
+              p.rk_stream_row[o] = cx.row;
+            }
+          }
+        }
+      }
+      }
+    }
+  }
+  static __device__ __forceinline__ void tile_end(const Params&, const SimShape&, const EpiCtx&, State&, int, int) {}
+  static __device__ __forceinline__ void unit_end(const Params& p, const SimShape& shp, const EpiCtx& cx, State& st) {
+    if (!cx.row_ok) return;
+    const long long o0 = (static_cast<long long>(cx.list) * shp.n_rows + cx.row) * KT;
+    float4* o = reinterpret_cast<float4*>(p.part + o0);
+    int4* oi = reinterpret_cast<int4*>(p.part_idx + o0);
+#pragma unroll
+    for (int t = 0; t < KT; t += 4) {
+      o[t / 4] = make_float4(st.top[t], st.top[t + 1], st.top[t + 2], st.top[t + 3]);
+      oi[t / 4] = make_int4(st.topi[t], st.topi[t + 1], st.topi[t + 2], st.topi[t + 3]);
+    }
+  }
+};
+struct EpiRowColTopKF32 {
   static constexpr bool kNoLoad = false;
   struct Params {
     const float* xn;       // [n_rows]
@@ -791,6 +1064,9 @@ struct EpiRowColTopK {
     }
   }
 };
+
+using EpiRowColTopK = EpiRowColTopKT<false>;
+using EpiOnePass = EpiRowColTopKT<true>;
 
 // ------------------------------------------------------------------------------------------------
 // Epilogue: mutual nearest neighbours (model/SNAG.py:192-208, Iter_new_links): for every row the column with the
@@ -1071,6 +1347,8 @@ struct EpiRankBand {
     uint2* band;         // [band_cap] deferred elements: x = view row | direction flags << 30, y = view column
     unsigned int* band_cnt;   // number of deferred elements (may exceed band_cap: overflow, caller re-runs)
     unsigned int band_cap;
+    const int* row_gids;      // [n_rows] or null: global pair id of every view row when the rows are a gathered subset
+                              // (recount of selected entities); null: row_gid0 + row
   };
   struct State {
     float r_lo, r_hi, rp;
@@ -1080,7 +1358,7 @@ struct EpiRankBand {
     int t4i[4];
   };
   static __device__ __forceinline__ void unit_begin(const Params& p, const SimShape&, const EpiCtx& cx, State& st) {
-    st.gid = p.row_gid0 + cx.row;
+    st.gid = (p.row_gids != nullptr && cx.row_ok) ? p.row_gids[cx.row] : p.row_gid0 + cx.row;
     st.cnt = 0;
     if (cx.row_ok) {
       const float xn = p.xn[cx.row], g = p.g_row[cx.row];

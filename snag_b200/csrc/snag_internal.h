@@ -76,7 +76,7 @@ int launch_top3_merge(const float* val, const int* idx, int n_lists, long long n
 int launch_band_rescore(const __nv_bfloat16* X, const __nv_bfloat16* Y, int Dpad, const float* xn, const float* yn,
                         const float* nv1, const float* nv2, const float* g_row, const float* g_col, int row_gid0, int col_gid0,
                         int use_csls, const uint2* band, const unsigned int* band_cnt, unsigned int band_cap, int* cnt_row,
-                        int* cnt_col, cudaStream_t st);
+                        int* cnt_col, cudaStream_t st, const int* row_gids = nullptr, int swapped = 0);
 int launch_pairs_dot(const __nv_bfloat16* X, const __nv_bfloat16* Y, int Dpad, const int* rows, const int* cols,
                      long long n_pairs, float* s_out, cudaStream_t st);
 int launch_top4_merge(const float* val, const int* idx, int n_lists, long long n_rows, float* oval, int* oidx, cudaStream_t st);
@@ -108,7 +108,8 @@ int launch_eval_rank(const __nv_bfloat16* X, const __nv_bfloat16* Y, const float
 int launch_eval_rank_band(const __nv_bfloat16* X, const __nv_bfloat16* Y, const float* xn, const float* yn, const float* nv1,
                           const float* nv2, const float* g_row, const float* g_col, int row_gid0, int col_gid0, int n1, int n2,
                           int Dpad, int use_csls, float eps, int* cnt_row, int* cnt_col, float* top4_val, int* top4_idx,
-                          uint2* band, unsigned int* band_cnt, unsigned int band_cap, cudaStream_t st);
+                          uint2* band, unsigned int* band_cnt, unsigned int band_cap, cudaStream_t st,
+                          const int* row_gids = nullptr);
 int launch_icl_rowsum(const __nv_bfloat16* X, const __nv_bfloat16* Y, int B, int Bp, int row0, int nx, int Dpad, float inv_tau,
                       float* rowsum_part, float* pos, cudaStream_t st);
 
@@ -117,7 +118,24 @@ int launch_mutual_nn(const __nv_bfloat16* X, const __nv_bfloat16* Y, const float
                      cudaStream_t st);
 int launch_eval_rowcoltopk(const __nv_bfloat16* X, const __nv_bfloat16* Y, const float* xn, const float* yn, int n1, int n2,
                            int Dpad, float* part, int* part_idx, const float* rowthr, const float* colthr, const float* colb,
-                           uint2* stream, int* stream_row, int* stream_cnt, int cta_cap, cudaStream_t st);
+                           uint2* stream, int* stream_row, int* stream_cnt, int cta_cap, float norm2_max, cudaStream_t st);
+int launch_eval_onepass(const __nv_bfloat16* X, const __nv_bfloat16* Y, const float* xn, const float* yn, int n1, int n2,
+                        int Dpad, float* part, int* part_idx, const float* rowthr, const float* colthr, const float* colb,
+                        uint2* stream, int* stream_row, int* stream_cnt, int cta_cap, const float* rk_r, const float* rk_rp,
+                        const float* rk_c, const float* rk_cp, uint2* rk_stream, int* rk_stream_row, int* rk_cnt, int rk_cap,
+                        float norm2_max, cudaStream_t st);
+// largest squared row norm for which the fp16x2 pre-filter of the fused CSLS sweep is used (F.normalize'd rows rounded to
+// bf16 are 1 +- 4e-3); above it snag_eval_rowcoltopk runs its fp32 per-element tests and snag_eval_onepass refuses
+#define SNAG_HALF_PREFILTER_NORM2_MAX 1.05f
+int launch_spec_bounds(const float* cand, long long n, int k, const float* cdiag, float shift, float delta, float* lo,
+                       float* hi, cudaStream_t st);
+int launch_rank_judge(const uint2* rk_stream, const int* rk_stream_row, const int* rk_cnt, int n_ctas, int rk_cap,
+                      const float* R, const float* Rp, const float* C, const float* Cp, const unsigned char* row_ok,
+                      const unsigned char* col_ok, float eps, int row_gid0, int col_gid0, int* cnt_row, int* cnt_col,
+                      uint2* band, unsigned int* band_cnt, unsigned int band_cap, int* overflow, cudaStream_t st);
+int launch_rank_exhaustive(const __nv_bfloat16* A, const __nv_bfloat16* B, int Dpad, long long n_b, const float* an,
+                           const float* bn, const float* nva, const float* nvb, const float* g, const int* rows, int n_rows,
+                           int a_gid0, int b_gid0, int use_csls, int swapped, int* cnt, cudaStream_t st);
 int launch_col_threshold(const float* cand, long long n, int k, const float* yn, float* colthr, float* colb, cudaStream_t st);
 int launch_cand_hist(const uint2* stream, const int* stream_cnt, int n_ctas, int cta_cap, int* hist, int* overflow,
                      cudaStream_t st);

@@ -71,6 +71,16 @@ def two_sweep_plan(n: int, k: int, n_targets: int | None = None, n_ctas: int = 1
     return m, cap
 
 
+# One-pass evaluation (n >= TWO_SWEEP_MIN_N, CSLS, no prediction file): the main sweep also streams out every element that
+# may count towards a rank, judged after the neighbourhood means are final — the second sweep over S is not needed.
+ONE_PASS = True
+ONE_PASS_GAMMA = 1.5                 # safety factor on the sample -> population extrapolation of the guessed upper bounds
+ONE_PASS_STREAM_PER_TARGET = 1024    # rank-stream entries provided per owned target (both directions together)
+ONE_PASS_EXHAUSTIVE_MAX = 32         # up to this many entities whose guess failed are recounted with fp64 dots ...
+ONE_PASS_RECOUNT_MAX_FRAC = 0.8      # ... more by tensor-core sweeps over the gathered sub-panels (a fraction failed_rows / n +
+                                     # failed_cols / n_targets of a sweep), unless that exceeds this much of sweep 2
+_ONE_PASS_CAP: dict = {}             # (n, ns, k, dpad) -> per-CTA stream capacity that was enough last time
+
 _SAMPLES: dict = {}
 
 
@@ -93,7 +103,7 @@ LAZY_NORM2_BOUND = 1.02     # squared row norm the sync-free path assumes (F.nor
 
 
 def _align_ranks_steps(be, X, Y, xn, yn, n: int, csls_k: int, use_csls: bool, want_top3: bool, world: int, rank: int,
-                       two_sweep: bool = True, lazy: bool = False):
+                       two_sweep: bool = True, lazy: bool = False, one_pass: bool | None = None):
     """Generator form of the sharded evaluation. Yields ("all_gather", t) / ("all_reduce", t) whenever the ranks
     must exchange data and receives the collective's result (all_gather: tensor with a new leading dim of size
     world; all_reduce: the elementwise sum). Returning through StopIteration.value keeps the data path identical
@@ -121,11 +131,25 @@ def _align_ranks_steps(be, X, Y, xn, yn, n: int, csls_k: int, use_csls: bool, wa
         col_val = col_idx = col_bound = None
         plan2 = two_sweep_plan(n, csls_k, ns, be.num_sms()) if (two_sweep and hasattr(be, "eval_rowcoltopk")) else None
         part = pidx = None
+        one = None          # state of the one-pass evaluation (relaxed constants, rank streams) or None
         if plan2 is not None:
             # two-sweep path: sample pre-passes bound every target's k-th best and every source's KT-th best from
             # below; the main sweep then builds the row lists from those bounds and collects, per target, every source
             # at or above its bound, so the swapped sweep is not needed.
             m, cap = plan2
+            if one_pass is None:
+                one_pass = ONE_PASS
+            # largest squared row norm: the fused sweep's fp16x2 pre-filter (and with it the one-pass evaluation) is for
+            # L2-normalised rows; anything else takes the fp32 form of the two-sweep path
+            nrm2 = float(torch.maximum(xn[:n].max(), yn[:n].max()).item())
+            if one_pass and not want_top3 and hasattr(be, "eval_onepass") and nrm2 <= be.HALF_PREFILTER_NORM2_MAX:
+                import math
+                eps = be.rank_band_eps(xn, yn, X.shape[1])
+                one = {"eps": eps, "delta": 2.0 * eps + 2e-6,
+                       "shift": ONE_PASS_GAMMA * math.log(max(n / m, 1.0))}
+                # canonical c of every ground-truth pair: the one neighbour of an entity known before the sweep
+                one["c_diag"] = 1.0 - be.pair_score(X, Y, n, xn, yn, None, None, False)
+                launches += 1
             sel, selc = _sample_rows(n, m, dev)
             # Row bounds: the KT-th best of a source over a random sample of ALL targets can only be lower than its
             # KT-th best overall, so lists seeded with it lose nothing and skip their warm-up. (A sample of 8192 instead
@@ -135,32 +159,73 @@ def _align_ranks_steps(be, X, Y, xn, yn, n: int, csls_k: int, use_csls: bool, wa
             Yc, ync = Y.index_select(0, selc), yn.index_select(0, selc)
             per_r = (n + world - 1) // world
             a0, a1 = min(rank * per_r, n), min((rank + 1) * per_r, n)
-            thr_loc = torch.full((per_r,), float("-inf"), dtype=torch.float32, device=dev)
+            nrow = 3 if one is not None else 1          # rows of the exchanged block: rowthr (, lo1, hi1)
+            thr_loc = torch.full((nrow, per_r), float("-inf"), dtype=torch.float32, device=dev)
             if a1 > a0:
                 part_r = be.eval_rowtopk(X[a0:a1], Yc, xn[a0:a1], ync, a1 - a0, m)
                 _, cand_r = be.topk_merge_mean(part_r, csls_k, want_nv=False, want_cand=True)
-                thr_loc[:a1 - a0] = cand_r[:, 0] - 2e-6                # lists are ascending: [0] is the KT-th largest
-                del part_r, cand_r
+                thr_loc[0, :a1 - a0] = cand_r[:, 0] - 2e-6             # lists are ascending: [0] is the KT-th largest
                 launches += 2
+                if one is not None:
+                    lo1, hi1 = be.spec_bounds(cand_r, one["c_diag"][a0:a1].contiguous(), csls_k, one["shift"], one["delta"])
+                    thr_loc[1, :a1 - a0] = lo1
+                    thr_loc[2, :a1 - a0] = hi1
+                    launches += 1
+                del part_r, cand_r
             if world == 1:
-                rowthr = thr_loc[:n].contiguous()
+                allt = thr_loc[None]
             else:
-                allt = yield ("all_gather", thr_loc)                    # [world, per_r]
-                rowthr = allt.reshape(-1)[:n].contiguous()
-            del Yc, ync
+                allt = yield ("all_gather", thr_loc)                    # [world, nrow, per_r]
+            rowthr = allt[:, 0].reshape(-1)[:n].contiguous()
+            if one is not None:
+                one["lo1"] = allt[:, 1].reshape(-1)[:n].contiguous()
+                one["hi1"] = allt[:, 2].reshape(-1)[:n].contiguous()
+            del Yc, ync, allt
+            colthr = colb = None
+            hi2_loc = torch.full((per,), float("inf"), dtype=torch.float32, device=dev) if one is not None else None
             if ns > 0:
                 # column bounds: this rank's targets against a sample of the sources
                 Xs, xns = X.index_select(0, sel), xn.index_select(0, sel)
                 part_s = be.eval_rowtopk(Ys, Xs, yns, xns, ns, m)
                 _, cand_s = be.topk_merge_mean(part_s, csls_k, want_nv=False, want_cand=True)
                 colthr, colb = be.col_threshold(cand_s, csls_k, yns)
-                part, pidx, stream, stream_row, stream_cnt = be.eval_rowcoltopk(X, Ys, xn, yns, n, ns, colthr, colb, cap, rowthr)
+                launches += 3
+                if one is not None:
+                    one["lo2"], hi2_loc[:ns] = be.spec_bounds(cand_s, one["c_diag"][c0:c1].contiguous(), csls_k, one["shift"],
+                                                              one["delta"])
+                    launches += 1
+                del part_s, cand_s, Xs, xns
+            if one is not None:
+                if world == 1:
+                    hi2 = hi2_loc[:n]
+                else:
+                    allh = yield ("all_gather", hi2_loc)                # [world, per]
+                    hi2 = allh.reshape(-1)[:n].contiguous()
+                # relaxed rank constants (see EpiRankBand for R, R', C, C'): with nv1 - g = 2 c_ii - 1 - nv2_i (the CSLS
+                # distance of the own pair) R_i depends on the pair's COLUMN mean only, C'_j on its ROW mean only
+                slack = one["eps"] + 1e-6
+                cd = one["c_diag"]
+                one["rk_r"] = 0.25 * (2.0 * xn[:n] + 2.0 * cd - 2.0 - hi2) - slack
+                one["rk_rp"] = 0.25 * ((2.0 * xn[:n] + one["lo1"]) - 1.0) - 1e-6
+            if ns > 0:
+                if one is not None:
+                    one["rk_c"] = 0.25 * (2.0 * yns + one["lo2"]) - 1e-6
+                    one["rk_cp"] = 0.25 * (2.0 * yns + 2.0 * cd[c0:c1] - 1.0 - one["hi1"][c0:c1]) - slack
+                    key = (n, ns, csls_k, X.shape[1])
+                    rk_cap = _ONE_PASS_CAP.get(key) or round_up(ONE_PASS_STREAM_PER_TARGET * ns // max(1, be.num_sms()) + 4096, 1024)
+                    (part, pidx, stream, stream_row, stream_cnt, one["stream"], one["stream_row"], one["cnt"]) = be.eval_onepass(
+                        X, Ys, xn, yns, n, ns, colthr, colb, cap, rowthr, one["rk_r"].contiguous(), one["rk_rp"].contiguous(),
+                        one["rk_c"].contiguous(), one["rk_cp"].contiguous(), rk_cap, nrm2)
+                    one["cap_key"], one["rk_cap"] = key, rk_cap
+                else:
+                    part, pidx, stream, stream_row, stream_cnt = be.eval_rowcoltopk(X, Ys, xn, yns, n, ns, colthr, colb, cap, rowthr,
+                                                                                    nrm2)
                 col_val, col_idx, overflow = be.col_cand_reduce(stream, stream_row, stream_cnt, ns, csls_k)
                 col_bound = colthr                 # nothing below a target's threshold was ever streamed
-                launches += 7
+                launches += 4
                 if int(overflow.item()) != 0:      # a candidate stream filled up: redo the columns the classic way
                     col_val = col_idx = col_bound = None
-                del stream, stream_row, Xs, xns
+                del stream, stream_row
         elif ns > 0:
             part, pidx = be.eval_rowtopk(X, Ys, xn, yns, n, ns, want_idx=True)
             launches += 1
@@ -210,15 +275,21 @@ def _align_ranks_steps(be, X, Y, xn, yn, n: int, csls_k: int, use_csls: bool, wa
     g = be.pair_score(X, Y, n, xn, yn, nv1, nv2, use_csls)
     launches += 1
 
-    # sweep 2: rank counters
+    # rank counters: settled on the streamed candidates of the one-pass sweep when it ran, else by sweep 2
     cnt_row = torch.zeros((n,), dtype=torch.int32, device=dev)
     cnt_col_loc = torch.zeros((per,), dtype=torch.int32, device=dev)
     t3v = t3i = None
+    one_info = None
     if ns > 0:
         nv2s = nv2[c0:c1] if use_csls else None
-        t3v, t3i = be.eval_rank(X, Ys, xn, yns, nv1, nv2s, g, g[c0:c1], 0, c0, n, ns, use_csls, cnt_row, cnt_col_loc,
-                                want_top3, **kw)
-        launches += 2                                   # the sweep and the re-score of its deferred elements
+        done = False
+        if use_csls and one is not None and "stream" in one:
+            done, one_info, nl = _one_pass_ranks(be, one, X, Ys, xn, yns, nv1, nv2s, g, c0, n, ns, cnt_row, cnt_col_loc)
+            launches += nl
+        if not done:
+            t3v, t3i = be.eval_rank(X, Ys, xn, yns, nv1, nv2s, g, g[c0:c1], 0, c0, n, ns, use_csls, cnt_row, cnt_col_loc,
+                                    want_top3, **kw)
+            launches += 2                               # the sweep and the re-score of its deferred elements
     top3_idx = top3_val = None
     if want_top3:
         # each list holds the row's 4 nearest candidates (by the tensor-core score); merged here, exchanged when sharded,
@@ -246,7 +317,60 @@ def _align_ranks_steps(be, X, Y, xn, yn, n: int, csls_k: int, use_csls: bool, wa
         top3_idx, top3_val = t3i[:, :3], t3v[:, :3]
     return AlignRanks(rank_l2r, rank_r2l, nv1, nv2, g, top3_idx, top3_val, launches,
                       {"world": world, "rank": rank, "shard": (c0, c1), "rank_sweep": dict(getattr(be, "LAST_RANK_INFO", {})),
-                       "neighbourhoods": dict(getattr(be, "LAST_TOPK_INFO", {}))})
+                       "neighbourhoods": dict(getattr(be, "LAST_TOPK_INFO", {})), "one_pass": one_info})
+
+
+def _one_pass_ranks(be, one, X, Ys, xn, yns, nv1, nv2s, g, c0: int, n: int, ns: int, cnt_row, cnt_col_loc):
+    """Rank counters from the streamed candidates of the one-pass sweep. Returns (done, info, launches); done False means
+    the classic sweep 2 has to run (a stream overflowed, a guaranteed bound was violated, or too many guesses failed) —
+    the counters are zero again in that case."""
+    eps = one["eps"]
+    gs = g[c0:c0 + ns]
+    base_r = (2.0 * xn[:n] + nv1) - 1.0
+    R, Rp = 0.25 * (base_r - g), 0.25 * base_r
+    base_c = 2.0 * yns + nv2s
+    C, Cp = 0.25 * base_c, 0.25 * (base_c - gs)
+    tol = eps + 5e-7
+    row_ok = one["rk_r"] <= R - tol
+    col_ok = one["rk_cp"] <= Cp - tol
+    broken = (one["rk_rp"] > Rp).sum() + (one["rk_c"] > C).sum()       # provable bounds: never expected
+    overflow, deferred = be.rank_judge(X, Ys, xn, yns, nv1, nv2s, g, gs, 0, c0, one["stream"], one["stream_row"], one["cnt"],
+                                       R.contiguous(), Rp.contiguous(), C.contiguous(), Cp.contiguous(),
+                                       row_ok.to(torch.uint8), col_ok.to(torch.uint8), eps, cnt_row, cnt_col_loc)
+    status = torch.stack([overflow[0].to(torch.int64), (~row_ok).sum(), (~col_ok).sum(), broken, one["cnt"].max().to(torch.int64),
+                          one["cnt"].to(torch.int64).sum()]).tolist()
+    ovf, fail_r, fail_c, brk, cnt_max, streamed = (int(v) for v in status)
+    info = {"streamed": streamed, "deferred": deferred, "failed_rows": fail_r, "failed_cols": fail_c, "eps": eps,
+            "stream_cap": one["rk_cap"], "stream_max": cnt_max, "fallback": None}
+    launches = 2
+    if ovf:
+        _ONE_PASS_CAP[one["cap_key"]] = one["rk_cap"] * 4                # (the stream counters saturate) for the next evaluation
+        info["fallback"] = "rank stream overflow"
+    elif brk:
+        info["fallback"] = "a lower bound from the sample exceeded the final neighbourhood mean"
+    elif fail_r / n + fail_c / ns > ONE_PASS_RECOUNT_MAX_FRAC:
+        info["fallback"] = "too many failed guesses"
+    if info["fallback"] is not None:
+        cnt_row.zero_()
+        cnt_col_loc.zero_()
+        return False, info, launches
+    if cnt_max * 2 > one["rk_cap"]:
+        _ONE_PASS_CAP[one["cap_key"]] = round_up(int(cnt_max * 2.5) + 4096, 1024)
+    if fail_r:
+        rows = (~row_ok).nonzero().reshape(-1).to(torch.int32)
+        if fail_r <= ONE_PASS_EXHAUSTIVE_MAX:
+            be.rank_exhaustive(X, Ys, xn, yns, nv1, nv2s, g, rows, 0, c0, True, False, cnt_row, ns)
+        else:
+            cnt_row[rows.long()] = be.rank_recount_rows(X, Ys, xn, yns, nv1, nv2s, g, gs, rows, 0, c0, ns, False, eps)
+        launches += 2
+    if fail_c:
+        cols = (~col_ok).nonzero().reshape(-1).to(torch.int32)
+        if fail_c <= ONE_PASS_EXHAUSTIVE_MAX:
+            be.rank_exhaustive(Ys, X, yns, xn, nv2s, nv1, gs.contiguous(), cols, c0, 0, True, True, cnt_col_loc, n)
+        else:
+            cnt_col_loc[cols.long()] = be.rank_recount_rows(Ys, X, yns, xn, nv2s, nv1, gs.contiguous(), g, cols, c0, 0, n, True, eps)
+        launches += 2
+    return True, info, launches
 
 
 def _drive_with_torch_distributed(gen, group):
@@ -357,12 +481,15 @@ def _align_ranks_lazy(be, X, Y, xn, yn, n, csls_k, use_csls, want_top3):
 
 def align_ranks(X: torch.Tensor, Y: torch.Tensor, xn: torch.Tensor, yn: torch.Tensor, n: int, csls_k: int = 10,
                 use_csls: bool = True, want_top3: bool = False, group=None, backend=None,
-                two_sweep: bool = True, lazy: bool | None = None) -> AlignRanks:
+                two_sweep: bool = True, lazy: bool | None = None, one_pass: bool | None = None) -> AlignRanks:
     """Fused evaluation of n aligned pairs (x_i <-> y_i).
 
     X, Y : bf16 operands [>=n, Dpad] from ops.prep_bf16; xn, yn : their squared norms [n].
     With `group` (a torch.distributed process group, NCCL on GPUs) every rank holds all of X and Y and sweeps
-    only its own shard of the targets."""
+    only its own shard of the targets.
+    one_pass (default ONE_PASS; n >= TWO_SWEEP_MIN_N with CSLS and without the prediction file): rank verdicts are taken
+    on candidates streamed out of the single main sweep instead of a second sweep (info["one_pass"] reports the volume,
+    the guesses that failed and any fallback); the result is the same bit for bit."""
     if use_csls and not 1 <= csls_k <= KT:
         raise SnagError(f"csls_k={csls_k} unsupported: the fused CSLS path keeps {KT} candidates per row")
     if use_csls and csls_k > n:
@@ -386,7 +513,7 @@ def align_ranks(X: torch.Tensor, Y: torch.Tensor, xn: torch.Tensor, yn: torch.Te
             return res                                   # else: an assumption did not hold — take the synchronising path
     if float(torch.maximum(xn[:n].max(), yn[:n].max()).item()) > 8.0:
         raise SnagError("align_ranks expects L2-normalised rows (evaluate_alignment(normalize=True))")
-    gen = _align_ranks_steps(be, X, Y, xn, yn, n, csls_k, use_csls, want_top3, world, rank, two_sweep)
+    gen = _align_ranks_steps(be, X, Y, xn, yn, n, csls_k, use_csls, want_top3, world, rank, two_sweep, one_pass=one_pass)
     if world == 1:
         try:
             next(gen)

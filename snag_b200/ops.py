@@ -219,7 +219,11 @@ def col_threshold(cand: torch.Tensor, k: int, yn: torch.Tensor):
     return colthr, colb
 
 
-def eval_rowcoltopk(X, Y, xn, yn, n1: int, n2: int, colthr, colb, cta_cap: int, rowthr: torch.Tensor | None = None):
+HALF_PREFILTER_NORM2_MAX = 1.05    # SNAG_HALF_PREFILTER_NORM2_MAX of the library
+
+
+def eval_rowcoltopk(X, Y, xn, yn, n1: int, n2: int, colthr, colb, cta_cap: int, rowthr: torch.Tensor | None = None,
+                    norm2_max: float | None = None):
     """One sweep for both CSLS directions: returns (row candidate lists [n_lists, n1, KT], their columns (int32, same
     shape), per-CTA candidate streams int64 [n_ctas, cta_cap] (low word column, high word c bits), the row of every
     stream entry int32 [n_ctas, cta_cap], stream_cnt int32 [n_ctas])."""
@@ -241,9 +245,140 @@ def eval_rowcoltopk(X, Y, xn, yn, n1: int, n2: int, colthr, colb, cta_cap: int, 
     stream_row = torch.empty((n_ctas, cta_cap), dtype=torch.int32, device=X.device)
     stream_cnt = torch.zeros((n_ctas,), dtype=torch.int32, device=X.device)
     with _SweepTimer("sim_kernel<EpiRowColTopK>", n1, n2):
+        if norm2_max is None:
+            norm2_max = float(torch.maximum(xn.max(), yn.max()).item())
         call("snag_eval_rowcoltopk", ptr(X), ptr(Y), ptr(xn), ptr(yn), n1, n2, X.shape[1], ptr(part), ptr(pidx), ptr(rowthr),
-             ptr(colthr), ptr(colb), ptr(stream), ptr(stream_row), ptr(stream_cnt), cta_cap, current_stream())
+             ptr(colthr), ptr(colb), ptr(stream), ptr(stream_row), ptr(stream_cnt), cta_cap, float(norm2_max), current_stream())
     return part, pidx, stream, stream_row, stream_cnt
+
+
+def spec_bounds(cand: torch.Tensor, cdiag: torch.Tensor, k: int, shift: float, delta: float):
+    """(lo, hi) of every entity's CSLS neighbourhood mean from its merged sample list [n, KT] and the canonical c of
+    its own pair (see snag_spec_bounds): lo is a guaranteed lower bound, hi an extrapolated guess."""
+    _need(cand, torch.float32, "cand", 2)
+    _need(cdiag, torch.float32, "cdiag", 1)
+    n = cand.shape[0]
+    if cand.shape[1] != KT or cdiag.numel() != n:
+        raise ValueError("cand must be [n, SNAG_KT] and cdiag [n]")
+    lo = torch.empty((n,), dtype=torch.float32, device=cand.device)
+    hi = torch.empty((n,), dtype=torch.float32, device=cand.device)
+    call("snag_spec_bounds", ptr(cand), n, k, ptr(cdiag), float(shift), float(delta), ptr(lo), ptr(hi), current_stream())
+    return lo, hi
+
+
+def eval_onepass(X, Y, xn, yn, n1: int, n2: int, colthr, colb, cta_cap: int, rowthr, rk_r, rk_rp, rk_c, rk_cp, rk_cap: int,
+                 norm2_max: float | None = None):
+    """eval_rowcoltopk that also streams the rank candidates (snag_eval_onepass). Returns the five outputs of
+    eval_rowcoltopk followed by (rk_stream int64 [n_ctas, rk_cap], rk_stream_row int32 [n_ctas, rk_cap], rk_cnt int32 [n_ctas])."""
+    _check_operand(X, "X")
+    _check_operand(Y, "Y")
+    for name, t, cnt in (("xn", xn, n1), ("yn", yn, n2), ("colthr", colthr, n2), ("colb", colb, n2), ("rowthr", rowthr, n1),
+                         ("rk_r", rk_r, n1), ("rk_rp", rk_rp, n1), ("rk_c", rk_c, n2), ("rk_cp", rk_cp, n2)):
+        _need(t, torch.float32, name, 1)
+        if t.numel() < cnt:
+            raise ValueError(f"{name} needs {cnt} entries")
+    _, nch = sim_plan(n1, n2, X.shape[1])
+    n_ctas = num_sms()
+    dev = X.device
+    part = torch.empty((nch, n1, KT), dtype=torch.float32, device=dev)
+    pidx = torch.empty((nch, n1, KT), dtype=torch.int32, device=dev)
+    stream = torch.empty((n_ctas, cta_cap), dtype=torch.int64, device=dev)
+    stream_row = torch.empty((n_ctas, cta_cap), dtype=torch.int32, device=dev)
+    stream_cnt = torch.zeros((n_ctas,), dtype=torch.int32, device=dev)
+    rk_stream = torch.empty((n_ctas, rk_cap), dtype=torch.int64, device=dev)
+    rk_stream_row = torch.empty((n_ctas, rk_cap), dtype=torch.int32, device=dev)
+    rk_cnt = torch.zeros((n_ctas,), dtype=torch.int32, device=dev)
+    if norm2_max is None:
+        norm2_max = float(torch.maximum(xn.max(), yn.max()).item())
+    with _SweepTimer("sim_kernel<EpiOnePass>", n1, n2):
+        call("snag_eval_onepass", ptr(X), ptr(Y), ptr(xn), ptr(yn), n1, n2, X.shape[1], ptr(part), ptr(pidx), ptr(rowthr),
+             ptr(colthr), ptr(colb), ptr(stream), ptr(stream_row), ptr(stream_cnt), cta_cap, ptr(rk_r), ptr(rk_rp), ptr(rk_c),
+             ptr(rk_cp), ptr(rk_stream), ptr(rk_stream_row), ptr(rk_cnt), rk_cap, float(norm2_max), current_stream())
+    return part, pidx, stream, stream_row, stream_cnt, rk_stream, rk_stream_row, rk_cnt
+
+
+def rank_judge(X, Y, xn, yn, nv1, nv2, g_row, g_col, row_gid0: int, col_gid0: int, rk_stream, rk_stream_row, rk_cnt,
+               R, Rp, C, Cp, row_ok, col_ok, eps: float, cnt_row: torch.Tensor, cnt_col: torch.Tensor):
+    """Settle the streamed rank candidates of eval_onepass against the final constants (snag_rank_judge) and re-score
+    the elements inside the band canonically (snag_band_rescore); counts are accumulated into cnt_row / cnt_col.
+    Returns (overflow int32[1] device tensor — a rank stream was full, the counts are incomplete —, deferred count)."""
+    _need(rk_stream, torch.int64, "rk_stream", 2)
+    _need(rk_stream_row, torch.int32, "rk_stream_row", 2)
+    _need(rk_cnt, torch.int32, "rk_cnt", 1)
+    for name, t in (("R", R), ("Rp", Rp), ("C", C), ("Cp", Cp)):
+        _need(t, torch.float32, name, 1)
+    _need(row_ok, torch.uint8, "row_ok", 1)
+    _need(col_ok, torch.uint8, "col_ok", 1)
+    dev = X.device
+    n_ctas, rk_cap = rk_stream.shape
+    st = current_stream()
+    overflow = torch.zeros((1,), dtype=torch.int32, device=dev)
+    cap = max(RANK_BAND_MIN_CAP, RANK_BAND_PER_ROW * (R.numel() + C.numel()))
+    row_save, col_save = cnt_row.clone(), cnt_col.clone()
+    while True:
+        band = torch.empty((cap,), dtype=torch.int64, device=dev)
+        band_cnt = torch.zeros((1,), dtype=torch.int32, device=dev)
+        call("snag_rank_judge", ptr(rk_stream), ptr(rk_stream_row), ptr(rk_cnt), n_ctas, rk_cap, ptr(R), ptr(Rp), ptr(C), ptr(Cp),
+             ptr(row_ok), ptr(col_ok), float(eps), row_gid0, col_gid0, ptr(cnt_row), ptr(cnt_col), ptr(band), ptr(band_cnt), cap,
+             ptr(overflow), st)
+        call("snag_band_rescore", ptr(X), ptr(Y), X.shape[1], ptr(xn), ptr(yn), ptr(nv1), ptr(nv2), ptr(g_row), ptr(g_col),
+             row_gid0, col_gid0, 1, ptr(band), ptr(band_cnt), cap, ptr(cnt_row), ptr(cnt_col), st)
+        deferred = int(band_cnt.item()) & 0xFFFFFFFF
+        if deferred <= cap:
+            return overflow, deferred
+        cnt_row.copy_(row_save)
+        cnt_col.copy_(col_save)
+        cap = round_up(deferred + deferred // 8, 1024)
+
+
+def rank_exhaustive(A, B, an, bn, nva, nvb, g, rows: torch.Tensor, a_gid0: int, b_gid0: int, use_csls: bool, swapped: bool,
+                    cnt: torch.Tensor, n_b: int | None = None) -> None:
+    """cnt[row] += canonical rank count of every listed row of A against the first n_b rows of B (snag_rank_exhaustive)."""
+    _check_operand(A, "A")
+    _check_operand(B, "B")
+    _need(rows, torch.int32, "rows", 1)
+    _need(cnt, torch.int32, "cnt", 1)
+    if rows.numel() == 0:
+        return
+    call("snag_rank_exhaustive", ptr(A), ptr(B), A.shape[1], B.shape[0] if n_b is None else n_b, ptr(an), ptr(bn), ptr(nva),
+         ptr(nvb), ptr(g), ptr(rows), rows.numel(), a_gid0, b_gid0, int(use_csls), int(swapped), ptr(cnt), current_stream())
+
+
+def rank_recount_rows(A, B, an, bn, nva, nvb, g_a, g_b, rows: torch.Tensor, a_gid0: int, b_gid0: int, n_b: int,
+                      swapped: bool, eps: float) -> torch.Tensor:
+    """Rank counts of the listed rows of A against the first n_b rows of B by a tensor-core sweep over the gathered
+    sub-panel (snag_eval_rank_band_rows + snag_band_rescore_rows): the recount of entities whose one-pass guess failed.
+    A = sources and B = targets (swapped False: l2r ranks of the listed sources), or A = targets and B = sources
+    (swapped True: r2l ranks of the listed targets). an / nva / g_a are indexed like A, bn / nvb / g_b like B.
+    Returns int32 [len(rows)]."""
+    _check_operand(A, "A")
+    _check_operand(B, "B")
+    _need(rows, torch.int32, "rows", 1)
+    f = rows.numel()
+    dev = A.device
+    cnt = torch.zeros((f,), dtype=torch.int32, device=dev)
+    if f == 0:
+        return cnt
+    idx = rows.long()
+    Af = A.index_select(0, idx)
+    anf, nvaf, gf = an.index_select(0, idx), nva.index_select(0, idx), g_a.index_select(0, idx)
+    gids = (rows + a_gid0).contiguous()
+    scratch = torch.zeros((n_b,), dtype=torch.int32, device=dev)
+    st = current_stream()
+    cap = max(RANK_BAND_MIN_CAP, RANK_BAND_PER_ROW * (f + n_b))
+    while True:
+        band = torch.empty((cap,), dtype=torch.int64, device=dev)
+        band_cnt = torch.zeros((1,), dtype=torch.int32, device=dev)
+        with _SweepTimer("sim_kernel<EpiRank>[recount]", f, n_b):
+            call("snag_eval_rank_band_rows", ptr(Af), ptr(B), ptr(anf), ptr(bn), ptr(nvaf), ptr(nvb), ptr(gf), ptr(g_b), ptr(gids),
+                 b_gid0, f, n_b, A.shape[1], 1, float(eps), ptr(cnt), ptr(scratch), ptr(band), ptr(band_cnt), cap, st)
+        call("snag_band_rescore_rows", ptr(Af), ptr(B), A.shape[1], ptr(anf), ptr(bn), ptr(nvaf), ptr(nvb), ptr(gf), ptr(g_b),
+             ptr(gids), b_gid0, 1, int(swapped), ptr(band), ptr(band_cnt), cap, ptr(cnt), ptr(scratch), st)
+        deferred = int(band_cnt.item()) & 0xFFFFFFFF
+        if deferred <= cap:
+            return cnt
+        cnt.zero_()
+        cap = round_up(deferred + deferred // 8, 1024)
 
 
 def col_cand_reduce(stream: torch.Tensor, stream_row: torch.Tensor, stream_cnt: torch.Tensor, n_cols: int, k: int):
@@ -416,6 +551,13 @@ def _error_scale(xn: torch.Tensor, yn: torch.Tensor, dpad: int) -> float:
     ||x|| ||y|| present (align_ranks only lets nearly-unit rows through)."""
     norm = float(torch.sqrt(xn.max() * yn.max()).item())
     return tc_margin(dpad, norm)
+
+
+def rank_band_eps(xn: torch.Tensor, yn: torch.Tensor, dpad: int) -> float:
+    """Half-width of the deferral band (in s) for these operands — what eval_rank uses."""
+    return RANK_BAND_EPS * _error_scale(xn, yn, dpad)
+
+
 RANK_BAND_MIN_CAP = 1 << 20
 RANK_BAND_PER_ROW = 16         # initial list capacity per evaluated row + column
 RANK_BAND_MAX_CAP = 1 << 28    # beyond this many deferred elements (2 GB list) the in-kernel chain takes over

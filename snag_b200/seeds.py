@@ -54,7 +54,8 @@ def topk_similarity_entries(left_f: torch.Tensor, right_f: torch.Tensor, K: int,
         cnt = stream_cnt.to(torch.int64)
         if int(cnt.max().item()) <= cap:
             break
-        cap = _cuda_ops.round_up(int(cnt.max().item()) + 1024, 1024)               # a stream filled up: size it and redo
+        cap *= 4                                                                   # a stream filled up (its counter saturates
+                                                                                   # just above the capacity): enlarge and redo
         if cap * stream.shape[0] * 12 > (32 << 30):
             raise SnagError("topk_similarity_entries: too many entries above the threshold (degenerate similarities)")
     keep = torch.arange(stream.shape[1], device=dev)[None, :] < cnt[:, None]

@@ -75,32 +75,101 @@ def test_baseline_config_against_oracle(cuda_device, name, n, d, k, csls):
 
 
 def test_two_sweep_size_against_oracle(cuda_device):
-    """n just above TWO_SWEEP_MIN_N at the headline width D = 1200, k = 10: the path bench.py's c4 workloads run."""
+    """n just above TWO_SWEEP_MIN_N at the headline width D = 1200, k = 10: the paths bench.py's c4 workloads run — the
+    one-pass evaluation (default) and the two-sweep evaluation — against the oracle on every pair."""
     import psutil
     oracle.set_threads()
     n, d, k = evaluate.TWO_SWEEP_MIN_N + 1, 1200, 10
     assert evaluate.two_sweep_plan(n, k) is not None
     x, y = _clustered(n, d, 8.0, 3409)
     X, Y, xn, yn = _prep(x, y, cuda_device)
-    sweeps = []
-    ops.SWEEP_EVENT_SINK = sweeps
-    try:
-        res = evaluate.align_ranks(X, Y, xn, yn, n, k, True)
-    finally:
-        ops.SWEEP_EVENT_SINK = None
-    kinds = {nm for nm, *_ in sweeps}
-    assert "sim_kernel<EpiRowColTopK>" in kinds      # the two-sweep path really ran (one sweep for both directions)
     # the oracle: materialised when the n x n fp32 matrix fits comfortably in host memory (one pass over the dot
     # products), streaming otherwise (two passes)
     if psutil.virtual_memory().available > 3 * 4 * n * n:
         ref = oracle.align_eval(x, y, True, k)
     else:
         ref = oracle.align_eval_stream(x, y, True, k, 2048)
-    _assert_equal_to_oracle(res, ref, True)
-    # the same through 4 simulated ranks
+    for one_pass, kernel in ((True, "sim_kernel<EpiOnePass>"), (False, "sim_kernel<EpiRowColTopK>")):
+        sweeps = []
+        ops.SWEEP_EVENT_SINK = sweeps
+        try:
+            res = evaluate.align_ranks(X, Y, xn, yn, n, k, True, one_pass=one_pass)
+        finally:
+            ops.SWEEP_EVENT_SINK = None
+        kinds = [nm for nm, *_ in sweeps]
+        assert kernel in kinds                           # one sweep for both CSLS directions
+        _assert_equal_to_oracle(res, ref, True)
+        if one_pass:
+            info = res.info["one_pass"]
+            assert info["fallback"] is None and "sim_kernel<EpiRank>" not in kinds, info    # no second sweep
+            assert 0 < info["streamed"] < 2e-3 * n * n, info
+            print(f"\n[one-pass] n={n}: streamed {info['streamed']} ({info['streamed'] / n / n:.2e} of the pairs), "
+                  f"deferred {info['deferred']}, failed guesses rows/cols {info['failed_rows']}/{info['failed_cols']}")
+        # the same through 4 simulated ranks
+        many = evaluate.simulate_sharded(
+            lambda r: evaluate._align_ranks_steps(ops, X, Y, xn, yn, n, k, True, False, 4, r, one_pass=one_pass), 4)
+        _assert_equal_to_oracle(many[1], ref, True)
+        if one_pass:
+            assert all(mr.info["one_pass"]["fallback"] is None for mr in many)
+
+
+def test_one_pass_fallbacks_are_exact(cuda_device, monkeypatch):
+    """The one-pass evaluation speculates on upper bounds of the neighbourhood means; whatever happens to the guesses the
+    ranks must not change: (a) guesses that are far too low -> the failed entities are recounted exhaustively,
+    (b) more failures than the exhaustive budget -> classic sweep 2, (c) a rank stream that overflows -> classic sweep 2
+    and a larger stream next time. Compared bit for bit with the two-sweep evaluation."""
+    n, d, k = evaluate.TWO_SWEEP_MIN_N + 777, 320, 10
+    g = torch.Generator(device="cuda").manual_seed(12)
+    centres = torch.randn((64, d), generator=g, device="cuda")
+    x = torch.randn((n, d), generator=g, device="cuda") + centres[torch.randint(0, 64, (n,), generator=g, device="cuda")]
+    y = x + 3.0 * torch.randn((n, d), generator=g, device="cuda")
+    X, xn = ops.prep_bf16(x, None, True)
+    Y, yn = ops.prep_bf16(y, None, True)
+    del x, y
+    ref = evaluate.align_ranks(X, Y, xn, yn, n, k, True, one_pass=False)
+    assert ref.info["one_pass"] is None
+
+    def same(res):
+        return (torch.equal(res.rank_l2r, ref.rank_l2r) and torch.equal(res.rank_r2l, ref.rank_r2l) and
+                torch.equal(res.nv1, ref.nv1) and torch.equal(res.nv2, ref.nv2) and torch.equal(res.g, ref.g))
+
+    a = evaluate.align_ranks(X, Y, xn, yn, n, k, True, one_pass=True)
+    assert same(a) and a.info["one_pass"]["fallback"] is None, a.info["one_pass"]
+    # (a) no extrapolation at all: the guess is the sample's own mean -> many entities fail and are recounted by
+    # tensor-core sweeps over the gathered sub-panels
+    monkeypatch.setattr(evaluate, "ONE_PASS_GAMMA", -0.02)
+    monkeypatch.setattr(evaluate, "ONE_PASS_RECOUNT_MAX_FRAC", 10.0)
+    b = evaluate.align_ranks(X, Y, xn, yn, n, k, True, one_pass=True)
+    ib = b.info["one_pass"]
+    assert ib["fallback"] is None and ib["failed_rows"] > 32 and ib["failed_cols"] > 32, ib
+    assert same(b)
+    # ... or, when they are few (here: forced), exhaustively with fp64 dot products
+    monkeypatch.setattr(evaluate, "ONE_PASS_EXHAUSTIVE_MAX", 1 << 30)
+    b2 = evaluate.align_ranks(X, Y, xn, yn, n, k, True, one_pass=True)
+    assert b2.info["one_pass"]["fallback"] is None and same(b2)
+    monkeypatch.setattr(evaluate, "ONE_PASS_EXHAUSTIVE_MAX", 32)
+    # sharded (3 simulated ranks) with failing guesses
     many = evaluate.simulate_sharded(
-        lambda r: evaluate._align_ranks_steps(ops, X, Y, xn, yn, n, k, True, False, 4, r), 4)
-    _assert_equal_to_oracle(many[1], ref, True)
+        lambda r: evaluate._align_ranks_steps(ops, X, Y, xn, yn, n, k, True, False, 3, r, one_pass=True), 3)
+    assert all(same(mr) for mr in many)
+    # (b) recounting would cost more than sweep 2 -> sweep 2
+    monkeypatch.setattr(evaluate, "ONE_PASS_RECOUNT_MAX_FRAC", 0.0)
+    c = evaluate.align_ranks(X, Y, xn, yn, n, k, True, one_pass=True)
+    assert c.info["one_pass"]["fallback"] == "too many failed guesses" and same(c)
+    # (c) stream overflow -> sweep 2, and the capacity is raised for the next evaluations of this shape
+    monkeypatch.setattr(evaluate, "ONE_PASS_GAMMA", 1.5)
+    monkeypatch.setattr(evaluate, "ONE_PASS_RECOUNT_MAX_FRAC", 0.8)
+    evaluate._ONE_PASS_CAP.clear()
+    evaluate._ONE_PASS_CAP[(n, n, k, X.shape[1])] = 64               # far too small on purpose
+    e = evaluate.align_ranks(X, Y, xn, yn, n, k, True, one_pass=True)
+    assert e.info["one_pass"]["fallback"] == "rank stream overflow" and same(e), e.info["one_pass"]
+    for _ in range(8):
+        f = evaluate.align_ranks(X, Y, xn, yn, n, k, True, one_pass=True)
+        assert same(f)
+        if f.info["one_pass"]["fallback"] is None:
+            break
+    assert f.info["one_pass"]["fallback"] is None, f.info["one_pass"]
+    evaluate._ONE_PASS_CAP.clear()
 
 
 def _adversarial_rows(n, d, seed):

@@ -392,7 +392,7 @@ def test_graphed_evaluation_replays(cuda_device):
         emb = rng.randn(N, d).astype(np.float32)
         left = rng.permutation(N // 2)[:n]
         right = N // 2 + rng.permutation(N // 2)[:n]
-        emb[right] = emb[left] + 0.9 * rng.randn(n, d).astype(np.float32)
+        emb[right] = emb[left] + 5.0 * rng.randn(n, d).astype(np.float32)   # noisy enough that the three MRRs differ
         args = (torch.from_numpy(emb).to(cuda_device), torch.from_numpy(left).to(cuda_device), torch.from_numpy(right).to(cuda_device))
         g = evaluate.evaluate_alignment(*args, csls=True, csls_k=10, want_top3=True, graph=True)
         e = evaluate.evaluate_alignment(*args, csls=True, csls_k=10, want_top3=True, graph=False)
