@@ -400,8 +400,10 @@ def eval_bench(ctx, args, name):
     dt = ctx.max_over_ranks((time.perf_counter() - t0) / n_e2e)
     out["e2e"] = {"value": n * n / dt, "unit": UNIT, "h2d_bytes_per_step": int(2 * (c1 - c0) * d * 4),
                   "d2h_bytes_per_step": int(2 * n * 4), "ms_per_step": dt * 1e3, "steps": n_e2e,
+                  "streamed": bool(o.get("streamed")),
                   "note": "per rank: H2D of its slice of both fp32 tables from pinned memory (+ NVLink all-gather of the bf16 "
-                          "operands when sharded), evaluation, D2H of both rank vectors, host Hits/MR/MRR"}
+                          "operands when sharded), evaluation, D2H of both rank vectors, host Hits/MR/MRR; on one GPU the "
+                          "transfer is chunked and the prologue + sample pre-passes run on the chunks as they arrive"}
     m = o["l2r"]
     out["quality"] = {"hits@1_l2r": float(m.acc[0]), "hits@10_l2r": float(m.acc[1]), "mrr_l2r": m.mrr}
     del host, o

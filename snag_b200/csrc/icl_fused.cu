@@ -21,8 +21,12 @@
 //                                 64 d-elements x 8 rows j, LBO = k-block stride, SBO = 1024 B)
 //     dZ [128 x Dpad] fp32 accumulator (TMEM, 320 columns) -> global, one partial per column split
 //
-// TMEM: S 2 x 64 + P 2 x 32 + dZ 320 = 512 columns. Shared memory: X 80 KB + Y 3 x 40 KB. The issue order of the single
-// MMA thread — MMA1(t), then MMA2(t-1) — keeps the tensor pipe busy while the epilogue works on tile t.
+// TMEM: S 2 x 64 + P 2 x 32 + dZ 320 = 512 columns. Shared memory: X 80 KB + Y 3 x 40 KB (a 128-column tile would halve
+// the number of MMA1 instructions, but two of its Y tiles and X do not fit in 227 KB).
+// Roles: TMA producer warp; TWO issuing warps — one for MMA1, running ahead as far as the S stages and the Y ring
+// allow, one for MMA2, following the epilogue — so that neither product waits behind the other's barriers in a single
+// instruction stream; and two PAIRS of epilogue warpgroups that take alternate tiles (pair g owns S stage g and P
+// buffer g), so that two tiles are always inside the TMEM-read -> exp2 -> pack -> TMEM-write chain.
 // Several problems (the calls of one step share B) are batched into one launch so that B = 3500 fills the machine.
 #include <mutex>
 #include "common.cuh"
@@ -40,9 +44,15 @@ constexpr int FB_YKB_BYTES = FB_BN * FB_BK * 2;              // 8 KB per k-block
 constexpr int FB_X_BYTES = FB_MAX_KB * FB_XKB_BYTES;         // 80 KB
 constexpr int FB_Y_BYTES = FB_MAX_KB * FB_YKB_BYTES;         // 40 KB per ring slot
 constexpr int FB_BAR_BYTES = 256;
-constexpr int FB_SMEM_BYTES = 1024 + FB_X_BYTES + FB_YBUFS * FB_Y_BYTES + FB_BAR_BYTES;
-constexpr int FB_EPI_THREADS = 256;            // 2 warpgroups: WG w owns columns [32 w, 32 w + 32) of every tile
+constexpr int FB_PAIR_THREADS = 256;           // a PAIR of warpgroups consumes one tile: WG h of the pair owns columns [32 h, 32 h + 32)
+constexpr int FB_EPI_PAIRS = 2;                // pair g takes every other tile (those that land in S stage g / P buffer g), so two
+                                               // tiles are in the epilogue at any time: its latency chain (TMEM read -> exp2 -> pack ->
+                                               // TMEM write, ~2 800 clocks per tile with one pair — ncu: tensor pipe 52 % busy, issue
+                                               // slots 26 %) is overlapped with itself instead of pacing the MMAs
+constexpr int FB_EPI_THREADS = FB_EPI_PAIRS * FB_PAIR_THREADS;
 constexpr int FB_THREADS = FB_EPI_THREADS + 96;
+constexpr int FB_COEF_FLOATS = FB_EPI_PAIRS * 2 * FB_BN;     // per pair: the tile's column coefficients, double-buffered
+constexpr int FB_SMEM_BYTES = 1024 + FB_X_BYTES + FB_YBUFS * FB_Y_BYTES + FB_BAR_BYTES + FB_COEF_FLOATS * 4;
 constexpr int FB_TMEM_S = 0;                   // 2 stages x 64 fp32 columns
 constexpr int FB_TMEM_P = 128;                 // 2 buffers x 32 columns (64 bf16 per lane)
 constexpr int FB_TMEM_DZ = 192;                // 320 fp32 columns
@@ -128,6 +138,23 @@ __device__ __forceinline__ bool fb_tile_valid(const FbParams& p, int t) {
   return idx0 < p.B;
 }
 
+// The valid tiles of a part are its first ceil(B / 64); of a unit's tiles [t0, t1) the valid ones are therefore two
+// contiguous runs (one per part). FbValid enumerates them: n valid tiles, the j-th being tile(j).
+struct FbValid {
+  int lo0, n0, lo1, n;
+  __device__ __forceinline__ int tile(int j) const { return j < n0 ? lo0 + j : lo1 + (j - n0); }
+};
+__device__ __forceinline__ FbValid fb_valid_tiles(const FbParams& p, int t0, int t1) {
+  const int tpp = p.Bp / FB_BN;                              // tiles per part
+  const int nvp = (p.B + FB_BN - 1) / FB_BN;                 // valid tiles per part
+  FbValid v;
+  v.lo0 = t0;
+  v.n0 = max(0, min(t1, nvp) - v.lo0);
+  v.lo1 = max(t0, tpp);
+  v.n = v.n0 + max(0, min(t1, tpp + nvp) - v.lo1);
+  return v;
+}
+
 __global__ void __launch_bounds__(FB_THREADS, 1) icl_bwd_fused_kernel(const __grid_constant__ FbParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -144,7 +171,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) icl_bwd_fused_kernel(const __gr
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int cwarp = warp - FB_EPI_THREADS / 32;       // 0 = TMA producer, 1 = UMMA issuer, 2 = TMEM allocator; < 0: epilogue
+  const int cwarp = warp - FB_EPI_THREADS / 32;       // 0 = TMA producer, 1 = UMMA issuer of S, 2 = TMEM allocator + UMMA issuer of dZ; < 0: epilogue
 
   if (cwarp == 1 && lane == 0) {
     mbar_init(bar(0), 1);
@@ -152,8 +179,8 @@ __global__ void __launch_bounds__(FB_THREADS, 1) icl_bwd_fused_kernel(const __gr
     for (int i = 0; i < FB_YBUFS; ++i) { mbar_init(bar(2 + i), 1); mbar_init(bar(5 + i), 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar(8 + i), 1);
-      mbar_init(bar(10 + i), FB_EPI_THREADS);
-      mbar_init(bar(12 + i), FB_EPI_THREADS);
+      mbar_init(bar(10 + i), FB_PAIR_THREADS);            // S stage i / P buffer i belong to epilogue pair i
+      mbar_init(bar(12 + i), FB_PAIR_THREADS);
       mbar_init(bar(14 + i), 1);
     }
     mbar_init(bar(16), 1);
@@ -202,51 +229,21 @@ __global__ void __launch_bounds__(FB_THREADS, 1) icl_bwd_fused_kernel(const __gr
       }
     }
   } else if (cwarp == 1) {
-    // ------------------------------------------------------------------ UMMA issuer
+    // ------------------------------------------------------------------ UMMA issuer 1: S_t = X . Y_t^T
+    // Two issuing warps: a 128x64x16 MMA occupies the tensor pipe for only 32-64 clocks, so 28 of them per tile plus
+    // the barrier waits of BOTH products were more than one thread could issue in a tile's time. This warp runs ahead
+    // as far as the S stages and the Y ring allow; the second one (below) follows the epilogue.
     const uint32_t leader = elect_one_sync();
     const uint32_t idesc1 = make_idesc_bf16(FB_BM, FB_BN);
-    // dZ is up to 320 columns wide, a UMMA at most 256: two instructions of 192 + 128 rather than 256 + 64 — a 64-wide
-    // instruction keeps the tensor pipe busy for 32 clocks but occupies it for about twice that
-    const int n_lo = Dpad <= 256 ? Dpad : 192;
-    const int n_hi = Dpad - n_lo;                            // 0 or 128
-    const uint32_t idesc2_lo = make_idesc_bf16_bmn(FB_BM, n_lo);
-    const uint32_t idesc2_hi = make_idesc_bf16_bmn(FB_BM, n_hi > 0 ? n_hi : 16);
-    uint32_t xph = 0, yb = 0, yph = 0, sb = 0, sph = 0, pb = 0, pph = 0, dzph = 0;
+    uint32_t xph = 0, yb = 0, yph = 0, sb = 0, sph = 0;
     for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
       const FbUnit q = fb_decode(p, u);
-      bool any = false;
-      for (int t = q.t0; t < q.t1; ++t) any |= fb_tile_valid(p, t);
-      if (!any) continue;
+      const FbValid vt = fb_valid_tiles(p, q.t0, q.t1);
+      if (vt.n == 0) continue;
       mbar_wait(bar(0), xph);                                // X landed
       xph ^= 1;
       tc_fence_after();
-      bool have_prev = false, first_mma2 = true;
-      uint32_t prev_yb = 0, prev_pb = 0, prev_pph = 0;
-      auto issue_mma2 = [&]() {
-        mbar_wait(bar(12 + prev_pb), prev_pph);              // P of the previous tile is in TMEM
-        if (first_mma2) mbar_wait(bar(17), dzph ^ 1);        // the epilogue has read the previous unit's dZ
-        tc_fence_after();
-        if (leader) {
-          const uint32_t ytile = y_base + prev_yb * FB_Y_BYTES;
-#pragma unroll
-          for (int ks = 0; ks < FB_BN / 16; ++ks) {
-            const uint32_t a_tmem = tmem_base + FB_TMEM_P + prev_pb * 32 + ks * 8;
-            // 16 rows j of the tile = 2 groups of 8 rows = 2048 B further along K
-            const uint64_t bdesc = make_sdesc_mn128(ytile + ks * 2048, FB_YKB_BYTES);
-            const uint32_t acc = (first_mma2 && ks == 0) ? 0u : 1u;
-            umma_bf16_ts(tmem_base + FB_TMEM_DZ, a_tmem, bdesc, idesc2_lo, acc);
-            if (n_hi > 0)
-              umma_bf16_ts(tmem_base + FB_TMEM_DZ + n_lo, a_tmem,
-                           bdesc + static_cast<uint64_t>(((n_lo / FB_BK) * FB_YKB_BYTES) >> 4), idesc2_hi, acc);
-          }
-          umma_commit(bar(5 + prev_yb));                      // Y slot free
-          umma_commit(bar(14 + prev_pb));                     // P buffer free
-        }
-        __syncwarp();
-        first_mma2 = false;
-      };
-      for (int t = q.t0; t < q.t1; ++t) {
-        if (!fb_tile_valid(p, t)) continue;
+      for (int j = 0; j < vt.n; ++j) {
         mbar_wait(bar(2 + yb), yph);                         // Y_t landed
         mbar_wait(bar(10 + sb), sph ^ 1);                    // accumulator stage drained by the epilogue
         tc_fence_after();
@@ -262,28 +259,69 @@ __global__ void __launch_bounds__(FB_THREADS, 1) icl_bwd_fused_kernel(const __gr
           umma_commit(bar(8 + sb));                           // S_t complete -> epilogue
         }
         __syncwarp();
-        if (have_prev) issue_mma2();
-        have_prev = true;
-        prev_yb = yb; prev_pb = pb; prev_pph = pph;
         if (++yb == FB_YBUFS) { yb = 0; yph ^= 1; }
         if (++sb == 2) { sb = 0; sph ^= 1; }
-        if (++pb == 2) { pb = 0; pph ^= 1; }
       }
       if (leader) umma_commit(bar(1));                        // every MMA1 of the unit has read X
       __syncwarp();
-      issue_mma2();
+    }
+  } else if (cwarp == 2) {
+    // ------------------------------------------------------------------ UMMA issuer 2: dZ += P_t . Y_t
+    const uint32_t leader = elect_one_sync();
+    // dZ is up to 320 columns wide, a UMMA at most 256: two instructions of 192 + 128 rather than 256 + 64 — a 64-wide
+    // instruction keeps the tensor pipe busy for 32 clocks but occupies it for about twice that
+    const int n_lo = Dpad <= 256 ? Dpad : 192;
+    const int n_hi = Dpad - n_lo;                            // 0 or 128
+    const uint32_t idesc2_lo = make_idesc_bf16_bmn(FB_BM, n_lo);
+    const uint32_t idesc2_hi = make_idesc_bf16_bmn(FB_BM, n_hi > 0 ? n_hi : 16);
+    uint32_t yb = 0, yph = 0, pb = 0, pph = 0, dzph = 0;
+    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+      const FbUnit q = fb_decode(p, u);
+      const FbValid vt = fb_valid_tiles(p, q.t0, q.t1);
+      if (vt.n == 0) continue;
+      for (int j = 0; j < vt.n; ++j) {
+        mbar_wait(bar(12 + pb), pph);                        // P_t is in TMEM (hence S_t was complete and Y_t had landed)
+        mbar_wait(bar(2 + yb), yph);                         // this thread's own view of the Y_t barrier (already complete)
+        if (j == 0) mbar_wait(bar(17), dzph ^ 1);            // the epilogue has read the previous unit's dZ
+        tc_fence_after();
+        if (leader) {
+          const uint32_t ytile = y_base + yb * FB_Y_BYTES;
+#pragma unroll
+          for (int ks = 0; ks < FB_BN / 16; ++ks) {
+            const uint32_t a_tmem = tmem_base + FB_TMEM_P + pb * 32 + ks * 8;
+            // 16 rows j of the tile = 2 groups of 8 rows = 2048 B further along K
+            const uint64_t bdesc = make_sdesc_mn128(ytile + ks * 2048, FB_YKB_BYTES);
+            const uint32_t acc = (j == 0 && ks == 0) ? 0u : 1u;
+            umma_bf16_ts(tmem_base + FB_TMEM_DZ, a_tmem, bdesc, idesc2_lo, acc);
+            if (n_hi > 0)
+              umma_bf16_ts(tmem_base + FB_TMEM_DZ + n_lo, a_tmem,
+                           bdesc + static_cast<uint64_t>(((n_lo / FB_BK) * FB_YKB_BYTES) >> 4), idesc2_hi, acc);
+          }
+          umma_commit(bar(5 + yb));                           // Y slot free
+          umma_commit(bar(14 + pb));                          // P buffer free
+        }
+        __syncwarp();
+        if (++yb == FB_YBUFS) { yb = 0; yph ^= 1; }
+        if (++pb == 2) { pb = 0; pph ^= 1; }
+      }
       if (leader) umma_commit(bar(16));                       // dZ complete -> epilogue
       __syncwarp();
       dzph ^= 1;
     }
   } else if (cwarp < 0) {
-    // ------------------------------------------------------------------ epilogue warpgroups
+    // ------------------------------------------------------------------ epilogue: two pairs of warpgroups
     const int tid = threadIdx.x;
     const int et = tid & 127;                                // row within the block == TMEM lane
     const int wg = tid >> 7;
+    const int g = wg >> 1;                                   // pair: owns S stage g, P buffer g, i.e. every other valid tile
+    const int h = wg & 1;                                    // which 32 of the tile's 64 columns
+    const int pt = tid & (FB_PAIR_THREADS - 1);              // thread within the pair
     const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
     const float nb = -p.scale_log2;
-    uint32_t sb = 0, sph = 0, pb = 0, pph = 0, dzph = 0;
+    float* coef = reinterpret_cast<float*>(smem + FB_X_BYTES + FB_YBUFS * FB_Y_BYTES + FB_BAR_BYTES) + g * 2 * FB_BN;
+    uint32_t kglob = 0;                                      // valid tiles of this CTA's earlier units (stage = k & 1)
+    uint32_t ph = 0;                                         // phase of this pair's S stage / P buffer
+    uint32_t dzph = 0;
     for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
       const FbUnit q = fb_decode(p, u);
       const FbProblem& pr = p.prob[q.prob];
@@ -293,88 +331,106 @@ __global__ void __launch_bounds__(FB_THREADS, 1) icl_bwd_fused_kernel(const __gr
       const int gr0 = (p.rb0 + q.rb) * FB_BM;
       const int gr = gr0 + et;                               // batch index of this thread's anchor
       const long long orow_idx = static_cast<long long>(q.rb) * FB_BM + et;   // row of the (launch-local) output
+      float* orow = dz + orow_idx * Dpad;
+      const FbValid vt = fb_valid_tiles(p, q.t0, q.t1);
+      if (vt.n == 0) {
+        // a split that lies entirely in the padding: its partial gradient is zero
+        for (int c = wg * 32; c < Dpad; c += 32 * (FB_EPI_THREADS / 128))
+#pragma unroll
+          for (int hh = 0; hh < 4; ++hh) st_global_256(orow + c + 8 * hh, make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0));
+        continue;
+      }
       const bool ok = gr < p.B;
       const float cr = ok ? __ldg(cr_this + gr) * p.inv_tau : 0.f;
       const float dg = ok ? __ldg(pr.dg + gr) * p.inv_tau : 0.f;
-      bool any = false;
-      for (int t = q.t0; t < q.t1; ++t) {
-        if (!fb_tile_valid(p, t)) continue;
-        any = true;
-        const int col0 = t * FB_BN + wg * 32;                // this warpgroup's 32 columns
+      // column coefficient of tile t's column pt (pt < 64), 1/tau folded in; zero in the padding
+      auto coef_of = [&](int t) -> float {
+        const int col = t * FB_BN + pt;
+        const int part = col >= p.Bp ? 1 : 0;
+        const int idx = col - part * p.Bp;
+        return idx < p.B ? __ldg((part ? cr_this : cr_other) + idx) * p.inv_tau : 0.f;
+      };
+      const int j0 = ((kglob & 1u) == static_cast<uint32_t>(g)) ? 0 : 1;    // this pair's first valid tile of the unit
+      if (j0 < vt.n && pt < FB_BN) coef[pt] = coef_of(vt.tile(j0));
+      named_bar_sync(1 + g, FB_PAIR_THREADS);
+      int jj = 0;
+      for (int j = j0; j < vt.n; j += 2, ++jj) {
+        const int t = vt.tile(j);
+        // the next tile's coefficients travel from global memory while this tile is consumed
+        const bool has_next = j + 2 < vt.n;
+        float nxt = 0.f;
+        if (has_next && pt < FB_BN) nxt = coef_of(vt.tile(j + 2));
+        const int col0 = t * FB_BN + h * 32;                 // this warpgroup's 32 columns
         const int part = col0 >= p.Bp ? 1 : 0;
         const int idx0 = col0 - part * p.Bp;
-        const float* ccp = part ? cr_this : cr_other;
-        mbar_wait(bar(8 + sb), sph);
+        const float* cs = coef + (jj & 1) * FB_BN + h * 32;
+        mbar_wait(bar(8 + g), ph);
         tc_fence_after();
         uint32_t r[32];
-        SNAG_TMEM_LD32(tmem_base + lane_base + FB_TMEM_S + sb * FB_BN + wg * 32, r);
+        SNAG_TMEM_LD32(tmem_base + lane_base + FB_TMEM_S + g * FB_BN + h * 32, r);
         SNAG_TMEM_WAIT32(r);
         tc_fence_before();
-        mbar_arrive(bar(10 + sb));                           // S stage free: the next MMA1 may overwrite it
-        if (++sb == 2) { sb = 0; sph ^= 1; }
+        mbar_arrive(bar(10 + g));                            // S stage free: the MMA1 two tiles ahead may overwrite it
         uint32_t w[16];
         // plain strip (warp-uniform): all 128 anchors and all 32 columns valid, no diagonal element inside
         const bool plain = (gr0 + FB_BM <= p.B) && (idx0 + 32 <= p.B) && (idx0 + 31 < gr0 || idx0 > gr0 + FB_BM - 1);
         if (plain) {
 #pragma unroll
           for (int q4 = 0; q4 < 32; q4 += 4) {
-            const float4 c4 = __ldg(reinterpret_cast<const float4*>(ccp + idx0 + q4));
+            const float4 c4 = *reinterpret_cast<const float4*>(cs + q4);       // broadcast read
             const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
 #pragma unroll
             for (int e = 0; e < 4; e += 2) {
               const float e0 = ex2_approx(__fmaf_rn(__uint_as_float(r[q4 + e]), p.scale_log2, nb));
               const float e1 = ex2_approx(__fmaf_rn(__uint_as_float(r[q4 + e + 1]), p.scale_log2, nb));
-              const __nv_bfloat162 h = __floats2bfloat162_rn(__fmaf_rn(cc[e], p.inv_tau, cr) * e0,
-                                                             __fmaf_rn(cc[e + 1], p.inv_tau, cr) * e1);
-              w[(q4 + e) >> 1] = *reinterpret_cast<const uint32_t*>(&h);
+              const __nv_bfloat162 hv = __floats2bfloat162_rn((cc[e] + cr) * e0, (cc[e + 1] + cr) * e1);
+              w[(q4 + e) >> 1] = *reinterpret_cast<const uint32_t*>(&hv);
             }
           }
         } else {
 #pragma unroll
-          for (int e = 0; e < 32; e += 2) {
-            float v[2];
+          for (int q4 = 0; q4 < 32; q4 += 4) {
+            const float4 c4 = *reinterpret_cast<const float4*>(cs + q4);
+            const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const int idx = idx0 + e + h;
-              const float ccj = idx < p.B ? __ldg(ccp + idx) * p.inv_tau : 0.f;
-              const float E = ex2_approx(__fmaf_rn(__uint_as_float(r[e + h]), p.scale_log2, nb));
-              float g = (cr + ccj) * E;
-              if (idx == gr) g = part ? 0.f : g - dg;
-              if (!ok || idx >= p.B) g = 0.f;
-              v[h] = g;
+            for (int e = 0; e < 4; e += 2) {
+              float v[2];
+#pragma unroll
+              for (int hh = 0; hh < 2; ++hh) {
+                const int idx = idx0 + q4 + e + hh;
+                const float E = ex2_approx(__fmaf_rn(__uint_as_float(r[q4 + e + hh]), p.scale_log2, nb));
+                float gv = (cr + cc[e + hh]) * E;
+                if (idx == gr) gv = part ? 0.f : gv - dg;
+                if (!ok || idx >= p.B) gv = 0.f;
+                v[hh] = gv;
+              }
+              const __nv_bfloat162 hv = __floats2bfloat162_rn(v[0], v[1]);
+              w[(q4 + e) >> 1] = *reinterpret_cast<const uint32_t*>(&hv);
             }
-            const __nv_bfloat162 hh = __floats2bfloat162_rn(v[0], v[1]);
-            w[e >> 1] = *reinterpret_cast<const uint32_t*>(&hh);
           }
         }
-        mbar_wait(bar(14 + pb), pph ^ 1);                    // MMA2 of two tiles ago has consumed this P buffer
+        mbar_wait(bar(14 + g), ph ^ 1);                      // the MMA2 of this pair's previous tile has consumed the P buffer
         tc_fence_after();
-        FB_TMEM_ST16(tmem_base + lane_base + FB_TMEM_P + pb * 32 + wg * 16, w);
+        FB_TMEM_ST16(tmem_base + lane_base + FB_TMEM_P + g * 32 + h * 16, w);
         tmem_wait_st();
         tc_fence_before();
-        mbar_arrive(bar(12 + pb));
-        if (++pb == 2) { pb = 0; pph ^= 1; }
+        mbar_arrive(bar(12 + g));
+        ph ^= 1;
+        if (has_next && pt < FB_BN) coef[((jj + 1) & 1) * FB_BN + pt] = nxt;
+        named_bar_sync(1 + g, FB_PAIR_THREADS);              // next coefficients visible; this tile's no longer read
       }
-      if (!any) {
-        // a split that lies entirely in the padding: its partial gradient is zero
-        float* orow = dz + orow_idx * Dpad;
-        for (int c = wg * 32; c < Dpad; c += 64)
-#pragma unroll
-          for (int h = 0; h < 4; ++h) st_global_256(orow + c + 8 * h, make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0));
-        continue;
-      }
+      kglob += static_cast<uint32_t>(vt.n);
       mbar_wait(bar(16), dzph);
       dzph ^= 1;
       tc_fence_after();
-      float* orow = dz + orow_idx * Dpad;
-      for (int c = wg * 32; c < Dpad; c += 64) {             // warpgroup w takes every other 32-column strip
+      for (int c = wg * 32; c < Dpad; c += 32 * (FB_EPI_THREADS / 128)) {    // warpgroup w takes every fourth 32-column strip
         uint32_t r[32];
         SNAG_TMEM_LD32(tmem_base + lane_base + FB_TMEM_DZ + c, r);
         SNAG_TMEM_WAIT32(r);
 #pragma unroll
-        for (int h = 0; h < 4; ++h)
-          st_global_256(orow + c + 8 * h, make_uint4(r[8 * h], r[8 * h + 1], r[8 * h + 2], r[8 * h + 3]),
-                        make_uint4(r[8 * h + 4], r[8 * h + 5], r[8 * h + 6], r[8 * h + 7]));
+        for (int hh = 0; hh < 4; ++hh)
+          st_global_256(orow + c + 8 * hh, make_uint4(r[8 * hh], r[8 * hh + 1], r[8 * hh + 2], r[8 * hh + 3]),
+                        make_uint4(r[8 * hh + 4], r[8 * hh + 5], r[8 * hh + 6], r[8 * hh + 7]));
       }
       tc_fence_before();
       mbar_arrive(bar(17));                                  // dZ drained: the next unit may start accumulating

@@ -91,19 +91,25 @@ def _sample_rows(n: int, m: int, dev):
     key = (n, m, str(dev))
     if key not in _SAMPLES:
         gsel = torch.Generator(device="cpu").manual_seed(3408)
-        sel = torch.randperm(n, generator=gsel)[:m].sort()[0].to(dev)
-        selc = torch.randperm(n, generator=gsel)[:m].sort()[0].to(dev)
+        sel_h = torch.randperm(n, generator=gsel)[:m].sort()[0]
+        selc_h = torch.randperm(n, generator=gsel)[:m].sort()[0]
         if len(_SAMPLES) > 16:
             _SAMPLES.clear()
-        _SAMPLES[key] = (sel, selc)
-    return _SAMPLES[key]
+        _SAMPLES[key] = (sel_h.to(dev), selc_h.to(dev), sel_h, selc_h)
+    return _SAMPLES[key][:2]
+
+
+def _sample_rows_host(n: int, m: int, dev):
+    """The same two samples as host tensors (for gathering sampled rows out of host memory)."""
+    _sample_rows(n, m, dev)
+    return _SAMPLES[(n, m, str(dev))][2:]
 
 
 LAZY_NORM2_BOUND = 1.02     # squared row norm the sync-free path assumes (F.normalize'd rows rounded to bf16: 1 +- 4e-3)
 
 
 def _align_ranks_steps(be, X, Y, xn, yn, n: int, csls_k: int, use_csls: bool, want_top3: bool, world: int, rank: int,
-                       two_sweep: bool = True, lazy: bool = False, one_pass: bool | None = None):
+                       two_sweep: bool = True, lazy: bool = False, one_pass: bool | None = None, pre: dict | None = None):
     """Generator form of the sharded evaluation. Yields ("all_gather", t) / ("all_reduce", t) whenever the ranks
     must exchange data and receives the collective's result (all_gather: tensor with a new leading dim of size
     world; all_reduce: the elementwise sum). Returning through StopIteration.value keeps the data path identical
@@ -111,7 +117,10 @@ def _align_ranks_steps(be, X, Y, xn, yn, n: int, csls_k: int, use_csls: bool, wa
     `be` is the kernel backend (snag_b200.ops).
     lazy (single rank, three-sweep path only): nothing in here synchronises with the host — the tolerances assume
     nearly-unit rows (LAZY_NORM2_BOUND) and the device-side counters that normally steer retries are returned in
-    info["pending"] for align_ranks to check once, after everything has been enqueued."""
+    info["pending"] for align_ranks to check once, after everything has been enqueued.
+    pre (single rank, two-sweep sizes): {"cand_r": [n, KT], "cand_s": [n, KT]} — the merged candidate lists of the two
+    sample pre-passes when the caller already ran them (evaluate_alignment_host does, chunk by chunk, while the tables
+    are still arriving from the host); they must come from the samples _sample_rows(n, m, device) names."""
     dev = X.device
     launches = 0
     kw = dict(norm_bound=LAZY_NORM2_BOUND ** 0.5, lazy=True) if lazy else {}
@@ -156,16 +165,19 @@ def _align_ranks_steps(be, X, Y, xn, yn, n: int, csls_k: int, use_csls: bool, wa
             # of 32768 targets was measured at 4 ranks: pre-pass 21 ms cheaper, sweep 88 ms slower.) The sample is
             # global and identical on every rank; each rank computes the bounds of its slice of the sources and the
             # slices are all-gathered, so this pre-pass shrinks with the number of ranks like the sweeps do.
-            Yc, ync = Y.index_select(0, selc), yn.index_select(0, selc)
+            Yc, ync = (Y.index_select(0, selc), yn.index_select(0, selc)) if pre is None else (None, None)
             per_r = (n + world - 1) // world
             a0, a1 = min(rank * per_r, n), min((rank + 1) * per_r, n)
             nrow = 3 if one is not None else 1          # rows of the exchanged block: rowthr (, lo1, hi1)
             thr_loc = torch.full((nrow, per_r), float("-inf"), dtype=torch.float32, device=dev)
             if a1 > a0:
-                part_r = be.eval_rowtopk(X[a0:a1], Yc, xn[a0:a1], ync, a1 - a0, m)
-                _, cand_r = be.topk_merge_mean(part_r, csls_k, want_nv=False, want_cand=True)
+                if pre is not None:
+                    part_r, cand_r = None, pre["cand_r"]
+                else:
+                    part_r = be.eval_rowtopk(X[a0:a1], Yc, xn[a0:a1], ync, a1 - a0, m)
+                    _, cand_r = be.topk_merge_mean(part_r, csls_k, want_nv=False, want_cand=True)
+                    launches += 2
                 thr_loc[0, :a1 - a0] = cand_r[:, 0] - 2e-6             # lists are ascending: [0] is the KT-th largest
-                launches += 2
                 if one is not None:
                     lo1, hi1 = be.spec_bounds(cand_r, one["c_diag"][a0:a1].contiguous(), csls_k, one["shift"], one["delta"])
                     thr_loc[1, :a1 - a0] = lo1
@@ -185,11 +197,16 @@ def _align_ranks_steps(be, X, Y, xn, yn, n: int, csls_k: int, use_csls: bool, wa
             hi2_loc = torch.full((per,), float("inf"), dtype=torch.float32, device=dev) if one is not None else None
             if ns > 0:
                 # column bounds: this rank's targets against a sample of the sources
-                Xs, xns = X.index_select(0, sel), xn.index_select(0, sel)
-                part_s = be.eval_rowtopk(Ys, Xs, yns, xns, ns, m)
-                _, cand_s = be.topk_merge_mean(part_s, csls_k, want_nv=False, want_cand=True)
+                if pre is not None:
+                    Xs = xns = part_s = None
+                    cand_s = pre["cand_s"]
+                else:
+                    Xs, xns = X.index_select(0, sel), xn.index_select(0, sel)
+                    part_s = be.eval_rowtopk(Ys, Xs, yns, xns, ns, m)
+                    _, cand_s = be.topk_merge_mean(part_s, csls_k, want_nv=False, want_cand=True)
+                    launches += 2
                 colthr, colb = be.col_threshold(cand_s, csls_k, yns)
-                launches += 3
+                launches += 1
                 if one is not None:
                     one["lo2"], hi2_loc[:ns] = be.spec_bounds(cand_s, one["c_diag"][c0:c1].contiguous(), csls_k, one["shift"],
                                                               one["delta"])
@@ -481,7 +498,8 @@ def _align_ranks_lazy(be, X, Y, xn, yn, n, csls_k, use_csls, want_top3):
 
 def align_ranks(X: torch.Tensor, Y: torch.Tensor, xn: torch.Tensor, yn: torch.Tensor, n: int, csls_k: int = 10,
                 use_csls: bool = True, want_top3: bool = False, group=None, backend=None,
-                two_sweep: bool = True, lazy: bool | None = None, one_pass: bool | None = None) -> AlignRanks:
+                two_sweep: bool = True, lazy: bool | None = None, one_pass: bool | None = None,
+                pre: dict | None = None) -> AlignRanks:
     """Fused evaluation of n aligned pairs (x_i <-> y_i).
 
     X, Y : bf16 operands [>=n, Dpad] from ops.prep_bf16; xn, yn : their squared norms [n].
@@ -513,7 +531,10 @@ def align_ranks(X: torch.Tensor, Y: torch.Tensor, xn: torch.Tensor, yn: torch.Te
             return res                                   # else: an assumption did not hold — take the synchronising path
     if float(torch.maximum(xn[:n].max(), yn[:n].max()).item()) > 8.0:
         raise SnagError("align_ranks expects L2-normalised rows (evaluate_alignment(normalize=True))")
-    gen = _align_ranks_steps(be, X, Y, xn, yn, n, csls_k, use_csls, want_top3, world, rank, two_sweep, one_pass=one_pass)
+    if pre is not None and (world != 1 or not use_csls or two_sweep_plan(n, csls_k) is None or not two_sweep):
+        raise ValueError("pre-computed sample pre-passes apply to the single-rank two-sweep CSLS path only")
+    gen = _align_ranks_steps(be, X, Y, xn, yn, n, csls_k, use_csls, want_top3, world, rank, two_sweep, one_pass=one_pass,
+                             pre=pre)
     if world == 1:
         try:
             next(gen)
@@ -694,13 +715,97 @@ def evaluate_alignment_l1(final_emb: torch.Tensor, test_left: torch.Tensor, test
     return {"l2r": metrics_from_ranks(rank_l2r), "r2l": metrics_from_ranks(rank_r2l), "ranks": res, "launches": 7}
 
 
+STREAM_CHUNK_ROWS = 65536      # rows per host -> device chunk of the streamed entry point (315 MB at D = 1200: ~6 ms of PCIe 5)
+_PINNED: dict = {}
+
+
+def _pinned(shape, key):
+    """A cached pinned staging buffer (pinning 150 MB costs more than the copy it speeds up)."""
+    buf = _PINNED.get(key)
+    if buf is None or tuple(buf.shape) != tuple(shape):
+        if len(_PINNED) > 4:
+            _PINNED.clear()
+        buf = torch.empty(shape, dtype=torch.float32).pin_memory()
+        _PINNED[key] = buf
+    return buf
+
+
+def _stream_in_with_prepasses(src_rows, tgt_rows, n: int, csls_k: int, normalize: bool, device, m: int):
+    """Host -> device transfer of both tables in row chunks on a copy stream, overlapped with everything that needs only
+    the rows that have arrived: normalise + round (prep_bf16) and the two sample pre-passes of the two-sweep evaluation.
+    Order: the m sampled TARGET rows first (gathered on the host into pinned staging while the first source chunks are
+    already in flight), then the sources — each chunk's row pre-pass (its sources x the sampled targets) runs as soon
+    as it lands — then the targets, each chunk's column pre-pass running against the sampled sources, which are on the
+    device by then. Returns X, Y, xn, yn and the merged pre-pass candidates for align_ranks(pre=...). The PCIe copy
+    (9.6 GB at 1M x 1200) is the critical path; 2 x m/n of a sweep and the prologue hide behind it."""
+    be = _cuda_ops
+    d = src_rows.shape[1]
+    dpad = round_up(d, 64)
+    cur = torch.cuda.current_stream(device)
+    copy_s, copy_s2 = torch.cuda.Stream(device=device), torch.cuda.Stream(device=device)
+    copy_s.wait_stream(cur)
+    copy_s2.wait_stream(cur)
+    sel, selc = _sample_rows(n, m, device)
+    xs = torch.empty((n, d), dtype=torch.float32, device=device)
+    ys = torch.empty((n, d), dtype=torch.float32, device=device)
+    X = torch.empty((n, dpad), dtype=torch.bfloat16, device=device)
+    Y = torch.empty((n, dpad), dtype=torch.bfloat16, device=device)
+    xn = torch.empty((n,), dtype=torch.float32, device=device)
+    yn = torch.empty((n,), dtype=torch.float32, device=device)
+    cand_r = torch.empty((n, KT), dtype=torch.float32, device=device)
+    cand_s = torch.empty((n, KT), dtype=torch.float32, device=device)
+    ysamp = torch.empty((m, d), dtype=torch.float32, device=device)
+    bounds = [(r0, min(n, r0 + STREAM_CHUNK_ROWS)) for r0 in range(0, n, STREAM_CHUNK_ROWS)]
+    events = {}
+    for tag, host, dst in (("x", src_rows, xs), ("y", tgt_rows, ys)):
+        with torch.cuda.stream(copy_s):
+            for i, (r0, r1) in enumerate(bounds):
+                dst[r0:r1].copy_(host[r0:r1], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_s)
+                events[tag, i] = ev
+        if tag == "x":
+            # the source chunks are queued: gather the sampled target rows on the host while the DMA engine works, then
+            # send them on a second stream so that they overtake the queue
+            stage = _pinned((m, d), ("ysamp", m, d))
+            torch.index_select(tgt_rows, 0, _sample_rows_host(n, m, device)[1], out=stage)
+            with torch.cuda.stream(copy_s2):
+                ysamp.copy_(stage, non_blocking=True)
+                ev_samp = torch.cuda.Event()
+                ev_samp.record(copy_s2)
+    cur.wait_event(ev_samp)
+    Yc, ync = be.prep_bf16(ysamp, None, normalize)
+    launches = 1
+    for i, (r0, r1) in enumerate(bounds):                           # sources: prologue + row pre-pass per chunk
+        cur.wait_event(events["x", i])
+        _, a = be.prep_bf16(xs[r0:r1], None, normalize, out=X[r0:r1])
+        xn[r0:r1] = a
+        part = be.eval_rowtopk(X[r0:r1], Yc, xn[r0:r1], ync, r1 - r0, m)
+        _, c = be.topk_merge_mean(part, csls_k, want_nv=False, want_cand=True)
+        cand_r[r0:r1] = c
+        launches += 3
+    Xs, xns = X.index_select(0, sel), xn.index_select(0, sel)
+    for i, (r0, r1) in enumerate(bounds):                           # targets: prologue + column pre-pass per chunk
+        cur.wait_event(events["y", i])
+        _, b = be.prep_bf16(ys[r0:r1], None, normalize, out=Y[r0:r1])
+        yn[r0:r1] = b
+        part = be.eval_rowtopk(Y[r0:r1], Xs, yn[r0:r1], xns, r1 - r0, m)
+        _, c = be.topk_merge_mean(part, csls_k, want_nv=False, want_cand=True)
+        cand_s[r0:r1] = c
+        launches += 3
+    # every copy has been waited for on the current stream: the staging buffers may be reused by later allocations on it
+    return X, Y, xn, yn, {"cand_r": cand_r, "cand_s": cand_s}, launches
+
+
 def evaluate_alignment_host(src_rows: torch.Tensor, tgt_rows: torch.Tensor, n: int, row0: int = 0, csls: bool = True,
-                            csls_k: int = 10, normalize: bool = True, group=None, device=None) -> dict:
+                            csls_k: int = 10, normalize: bool = True, group=None, device=None, stream_in: bool | None = None) -> dict:
     """End-to-end entry point from HOST memory: `src_rows` / `tgt_rows` are (ideally pinned) fp32 [m, D] host tensors
     holding pairs row0 .. row0+m of the n evaluated pairs — all of them on a single GPU, or this rank's contiguous
     slice (ceil(n / world) pairs per rank) when `group` is given. Copies them to the device, normalises and rounds
     them, exchanges the bf16 operands over NCCL so that every rank holds both tables, runs the sharded fused
-    evaluation, brings the ranks back and reduces them to Hits@k / MR / MRR on the host."""
+    evaluation, brings the ranks back and reduces them to Hits@k / MR / MRR on the host.
+    stream_in (default: single GPU, CSLS, n >= TWO_SWEEP_MIN_N): transfer the tables in chunks and run the prologue and
+    the sample pre-passes on the chunks as they arrive (_stream_in_with_prepasses); the result is bit-identical."""
     if device is None:
         device = torch.device("cuda", torch.cuda.current_device())
     m, d = src_rows.shape
@@ -716,6 +821,18 @@ def evaluate_alignment_host(src_rows: torch.Tensor, tgt_rows: torch.Tensor, n: i
         per = (n + world - 1) // world
         if row0 != dist.get_rank(group) * per or m != max(0, min(n, row0 + per) - row0):
             raise ValueError("host slice does not match this rank's share of the pairs")
+    plan2 = two_sweep_plan(n, csls_k) if (csls and 1 <= csls_k <= KT and csls_k <= n) else None
+    if stream_in is None:
+        stream_in = world == 1 and plan2 is not None
+    if stream_in:
+        if world != 1 or plan2 is None:
+            raise ValueError("stream_in applies to the single-GPU two-sweep CSLS evaluation (n >= TWO_SWEEP_MIN_N)")
+        X, Y, xn, yn, pre, launches = _stream_in_with_prepasses(src_rows, tgt_rows, n, csls_k, normalize, device, plan2[0])
+        res = align_ranks(X, Y, xn, yn, n, csls_k, csls, False, None, pre=pre)
+        l2r = res.rank_l2r.cpu()
+        r2l = res.rank_r2l.cpu()
+        return {"l2r": metrics_from_ranks(l2r), "r2l": metrics_from_ranks(r2l), "ranks": res,
+                "launches": res.launches + launches, "streamed": True}
     xs = src_rows.to(device, non_blocking=True)
     ys = tgt_rows.to(device, non_blocking=True)
     dpad = round_up(d, 64)

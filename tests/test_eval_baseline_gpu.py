@@ -113,6 +113,30 @@ def test_two_sweep_size_against_oracle(cuda_device):
             assert all(mr.info["one_pass"]["fallback"] is None for mr in many)
 
 
+def test_streamed_host_entry_point_equals_resident(cuda_device):
+    """evaluate_alignment_host with the chunked, overlapped transfer (prologue and sample pre-passes run on the chunks as
+    they arrive) returns the same ranks and neighbourhood means, bit for bit, as the same tables evaluated after one
+    plain copy — with a chunk size that does not divide n."""
+    n, d, k = evaluate.TWO_SWEEP_MIN_N + 4321, 320, 10
+    rng = np.random.RandomState(11)
+    centres = rng.randn(64, d).astype(np.float32)
+    x = rng.randn(n, d).astype(np.float32) + centres[rng.randint(0, 64, n)]
+    y = x + np.float32(3.0) * rng.randn(n, d).astype(np.float32)
+    hx, hy = torch.from_numpy(x).pin_memory(), torch.from_numpy(y).pin_memory()
+    old = evaluate.STREAM_CHUNK_ROWS
+    evaluate.STREAM_CHUNK_ROWS = 20000
+    try:
+        a = evaluate.evaluate_alignment_host(hx, hy, n, csls=True, csls_k=k, device=cuda_device)
+    finally:
+        evaluate.STREAM_CHUNK_ROWS = old
+    b = evaluate.evaluate_alignment_host(hx, hy, n, csls=True, csls_k=k, device=cuda_device, stream_in=False)
+    assert a.get("streamed") and not b.get("streamed")
+    for key in ("rank_l2r", "rank_r2l", "nv1", "nv2", "g"):
+        assert torch.equal(getattr(a["ranks"], key), getattr(b["ranks"], key)), key
+    assert a["l2r"].mrr == b["l2r"].mrr and a["r2l"].mrr == b["r2l"].mrr
+    assert a["ranks"].info["one_pass"]["fallback"] is None
+
+
 def test_one_pass_fallbacks_are_exact(cuda_device, monkeypatch):
     """The one-pass evaluation speculates on upper bounds of the neighbourhood means; whatever happens to the guesses the
     ranks must not change: (a) guesses that are far too low -> the failed entities are recounted exhaustively,
