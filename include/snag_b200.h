@@ -305,7 +305,9 @@ int snag_top3_merge(const float* val, const int32_t* idx, int32_t n_lists, int64
 
 /* csls_sim (src/utils.py:417-435) on a MATERIALISED fp32 similarity matrix [n1, ld]: nv1[i] / nv2[j] = mean of the k
  * largest entries of row i / column j; out[i,j] = (2*sim[i,j] - nv1[i]) - nv2[j] (out may be NULL to get only the
- * neighbourhood means, and may alias sim). workspace: snag_csls_workspace_bytes(n1, n2) bytes, 16-byte aligned. */
+ * neighbourhood means, and may alias sim). workspace: snag_csls_workspace_bytes(n1, n2) bytes, 16-byte aligned.
+ * k <= SNAG_KT runs the three bandwidth passes; SNAG_KT < k <= 1024 (the reference takes any k) selects per row /
+ * column with a radix select + sorted largest-first sum (one block per vector; the column pass reads strided). */
 int64_t snag_csls_workspace_bytes(int64_t n1, int64_t n2);
 int snag_csls_sim(const float* sim, int64_t n1, int64_t n2, int64_t ld, int32_t k, float* out, int64_t ld_out, float* nv1,
                   float* nv2, void* workspace, void* stream);

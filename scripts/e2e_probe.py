@@ -41,10 +41,12 @@ print(f"pinned staging alloc {1e3 * (t1 - t0):.1f} ms, index_select of {m} rows 
 for it in range(3):
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    X, Y, xn, yn, pre, launches = evaluate._stream_in_with_prepasses(host[0], host[1], n, k, True, dev, m)
+    tl = {}
+    X, Y, xn, yn, pre, launches = evaluate._stream_in_with_prepasses(host[0], host[1], n, k, True, dev, m, timeline=tl)
     t1 = time.perf_counter()
     torch.cuda.synchronize()
     t2 = time.perf_counter()
+    print("   timeline (ms after start):", {kk: round(tl["start"].elapsed_time(v), 1) for kk, v in tl.items() if kk != "start"}, flush=True)
     res = evaluate.align_ranks(X, Y, xn, yn, n, k, True, False, None, pre=pre)
     torch.cuda.synchronize()
     t3 = time.perf_counter()

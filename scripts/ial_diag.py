@@ -54,3 +54,44 @@ for B, Ds, Dt, tau, red in [(700, 96, 320, 0.5, "mean"), (1000, 300, 1200, 4.0, 
     print(json.dumps({"B": B, "Ds": Ds, "Dt": Dt, "tau": tau, "red": red, "loss64": l64,
                       "fused_loss_rel": abs(float(fused) - l64) / abs(l64), "fp32_loss_rel": abs(outs["fp32"][0] - l64) / abs(l64),
                       "fused_grad_rel": rel(a.grad, g64), "fp32_grad_rel": rel(outs["fp32"][1], g64)}), flush=True)
+
+# goldens: the reference's own fp32 outputs on fp32 inputs (the fused path rounds the normalised rows to bf16)
+import os  # noqa: E402
+GD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
+for f in sorted(os.listdir(GD)):
+    if not (f.startswith("ial_") and f.endswith(".npz")):
+        continue
+    with np.load(os.path.join(GD, f)) as z:
+        fx = {k: z[k] for k in z.files}
+    src = torch.from_numpy(fx["src"]).to(dev).requires_grad_(True)
+    tar = torch.from_numpy(fx["tar"]).to(dev)
+    crit = sloss.ial_loss(tau=float(fx["tau"]), ab_weight=float(fx["ab_weight"]), zoom=float(fx["zoom"]), reduction=str(fx["reduction"]))
+    out = crit(src, tar, fx["links"])
+    out.backward()
+    # the same reference arithmetic in fp64 on the fp32 inputs and on bf16-rounded normalised rows
+    il, ir = sloss._links_to_index(fx["links"], dev)
+    outs = {}
+    for name, rounded in (("fp64_fp32rows", False), ("fp64_bf16rows", True)):
+        b = torch.from_numpy(fx["src"]).to(dev).requires_grad_(True)
+        if rounded:
+            r = ref(b, tar, il, ir, float(fx["tau"]), float(fx["ab_weight"]), float(fx["zoom"]), str(fx["reduction"]), torch.float64)
+        else:
+            zs = F.normalize(b.double(), dim=1)
+            rt = F.normalize(tar.double(), dim=1)
+            tau = float(fx["tau"])
+            B = il.numel()
+            eye = torch.eye(B, device=dev, dtype=torch.float64) * 1e9
+            cat = lambda u, v: torch.cat([u @ v.t() / tau, u @ u.t() / tau - eye], 1)
+            la = F.kl_div(F.log_softmax(cat(zs[il], zs[ir]), 1), F.softmax(cat(rt[il], rt[ir]), 1), reduction="none")
+            lb = F.kl_div(F.log_softmax(cat(zs[ir], zs[il]), 1), F.softmax(cat(rt[ir], rt[il]), 1), reduction="none")
+            red = str(fx["reduction"])
+            la, lb = (la.mean(), lb.mean()) if red == "mean" else (la.sum(), lb.sum())
+            r = float(fx["zoom"]) * (float(fx["ab_weight"]) * la + (1 - float(fx["ab_weight"])) * lb)
+        r.backward()
+        outs[name] = (float(r), b.grad.clone())
+    print(json.dumps({"golden": f, "shape": list(fx["src"].shape), "golden_loss": float(fx["loss"]),
+                      "fused_vs_golden_loss": abs(float(out) - float(fx["loss"])) / abs(float(fx["loss"])),
+                      "fused_vs_golden_grad": rel(src.grad.cpu(), torch.from_numpy(fx["grad_src"])),
+                      "bf16rows_fp64_vs_golden_loss": abs(outs["fp64_bf16rows"][0] - float(fx["loss"])) / abs(float(fx["loss"])),
+                      "bf16rows_fp64_vs_golden_grad": rel(outs["fp64_bf16rows"][1].cpu(), torch.from_numpy(fx["grad_src"])),
+                      "fp32rows_fp64_vs_golden_loss": abs(outs["fp64_fp32rows"][0] - float(fx["loss"])) / abs(float(fx["loss"]))}), flush=True)

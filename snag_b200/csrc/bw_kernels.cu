@@ -1317,6 +1317,85 @@ int launch_topk_exhaustive(const __nv_bfloat16* A, const __nv_bfloat16* B, int D
   return static_cast<int>(cudaGetLastError());
 }
 static inline int grid_for(long long work_items, int block, int num_sms, int ctas_per_sm);
+// k > KT_LIST (the reference takes any k, src/utils.py:431): one block per row (or, with strides swapped, per column).
+// A 4-pass radix select on the order-preserving integer image of the floats finds the k-th largest value; the values
+// above it are collected in shared memory, sorted (bitonic, descending) and summed largest-first together with the
+// needed copies of the k-th value — the oracle's arithmetic (mean_desc). k <= CSLS_ANYK_MAX.
+constexpr int CSLS_ANYK_MAX = 1024;
+__device__ __forceinline__ uint32_t float_order_key(float v) {
+  const uint32_t u = __float_as_uint(v);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__global__ void __launch_bounds__(256) vec_topk_mean_any_kernel(const float* __restrict__ sim, long long n_vec, long long len,
+                                                                long long vec_stride, long long elem_stride, int k,
+                                                                float* __restrict__ nv) {
+  __shared__ int hist[256];
+  __shared__ float buf[CSLS_ANYK_MAX];
+  __shared__ uint32_t sh_prefix;
+  __shared__ int sh_remaining, sh_cnt;
+  for (long long v = blockIdx.x; v < n_vec; v += gridDim.x) {
+    const float* base = sim + v * vec_stride;
+    uint32_t prefix = 0, mask = 0;
+    int remaining = k;                                   // rank (from the top) of the wanted value among keys matching prefix
+    for (int shift = 24; shift >= 0; shift -= 8) {
+      hist[threadIdx.x] = 0;
+      __syncthreads();
+      for (long long j = threadIdx.x; j < len; j += 256) {
+        const uint32_t key = float_order_key(__ldg(base + j * elem_stride));
+        if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1);
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        int cum = 0, d = 255;
+        for (; d > 0; --d) {
+          if (cum + hist[d] >= remaining) break;
+          cum += hist[d];
+        }
+        sh_prefix = prefix | (static_cast<uint32_t>(d) << shift);
+        sh_remaining = remaining - cum;
+        sh_cnt = 0;
+      }
+      __syncthreads();
+      prefix = sh_prefix;
+      remaining = sh_remaining;
+      mask |= 255u << shift;
+    }
+    // prefix = key of the k-th largest value; `remaining` copies of it belong to the top k, after the c = k - remaining
+    // strictly larger values
+    for (long long j = threadIdx.x; j < len; j += 256) {
+      const float x = __ldg(base + j * elem_stride);
+      if (float_order_key(x) > prefix) buf[atomicAdd(&sh_cnt, 1)] = x;
+    }
+    __syncthreads();
+    const int c = sh_cnt;                                // == k - remaining
+    int P = 1;
+    while (P < c) P <<= 1;
+    for (int t = c + threadIdx.x; t < P; t += 256) buf[t] = -INFINITY;
+    __syncthreads();
+    for (int size = 2; size <= P; size <<= 1)
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        for (int t = threadIdx.x; t < P; t += 256) {
+          const int partner = t ^ stride;
+          if (partner > t) {
+            const bool desc = (t & size) == 0;
+            const float a = buf[t], b = buf[partner];
+            if (desc ? (a < b) : (a > b)) { buf[t] = b; buf[partner] = a; }
+          }
+        }
+        __syncthreads();
+      }
+    if (threadIdx.x == 0) {
+      const uint32_t u = (prefix & 0x80000000u) ? (prefix & 0x7FFFFFFFu) : ~prefix;
+      const float kth = __uint_as_float(u);
+      float acc = 0.f;
+      for (int t = 0; t < c; ++t) acc = __fadd_rn(acc, buf[t]);
+      for (int t = 0; t < remaining; ++t) acc = __fadd_rn(acc, kth);
+      nv[v] = __fdiv_rn(acc, static_cast<float>(k));
+    }
+    __syncthreads();
+  }
+}
+
 static int csls_col_slabs(long long n1) {
   long long s = (n1 + 255) / 256;          // >= 256 rows per slab
   if (s > 64) s = 64;
@@ -1329,8 +1408,19 @@ long long csls_workspace_floats(long long n1, long long n2) {
 int launch_csls_sim(const float* sim, long long n1, long long n2, long long ld, int k, float* out, long long ld_out,
                     float* nv1, float* nv2, float* workspace, cudaStream_t st) {
   if (!sim || !nv1 || !nv2 || !workspace || n1 <= 0 || n2 <= 0 || ld < n2) return SNAG_ERR_ARG;
-  if (k < 1 || k > KT_LIST || k > n1 || k > n2) return SNAG_ERR_SHAPE;
+  if (k < 1 || k > CSLS_ANYK_MAX || k > n1 || k > n2) return SNAG_ERR_SHAPE;
   if (reinterpret_cast<uintptr_t>(workspace) & 15) return SNAG_ERR_ALIGN;
+  if (k > KT_LIST) {
+    const int g1 = static_cast<int>(n1 < 8ll * num_sms() ? n1 : 8ll * num_sms());
+    const int g2 = static_cast<int>(n2 < 8ll * num_sms() ? n2 : 8ll * num_sms());
+    vec_topk_mean_any_kernel<<<g1, 256, 0, st>>>(sim, n1, n2, ld, 1, k, nv1);       // rows
+    vec_topk_mean_any_kernel<<<g2, 256, 0, st>>>(sim, n2, n1, 1, ld, k, nv2);       // columns (strided reads)
+    if (out) {
+      const int g = grid_for(n1 * n2, 256, num_sms(), 8);
+      csls_apply_kernel<<<g, 256, 0, st>>>(sim, nv1, nv2, out, n1, n2, ld, ld_out);
+    }
+    return static_cast<int>(cudaGetLastError());
+  }
   float* part_r = workspace;
   float* part_c = workspace + 32 * n1 * KT_LIST;
   const int slabs = csls_col_slabs(n1);

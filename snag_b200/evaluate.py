@@ -663,10 +663,14 @@ def evaluate_alignment(final_emb: torch.Tensor, test_left: torch.Tensor, test_ri
     n = test_left.numel()
     if test_right.numel() != n:
         raise ValueError("test_left and test_right must pair up")
-    if csls and not 1 <= csls_k <= KT:
-        raise SnagError(f"csls_k={csls_k} unsupported: the fused CSLS path keeps {KT} candidates per row")
+    if csls and csls_k < 1:
+        raise ValueError(f"csls_k={csls_k}")
     if csls and csls_k > n:
         raise ValueError(f"csls_k={csls_k} exceeds the number of evaluated pairs n={n}")
+    if csls and csls_k > KT:
+        # the fused sweeps keep KT candidates per entity; larger neighbourhoods (the reference takes any k) are evaluated
+        # on the materialised matrix
+        return evaluate_alignment_materialised(final_emb, test_left, test_right, csls, csls_k, want_top3, normalize, group)
     if graph is None:
         graph = USE_EVAL_GRAPH and group is None and n < TWO_SWEEP_MIN_N and not torch.cuda.is_current_stream_capturing()
     if graph and group is None and final_emb.is_cuda and final_emb.dtype == torch.float32:
@@ -684,6 +688,37 @@ def evaluate_alignment(final_emb: torch.Tensor, test_left: torch.Tensor, test_ri
         "ranks": res,
         "launches": res.launches + 2,
     }
+
+
+def evaluate_alignment_materialised(final_emb: torch.Tensor, test_left: torch.Tensor, test_right: torch.Tensor, csls: bool = True,
+                                    csls_k: int = 10, want_top3: bool = False, normalize: bool = True, group=None) -> dict:
+    """Runner._test (main.py:379-429) for CSLS neighbourhoods larger than the fused path's KT candidates (csls_k up to
+    ops.CSLS_MATRIX_K_MAX; no script of the reference goes beyond 10): the reference's own composition —
+    pairwise_distances -> 1 - csls_sim(1 - d, k) -> rank of the diagonal — with the [n, n] fp32 matrix materialised on
+    the device by the drop-in kernels (tensor-core distances, radix-select neighbourhood means, counting ranks with the
+    stable-sort tie-break). Single GPU; needs 3 * 4 n^2 bytes."""
+    if group is not None:
+        raise SnagError(f"csls_k={csls_k} > {KT}: the materialised evaluation is not sharded")
+    n = test_left.numel()
+    free, _total = torch.cuda.mem_get_info(final_emb.device)
+    if 3 * 4 * n * n > free:
+        raise SnagError(f"csls_k={csls_k} > {KT} needs the materialised {n} x {n} matrix, which does not fit this device")
+    X, xn = _cuda_ops.prep_bf16(final_emb, test_left.to(torch.int64).contiguous(), normalize)
+    Y, yn = _cuda_ops.prep_bf16(final_emb, test_right.to(torch.int64).contiguous(), normalize)
+    dist = _cuda_ops.sim_write(X, Y, xn, yn, n, n, mode=1)                            # main.py:386
+    nv1 = nv2 = None
+    if csls:
+        out, nv1, nv2 = _cuda_ops.csls_sim_matrix(1 - dist, int(csls_k))              # main.py:393
+        dist = 1 - out
+        del out
+    rank_l2r, rank_r2l = _cuda_ops.matrix_rank(dist)
+    top3_idx = top3_val = None
+    if want_top3:
+        order = torch.sort(dist, dim=1, stable=True)
+        top3_idx, top3_val = order[1][:, :3].to(torch.int32), order[0][:, :3]
+    res = AlignRanks(rank_l2r, rank_r2l, nv1, nv2, torch.diagonal(dist).clone(), top3_idx, top3_val, 7,
+                     {"materialised": True, "csls_k": int(csls_k)})
+    return {"l2r": metrics_from_ranks(rank_l2r), "r2l": metrics_from_ranks(rank_r2l), "ranks": res, "launches": 7}
 
 
 def evaluate_alignment_l1(final_emb: torch.Tensor, test_left: torch.Tensor, test_right: torch.Tensor, csls: bool = True,
@@ -730,11 +765,11 @@ def _pinned(shape, key):
     return buf
 
 
-def _stream_in_with_prepasses(src_rows, tgt_rows, n: int, csls_k: int, normalize: bool, device, m: int):
+def _stream_in_with_prepasses(src_rows, tgt_rows, n: int, csls_k: int, normalize: bool, device, m: int, timeline: dict | None = None):
     """Host -> device transfer of both tables in row chunks on a copy stream, overlapped with everything that needs only
     the rows that have arrived: normalise + round (prep_bf16) and the two sample pre-passes of the two-sweep evaluation.
-    Order: the m sampled TARGET rows first (gathered on the host into pinned staging while the first source chunks are
-    already in flight), then the sources — each chunk's row pre-pass (its sources x the sampled targets) runs as soon
+    Order: a few source chunks, the m sampled TARGET rows (gathered on the host into pinned staging while those chunks
+    are in flight), the remaining sources — each chunk's row pre-pass (its sources x the sampled targets) runs as soon
     as it lands — then the targets, each chunk's column pre-pass running against the sampled sources, which are on the
     device by then. Returns X, Y, xn, yn and the merged pre-pass candidates for align_ranks(pre=...). The PCIe copy
     (9.6 GB at 1M x 1200) is the critical path; 2 x m/n of a sweep and the prologue hide behind it."""
@@ -742,9 +777,8 @@ def _stream_in_with_prepasses(src_rows, tgt_rows, n: int, csls_k: int, normalize
     d = src_rows.shape[1]
     dpad = round_up(d, 64)
     cur = torch.cuda.current_stream(device)
-    copy_s, copy_s2 = torch.cuda.Stream(device=device), torch.cuda.Stream(device=device)
+    copy_s = torch.cuda.Stream(device=device)
     copy_s.wait_stream(cur)
-    copy_s2.wait_stream(cur)
     sel, selc = _sample_rows(n, m, device)
     xs = torch.empty((n, d), dtype=torch.float32, device=device)
     ys = torch.empty((n, d), dtype=torch.float32, device=device)
@@ -757,23 +791,40 @@ def _stream_in_with_prepasses(src_rows, tgt_rows, n: int, csls_k: int, normalize
     ysamp = torch.empty((m, d), dtype=torch.float32, device=device)
     bounds = [(r0, min(n, r0 + STREAM_CHUNK_ROWS)) for r0 in range(0, n, STREAM_CHUNK_ROWS)]
     events = {}
-    for tag, host, dst in (("x", src_rows, xs), ("y", tgt_rows, ys)):
+    lead = min(3, len(bounds))     # source chunks queued ahead of the sampled rows: the DMA engine stays busy during the host gather
+
+    def queue(tag, host, dst, chunks):
         with torch.cuda.stream(copy_s):
-            for i, (r0, r1) in enumerate(bounds):
+            for i in chunks:
+                r0, r1 = bounds[i]
                 dst[r0:r1].copy_(host[r0:r1], non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(copy_s)
                 events[tag, i] = ev
-        if tag == "x":
-            # the source chunks are queued: gather the sampled target rows on the host while the DMA engine works, then
-            # send them on a second stream so that they overtake the queue
-            stage = _pinned((m, d), ("ysamp", m, d))
-            torch.index_select(tgt_rows, 0, _sample_rows_host(n, m, device)[1], out=stage)
-            with torch.cuda.stream(copy_s2):
-                ysamp.copy_(stage, non_blocking=True)
-                ev_samp = torch.cuda.Event()
-                ev_samp.record(copy_s2)
+
+    # ONE copy stream, in the order the data is needed (copies queued on a second stream were measured to be served only
+    # after the first stream's queue had drained): a few source chunks, the sampled target rows — gathered on the host
+    # into pinned staging while those chunks are in flight — the remaining sources, then the targets
+    queue("x", src_rows, xs, range(lead))
+    stage = _pinned((m, d), ("ysamp", m, d))
+    torch.index_select(tgt_rows, 0, _sample_rows_host(n, m, device)[1], out=stage)
+    with torch.cuda.stream(copy_s):
+        ysamp.copy_(stage, non_blocking=True)
+        ev_samp = torch.cuda.Event()
+        ev_samp.record(copy_s)
+    queue("x", src_rows, xs, range(lead, len(bounds)))
+    queue("y", tgt_rows, ys, range(len(bounds)))
+
+    def mark(name, stream):
+        if timeline is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(stream)
+            timeline[name] = ev
+
+    mark("copies_done", copy_s)
+    mark("start", cur)
     cur.wait_event(ev_samp)
+    mark("sample_landed", cur)
     Yc, ync = be.prep_bf16(ysamp, None, normalize)
     launches = 1
     for i, (r0, r1) in enumerate(bounds):                           # sources: prologue + row pre-pass per chunk
@@ -784,6 +835,7 @@ def _stream_in_with_prepasses(src_rows, tgt_rows, n: int, csls_k: int, normalize
         _, c = be.topk_merge_mean(part, csls_k, want_nv=False, want_cand=True)
         cand_r[r0:r1] = c
         launches += 3
+    mark("sources_done", cur)
     Xs, xns = X.index_select(0, sel), xn.index_select(0, sel)
     for i, (r0, r1) in enumerate(bounds):                           # targets: prologue + column pre-pass per chunk
         cur.wait_event(events["y", i])
@@ -793,6 +845,7 @@ def _stream_in_with_prepasses(src_rows, tgt_rows, n: int, csls_k: int, normalize
         _, c = be.topk_merge_mean(part, csls_k, want_nv=False, want_cand=True)
         cand_s[r0:r1] = c
         launches += 3
+    mark("targets_done", cur)
     # every copy has been waited for on the current stream: the staging buffers may be reused by later allocations on it
     return X, Y, xn, yn, {"cand_r": cand_r, "cand_s": cand_s}, launches
 

@@ -171,20 +171,24 @@ class _IclMany(torch.autograd.Function):
                 be.prep_bf16(emb, idx_r, normalize=normalize, out=S3[Bp:2 * Bp])
                 S3[2 * Bp:2 * Bp + B].copy_(S3[0:B])
                 stacks.append(S3)
-        for emb, S3 in zip(embs, stacks):
+        loc_all = None
+        if shard.world > 1:
+            # this rank's anchors of every table, then ONE all-gather of the per-anchor (lse, nll) of both sides
+            loc_all = torch.zeros((len(embs), 4, per), dtype=torch.float32, device=embs[0].device)
+            if r1 > r0:
+                nx = r1 - r0
+                for p, S3 in enumerate(stacks):
+                    la, na, _ = be.icl_side(S3[r0:r0 + nx], S3[Bp:3 * Bp], B, Bp, inv_tau, r0, nx)
+                    lb, nb, _ = be.icl_side(S3[Bp + r0:Bp + r0 + nx], S3[0:2 * Bp], B, Bp, inv_tau, r0, nx)
+                    loc_all[p, 0, :nx], loc_all[p, 1, :nx], loc_all[p, 2, :nx], loc_all[p, 3, :nx] = la, na, lb, nb
+            allv = shard.all_gather(loc_all).permute(1, 2, 0, 3).reshape(len(embs), 4, -1)[:, :, :B].contiguous()   # anchor order
+        for p, (emb, S3) in enumerate(zip(embs, stacks)):
             D = emb.shape[1]
             if shard.world == 1:
                 lse_a, nll_a, _ = be.icl_side(S3[0:Bp], S3[Bp:3 * Bp], B, Bp, inv_tau)
                 lse_b, nll_b, _ = be.icl_side(S3[Bp:2 * Bp], S3[0:2 * Bp], B, Bp, inv_tau)
             else:
-                loc = torch.zeros((4, per), dtype=torch.float32, device=emb.device)
-                if r1 > r0:
-                    nx = r1 - r0
-                    la, na, _ = be.icl_side(S3[r0:r0 + nx], S3[Bp:3 * Bp], B, Bp, inv_tau, r0, nx)
-                    lb, nb, _ = be.icl_side(S3[Bp + r0:Bp + r0 + nx], S3[0:2 * Bp], B, Bp, inv_tau, r0, nx)
-                    loc[0, :nx], loc[1, :nx], loc[2, :nx], loc[3, :nx] = la, na, lb, nb
-                allv = shard.all_gather(loc).permute(1, 0, 2).reshape(4, -1)[:, :B]      # [4, B] in anchor order
-                lse_a, nll_a, lse_b, nll_b = (allv[i].contiguous() for i in range(4))
+                lse_a, nll_a, lse_b, nll_b = (allv[p, i] for i in range(4))
             saved += [S3, lse_a, lse_b, emb]
             outs += [nll_a, nll_b]
             dims.append(D)
@@ -242,39 +246,52 @@ class _IclMany(torch.autograd.Function):
                 kp = {"keep_parts": True} if (shard.world == 1 and hasattr(be, "normalize_bwd_scatter_many")) else {}
                 dz[p] = (be.grad_contract(Ga, Ya.t().contiguous(), nx, D, **kp), be.grad_contract(Gb, Yb.t().contiguous(), nx, D, **kp))
         out = []
-        batched = shard.world == 1 and hasattr(be, "normalize_bwd_scatter_many")
-        if batched:                                       # both sides of every table: one launch
-            live = [p for p in range(n) if probs[p] is not None]
-            dembs = {p: torch.zeros_like(probs[p]["emb"]) for p in live}
-            if live:
-                be.normalize_bwd_scatter_many([probs[p]["emb"] for p in live], idx_l, idx_r, [dz[p] for p in live],
-                                              [dembs[p] for p in live], nrm)
-        for p in range(n):
-            if probs[p] is None:
-                out.append(None)
-                continue
-            if batched:
-                out.append(dembs[p])
-                continue
-            emb, D = probs[p]["emb"], probs[p]["D"]
-            demb = torch.zeros_like(emb)
-            if shard.world == 1:
-                be.normalize_bwd_scatter(emb, idx_l, dz[p][0], demb, nrm)
-                be.normalize_bwd_scatter(emb, idx_r, dz[p][1], demb, nrm)
+        many = hasattr(be, "normalize_bwd_scatter_many")
+        live = [p for p in range(n) if probs[p] is not None]
+        dembs = {p: torch.zeros_like(probs[p]["emb"]) for p in live}
+
+        def scatter(il, ir, pairs):
+            """d emb[p] += backward of normalise + gather applied to (dz_a, dz_b) of every live table"""
+            if many:                                      # both sides of every table: one launch
+                be.normalize_bwd_scatter_many([probs[p]["emb"] for p in live], il, ir, pairs, [dembs[p] for p in live], nrm)
             else:
-                loc = torch.zeros((2, per, D), dtype=torch.float32, device=emb.device)
+                for p, (ga, gb) in zip(live, pairs):
+                    be.normalize_bwd_scatter(probs[p]["emb"], il, ga, dembs[p], nrm)
+                    be.normalize_bwd_scatter(probs[p]["emb"], ir, gb, dembs[p], nrm)
+
+        if live and shard.world == 1:
+            if many:
+                scatter(idx_l, idx_r, [dz[p] for p in live])
+            else:
+                scatter(idx_l, idx_r, [tuple(t.sum(0) if t.dim() == 3 else t for t in dz[p]) for p in live])
+        elif live:
+            # the owned rows of dA, dB of every table in one flat buffer: one all-gather (grads="gather") instead of one
+            # per table, then one scatter launch
+            sizes = [2 * per * dims[p] for p in live]
+            flat = torch.zeros((sum(sizes),), dtype=torch.float32, device=idx_l.device)
+            locs, off = [], 0
+            for p, sz in zip(live, sizes):
+                loc = flat[off:off + sz].view(2, per, dims[p])
+                off += sz
                 if nx > 0:
                     for s_ in range(2):
                         t = dz[p][s_]
-                        loc[s_, :nx] = (t.sum(0) if t.dim() == 3 else t)[:, :D]
-                if shard.grads == "gather":
-                    allg = shard.all_gather(loc).permute(1, 0, 2, 3).reshape(2, -1, D)[:, :B]   # [2, B, D]
-                    be.normalize_bwd_scatter(emb, idx_l, allg[0].contiguous(), demb, nrm)
-                    be.normalize_bwd_scatter(emb, idx_r, allg[1].contiguous(), demb, nrm)
-                elif r1 > r0:                 # "local": only the owned anchors' rows; the SUM over ranks is the gradient
-                    be.normalize_bwd_scatter(emb, idx_l[r0:r1].contiguous(), loc[0, :r1 - r0].contiguous(), demb, nrm)
-                    be.normalize_bwd_scatter(emb, idx_r[r0:r1].contiguous(), loc[1, :r1 - r0].contiguous(), demb, nrm)
-            out.append(demb)
+                        loc[s_, :nx] = (t.sum(0) if t.dim() == 3 else t)[:, :dims[p]]
+                locs.append(loc)
+            if shard.grads == "gather":
+                allf = shard.all_gather(flat)                                            # [world, total]
+                pairs, off = [], 0
+                for p, sz in zip(live, sizes):
+                    g = allf[:, off:off + sz].reshape(shard.world, 2, per, dims[p]).permute(1, 0, 2, 3) \
+                        .reshape(2, shard.world * per, dims[p])                          # anchor order, contiguous copy
+                    off += sz
+                    pairs.append((g[0], g[1]))
+                scatter(idx_l, idx_r, pairs)
+            elif r1 > r0:                 # "local": only the owned anchors' rows; the SUM over ranks is the gradient
+                cnt = r1 - r0
+                scatter(idx_l[r0:r1].contiguous(), idx_r[r0:r1].contiguous(), [(loc[0, :cnt], loc[1, :cnt]) for loc in locs])
+        for p in range(n):
+            out.append(dembs.get(p))
         return (None, None, None, None, None, *out)
 
 
@@ -311,16 +328,13 @@ class icl_loss(nn.Module):
             raise NotImplementedError("explicit negatives (MEAformer replay, MEAformer.py:126) are outside the SNAG path")
         if self.inversion:
             raise NotImplementedError("inversion=True is unreachable from SNAG (model/SNAG.py:50-51)")
-        if not norm:
-            # no caller in the reference passes norm=False (model/SNAG.py:106,147-159; MCLEA.py; MEAformer.py)
-            raise NotImplementedError("norm=False: the fused kernel relies on unit rows (logits bounded by 1/tau)")
         if self.n_view != 2:
             # the reference itself fails here: labels are [B, B*n_view] against logits [B, 2B] (model/SNAG_loss.py:84-89)
             raise RuntimeError(f"n_view={self.n_view}: labels [B, B*n_view] do not match the [B, 2B] logits "
                                f"(model/SNAG_loss.py:84-89 raises as well)")
-        return self.forward_many([emb], train_links, [weight_norm])[0]
+        return self.forward_many([emb], train_links, [weight_norm], norm=norm)[0]
 
-    def forward_many(self, embs, train_links, weight_norms=None):
+    def forward_many(self, embs, train_links, weight_norms=None, norm=True):
         """The same loss for several embedding tables that share the batch `train_links` (what one SNAG step does 2 + 2M
         times, model/SNAG.py:106,147-159): returns one scalar per table, each equal to forward(emb, train_links,
         weight_norm=w). One autograd node covers all tables, so their backward sweeps are batched into one launch."""
@@ -331,8 +345,24 @@ class icl_loss(nn.Module):
                                f"(model/SNAG_loss.py:84-89 raises as well)")
         weight_norms = [None] * len(embs) if weight_norms is None else list(weight_norms)
         idx_l, idx_r = _links_to_index(train_links, embs[0].device)
+        embs = [e.float() for e in embs]
+        inv_tau = _check_tau(self.tau)
+        if not norm:
+            # model/SNAG_loss.py:59 skips F.normalize (no caller in the reference does: model/SNAG.py:106,147-159; MCLEA.py;
+            # MEAformer.py). The sweeps evaluate exp(s/tau - 1/tau) with the fixed maximum 1/tau, i.e. they need |s| <= 1:
+            # scale the rows by a power of two 2^-e (exact in fp32 and bf16) so that the largest gathered row has norm <= 1
+            # and fold 4^e into the temperature — s/tau is unchanged, term by term.
+            with torch.no_grad():
+                m2 = max(float(torch.maximum(e.index_select(0, idx_l).square().sum(1).max(),
+                                             e.index_select(0, idx_r).square().sum(1).max())) for e in embs)
+            e2 = max(0, int(np.ceil(0.5 * np.log2(max(m2, 1e-30)))))
+            inv_tau = inv_tau * 4.0 ** e2
+            if inv_tau > MAX_INV_TAU:
+                raise ValueError(f"norm=False with squared row norms up to {m2:.3g} at tau={self.tau}: logits reach "
+                                 f"{inv_tau:.3g}, beyond the fused kernels' range of {MAX_INV_TAU:g}")
+            embs = [e * (2.0 ** -e2) for e in embs]
         # normalising only the 2B gathered rows equals normalising all N first (model/SNAG_loss.py:60-64), row by row
-        nll = _IclMany.apply(idx_l, idx_r, _check_tau(self.tau), self.shard or _unsharded(), True, *[e.float() for e in embs])
+        nll = _IclMany.apply(idx_l, idx_r, inv_tau, self.shard or _unsharded(), bool(norm), *embs)
         batch = idx_l.numel()
         alpha = self.weight
         losses = []

@@ -705,14 +705,17 @@ def matrix_rank(dist: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
     return cnt_row, cnt_col
 
 
+CSLS_MATRIX_K_MAX = 1024      # snag_csls_sim: k <= KT through the candidate-list passes, above that by radix selection
+
+
 def csls_sim_matrix(sim: torch.Tensor, k: int, want_out: bool = True):
     """csls_sim on a materialised fp32 matrix: returns (out or None, nv1, nv2)."""
     _need(sim, torch.float32, "sim_mat", 2)
     n1, n2 = sim.shape
     if k > n1 or k > n2:
         raise RuntimeError("selected index k out of range")          # torch.topk's error in the reference
-    if not 1 <= k <= KT:
-        raise SnagError(f"csls_k={k} unsupported: at most {KT} neighbours")
+    if not 1 <= k <= CSLS_MATRIX_K_MAX:
+        raise SnagError(f"csls_k={k} unsupported: at most {CSLS_MATRIX_K_MAX} neighbours on a materialised matrix")
     ws = torch.empty((_lib.load().snag_csls_workspace_bytes(n1, n2) // 4,), dtype=torch.float32, device=sim.device)
     nv1 = torch.empty((n1,), dtype=torch.float32, device=sim.device)
     nv2 = torch.empty((n2,), dtype=torch.float32, device=sim.device)

@@ -306,6 +306,43 @@ def test_csls_sim_dropin_bitwise(cuda_device, n1, n2, k):
         evaluate.csls_sim(torch.from_numpy(sim[:4, :4].copy()).to(cuda_device), 5)     # k > n, as torch.topk raises
 
 
+@pytest.mark.parametrize("n1,n2,k", [(300, 421, 17), (700, 650, 64), (1500, 1100, 1000), (64, 2100, 33)])
+def test_csls_sim_dropin_large_k_bitwise(cuda_device, n1, n2, k):
+    """k beyond the candidate-list length (the reference's torch.topk takes any k): radix selection + sorted
+    largest-first sum, bit-identical to the oracle — including rows with many copies of the k-th value."""
+    rng = np.random.RandomState(n1 + n2 + k)
+    sim = rng.randn(n1, n2).astype(np.float32)
+    sim[3, :] = np.float32(0.25)                 # a constant row: every copy of the k-th value
+    sim[:, 5] = np.round(sim[:, 5] * 4) / 4      # a column with heavy ties
+    sim[7, :40] = -0.0
+    got = evaluate.csls_sim(torch.from_numpy(sim).to(cuda_device), k)
+    ref, nv1, nv2 = oracle.csls_sim(sim, k, return_nv=True)
+    _, g1, g2 = ops.csls_sim_matrix(torch.from_numpy(sim).to(cuda_device), k, want_out=False)
+    np.testing.assert_array_equal(g1.cpu().numpy(), nv1)
+    np.testing.assert_array_equal(g2.cpu().numpy(), nv2)
+    np.testing.assert_array_equal(got.cpu().numpy(), ref)
+
+
+def test_evaluation_with_large_k_is_the_reference_composition(cuda_device):
+    """csls_k > KT no longer raises: evaluate_alignment takes the materialised route and returns what the reference's
+    call sequence (main.py:386-429) returns on the same distance matrix."""
+    rng = np.random.RandomState(5)
+    n, d, k = 900, 200, 40
+    emb = torch.from_numpy(rng.randn(2 * n, d).astype(np.float32)).to(cuda_device)
+    emb[n:] = emb[:n] + 2.0 * torch.from_numpy(rng.randn(n, d).astype(np.float32)).to(cuda_device)
+    left, right = torch.arange(n, device=cuda_device), torch.arange(n, 2 * n, device=cuda_device)
+    out = evaluate.evaluate_alignment(emb, left, right, csls=True, csls_k=k)
+    assert out["ranks"].info["materialised"]
+    fe = torch.nn.functional.normalize(emb)
+    distance = evaluate.pairwise_distances(fe[left], fe[right])
+    sim = (1 - distance).cpu().numpy()
+    ref = 1 - torch.from_numpy(oracle.csls_sim(sim, k))
+    want = np.asarray([(torch.sort(ref[i], stable=True)[1] == i).nonzero().item() for i in range(n)], np.int32)
+    np.testing.assert_array_equal(out["ranks"].rank_l2r.cpu().numpy(), want)
+    want_c = np.asarray([(torch.sort(ref[:, j], stable=True)[1] == j).nonzero().item() for j in range(n)], np.int32)
+    np.testing.assert_array_equal(out["ranks"].rank_r2l.cpu().numpy(), want_c)
+
+
 def test_reference_call_sequence_materialised(cuda_device):
     """main.py:386-393 exactly as the reference writes it, through the two materialising drop-ins."""
     fx = load_golden("eval_n384_d96_k10")

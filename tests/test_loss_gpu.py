@@ -155,6 +155,38 @@ def test_icl_oracle_numpy(cuda_device):
     np.testing.assert_allclose(got.item(), float(ref), rtol=2e-3)
 
 
+def test_icl_norm_false_matches_oracle_and_torch(cuda_device):
+    """icl_loss(..., norm=False) (model/SNAG_loss.py:59): un-normalised rows. The fused path scales them by an exact power
+    of two and folds it into the temperature; loss against the oracle, gradient against fp32 torch autograd of the
+    reference's op sequence on the same bf16-rounded rows. Rows too long for the kernels' range raise ValueError."""
+    rng = np.random.RandomState(4)
+    N, D, B, tau = 400, 96, 150, 0.5
+    emb = oracle.bf16_round((rng.randn(N, D) * 0.17).astype(np.float32))           # squared norms ~ 2.8: e = 1, 1/tau' = 8
+    links = np.stack([rng.permutation(N // 2)[:B], N // 2 + rng.permutation(N // 2)[:B]], 1).astype(np.int32)
+    wn = (rng.rand(N) + 0.5).astype(np.float32)
+    ref = oracle.icl_loss(emb, links, tau, 0.4, wn, norm=False)
+    e = torch.from_numpy(emb).to(cuda_device).requires_grad_(True)
+    got = sloss.icl_loss(tau, 0.4)(e, links, weight_norm=torch.from_numpy(wn).to(cuda_device), norm=False)
+    np.testing.assert_allclose(got.item(), float(ref), rtol=5e-4)
+    got.backward()
+    t = torch.from_numpy(emb).to(cuda_device).requires_grad_(True)
+    il, ir = torch.from_numpy(links[:, 0].astype(np.int64)).to(cuda_device), torch.from_numpy(links[:, 1].astype(np.int64)).to(cuda_device)
+    a, b = t[il], t[ir]
+    eye = torch.eye(B, device=cuda_device) * 1e9
+    la = torch.cat([a @ b.t() / tau, a @ a.t() / tau - eye], 1)
+    lb = torch.cat([b @ a.t() / tau, b @ b.t() / tau - eye], 1)
+    w = torch.minimum(torch.from_numpy(wn).to(cuda_device)[il], torch.from_numpy(wn).to(cuda_device)[ir])
+    ar = torch.arange(B, device=cuda_device)
+    nll_a = -torch.log_softmax(la, 1)[ar, ar]
+    nll_b = -torch.log_softmax(lb, 1)[ar, ar]
+    loss = 0.4 * (nll_a * w).sum() / B + 0.6 * (nll_b * w).sum() / B
+    loss.backward()
+    np.testing.assert_allclose(got.item(), loss.item(), rtol=5e-4)
+    assert _relerr(e.grad, t.grad) < 1e-2
+    with pytest.raises(ValueError):
+        sloss.icl_loss(0.05, 0.5)(torch.randn(60, 300, device=cuda_device), links[:20] % 60, norm=False)   # logits ~ 6000
+
+
 def test_icl_interface_contract(cuda_device):
     crit = sloss.icl_loss(tau=0.1, ab_weight=0.5, n_view=2, neg_cross_kg=False)
     emb = torch.randn(50, 32, device=cuda_device)
