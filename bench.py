@@ -499,12 +499,8 @@ def train_bench(ctx, args, name, cpu_leg=True):
     W, K = max(3, args.warmup), max(1, args.steps)
     streams, hidden, joint, joint_fz, wn, links, leaves = _train_tables(B, M, dm, dev)
     layer = sloss.SnagLossLayer(tau=0.1, ab_weight=0.5).to(dev)       # --awloss 0 (config.py:114): the reference's default
-    if group is not None:
-        layer.distribute(group, grads="gather")
     links_pinned = torch.from_numpy(links).pin_memory()
     links_dev = links_pinned.to(dev)
-    eager_ms = None
-    graph_note = None
 
     def eager_step():
         for t in leaves:
@@ -513,51 +509,74 @@ def train_bench(ctx, args, name, cpu_leg=True):
         loss.backward()
         return loss
 
-    for _ in range(3):
-        eager_step()
-    torch.cuda.synchronize()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ctx.barrier()
-    a.record()
-    for _ in range(K):
-        eager_step()
-    b.record()
-    ctx.barrier()
-    eager_ms = ctx.max_over_ranks(a.elapsed_time(b) / K)
-    # Whole-step CUDA graph: every entry point of libsnag_b200.so only enqueues on the stream it is given, and NCCL's
-    # all-gathers are capturable, so the sharded step replays as one graph launch as well (at the reference's batch
-    # sizes the eager step is launch bound). Every rank must take the same path: agree on the outcome of the capture.
-    use_graph = not args.no_graph
-    graphed = None
-    if use_graph:
-        ok = 1.0
-        try:
-            from snag_b200.graphs import GraphedStep
-            graphed = GraphedStep(lambda: layer(streams, hidden, joint, joint_fz, links_dev, wn), leaves)
-        except Exception as exc:                          # noqa: BLE001 — reported on the bench line, eager numbers stand
-            ok, graph_note = 0.0, f"graph capture failed on rank {rank}: {type(exc).__name__}: {exc}"[:300]
-        if -ctx.max_over_ranks(-ok) < 1.0:
-            use_graph, graphed = False, None
-            graph_note = graph_note or "graph capture failed on another rank"
-
-    def step(from_host):
-        if from_host:                                       # this step's batch arrives from pinned host memory
-            links_dev.copy_(links_pinned, non_blocking=True)
-        loss = graphed() if use_graph else eager_step()
-        return loss.item() if from_host else loss
-
-    for _ in range(W):
-        step(False)
-    ctx.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(ctx.local) as clocks:
+    def measure(grads_mode):
+        """Timed region of the slice with the gradient exchange `grads_mode` ("local": every rank returns the rows of
+        dL/d emb of the anchors it owns, zeros elsewhere — the sum over ranks is the gradient, which the data-parallel
+        gradient all-reduce of a replicated encoder completes anyway; "gather": the owned rows are all-gathered so that
+        every rank returns the full gradient, as an unsharded call would)."""
+        if group is not None:
+            layer.distribute(group, grads=grads_mode)
+        graph_note = None
+        for _ in range(3):
+            eager_step()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ctx.barrier()
-        e0.record()
+        a.record()
         for _ in range(K):
-            step(False)
-        e1.record()
+            eager_step()
+        b.record()
         ctx.barrier()
-    ms_per_step = ctx.max_over_ranks(e0.elapsed_time(e1) / K)
+        eager_ms = ctx.max_over_ranks(a.elapsed_time(b) / K)
+        # Whole-step CUDA graph: every entry point of libsnag_b200.so only enqueues on the stream it is given, and NCCL's
+        # all-gathers are capturable, so the sharded step replays as one graph launch as well (at the reference's batch
+        # sizes the eager step is launch bound). Every rank must take the same path: agree on the outcome of the capture.
+        use_graph = not args.no_graph
+        graphed = None
+        if use_graph:
+            ok = 1.0
+            try:
+                from snag_b200.graphs import GraphedStep
+                graphed = GraphedStep(lambda: layer(streams, hidden, joint, joint_fz, links_dev, wn), leaves)
+            except Exception as exc:                          # noqa: BLE001 — reported on the bench line, eager numbers stand
+                ok, graph_note = 0.0, f"graph capture failed on rank {rank}: {type(exc).__name__}: {exc}"[:300]
+            if -ctx.max_over_ranks(-ok) < 1.0:
+                use_graph, graphed = False, None
+                graph_note = graph_note or "graph capture failed on another rank"
+
+        def step(from_host):
+            if from_host:                                       # this step's batch arrives from pinned host memory
+                links_dev.copy_(links_pinned, non_blocking=True)
+            loss = graphed() if use_graph else eager_step()
+            return loss.item() if from_host else loss
+
+        for _ in range(W):
+            step(False)
+        ctx.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(ctx.local) as clocks:
+            ctx.barrier()
+            e0.record()
+            for _ in range(K):
+                step(False)
+            e1.record()
+            ctx.barrier()
+        ms = ctx.max_over_ranks(e0.elapsed_time(e1) / K)
+        # end to end: the step's input (the batch of links) comes from pinned host memory, the loss goes back to the host
+        step(True)
+        ctx.barrier()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            lv = step(True)
+        ctx.barrier()
+        dt = ctx.max_over_ranks((time.perf_counter() - t0) / K)
+        del graphed
+        return {"ms": ms, "eager_ms": eager_ms, "use_graph": use_graph, "graph_note": graph_note, "clocks": clocks.summary(),
+                "e2e_s": dt, "loss": lv}
+
+    gather = measure("gather") if group is not None else None
+    head = measure("local")
+    ms_per_step, eager_ms, use_graph, graph_note = head["ms"], head["eager_ms"], head["use_graph"], head["graph_note"]
     # per-kernel CUDA events cannot be recorded into a replayed graph: time the sweeps of K eager steps of the same work
     events = []
     ops.SWEEP_EVENT_SINK = events
@@ -584,30 +603,33 @@ def train_bench(ctx, args, name, cpu_leg=True):
                 "kernels": kstats, "note": "flops counted on the padded contraction width the kernel executes",
                 "algorithmic_flops_per_step": alg_fwd + alg_bwd,
                 "algorithmic_tflops_whole_step": (alg_fwd + alg_bwd) / world / ms_per_step / 1e9}
-    # end to end: the step's input (the batch of links) comes from pinned host memory, the loss goes back to the host
-    step(True)
-    ctx.barrier()
-    t0 = time.perf_counter()
-    for _ in range(K):
-        lv = step(True)
-    ctx.barrier()
-    dt = ctx.max_over_ranks((time.perf_counter() - t0) / K)
+    dt, lv = head["e2e_s"], head["loss"]
     out = {"metric": TRAIN_METRIC, "value": 1e3 / ms_per_step, "unit": "steps/s", "n_gpus": world, "steps": K, "warmup": W,
            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
            "dtype": "bf16 operands, fp32 accumulate (tcgen05 kind::f16), fp32 softmax statistics",
            "data": "synthetic",
            "config": {"workload": name, "description": desc, "batch": B, "modalities": M, "width": dm, "tau": 0.1,
                       "icl_calls_per_step": n_calls, "parallelism": f"anchors sharded over {world} rank(s)", "awloss": 0,
+                      "grads": "n/a (one rank)" if group is None else
+                               "local: each rank returns the rows of dL/d emb of its own anchors; their sum over the ranks is the "
+                               "gradient (what a data-parallel trainer's gradient all-reduce forms) — the all-gathered form is "
+                               "timed beside it as grads_gather",
                       "cuda_graph": use_graph, "graph_note": graph_note, "eager_ms_per_step": eager_ms,
                       "l2": "every step rewrites the bf16 operands and gradients (> L2) between launches"},
-           "clocks": clocks.summary(),
+           "clocks": head["clocks"],
            "e2e": {"value": 1.0 / dt, "unit": "steps/s", "h2d_bytes_per_step": int(links_pinned.numel() * 4),
                    "d2h_bytes_per_step": 4, "ms_per_step": dt * 1e3, "loss": lv},
            "gpu_launches": (sum(v["launches"] for v in kern.values()) // K + 4 * n_calls) * K,
            "roofline": roofline}
+    if gather is not None:
+        out["grads_gather"] = {"ms_per_step": gather["ms"], "value": 1e3 / gather["ms"], "unit": "steps/s",
+                               "eager_ms_per_step": gather["eager_ms"], "cuda_graph": gather["use_graph"],
+                               "e2e_ms_per_step": gather["e2e_s"] * 1e3,
+                               "what": "the same step with the owned gradient rows all-gathered: every rank returns the full "
+                                       "dL/d emb of all 2 + 2M tables"}
     if cpu_leg and rank == 0:
         out["cpu_baseline"] = cpu_icl_sample(min(B, 1024), M, dm, 1, B)
-    del graphed, layer, streams, hidden, joint, joint_fz, wn, leaves
+    del layer, streams, hidden, joint, joint_fz, wn, leaves
     torch.cuda.empty_cache()
     return out
 

@@ -21,8 +21,13 @@ from tests.conftest import golden_names, load_golden
 
 pytestmark = pytest.mark.gpu
 
-IAL_GOLDEN_LOSS_RTOL, IAL_GOLDEN_GRAD_RTOL = 3e-2, 5e-2
-IAL_LOSS_RTOL, IAL_GRAD_RTOL = 2e-2, 3e-2
+# Measured (scripts/ial_diag.py, profiles/r02s_ial_error_vs_fp64.log, profiles/r02y_ial_golden_errors.log): against an fp64
+# evaluation of the same bf16-rounded operands the fused path is within 3e-4 (loss) / 2.6e-3 (gradient), a plain fp32 torch
+# evaluation within 5.5e-5 / 2e-5; against the reference's fp32 goldens on UNROUNDED rows 1.6e-3 / 4.0e-3, of which 3.0e-3 to
+# 3.5e-3 of the gradient difference is the bf16 rounding of the inputs itself (an fp64 evaluation of the rounded rows
+# shows it). The bounds below leave a factor >= 3.
+IAL_GOLDEN_LOSS_RTOL, IAL_GOLDEN_GRAD_RTOL = 5e-3, 2e-2
+IAL_LOSS_RTOL, IAL_GRAD_RTOL = 2e-3, 1e-2
 
 
 def _relerr(a, b):
