@@ -134,6 +134,28 @@ int snag_icl_bwd_fused(int32_t n_prob, const uint16_t* const* S3, const float* c
                        const float* const* dg, float* const* dz_a, float* const* dz_b, int32_t B, int32_t Bp, int32_t rb0,
                        int32_t row_blocks, int32_t Dpad, float inv_tau, int32_t nsplit, int64_t part_stride, void* stream);
 
+/* Forward of icl_loss (model/SNAG_loss.py:98-126) for n_prob <= 16 tables that share the batch, on HALF the Gram matrix
+ * of the stacked rows Z = [a ; b] (S3[p]: [>= 2 Bp, Dpad] bf16, each part zero padded to Bp = multiple of 256 rows): the
+ * four logit blocks of the reference are the quadrants of the symmetric Z.Z^T, and both directions' softmax denominators
+ * are its row sums without the diagonal — only tiles meeting the strict upper triangle are computed, every element
+ * E = exp(s/tau - 1/tau) is added to the row sum of its row and (as a column sum of the tile) of its column.
+ *   snag_icl_fwd_sym_plan : sizes[0] = number of work units of the launch, sizes[1] / sizes[2] = floats of the per-table
+ *                           workspaces rowpart / colpart
+ *   snag_icl_fwd_sym      : processes the units [unit_begin, unit_end) (all of them: 0, sizes[0]; a rank's contiguous
+ *                           share when the loss is sharded) and writes total[p][r] (fp32 [n_prob, 2 Bp]) = the sum over
+ *                           those units' contributions to sum_{j != r} E[r, j], added in a fixed order, and
+ *                           pos[p][i] = Z_i . Z_{Bp+i} ([n_prob, Bp]; only entries whose tile lies in the unit range are
+ *                           written — zero the buffer first when sharding). Sharded: all-reduce(sum) total and pos.
+ *   snag_icl_sym_finalize : out[p][0..3][i] ([n_prob, 4, B]) = lse_a, nll_a, lse_b, nll_b of anchor i:
+ *                           lse = log(total) + 1/tau, nll = lse - pos/tau.
+ * Pointer arguments S3 / rowpart / colpart are HOST arrays of n_prob device pointers. */
+int snag_icl_fwd_sym_plan(int32_t n_prob, int32_t B, int32_t Bp, int64_t* sizes);
+int snag_icl_fwd_sym(int32_t n_prob, const uint16_t* const* S3, float* const* rowpart, float* const* colpart, float* pos,
+                     int32_t B, int32_t Bp, int32_t Dpad, float inv_tau, int32_t unit_begin, int32_t unit_end, float* total,
+                     void* stream);
+int snag_icl_sym_finalize(const float* total, const float* pos, int32_t n_prob, int32_t B, int32_t Bp, float inv_tau,
+                          float* out, void* stream);
+
 /* ---- alignment evaluation ------------------------------------------------------------------- */
 /* pairwise_distances (src/utils.py:202-218), materialising: mode 1: out[i,j] = clamp(xn_i + yn_j - 2 x_i.y_j, 0);
  * mode 0: out[i,j] = x_i.y_j. out is fp32 [n1, ld]. */

@@ -76,6 +76,9 @@ _SIGNATURES = {
     "snag_mutual_nn": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp],
     "snag_icl_rowsum": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _vp, _vp, _vp],
     "snag_icl_finalize": [_vp, _i32, _i32, _i32, _vp, _f32, _vp, _vp, _vp],
+    "snag_icl_fwd_sym_plan": [_i32, _i32, _i32, _vp],
+    "snag_icl_fwd_sym": [_i32, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _f32, _i32, _i32, _vp, _vp],
+    "snag_icl_sym_finalize": [_vp, _vp, _i32, _i32, _i32, _f32, _vp, _vp],
     "snag_icl_bwd_logits": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _i32, _f32, _vp],
 }
 EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["snag_error_string", "snag_csls_workspace_bytes", "snag_sim_write_t_splits",

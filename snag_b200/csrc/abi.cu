@@ -118,6 +118,25 @@ int snag_icl_bwd_fused(int32_t n_prob, const uint16_t* const* S3, const float* c
                               rb0, row_blocks, Dpad, inv_tau, nsplit, part_stride, S(stream));
 }
 
+int snag_icl_fwd_sym_plan(int32_t n_prob, int32_t B, int32_t Bp, int64_t* sizes) {
+  if (!sizes) return SNAG_ERR_ARG;
+  long long out[3];
+  const int rc = icl_fwd_sym_plan(n_prob, B, Bp, out);
+  if (rc) return rc;
+  sizes[0] = out[0]; sizes[1] = out[1]; sizes[2] = out[2];
+  return SNAG_OK;
+}
+int snag_icl_fwd_sym(int32_t n_prob, const uint16_t* const* S3, float* const* rowpart, float* const* colpart, float* pos,
+                     int32_t B, int32_t Bp, int32_t Dpad, float inv_tau, int32_t unit_begin, int32_t unit_end, float* total,
+                     void* stream) {
+  return launch_icl_fwd_sym(n_prob, reinterpret_cast<const __nv_bfloat16* const*>(S3), rowpart, colpart, pos, B, Bp, Dpad,
+                            inv_tau, unit_begin, unit_end, total, S(stream));
+}
+int snag_icl_sym_finalize(const float* total, const float* pos, int32_t n_prob, int32_t B, int32_t Bp, float inv_tau,
+                          float* out, void* stream) {
+  return launch_icl_sym_finalize(total, pos, n_prob, B, Bp, inv_tau, out, S(stream));
+}
+
 int snag_sim_mainloop_only(const uint16_t* X, const uint16_t* Y, int32_t n1, int32_t n2, int32_t Dpad, void* stream) {
   return launch_sim_null(BF(X), BF(Y), n1, n2, Dpad, S(stream));
 }

@@ -61,6 +61,12 @@ int icl_bwd_fused_splits(int n_prob, int B, int Bp, int row_blocks);
 int launch_icl_bwd_fused(int n_prob, const __nv_bfloat16* const* S3, const float* const* cr_a, const float* const* cr_b,
                          const float* const* dg, float* const* dz_a, float* const* dz_b, int B, int Bp, int rb0,
                          int row_blocks, int Dpad, float inv_tau, int nsplit, long long part_stride, cudaStream_t st);
+// ICL forward on half the Gram matrix, all tables of a step in one launch (icl_fwd_sym.cu)
+int icl_fwd_sym_plan(int n_prob, int B, int Bp, long long* out);
+int launch_icl_fwd_sym(int n_prob, const __nv_bfloat16* const* S3, float* const* rowpart, float* const* colpart, float* pos,
+                       int B, int Bp, int Dpad, float inv_tau, int unit_begin, int unit_end, float* total, cudaStream_t st);
+int launch_icl_sym_finalize(const float* total, const float* pos, int n_prob, int B, int Bp, float inv_tau, float* out,
+                            cudaStream_t st);
 int launch_topk_merge_mean(const float* part, const int* part_idx, int n_lists, long long n_rows, int k, float* nv,
                            float* cand_out, int* cand_idx_out, cudaStream_t st);
 int launch_topk_rescore(const __nv_bfloat16* A, const __nv_bfloat16* B, int Dpad, long long n_rows, const float* an,

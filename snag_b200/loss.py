@@ -118,6 +118,13 @@ class AnchorShard:
         r0 = min(self.rank * per, B)
         return r0, min(r0 + per, B), per
 
+    def all_reduce(self, t: torch.Tensor) -> torch.Tensor:
+        """elementwise sum over the ranks (in place)"""
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(t, group=self.group)
+        return t
+
     def all_gather(self, t: torch.Tensor) -> torch.Tensor:
         """[...] per rank -> [world, ...]"""
         if self.world == 1:
@@ -142,6 +149,9 @@ def _unsharded() -> AnchorShard:
 # recomputed, dL/dlogits formed in registers and kept in tensor memory as the A operand of a second tcgen05.mma — no
 # [B, 2B] matrix in HBM. Wider tables (the joint embeddings) keep the two-kernel form, where the MMAs dominate anyway.
 FUSED_BACKWARD = os.environ.get("SNAG_FUSED_BACKWARD", "1") != "0"      # A/B switch for measurements
+# Forward on half the Gram matrix of the stacked rows, all tables of a step in one launch per contraction width
+# (ops.icl_fwd_sym); off: two per-side sweeps per table (sim_kernel<EpiIclFwd>), which execute the whole matrix.
+SYM_FORWARD = os.environ.get("SNAG_SYM_FORWARD", "1") != "0"
 
 
 class _IclMany(torch.autograd.Function):
@@ -172,7 +182,21 @@ class _IclMany(torch.autograd.Function):
                 S3[2 * Bp:2 * Bp + B].copy_(S3[0:B])
                 stacks.append(S3)
         loc_all = None
-        if shard.world > 1:
+        stats = None
+        if SYM_FORWARD and hasattr(be, "icl_fwd_sym"):
+            # sharded: every rank takes a contiguous share of the launch's work units (tiles of the half matrix, not
+            # anchors) and one all-reduce of the partial row sums replaces the all-gather of per-anchor results
+            stats = [None] * len(embs)
+            by_width = {}
+            for p, S3 in enumerate(stacks):
+                by_width.setdefault(S3.shape[1], []).append(p)
+            for group in by_width.values():
+                for i in range(0, len(group), ops.ICL_SYM_MAX_PROBLEMS):
+                    chunk = group[i:i + ops.ICL_SYM_MAX_PROBLEMS]
+                    res = be.icl_fwd_sym([stacks[p] for p in chunk], B, Bp, inv_tau, shard.rank, shard.world, shard.all_reduce)
+                    for q, p in enumerate(chunk):
+                        stats[p] = res[q]
+        elif shard.world > 1:
             # this rank's anchors of every table, then ONE all-gather of the per-anchor (lse, nll) of both sides
             loc_all = torch.zeros((len(embs), 4, per), dtype=torch.float32, device=embs[0].device)
             if r1 > r0:
@@ -184,7 +208,9 @@ class _IclMany(torch.autograd.Function):
             allv = shard.all_gather(loc_all).permute(1, 2, 0, 3).reshape(len(embs), 4, -1)[:, :, :B].contiguous()   # anchor order
         for p, (emb, S3) in enumerate(zip(embs, stacks)):
             D = emb.shape[1]
-            if shard.world == 1:
+            if stats is not None:
+                lse_a, nll_a, lse_b, nll_b = (stats[p][i] for i in range(4))
+            elif shard.world == 1:
                 lse_a, nll_a, _ = be.icl_side(S3[0:Bp], S3[Bp:3 * Bp], B, Bp, inv_tau)
                 lse_b, nll_b, _ = be.icl_side(S3[Bp:2 * Bp], S3[0:2 * Bp], B, Bp, inv_tau)
             else:

@@ -747,6 +747,49 @@ def icl_side(X: torch.Tensor, Y: torch.Tensor, B: int, Bp: int, inv_tau: float, 
     return lse, nll, pos
 
 
+ICL_SYM_MAX_PROBLEMS = 16
+
+
+def icl_fwd_sym(S3s, B: int, Bp: int, inv_tau: float, rank: int = 0, world: int = 1, all_reduce=None) -> torch.Tensor:
+    """Forward statistics of icl_loss for several tables that share the batch, on half the Gram matrix of the stacked
+    rows (snag_icl_fwd_sym): S3s[p] = [a ; b ; ...] as [>= 2 Bp, Dpad] bf16 (same Dpad). Returns fp32 [n_prob, 4, B] =
+    (lse_a, nll_a, lse_b, nll_b) per table. With world > 1 this rank processes its contiguous share of the work units
+    and `all_reduce(tensor) -> tensor` (sum over the ranks) combines the partial sums before the logarithm."""
+    import ctypes
+    n_prob = len(S3s)
+    if not 1 <= n_prob <= ICL_SYM_MAX_PROBLEMS:
+        raise ValueError(f"1..{ICL_SYM_MAX_PROBLEMS} tables per launch")
+    dpad = S3s[0].shape[1]
+    for t in S3s:
+        _check_operand(t, "S3")
+        if t.shape[0] < 2 * Bp or t.shape[1] != dpad:
+            raise ValueError("every stacked operand must be [>= 2 * Bp, Dpad] with the same Dpad")
+    dev = S3s[0].device
+    sizes = (ctypes.c_int64 * 3)()
+    call("snag_icl_fwd_sym_plan", n_prob, B, Bp, sizes)
+    units, rp, cp = int(sizes[0]), int(sizes[1]), int(sizes[2])
+    u0, u1 = units * rank // world, units * (rank + 1) // world
+    rowpart = torch.empty((n_prob, rp), dtype=torch.float32, device=dev)
+    colpart = torch.empty((n_prob, cp), dtype=torch.float32, device=dev)
+    # total and pos travel in one buffer so that a sharded step needs a single all-reduce
+    buf = torch.zeros((n_prob * 3 * Bp,), dtype=torch.float32, device=dev) if world > 1 else \
+        torch.empty((n_prob * 3 * Bp,), dtype=torch.float32, device=dev)
+    total, pos = buf[:n_prob * 2 * Bp], buf[n_prob * 2 * Bp:]
+    arr = lambda ts: (ctypes.c_void_p * n_prob)(*[t.data_ptr() for t in ts])
+    tiles = (2 * Bp // 256) ** 2 + 2 * Bp // 256            # per table: the staircase of 128-row blocks x 256-column tiles
+    share = (u1 - u0) / max(1, units)
+    with _SweepTimer("icl_fwd_sym_kernel", int(n_prob * tiles * share) * 128, 256, dpad):
+        call("snag_icl_fwd_sym", n_prob, arr(S3s), arr([rowpart[i] for i in range(n_prob)]),
+             arr([colpart[i] for i in range(n_prob)]), ptr(pos), B, Bp, dpad, float(inv_tau), u0, u1, ptr(total),
+             current_stream())
+    if world > 1:
+        buf = all_reduce(buf)
+        total, pos = buf[:n_prob * 2 * Bp], buf[n_prob * 2 * Bp:]
+    out = torch.empty((n_prob, 4, B), dtype=torch.float32, device=dev)
+    call("snag_icl_sym_finalize", ptr(total), ptr(pos), n_prob, B, Bp, float(inv_tau), ptr(out), current_stream())
+    return out
+
+
 def icl_bwd_logits(X: torch.Tensor, Y: torch.Tensor, B: int, Bp: int, inv_tau: float, cr: torch.Tensor,
                    cc: torch.Tensor, dg: torch.Tensor, row0: int = 0, nx: int | None = None,
                    self_cols: bool = True, ebar: float = 0.0) -> torch.Tensor:

@@ -111,6 +111,13 @@ class _LockstepShard(sloss.AnchorShard):
         blocks[self.rank] = t.clone()
         return torch.stack([blocks.get(r, torch.zeros_like(t)) for r in range(self.world)], 0)
 
+    def all_reduce(self, t):
+        key = (len(self.store.setdefault(("n", self.rank), [])), tuple(t.shape), "sum")
+        self.store[("n", self.rank)].append(key)
+        blocks = self.store.setdefault(key, {})
+        blocks[self.rank] = t.clone()
+        return sum(blocks[r] for r in sorted(blocks))
+
 
 @pytest.mark.parametrize("B,D,world", [(1000, 300, 2), (700, 96, 3), (3500, 320, 8), (100, 64, 2)])
 def test_icl_anchor_shards_match_full(cuda_device, B, D, world):
@@ -146,6 +153,41 @@ def test_icl_anchor_shards_match_full(cuda_device, B, D, world):
         mask = torch.ones(B, dtype=torch.bool, device=cuda_device)
         mask[r0:r1] = False
         assert float(o[2][mask].abs().max() if mask.any() else 0.0) == 0.0
+
+
+@pytest.mark.parametrize("B,dims,tau", [(1000, (300, 300, 96), 0.1), (3500, (300,) * 8, 0.1), (130, (64,), 0.05),
+                                        (2049, (1200, 1200), 0.1), (256, (320, 64), 0.5)])
+def test_icl_forward_on_half_gram_matches_per_side_sweeps(cuda_device, B, dims, tau):
+    """ops.icl_fwd_sym (upper triangle of [a;b].[a;b]^T, all tables of a width in one launch, row + column sums) against
+    the per-side sweeps ops.icl_side (the whole matrix, one launch per side and table) on the same stacked operands:
+    lse and nll of both directions, per anchor; and the work-unit sharding (3 ranks, summed partial totals)."""
+    g = torch.Generator(device="cuda").manual_seed(B + len(dims))
+    N = 2 * B + 17
+    perm = torch.randperm(N, generator=g, device=cuda_device)
+    il, ir = perm[:B].contiguous(), perm[B:2 * B].contiguous()
+    Bp = ops.round_up(B, 256)
+    embs = [torch.randn((N, d), generator=g, device=cuda_device) for d in dims]
+    for e in embs:                                       # correlated pairs, so that the positive logit matters
+        e[ir] = e[il] + 0.8 * torch.randn((B, e.shape[1]), generator=g, device=cuda_device)
+    stacks = ops.icl_stack_prep(embs, il, ir, Bp, True)
+    by_width = {}
+    for p, S3 in enumerate(stacks):
+        by_width.setdefault(S3.shape[1], []).append(p)
+    for group in by_width.values():
+        got = ops.icl_fwd_sym([stacks[p] for p in group], B, Bp, 1.0 / tau)
+        parts = []
+        for r in range(3):
+            parts.append(ops.icl_fwd_sym([stacks[p] for p in group], B, Bp, 1.0 / tau, r, 3, lambda t, _parts=parts: t))
+        for q, p in enumerate(group):
+            S3 = stacks[p]
+            la, na, _ = ops.icl_side(S3[0:Bp], S3[Bp:3 * Bp], B, Bp, 1.0 / tau)
+            lb, nb, _ = ops.icl_side(S3[Bp:2 * Bp], S3[0:2 * Bp], B, Bp, 1.0 / tau)
+            for i, ref in enumerate((la, na, lb, nb)):
+                np.testing.assert_allclose(got[q, i].cpu().numpy(), ref.cpu().numpy(), rtol=0, atol=2e-5)
+        # sharded: exp(lse - 1/tau) of the ranks' partial results add up to the full row sums
+        full_sum = torch.exp(got[:, 0::2].double() - 1.0 / tau)
+        shard_sum = sum(torch.exp(pt[:, 0::2].double() - 1.0 / tau) for pt in parts)
+        np.testing.assert_allclose(shard_sum.cpu().numpy(), full_sum.cpu().numpy(), rtol=1e-5)
 
 
 def test_icl_oracle_numpy(cuda_device):
