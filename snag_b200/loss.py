@@ -42,12 +42,15 @@ class CustomMultiLossLayer(nn.Module):
         self.log_vars = nn.Parameter(torch.zeros(self.loss_num, ), requires_grad=True)
 
     def forward(self, loss_list):
-        assert len(loss_list) <= self.loss_num
-        precision = torch.exp(-self.log_vars)
-        loss = 0
-        for i in range(len(loss_list)):
-            loss += precision[i] * loss_list[i] + self.log_vars[i]
-        return loss
+        """sum_i exp(-s_i) * L_i + s_i over the first len(loss_list) entries; an entry may be the int 0 of an absent
+        modality (model/SNAG.py:147-160), which still contributes its s_i."""
+        k = len(loss_list)
+        assert k <= self.loss_num
+        if k == 0:
+            return 0
+        zero = self.log_vars.new_zeros(())
+        terms = torch.stack([l.to(self.log_vars.dtype) if isinstance(l, torch.Tensor) else zero for l in loss_list])
+        return (torch.exp(-self.log_vars[:k]) * terms + self.log_vars[:k]).sum()
 
 
 class AutomaticWeightedLoss(nn.Module):
@@ -155,7 +158,7 @@ SYM_FORWARD = os.environ.get("SNAG_SYM_FORWARD", "1") != "0"
 
 
 class _IclMany(torch.autograd.Function):
-    """(idx_l, idx_r [B], emb_0 .. emb_{n-1} [N, D_p] fp32) -> (nll_a_0, nll_b_0, nll_a_1, ...): per-row NLL of both
+    """(idx_l, idx_r [B], emb_0 .. emb_{n-1} [N, D_p] fp32) -> NLL [n, 2, B] (nll_a, nll_b per table): per-row NLL of both
     directions of the in-batch contrastive loss of the L2-normalised rows emb_p[idx_l], emb_p[idx_r], for n embedding
     tables that share one batch of links (the 2 + 2M icl_loss calls of a step, model/SNAG.py:106,147-159), fused on
     the tensor cores; with an AnchorShard of more than one rank every rank sweeps only its own anchors. Gather +
@@ -206,42 +209,52 @@ class _IclMany(torch.autograd.Function):
                     lb, nb, _ = be.icl_side(S3[Bp + r0:Bp + r0 + nx], S3[0:2 * Bp], B, Bp, inv_tau, r0, nx)
                     loc_all[p, 0, :nx], loc_all[p, 1, :nx], loc_all[p, 2, :nx], loc_all[p, 3, :nx] = la, na, lb, nb
             allv = shard.all_gather(loc_all).permute(1, 2, 0, 3).reshape(len(embs), 4, -1)[:, :, :B].contiguous()   # anchor order
-        for p, (emb, S3) in enumerate(zip(embs, stacks)):
-            D = emb.shape[1]
-            if stats is not None:
-                lse_a, nll_a, lse_b, nll_b = (stats[p][i] for i in range(4))
-            elif shard.world == 1:
-                lse_a, nll_a, _ = be.icl_side(S3[0:Bp], S3[Bp:3 * Bp], B, Bp, inv_tau)
-                lse_b, nll_b, _ = be.icl_side(S3[Bp:2 * Bp], S3[0:2 * Bp], B, Bp, inv_tau)
+        n = len(embs)
+        if stats is not None:
+            groups = list(by_width.values())
+            if len(groups) == 1 and len(groups[0]) <= ops.ICL_SYM_MAX_PROBLEMS:
+                allstats = res                                      # [n, 4, B] of the single launch, already in table order
             else:
-                lse_a, nll_a, lse_b, nll_b = (allv[p, i] for i in range(4))
-            saved += [S3, lse_a, lse_b, emb]
-            outs += [nll_a, nll_b]
-            dims.append(D)
-        ctx.save_for_backward(idx_l, idx_r, *saved)
-        ctx.dims = (B, Bp, inv_tau, bool(normalize), tuple(dims))
+                allstats = torch.stack(stats, 0)
+        else:
+            rows = []
+            for p, S3 in enumerate(stacks):
+                if shard.world == 1:
+                    lse_a, nll_a, _ = be.icl_side(S3[0:Bp], S3[Bp:3 * Bp], B, Bp, inv_tau)
+                    lse_b, nll_b, _ = be.icl_side(S3[Bp:2 * Bp], S3[0:2 * Bp], B, Bp, inv_tau)
+                    rows.append(torch.stack([lse_a, nll_a, lse_b, nll_b], 0))
+                else:
+                    rows.append(allv[p])
+            allstats = torch.stack(rows, 0)
+        lse = allstats[:, 0::2].contiguous()                         # [n, 2, B]
+        nll = allstats[:, 1::2].contiguous()
+        ctx.save_for_backward(idx_l, idx_r, lse, *stacks, *embs)
+        ctx.dims = (B, Bp, inv_tau, bool(normalize), tuple(int(e.shape[1]) for e in embs))
         ctx.shard = shard
-        return tuple(outs)
+        return nll
 
     @staticmethod
-    def backward(ctx, *grads):
-        idx_l, idx_r, *saved = ctx.saved_tensors
+    def backward(ctx, grad):
+        idx_l, idx_r, lse, *saved = ctx.saved_tensors
         B, Bp, inv_tau, nrm, dims = ctx.dims
         shard = ctx.shard
         be = shard.be
         n = len(dims)
+        stacks, embs = saved[:n], saved[n:]
         r0, r1, per = shard.bounds(B)
+        # row coefficients of every table at once: cr_x = g_x exp(1/tau - lse_x), dg = g_a + g_b   ([n, B] each)
+        grad = grad.contiguous().float()
+        cr = grad * torch.exp(inv_tau - lse)
+        dg_all = grad[:, 0] + grad[:, 1]
+        if B % 4:                                         # per-table rows must stay 16-byte aligned
+            cr = torch.nn.functional.pad(cr, (0, 4 - B % 4))
+            dg_all = torch.nn.functional.pad(dg_all, (0, 4 - B % 4))
         probs = []
         for p in range(n):
-            S3, lse_a, lse_b, emb = saved[4 * p:4 * p + 4]
-            g_a, g_b = grads[2 * p], grads[2 * p + 1]
-            if not ctx.needs_input_grad[5 + p] or (g_a is None and g_b is None):
+            if not ctx.needs_input_grad[5 + p]:
                 probs.append(None)
                 continue
-            g_a = torch.zeros_like(lse_a) if g_a is None else g_a.contiguous().float()
-            g_b = torch.zeros_like(lse_b) if g_b is None else g_b.contiguous().float()
-            probs.append(dict(S3=S3, emb=emb, D=dims[p], cra=(g_a * torch.exp(inv_tau - lse_a)).contiguous(),
-                              crb=(g_b * torch.exp(inv_tau - lse_b)).contiguous(), dg=(g_a + g_b).contiguous()))
+            probs.append(dict(S3=stacks[p], emb=embs[p], D=dims[p], cra=cr[p, 0], crb=cr[p, 1], dg=dg_all[p]))
         # the anchors this rank differentiates: all of them, or its shard (whole blocks of 128 rows inside [0, Bp))
         a0, nx = (0, Bp) if shard.world == 1 else (r0, max(0, min(per, Bp - r0)) if r1 > r0 else 0)
         dz = [None] * n                                   # per problem: (dz_a, dz_b), rows = anchors a0 .. a0 + nx
@@ -274,7 +287,13 @@ class _IclMany(torch.autograd.Function):
         out = []
         many = hasattr(be, "normalize_bwd_scatter_many")
         live = [p for p in range(n) if probs[p] is not None]
-        dembs = {p: torch.zeros_like(probs[p]["emb"]) for p in live}
+        # one zero-filled allocation for all gradients (each table's block starts 16-byte aligned)
+        offs, total_el = {}, 0
+        for p in live:
+            offs[p] = total_el
+            total_el += ops.round_up(probs[p]["emb"].numel(), 4)
+        flat_g = torch.zeros((max(total_el, 1),), dtype=torch.float32, device=idx_l.device)
+        dembs = {p: flat_g[offs[p]:offs[p] + probs[p]["emb"].numel()].view_as(probs[p]["emb"]) for p in live}
 
         def scatter(il, ir, pairs):
             """d emb[p] += backward of normalise + gather applied to (dz_a, dz_b) of every live table"""
@@ -326,7 +345,8 @@ class _IclPair:
 
     @staticmethod
     def apply(emb, idx_l, idx_r, inv_tau, shard, normalize=True):
-        return _IclMany.apply(idx_l, idx_r, inv_tau, shard, normalize, emb)
+        out = _IclMany.apply(idx_l, idx_r, inv_tau, shard, normalize, emb)
+        return out[0, 0], out[0, 1]
 
 
 class icl_loss(nn.Module):
@@ -391,20 +411,25 @@ class icl_loss(nn.Module):
         nll = _IclMany.apply(idx_l, idx_r, inv_tau, self.shard or _unsharded(), bool(norm), *embs)
         batch = idx_l.numel()
         alpha = self.weight
-        losses = []
-        for p, weight_norm in enumerate(weight_norms):
-            nll_a, nll_b = nll[2 * p], nll[2 * p + 1]
-            if weight_norm is not None:
-                # :66-69 (index_select: same values and the same argmin routing of the gradient as weight_norm[idx],
-                # with an index_add backward instead of index_put's sort)
-                w = torch.min(torch.stack([weight_norm.index_select(0, idx_l), weight_norm.index_select(0, idx_r)], dim=1), 1)[0]
-                loss_a = (nll_a * w).sum() / batch                                                   # softXEnt :51
-                loss_b = (nll_b * w).sum() / batch
+        # softXEnt (:42-54) and the alpha mix (:126) for all tables at once — the same elementwise operations and one
+        # reduction per table and side as the reference's per-call code, without 2 + 2M rounds of tiny launches
+        weighted = [p for p, w in enumerate(weight_norms) if w is not None]
+        if weighted:
+            # :66-69 — min over (w[left], w[right]); torch.min along a stacked dim routes the gradient to the first
+            # minimum exactly like the reference's torch.min(torch.stack([...], dim=1), 1)[0]
+            wn = torch.stack([weight_norms[p] for p in weighted], 0)                                   # [n_w, N]
+            wmin = torch.min(torch.stack([wn.index_select(1, idx_l), wn.index_select(1, idx_r)], dim=2), 2)[0]   # [n_w, B]
+            if len(weighted) == len(weight_norms):
+                w_all = wmin
             else:
-                loss_a = nll_a.sum() / batch                                                         # softXEnt :53
-                loss_b = nll_b.sum() / batch
-            losses.append(alpha * loss_a + (1 - alpha) * loss_b)
-        return losses
+                ones = torch.ones((batch,), dtype=wmin.dtype, device=wmin.device)
+                it = iter(range(len(weighted)))
+                w_all = torch.stack([wmin[next(it)] if w is not None else ones for w in weight_norms], 0)
+            per_side = (nll * w_all[:, None, :]).sum(2) / batch                                        # softXEnt :51
+        else:
+            per_side = nll.sum(2) / batch                                                              # softXEnt :53
+        loss = alpha * per_side[:, 0] + (1 - alpha) * per_side[:, 1]                                   # :126
+        return list(loss.unbind(0))
 
 
 class _Contract(torch.autograd.Function):
