@@ -168,6 +168,12 @@ int snag_sim_write(const uint16_t* X, const uint16_t* Y, const float* xn, const 
 int snag_sim_write_t_splits(int32_t n1, int32_t n2, int32_t Dpad);
 int snag_sim_write_t(const uint16_t* X, const uint16_t* Y, int32_t n1, int32_t n2, int32_t Dpad, int32_t ksplits, float* out,
                      int64_t ld, int64_t split_stride, void* stream);
+/* snag_sim_write_t with X given TRANSPOSED: XT is [Dpad rows (the contraction index), xt_ld columns] bf16 (xt_ld a
+ * multiple of 64, first n1 columns valid) and its tiles are read MN-major by the tensor cores. For the loss's gradient
+ * GEMMs dX = dL/dlogits . [other ; this] XT is the stacked, normalised embedding matrix as it lies in memory
+ * ([2 Bp, Dpad_emb]): no transposed copy is made. Same outputs and split rules as snag_sim_write_t. */
+int snag_sim_write_t_mn(const uint16_t* XT, int32_t xt_ld, const uint16_t* Y, int32_t n1, int32_t n2, int32_t Dpad,
+                        int32_t ksplits, float* out, int64_t ld, int64_t split_stride, void* stream);
 /* Measurement aid: the same TMA + tcgen05 sweep with the accumulators dropped (no epilogue, no output).
  * Times the mainloop alone so that bench.py can attribute a sweep's time to mainloop vs fused epilogue. */
 int snag_sim_mainloop_only(const uint16_t* X, const uint16_t* Y, int32_t n1, int32_t n2, int32_t Dpad, void* stream);

@@ -41,6 +41,7 @@ _SIGNATURES = {
     "snag_icl_bwd_fused": [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _i32, _i64, _vp],
     "snag_sim_write": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _i64, _vp],
     "snag_sim_write_t": [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _i64, _i64, _vp],
+    "snag_sim_write_t_mn": [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _vp, _i64, _i64, _vp],
     "snag_sim_mainloop_only": [_vp, _vp, _i32, _i32, _i32, _vp],
     "snag_debug_counters": [_vp],
     "snag_sim_readout_only": [_vp, _vp, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _vp],

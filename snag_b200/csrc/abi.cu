@@ -153,6 +153,10 @@ int snag_sim_write(const uint16_t* X, const uint16_t* Y, const float* xn, const 
   return launch_sim_write(BF(X), BF(Y), xn, yn, n1, n2, Dpad, mode, out, ld, S(stream));
 }
 int snag_sim_write_t_splits(int32_t n1, int32_t n2, int32_t Dpad) { return sim_write_t_splits(n1, n2, Dpad); }
+int snag_sim_write_t_mn(const uint16_t* XT, int32_t xt_ld, const uint16_t* Y, int32_t n1, int32_t n2, int32_t Dpad,
+                        int32_t ksplits, float* out, int64_t ld, int64_t split_stride, void* stream) {
+  return launch_sim_write_t_mn(BF(XT), xt_ld, BF(Y), n1, n2, Dpad, ksplits, out, ld, split_stride, S(stream));
+}
 int snag_sim_write_t(const uint16_t* X, const uint16_t* Y, int32_t n1, int32_t n2, int32_t Dpad, int32_t ksplits, float* out,
                      int64_t ld, int64_t split_stride, void* stream) {
   return launch_sim_write_t(BF(X), BF(Y), n1, n2, Dpad, ksplits, out, ld, split_stride, S(stream));

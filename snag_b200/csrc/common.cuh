@@ -162,6 +162,14 @@ __device__ __forceinline__ uint64_t make_sdesc_k128(uint32_t smem_addr) {
          (1ull << 46) | (2ull << 61);
 }
 
+// MN-major shared-memory descriptor over 128-byte-swizzled rows (an operand whose M / N index is the contiguous one:
+// a [K rows x 64 MN-elements] TMA box read "transposed"): atoms of 64 MN-elements x 8 K-rows (1024 B);
+// LBO = byte stride between atoms along MN, SBO = byte stride between 8-row groups along K (1024).
+__device__ __forceinline__ uint64_t make_sdesc_mn128(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4) | (static_cast<uint64_t>(lbo_bytes >> 4) << 16) |
+         (static_cast<uint64_t>(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
 // TMEM -> registers: 32 lanes x 32 consecutive fp32 columns; thread t of the warp owns lane (base+t).
 #define SNAG_TMEM_LD32(taddr, r)                                                                                     \
   asm volatile(                                                                                                      \

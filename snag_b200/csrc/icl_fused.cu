@@ -83,12 +83,6 @@ struct FbParams {
   FbProblem prob[FB_MAX_PROB];
 };
 
-// MN-major shared-memory descriptor over 128-byte-swizzled rows: atoms of 64 MN-elements x 8 K-rows (1024 B);
-// LBO = byte stride between atoms along MN, SBO = byte stride between 8-row groups along K (1024).
-__device__ __forceinline__ uint64_t make_sdesc_mn128(uint32_t smem_addr, uint32_t lbo_bytes) {
-  return static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4) | (static_cast<uint64_t>(lbo_bytes >> 4) << 16) |
-         (static_cast<uint64_t>(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
-}
 // instruction descriptor as make_idesc_bf16, with B read MN-major ([16] b_major = 1)
 __host__ __device__ constexpr uint32_t make_idesc_bf16_bmn(int m, int n) { return make_idesc_bf16(m, n) | (1u << 16); }
 

@@ -149,16 +149,21 @@ int make_operand_map(CUtensorMap* m, const __nv_bfloat16* ptr, long long rows, i
 static unsigned long long* g_dbg_counters = nullptr;
 void set_debug_counters(unsigned long long* p) { g_dbg_counters = p; }
 
+// xt_ld > 0: X is given transposed, as a [Dpad rows, xt_ld columns] matrix whose first n1 columns are the operand
+// (SimShape::a_mn)
 template <class Epi>
 static int launch_sim(const __nv_bfloat16* X, const __nv_bfloat16* Y, int n1, int n2, int Dpad,
-                      const typename Epi::Params& ep, cudaStream_t st, int ksplits = 1) {
+                      const typename Epi::Params& ep, cudaStream_t st, int ksplits = 1, int xt_ld = 0) {
   if (!X || !Y) return SNAG_ERR_ARG;
   if (!device_is_sm100()) return SNAG_ERR_DEVICE;
   SimPlan pl;
   int rc = make_plan(n1, n2, Dpad, &pl);
   if (rc) return rc;
   CUtensorMap tmX, tmY;
-  if ((rc = make_operand_map(&tmX, X, n1, Dpad, BM))) return rc;
+  if (xt_ld > 0) {
+    if ((xt_ld % 64) != 0 || xt_ld < n1) return SNAG_ERR_SHAPE;
+    if ((rc = make_operand_map(&tmX, X, Dpad, xt_ld, 64))) return rc;
+  } else if ((rc = make_operand_map(&tmX, X, n1, Dpad, BM))) return rc;
   if ((rc = make_operand_map(&tmY, Y, n2, Dpad, BN))) return rc;
   // the attribute is per device; setting it on every call is cheap and covers multi-device processes
   const cudaError_t attr_err =
@@ -179,6 +184,7 @@ static int launch_sim(const __nv_bfloat16* X, const __nv_bfloat16* Y, int n1, in
   if (shp.ksplits != ksplits) return SNAG_ERR_SHAPE;                 // the caller sized its partial buffers for ksplits
   if (static_cast<long long>(pl.n_units) * shp.ksplits > 0x7fffffffll) return SNAG_ERR_SHAPE;
   shp.dbg = g_dbg_counters;
+  shp.a_mn = xt_ld > 0 ? 1 : 0;
   const long long all_units = static_cast<long long>(pl.n_units) * shp.ksplits;
   const int grid = all_units < num_sms() ? static_cast<int>(all_units) : num_sms();
   sim_kernel<Epi><<<grid, NUM_CTRL_THREADS + 128 * EpiWG<Epi>::value, SIM_SMEM_BYTES, st>>>(tmX, tmY, shp, ep);
@@ -234,6 +240,15 @@ int launch_sim_write_t(const __nv_bfloat16* X, const __nv_bfloat16* Y, int n1, i
   if (!out || ld < n1 || ksplits < 1 || (ksplits > 1 && split_stride < static_cast<long long>(n2) * ld)) return SNAG_ERR_ARG;
   EpiWrite::Params p{out, ld, nullptr, nullptr, 0, 1, split_stride};
   return launch_sim<EpiWrite>(X, Y, n1, n2, Dpad, p, st, ksplits);
+}
+
+// The same product with X given transposed: XT [Dpad rows (the contraction), xt_ld columns], first n1 columns valid — for
+// the gradient GEMMs XT is the stacked embedding matrix itself ([2 Bp, Dpad_emb]), so no transposed copy is needed.
+int launch_sim_write_t_mn(const __nv_bfloat16* XT, int xt_ld, const __nv_bfloat16* Y, int n1, int n2, int Dpad, int ksplits,
+                          float* out, long long ld, long long split_stride, cudaStream_t st) {
+  if (!out || ld < n1 || ksplits < 1 || (ksplits > 1 && split_stride < static_cast<long long>(n2) * ld)) return SNAG_ERR_ARG;
+  EpiWrite::Params p{out, ld, nullptr, nullptr, 0, 1, split_stride};
+  return launch_sim<EpiWrite>(XT, Y, n1, n2, Dpad, p, st, ksplits, xt_ld);
 }
 
 int launch_eval_rowtopk(const __nv_bfloat16* X, const __nv_bfloat16* Y, const float* xn, const float* yn, int n1, int n2,

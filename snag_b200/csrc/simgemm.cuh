@@ -55,6 +55,9 @@ struct SimShape {
   int n_units;          // row_blocks * n_chunks
   int ksplits;          // split-K factor (1 for every epilogue that needs complete dot products); unit ids run over
   int kb_split;         // [0, n_units * ksplits): split = id / n_units owns k-blocks [split*kb_split, +kb_split)
+  int a_mn;             // 1: the X operand is given TRANSPOSED — tmX maps a [K rows, n_rows columns] matrix (box 64 x 64) and
+                        // the A tile is read MN-major (the gradient GEMMs contract over the rows of the stacked embeddings,
+                        // which are stored with the output dimension contiguous; no transposed copy is made)
   unsigned long long* dbg;   // optional [2*gridDim.x][4] cycle counters (zeroed by the caller) or null. Row cta: UMMA issuer
                              // total, its wait for a free accumulator stage, sum over epilogue warps of strip time,
                              // tiles. Row gridDim.x + cta: sum over epilogue warps of commit + barrier time.
@@ -193,7 +196,12 @@ sim_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
           if (leader) {
             mbar_expect_tx(full_bar(stage), STAGE_BYTES);
             const uint32_t sa = base + stage * STAGE_BYTES;
-            tma_load_2d(sa, &tmX, full_bar(stage), kb * BK, rb * BM);
+            if (shp.a_mn) {          // two [64 k-rows x 64 output columns] boxes: MN-major atoms, 8 KB apart along M
+              tma_load_2d(sa, &tmX, full_bar(stage), rb * BM, kb * BK);
+              tma_load_2d(sa + A_STAGE_BYTES / 2, &tmX, full_bar(stage), rb * BM + 64, kb * BK);
+            } else {
+              tma_load_2d(sa, &tmX, full_bar(stage), kb * BK, rb * BM);
+            }
             tma_load_2d(sa + A_STAGE_BYTES, &tmY, full_bar(stage), kb * BK, ct * BN);
           }
           SNAG_CTRL_SYNC();
@@ -204,7 +212,10 @@ sim_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
   } else if (cwarp == 1) {
     // ------------------------------------------------------------------ UMMA issuer (same structure)
     const uint32_t leader = SNAG_CTRL_LEADER;
-    const uint64_t adesc0 = make_sdesc_k128(base);
+    // K-major A: +2 descriptor units (32 B) per 16-element K step; MN-major A: 16 k-rows = two 8-row groups = 2048 B
+    const uint64_t adesc0 = shp.a_mn ? make_sdesc_mn128(base, A_STAGE_BYTES / 2) : make_sdesc_k128(base);
+    const uint64_t a_kstep = shp.a_mn ? (2048u >> 4) : 2u;
+    const uint32_t a_major = shp.a_mn ? (1u << 15) : 0u;
     const uint64_t bdesc0 = make_sdesc_k128(base + A_STAGE_BYTES);
     uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
     const bool dbg = shp.dbg != nullptr;
@@ -224,7 +235,7 @@ sim_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
         const uint32_t tmem_d = tmem_base + as * BN;
         // ragged last column tile: only the 32-column strips that hold valid columns are computed (UMMA N = 32..256);
         // the epilogue skips the others
-        const uint32_t idesc = make_idesc_bf16(BM, tile_strips(shp, ct) * 32);
+        const uint32_t idesc = make_idesc_bf16(BM, tile_strips(shp, ct) * 32) | a_major;
         uint32_t accumulate = 0;
         for (int kb = 0; kb < n_kb; ++kb) {
           mbar_wait(full_bar(stage), phase);
@@ -234,9 +245,9 @@ sim_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUte
             const uint64_t adesc = adesc0 + static_cast<uint64_t>(stage * (STAGE_BYTES >> 4));
             const uint64_t bdesc = bdesc0 + static_cast<uint64_t>(stage * (STAGE_BYTES >> 4));
             umma_bf16_ss(tmem_d, adesc, bdesc, idesc, accumulate);
-            umma_bf16_ss(tmem_d, adesc + 2u, bdesc + 2u, idesc, 1u);
-            umma_bf16_ss(tmem_d, adesc + 4u, bdesc + 4u, idesc, 1u);
-            umma_bf16_ss(tmem_d, adesc + 6u, bdesc + 6u, idesc, 1u);
+            umma_bf16_ss(tmem_d, adesc + a_kstep, bdesc + 2u, idesc, 1u);
+            umma_bf16_ss(tmem_d, adesc + 2u * a_kstep, bdesc + 4u, idesc, 1u);
+            umma_bf16_ss(tmem_d, adesc + 3u * a_kstep, bdesc + 6u, idesc, 1u);
             umma_commit(empty_bar(stage));           // smem slot free once these MMAs retire
           }
           SNAG_CTRL_SYNC();

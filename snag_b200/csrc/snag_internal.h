@@ -104,6 +104,8 @@ int launch_sim_loadonly(const __nv_bfloat16* X, const __nv_bfloat16* Y, int n1, 
 int launch_sim_write(const __nv_bfloat16* X, const __nv_bfloat16* Y, const float* xn, const float* yn, int n1, int n2,
                      int Dpad, int mode, float* out, long long ld, cudaStream_t st);
 int sim_write_t_splits(int n1, int n2, int Dpad);
+int launch_sim_write_t_mn(const __nv_bfloat16* XT, int xt_ld, const __nv_bfloat16* Y, int n1, int n2, int Dpad, int ksplits,
+                          float* out, long long ld, long long split_stride, cudaStream_t st);
 int launch_sim_write_t(const __nv_bfloat16* X, const __nv_bfloat16* Y, int n1, int n2, int Dpad, int ksplits, float* out,
                        long long ld, long long split_stride, cudaStream_t st);
 int launch_eval_rowtopk(const __nv_bfloat16* X, const __nv_bfloat16* Y, const float* xn, const float* yn, int n1, int n2,

@@ -283,7 +283,11 @@ class _IclMany(torch.autograd.Function):
                 # row i of G carries every term of dL/d(anchor i) — its own softmax row and its appearances as a column
                 # in the other rows' softmaxes (the cc / cr_j terms of EpiIclBwd) — so the owned rows of dA, dB are complete
                 kp = {"keep_parts": True} if (shard.world == 1 and hasattr(be, "normalize_bwd_scatter_many")) else {}
-                dz[p] = (be.grad_contract(Ga, Ya.t().contiguous(), nx, D, **kp), be.grad_contract(Gb, Yb.t().contiguous(), nx, D, **kp))
+                if hasattr(be, "grad_contract_rows"):         # the stacked rows as they lie in memory, read MN-major
+                    dz[p] = (be.grad_contract_rows(Ga, Ya, nx, D, **kp), be.grad_contract_rows(Gb, Yb, nx, D, **kp))
+                else:
+                    dz[p] = (be.grad_contract(Ga, Ya.t().contiguous(), nx, D, **kp),
+                             be.grad_contract(Gb, Yb.t().contiguous(), nx, D, **kp))
         out = []
         many = hasattr(be, "normalize_bwd_scatter_many")
         live = [p for p in range(n) if probs[p] is not None]

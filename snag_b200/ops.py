@@ -914,6 +914,25 @@ def contract(P: torch.Tensor, Q: torch.Tensor, n1: int, n2: int) -> torch.Tensor
     return sim_write(P, Q, None, None, n1, n2, 0)
 
 
+def grad_contract_rows(G: torch.Tensor, Yrows: torch.Tensor, n_rows: int, d: int, keep_parts: bool = False) -> torch.Tensor:
+    """fp32 [n_rows, d] = G[:n_rows] . Yrows[:, :d] for bf16 G [>= n_rows, K] and Yrows [K, Dpad] (contiguous rows, Dpad a
+    multiple of 64, K a multiple of 64): grad_contract without the transposed copy of the stacked embeddings — the tensor
+    cores read Yrows' tiles MN-major (snag_sim_write_t_mn)."""
+    _check_operand(G, "G")
+    _check_operand(Yrows, "Yrows")
+    k = G.shape[1]
+    if Yrows.shape[0] != k or Yrows.shape[1] < d:
+        raise ValueError("Yrows must be [K, >= d] with K = G's contraction width")
+    ks = int(_lib.load().snag_sim_write_t_splits(d, n_rows, k))
+    part = torch.empty((ks, n_rows, d), dtype=torch.float32, device=G.device)
+    with _SweepTimer("sim_kernel<EpiWrite>", d, n_rows, k):
+        call("snag_sim_write_t_mn", ptr(Yrows), Yrows.shape[1], ptr(G), d, n_rows, k, ks, ptr(part), d, n_rows * d,
+             current_stream())
+    if keep_parts:
+        return part
+    return part[0] if ks == 1 else part.sum(0)
+
+
 def grad_contract(G: torch.Tensor, YT: torch.Tensor, n_rows: int, d: int, keep_parts: bool = False) -> torch.Tensor:
     """fp32 [n_rows, d] = G[:n_rows] . YT[:d]^T for bf16 G [>= n_rows, K] and YT [>= d, K] (K a multiple of 64): the
     loss's gradient GEMMs dX = dL/dlogits . [other ; this]. Runs with the d rows of YT as the X operand, the output

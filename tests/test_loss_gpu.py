@@ -411,6 +411,25 @@ def test_fused_backward_kernel_matches_two_kernel_form(cuda_device, B, D, n_prob
             assert float(tot[:, D:].abs().max() if D < dpad else 0.0) == 0.0              # padded columns stay zero
 
 
+@pytest.mark.parametrize("n_rows,d,k", [(256, 300, 512), (1000, 1200, 2048), (3584, 1800, 7168), (130, 64, 256)])
+def test_grad_contract_rows_equals_transposed_form(cuda_device, n_rows, d, k):
+    """snag_sim_write_t_mn (the stacked rows read MN-major by the tensor cores, no transposed copy) against
+    snag_sim_write_t on an explicit transpose, and against fp32 torch."""
+    g = torch.Generator(device="cuda").manual_seed(n_rows + d)
+    dpad = ops.round_up(d, 64)
+    G = (torch.randn((n_rows, k), generator=g, device=cuda_device) * 0.1).to(torch.bfloat16)
+    Y = torch.zeros((k, dpad), dtype=torch.bfloat16, device=cuda_device)
+    Y[:, :d] = torch.randn((k, d), generator=g, device=cuda_device).to(torch.bfloat16)
+    got = ops.grad_contract_rows(G, Y, n_rows, d)
+    ref = ops.grad_contract(G, Y.t().contiguous(), n_rows, d)
+    want = G.float() @ Y.float()[:, :d]
+    assert got.shape == (n_rows, d)
+    assert _relerr(got, want) < 1e-5 and _relerr(ref, want) < 1e-5
+    assert float((got - ref).abs().max()) <= 1e-5 * float(want.abs().max())
+    parts = ops.grad_contract_rows(G, Y, n_rows, d, keep_parts=True)
+    assert _relerr(parts.sum(0), want) < 1e-5
+
+
 @pytest.mark.parametrize("B,D,M", [(1000, 300, 4), (3500, 300, 6)])
 def test_loss_layer_fused_equals_unfused(cuda_device, B, D, M, monkeypatch):
     """The whole loss-layer slice (2 + 2M icl_loss calls) with the batched fused backward against the same slice on the
