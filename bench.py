@@ -816,7 +816,8 @@ def run_snag(args, name):
             train[tname] = train_bench(ctx, args, tname, cpu_leg=(ctx.world == 1))
     if ctx.rank == 0:
         line["train"] = {t: {kk: v[kk] for kk in ("metric", "value", "unit", "ms_per_step", "scaling", "config", "e2e", "roofline",
-                                                    "gpu_launches", "clocks") + (("cpu_baseline",) if "cpu_baseline" in v else ())}
+                                                    "gpu_launches", "clocks") + (("cpu_baseline",) if "cpu_baseline" in v else ()) +
+                             (("grads_gather",) if "grads_gather" in v else ())}
                          for t, v in train.items()}
         n_s = min(CPU_SAMPLE_N, n)
         cb = cpu_port_sample(n_s, d, k, sigma, 3, 1)

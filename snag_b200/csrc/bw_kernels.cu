@@ -573,19 +573,27 @@ __global__ void __launch_bounds__(256) normalize_bwd_scatter_kernel(const float*
 // Optionally also emits the merged KT-list (descending) for the cross-GPU candidate exchange.
 // ------------------------------------------------------------------------------------------------
 // canonical dot product of two bf16 rows: fp64 accumulation in index order, rounded once to fp32 (the oracle's s_ij)
+// Dpad is a multiple of 64: every trip fetches 64 contiguous bytes of each row with four 16-byte loads issued back to
+// back (whole 32-byte sectors; with one 16-byte load per trip the second half of every sector had usually left L1
+// before its turn came — the re-scores are gathers of whole rows and bandwidth bound), then accumulates in index order.
 __device__ __forceinline__ float canonical_dot(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ y, int Dpad) {
   const uint4* xr = reinterpret_cast<const uint4*>(x);
   const uint4* yr = reinterpret_cast<const uint4*>(y);
   double acc = 0.0;
-  for (int c = 0; c < Dpad / 8; ++c) {
-    const uint4 a = __ldg(xr + c), b = __ldg(yr + c);
-    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+  for (int c = 0; c < Dpad / 8; c += 4) {
+    uint4 a[4], b[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float a0 = __uint_as_float(aw[e] << 16), a1 = __uint_as_float(aw[e] & 0xffff0000u);
-      const float b0 = __uint_as_float(bw[e] << 16), b1 = __uint_as_float(bw[e] & 0xffff0000u);
-      acc = fma(static_cast<double>(a0), static_cast<double>(b0), acc);
-      acc = fma(static_cast<double>(a1), static_cast<double>(b1), acc);
+    for (int u = 0; u < 4; ++u) { a[u] = __ldg(xr + c + u); b[u] = __ldg(yr + c + u); }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint32_t aw[4] = {a[u].x, a[u].y, a[u].z, a[u].w}, bw[4] = {b[u].x, b[u].y, b[u].z, b[u].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float a0 = __uint_as_float(aw[e] << 16), a1 = __uint_as_float(aw[e] & 0xffff0000u);
+        const float b0 = __uint_as_float(bw[e] << 16), b1 = __uint_as_float(bw[e] & 0xffff0000u);
+        acc = fma(static_cast<double>(a0), static_cast<double>(b0), acc);
+        acc = fma(static_cast<double>(a1), static_cast<double>(b1), acc);
+      }
     }
   }
   return static_cast<float>(acc);
