@@ -597,8 +597,13 @@ def train_bench(ctx, args, name, cpu_leg=True):
     d_sum = 2 * M * dm + 2 * M * dm                        # sum of the contraction widths over the calls
     alg_fwd = 6.0 * B * B * d_sum                          # 3 distinct B x B x D contractions per call
     alg_bwd = 14.0 * B * B * d_sum
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get(f"{dom}:{name}:{world}")
     roofline = {"bound": "tensor", "kernel": dom, "achieved": kstats[dom]["tflops"], "peak": peaks["tensor_burst"],
-                "unit": "TFLOP/s", "frac": kstats[dom]["tflops"] / peaks["tensor_burst"], "traffic": None,
+                "unit": "TFLOP/s", "frac": kstats[dom]["tflops"] / peaks["tensor_burst"], "traffic": traffic,
                 "peak_source": peaks["source"] + ", bf16_tflops (burst: launches of a few ms, timed alone with CUDA events)",
                 "kernels": kstats, "note": "flops counted on the padded contraction width the kernel executes",
                 "algorithmic_flops_per_step": alg_fwd + alg_bwd,

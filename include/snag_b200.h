@@ -181,11 +181,6 @@ int snag_sim_mainloop_only(const uint16_t* X, const uint16_t* Y, int32_t n1, int
  * issuing thread of every CTA of every sweep records {total cycles, cycles waiting for a free accumulator stage
  * (epilogue-bound), cycles waiting for operands (TMA-bound), tiles}. Process-global, not thread-safe. */
 int snag_debug_counters(uint64_t* counters);
-/* Measurement aid: mainloop + TMEM read-out of every accumulator (sink: >= 512 uint32, never written in practice),
- * plus a synthetic epilogue load per 32-column strip and thread: n_lds broadcast 16-byte shared loads, n_alu dependent
- * FMAs, n_sts shared stores. Used to find which resource an epilogue takes away from the tensor pipe. */
-int snag_sim_readout_only(const uint16_t* X, const uint16_t* Y, int32_t n1, int32_t n2, int32_t Dpad, uint32_t* sink,
-                          int32_t n_lds, int32_t n_alu, int32_t n_sts, void* stream);
 /* CSLS sweep 1 (src/utils.py:431-432 without the matrix): for every row of X the SNAG_KT largest
  * c_ij = 1 - d_ij over the columns of each chunk. part: fp32 [n_lists][n1][SNAG_KT] (n_lists from
  * snag_sim_plan(n1, n2, Dpad)); part_idx (may be NULL): int32, same shape, the column j of every entry (-1 for the
@@ -281,7 +276,7 @@ int snag_pair_score(const uint16_t* X, const uint16_t* Y, int32_t Dpad, int64_t 
  *   cnt_col[j] += #{i != j : dist_ij < g_col[j] or (== and gid(i) < gid(j))}     r2l rank of pair gid(j)
  * gid(i) = row_gid0 + i, gid(j) = col_gid0 + j (column shards of a multi-GPU evaluation pass their offset).
  * Counters are accumulated atomically: zero them first. top3_val/top3_idx (both NULL or both fp32/int32
- * [n_lists][n1][4]) receive each row's 3 nearest columns per list (merge with snag_top3_merge). */
+ * [n_lists][n1][4]) receive each row's 3 nearest columns per list (merge with snag_top4_merge). */
 int snag_eval_rank(const uint16_t* X, const uint16_t* Y, const float* xn, const float* yn, const float* nv1,
                    const float* nv2, const float* g_row, const float* g_col, int32_t row_gid0, int32_t col_gid0,
                    int32_t n1, int32_t n2, int32_t Dpad, int32_t use_csls, int32_t* cnt_row, int32_t* cnt_col,
@@ -328,8 +323,6 @@ int snag_top4_merge(const float* val, const int32_t* idx, int32_t n_lists, int64
 int snag_top3_rescore(const uint16_t* X, const uint16_t* Y, int32_t Dpad, int64_t n_rows, const float* xn, const float* yn,
                       const float* nv1, const float* nv2, int32_t use_csls, const int32_t* cand, float* oval, int32_t* oidx,
                       void* stream);
-int snag_top3_merge(const float* val, const int32_t* idx, int32_t n_lists, int64_t n_rows, float* oval, int32_t* oidx,
-                    void* stream);
 
 /* csls_sim (src/utils.py:417-435) on a MATERIALISED fp32 similarity matrix [n1, ld]: nv1[i] / nv2[j] = mean of the k
  * largest entries of row i / column j; out[i,j] = (2*sim[i,j] - nv1[i]) - nv2[j] (out may be NULL to get only the

@@ -144,10 +144,6 @@ int snag_debug_counters(uint64_t* counters) {
   set_debug_counters(reinterpret_cast<unsigned long long*>(counters));
   return SNAG_OK;
 }
-int snag_sim_readout_only(const uint16_t* X, const uint16_t* Y, int32_t n1, int32_t n2, int32_t Dpad, uint32_t* sink,
-                          int32_t n_lds, int32_t n_alu, int32_t n_sts, void* stream) {
-  return launch_sim_loadonly(BF(X), BF(Y), n1, n2, Dpad, sink, n_lds, n_alu, n_sts, S(stream));
-}
 int snag_sim_write(const uint16_t* X, const uint16_t* Y, const float* xn, const float* yn, int32_t n1, int32_t n2,
                    int32_t Dpad, int32_t mode, float* out, int64_t ld, void* stream) {
   return launch_sim_write(BF(X), BF(Y), xn, yn, n1, n2, Dpad, mode, out, ld, S(stream));
@@ -240,10 +236,6 @@ int snag_top3_rescore(const uint16_t* X, const uint16_t* Y, int32_t Dpad, int64_
                       const float* nv1, const float* nv2, int32_t use_csls, const int32_t* cand, float* oval, int32_t* oidx,
                       void* stream) {
   return launch_top3_rescore(BF(X), BF(Y), Dpad, n_rows, xn, yn, nv1, nv2, use_csls, cand, oval, oidx, S(stream));
-}
-int snag_top3_merge(const float* val, const int32_t* idx, int32_t n_lists, int64_t n_rows, float* oval, int32_t* oidx,
-                    void* stream) {
-  return launch_top3_merge(val, idx, n_lists, n_rows, oval, oidx, S(stream));
 }
 
 int64_t snag_csls_workspace_bytes(int64_t n1, int64_t n2) { return csls_workspace_floats(n1, n2) * 4; }

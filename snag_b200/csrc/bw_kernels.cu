@@ -1114,34 +1114,6 @@ __global__ void __launch_bounds__(128) top3_rescore_kernel(const __nv_bfloat16* 
 }
 
 // merge per-chunk top-3 (value asc, index asc on ties) lists of each row
-__global__ void __launch_bounds__(128) top3_merge_kernel(const float* __restrict__ val, const int* __restrict__ idx, int n_lists,
-                                                         long long n_rows, float* __restrict__ oval, int* __restrict__ oidx) {
-  const long long row = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  if (row >= n_rows) return;
-  float v[3] = {INFINITY, INFINITY, INFINITY};
-  int id[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff};
-  for (int l = 0; l < n_lists; ++l) {
-    const float4 cv = __ldg(reinterpret_cast<const float4*>(val + (static_cast<long long>(l) * n_rows + row) * 4));
-    const int4 ci = __ldg(reinterpret_cast<const int4*>(idx + (static_cast<long long>(l) * n_rows + row) * 4));
-    const float cvv[3] = {cv.x, cv.y, cv.z};
-    const int cii[3] = {ci.x, ci.y, ci.z};
-#pragma unroll
-    for (int e = 0; e < 3; ++e) {
-      if (cvv[e] < v[2] || (cvv[e] == v[2] && cii[e] < id[2])) {
-        v[2] = cvv[e]; id[2] = cii[e];
-#pragma unroll
-        for (int t = 2; t > 0; --t) {
-          if (v[t] < v[t - 1] || (v[t] == v[t - 1] && id[t] < id[t - 1])) {
-            const float tv = v[t]; v[t] = v[t - 1]; v[t - 1] = tv;
-            const int ti = id[t]; id[t] = id[t - 1]; id[t - 1] = ti;
-          }
-        }
-      }
-    }
-  }
-  *reinterpret_cast<float4*>(oval + row * 4) = make_float4(v[0], v[1], v[2], 0.f);
-  *reinterpret_cast<int4*>(oidx + row * 4) = make_int4(id[0], id[1], id[2], 0);
-}
 
 // ICL forward finalize: lse = log(sum over chunks) + 1/tau ; nll = lse - pos/tau
 __global__ void icl_finalize_kernel(const float* __restrict__ rowsum_part, int n_chunks, int B, int Bp,
@@ -1860,11 +1832,6 @@ int launch_top3_rescore(const __nv_bfloat16* X, const __nv_bfloat16* Y, int Dpad
   return static_cast<int>(cudaGetLastError());
 }
 
-int launch_top3_merge(const float* val, const int* idx, int n_lists, long long n_rows, float* oval, int* oidx, cudaStream_t st) {
-  if (!val || !idx || !oval || !oidx || n_lists <= 0 || n_rows <= 0) return SNAG_ERR_ARG;
-  top3_merge_kernel<<<static_cast<int>((n_rows + 127) / 128), 128, 0, st>>>(val, idx, n_lists, n_rows, oval, oidx);
-  return static_cast<int>(cudaGetLastError());
-}
 
 int launch_icl_finalize(const float* rowsum_part, int n_chunks, int B, int Bp, const float* pos, float inv_tau, float* lse,
                         float* nll, cudaStream_t st) {

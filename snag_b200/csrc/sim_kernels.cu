@@ -195,12 +195,6 @@ int launch_sim_null(const __nv_bfloat16* X, const __nv_bfloat16* Y, int n1, int 
   EpiNull::Params p{0};
   return launch_sim<EpiNull>(X, Y, n1, n2, Dpad, p, st);
 }
-int launch_sim_loadonly(const __nv_bfloat16* X, const __nv_bfloat16* Y, int n1, int n2, int Dpad, uint32_t* sink,
-                        int n_lds, int n_alu, int n_sts, cudaStream_t st) {
-  if (!sink) return SNAG_ERR_ARG;
-  EpiLoadOnly::Params p{sink, n_lds, n_alu, n_sts};
-  return launch_sim<EpiLoadOnly>(X, Y, n1, n2, Dpad, p, st);
-}
 
 int launch_sim_write(const __nv_bfloat16* X, const __nv_bfloat16* Y, const float* xn, const float* yn, int n1, int n2,
                      int Dpad, int mode, float* out, long long ld, cudaStream_t st) {

@@ -397,48 +397,6 @@ struct EpiNull {
   static __device__ __forceinline__ void unit_end(const Params&, const SimShape&, const EpiCtx&, State&) {}
 };
 
-// Epilogue: read every accumulator out of TMEM and fold it into one word per thread — measures what the TMEM
-// read-out alone costs the mainloop (diagnostics only)
-struct EpiLoadOnly {
-  static constexpr bool kNoLoad = false;
-  struct Params { uint32_t* sink; int n_lds; int n_alu; int n_sts; };   // synthetic per-strip load: see gpu_probe.py
-  struct State { uint32_t acc; };
-  static __device__ __forceinline__ void unit_begin(const Params&, const SimShape&, const EpiCtx&, State& st) { st.acc = 0; }
-  static __device__ __forceinline__ EpiPre tile_prefetch(const Params&, const SimShape&, const EpiCtx&, int) { return EpiPre{}; }
-  static __device__ __forceinline__ void tile_commit(const Params&, const SimShape&, const EpiCtx&, State&, const EpiPre&, int, int) {}
-  static __device__ __forceinline__ void chunk(const Params& p, const SimShape&, const EpiCtx& cx, State& st, int, int c,
-                                               const uint32_t (&r)[32], int) {
-#pragma unroll
-    for (int q = 0; q < 32; ++q) st.acc ^= r[q];
-    const float4* v = reinterpret_cast<const float4*>(cx.scratch);
-    for (int i = 0; i < p.n_lds; ++i) {                 // warp-uniform 16-byte shared loads (broadcast)
-      const float4 t = v[(i + c) & 127];
-      st.acc ^= __float_as_uint(t.x) + __float_as_uint(t.w);
-    }
-    float f = __uint_as_float(st.acc | 0x3f800000u);
-    if (p.n_alu >= 0) {
-      for (int i = 0; i < p.n_alu; ++i) f = __fmaf_rn(f, 1.0000001f, 1e-9f);       // one dependent chain (low IPC)
-    } else {
-      float g[8];                                                                     // 8 independent chains (high IPC)
-#pragma unroll
-      for (int e = 0; e < 8; ++e) g[e] = f + static_cast<float>(e);
-      for (int i = 0; i < -p.n_alu; i += 8) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) g[e] = __fmaf_rn(g[e], 1.0000001f, 1e-9f);
-      }
-#pragma unroll
-      for (int e = 0; e < 8; ++e) f += g[e];
-    }
-    st.acc ^= __float_as_uint(f);
-    for (int i = 0; i < p.n_sts; ++i)                   // conflict-free 4-byte shared stores
-      cx.scratch[EPI_VEC_FLOATS + (i & 7) * NUM_EPI_THREADS + cx.tid] = f;
-  }
-  static __device__ __forceinline__ void tile_end(const Params&, const SimShape&, const EpiCtx&, State&, int, int) {}
-  static __device__ __forceinline__ void unit_end(const Params& p, const SimShape&, const EpiCtx& cx, State& st) {
-    if (st.acc == 0x12345678u) p.sink[cx.tid] = st.acc;     // practically never true; keeps the work alive
-  }
-};
-
 // ------------------------------------------------------------------------------------------------
 // Epilogue: write S (mode 0) or the squared-L2 distance (mode 1) — drop-in pairwise_distances
 // ------------------------------------------------------------------------------------------------

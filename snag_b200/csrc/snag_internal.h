@@ -78,7 +78,6 @@ int launch_topk_exhaustive(const __nv_bfloat16* A, const __nv_bfloat16* B, int D
                            float* best_d, int* best_idx, cudaStream_t st);
 int launch_pair_score(const __nv_bfloat16* X, const __nv_bfloat16* Y, int Dpad, long long n, const float* xn, const float* yn,
                       const float* nv1, const float* nv2, int use_csls, float* g, float* s_out, cudaStream_t st);
-int launch_top3_merge(const float* val, const int* idx, int n_lists, long long n_rows, float* oval, int* oidx, cudaStream_t st);
 int launch_band_rescore(const __nv_bfloat16* X, const __nv_bfloat16* Y, int Dpad, const float* xn, const float* yn,
                         const float* nv1, const float* nv2, const float* g_row, const float* g_col, int row_gid0, int col_gid0,
                         int use_csls, const uint2* band, const unsigned int* band_cnt, unsigned int band_cap, int* cnt_row,
@@ -99,8 +98,6 @@ int launch_csls_sim(const float* sim, long long n1, long long n2, long long ld, 
 // ---- tcgen05 similarity sweeps (sim_kernels.cu)
 void set_debug_counters(unsigned long long* p);
 int launch_sim_null(const __nv_bfloat16* X, const __nv_bfloat16* Y, int n1, int n2, int Dpad, cudaStream_t st);
-int launch_sim_loadonly(const __nv_bfloat16* X, const __nv_bfloat16* Y, int n1, int n2, int Dpad, uint32_t* sink,
-                        int n_lds, int n_alu, int n_sts, cudaStream_t st);
 int launch_sim_write(const __nv_bfloat16* X, const __nv_bfloat16* Y, const float* xn, const float* yn, int n1, int n2,
                      int Dpad, int mode, float* out, long long ld, cudaStream_t st);
 int sim_write_t_splits(int n1, int n2, int Dpad);

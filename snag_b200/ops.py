@@ -671,16 +671,6 @@ def top3_rescore(X, Y, xn, yn, nv1, nv2, use_csls: bool, cand: torch.Tensor):
     return oval, oidx
 
 
-def top3_merge(val: torch.Tensor, idx: torch.Tensor):
-    _need(val, torch.float32, "val", 3)
-    _need(idx, torch.int32, "idx", 3)
-    n_lists, n_rows = val.shape[0], val.shape[1]
-    oval = torch.empty((n_rows, 4), dtype=torch.float32, device=val.device)
-    oidx = torch.empty((n_rows, 4), dtype=torch.int32, device=val.device)
-    call("snag_top3_merge", ptr(val), ptr(idx), n_lists, n_rows, ptr(oval), ptr(oidx), current_stream())
-    return oval, oidx
-
-
 def l1_distance(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
     """fp32 [n1, n2] cityblock distances of fp32 rows (fp64 index-order accumulation, rounded once): --distance 1."""
     _need(x, torch.float32, "x", 2)
