@@ -190,6 +190,40 @@ def test_icl_forward_on_half_gram_matches_per_side_sweeps(cuda_device, B, dims, 
         np.testing.assert_allclose(shard_sum.cpu().numpy(), full_sum.cpu().numpy(), rtol=1e-5)
 
 
+@pytest.mark.parametrize("B,D", [(1, 8), (2, 64), (3, 100), (127, 40), (129, 300), (255, 64), (257, 96), (513, 320)])
+def test_icl_ragged_batches_against_oracle(cuda_device, B, D):
+    """Batch sizes around the tile edges (one pair, one short of / one past a block of 128 / 256 anchors) and widths
+    that need zero padding: loss against the oracle, gradient against fp32 torch autograd of the reference's op sequence
+    on the same bf16-rounded unit rows."""
+    rng = np.random.RandomState(B * 7 + D)
+    N = 2 * B + 3
+    emb = oracle.bf16_round(oracle.normalize_rows(rng.randn(N, D).astype(np.float32)))
+    links = np.stack([rng.permutation(N // 2)[:B], N // 2 + rng.permutation(N - N // 2)[:B]], 1).astype(np.int32)
+    wn = (rng.rand(N) + 0.5).astype(np.float32)
+    ref = oracle.icl_loss(emb, links, 0.1, 0.3, wn, norm=True)
+    e = torch.from_numpy(emb).to(cuda_device).requires_grad_(True)
+    got = sloss.icl_loss(0.1, 0.3)(e, links, weight_norm=torch.from_numpy(wn).to(cuda_device))
+    np.testing.assert_allclose(got.item(), float(ref), rtol=1e-3, atol=1e-5)
+    got.backward()
+    t = torch.from_numpy(emb).to(cuda_device).requires_grad_(True)
+    z = F.normalize(t, dim=1)
+    z = z + (torch.from_numpy(emb).to(cuda_device) - z).detach()            # value = the rounded rows, gradient through normalize
+    il = torch.from_numpy(links[:, 0].astype(np.int64)).to(cuda_device)
+    ir = torch.from_numpy(links[:, 1].astype(np.int64)).to(cuda_device)
+    a, b = z[il], z[ir]
+    eye = torch.eye(B, device=cuda_device) * 1e9
+    la = torch.cat([a @ b.t() / 0.1, a @ a.t() / 0.1 - eye], 1)
+    lb = torch.cat([b @ a.t() / 0.1, b @ b.t() / 0.1 - eye], 1)
+    w = torch.minimum(torch.from_numpy(wn).to(cuda_device)[il], torch.from_numpy(wn).to(cuda_device)[ir])
+    ar = torch.arange(B, device=cuda_device)
+    loss = 0.3 * (-torch.log_softmax(la, 1)[ar, ar] * w).sum() / B + 0.7 * (-torch.log_softmax(lb, 1)[ar, ar] * w).sum() / B
+    loss.backward()
+    if float(t.grad.norm()) > 1e-6:
+        assert _relerr(e.grad, t.grad) < 2e-2
+    else:
+        assert float(e.grad.abs().max()) < 1e-5                  # B = 1: the only logit is the positive one, the loss is constant
+
+
 def test_icl_oracle_numpy(cuda_device):
     """The numpy restatement of the reference (oracle.icl_loss) on rounded unit rows vs the CUDA path."""
     rng = np.random.RandomState(0)
