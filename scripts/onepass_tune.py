@@ -33,12 +33,17 @@ def timed(**kw):
     return res, e0.elapsed_time(e1), {nm: round(a.elapsed_time(b), 2) for nm, a, b, *_ in ev}
 
 
+samples = [int(v) for v in sys.argv[3].split(",")] if len(sys.argv) > 3 else [evaluate.SAMPLE_MAX]
 ref, ms, ev = timed(one_pass=False)
 ref, ms, ev = timed(one_pass=False)
 print(json.dumps({"mode": "two_sweep", "ms": ms, "sweeps": ev, "rank_sweep": {k_: v for k_, v in ref.info["rank_sweep"].items()}}), flush=True)
-for gm in gammas:
-    evaluate.ONE_PASS_GAMMA = gm
-    res, ms, ev = timed(one_pass=True)
-    res, ms, ev = timed(one_pass=True)
-    same = bool(torch.equal(res.rank_l2r, ref.rank_l2r) and torch.equal(res.rank_r2l, ref.rank_r2l))
-    print(json.dumps({"mode": "one_pass", "gamma": gm, "ms": ms, "same": same, "sweeps": ev, "info": res.info["one_pass"]}), flush=True)
+for m_max in samples:
+    evaluate.SAMPLE_MAX = m_max
+    evaluate._ONE_PASS_CAP.clear()
+    for gm in gammas:
+        evaluate.ONE_PASS_GAMMA = gm
+        res, ms, ev = timed(one_pass=True)
+        res, ms, ev = timed(one_pass=True)
+        same = bool(torch.equal(res.rank_l2r, ref.rank_l2r) and torch.equal(res.rank_r2l, ref.rank_r2l))
+        print(json.dumps({"mode": "one_pass", "sample_max": m_max, "gamma": gm, "ms": ms, "same": same, "sweeps": ev,
+                          "info": res.info["one_pass"]}), flush=True)

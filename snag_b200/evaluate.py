@@ -55,6 +55,7 @@ def shard_bounds(n: int, world: int, rank: int, align: int = 256) -> tuple[int, 
 
 
 TWO_SWEEP_MIN_N = 65536     # below this the sample pre-pass costs more than the sweep it saves
+SAMPLE_MAX = 32768          # largest pre-pass sample (sources and targets each)
 
 
 def two_sweep_plan(n: int, k: int, n_targets: int | None = None, n_ctas: int = 148) -> tuple[int, int] | None:
@@ -65,7 +66,7 @@ def two_sweep_plan(n: int, k: int, n_targets: int | None = None, n_ctas: int = 1
     share. m depends on n alone, so every rank of a sharded evaluation draws the same sample."""
     if n < TWO_SWEEP_MIN_N:
         return None
-    m = min(max(round_up(n // 16, 256), 8192), 32768)
+    m = min(max(round_up(n // 16, 256), 8192), SAMPLE_MAX)
     nt = n if n_targets is None else max(1, int(n_targets))
     cap = round_up(int(2.0 * k * n / m * nt / max(1, n_ctas)) + 4096, 1024)
     return m, cap
