@@ -579,11 +579,19 @@ __global__ void __launch_bounds__(256) normalize_bwd_scatter_kernel(const float*
 __device__ __forceinline__ float canonical_dot(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ y, int Dpad) {
   const uint4* xr = reinterpret_cast<const uint4*>(x);
   const uint4* yr = reinterpret_cast<const uint4*>(y);
+  const int n = Dpad / 8;                        // 16-byte words per row; a multiple of 8
   double acc = 0.0;
-  for (int c = 0; c < Dpad / 8; c += 4) {
-    uint4 a[4], b[4];
+  // software pipelined: the 64 bytes of the NEXT trip are requested before the 32 dependent fp64 FMAs of this one run
+  // (ncu, profiles/r03o: the re-score kernels issue on 10 % of the cycles and wait on loads for the rest — one trip's
+  // loads in flight per thread are not enough to cover the latency of a gather of whole rows)
+  uint4 a[4], b[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) { a[u] = __ldg(xr + c + u); b[u] = __ldg(yr + c + u); }
+  for (int u = 0; u < 4; ++u) { a[u] = __ldg(xr + u); b[u] = __ldg(yr + u); }
+  for (int c = 0; c < n; c += 4) {
+    uint4 na[4], nb[4];
+    const int cn = c + 4 < n ? c + 4 : c;        // the last trip re-requests its own (cached) words: no branch in the loop
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { na[u] = __ldg(xr + cn + u); nb[u] = __ldg(yr + cn + u); }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const uint32_t aw[4] = {a[u].x, a[u].y, a[u].z, a[u].w}, bw[4] = {b[u].x, b[u].y, b[u].z, b[u].w};
@@ -595,6 +603,8 @@ __device__ __forceinline__ float canonical_dot(const __nv_bfloat16* __restrict__
         acc = fma(static_cast<double>(a1), static_cast<double>(b1), acc);
       }
     }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { a[u] = na[u]; b[u] = nb[u]; }
   }
   return static_cast<float>(acc);
 }
