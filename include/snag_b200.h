@@ -152,7 +152,17 @@ int snag_icl_bwd_fused(int32_t n_prob, const uint16_t* const* S3, const float* c
 int snag_icl_fwd_sym_plan(int32_t n_prob, int32_t B, int32_t Bp, int64_t* sizes);
 int snag_icl_fwd_sym(int32_t n_prob, const uint16_t* const* S3, float* const* rowpart, float* const* colpart, float* pos,
                      int32_t B, int32_t Bp, int32_t Dpad, float inv_tau, int32_t unit_begin, int32_t unit_end, float* total,
-                     void* stream);
+                     uint16_t* const* esave, void* stream);
+/* esave (NULL, or a HOST array of n_prob device pointers, each NULL or a [2 Bp, 2 Bp] bf16 buffer, 32-byte aligned):
+ * the forward also stores E of every computed element at esave[p][row][column] (row < column; other entries are left
+ * untouched). snag_icl_g_from_e then forms dL/dlogits of one side (G [Bp, 2 Bp] bf16, the operand of the gradient GEMM
+ * snag_sim_write_t_mn; same definition and arguments as snag_icl_bwd_logits) from it with a bandwidth kernel instead of
+ * recomputing the logits — for tables too wide for snag_icl_bwd_fused. Requires a forward over ALL work units.
+ * cr_this / cr_other [B] as cr / cc of snag_icl_bwd_logits; diag [B] = the value of the cross diagonal G[i, i] itself,
+ * (g_a[i] expm1(-nll_a[i]) + g_b[i] expm1(-nll_b[i])) / tau from the forward's fp32 NLL: that element is a small
+ * difference of large terms which the bf16 E cannot carry. */
+int snag_icl_g_from_e(const uint16_t* E, int32_t side, int32_t B, int32_t Bp, const float* cr_this, const float* cr_other,
+                      const float* diag, float inv_tau, uint16_t* G, void* stream);
 int snag_icl_sym_finalize(const float* total, const float* pos, int32_t n_prob, int32_t B, int32_t Bp, float inv_tau,
                           float* out, void* stream);
 

@@ -76,7 +76,8 @@ _SIGNATURES = {
     "snag_icl_rowsum": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _vp, _vp, _vp],
     "snag_icl_finalize": [_vp, _i32, _i32, _i32, _vp, _f32, _vp, _vp, _vp],
     "snag_icl_fwd_sym_plan": [_i32, _i32, _i32, _vp],
-    "snag_icl_fwd_sym": [_i32, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _f32, _i32, _i32, _vp, _vp],
+    "snag_icl_fwd_sym": [_i32, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _f32, _i32, _i32, _vp, _vp, _vp],
+    "snag_icl_g_from_e": [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _f32, _vp, _vp],
     "snag_icl_sym_finalize": [_vp, _vp, _i32, _i32, _i32, _f32, _vp, _vp],
     "snag_icl_bwd_logits": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _i32, _f32, _vp],
 }

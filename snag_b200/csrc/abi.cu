@@ -128,9 +128,13 @@ int snag_icl_fwd_sym_plan(int32_t n_prob, int32_t B, int32_t Bp, int64_t* sizes)
 }
 int snag_icl_fwd_sym(int32_t n_prob, const uint16_t* const* S3, float* const* rowpart, float* const* colpart, float* pos,
                      int32_t B, int32_t Bp, int32_t Dpad, float inv_tau, int32_t unit_begin, int32_t unit_end, float* total,
-                     void* stream) {
+                     uint16_t* const* esave, void* stream) {
   return launch_icl_fwd_sym(n_prob, reinterpret_cast<const __nv_bfloat16* const*>(S3), rowpart, colpart, pos, B, Bp, Dpad,
-                            inv_tau, unit_begin, unit_end, total, S(stream));
+                            inv_tau, unit_begin, unit_end, total, reinterpret_cast<__nv_bfloat16* const*>(esave), S(stream));
+}
+int snag_icl_g_from_e(const uint16_t* E, int32_t side, int32_t B, int32_t Bp, const float* cr_this, const float* cr_other,
+                      const float* diag, float inv_tau, uint16_t* G, void* stream) {
+  return launch_icl_g_from_e(BF(E), side, B, Bp, cr_this, cr_other, diag, inv_tau, reinterpret_cast<__nv_bfloat16*>(G), S(stream));
 }
 int snag_icl_sym_finalize(const float* total, const float* pos, int32_t n_prob, int32_t B, int32_t Bp, float inv_tau,
                           float* out, void* stream) {

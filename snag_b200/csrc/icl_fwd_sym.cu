@@ -57,7 +57,9 @@ struct alignas(64) FsProblem {
   float* rowpart;          // [nch_max][FS_WG][2 Bp]  row sums of the row's chunks, per epilogue warpgroup
   float* colpart;          // [R][2 Bp]        column sums per (row block, column)
   float* pos;              // [Bp]             S[i, Bp + i]
-  long long pad_[5];
+  __nv_bfloat16* esave;    // [2 Bp][2 Bp] or null: E = exp(S/tau - 1/tau) of every computed element (bf16), kept for a
+                           // backward that forms dL/dlogits from it instead of recomputing S (wide tables)
+  long long pad_[4];
 };
 static_assert(sizeof(FsProblem) == 192, "FsProblem layout");
 
@@ -282,6 +284,17 @@ __global__ void __launch_bounds__(FS_THREADS, 1) icl_fwd_sym_kernel(const __grid
               if (has_pos && row_ok && j == i + g.Bp) pr.pos[idx_i] = sv;
             }
           }
+          if (pr.esave != nullptr) {
+            uint32_t pk[16];
+#pragma unroll
+            for (int q = 0; q < 32; q += 2) {
+              const __nv_bfloat162 h2 = __floats2bfloat162_rn(e[q], e[q + 1]);
+              pk[q >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
+            }
+            uint8_t* dst = reinterpret_cast<uint8_t*>(pr.esave + static_cast<long long>(i) * twoBp + col0);
+            st_global_256(dst, make_uint4(pk[0], pk[1], pk[2], pk[3]), make_uint4(pk[4], pk[5], pk[6], pk[7]));
+            st_global_256(dst + 32, make_uint4(pk[8], pk[9], pk[10], pk[11]), make_uint4(pk[12], pk[13], pk[14], pk[15]));
+          }
           acc_s[wq * FS_WG_COLS + s * 32 + lane] = fs_transpose_sum(e, lane);
         }
         tc_fence_before();
@@ -387,7 +400,8 @@ int icl_fwd_sym_plan(int n_prob, int B, int Bp, long long* out) {
 }
 
 int launch_icl_fwd_sym(int n_prob, const __nv_bfloat16* const* S3, float* const* rowpart, float* const* colpart, float* pos,
-                       int B, int Bp, int Dpad, float inv_tau, int unit_begin, int unit_end, float* total, cudaStream_t st) {
+                       int B, int Bp, int Dpad, float inv_tau, int unit_begin, int unit_end, float* total,
+                       __nv_bfloat16* const* esave, cudaStream_t st) {
   if (!S3 || !rowpart || !colpart || !pos || !total) return SNAG_ERR_ARG;
   if (Dpad <= 0 || (Dpad % FS_BK) != 0) return SNAG_ERR_SHAPE;
   if (!device_is_sm100()) return SNAG_ERR_DEVICE;
@@ -408,6 +422,8 @@ int launch_icl_fwd_sym(int n_prob, const __nv_bfloat16* const* S3, float* const*
     p.prob[i].rowpart = rowpart[i];
     p.prob[i].colpart = colpart[i];
     p.prob[i].pos = pos + static_cast<long long>(i) * Bp;
+    p.prob[i].esave = esave ? esave[i] : nullptr;
+    if (p.prob[i].esave && (reinterpret_cast<uintptr_t>(p.prob[i].esave) & 31)) return SNAG_ERR_ALIGN;
     ta.rowpart[i] = rowpart[i];
     ta.colpart[i] = colpart[i];
   }
@@ -420,6 +436,61 @@ int launch_icl_fwd_sym(int n_prob, const __nv_bfloat16* const* S3, float* const*
     icl_fwd_sym_kernel<<<grid, FS_THREADS, FS_SMEM_BYTES, st>>>(p);
   }
   icl_sym_total_kernel<<<dim3((2 * Bp + 255) / 256, n_prob), 256, 0, st>>>(ta, p.g, unit_begin, unit_end, total);
+  return static_cast<int>(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------
+// dL/dlogits of one side from the saved E (instead of recomputing the logits): the bandwidth-bound replacement of
+// sim_kernel<EpiIclBwd> for tables too wide for the fused backward. With zi = side Bp + i the anchor's row of
+// Z = [a ; b] and zj the column's row (part 0 = the other side, part 1 = this side), E[zi, zj] was stored at
+// esave[min][max] by the half-Gram forward; a 64 x 64 tile is staged in shared memory and read straight, transposed
+// or — on the diagonal — folded. Same formula as EpiIclBwd:
+//   part 0: G[i,j] = ((cr_i + cc_j) E - [i == j] dg_i) / tau     part 1: G[i,j] = (cr_i + cr_j) E / tau, 0 on the diagonal
+// The cross diagonal (the positive pair) is a small difference of large terms — g (P_ii - 1) / tau with P_ii close to 1 —
+// that the bf16 rounding of E would swamp: the caller passes it ready-made, from the fp32 NLL of the forward,
+//   diag_i = (g_a[i] expm1(-nll_a[i]) + g_b[i] expm1(-nll_b[i])) / tau .
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) icl_g_from_e_kernel(const __nv_bfloat16* __restrict__ E, int side, int B, int Bp,
+                                                           const float* __restrict__ cr_this, const float* __restrict__ cr_other,
+                                                           const float* __restrict__ diag, float inv_tau,
+                                                           __nv_bfloat16* __restrict__ G) {
+  __shared__ float tile[64][65];
+  const int twoBp = 2 * Bp;
+  const int i0 = blockIdx.y * 64;                    // anchors of the tile (batch index)
+  const int c0 = blockIdx.x * 64;                    // output columns of G
+  const int part = c0 >= Bp ? 1 : 0;
+  const int j0 = c0 - part * Bp;                     // batch index of the first column
+  const int zr0 = side * Bp + i0;                    // rows / columns of Z
+  const int zc0 = (part == 0 ? (1 - side) : side) * Bp + j0;
+  const bool any = i0 < B && j0 < B;
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;       // 4 rows per pass
+  if (any) {
+    const int R0 = min(zr0, zc0), C0 = max(zr0, zc0);
+#pragma unroll 4
+    for (int r = ty; r < 64; r += 4) tile[r][tx] = __bfloat162float(E[static_cast<long long>(R0 + r) * twoBp + C0 + tx]);
+  }
+  __syncthreads();
+  const float* ccp = part ? cr_this : cr_other;
+  const int j = j0 + tx;
+  const float cc = (any && j < B) ? __ldg(ccp + j) * inv_tau : 0.f;
+#pragma unroll 4
+  for (int r = ty; r < 64; r += 4) {
+    const int i = i0 + r;
+    float gv = 0.f;
+    if (any && i < B && j < B) {
+      const float e = zc0 > zr0 ? tile[r][tx] : (zc0 < zr0 ? tile[tx][r] : tile[min(r, tx)][max(r, tx)]);
+      gv = (__ldg(cr_this + i) * inv_tau + cc) * e;
+      if (i == j) gv = part ? 0.f : __ldg(diag + i);
+    }
+    G[static_cast<long long>(i) * twoBp + c0 + tx] = __float2bfloat16_rn(gv);
+  }
+}
+
+int launch_icl_g_from_e(const __nv_bfloat16* E, int side, int B, int Bp, const float* cr_this, const float* cr_other,
+                        const float* diag, float inv_tau, __nv_bfloat16* G, cudaStream_t st) {
+  if (!E || !cr_this || !cr_other || !diag || !G || B <= 0 || Bp < B || (Bp % 256) != 0 || (side != 0 && side != 1))
+    return SNAG_ERR_ARG;
+  icl_g_from_e_kernel<<<dim3(2 * Bp / 64, Bp / 64), 256, 0, st>>>(E, side, B, Bp, cr_this, cr_other, diag, inv_tau, G);
   return static_cast<int>(cudaGetLastError());
 }
 

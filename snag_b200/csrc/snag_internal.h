@@ -64,7 +64,10 @@ int launch_icl_bwd_fused(int n_prob, const __nv_bfloat16* const* S3, const float
 // ICL forward on half the Gram matrix, all tables of a step in one launch (icl_fwd_sym.cu)
 int icl_fwd_sym_plan(int n_prob, int B, int Bp, long long* out);
 int launch_icl_fwd_sym(int n_prob, const __nv_bfloat16* const* S3, float* const* rowpart, float* const* colpart, float* pos,
-                       int B, int Bp, int Dpad, float inv_tau, int unit_begin, int unit_end, float* total, cudaStream_t st);
+                       int B, int Bp, int Dpad, float inv_tau, int unit_begin, int unit_end, float* total,
+                       __nv_bfloat16* const* esave, cudaStream_t st);
+int launch_icl_g_from_e(const __nv_bfloat16* E, int side, int B, int Bp, const float* cr_this, const float* cr_other,
+                        const float* diag, float inv_tau, __nv_bfloat16* G, cudaStream_t st);
 int launch_icl_sym_finalize(const float* total, const float* pos, int n_prob, int B, int Bp, float inv_tau, float* out,
                             cudaStream_t st);
 int launch_topk_merge_mean(const float* part, const int* part_idx, int n_lists, long long n_rows, int k, float* nv,

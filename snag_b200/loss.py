@@ -155,6 +155,10 @@ FUSED_BACKWARD = os.environ.get("SNAG_FUSED_BACKWARD", "1") != "0"      # A/B sw
 # Forward on half the Gram matrix of the stacked rows, all tables of a step in one launch per contraction width
 # (ops.icl_fwd_sym); off: two per-side sweeps per table (sim_kernel<EpiIclFwd>), which execute the whole matrix.
 SYM_FORWARD = os.environ.get("SNAG_SYM_FORWARD", "1") != "0"
+# Tables too wide for the fused backward (the joint embeddings): the forward keeps E = exp(s/tau - 1/tau) of the half
+# matrix in bf16 ([2Bp, 2Bp]: 2 GB per table at B = 16 384) and the backward forms dL/dlogits from it with a bandwidth
+# kernel instead of a second pass over the 1200- / 1800-wide contraction. Single rank only (off: recompute).
+SAVE_E = os.environ.get("SNAG_SAVE_E", "1") != "0"
 
 
 class _IclMany(torch.autograd.Function):
@@ -186,17 +190,24 @@ class _IclMany(torch.autograd.Function):
                 stacks.append(S3)
         loc_all = None
         stats = None
+        esaved = {}                                       # table -> saved E (wide tables of an unsharded training step)
         if SYM_FORWARD and hasattr(be, "icl_fwd_sym"):
             # sharded: every rank takes a contiguous share of the launch's work units (tiles of the half matrix, not
             # anchors) and one all-reduce of the partial row sums replaces the all-gather of per-anchor results
             stats = [None] * len(embs)
+            if SAVE_E and shard.world == 1 and hasattr(be, "icl_g_from_e"):
+                for p, S3 in enumerate(stacks):
+                    if S3.shape[1] > ops.FUSED_BWD_MAX_DPAD and ctx.needs_input_grad[5 + p]:
+                        esaved[p] = torch.empty((2 * Bp, 2 * Bp), dtype=torch.bfloat16, device=S3.device)
             by_width = {}
             for p, S3 in enumerate(stacks):
                 by_width.setdefault(S3.shape[1], []).append(p)
             for group in by_width.values():
                 for i in range(0, len(group), ops.ICL_SYM_MAX_PROBLEMS):
                     chunk = group[i:i + ops.ICL_SYM_MAX_PROBLEMS]
-                    res = be.icl_fwd_sym([stacks[p] for p in chunk], B, Bp, inv_tau, shard.rank, shard.world, shard.all_reduce)
+                    kw = {"esave": [esaved.get(p) for p in chunk]} if esaved else {}
+                    res = be.icl_fwd_sym([stacks[p] for p in chunk], B, Bp, inv_tau, shard.rank, shard.world, shard.all_reduce,
+                                         **kw)
                     for q, p in enumerate(chunk):
                         stats[p] = res[q]
         elif shard.world > 1:
@@ -228,7 +239,8 @@ class _IclMany(torch.autograd.Function):
             allstats = torch.stack(rows, 0)
         lse = allstats[:, 0::2].contiguous()                         # [n, 2, B]
         nll = allstats[:, 1::2].contiguous()
-        ctx.save_for_backward(idx_l, idx_r, lse, *stacks, *embs)
+        ctx.save_for_backward(idx_l, idx_r, lse, *stacks, *embs, *[esaved[p] for p in sorted(esaved)], *([nll] if esaved else []))
+        ctx.esaved = tuple(sorted(esaved))
         ctx.dims = (B, Bp, inv_tau, bool(normalize), tuple(int(e.shape[1]) for e in embs))
         ctx.shard = shard
         return nll
@@ -240,12 +252,20 @@ class _IclMany(torch.autograd.Function):
         shard = ctx.shard
         be = shard.be
         n = len(dims)
-        stacks, embs = saved[:n], saved[n:]
+        stacks, embs = saved[:n], saved[n:2 * n]
+        esaved = dict(zip(ctx.esaved, saved[2 * n:]))
         r0, r1, per = shard.bounds(B)
         # row coefficients of every table at once: cr_x = g_x exp(1/tau - lse_x), dg = g_a + g_b   ([n, B] each)
         grad = grad.contiguous().float()
         cr = grad * torch.exp(inv_tau - lse)
         dg_all = grad[:, 0] + grad[:, 1]
+        diag_all = None
+        if esaved:
+            # the cross diagonal of dL/dlogits, g (P_ii - 1) / tau, from the forward's fp32 NLL (P_ii = exp(-nll_i))
+            nll_saved = saved[2 * n + len(esaved)]
+            diag_all = (grad[:, 0] * torch.expm1(-nll_saved[:, 0]) + grad[:, 1] * torch.expm1(-nll_saved[:, 1])) * inv_tau
+            if B % 4:
+                diag_all = torch.nn.functional.pad(diag_all, (0, 4 - B % 4))
         if B % 4:                                         # per-table rows must stay 16-byte aligned
             cr = torch.nn.functional.pad(cr, (0, 4 - B % 4))
             dg_all = torch.nn.functional.pad(dg_all, (0, 4 - B % 4))
@@ -278,8 +298,12 @@ class _IclMany(torch.autograd.Function):
                 q = probs[p]
                 S3, D = q["S3"], q["D"]
                 Ya, Yb = S3[Bp:3 * Bp], S3[0:2 * Bp]
-                Ga = be.icl_bwd_logits(S3[a0:a0 + nx], Ya, B, Bp, inv_tau, q["cra"], q["crb"], q["dg"], a0, nx)   # [nx, 2Bp] bf16
-                Gb = be.icl_bwd_logits(S3[Bp + a0:Bp + a0 + nx], Yb, B, Bp, inv_tau, q["crb"], q["cra"], q["dg"], a0, nx)
+                if p in esaved:                               # dL/dlogits from the E the forward kept: no second pass over D
+                    Ga = be.icl_g_from_e(esaved[p], 0, B, Bp, q["cra"], q["crb"], diag_all[p], inv_tau)
+                    Gb = be.icl_g_from_e(esaved[p], 1, B, Bp, q["crb"], q["cra"], diag_all[p], inv_tau)
+                else:
+                    Ga = be.icl_bwd_logits(S3[a0:a0 + nx], Ya, B, Bp, inv_tau, q["cra"], q["crb"], q["dg"], a0, nx)   # [nx, 2Bp] bf16
+                    Gb = be.icl_bwd_logits(S3[Bp + a0:Bp + a0 + nx], Yb, B, Bp, inv_tau, q["crb"], q["cra"], q["dg"], a0, nx)
                 # row i of G carries every term of dL/d(anchor i) — its own softmax row and its appearances as a column
                 # in the other rows' softmaxes (the cc / cr_j terms of EpiIclBwd) — so the owned rows of dA, dB are complete
                 kp = {"keep_parts": True} if (shard.world == 1 and hasattr(be, "normalize_bwd_scatter_many")) else {}

@@ -740,11 +740,14 @@ def icl_side(X: torch.Tensor, Y: torch.Tensor, B: int, Bp: int, inv_tau: float, 
 ICL_SYM_MAX_PROBLEMS = 16
 
 
-def icl_fwd_sym(S3s, B: int, Bp: int, inv_tau: float, rank: int = 0, world: int = 1, all_reduce=None) -> torch.Tensor:
+def icl_fwd_sym(S3s, B: int, Bp: int, inv_tau: float, rank: int = 0, world: int = 1, all_reduce=None,
+                esave=None) -> torch.Tensor:
     """Forward statistics of icl_loss for several tables that share the batch, on half the Gram matrix of the stacked
     rows (snag_icl_fwd_sym): S3s[p] = [a ; b ; ...] as [>= 2 Bp, Dpad] bf16 (same Dpad). Returns fp32 [n_prob, 4, B] =
     (lse_a, nll_a, lse_b, nll_b) per table. With world > 1 this rank processes its contiguous share of the work units
-    and `all_reduce(tensor) -> tensor` (sum over the ranks) combines the partial sums before the logarithm."""
+    and `all_reduce(tensor) -> tensor` (sum over the ranks) combines the partial sums before the logarithm.
+    esave: optional list (one entry per table, None to skip) of bf16 [2 Bp, 2 Bp] buffers that receive E of every computed
+    element for icl_g_from_e (single rank only: the buffer must see all work units)."""
     import ctypes
     n_prob = len(S3s)
     if not 1 <= n_prob <= ICL_SYM_MAX_PROBLEMS:
@@ -765,12 +768,20 @@ def icl_fwd_sym(S3s, B: int, Bp: int, inv_tau: float, rank: int = 0, world: int 
     buf = torch.zeros((n_prob * 3 * Bp,), dtype=torch.float32, device=dev) if world > 1 else \
         torch.empty((n_prob * 3 * Bp,), dtype=torch.float32, device=dev)
     total, pos = buf[:n_prob * 2 * Bp], buf[n_prob * 2 * Bp:]
-    arr = lambda ts: (ctypes.c_void_p * n_prob)(*[t.data_ptr() for t in ts])
+    arr = lambda ts: (ctypes.c_void_p * n_prob)(*[None if t is None else t.data_ptr() for t in ts])
+    es = None
+    if esave is not None and any(t is not None for t in esave):
+        if world != 1 or len(esave) != n_prob:
+            raise ValueError("esave needs one entry per table and an unsharded launch")
+        for t in esave:
+            if t is not None and (t.dtype != torch.bfloat16 or tuple(t.shape) != (2 * Bp, 2 * Bp) or not t.is_contiguous()):
+                raise ValueError("esave buffers must be contiguous bf16 [2 Bp, 2 Bp]")
+        es = arr(esave)
     tiles = (2 * Bp // 256) ** 2 + 2 * Bp // 256            # per table: the staircase of 128-row blocks x 256-column tiles
     share = (u1 - u0) / max(1, units)
     with _SweepTimer("icl_fwd_sym_kernel", int(n_prob * tiles * share) * 128, 256, dpad):
         call("snag_icl_fwd_sym", n_prob, arr(S3s), arr([rowpart[i] for i in range(n_prob)]),
-             arr([colpart[i] for i in range(n_prob)]), ptr(pos), B, Bp, dpad, float(inv_tau), u0, u1, ptr(total),
+             arr([colpart[i] for i in range(n_prob)]), ptr(pos), B, Bp, dpad, float(inv_tau), u0, u1, ptr(total), es,
              current_stream())
     if world > 1:
         buf = all_reduce(buf)
@@ -778,6 +789,23 @@ def icl_fwd_sym(S3s, B: int, Bp: int, inv_tau: float, rank: int = 0, world: int 
     out = torch.empty((n_prob, 4, B), dtype=torch.float32, device=dev)
     call("snag_icl_sym_finalize", ptr(total), ptr(pos), n_prob, B, Bp, float(inv_tau), ptr(out), current_stream())
     return out
+
+
+def icl_g_from_e(E: torch.Tensor, side: int, B: int, Bp: int, cr_this: torch.Tensor, cr_other: torch.Tensor,
+                 diag: torch.Tensor, inv_tau: float) -> torch.Tensor:
+    """dL/dlogits of one side (bf16 [Bp, 2 Bp], what icl_bwd_logits returns for all anchors) formed from the E the
+    half-Gram forward saved (snag_icl_g_from_e): a bandwidth kernel instead of a recomputation of the logits.
+    diag [B]: the cross-diagonal values G[i, i] = (g_a expm1(-nll_a) + g_b expm1(-nll_b)) / tau (see the header)."""
+    if E.dtype != torch.bfloat16 or tuple(E.shape) != (2 * Bp, 2 * Bp) or not E.is_contiguous():
+        raise ValueError("E must be contiguous bf16 [2 Bp, 2 Bp]")
+    for t, nm in ((cr_this, "cr_this"), (cr_other, "cr_other"), (diag, "diag")):
+        _need(t, torch.float32, nm, 1)
+        if t.numel() < B:
+            raise ValueError(f"{nm} needs at least B entries")
+    G = torch.empty((Bp, 2 * Bp), dtype=torch.bfloat16, device=E.device)
+    call("snag_icl_g_from_e", ptr(E), int(side), B, Bp, ptr(cr_this), ptr(cr_other), ptr(diag), float(inv_tau), ptr(G),
+         current_stream())
+    return G
 
 
 def icl_bwd_logits(X: torch.Tensor, Y: torch.Tensor, B: int, Bp: int, inv_tau: float, cr: torch.Tensor,

@@ -445,6 +445,40 @@ def test_fused_backward_kernel_matches_two_kernel_form(cuda_device, B, D, n_prob
             assert float(tot[:, D:].abs().max() if D < dpad else 0.0) == 0.0              # padded columns stay zero
 
 
+@pytest.mark.parametrize("B,D,tau", [(1000, 1200, 0.1), (300, 384, 0.05), (2049, 640, 0.1), (130, 1800, 0.5)])
+def test_dlogits_from_saved_e_equals_recomputation(cuda_device, B, D, tau):
+    """The backward of the wide tables: dL/dlogits formed from the E the half-Gram forward saved (bandwidth kernel,
+    straight / transposed / diagonal tile reads) against the sweep that recomputes the logits (sim_kernel<EpiIclBwd>).
+    E is rounded to bf16 once more than in the recomputation: elementwise agreement to two bf16 ulps."""
+    g = torch.Generator(device="cuda").manual_seed(B + D)
+    N = 2 * B + 9
+    emb = torch.randn((N, D), generator=g, device=cuda_device)
+    perm = torch.randperm(N, generator=g, device=cuda_device)
+    il, ir = perm[:B].contiguous(), perm[B:2 * B].contiguous()
+    emb[ir] = emb[il] + 0.9 * torch.randn((B, D), generator=g, device=cuda_device)
+    Bp = ops.round_up(B, 256)
+    S3 = ops.icl_stack_prep([emb], il, ir, Bp, True)[0]
+    E = torch.full((2 * Bp, 2 * Bp), float("nan"), dtype=torch.bfloat16, device=cuda_device)   # unwritten entries must not matter
+    st = ops.icl_fwd_sym([S3], B, Bp, 1.0 / tau, esave=[E])
+    ref_st = ops.icl_fwd_sym([S3], B, Bp, 1.0 / tau)
+    assert torch.equal(st, ref_st)                                       # saving E does not change the statistics
+    ga = torch.rand((B,), generator=g, device=cuda_device) / B
+    gb = torch.rand((B,), generator=g, device=cuda_device) / B
+    cra = (ga * torch.exp(1.0 / tau - st[0, 0])).contiguous()
+    crb = (gb * torch.exp(1.0 / tau - st[0, 2])).contiguous()
+    dg = (ga + gb).contiguous()
+    diag = ((ga * torch.expm1(-st[0, 1]) + gb * torch.expm1(-st[0, 3])) / tau).contiguous()     # from the fp32 NLL
+    for side, (x0, ys, cr, cc) in enumerate(((0, slice(Bp, 3 * Bp), cra, crb), (Bp, slice(0, 2 * Bp), crb, cra))):
+        want = ops.icl_bwd_logits(S3[x0:x0 + Bp], S3[ys], B, Bp, 1.0 / tau, cr, cc, dg).float()
+        got = ops.icl_g_from_e(E, side, B, Bp, cr, cc, diag, 1.0 / tau).float()
+        assert torch.isfinite(got).all()
+        err = (got - want).abs()
+        tol = 2.0 ** -6 * want.abs() + 1e-4 * float(want.abs().max())     # (the cross diagonal: two fp32 routes to a small difference)
+        bad = err > tol
+        assert int(bad.sum()) == 0, (side, int(bad.sum()), float(err.max()), float(want.abs().max()))
+        assert _relerr(got, want) < 6e-3
+
+
 @pytest.mark.parametrize("n_rows,d,k", [(256, 300, 512), (1000, 1200, 2048), (3584, 1800, 7168), (130, 64, 256)])
 def test_grad_contract_rows_equals_transposed_form(cuda_device, n_rows, d, k):
     """snag_sim_write_t_mn (the stacked rows read MN-major by the tensor cores, no transposed copy) against
@@ -491,6 +525,17 @@ def test_loss_layer_fused_equals_unfused(cuda_device, B, D, M, monkeypatch):
     assert results[0][0] == results[1][0]
     for a, b in zip(results[0][1], results[1][1]):
         assert _relerr(a, b) < 2e-3
+    # the wide tables' backward from the saved E (default) against the recomputing backward
+    monkeypatch.setattr(sloss, "FUSED_BACKWARD", True)
+    monkeypatch.setattr(sloss, "SAVE_E", False)
+    for t in leaves:
+        t.grad = None
+    loss = layer(streams, hidden, joint, joint_fz, links, wn)
+    loss.backward()
+    assert loss.item() == results[0][0]
+    for a, t in zip(results[0][1], leaves):
+        assert _relerr(a, t.grad) < 6e-3
+    monkeypatch.setattr(sloss, "SAVE_E", True)
     # and the batched call equals separate icl_loss calls
     crit = sloss.icl_loss(tau=0.1, ab_weight=0.5)
     single = crit(streams[0], links, weight_norm=(wn * 6)[:, 3])
