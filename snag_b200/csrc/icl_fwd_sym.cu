@@ -463,26 +463,56 @@ __global__ void __launch_bounds__(256) icl_g_from_e_kernel(const __nv_bfloat16* 
   const int zr0 = side * Bp + i0;                    // rows / columns of Z
   const int zc0 = (part == 0 ? (1 - side) : side) * Bp + j0;
   const bool any = i0 < B && j0 < B;
-  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;       // 4 rows per pass
+  const int cg = threadIdx.x & 7;                    // 8 groups of 8 consecutive columns: 16-byte loads and stores
+  const int r0 = threadIdx.x >> 3;                   // 32 rows per pass
   if (any) {
     const int R0 = min(zr0, zc0), C0 = max(zr0, zc0);
-#pragma unroll 4
-    for (int r = ty; r < 64; r += 4) tile[r][tx] = __bfloat162float(E[static_cast<long long>(R0 + r) * twoBp + C0 + tx]);
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+      const int r = r0 + 32 * pass;
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(E + static_cast<long long>(R0 + r) * twoBp + C0 + cg * 8));
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        tile[r][cg * 8 + 2 * k] = __uint_as_float(w[k] << 16);
+        tile[r][cg * 8 + 2 * k + 1] = __uint_as_float(w[k] & 0xffff0000u);
+      }
+    }
   }
   __syncthreads();
   const float* ccp = part ? cr_this : cr_other;
-  const int j = j0 + tx;
-  const float cc = (any && j < B) ? __ldg(ccp + j) * inv_tau : 0.f;
-#pragma unroll 4
-  for (int r = ty; r < 64; r += 4) {
+  float cc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int j = j0 + cg * 8 + k;
+    cc[k] = (any && j < B) ? __ldg(ccp + j) * inv_tau : 0.f;
+  }
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    const int r = r0 + 32 * pass;
     const int i = i0 + r;
-    float gv = 0.f;
-    if (any && i < B && j < B) {
-      const float e = zc0 > zr0 ? tile[r][tx] : (zc0 < zr0 ? tile[tx][r] : tile[min(r, tx)][max(r, tx)]);
-      gv = (__ldg(cr_this + i) * inv_tau + cc) * e;
-      if (i == j) gv = part ? 0.f : __ldg(diag + i);
+    const bool row_ok = any && i < B;
+    const float cri = row_ok ? __ldg(cr_this + i) * inv_tau : 0.f;
+    uint32_t pk[4];
+#pragma unroll
+    for (int k = 0; k < 8; k += 2) {
+      float gv[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c = cg * 8 + k + h;
+        const int j = j0 + c;
+        float v = 0.f;
+        if (row_ok && j < B) {
+          const float e = zc0 > zr0 ? tile[r][c] : (zc0 < zr0 ? tile[c][r] : tile[min(r, c)][max(r, c)]);
+          v = (cri + cc[k + h]) * e;
+          if (i == j) v = part ? 0.f : __ldg(diag + i);
+        }
+        gv[h] = v;
+      }
+      const __nv_bfloat162 h2 = __floats2bfloat162_rn(gv[0], gv[1]);
+      pk[k >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
     }
-    G[static_cast<long long>(i) * twoBp + c0 + tx] = __float2bfloat16_rn(gv);
+    *reinterpret_cast<uint4*>(G + static_cast<long long>(i) * twoBp + c0 + cg * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
   }
 }
 
