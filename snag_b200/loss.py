@@ -528,8 +528,12 @@ class _IalPair(torch.autograd.Function):
             lq, _, _ = be.icl_side(St[xs], St[ys], B, Bp, inv_tau)
             crq = (torch.exp(inv_tau - lq) / inv_tau).contiguous()            # EpiIclBwd multiplies by 1/tau: Q = cr E / tau
             Q = be.icl_bwd_logits(St[xs], St[ys], B, Bp, inv_tau, crq, zero, zero, self_cols=False)   # row softmax of q
-            Ut = be.grad_contract(Q, St[ys].t().contiguous(), B, Dt)          # (Q Y^t) [B, Dt]
-            Us = be.grad_contract(Q, Ss[ys].t().contiguous(), B, Ds)
+            if hasattr(be, "grad_contract_rows"):                               # stacked rows read MN-major: no transposed copy
+                Ut = be.grad_contract_rows(Q, St[ys], B, Dt)                    # (Q Y^t) [B, Dt]
+                Us = be.grad_contract_rows(Q, Ss[ys], B, Ds)
+            else:
+                Ut = be.grad_contract(Q, St[ys].t().contiguous(), B, Dt)
+                Us = be.grad_contract(Q, Ss[ys].t().contiguous(), B, Ds)
             zq = (St[xs][:B, :Dt].float() * Ut).sum(1) * inv_tau
             zp = (Ss[xs][:B, :Ds].float() * Us).sum(1) * inv_tau
             kl.append(zq - zp - lq + lp)
@@ -561,7 +565,8 @@ class _IalPair(torch.autograd.Function):
         for xs, ys, cp_row, cp_col, cq_row, cq_col, idx in sides:
             Gs = be.icl_bwd_logits(Ss[xs], Ss[ys], B, Bp, inv_tau, cp_row, cp_col, zero, ebar=ebar)   # g (P + transposed-role P) / tau
             Gt = be.icl_bwd_logits(St[xs], St[ys], B, Bp, inv_tau, cq_row, cq_col, zero, ebar=ebar)   # the same for Q
-            dz = be.grad_contract(Gs - Gt, Ss[ys].t().contiguous(), B, Ds)
+            dz = be.grad_contract_rows(Gs - Gt, Ss[ys], B, Ds) if hasattr(be, "grad_contract_rows") else \
+                be.grad_contract(Gs - Gt, Ss[ys].t().contiguous(), B, Ds)
             Y0 = Ss[ys][:B, :Ds].float()                       # cross columns: the other side
             Y1 = Ss[ys][Bp:Bp + B, :Ds].float()                # self columns: this side (column i is masked for row i)
             dr, dc0, dc1 = cp_row - cq_row, cp_col - cq_col, cp_row - cq_row
