@@ -560,16 +560,22 @@ def metrics_from_ranks(ranks, top_k=TOP_K) -> AlignMetrics:
     """Hits@k / MR / MRR from 0-based integer ranks, reproducing the reference's accumulators:
     hit counters are np.float32 (main.py:382-383), mean uses Python ints, mrr is a Python float summed in
     index order (main.py:403-404) -> np.cumsum in float64 is the same sequence of additions."""
-    r = np.asarray(ranks.detach().cpu().numpy() if isinstance(ranks, torch.Tensor) else ranks).astype(np.int64)
+    r = np.asarray(ranks.detach().cpu().numpy() if isinstance(ranks, torch.Tensor) else ranks)
     n = r.shape[0]
     if n == 0:
         raise ValueError("no test pairs")
-    hits = np.array([(r < k).sum() for k in top_k], dtype=np.int64)
+    hits = np.array([np.count_nonzero(r < k) for k in top_k], dtype=np.int64)
     acc = np.zeros((len(top_k),), dtype=np.float32)
     for i in range(len(top_k)):
         acc[i] = round(np.float32(hits[i]) / n, 4)
-    mr = float(int((r + 1).sum())) / n
-    mrr = float(np.cumsum(1.0 / (r + 1).astype(np.float64))[-1]) / n
+    mr = float(int(r.sum(dtype=np.int64)) + n) / n                 # sum of the 1-based ranks, exact in integers
+    # 1 / (rank + 1) in float64 (rank + 1 is exact), then the SEQUENTIAL left-to-right sum of main.py:404 — accumulate, not
+    # np.sum, whose pairwise summation rounds differently. In place: one 8 MB buffer at 1M pairs (this runs on the host after
+    # every evaluation; at 8 GPUs it is a visible part of the step).
+    rec = r.astype(np.float64)
+    rec += 1.0
+    np.reciprocal(rec, out=rec)
+    mrr = float(np.add.accumulate(rec, out=rec)[-1]) / n
     return AlignMetrics(acc, mr, mrr, hits)
 
 
