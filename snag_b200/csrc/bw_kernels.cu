@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(256) col_stats_partial_kernel(const float* __r
     atomicAdd(cnt, n);
   }
 }
-// float4 variant (F % 4 == 0, 16-byte aligned rows): 4 columns per thread, 4 rows in flight per thread
+// float4 variant (F % 4 == 0, 16-byte aligned rows): 4 columns per thread, 8 rows in flight per thread
 __global__ void __launch_bounds__(256) col_stats_partial4_kernel(const float* __restrict__ x, const uint8_t* __restrict__ valid,
                                                                  long long N, int F, long long ld, int rows_per_slab,
                                                                  double* __restrict__ acc, unsigned long long* __restrict__ cnt) {
@@ -156,16 +156,16 @@ __global__ void __launch_bounds__(256) col_stats_partial4_kernel(const float* __
   if (col < F) {
     const float* base = x + col;
     long long r = r0;
-    for (; r + 4 <= r1; r += 4) {
-      float4 v[4];
-      bool ok[4];
+    for (; r + 8 <= r1; r += 8) {                     // 8 rows (128 bytes per thread) in flight: the kernel is latency bound
+      float4 v[8];
+      bool ok[8];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < 8; ++u) {
         ok[u] = !valid || valid[r + u];
         v[u] = ok[u] ? __ldg(reinterpret_cast<const float4*>(base + (r + u) * ld)) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < 8; ++u) {
         const double a = v[u].x, b = v[u].y, c = v[u].z, d = v[u].w;
         s[0] += a; s[1] += b; s[2] += c; s[3] += d;
         ss[0] += a * a; ss[1] += b * b; ss[2] += c * c; ss[3] += d * d;
@@ -243,6 +243,74 @@ __global__ void __launch_bounds__(256) rowblend_bwd_kernel(const float* __restri
 // pairwise_distances (src/utils.py:210-212) on exactly the values the tensor cores will see.
 // One warp per row; lanes stride the row so loads/stores are coalesced.
 // ------------------------------------------------------------------------------------------------
+// One row (warp-cooperative): normalise (optional), round to bf16, zero pad to Dpad, return the fp64 sum of squares of the
+// rounded values (valid on every lane). Rows whose width is a multiple of 4 and whose storage is 16-byte aligned take the
+// float4 path: the row is read ONCE (up to 16 float4 per lane stay in registers between the norm and the rounding; wider
+// rows re-read the tail from L1), 8-byte stores. The scalar path handles everything else. Both kernels below use it, so
+// their outputs are bit-identical.
+__device__ __forceinline__ double prep_row(const float* __restrict__ src, int D, int Dpad, int normalize,
+                                           __nv_bfloat16* __restrict__ dst, int lane, bool vec4) {
+  double acc = 0.0;
+  if (vec4) {
+    constexpr int KEEP = 16;                          // float4 per lane kept in registers: D <= 2048
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    const int n4 = D >> 2, np4 = Dpad >> 2;
+    float4 v[KEEP];
+    float ss = 0.f;
+#pragma unroll
+    for (int u = 0; u < KEEP; ++u) {
+      const int c4 = lane + 32 * u;
+      v[u] = c4 < n4 ? __ldg(s4 + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      ss = __fmaf_rn(v[u].x, v[u].x, ss); ss = __fmaf_rn(v[u].y, v[u].y, ss);
+      ss = __fmaf_rn(v[u].z, v[u].z, ss); ss = __fmaf_rn(v[u].w, v[u].w, ss);
+    }
+    for (int c4 = lane + 32 * KEEP; c4 < n4; c4 += 32) {
+      const float4 t = __ldg(s4 + c4);
+      ss = __fmaf_rn(t.x, t.x, ss); ss = __fmaf_rn(t.y, t.y, ss); ss = __fmaf_rn(t.z, t.z, ss); ss = __fmaf_rn(t.w, t.w, ss);
+    }
+    float denom = 1.0f;
+    if (normalize) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      denom = fmaxf(sqrtf(ss), 1e-12f);
+    }
+    auto emit = [&](int c4, float4 t) {
+      if (normalize) { t.x = __fdiv_rn(t.x, denom); t.y = __fdiv_rn(t.y, denom); t.z = __fdiv_rn(t.z, denom); t.w = __fdiv_rn(t.w, denom); }
+      const __nv_bfloat162 lo = __floats2bfloat162_rn(t.x, t.y), hi = __floats2bfloat162_rn(t.z, t.w);
+      *reinterpret_cast<uint2*>(dst + 4 * c4) = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+      const double a = __bfloat162float(lo.x), b = __bfloat162float(lo.y), c = __bfloat162float(hi.x), d = __bfloat162float(hi.y);
+      acc += a * a; acc += b * b; acc += c * c; acc += d * d;
+    };
+#pragma unroll
+    for (int u = 0; u < KEEP; ++u) {
+      const int c4 = lane + 32 * u;
+      if (c4 < np4) emit(c4, v[u]);                   // beyond n4 the registers hold zeros: the padding
+    }
+    for (int c4 = lane + 32 * KEEP; c4 < np4; c4 += 32)
+      emit(c4, c4 < n4 ? __ldg(s4 + c4) : make_float4(0.f, 0.f, 0.f, 0.f));
+  } else {
+    float denom = 1.0f;
+    if (normalize) {
+      float ss = 0.f;
+      for (int c = lane; c < D; c += 32) { const float v = __ldg(src + c); ss = __fmaf_rn(v, v, ss); }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      denom = fmaxf(sqrtf(ss), 1e-12f);
+    }
+    for (int c = lane; c < Dpad; c += 32) {
+      float v = 0.f;
+      if (c < D) v = normalize ? __fdiv_rn(__ldg(src + c), denom) : __ldg(src + c);
+      const __nv_bfloat16 b = __float2bfloat16_rn(v);
+      dst[c] = b;
+      const double w = static_cast<double>(__bfloat162float(b));
+      acc += w * w;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  return acc;
+}
+
 __global__ void __launch_bounds__(256) prep_bf16_kernel(const float* __restrict__ emb, long long ld,
                                                         const long long* __restrict__ idx, int n, int D, int normalize,
                                                         __nv_bfloat16* __restrict__ out, int Dpad,
@@ -251,26 +319,8 @@ __global__ void __launch_bounds__(256) prep_bf16_kernel(const float* __restrict_
   const int lane = threadIdx.x & 31;
   if (warp >= n) return;
   const float* src = emb + (idx ? idx[warp] : static_cast<long long>(warp)) * ld;
-  float denom = 1.0f;
-  if (normalize) {
-    float ss = 0.f;
-    for (int c = lane; c < D; c += 32) { const float v = __ldg(src + c); ss = __fmaf_rn(v, v, ss); }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-    denom = fmaxf(sqrtf(ss), 1e-12f);
-  }
-  double acc = 0.0;
-  __nv_bfloat16* dst = out + static_cast<long long>(warp) * Dpad;
-  for (int c = lane; c < Dpad; c += 32) {
-    float v = 0.f;
-    if (c < D) v = normalize ? __fdiv_rn(__ldg(src + c), denom) : __ldg(src + c);
-    const __nv_bfloat16 b = __float2bfloat16_rn(v);
-    dst[c] = b;
-    const double w = static_cast<double>(__bfloat162float(b));
-    acc += w * w;
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  const bool vec4 = (D % 4 == 0) && (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(emb) & 15) == 0);
+  const double acc = prep_row(src, D, Dpad, normalize, out + static_cast<long long>(warp) * Dpad, lane, vec4);
   if (lane == 0 && norm2) norm2[warp] = static_cast<float>(acc);
 }
 
@@ -307,19 +357,8 @@ __global__ void __launch_bounds__(256) icl_stack_prep_kernel(const __grid_consta
     return;
   }
   const float* src = a.emb[p] + (part == 1 ? idx_r[i] : idx_l[i]) * a.ld[p];
-  float denom = 1.0f;
-  if (normalize) {
-    float ss = 0.f;
-    for (int c = lane; c < D; c += 32) { const float v = __ldg(src + c); ss = __fmaf_rn(v, v, ss); }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-    denom = fmaxf(sqrtf(ss), 1e-12f);
-  }
-  for (int c = lane; c < Dpad; c += 32) {
-    float v = 0.f;
-    if (c < D) v = normalize ? __fdiv_rn(__ldg(src + c), denom) : __ldg(src + c);
-    dst[c] = __float2bfloat16_rn(v);
-  }
+  const bool vec4 = (D % 4 == 0) && (a.ld[p] % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.emb[p]) & 15) == 0);
+  prep_row(src, D, Dpad, normalize, dst, lane, vec4);
 }
 
 struct ScatterManyArgs {
@@ -1607,7 +1646,8 @@ int launch_col_mean_std(const float* x, const uint8_t* valid, long long N, int F
   if (e != cudaSuccess) return static_cast<int>(e);
   const bool vec4 = (F % 4 == 0) && (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
   const int bx = vec4 ? (F / 4 + 255) / 256 : (F + 255) / 256;
-  // enough row slabs to fill the machine a few times over, at least 64 rows each
+  // enough row slabs to fill the machine a few times over, at least 64 rows each (every slab ends in 2 F fp64 atomics:
+  // 32-row slabs measured slower at N = 39.6k)
   long long slabs = (static_cast<long long>(num_sms()) * 8 + bx - 1) / bx;
   long long rows_per_slab = (N + slabs - 1) / slabs;
   if (rows_per_slab < 64) rows_per_slab = 64;
