@@ -48,8 +48,8 @@ class CustomMultiLossLayer(nn.Module):
         assert k <= self.loss_num
         if k == 0:
             return 0
-        zero = self.log_vars.new_zeros(())
-        terms = torch.stack([l.to(self.log_vars.dtype) if isinstance(l, torch.Tensor) else zero for l in loss_list])
+        lv = self.log_vars
+        terms = torch.stack([l.to(lv.dtype) if isinstance(l, torch.Tensor) else lv.new_tensor(float(l)) for l in loss_list])
         return (torch.exp(-self.log_vars[:k]) * terms + self.log_vars[:k]).sum()
 
 
