@@ -92,6 +92,32 @@ def test_against_oracle(cuda_device, n, d, k, csls, sigma):
         assert m.mr == mo.mr and m.mrr == mo.mrr and np.array_equal(m.acc, mo.acc)
 
 
+def test_wide_dynamic_range_rows_stay_bit_exact(cuda_device):
+    """The canonical re-scores add the fp64 products across 8 lanes only when no addition can round in ANY order
+    (canonical_dot_coop: bound < 2^(39 + Ea + Eb)); rows holding very small elements fail that test and must take the
+    index-order loop. Elements scaled down to 2^-12 .. 2^-40 of their size (and exact zeros, and a few bf16 denormals)
+    exercise both branches; everything stays bit-identical to the oracle, whose fp64 sums DO round here."""
+    rng = np.random.RandomState(77)
+    n, d, k = 700, 200, 10
+    x, y = _clustered(n, d, 2.0, 5)
+    scale = np.float32(2.0) ** -rng.randint(12, 41, size=(n, d)).astype(np.float32)
+    pick = rng.rand(n, d) < 0.05
+    x = np.where(pick, x * scale, x).astype(np.float32)
+    y = np.where(rng.rand(n, d) < 0.05, y * scale[::-1], y).astype(np.float32)
+    x[rng.rand(n, d) < 0.02] = 0.0
+    y[3] = 0.0                                                   # a row of zeros
+    x[5, :4] = np.float32(1e-39)                                 # below bf16's normal range
+    x, y = oracle.bf16_round(x), oracle.bf16_round(y)
+    X, Y, xn, yn = _prep(x, y, cuda_device)
+    res = evaluate.align_ranks(X, Y, xn, yn, n, k, True)
+    ref = oracle.align_eval(x, y, True, k)
+    np.testing.assert_array_equal(res.nv1.cpu().numpy(), ref["nv1"])
+    np.testing.assert_array_equal(res.nv2.cpu().numpy(), ref["nv2"])
+    np.testing.assert_array_equal(res.g.cpu().numpy(), ref["g"])
+    np.testing.assert_array_equal(res.rank_l2r.cpu().numpy(), ref["rank_l2r"])
+    np.testing.assert_array_equal(res.rank_r2l.cpu().numpy(), ref["rank_r2l"])
+
+
 @pytest.mark.parametrize("n,d", [(1500, 1200), (1100, 1800), (2100, 300)])
 def test_tensor_core_dot_error(cuda_device, n, d):
     """The deferral band of the rank sweep (ops.tc_margin) must cover the distance between the tensor core's dot
