@@ -498,7 +498,7 @@ def _align_ranks_lazy(be, X, Y, xn, yn, n, csls_k, use_csls, want_top3):
 
 
 def align_ranks(X: torch.Tensor, Y: torch.Tensor, xn: torch.Tensor, yn: torch.Tensor, n: int, csls_k: int = 10,
-                use_csls: bool = True, want_top3: bool = False, group=None, backend=None,
+                use_csls: bool = True, want_top3: bool = False, group=None, _backend=None,
                 two_sweep: bool = True, lazy: bool | None = None, one_pass: bool | None = None,
                 pre: dict | None = None) -> AlignRanks:
     """Fused evaluation of n aligned pairs (x_i <-> y_i).
@@ -518,14 +518,14 @@ def align_ranks(X: torch.Tensor, Y: torch.Tensor, xn: torch.Tensor, yn: torch.Te
     # produces; the re-score tolerances scale with the norms, the in-kernel margins do not): refuse rows that are far
     # from that instead of silently weakening the guarantee. Squared norms up to 8 are let through for small exact
     # (dyadic) test inputs.
-    be = _cuda_ops if backend is None else backend
+    be = _cuda_ops if _backend is None else _backend     # test seam: host-logic tests run the generator on a CPU stand-in
     if group is None:
         world, rank = 1, 0
     else:
         import torch.distributed as dist
         world, rank = dist.get_world_size(group), dist.get_rank(group)
     if lazy is None:
-        lazy = world == 1 and backend is None and n < TWO_SWEEP_MIN_N
+        lazy = world == 1 and _backend is None and n < TWO_SWEEP_MIN_N
     if lazy:
         res = _align_ranks_lazy(be, X, Y, xn, yn, n, csls_k, use_csls, want_top3)
         if res is not None:

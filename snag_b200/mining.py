@@ -15,7 +15,7 @@ from . import ops as _cuda_ops
 from ._lib import KT, SnagError
 
 
-def mutual_nearest(x: torch.Tensor, y: torch.Tensor, normalize: bool = False, backend=None, canonical: bool = True):
+def mutual_nearest(x: torch.Tensor, y: torch.Tensor, normalize: bool = False, _backend=None, canonical: bool = True):
     """(preds_l int64 [n1], preds_r int64 [n2], dmin_l fp32 [n1], dmin_r fp32 [n2]): for every row of x its nearest row
     of y under the squared distance of src/utils.pairwise_distances, and vice versa.
 
@@ -25,7 +25,7 @@ def mutual_nearest(x: torch.Tensor, y: torch.Tensor, normalize: bool = False, ba
     exhaustive completion as the CSLS neighbourhoods. The result does not depend on the MMA accumulation order.
     canonical=False: the single fused sweep (sim_kernel<EpiMutualNN>) that takes both argmins straight from the
     tensor-core distances — exact ties still go to the lowest index, near-ties (< 1e-6) follow the tensor core."""
-    be = _cuda_ops if backend is None else backend
+    be = _cuda_ops if _backend is None else _backend     # test seam (tests/oracle_backend.py); the product never passes it
     n1, n2 = x.shape[0], y.shape[0]
     X, xn = be.prep_bf16(x.contiguous().float(), None, normalize)
     Y, yn = be.prep_bf16(y.contiguous().float(), None, normalize)
@@ -61,7 +61,7 @@ def mutual_nearest(x: torch.Tensor, y: torch.Tensor, normalize: bool = False, ba
     return preds_l, preds_r, dmin_l, dmin_r
 
 
-def iter_new_links(left_non_train, right_non_train, final_emb: torch.Tensor, new_links, refresh: bool, backend=None):
+def iter_new_links(left_non_train, right_non_train, final_emb: torch.Tensor, new_links, refresh: bool, _backend=None):
     """Body of Iter_new_links: mutual nearest pairs; when `refresh` is False only those already in `new_links` survive
     (model/SNAG.py:203-206). Entity ids in, list of (left id, right id) tuples out, in increasing order of the position
     in `left_non_train` (the order of the reference's list comprehension)."""
@@ -70,7 +70,7 @@ def iter_new_links(left_non_train, right_non_train, final_emb: torch.Tensor, new
     dev = final_emb.device
     left = torch.as_tensor(list(left_non_train), dtype=torch.int64, device=dev)
     right = torch.as_tensor(list(right_non_train), dtype=torch.int64, device=dev)
-    preds_l, preds_r, _, _ = mutual_nearest(final_emb.index_select(0, left), final_emb.index_select(0, right), backend=backend)
+    preds_l, preds_r, _, _ = mutual_nearest(final_emb.index_select(0, left), final_emb.index_select(0, right), _backend=_backend)
     pos = torch.arange(left.numel(), device=dev)
     keep = preds_r[preds_l] == pos
     pl, pr = left[keep], right[preds_l[keep]]

@@ -22,10 +22,10 @@ from . import ops as _cuda_ops
 from ._lib import KT, SnagError
 
 
-def topk_similarity_entries(left_f: torch.Tensor, right_f: torch.Tensor, K: int, backend=None):
+def topk_similarity_entries(left_f: torch.Tensor, right_f: torch.Tensor, K: int, _backend=None):
     """(rows int64 [K'], cols int64 [K'], sims fp32 [K']) — the K' = min(K, n_l * n_r) largest entries of
     left_f @ right_f.T in descending order, ties by ascending flat index (get_topk_indices, src/utils.py:437-443)."""
-    be = _cuda_ops if backend is None else backend
+    be = _cuda_ops if _backend is None else _backend     # test seam (tests/oracle_backend.py); the product never passes it
     n_l, n_r = left_f.shape[0], right_f.shape[0]
     K = min(int(K), n_l * n_r)
     if K <= 0:
@@ -47,7 +47,7 @@ def topk_similarity_entries(left_f: torch.Tensor, right_f: torch.Tensor, K: int,
         thr = torch.topk(pool, K).values[-1] - 4e-6
     colthr = torch.full((n_r,), float(thr), dtype=torch.float32, device=dev)
     colb = (0.5 * colthr - 4e-6).contiguous()                                       # s > (yn - 1 + thr)/2 with yn = 1
-    n_ctas = int(_cuda_ops._lib.load().snag_num_sms()) if backend is None else 148
+    n_ctas = int(_cuda_ops._lib.load().snag_num_sms()) if _backend is None else 148
     cap = _cuda_ops.round_up(int(2.5 * max(K, 4096) / n_ctas) + 4096, 1024)
     while True:
         _, _, stream, stream_row, stream_cnt = be.eval_rowcoltopk(X, Y, one_l, one_r, n_l, n_r, colthr, colb, cap)

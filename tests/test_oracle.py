@@ -249,13 +249,13 @@ def test_mining_host_logic_on_cpu_backend(name):
     fx = load_golden(name)
     emb = torch.from_numpy(fx["emb"])
     left, right = fx["left"].tolist(), fx["right"].tolist()
-    pl, pr, dl, dr = mining.mutual_nearest(emb[left], emb[right], backend=oracle_backend)
+    pl, pr, dl, dr = mining.mutual_nearest(emb[left], emb[right], _backend=oracle_backend)
     np.testing.assert_array_equal(pl.numpy(), fx["preds_l"])
     np.testing.assert_array_equal(pr.numpy(), fx["preds_r"])
     np.testing.assert_allclose(dr.numpy(), fx["dmin_r"], atol=1e-6, rtol=0)
-    assert mining.iter_new_links(left, right, emb, [], True, backend=oracle_backend) == [tuple(t) for t in fx["links_refresh"].tolist()]
+    assert mining.iter_new_links(left, right, emb, [], True, _backend=oracle_backend) == [tuple(t) for t in fx["links_refresh"].tolist()]
     prev = [tuple(t) for t in fx["prev"].tolist()]
-    assert mining.iter_new_links(left, right, emb, prev, False, backend=oracle_backend) == [tuple(t) for t in fx["links_filter"].tolist()]
+    assert mining.iter_new_links(left, right, emb, prev, False, _backend=oracle_backend) == [tuple(t) for t in fx["links_filter"].tolist()]
 
 
 @pytest.mark.parametrize("name", golden_names("fusion_"))

@@ -71,7 +71,7 @@ def _gloo_worker(rank, world, port, name, out):
     fx = load_golden(name)
     X, Y, xn, yn, n = _operands(fx)
     res = evaluate.align_ranks(X, Y, xn, yn, n, int(fx["k"]), bool(fx["csls"]), True, group=dist.group.WORLD,
-                               backend=oracle_backend)
+                               _backend=oracle_backend)
     ok = (np.array_equal(res.rank_l2r.numpy(), fx["rank_l2r"]) and np.array_equal(res.rank_r2l.numpy(), fx["rank_r2l"])
           and np.array_equal(res.top3_idx.numpy(), fx["top3"]))
     out[rank] = bool(ok)
