@@ -37,6 +37,40 @@ def _sig(f):
 
 
 @needs_ref
+def test_loss_weighting_layers_equal_the_reference_classes():
+    """CustomMultiLossLayer (evaluated on stacked tensors here) and AutomaticWeightedLoss against the reference's own
+    classes on CPU: value and gradients, with the int 0 an absent modality contributes (model/SNAG.py:147-160), with a
+    short list, and the state-dict keys the optimiser groups by (src/utils.py:46-54)."""
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    from refshim import load_reference
+    ref = load_reference()
+    import importlib
+    from snag_b200 import loss
+    torch.manual_seed(0)
+    for entries in ([0.7, 1.3, 0, 0.2], [2.0, 0, 0, 0, 0.5, 1.0], [0.4], [0, 0]):
+        mine, theirs = loss.CustomMultiLossLayer(loss_num=6), ref.loss.CustomMultiLossLayer(loss_num=6)
+        assert list(mine.state_dict().keys()) == list(theirs.state_dict().keys()) == ["log_vars"]
+        lv = torch.randn(6)
+        with torch.no_grad():
+            mine.log_vars.copy_(lv)
+            theirs.log_vars.copy_(lv)
+        outs = []
+        for layer in (mine, theirs):
+            ls = [torch.tensor(float(v), requires_grad=True) if v != 0 else 0 for v in entries]
+            out = layer(ls)
+            out.backward()
+            outs.append((out.item(), layer.log_vars.grad.clone(), [l.grad.item() for l in ls if isinstance(l, torch.Tensor)]))
+        np.testing.assert_allclose(outs[0][0], outs[1][0], rtol=1e-6)
+        np.testing.assert_allclose(outs[0][1].numpy(), outs[1][1].numpy(), rtol=1e-6, atol=1e-7)
+        np.testing.assert_allclose(outs[0][2], outs[1][2], rtol=1e-6)
+    awl_ref = importlib.import_module("model.Tool_model").AutomaticWeightedLoss(7)
+    awl = loss.AutomaticWeightedLoss(7)
+    assert list(awl.state_dict().keys()) == list(awl_ref.state_dict().keys())
+    xs = [torch.tensor(v) for v in (0.3, 1.1, 2.0)]
+    np.testing.assert_allclose(awl(*xs).item(), awl_ref(*xs).item(), rtol=1e-6)
+
+
+@needs_ref
 def test_signatures_match_reference():
     sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
     from refshim import load_reference
