@@ -49,7 +49,8 @@ class CustomMultiLossLayer(nn.Module):
         if k == 0:
             return 0
         lv = self.log_vars
-        terms = torch.stack([l.to(lv.dtype) if isinstance(l, torch.Tensor) else lv.new_tensor(float(l)) for l in loss_list])
+        # numeric entries become device scalars through a fill (no host -> device copy: the step stays graph capturable)
+        terms = torch.stack([l.to(lv.dtype) if isinstance(l, torch.Tensor) else lv.new_full((), float(l)) for l in loss_list])
         return (torch.exp(-self.log_vars[:k]) * terms + self.log_vars[:k]).sum()
 
 
