@@ -192,6 +192,45 @@ def icl_side(X, Y, B, Bp, inv_tau, row0=0, nx=None):
     return lse, lse - pos * inv_tau, pos
 
 
+ICL_SYM_MAX_PROBLEMS = 16
+
+
+def icl_fwd_sym(S3s, B, Bp, inv_tau, rank=0, world=1, all_reduce=None, esave=None):
+    """CPU stand-in for ops.icl_fwd_sym: the strict upper triangle of Z.Z^T (Z = [a ; b]) contributes every element to the
+    row sum of its row and of its column; with world > 1 this rank takes the elements whose ROW index is congruent to its
+    rank (a different split of the same work than the kernel's unit ranges — any split must add up) and `all_reduce` sums
+    the partial totals and the positive logits. Returns [n_prob, 4, B] = (lse_a, nll_a, lse_b, nll_b)."""
+    outs = []
+    parts = []
+    for S3 in S3s:
+        Z = S3[:2 * Bp].float()
+        S = Z @ Z.t()
+        valid = torch.zeros(2 * Bp, dtype=torch.bool)
+        valid[:B] = True
+        valid[Bp:Bp + B] = True
+        E = torch.exp(S * inv_tau - inv_tau)
+        keep = torch.triu(torch.ones_like(S, dtype=torch.bool), 1) & valid[:, None] & valid[None, :]
+        mine = (torch.arange(2 * Bp) % world == rank)[:, None]
+        E = torch.where(keep & mine, E, torch.zeros(()))
+        total = E.sum(1) + E.sum(0)
+        pos = torch.zeros(Bp)
+        own = (torch.arange(B) % world == rank)
+        idx = torch.arange(B)[own]
+        pos[idx] = S[idx, Bp + idx]
+        parts.append(torch.cat([total, pos]))
+    buf = torch.stack(parts, 0).reshape(-1).contiguous()
+    if world > 1:
+        buf = all_reduce(buf)
+    buf = buf.view(len(S3s), 3 * Bp)
+    for p in range(len(S3s)):
+        total, pos = buf[p, :2 * Bp], buf[p, 2 * Bp:]
+        la = torch.log(total[:B]) + inv_tau
+        lb = torch.log(total[Bp:Bp + B]) + inv_tau
+        ps = pos[:B] * inv_tau
+        outs.append(torch.stack([la, la - ps, lb, lb - ps], 0))
+    return torch.stack(outs, 0)
+
+
 def icl_bwd_logits(X, Y, B, Bp, inv_tau, cr, cc, dg, row0=0, nx=None, self_cols=True, ebar=0.0):
     nx = Bp if nx is None else nx
     s, dead, gr = _icl_logits(X, Y, B, Bp, inv_tau, row0, nx)
