@@ -862,14 +862,17 @@ def run_snag(args, name):
         line["cpu_baseline"] = {kk: cb[kk] for kk in ("value", "unit", "cores", "kind", "sample")}
         line["reference_literal_steps"] = reference_steps_sample(min(2048, n), d, k, sigma)
         if not args.no_context:
-            try:
-                line["snag_step"] = snag_full_step(ctx.dev)
-            except Exception as exc:                      # noqa: BLE001 — a context leg must not take the headline down
-                line["snag_step"] = {"error": f"{type(exc).__name__}: {exc}"[:400]}
-            try:
-                line["reference_gpu_eager"] = reference_gpu_eager(ctx.dev)
-            except Exception as exc:                      # noqa: BLE001
-                line["reference_gpu_eager"] = {"error": f"{type(exc).__name__}: {exc}"[:400]}
+            import contextlib
+            # the reference print()s its progress ("loading raw data...") — keep stdout to the ONE JSON line
+            with contextlib.redirect_stdout(sys.stderr):
+                try:
+                    line["snag_step"] = snag_full_step(ctx.dev)
+                except Exception as exc:                  # noqa: BLE001 — a context leg must not take the headline down
+                    line["snag_step"] = {"error": f"{type(exc).__name__}: {exc}"[:400]}
+                try:
+                    line["reference_gpu_eager"] = reference_gpu_eager(ctx.dev)
+                except Exception as exc:                  # noqa: BLE001
+                    line["reference_gpu_eager"] = {"error": f"{type(exc).__name__}: {exc}"[:400]}
         print(json.dumps(line), flush=True)
     ctx.close()
 
