@@ -61,7 +61,8 @@ TRAIN_WORKLOADS = {
 TRAIN_METRIC = "train steps/sec (loss-layer slice: 2+2M icl_loss fwd+bwd)"
 DEFAULT_WORKLOAD = "c4_1m"
 SEED = 3408                       # the reference's scripted seed (run.sh:2)
-CPU_SAMPLE_N = 4096               # bounded sample for the CPU legs: a CPU_SAMPLE_N x CPU_SAMPLE_N sub-problem
+CPU_SAMPLE_N = 8192               # bounded sample for the CPU legs: a CPU_SAMPLE_N x CPU_SAMPLE_N sub-problem (~1 s per pass on
+                                  # 16 host threads: 4 passes of the cpu_baseline leg, K + W passes of the reference arm)
 
 
 # ================================================================================================ helpers
