@@ -243,16 +243,21 @@ __global__ void __launch_bounds__(256) rowblend_bwd_kernel(const float* __restri
 // pairwise_distances (src/utils.py:210-212) on exactly the values the tensor cores will see.
 // One warp per row; lanes stride the row so loads/stores are coalesced.
 // ------------------------------------------------------------------------------------------------
+constexpr int PREP_NARROW_MAX_D = 512;            // rows up to this width fit 4 float4 per lane
 // One row (warp-cooperative): normalise (optional), round to bf16, zero pad to Dpad, return the fp64 sum of squares of the
-// rounded values (valid on every lane). Rows whose width is a multiple of 4 and whose storage is 16-byte aligned take the
-// float4 path: the row is read ONCE (up to 16 float4 per lane stay in registers between the norm and the rounding; wider
-// rows re-read the tail from L1), 8-byte stores. The scalar path handles everything else. Both kernels below use it, so
-// their outputs are bit-identical.
+// rounded values (valid on every lane; only when WANT_SS). Rows whose width is a multiple of 4 and whose storage is 16-byte
+// aligned take the float4 path: the row is read ONCE (up to KEEP float4 per lane stay in registers between the norm and
+// the rounding; wider rows re-read the tail from L1), 8-byte stores. The scalar path handles everything else. Both kernels
+// below use it, and every lane adds its elements in increasing column order whatever KEEP is, so their outputs are
+// bit-identical. KEEP = 4 (D <= 512, the per-modality tables) needs ~40 registers instead of ~100 for KEEP = 16
+// (D <= 2048): the kernels are gathers whose only latency hiding is the number of resident warps. dst2 (or null): a second
+// copy of the row (the repeated part of the stacked ICL operand).
+template <int KEEP, bool WANT_SS>
 __device__ __forceinline__ double prep_row(const float* __restrict__ src, int D, int Dpad, int normalize,
-                                           __nv_bfloat16* __restrict__ dst, int lane, bool vec4) {
+                                           __nv_bfloat16* __restrict__ dst, __nv_bfloat16* __restrict__ dst2, int lane,
+                                           bool vec4) {
   double acc = 0.0;
   if (vec4) {
-    constexpr int KEEP = 16;                          // float4 per lane kept in registers: D <= 2048
     const float4* s4 = reinterpret_cast<const float4*>(src);
     const int n4 = D >> 2, np4 = Dpad >> 2;
     float4 v[KEEP];
@@ -277,9 +282,13 @@ __device__ __forceinline__ double prep_row(const float* __restrict__ src, int D,
     auto emit = [&](int c4, float4 t) {
       if (normalize) { t.x = __fdiv_rn(t.x, denom); t.y = __fdiv_rn(t.y, denom); t.z = __fdiv_rn(t.z, denom); t.w = __fdiv_rn(t.w, denom); }
       const __nv_bfloat162 lo = __floats2bfloat162_rn(t.x, t.y), hi = __floats2bfloat162_rn(t.z, t.w);
-      *reinterpret_cast<uint2*>(dst + 4 * c4) = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
-      const double a = __bfloat162float(lo.x), b = __bfloat162float(lo.y), c = __bfloat162float(hi.x), d = __bfloat162float(hi.y);
-      acc += a * a; acc += b * b; acc += c * c; acc += d * d;
+      const uint2 packed = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+      *reinterpret_cast<uint2*>(dst + 4 * c4) = packed;
+      if (dst2) *reinterpret_cast<uint2*>(dst2 + 4 * c4) = packed;
+      if (WANT_SS) {
+        const double a = __bfloat162float(lo.x), b = __bfloat162float(lo.y), c = __bfloat162float(hi.x), d = __bfloat162float(hi.y);
+        acc += a * a; acc += b * b; acc += c * c; acc += d * d;
+      }
     };
 #pragma unroll
     for (int u = 0; u < KEEP; ++u) {
@@ -302,15 +311,21 @@ __device__ __forceinline__ double prep_row(const float* __restrict__ src, int D,
       if (c < D) v = normalize ? __fdiv_rn(__ldg(src + c), denom) : __ldg(src + c);
       const __nv_bfloat16 b = __float2bfloat16_rn(v);
       dst[c] = b;
-      const double w = static_cast<double>(__bfloat162float(b));
-      acc += w * w;
+      if (dst2) dst2[c] = b;
+      if (WANT_SS) {
+        const double w = static_cast<double>(__bfloat162float(b));
+        acc += w * w;
+      }
     }
   }
+  if (WANT_SS) {
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  }
   return acc;
 }
 
+template <int KEEP>
 __global__ void __launch_bounds__(256) prep_bf16_kernel(const float* __restrict__ emb, long long ld,
                                                         const long long* __restrict__ idx, int n, int D, int normalize,
                                                         __nv_bfloat16* __restrict__ out, int Dpad,
@@ -320,7 +335,7 @@ __global__ void __launch_bounds__(256) prep_bf16_kernel(const float* __restrict_
   if (warp >= n) return;
   const float* src = emb + (idx ? idx[warp] : static_cast<long long>(warp)) * ld;
   const bool vec4 = (D % 4 == 0) && (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(emb) & 15) == 0);
-  const double acc = prep_row(src, D, Dpad, normalize, out + static_cast<long long>(warp) * Dpad, lane, vec4);
+  const double acc = prep_row<KEEP, true>(src, D, Dpad, normalize, out + static_cast<long long>(warp) * Dpad, nullptr, lane, vec4);
   if (lane == 0 && norm2) norm2[warp] = static_cast<float>(acc);
 }
 
@@ -341,24 +356,31 @@ struct StackPrepArgs {
   int D[MANY_MAX];
   int Dpad[MANY_MAX];
 };
+// One warp per row of [a ; b]; the warp of row i of part a also writes row i of the third part (the repeated a), so every
+// source row is read and normalised once.
+template <int KEEP>
 __global__ void __launch_bounds__(256) icl_stack_prep_kernel(const __grid_constant__ StackPrepArgs a,
                                                              const long long* __restrict__ idx_l,
                                                              const long long* __restrict__ idx_r, int B, int Bp,
                                                              int normalize) {
   const int p = blockIdx.y;
-  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;       // row of S3_p
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;       // row of the first two parts of S3_p
   const int lane = threadIdx.x & 31;
-  if (r >= 3 * Bp) return;
-  const int part = r / Bp, i = r - part * Bp;
+  if (r >= 2 * Bp) return;
+  const int part = r >= Bp ? 1 : 0, i = r - part * Bp;
   const int D = a.D[p], Dpad = a.Dpad[p];
   __nv_bfloat16* dst = a.out[p] + static_cast<long long>(r) * Dpad;
+  __nv_bfloat16* dst2 = part == 0 ? dst + 2ll * Bp * Dpad : nullptr;
   if (i >= B) {
-    for (int c = lane; c < Dpad; c += 32) dst[c] = __float2bfloat16_rn(0.f);
+    for (int c = lane; c < Dpad; c += 32) {
+      dst[c] = __float2bfloat16_rn(0.f);
+      if (dst2) dst2[c] = __float2bfloat16_rn(0.f);
+    }
     return;
   }
   const float* src = a.emb[p] + (part == 1 ? idx_r[i] : idx_l[i]) * a.ld[p];
   const bool vec4 = (D % 4 == 0) && (a.ld[p] % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.emb[p]) & 15) == 0);
-  prep_row(src, D, Dpad, normalize, dst, lane, vec4);
+  prep_row<KEEP, false>(src, D, Dpad, normalize, dst, dst2, lane, vec4);
 }
 
 struct ScatterManyArgs {
@@ -1684,7 +1706,11 @@ int launch_prep_bf16(const float* emb, long long ld, const long long* idx, int n
   if (!emb || !out || n <= 0 || D <= 0) return SNAG_ERR_ARG;
   if (Dpad < D || (Dpad % 64) != 0) return SNAG_ERR_SHAPE;
   const long long threads = static_cast<long long>(n) * 32;
-  prep_bf16_kernel<<<static_cast<int>((threads + 255) / 256), 256, 0, st>>>(emb, ld, idx, n, D, normalize, out, Dpad, norm2);
+  const int grid = static_cast<int>((threads + 255) / 256);
+  if (D <= PREP_NARROW_MAX_D)
+    prep_bf16_kernel<4><<<grid, 256, 0, st>>>(emb, ld, idx, n, D, normalize, out, Dpad, norm2);
+  else
+    prep_bf16_kernel<16><<<grid, 256, 0, st>>>(emb, ld, idx, n, D, normalize, out, Dpad, norm2);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -1693,14 +1719,20 @@ int launch_icl_stack_prep(int n_prob, const float* const* emb, const long long* 
                           cudaStream_t st) {
   if (n_prob < 1 || n_prob > MANY_MAX || !emb || !ld || !D || !out || !Dpad || !idx_l || !idx_r) return SNAG_ERR_ARG;
   if (B <= 0 || Bp < B || (Bp % 256) != 0) return SNAG_ERR_ARG;
-  StackPrepArgs a{};
+  // narrow tables (the per-modality embeddings) and wide ones (the joint embeddings) go to different instantiations: the
+  // narrow one keeps 4 float4 per lane and runs at more than twice the occupancy
+  StackPrepArgs narrow{}, wide{};
+  int n_narrow = 0, n_wide = 0;
   for (int p = 0; p < n_prob; ++p) {
     if (!emb[p] || !out[p] || D[p] <= 0 || ld[p] < D[p]) return SNAG_ERR_ARG;
     if (Dpad[p] < D[p] || (Dpad[p] % 64) != 0) return SNAG_ERR_SHAPE;
-    a.emb[p] = emb[p]; a.ld[p] = ld[p]; a.out[p] = out[p]; a.D[p] = D[p]; a.Dpad[p] = Dpad[p];
+    StackPrepArgs& a = D[p] <= PREP_NARROW_MAX_D ? narrow : wide;
+    const int q = D[p] <= PREP_NARROW_MAX_D ? n_narrow++ : n_wide++;
+    a.emb[q] = emb[p]; a.ld[q] = ld[p]; a.out[q] = out[p]; a.D[q] = D[p]; a.Dpad[q] = Dpad[p];
   }
-  const dim3 grid(static_cast<unsigned>((3ll * Bp * 32 + 255) / 256), static_cast<unsigned>(n_prob));
-  icl_stack_prep_kernel<<<grid, 256, 0, st>>>(a, idx_l, idx_r, B, Bp, normalize);
+  const unsigned gx = static_cast<unsigned>((2ll * Bp * 32 + 255) / 256);
+  if (n_narrow) icl_stack_prep_kernel<4><<<dim3(gx, static_cast<unsigned>(n_narrow)), 256, 0, st>>>(narrow, idx_l, idx_r, B, Bp, normalize);
+  if (n_wide) icl_stack_prep_kernel<16><<<dim3(gx, static_cast<unsigned>(n_wide)), 256, 0, st>>>(wide, idx_l, idx_r, B, Bp, normalize);
   return static_cast<int>(cudaGetLastError());
 }
 int launch_normalize_bwd_scatter_many(int n_prob, const float* const* emb, const long long* ld, const int* D,
