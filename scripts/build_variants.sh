@@ -1,12 +1,12 @@
 #!/bin/bash
-# Builds kernel variants of libsnag_b200.so for A/B power/throughput measurements (scripts/gpu_variants.py).
+# Builds kernel variants of libsnag_b200.so for A/B power/throughput measurements (load one with SNAG_B200_LIB=snag_b200/_variants/lib_<name>.so).
 set -e
 cd "$(dirname "$0")/.."
 mkdir -p snag_b200/_variants
 build() {  # name, extra flags
   name=$1; shift
   objs=""
-  for f in abi bw_kernels sim_kernels icl_fused; do
+  for f in abi bw_kernels sim_kernels icl_fused icl_fwd_sym; do
     nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC --expt-relaxed-constexpr "$@" \
       -c snag_b200/csrc/$f.cu -o snag_b200/_variants/${name}_$f.o &
     objs="$objs snag_b200/_variants/${name}_$f.o"
