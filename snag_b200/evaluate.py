@@ -674,6 +674,8 @@ def evaluate_alignment(final_emb: torch.Tensor, test_left: torch.Tensor, test_ri
         raise ValueError(f"csls_k={csls_k}")
     if csls and csls_k > n:
         raise ValueError(f"csls_k={csls_k} exceeds the number of evaluated pairs n={n}")
+    if not final_emb.is_cuda:
+        raise SnagError("evaluate_alignment: final_emb must live on the GPU (there is no CPU path)")
     if csls and csls_k > KT:
         # the fused sweeps keep KT candidates per entity; larger neighbourhoods (the reference takes any k) are evaluated
         # on the materialised matrix
